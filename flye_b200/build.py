@@ -1,0 +1,89 @@
+"""Build everything native, in-tree.
+
+  flye_b200/libflye_b200.so   the product: CUDA kernels + C ABI, sm_100a only
+  tools/_bin/simreads         synthetic read generator
+  oracle/_ref/*               the checkers (reference harness when /root/reference exists, CPU restatement)
+  tests/cpu_models/_bin/*     host builds of device headers (introsort emulation check)
+"""
+import os
+import shutil
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CSRC = os.path.join(ROOT, "flye_b200", "csrc")
+BUILD = os.path.join(ROOT, "build")
+LIB = os.path.join(ROOT, "flye_b200", "libflye_b200.so")
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-Wno-deprecated-declarations"]
+SOURCES = ["api.cu", "count_index.cu", "overlap.cu"]
+
+
+def _run(cmd, **kw):
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, **kw)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout)
+        raise RuntimeError("command failed: " + " ".join(cmd))
+    return r.stdout
+
+
+def _newer(target, deps):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build_lib(force=False):
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    os.makedirs(BUILD, exist_ok=True)
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    headers.append(os.path.join(ROOT, "include", "flye_b200.h"))
+    objs, jobs = [], []
+    for s in SOURCES:
+        src, obj = os.path.join(CSRC, s), os.path.join(BUILD, s.replace(".cu", ".o"))
+        objs.append(obj)
+        if force or _newer(obj, [src] + headers):
+            jobs.append([nvcc] + NVCC_FLAGS + ["-c", src, "-o", obj])
+    with ThreadPoolExecutor(max_workers=4) as ex:
+        list(ex.map(_run, jobs))
+    if jobs or not os.path.exists(LIB):
+        _run([nvcc, "-shared", "-o", LIB] + objs + ["-ldl"])
+    return LIB
+
+
+def build_tools():
+    out = os.path.join(ROOT, "tools", "_bin")
+    os.makedirs(out, exist_ok=True)
+    src, exe = os.path.join(ROOT, "tools", "simreads.cpp"), os.path.join(out, "simreads")
+    if _newer(exe, [src]):
+        _run(["g++", "-O2", "-std=c++17", src, "-o", exe])
+    out = os.path.join(ROOT, "tests", "cpu_models", "_bin")
+    os.makedirs(out, exist_ok=True)
+    src, exe = os.path.join(ROOT, "tests", "cpu_models", "introsort_check.cpp"), os.path.join(out, "introsort_check")
+    if _newer(exe, [src, os.path.join(CSRC, "introsort_warp.cuh")]):
+        _run(["g++", "-O2", "-std=c++17", src, "-o", exe])
+
+
+    src, so = os.path.join(ROOT, "tests", "cpu_models", "stdsort_lib.cpp"), os.path.join(out, "libstdsort.so")
+    if _newer(so, [src]):
+        _run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", src, "-o", so])
+
+
+def build_oracle():
+    odir = os.path.join(ROOT, "oracle")
+    _run(["make", "-C", odir, "restate"])
+    if os.path.isdir("/root/reference/src/sequence"):
+        _run(["make", "-C", odir, "ref", "-j4"])
+
+
+def build_all(force=False):
+    build_lib(force)
+    build_tools()
+    build_oracle()
+
+
+if __name__ == "__main__":
+    build_all(force="--force" in sys.argv)
+    print("built", LIB)

@@ -1,0 +1,209 @@
+// flye_b200 — shared device/host helpers for the sm_100a read-overlap path.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/flye_b200.h"
+
+namespace fg {
+
+// ---------------------------------------------------------------------------------------------
+// errors: internal code throws fg::Error; the extern "C" layer converts to a status + message
+// ---------------------------------------------------------------------------------------------
+struct Error : std::runtime_error {
+    int code;
+    Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+#define FG_CUDA(call)                                                                              \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            throw fg::Error(FG_ERR_CUDA, std::string(#call) + " failed at " + __FILE__ + ":" +      \
+                                             std::to_string(__LINE__) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// device buffers (plain cudaMalloc; phases free their temporaries when they return)
+// ---------------------------------------------------------------------------------------------
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    DevBuf() = default;
+    explicit DevBuf(size_t count) { alloc(count); }
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+    DevBuf& operator=(DevBuf&& o) noexcept {
+        if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; }
+        return *this;
+    }
+    ~DevBuf() { release(); }
+    void alloc(size_t count) {
+        release();
+        n = count;
+        if (count) FG_CUDA(cudaMalloc((void**)&p, count * sizeof(T)));
+    }
+    void ensure(size_t count) { if (count > n) alloc(count + count / 8); }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    size_t bytes() const { return n * sizeof(T); }
+};
+
+template <class T>
+struct PinnedBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    PinnedBuf() = default;
+    PinnedBuf(const PinnedBuf&) = delete;
+    PinnedBuf& operator=(const PinnedBuf&) = delete;
+    ~PinnedBuf() { release(); }
+    void ensure(size_t count) {
+        if (count <= n) return;
+        release();
+        n = count + count / 4 + 16;
+        FG_CUDA(cudaMallocHost((void**)&p, n * sizeof(T)));
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; n = 0; }
+};
+
+// ---------------------------------------------------------------------------------------------
+// k-mer arithmetic.  Reads are packed like DnaSequence (reference sequence.h:54-69): base j at bits
+// 2*(j%32) of word j/32.  `v` below is the 2k-bit little-endian window (base p in the lowest bits).
+// The reference's Kmer keeps the FIRST base most significant (kmer.h:32-36), so
+//     forward k-mer  = 2-bit-group reversal of v          (fwdFromWindow)
+//     reverse compl. = ~v & mask                            (kmer.h:39-52 collapses to this)
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ inline uint64_t kmerMask(int k) { return k >= 32 ? ~0ULL : ((1ULL << (2 * k)) - 1); }
+
+__host__ __device__ inline uint64_t rev2(uint64_t x) {   // reverse the order of the 32 2-bit groups
+#ifdef __CUDA_ARCH__
+    x = __brevll(x);
+#else
+    x = ((x >> 32) | (x << 32));
+    x = ((x & 0xFFFF0000FFFF0000ULL) >> 16) | ((x & 0x0000FFFF0000FFFFULL) << 16);
+    x = ((x & 0xFF00FF00FF00FF00ULL) >> 8) | ((x & 0x00FF00FF00FF00FFULL) << 8);
+    x = ((x & 0xF0F0F0F0F0F0F0F0ULL) >> 4) | ((x & 0x0F0F0F0F0F0F0F0FULL) << 4);
+    x = ((x & 0xCCCCCCCCCCCCCCCCULL) >> 2) | ((x & 0x3333333333333333ULL) << 2);
+    x = ((x & 0xAAAAAAAAAAAAAAAAULL) >> 1) | ((x & 0x5555555555555555ULL) << 1);
+#endif
+    return ((x & 0xAAAAAAAAAAAAAAAAULL) >> 1) | ((x & 0x5555555555555555ULL) << 1);
+}
+
+__host__ __device__ inline uint64_t fwdFromWindow(uint64_t v, int k) { return rev2(v) >> (64 - 2 * k); }
+
+// 2k-bit window starting at base `pos` of a packed read (words must be readable up to pos+k-1 >> 5, +1)
+__host__ __device__ inline uint64_t windowAt(const uint64_t* words, uint32_t pos, int k) {
+    uint32_t w = pos >> 5, sh = (pos & 31) * 2;
+    uint64_t lo = words[w] >> sh;
+    if (sh && sh + 2 * k > 64) lo |= words[w + 1] << (64 - sh);
+    return lo & kmerMask(k);
+}
+
+// canonical k-mer of the forward-strand position; isRc = reverse complement strictly smaller (kmer.h:54-63)
+__host__ __device__ inline uint64_t canonFromWindow(uint64_t v, int k, bool& isRc) {
+    uint64_t f = fwdFromWindow(v, k), r = (~v) & kmerMask(k);
+    isRc = r < f;
+    return isRc ? r : f;
+}
+
+__host__ __device__ inline uint64_t splitmix64(uint64_t x) {   // Kmer::hash, kmer.h:91-98
+    uint64_t z = (x += 0x9E3779B97F4A7C15ULL);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+
+__host__ __device__ inline uint64_t mix64(uint64_t h) {   // table hash (murmur3 finaliser)
+    h ^= h >> 33; h *= 0xff51afd7ed558ccdULL; h ^= h >> 33; h *= 0xc4ceb9fe1a85ec53ULL; h ^= h >> 33;
+    return h;
+}
+
+// ---------------------------------------------------------------------------------------------
+// open-addressing table in HBM: 16-byte slots {key, payload}; one probe = one 32-byte sector
+// ---------------------------------------------------------------------------------------------
+static constexpr uint64_t EMPTY_KEY = ~0ULL;
+
+struct Table {
+    ulonglong2* slots = nullptr;
+    uint64_t mask = 0;   // capacity - 1 (capacity is a power of two)
+};
+
+__device__ inline bool tableFind(const Table& t, uint64_t key, uint64_t& payload) {
+    uint64_t i = mix64(key) & t.mask;
+    for (;;) {
+        ulonglong2 s = __ldg(&t.slots[i]);
+        if (s.x == key) { payload = s.y; return true; }
+        if (s.x == EMPTY_KEY) return false;
+        i = (i + 1) & t.mask;
+    }
+}
+
+// keys are unique among inserters: plain claim + store
+__device__ inline void tableInsertUnique(const Table& t, uint64_t key, uint64_t payload) {
+    uint64_t i = mix64(key) & t.mask;
+    for (;;) {
+        unsigned long long prev = atomicCAS((unsigned long long*)&t.slots[i].x, (unsigned long long)EMPTY_KEY,
+                                            (unsigned long long)key);
+        if (prev == EMPTY_KEY) { t.slots[i].y = payload; return; }
+        i = (i + 1) & t.mask;
+    }
+}
+
+// counting insert: payload += 1
+__device__ inline void tableAddOne(const Table& t, uint64_t key) {
+    uint64_t i = mix64(key) & t.mask;
+    for (;;) {
+        unsigned long long prev = atomicCAS((unsigned long long*)&t.slots[i].x, (unsigned long long)EMPTY_KEY,
+                                            (unsigned long long)key);
+        if (prev == EMPTY_KEY || prev == key) { atomicAdd((unsigned long long*)&t.slots[i].y, 1ULL); return; }
+        i = (i + 1) & t.mask;
+    }
+}
+
+// index payload: [63:24] first entry, [23:0] size; all-ones size = repetitive k-mer
+static constexpr uint64_t IDX_SIZE_BITS = 24;
+static constexpr uint64_t IDX_SIZE_MASK = (1ULL << IDX_SIZE_BITS) - 1;
+static constexpr uint64_t IDX_REPETITIVE = IDX_SIZE_MASK;
+
+// ---------------------------------------------------------------------------------------------
+// warp helpers
+// ---------------------------------------------------------------------------------------------
+__device__ inline int laneId() { return threadIdx.x & 31; }
+
+// position of the n-th (0-based) lowest set bit; requires popc(mask) > n
+__host__ __device__ inline int nthLowBit(uint32_t mask, int n) {
+    int pos = 0;
+#pragma unroll
+    for (int w = 16; w >= 1; w >>= 1) {
+        uint32_t part = (mask >> pos) & ((1u << w) - 1u);
+#ifdef __CUDA_ARCH__
+        int c = __popc(part);
+#else
+        int c = __builtin_popcount(part);
+#endif
+        if (n >= c) { n -= c; pos += w; }
+    }
+    return pos;
+}
+__host__ __device__ inline uint32_t brev32(uint32_t x) {
+#ifdef __CUDA_ARCH__
+    return __brev(x);
+#else
+    x = (x >> 16) | (x << 16);
+    x = ((x & 0xFF00FF00u) >> 8) | ((x & 0x00FF00FFu) << 8);
+    x = ((x & 0xF0F0F0F0u) >> 4) | ((x & 0x0F0F0F0Fu) << 4);
+    x = ((x & 0xCCCCCCCCu) >> 2) | ((x & 0x33333333u) << 2);
+    x = ((x & 0xAAAAAAAAu) >> 1) | ((x & 0x55555555u) << 1);
+    return x;
+#endif
+}
+__host__ __device__ inline int nthHighBit(uint32_t mask, int n) { return 31 - nthLowBit(brev32(mask), n); }
+
+}  // namespace fg

@@ -1,0 +1,119 @@
+// flye_b200 — device context shared by the translation units of libflye_b200.so.
+#pragma once
+#include "common.cuh"
+#include <algorithm>
+#include <map>
+#include <utility>
+
+struct fg_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    mutable std::mutex mtx;
+    std::string lastError;
+    uint64_t launches = 0;
+
+    // ---- reads (forward strands, 2-bit packed, every read word aligned) ----
+    uint32_t nReads = 0;
+    uint64_t totalBases = 0;              // over forward strands
+    std::vector<uint32_t> hLen;           // per read
+    std::vector<uint64_t> hWordOff;       // nReads+1
+    std::vector<uint64_t> hBasePrefix;    // nReads+1, prefix of lengths (global offset of id 2i = 2*prefix[i])
+    fg::DevBuf<uint64_t> dSeq;            // packed words (+2 words of slack)
+    fg::DevBuf<uint64_t> dWordOff;        // nReads+1
+    fg::DevBuf<uint32_t> dLen;            // nReads
+
+    // ---- k-mer slot space: read i owns slots [slotOff[i], slotOff[i]+n_i), n_i = max(L_i-k,0) (kmer.h:185-198),
+    //      slotOff is a prefix of roundup32(n_i) so that every read owns whole 32-bit bitmap words ----
+    int k = 0;
+    uint64_t nSlots = 0;                  // size of the slot space
+    uint64_t nKmers = 0;                  // sum of n_i
+    std::vector<uint64_t> hSlotOff;       // nReads+1
+    fg::DevBuf<uint64_t> dSlotOff;
+    // tiles of <=2048 slots inside one read (64 bitmap words): tile -> (read, first position)
+    std::vector<uint2> hTiles;
+    fg::DevBuf<uint2> dTiles;
+
+    // this rank's share of the reads for count / emission (multi-GPU); default = all
+    uint32_t shardFirst = 0, shardCount = 0;
+    bool shardSet = false;
+
+    // ---- k-mer counts ----
+    bool counted = false;
+    uint64_t nDistinct = 0;
+    std::map<uint64_t, uint64_t> hist;    // freq -> #distinct canonical k-mers
+    fg::DevBuf<ulonglong2> dCountSlots;   // table: canonical k-mer -> count, only counts >= 2 (absent = 1)
+    fg::Table countTable;
+
+    // ---- index ----
+    bool indexed = false;
+    bool minimizerMode = false;
+    fg_index_stats stats{};
+    fg::DevBuf<uint32_t> dSelBits;        // slot bitmap: position contributed an index entry candidate
+    fg::DevBuf<uint2> dEntries;           // (seqId,pos) sorted by (canonical k-mer, seqId, pos)
+    uint64_t nEntriesStored = 0;
+    fg::DevBuf<ulonglong2> dIndexSlots;
+    fg::Table indexTable;
+    // sorted unique keys with their class, for export / tests
+    fg::DevBuf<uint64_t> dUKeys;
+    fg::DevBuf<uint64_t> dUPayload;       // same encoding as the table payload; ~0 = not in index
+    uint64_t nUKeys = 0;
+
+    // ---- timings of the last call ----
+    std::vector<std::pair<std::string, float>> timings;
+
+    // ---- overlap results (host, library owned) ----
+    std::vector<uint64_t> resOffsets;
+    std::vector<fg_overlap> resOverlaps;
+    std::vector<int32_t> resAln;
+
+    // ---- NCCL ----
+    void* ncclComm = nullptr;
+    int nRanks = 1, rank = 0;
+};
+
+namespace fg {
+
+// RAII phase timer on the context stream (CUDA events; the phase list is what fg_last_timings reports)
+struct PhaseTimer {
+    fg_ctx* ctx;
+    const char* name;
+    cudaEvent_t a{}, b{};
+    PhaseTimer(fg_ctx* c, const char* n) : ctx(c), name(n) {
+        cudaEventCreate(&a); cudaEventCreate(&b);
+        cudaEventRecord(a, ctx->stream);
+    }
+    ~PhaseTimer() {
+        cudaEventRecord(b, ctx->stream);
+        cudaEventSynchronize(b);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, a, b);
+        bool found = false;
+        for (auto& t : ctx->timings) if (t.first == name) { t.second += ms; found = true; }
+        if (!found) ctx->timings.emplace_back(name, ms);
+        cudaEventDestroy(a); cudaEventDestroy(b);
+    }
+};
+
+inline void checkLaunch(fg_ctx* ctx, const char* what) {
+    ++ctx->launches;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) throw Error(FG_ERR_CUDA, std::string("launch of ") + what + ": " + cudaGetErrorString(e));
+}
+
+inline int gridFor(uint64_t n, int block = 256, int maxPerSm = 8) {
+    uint64_t g = (n + block - 1) / block;
+    return (int)std::max<uint64_t>(1, std::min<uint64_t>(g, (uint64_t)148 * maxPerSm));
+}
+
+// phases implemented in the other translation units
+void setKmerSize(fg_ctx* ctx, int k);
+void countKmers(fg_ctx* ctx, int k);
+void kmerFreqQuery(fg_ctx* ctx, const uint64_t* kmers, uint32_t n, uint32_t* out);
+void buildIndexSolid(fg_ctx* ctx, int minFreq, float selectRate, int tandemFreq, float repeatRate, float sampleRate);
+void buildIndexMinimizers(fg_ctx* ctx, int k, int minCov, int window, float repeatRate);
+void overlapsBatch(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQueries, const fg_overlap_params& p,
+                   fg_overlap_result* result);
+
+void debugWarpSort(fg_ctx* ctx, uint64_t* keys, uint32_t* vals, const uint64_t* segOffsets, uint32_t nSegs);
+
+}  // namespace fg

@@ -1,0 +1,331 @@
+// Warp-parallel, permutation-exact emulation of libstdc++ 13 std::sort (introsort).
+//
+// Why: the reference sorts with std::sort in four places on this path (overlap.cpp:201-204, :272-274,
+// :333-334, :432-434) and the ORDER OF TIES that libstdc++'s introsort happens to produce is
+// result-relevant.  Bit-exact overlaps therefore need the same permutation, not just
+// a sorted array.  This file produces that permutation with one warp per array:
+//
+//   * the recursion structure, depth limit (2*floor(lg n)), median-of-3 pivot selection, the
+//     16-element threshold and the heap-sort fallback follow bits/stl_algo.h:1848-1951 literally
+//     (small sequential pieces run on one lane);
+//   * the Hoare partition (__unguarded_partition, :1871-1889) — where all the time goes — is restated
+//     data-parallel.  With L_0<L_1<... the positions whose value is >= pivot (ascending) and
+//     R_0>R_1>... those whose value is <= pivot (descending), the sequential two-pointer loop swaps
+//     (L_m,R_m) for exactly the m with L_m < R_m (a prefix, s pairs) and returns
+//         cut = s==0 ? L_0 : min(L_s, R_{s-1}).
+//     The warp streams 32-element chunks from both ends, finds stops with ballots and lets lane m move
+//     pair m; when the chunks meet, the remaining pairs live inside the last chunk and are resolved from
+//     the ballot masks of its ORIGINAL values (kept in registers).
+//   * the final insertion sort (__final_insertion_sort, :1854-1865) is a stable sort that never moves an
+//     element across a partition cut, i.e. an independent stable insertion sort of every <=16-element
+//     leaf: one lane per leaf.
+//
+// The same source compiles for the host (FG_WARP_HOST) with the 32 lanes run as loops; that build is
+// checked against std::sort itself in tests/test_introsort_model.py, so the logic below is validated on
+// the CPU and the device build is checked against the CPU build on the GPU.
+#pragma once
+#include <cstdint>
+
+#ifndef FG_WARP_HOST
+#include "common.cuh"
+#define FG_DEV __device__ __forceinline__
+#define FG_FOR_LANES { const int lane = fg::laneId();
+#define FG_END_LANES }
+#define FG_LANEVAR(T, name) T name
+#define FG_L(name) name
+#define FG_BALLOT(out, pred) { const int lane = fg::laneId(); (void)lane; out = __ballot_sync(0xffffffffu, (pred)); }
+#define FG_SYNCWARP() __syncwarp()
+#define FG_POPC(x) __popc(x)
+#define FG_CTZ(x) (__ffs(x) - 1)
+#else
+#include <algorithm>
+namespace fg {
+inline int nthLowBit(uint32_t mask, int n) {
+    for (int b = 0; b < 32; ++b) if (mask >> b & 1) { if (n == 0) return b; --n; }
+    return 32;
+}
+inline int nthHighBit(uint32_t mask, int n) {
+    for (int b = 31; b >= 0; --b) if (mask >> b & 1) { if (n == 0) return b; --n; }
+    return -1;
+}
+}
+#define FG_DEV inline
+#define FG_FOR_LANES for (int lane = 0; lane < 32; ++lane) {
+#define FG_END_LANES }
+#define FG_LANEVAR(T, name) T name[32]
+#define FG_L(name) name[lane]
+#define FG_BALLOT(out, pred) { out = 0; for (int lane = 0; lane < 32; ++lane) if (pred) out |= (1u << lane); }
+#define FG_SYNCWARP() ((void)0)
+#define FG_POPC(x) __builtin_popcount(x)
+#define FG_CTZ(x) __builtin_ctz(x)
+#endif
+
+namespace fg {
+
+#ifdef FG_WARP_HOST
+static long g_heapSortCalls = 0;   // test visibility: how often the depth-limit fallback ran
+#endif
+
+// 16-byte sort element: only `key` is compared (ascending); val/aux ride along.
+struct
+#ifndef FG_WARP_HOST
+    __align__(16)
+#endif
+    Elem {
+    unsigned long long key;
+    unsigned int val;
+    unsigned int aux;
+};
+
+FG_DEV bool elemLess(const Elem& a, const Elem& b) { return a.key < b.key; }
+FG_DEV void elemSwap(Elem* a, long i, long j) { Elem t = a[i]; a[i] = a[j]; a[j] = t; }
+
+// ---- sequential pieces (one lane) -----------------------------------------------------------------
+// __move_median_to_first(result, a, b, c), stl_algo.h:85-111
+FG_DEV void seqMedianToFirst(Elem* arr, long result, long a, long b, long c) {
+    unsigned long long ka = arr[a].key, kb = arr[b].key, kc = arr[c].key;
+    long pick;
+    if (ka < kb) { if (kb < kc) pick = b; else if (ka < kc) pick = c; else pick = a; }
+    else if (ka < kc) pick = a;
+    else if (kb < kc) pick = c;
+    else pick = b;
+    elemSwap(arr, result, pick);
+}
+
+// stable insertion sort of a leaf (the part of __final_insertion_sort that touches this range)
+FG_DEV void seqInsertionSort(Elem* arr, long f, long l) {
+    for (long i = f + 1; i < l; ++i) {
+        Elem v = arr[i];
+        long j = i;
+        while (j > f && v.key < arr[j - 1].key) { arr[j] = arr[j - 1]; --j; }
+        arr[j] = v;
+    }
+}
+
+// __partial_sort(first,last,last) = __heap_select + __sort_heap  (stl_algo.h:1905-1912, stl_heap.h)
+FG_DEV void seqAdjustHeap(Elem* first, long hole, long len, Elem value) {
+    const long top = hole;
+    long child = hole;
+    while (child < (len - 1) / 2) {
+        child = 2 * (child + 1);
+        if (first[child].key < first[child - 1].key) --child;
+        first[hole] = first[child];
+        hole = child;
+    }
+    if ((len & 1) == 0 && child == (len - 2) / 2) {
+        child = 2 * (child + 1);
+        first[hole] = first[child - 1];
+        hole = child - 1;
+    }
+    long parent = (hole - 1) / 2;   // __push_heap
+    while (hole > top && first[parent].key < value.key) {
+        first[hole] = first[parent];
+        hole = parent;
+        parent = (hole - 1) / 2;
+    }
+    first[hole] = value;
+}
+FG_DEV void seqHeapSort(Elem* first, long len) {
+    if (len >= 2)
+        for (long parent = (len - 2) / 2;; --parent) {
+            Elem v = first[parent];
+            seqAdjustHeap(first, parent, len, v);
+            if (parent == 0) break;
+        }
+    for (long last = len; last > 1;) {
+        --last;
+        Elem v = first[last];
+        first[last] = first[0];
+        seqAdjustHeap(first, 0, last, v);
+    }
+}
+
+// ---- the data-parallel Hoare partition ---------------------------------------------------------------
+// Partitions arr[f,l) (l-f > 16) exactly like
+//     __move_median_to_first(f, f+1, f+(l-f)/2, l-1); return __unguarded_partition(f+1, l, f);
+// and returns the cut.  All control flow is warp-uniform.
+FG_DEV long warpPartition(Elem* arr, long f, long l) {
+#ifndef FG_WARP_HOST
+    if (fg::laneId() == 0)
+#endif
+        seqMedianToFirst(arr, f, f + 1, f + (l - f) / 2, l - 1);
+    FG_SYNCWARP();
+    const unsigned long long p = arr[f].key;
+
+    long lo = f + 1, hi = l;        // untouched middle [lo,hi)
+    long s = 0;                     // pairs swapped so far
+    long lastR = -1;                // position of R_{s-1}
+    long firstGeAbove = l;          // lowest position with original value >= p in retired right chunks
+    long Lb = 0, Rb = 0;            // base position of the current left / right chunk
+    uint32_t geL = 0, leL = 0, pendL = 0, geR = 0, leR = 0, pendR = 0;
+    bool haveR = false;
+    FG_LANEVAR(Elem, eL);
+    FG_LANEVAR(Elem, eR);
+
+    for (;;) {
+        if (pendL == 0 && lo < hi) {
+            Lb = lo;
+            const long nL = (hi - lo < 32) ? (hi - lo) : 32;
+            lo += nL;
+            FG_FOR_LANES if (lane < nL) FG_L(eL) = arr[Lb + lane]; FG_END_LANES
+            FG_BALLOT(geL, lane < nL && FG_L(eL).key >= p);
+            FG_BALLOT(leL, lane < nL && FG_L(eL).key <= p);
+            pendL = geL;
+        }
+        if (pendR == 0 && lo < hi) {
+            if (haveR && geR) firstGeAbove = Rb + FG_CTZ(geR);
+            const long nR = (hi - lo < 32) ? (hi - lo) : 32;
+            Rb = hi - nR;
+            hi = Rb;
+            FG_FOR_LANES if (lane < nR) FG_L(eR) = arr[Rb + lane]; FG_END_LANES
+            FG_BALLOT(geR, lane < nR && FG_L(eR).key >= p);
+            FG_BALLOT(leR, lane < nR && FG_L(eR).key <= p);
+            pendR = leR;
+            haveR = true;
+        }
+        const int cL = FG_POPC(pendL), cR = FG_POPC(pendR);
+        const int c = cL < cR ? cL : cR;
+        if (c > 0) {
+            // pair m: m-th lowest pending L  <->  m-th highest pending R   (every pending L < every pending R)
+            FG_FOR_LANES
+                if (pendL >> lane & 1) {
+                    int m = FG_POPC(pendL & ((1u << lane) - 1u));
+                    if (m < c) arr[Rb + nthHighBit(pendR, m)] = FG_L(eL);
+                }
+                if (pendR >> lane & 1) {
+                    int m = FG_POPC(pendR & ~((2u << lane) - 1u));
+                    if (m < c) arr[Lb + nthLowBit(pendL, m)] = FG_L(eR);
+                }
+            FG_END_LANES
+            lastR = Rb + nthHighBit(pendR, c - 1);
+            // drop the c lowest bits of pendL and the c highest of pendR
+            if (c == cL) pendL = 0; else pendL &= ~((2u << nthLowBit(pendL, c - 1)) - 1u);
+            if (c == cR) pendR = 0; else pendR &= ((1u << nthHighBit(pendR, c - 1)) - 1u);
+            s += c;
+        }
+        if (lo < hi && (pendL == 0 || pendR == 0)) continue;
+        break;
+    }
+    FG_SYNCWARP();
+
+    // The chunks have met (lo == hi).  Remaining pairs, if any, lie inside ONE chunk.
+    const long INF = l + 1;
+    long Ls;   // position of L_s, the first unpaired ">= pivot" stop in the original ordering
+    if (pendL != 0) {
+        // unpaired L stops remain in the current left chunk; the next R stops are that chunk's
+        // "<= pivot" positions, descending
+        const int nl = FG_POPC(pendL), nr = FG_POPC(leL);
+        uint32_t ok;
+        FG_BALLOT(ok, lane < nl && lane < nr && nthLowBit(pendL, lane) < nthHighBit(leL, lane));
+        const int e = FG_POPC(ok);
+        FG_FOR_LANES
+            const bool isL = pendL >> lane & 1, isR = leL >> lane & 1;
+            const int mL = FG_POPC(pendL & ((1u << lane) - 1u));
+            const int mR = FG_POPC(leL & ~((2u << lane) - 1u));
+            if (isL && mL < e) arr[Lb + nthHighBit(leL, mL)] = FG_L(eL);
+            if (isR && mR < e) arr[Lb + nthLowBit(pendL, mR)] = FG_L(eL);
+        FG_END_LANES
+        s += e;
+        if (e > 0) lastR = Lb + nthHighBit(leL, e - 1);
+        Ls = (e < nl) ? Lb + nthLowBit(pendL, e) : INF;
+    } else if (pendR != 0) {
+        // unpaired R stops remain in the current right chunk; the next L stops are that chunk's
+        // ">= pivot" positions, ascending, then those of the chunks above it
+        const int nr = FG_POPC(pendR), nl = FG_POPC(geR);
+        uint32_t ok;
+        FG_BALLOT(ok, lane < nl && lane < nr && nthLowBit(geR, lane) < nthHighBit(pendR, lane));
+        const int e = FG_POPC(ok);
+        FG_FOR_LANES
+            const bool isL = geR >> lane & 1, isR = pendR >> lane & 1;
+            const int mL = FG_POPC(geR & ((1u << lane) - 1u));
+            const int mR = FG_POPC(pendR & ~((2u << lane) - 1u));
+            if (isL && mL < e) arr[Rb + nthHighBit(pendR, mL)] = FG_L(eR);
+            if (isR && mR < e) arr[Rb + nthLowBit(geR, mR)] = FG_L(eR);
+        FG_END_LANES
+        s += e;
+        if (e > 0) lastR = Rb + nthHighBit(pendR, e - 1);
+        Ls = (e < nl) ? Rb + nthLowBit(geR, e) : firstGeAbove;
+    } else {
+        Ls = (haveR && geR) ? Rb + FG_CTZ(geR) : firstGeAbove;
+    }
+    FG_SYNCWARP();
+    if (s == 0) return Ls;
+    return Ls < lastR ? Ls : lastR;
+}
+
+// ---- the whole sort -------------------------------------------------------------------------------------
+// Sorts arr[0,n) ascending by key with std::sort's exact permutation.  One warp; no shared memory: the
+// explicit recursion stack (<= 2*lg n entries) and the pending-leaf list live in lane registers.
+FG_DEV void warpIntrosort(Elem* arr, long n) {
+    if (n < 2) return;
+    FG_LANEVAR(long, stF0); FG_LANEVAR(long, stL0); FG_LANEVAR(int, stD0);   // stack entries 0..31
+    FG_LANEVAR(long, stF1); FG_LANEVAR(long, stL1); FG_LANEVAR(int, stD1);   // stack entries 32..63
+    FG_LANEVAR(long, lfF);  FG_LANEVAR(long, lfL);                           // pending leaves
+    int sp = 0, nLeaf = 0;
+    FG_FOR_LANES FG_L(lfF) = 0; FG_L(lfL) = 0; FG_END_LANES
+
+    auto flushLeaves = [&]() {
+        FG_SYNCWARP();
+        FG_FOR_LANES if (lane < nLeaf) seqInsertionSort(arr, FG_L(lfF), FG_L(lfL)); FG_END_LANES
+        FG_SYNCWARP();
+        nLeaf = 0;
+    };
+    auto addLeaf = [&](long f, long l) {
+        if (l - f < 2) return;
+        FG_FOR_LANES if (lane == nLeaf) { FG_L(lfF) = f; FG_L(lfL) = l; } FG_END_LANES
+        if (++nLeaf == 32) flushLeaves();
+    };
+
+    int lg = 0;
+    while ((n >> (lg + 1)) != 0) ++lg;
+    long f = 0, l = n;
+    int d = 2 * lg;
+    bool have = true;
+    while (have) {
+        bool heapSorted = false;
+        while (l - f > 16) {
+            if (d == 0) {
+#ifndef FG_WARP_HOST
+                if (fg::laneId() == 0)
+#endif
+                    seqHeapSort(arr + f, l - f);
+#ifdef FG_WARP_HOST
+                ++g_heapSortCalls;
+#endif
+                FG_SYNCWARP();
+                heapSorted = true;
+                break;
+            }
+            --d;
+            const long cut = warpPartition(arr, f, l);
+            if (l - cut > 16) {   // "recurse" on the right part: push
+                FG_FOR_LANES
+                    if (lane == (sp & 31)) {
+                        if (sp < 32) { FG_L(stF0) = cut; FG_L(stL0) = l; FG_L(stD0) = d; }
+                        else { FG_L(stF1) = cut; FG_L(stL1) = l; FG_L(stD1) = d; }
+                    }
+                FG_END_LANES
+                ++sp;
+            } else addLeaf(cut, l);
+            l = cut;
+        }
+        if (!heapSorted) addLeaf(f, l);
+        if (sp == 0) have = false;
+        else {
+            --sp;
+#ifndef FG_WARP_HOST
+            long tf = sp < 32 ? stF0 : stF1, tl = sp < 32 ? stL0 : stL1; int td = sp < 32 ? stD0 : stD1;
+            f = __shfl_sync(0xffffffffu, tf, sp & 31);
+            l = __shfl_sync(0xffffffffu, tl, sp & 31);
+            d = __shfl_sync(0xffffffffu, td, sp & 31);
+#else
+            f = sp < 32 ? stF0[sp & 31] : stF1[sp & 31];
+            l = sp < 32 ? stL0[sp & 31] : stL1[sp & 31];
+            d = sp < 32 ? stD0[sp & 31] : stD1[sp & 31];
+#endif
+        }
+    }
+    if (nLeaf) flushLeaves();
+}
+
+}  // namespace fg

@@ -1,0 +1,662 @@
+// flye_b200 — OverlapDetector::getSeqOverlaps for a batch of query sequences on the device.
+//
+// Replaces src/sequence/overlap.cpp:99-508 (and overlapTest :29-69).  Pipeline per call:
+//   Q1 queryLookupKernel  every query k-mer (either strand) -> index table probe -> hit count, list start,
+//                         repetitive bit (curFilteredPos, :178-182), self-hit bit (:189-190)
+//   Q2 scans              hit offsets per slot / per query; prefix popcounts of the repetitive bitmap
+//   Q3 expandKernel       load-balanced expansion of the position lists into KmerMatch records in the
+//                         reference's emission order (query position ascending, list order) (:176-196)
+//   Q4 sortHitsKernel     one warp per query: std::sort-exact introsort by (extId,curPos) (:201-204)
+//   Q5 group kernels      target groups, uniqueMatches / bounding-box / overhang prefilters (:216-262)
+//   Q6 chainKernel        one warp per (query,target) pair: optional std::sort-exact re-sort by extPos
+//                         (:269-275), chaining DP with warp prefix-max emulating the sequential scan and its
+//                         two break rules (:277-323), std::sort-exact score ordering (:331-334), chain walk,
+//                         overlapTest, filtered-position count (:338-427), primary selection (:431-458)
+//   Q7 gather + host epilogue: seqDivergence with the reference's float expression and glibc logf (:417-423),
+//                         divergence filter (:470-473), maxOverlaps cut (:218-219).
+#include "ctx.cuh"
+#include "introsort_warp.cuh"
+
+#include <cub/cub.cuh>
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+
+namespace fg {
+
+static constexpr int QTILE = 2048;
+
+struct OvParams {
+    int k, maxJump, minOverlap, maxOverhang;
+    bool checkOverhang, forceLocal, onlyMaxExt;
+    float minUniqueF;   // 0.01f * minOverlap (overlap.cpp:110,235)
+};
+
+// per-slot info word: [39:0] first entry, bit 61 forward position stored reverse-complemented,
+// bit 62 the list contains the query's own position, bit 63 query k-mer was reverse-complemented
+static constexpr uint64_t INFO_FIRST_MASK = (1ULL << 40) - 1;
+static constexpr uint64_t INFO_FWDRC = 1ULL << 61, INFO_SELF = 1ULL << 62, INFO_QRC = 1ULL << 63;
+
+// ------------------------------------------------------------------------------------------------
+// Q1
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) queryLookupKernel(const uint64_t* __restrict__ seq, const uint64_t* __restrict__ wordOff,
+                                                         const uint32_t* __restrict__ len, const uint64_t* __restrict__ slotOff,
+                                                         const uint32_t* __restrict__ selBits, const uint32_t* __restrict__ qIds,
+                                                         const uint64_t* __restrict__ qSlotOff, const uint2* __restrict__ qTiles,
+                                                         int k, Table index, uint32_t* __restrict__ hitCnt,
+                                                         uint64_t* __restrict__ slotInfo, uint32_t* __restrict__ filtBits) {
+    const uint2 t = qTiles[blockIdx.x];
+    const uint32_t id = qIds[t.x], r = id >> 1;
+    const bool strand = id & 1;
+    const uint32_t L = len[r], n = L - k;
+    const uint32_t cnt = min((uint32_t)QTILE, n - t.y);
+    const uint32_t cntPad = (cnt + 31u) & ~31u;
+    const uint64_t* words = seq + wordOff[r];
+    const uint64_t qbase = qSlotOff[t.x] + t.y;
+    const uint64_t fbase = slotOff[r];
+    const uint64_t mask = kmerMask(k);
+    const int lane = threadIdx.x & 31;
+    for (uint32_t i0 = (threadIdx.x >> 5) * 32; i0 < cntPad; i0 += (blockDim.x >> 5) * 32) {
+        const uint32_t i = i0 + lane, p = t.y + i;
+        uint32_t c = 0; uint64_t info = 0; bool rep = false;
+        if (i < cnt) {
+            const uint32_t q = strand ? (L - k - p) : p;   // forward-strand position covering the same bases
+            const uint64_t v = windowAt(words, q, k);
+            const uint64_t f = fwdFromWindow(v, k), rcv = (~v) & mask;
+            const uint64_t qk = strand ? rcv : f, qrc = strand ? f : rcv;
+            const bool flagQ = qrc < qk;            // Kmer::standardForm on the query k-mer (kmer.h:54-63)
+            const uint64_t canon = flagQ ? qrc : qk;
+            const bool fwdRc = rcv < f;
+            uint64_t payload;
+            if (tableFind(index, canon, payload)) {
+                const uint64_t size = payload & IDX_SIZE_MASK;
+                if (size == IDX_REPETITIVE) rep = true;
+                else {
+                    bool self = false;
+                    if (q < n) self = (selBits[(fbase + q) >> 5] >> (q & 31)) & 1u;
+                    c = (uint32_t)size - (self ? 1u : 0u);
+                    info = (payload >> IDX_SIZE_BITS) | (fwdRc ? INFO_FWDRC : 0) | (self ? INFO_SELF : 0) | (flagQ ? INFO_QRC : 0);
+                }
+            }
+        }
+        hitCnt[qbase + i] = c;
+        slotInfo[qbase + i] = info;
+        const uint32_t m = __ballot_sync(0xffffffffu, rep);
+        if (lane == 0) filtBits[(qbase + i0) >> 5] = m;
+    }
+}
+
+struct CastU64 { __host__ __device__ uint64_t operator()(uint32_t x) const { return x; } };
+struct PopcU32 { __host__ __device__ uint32_t operator()(uint32_t x) const {
+#ifdef __CUDA_ARCH__
+    return __popc(x);
+#else
+    return __builtin_popcount(x);
+#endif
+} };
+
+__global__ void gatherQueryHitOffKernel(const uint64_t* __restrict__ hitOff, const uint64_t* __restrict__ qSlotOff, uint32_t nQ,
+                                        uint64_t* __restrict__ out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i <= nQ) out[i] = hitOff[qSlotOff[i]];
+}
+
+// ------------------------------------------------------------------------------------------------
+// Q3: expansion.  One CTA per query tile; the tile's slot offsets are staged in shared memory and every
+// output record finds its slot with a shared-memory binary search, so global writes are coalesced.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) expandKernel(const uint32_t* __restrict__ len, const uint2* __restrict__ entries,
+                                                    const uint32_t* __restrict__ qIds, const uint64_t* __restrict__ qSlotOff,
+                                                    const uint2* __restrict__ qTiles, int k, const uint64_t* __restrict__ hitOff,
+                                                    const uint64_t* __restrict__ slotInfo, uint64_t hitBase, Elem* __restrict__ hits) {
+    __shared__ uint32_t rel[QTILE + 1];
+    const uint2 t = qTiles[blockIdx.x];
+    const uint32_t id = qIds[t.x], r = id >> 1;
+    const bool strand = id & 1;
+    const uint32_t L = len[r], n = L - k;
+    const uint32_t cnt = min((uint32_t)QTILE, n - t.y);
+    const uint64_t qbase = qSlotOff[t.x] + t.y;
+    const uint64_t h0 = hitOff[qbase];
+    for (uint32_t i = threadIdx.x; i <= cnt; i += blockDim.x) rel[i] = (uint32_t)(hitOff[qbase + i] - h0);
+    __syncthreads();
+    const uint32_t T = rel[cnt];
+    Elem* out = hits + (h0 - hitBase);
+    for (uint32_t h = threadIdx.x; h < T; h += blockDim.x) {
+        uint32_t lo = 0, hi = cnt;   // largest s with rel[s] <= h
+        while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (rel[mid] <= h) lo = mid; else hi = mid; }
+        const uint32_t s = lo, j = h - rel[s], p = t.y + s;
+        const uint64_t info = slotInfo[qbase + s];
+        const uint64_t first = info & INFO_FIRST_MASK;
+        uint2 e = entries[first + j];
+        if (info & INFO_SELF) {
+            // the query's own position as it is stored in the index (vertex_index.cpp:78-85)
+            const uint32_t q = strand ? (L - k - p) : p;
+            const uint64_t self = (info & INFO_FWDRC) ? (((uint64_t)(2 * r + 1) << 32) | (L - q - k)) : (((uint64_t)(2 * r) << 32) | q);
+            if ((((uint64_t)e.x << 32) | e.y) >= self) e = entries[first + j + 1];   // lists are sorted and duplicate free
+        }
+        uint32_t extId = e.x; int32_t extPos = (int32_t)e.y;
+        if (info & INFO_QRC) { extPos = (int32_t)len[extId >> 1] - extPos - k; extId ^= 1u; }   // vertex_index.h:166-173
+        Elem o; o.key = ((unsigned long long)extId << 32) | p; o.val = (unsigned int)extPos; o.aux = 0;
+        out[h] = o;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Q4
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) sortHitsKernel(Elem* __restrict__ hits, const uint64_t* __restrict__ qHitOff, uint32_t qFirst,
+                                                      uint32_t nQ, uint64_t hitBase) {
+    const uint32_t w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (w >= nQ) return;
+    const uint64_t a = qHitOff[qFirst + w], b = qHitOff[qFirst + w + 1];
+    warpIntrosort(hits + (a - hitBase), (long)(b - a));
+}
+
+// ------------------------------------------------------------------------------------------------
+// Q5: groups
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) groupFlagKernel(const Elem* __restrict__ hits, uint64_t M, uint8_t* __restrict__ flags) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < M; i += (uint64_t)gridDim.x * blockDim.x)
+        flags[i] = (i == 0) || ((hits[i].key >> 32) != (hits[i - 1].key >> 32));
+}
+__global__ void queryStartFlagKernel(const uint64_t* __restrict__ qHitOff, uint32_t qFirst, uint32_t nQ, uint64_t hitBase,
+                                     uint64_t M, uint8_t* __restrict__ flags) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nQ) return;
+    uint64_t a = qHitOff[qFirst + i] - hitBase;
+    if (a < M && qHitOff[qFirst + i + 1] > qHitOff[qFirst + i]) flags[a] = 1;
+}
+
+// candidate = group with enough hits to possibly pass the uniqueMatches test
+__global__ void __launch_bounds__(256) groupCandidateKernel(const uint32_t* __restrict__ gStart, uint32_t G, uint64_t M, float minUniqueF,
+                                                            uint8_t* __restrict__ cand) {
+    uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= G) return;
+    uint64_t a = gStart[g], b = (g + 1 < G) ? gStart[g + 1] : M;
+    cand[g] = !((float)(b - a) < minUniqueF);
+}
+
+struct PairInfo { uint32_t start, n, qi, extId; };
+
+// one warp per candidate group: uniqueMatches, bounding box, overhang (overlap.cpp:222-262)
+__global__ void __launch_bounds__(256) pairFilterKernel(const Elem* __restrict__ hits, const uint32_t* __restrict__ gStart, uint32_t G, uint64_t M,
+                                                        const uint32_t* __restrict__ candIds, uint32_t C,
+                                                        const uint64_t* __restrict__ qHitOff, uint32_t qFirst, uint32_t nQ, uint64_t hitBase,
+                                                        const uint32_t* __restrict__ qIds, const uint32_t* __restrict__ len, OvParams P,
+                                                        uint8_t* __restrict__ pass, PairInfo* __restrict__ info) {
+    const uint32_t c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (c >= C) return;
+    const int lane = threadIdx.x & 31;
+    const uint32_t g = candIds[c];
+    const uint32_t a = gStart[g], b = (g + 1 < G) ? gStart[g + 1] : (uint32_t)M;
+    uint32_t uniq = 0; int32_t minExt = INT32_MAX, maxExt = INT32_MIN;
+    for (uint32_t i = a + lane; i < b; i += 32) {
+        const Elem e = hits[i];
+        const uint32_t cur = (uint32_t)e.key;
+        const uint32_t prev = (i == a) ? 0u : (uint32_t)hits[i - 1].key;   // prevPos starts at 0 (:223)
+        uniq += (cur != prev);
+        minExt = min(minExt, (int32_t)e.val); maxExt = max(maxExt, (int32_t)e.val);
+    }
+    uniq = __reduce_add_sync(0xffffffffu, uniq);
+    minExt = __reduce_min_sync(0xffffffffu, minExt);
+    maxExt = __reduce_max_sync(0xffffffffu, maxExt);
+    if (lane) return;
+    // query of this group: last q with qHitOff[q] - hitBase <= a
+    uint32_t lo = 0, hi = nQ;
+    while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (qHitOff[qFirst + mid] - hitBase <= a) lo = mid; else hi = mid; }
+    const uint32_t qi = qFirst + lo;
+    const uint32_t extId = (uint32_t)(hits[a].key >> 32);
+    const int32_t curLen = (int32_t)len[qIds[qi] >> 1], extLen = (int32_t)len[extId >> 1];
+    const int32_t minCur = (int32_t)(uint32_t)hits[a].key, maxCur = (int32_t)(uint32_t)hits[b - 1].key;
+    bool ok = !((float)uniq < P.minUniqueF);
+    if (maxCur - minCur < P.minOverlap || maxExt - minExt < P.minOverlap) ok = false;
+    if (P.checkOverhang && !P.forceLocal) {
+        if (min(minCur, minExt) > P.maxOverhang) ok = false;
+        if (min(curLen - maxCur, extLen - maxExt) > P.maxOverhang) ok = false;
+    }
+    pass[c] = ok;
+    PairInfo pi; pi.start = a; pi.n = b - a; pi.qi = qi; pi.extId = extId;
+    info[c] = pi;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Q6: chaining
+// ------------------------------------------------------------------------------------------------
+struct Cand { int32_t curBegin, curEnd, extBegin, extEnd, score, chainLength, filtered, pad; };
+
+__device__ __forceinline__ bool overlapTestDev(const OvParams& P, uint32_t curId, uint32_t extId, int32_t curBegin, int32_t curEnd,
+                                               int32_t extBegin, int32_t extEnd, int32_t curLen, int32_t extLen) {
+    // overlap.cpp:29-69
+    const int32_t cr = curEnd - curBegin, er = extEnd - extBegin;
+    if (cr < P.minOverlap || er < P.minOverlap) return false;
+    const float lengthDiff = (float)abs(cr - er);
+    if (lengthDiff > __fmul_rn(0.5f, (float)min(cr, er))) return false;
+    if (curId == extId) {
+        const int32_t intersect = min(curEnd, extEnd) - max(curBegin, extBegin);
+        if (intersect > cr / 2) return false;
+    }
+    if (curId == (extId ^ 1u)) {
+        const int32_t intersect = min(curEnd, extLen - extBegin) - max(curBegin, extLen - extEnd);
+        if (intersect > cr / 2) return false;
+    }
+    const int32_t lrOverhang = max(min(curBegin, extBegin), min(curLen - curEnd, extLen - extEnd));
+    if (!P.forceLocal && P.checkOverhang && lrOverhang > P.maxOverhang) return false;
+    return true;
+}
+
+__device__ __forceinline__ uint32_t filtRank(const uint32_t* __restrict__ filtBits, const uint32_t* __restrict__ filtPrefix, uint64_t qbase, uint32_t x) {
+    const uint64_t w = (qbase + x) >> 5;
+    return filtPrefix[w] + __popc(filtBits[w] & ((1u << (x & 31)) - 1u));
+}
+
+__global__ void __launch_bounds__(128) chainKernel(Elem* __restrict__ hits, const PairInfo* __restrict__ pairs, const uint32_t* __restrict__ pairIds,
+                                                   uint32_t nPairs, const uint32_t* __restrict__ qIds, const uint64_t* __restrict__ qSlotOff,
+                                                   const uint32_t* __restrict__ len, const uint32_t* __restrict__ filtBits,
+                                                   const uint32_t* __restrict__ filtPrefix, OvParams P,
+                                                   int32_t* __restrict__ curA, int32_t* __restrict__ extA, int32_t* __restrict__ score,
+                                                   int32_t* __restrict__ back, Elem* __restrict__ ord, Cand* __restrict__ cands,
+                                                   uint32_t* __restrict__ nCandOut, uint32_t* __restrict__ nKeptOut,
+                                                   unsigned long long* __restrict__ cellCount) {
+    const uint32_t w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (w >= nPairs) return;
+    const int lane = threadIdx.x & 31;
+    const PairInfo pi = pairs[pairIds[w]];
+    const uint32_t s0 = pi.start;
+    const int32_t n = (int32_t)pi.n;
+    const uint32_t curId = qIds[pi.qi], extId = pi.extId;
+    const int32_t curLen = (int32_t)len[curId >> 1], extLen = (int32_t)len[extId >> 1];
+    const int k = P.k;
+    Elem* h = hits + s0;
+    int32_t* cA = curA + s0; int32_t* eA = extA + s0; int32_t* sc = score + s0; int32_t* bk = back + s0;
+    Elem* od = ord + s0; Cand* cd = cands + s0;
+
+    // (a) optional re-sort by extPos (overlap.cpp:269-275), then split into position arrays
+    const bool extSorted = extLen > curLen;
+    if (extSorted) {
+        for (int32_t i = lane; i < n; i += 32) {
+            Elem e = h[i];
+            Elem t; t.key = (unsigned long long)e.val; t.val = (unsigned int)e.key; t.aux = 0;
+            h[i] = t;
+        }
+        __syncwarp();
+        warpIntrosort(h, n);
+        __syncwarp();
+        for (int32_t i = lane; i < n; i += 32) { Elem e = h[i]; cA[i] = (int32_t)e.val; eA[i] = (int32_t)(uint32_t)e.key; sc[i] = 0; bk[i] = -1; }
+    } else {
+        for (int32_t i = lane; i < n; i += 32) { Elem e = h[i]; cA[i] = (int32_t)(uint32_t)e.key; eA[i] = (int32_t)e.val; sc[i] = 0; bk[i] = -1; }
+    }
+    __syncwarp();
+
+    // (b) chaining DP (overlap.cpp:277-323).  Lanes evaluate 32 predecessors j = i-1, i-2, ... per step in
+    // the reference's traversal order; an inclusive prefix max over lanes reproduces "nextScore > maxScore"
+    // for every j, which is what the first break rule needs; the first lane that breaks ends the scan.
+    unsigned long long cells = 0;
+    for (int32_t i = 1; i < n; ++i) {
+        const int32_t curN = cA[i], extN = eA[i];
+        int32_t best = 0, bestId = 0;
+        for (int32_t jb = i - 1; jb >= 0; jb -= 32) {
+            const int32_t j = jb - lane;
+            const bool in = j >= 0;
+            int32_t cj = 0, ej = 0, sj = 0;
+            if (in) { cj = cA[j]; ej = eA[j]; sj = sc[j]; }
+            const int32_t dc = curN - cj, de = extN - ej;
+            const bool ok = in && 0 < dc && dc < P.maxJump && 0 < de && de < P.maxJump;
+            const int32_t jd = abs(dc - de);
+            const int32_t gap = jd > 100 ? 2 * jd : (jd >> 1);            // int32(float(LG_GAP|SM_GAP) * jd), :299
+            const int32_t s = ok ? sj + min(min(dc, de), k) - gap : INT32_MIN;
+            int32_t pm = s;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { int32_t t = __shfl_up_sync(0xffffffffu, pm, d); if (lane >= d) pm = max(pm, t); }
+            int32_t excl = __shfl_up_sync(0xffffffffu, pm, 1);
+            if (lane == 0) excl = INT32_MIN;
+            excl = max(excl, best);
+            const bool improved = ok && s > excl;
+            const bool brk = (improved && jd == 0 && dc < k) || (in && (extSorted ? de : dc) > P.maxJump);
+            const uint32_t bm = __ballot_sync(0xffffffffu, brk);
+            const int stopLane = bm ? (__ffs(bm) - 1) : 31;
+            const bool part = ok && lane <= stopLane;
+            const int32_t mx = __reduce_max_sync(0xffffffffu, part ? s : INT32_MIN);
+            if (mx > best) {
+                const uint32_t wm = __ballot_sync(0xffffffffu, part && s == mx);
+                best = mx; bestId = jb - (__ffs(wm) - 1);
+            }
+            cells += min(jb + 1, stopLane + 1);
+            if (bm) break;
+        }
+        if (lane == 0) { sc[i] = max(best, k); if (best > k) bk[i] = bestId; }
+        __syncwarp();
+    }
+    if (lane == 0 && cells) atomicAdd(cellCount, cells);
+
+    // (c) chain starts in std::sort order of scoreTable descending (overlap.cpp:331-334)
+    for (int32_t i = lane; i < n; i += 32) { Elem t; t.key = (unsigned long long)(0x7fffffff - sc[i]); t.val = (unsigned int)i; t.aux = 0; od[i] = t; }
+    __syncwarp();
+    warpIntrosort(od, n);
+    __syncwarp();
+
+    // (d) chain walk, overlapTest, filtered positions (overlap.cpp:338-427) — sequential by construction
+    uint32_t nCand = 0;
+    if (lane == 0) {
+        const uint64_t qbase = qSlotOff[pi.qi];
+        const uint32_t qn = (uint32_t)(curLen - k);
+        for (int32_t t = 0; t < n; ++t) {
+            const int32_t chainStart = (int32_t)od[t].val;
+            if (bk[chainStart] == -1) continue;
+            int32_t firstMatch = 0, chainLength = 0, pos = chainStart;
+            while (pos != -1) { firstMatch = pos; ++chainLength; const int32_t np = bk[pos]; bk[pos] = -1; pos = np; }
+            const int32_t curBegin = cA[firstMatch], extBegin = eA[firstMatch];
+            const int32_t curEnd = cA[chainStart] + k - 1, extEnd = eA[chainStart] + k - 1;
+            if (!overlapTestDev(P, curId, extId, curBegin, curEnd, extBegin, extEnd, curLen, extLen)) continue;
+            const uint32_t hiPos = min((uint32_t)curEnd + 1u, qn), loPos = min((uint32_t)curBegin, qn);
+            Cand c;
+            c.curBegin = curBegin; c.curEnd = curEnd; c.extBegin = extBegin; c.extEnd = extEnd;
+            c.score = sc[chainStart] - sc[firstMatch] + k - 1;
+            c.chainLength = chainLength;
+            c.filtered = (int32_t)(filtRank(filtBits, filtPrefix, qbase, hiPos) - filtRank(filtBits, filtPrefix, qbase, loPos));
+            c.pad = 0;
+            cd[nCand++] = c;
+        }
+    }
+    nCand = __shfl_sync(0xffffffffu, nCand, 0);
+    __syncwarp();
+
+    // (e) primary selection (overlap.cpp:431-458): std::sort by score descending, then best / containment filter
+    for (uint32_t i = lane; i < nCand; i += 32) { Elem t; t.key = (unsigned long long)(0x7fffffff - cd[i].score); t.val = i; t.aux = 0; od[i] = t; }
+    __syncwarp();
+    warpIntrosort(od, (long)nCand);
+    __syncwarp();
+    if (lane == 0) {
+        uint32_t kept = 0;
+        if (P.onlyMaxExt) { if (nCand) { od[0].aux = 1; kept = 1; } }
+        else {
+            for (uint32_t i = 0; i < nCand; ++i) {
+                const Cand c = cd[od[i].val];
+                bool contained = false;
+                for (uint32_t j = 0; j < i && !contained; ++j) {
+                    if (!od[j].aux) continue;
+                    const Cand p = cd[od[j].val];
+                    contained = p.curBegin <= c.curBegin && c.curEnd <= p.curEnd && p.extBegin <= c.extBegin && c.extEnd <= p.extEnd &&
+                                p.score > c.score;
+                }
+                od[i].aux = contained ? 0u : 1u;
+                kept += !contained;
+            }
+        }
+        nCandOut[w] = nCand;
+        nKeptOut[w] = kept;
+    }
+}
+
+// Q7: compact the kept candidates of every pair into the output, in the reference's order
+__global__ void __launch_bounds__(256) gatherOverlapsKernel(const PairInfo* __restrict__ pairs, const uint32_t* __restrict__ pairIds, uint32_t nPairs,
+                                                            const uint32_t* __restrict__ qIds, const uint32_t* __restrict__ len,
+                                                            const Elem* __restrict__ ord, const Cand* __restrict__ cands,
+                                                            const uint32_t* __restrict__ nCand, const uint64_t* __restrict__ outOff,
+                                                            uint32_t qiBase, fg_overlap* __restrict__ out) {
+    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= nPairs) return;
+    const PairInfo pi = pairs[pairIds[w]];
+    const uint32_t curId = qIds[pi.qi];
+    uint64_t o = outOff[w];
+    const uint32_t nc = nCand[w];
+    for (uint32_t i = 0; i < nc; ++i) {
+        const Elem e = ord[pi.start + i];
+        if (!e.aux) continue;
+        const Cand c = cands[pi.start + e.val];
+        fg_overlap r;
+        r.cur_id = curId; r.cur_begin = c.curBegin; r.cur_end = c.curEnd; r.cur_len = (int32_t)len[curId >> 1];
+        r.ext_id = pi.extId; r.ext_begin = c.extBegin; r.ext_end = c.extEnd; r.ext_len = (int32_t)len[pi.extId >> 1];
+        r.score = c.score; r.seq_divergence = 0.f; r.chain_length = c.chainLength; r.filtered_positions = c.filtered;
+        r.edit_distance = -1; r.aln_len = 0; r.aln_first = 0; r.aln_count = 0; r.reserved = pi.qi - qiBase;
+        out[o++] = r;
+    }
+}
+
+// test hook: sort caller-provided segments with the device introsort
+__global__ void __launch_bounds__(128) debugSortKernel(Elem* __restrict__ elems, const uint64_t* __restrict__ segOff, uint32_t nSegs) {
+    const uint32_t w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (w >= nSegs) return;
+    warpIntrosort(elems + segOff[w], (long)(segOff[w + 1] - segOff[w]));
+}
+
+void debugWarpSort(fg_ctx* ctx, uint64_t* keys, uint32_t* vals, const uint64_t* segOffsets, uint32_t nSegs) {
+    if (!nSegs) return;
+    const uint64_t n = segOffsets[nSegs];
+    std::vector<Elem> h(n);
+    for (uint64_t i = 0; i < n; ++i) { h[i].key = keys[i]; h[i].val = vals[i]; h[i].aux = 0; }
+    DevBuf<Elem> d(std::max<uint64_t>(n, 1));
+    DevBuf<uint64_t> dOff(nSegs + 1);
+    FG_CUDA(cudaMemcpyAsync(d.p, h.data(), n * sizeof(Elem), cudaMemcpyHostToDevice, ctx->stream));
+    FG_CUDA(cudaMemcpyAsync(dOff.p, segOffsets, (nSegs + 1) * 8ULL, cudaMemcpyHostToDevice, ctx->stream));
+    debugSortKernel<<<(nSegs + 3) / 4, 128, 0, ctx->stream>>>(d.p, dOff.p, nSegs);
+    checkLaunch(ctx, "debugSortKernel");
+    FG_CUDA(cudaMemcpyAsync(h.data(), d.p, n * sizeof(Elem), cudaMemcpyDeviceToHost, ctx->stream));
+    FG_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (uint64_t i = 0; i < n; ++i) { keys[i] = h[i].key; vals[i] = h[i].val; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host driver
+// ------------------------------------------------------------------------------------------------
+template <class InIt, class OutT>
+static void exclusiveScanToPlus1(fg_ctx* ctx, InIt in, OutT* outPlus1Base, uint64_t n) {
+    // outPlus1Base[0] = 0, outPlus1Base[i+1] = sum(in[0..i])
+    FG_CUDA(cudaMemsetAsync(outPlus1Base, 0, sizeof(OutT), ctx->stream));
+    if (!n) return;
+    size_t tmpBytes = 0;
+    FG_CUDA(cub::DeviceScan::InclusiveSum(nullptr, tmpBytes, in, outPlus1Base + 1, (int)n, ctx->stream));
+    DevBuf<char> tmp(tmpBytes);
+    FG_CUDA(cub::DeviceScan::InclusiveSum(tmp.p, tmpBytes, in, outPlus1Base + 1, (int)n, ctx->stream));
+    ++ctx->launches;
+    FG_CUDA(cudaStreamSynchronize(ctx->stream));
+}
+
+template <class FlagT>
+static uint32_t selectFlagged(fg_ctx* ctx, const FlagT* flags, uint32_t n, DevBuf<uint32_t>& out) {
+    out.ensure(std::max<uint32_t>(n, 1));
+    if (!n) return 0;
+    DevBuf<uint32_t> dNum(1);
+    cub::CountingInputIterator<uint32_t> it(0);
+    size_t tmpBytes = 0;
+    FG_CUDA(cub::DeviceSelect::Flagged(nullptr, tmpBytes, it, flags, out.p, dNum.p, (int)n, ctx->stream));
+    DevBuf<char> tmp(tmpBytes);
+    FG_CUDA(cub::DeviceSelect::Flagged(tmp.p, tmpBytes, it, flags, out.p, dNum.p, (int)n, ctx->stream));
+    ++ctx->launches;
+    uint32_t h = 0;
+    FG_CUDA(cudaMemcpyAsync(&h, dNum.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    FG_CUDA(cudaStreamSynchronize(ctx->stream));
+    return h;
+}
+
+void overlapsBatch(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, const fg_overlap_params& prm, fg_overlap_result* result) {
+    if (!ctx->indexed) throw Error(FG_ERR_ARG, "no index: call fg_build_index_* first");
+    if (prm.keep_alignment) throw Error(FG_ERR_ARG, "keep_alignment is not implemented on the device path yet");
+    if (prm.nucl_alignment) throw Error(FG_ERR_ARG, "nucl_alignment is not implemented on the device path yet");
+    ctx->timings.clear();
+    const int k = ctx->k;
+    for (uint32_t i = 0; i < nQ; ++i)
+        if (queryIds[i] >= 2 * ctx->nReads) throw Error(FG_ERR_ARG, "query id out of range");
+
+    OvParams P;
+    P.k = k; P.maxJump = prm.max_jump; P.minOverlap = prm.min_overlap; P.maxOverhang = prm.max_overhang;
+    P.checkOverhang = prm.max_overhang > 0; P.forceLocal = prm.force_local != 0; P.onlyMaxExt = prm.only_max_ext != 0;
+    { volatile float a = 0.01f; volatile float m = a * prm.min_overlap; P.minUniqueF = m; }   // minKmerSruvivalRate * _minOverlap
+
+    ctx->resOffsets.assign(nQ + 1, 0);
+    ctx->resOverlaps.clear();
+    ctx->resAln.clear();
+    uint64_t totHits = 0, totPairs = 0, totDpPairs = 0, totCells = 0;
+
+    // query slot space and tiles
+    std::vector<uint64_t> hQSlotOff(nQ + 1, 0);
+    std::vector<uint2> hQTiles;
+    std::vector<size_t> qTileFirst(nQ + 1, 0);
+    for (uint32_t i = 0; i < nQ; ++i) {
+        const uint32_t L = ctx->hLen[queryIds[i] >> 1];
+        const uint32_t n = L > (uint32_t)k ? L - k : 0;
+        qTileFirst[i] = hQTiles.size();
+        for (uint32_t t = 0; t < n; t += QTILE) hQTiles.push_back(make_uint2(i, t));
+        hQSlotOff[i + 1] = hQSlotOff[i] + ((n + 31u) & ~31u);
+    }
+    qTileFirst[nQ] = hQTiles.size();
+    const uint64_t nQSlots = hQSlotOff[nQ];
+    std::vector<uint64_t> hQHitOff(nQ + 1, 0);
+
+    DevBuf<uint32_t> dQIds(std::max<uint32_t>(nQ, 1));
+    DevBuf<uint64_t> dQSlotOff(nQ + 1);
+    DevBuf<uint2> dQTiles(std::max<size_t>(hQTiles.size(), 1));
+    DevBuf<uint32_t> hitCnt(nQSlots + 1), filtBits(nQSlots / 32 + 2), filtPrefix(nQSlots / 32 + 2);
+    DevBuf<uint64_t> slotInfo(nQSlots + 1), hitOff(nQSlots + 2), dQHitOff(nQ + 1);
+    if (nQ) FG_CUDA(cudaMemcpyAsync(dQIds.p, queryIds, nQ * 4ULL, cudaMemcpyHostToDevice, ctx->stream));
+    FG_CUDA(cudaMemcpyAsync(dQSlotOff.p, hQSlotOff.data(), (nQ + 1) * 8ULL, cudaMemcpyHostToDevice, ctx->stream));
+    if (!hQTiles.empty()) FG_CUDA(cudaMemcpyAsync(dQTiles.p, hQTiles.data(), hQTiles.size() * sizeof(uint2), cudaMemcpyHostToDevice, ctx->stream));
+    FG_CUDA(cudaMemsetAsync(filtBits.p, 0, filtBits.bytes(), ctx->stream));
+    FG_CUDA(cudaMemsetAsync(hitCnt.p, 0, hitCnt.bytes(), ctx->stream));
+
+    if (!hQTiles.empty()) {
+        if (nQSlots >= (1ULL << 31)) throw Error(FG_ERR_ARG, "query batch too large (>= 2^31 k-mer slots); split the call");
+        {
+            PhaseTimer pt(ctx, "gather");
+            queryLookupKernel<<<(unsigned)hQTiles.size(), 256, 0, ctx->stream>>>(ctx->dSeq.p, ctx->dWordOff.p, ctx->dLen.p, ctx->dSlotOff.p,
+                                                                                ctx->dSelBits.p, dQIds.p, dQSlotOff.p, dQTiles.p, k,
+                                                                                ctx->indexTable, hitCnt.p, slotInfo.p, filtBits.p);
+            checkLaunch(ctx, "queryLookupKernel");
+            cub::TransformInputIterator<uint64_t, CastU64, const uint32_t*> it64(hitCnt.p, CastU64());
+            exclusiveScanToPlus1(ctx, it64, hitOff.p, nQSlots);
+            cub::TransformInputIterator<uint32_t, PopcU32, const uint32_t*> itPop(filtBits.p, PopcU32());
+            exclusiveScanToPlus1(ctx, itPop, filtPrefix.p, nQSlots / 32);
+            gatherQueryHitOffKernel<<<(nQ + 256) / 256, 256, 0, ctx->stream>>>(hitOff.p, dQSlotOff.p, nQ, dQHitOff.p);
+            checkLaunch(ctx, "gatherQueryHitOffKernel");
+            FG_CUDA(cudaMemcpyAsync(hQHitOff.data(), dQHitOff.p, (nQ + 1) * 8ULL, cudaMemcpyDeviceToHost, ctx->stream));
+            FG_CUDA(cudaStreamSynchronize(ctx->stream));
+        }
+    }
+    totHits = hQHitOff[nQ];
+
+    // sub-batches of consecutive queries with a bounded number of hits
+    uint64_t budget = 64ULL << 20;
+    if (const char* e = getenv("FG_HIT_BUDGET")) budget = std::max<uint64_t>(1024, strtoull(e, nullptr, 10));
+    std::vector<fg_overlap> hOut;
+    DevBuf<Elem> hits, ord; DevBuf<int32_t> curA, extA, score, back; DevBuf<Cand> cands; DevBuf<uint8_t> flags;
+    DevBuf<uint32_t> gStart, candIds, pairIds;
+    PinnedBuf<fg_overlap> pinned;
+    std::vector<std::vector<fg_overlap>> perQuery;   // not used; results are appended in query order
+
+    uint32_t qa = 0;
+    while (qa < nQ) {
+        uint32_t qb = qa + 1;
+        while (qb < nQ && hQHitOff[qb + 1] - hQHitOff[qa] <= budget) ++qb;
+        const uint64_t hitBase = hQHitOff[qa], M = hQHitOff[qb] - hitBase;
+        const uint32_t nq = qb - qa;
+        if (M >= (1ULL << 31)) throw Error(FG_ERR_ARG, "a single query produced >= 2^31 k-mer hits");
+        if (M == 0) { qa = qb; continue; }
+        hits.ensure(M); ord.ensure(M); curA.ensure(M); extA.ensure(M); score.ensure(M); back.ensure(M); cands.ensure(M); flags.ensure(M);
+        const size_t tA = qTileFirst[qa], tB = qTileFirst[qb];
+        {
+            PhaseTimer pt(ctx, "gather");
+            expandKernel<<<(unsigned)(tB - tA), 256, 0, ctx->stream>>>(ctx->dLen.p, ctx->dEntries.p, dQIds.p, dQSlotOff.p, dQTiles.p + tA, k,
+                                                                      hitOff.p, slotInfo.p, hitBase, hits.p);
+            checkLaunch(ctx, "expandKernel");
+        }
+        {
+            PhaseTimer pt(ctx, "hit_sort");
+            sortHitsKernel<<<(nq + 3) / 4, 128, 0, ctx->stream>>>(hits.p, dQHitOff.p, qa, nq, hitBase);
+            checkLaunch(ctx, "sortHitsKernel");
+        }
+        uint32_t G = 0, C = 0, Pn = 0;
+        DevBuf<PairInfo> pairInfo;
+        DevBuf<uint8_t> candFlag, passFlag;
+        {
+            PhaseTimer pt(ctx, "group");
+            groupFlagKernel<<<gridFor(M), 256, 0, ctx->stream>>>(hits.p, M, flags.p);
+            checkLaunch(ctx, "groupFlagKernel");
+            queryStartFlagKernel<<<(nq + 255) / 256, 256, 0, ctx->stream>>>(dQHitOff.p, qa, nq, hitBase, M, flags.p);
+            checkLaunch(ctx, "queryStartFlagKernel");
+            G = selectFlagged(ctx, flags.p, (uint32_t)M, gStart);
+            candFlag.alloc(std::max<uint32_t>(G, 1));
+            groupCandidateKernel<<<(G + 255) / 256, 256, 0, ctx->stream>>>(gStart.p, G, M, P.minUniqueF, candFlag.p);
+            checkLaunch(ctx, "groupCandidateKernel");
+            C = selectFlagged(ctx, candFlag.p, G, candIds);
+            pairInfo.alloc(std::max<uint32_t>(C, 1)); passFlag.alloc(std::max<uint32_t>(C, 1));
+            if (C) {
+                pairFilterKernel<<<(C + 7) / 8, 256, 0, ctx->stream>>>(hits.p, gStart.p, G, M, candIds.p, C, dQHitOff.p, qa, nq, hitBase,
+                                                                      dQIds.p, ctx->dLen.p, P, passFlag.p, pairInfo.p);
+                checkLaunch(ctx, "pairFilterKernel");
+                Pn = selectFlagged(ctx, passFlag.p, C, pairIds);
+            }
+        }
+        totPairs += G; totDpPairs += Pn;
+        if (Pn) {
+            DevBuf<uint32_t> nCand(Pn), nKept(Pn);
+            DevBuf<uint64_t> outOff(Pn + 1);
+            DevBuf<unsigned long long> dCells(1);
+            FG_CUDA(cudaMemsetAsync(dCells.p, 0, 8, ctx->stream));
+            {
+                PhaseTimer pt(ctx, "chain");
+                chainKernel<<<(Pn + 3) / 4, 128, 0, ctx->stream>>>(hits.p, pairInfo.p, pairIds.p, Pn, dQIds.p, dQSlotOff.p, ctx->dLen.p,
+                                                                  filtBits.p, filtPrefix.p, P, curA.p, extA.p, score.p, back.p, ord.p,
+                                                                  cands.p, nCand.p, nKept.p, dCells.p);
+                checkLaunch(ctx, "chainKernel");
+            }
+            PhaseTimer pt(ctx, "d2h");
+            cub::TransformInputIterator<uint64_t, CastU64, const uint32_t*> it64(nKept.p, CastU64());
+            exclusiveScanToPlus1(ctx, it64, outOff.p, Pn);
+            uint64_t nOut = 0; unsigned long long cells = 0;
+            FG_CUDA(cudaMemcpyAsync(&nOut, outOff.p + Pn, 8, cudaMemcpyDeviceToHost, ctx->stream));
+            FG_CUDA(cudaMemcpyAsync(&cells, dCells.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+            FG_CUDA(cudaStreamSynchronize(ctx->stream));
+            totCells += cells;
+            if (nOut) {
+                DevBuf<fg_overlap> dOut(nOut);
+                gatherOverlapsKernel<<<(Pn + 255) / 256, 256, 0, ctx->stream>>>(pairInfo.p, pairIds.p, Pn, dQIds.p, ctx->dLen.p, ord.p, cands.p,
+                                                                               nCand.p, outOff.p, 0, dOut.p);
+                checkLaunch(ctx, "gatherOverlapsKernel");
+                pinned.ensure(nOut);
+                FG_CUDA(cudaMemcpyAsync(pinned.p, dOut.p, nOut * sizeof(fg_overlap), cudaMemcpyDeviceToHost, ctx->stream));
+                FG_CUDA(cudaStreamSynchronize(ctx->stream));
+                hOut.insert(hOut.end(), pinned.p, pinned.p + nOut);
+            }
+        }
+        qa = qb;
+    }
+
+    // host epilogue: divergence (overlap.cpp:417-423), threshold (:470), maxOverlaps (:218-219)
+    const float sampleRate = ctx->stats.sample_rate;
+    size_t pos = 0;
+    for (uint32_t qi = 0; qi < nQ; ++qi) {
+        ctx->resOffsets[qi] = ctx->resOverlaps.size();
+        size_t detected = 0;
+        while (pos < hOut.size() && hOut[pos].reserved == qi) {
+            // one target group = run of equal ext_id
+            size_t end = pos;
+            while (end < hOut.size() && hOut[end].reserved == qi && hOut[end].ext_id == hOut[pos].ext_id) ++end;
+            const bool stop = prm.max_overlaps != 0 && detected >= (size_t)prm.max_overlaps;
+            for (size_t i = pos; i < end && !stop; ++i) {
+                fg_overlap o = hOut[i];
+                const int32_t curRange = o.cur_end - o.cur_begin, extRange = o.ext_end - o.ext_begin;
+                volatile float normLen = std::max(curRange, extRange) - o.filtered_positions;
+                volatile float mr = (float)o.chain_length * sampleRate;
+                volatile float matchRate = mr / normLen;
+                matchRate = std::min((float)matchRate, 1.0f);
+                volatile float inv = 1 / matchRate;
+                volatile float lg = std::log((float)inv);
+                o.seq_divergence = lg / k;
+                o.reserved = 0;
+                if (o.seq_divergence < prm.max_divergence) { ctx->resOverlaps.push_back(o); ++detected; }
+            }
+            pos = end;
+        }
+    }
+    ctx->resOffsets[nQ] = ctx->resOverlaps.size();
+    if (pos != hOut.size()) throw Error(FG_ERR_INTERNAL, "overlap records out of query order");
+
+    result->n_queries = nQ;
+    result->offsets = ctx->resOffsets.data();
+    result->overlaps = ctx->resOverlaps.data();
+    result->aln_pairs = nullptr;
+    result->n_aln_pairs = 0;
+    result->n_hits = totHits; result->n_pairs = totPairs; result->n_dp_pairs = totDpPairs; result->n_dp_cells = totCells;
+}
+
+}  // namespace fg

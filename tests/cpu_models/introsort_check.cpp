@@ -1,0 +1,83 @@
+// Host build of flye_b200/csrc/introsort_warp.cuh (32 lanes run as loops) checked against std::sort.
+// Usage: introsort_check [n_trials] [seed]   -> prints "OK <arrays> <elements>" or the first mismatch.
+#define FG_WARP_HOST 1
+#include "../../flye_b200/csrc/introsort_warp.cuh"
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#include <algorithm>
+#include <random>
+
+static bool checkOne(std::vector<fg::Elem> a, const char* what) {
+    std::vector<fg::Elem> ref = a;
+    std::sort(ref.begin(), ref.end(), [](const fg::Elem& x, const fg::Elem& y) { return x.key < y.key; });
+    fg::warpIntrosort(a.data(), (long)a.size());
+    for (size_t i = 0; i < a.size(); ++i)
+        if (a[i].key != ref[i].key || a[i].val != ref[i].val) {
+            printf("MISMATCH %s n=%zu at %zu: got (%llu,%u) want (%llu,%u)\n", what, a.size(), i, a[i].key, a[i].val,
+                   ref[i].key, ref[i].val);
+            return false;
+        }
+    return true;
+}
+
+// median-of-3 killer (Musser) to drive introsort into its heap-sort fallback
+static std::vector<unsigned long long> killer(size_t n) {
+    std::vector<unsigned long long> v(n);
+    size_t k = n / 2;
+    for (size_t i = 0; i < k; ++i) { v[i] = (i % 2 == 0) ? i + 1 : k + i + (k % 2 == 0 ? 0 : 1); }
+    for (size_t i = 0; i < k; ++i) { if (i % 2 == 0) v[i] = i + 1; else v[i] = k + i + 1; v[k + i] = 2 * (i + 1); }
+    return v;
+}
+
+int main(int argc, char** argv) {
+    int trials = argc > 1 ? atoi(argv[1]) : 3000;
+    unsigned seed = argc > 2 ? atoi(argv[2]) : 12345;
+    std::mt19937_64 rng(seed);
+    size_t arrays = 0, elements = 0;
+    auto mk = [&](size_t n, int mode, unsigned long long distinct) {
+        std::vector<fg::Elem> a(n);
+        for (size_t i = 0; i < n; ++i) {
+            unsigned long long k;
+            switch (mode) {
+                case 0: k = rng() % distinct; break;                       // random with ties
+                case 1: k = i / (1 + rng() % 3); break;                    // presorted with runs
+                case 2: k = (n - i) / 2; break;                            // reversed with pairs
+                case 3: k = 7; break;                                      // all equal
+                case 4: k = i < n / 2 ? i : n - i; break;                  // organ pipe
+                case 5: k = (i * 2654435761ULL) % distinct; break;         // structured
+                default: k = rng(); break;                                 // distinct
+            }
+            a[i] = {k, (unsigned)i, 0u};
+        }
+        return a;
+    };
+    for (int t = 0; t < trials; ++t) {
+        size_t n;
+        int r = t % 10;
+        if (r < 4) n = 1 + rng() % 200; else if (r < 8) n = 1 + rng() % 5000; else n = 1 + rng() % 70000;
+        int mode = rng() % 7;
+        unsigned long long distinct = 1 + rng() % (r % 2 ? 50 : (n + 1));
+        auto a = mk(n, mode, distinct);
+        ++arrays; elements += n;
+        if (!checkOne(a, "random")) return 1;
+    }
+    for (size_t n : {17u, 18u, 31u, 32u, 33u, 34u, 48u, 49u, 50u, 63u, 64u, 65u, 66u, 96u, 97u, 128u, 129u, 1000u, 4096u, 100000u}) {
+        for (int mode = 0; mode < 7; ++mode) { auto a = mk(n, mode, 5); ++arrays; elements += n; if (!checkOne(a, "edge")) return 1; }
+        auto kv = killer(n);
+        std::vector<fg::Elem> a(n);
+        for (size_t i = 0; i < n; ++i) a[i] = {kv[i], (unsigned)i, 0u};
+        ++arrays; elements += n;
+        if (!checkOne(a, "killer")) return 1;
+    }
+    // exhaustive small alphabets around the chunk sizes: all arrays over {0,1,2} of length 17..20 is 3^20 -> sample
+    for (int t = 0; t < trials * 5; ++t) {
+        size_t n = 17 + rng() % 60;
+        std::vector<fg::Elem> a(n);
+        for (size_t i = 0; i < n; ++i) a[i] = {(unsigned long long)(rng() % 3), (unsigned)i, 0u};
+        ++arrays; elements += n;
+        if (!checkOne(a, "tiny-alphabet")) return 1;
+    }
+    printf("OK %zu %zu heapsorts=%ld\n", arrays, elements, fg::g_heapSortCalls);
+    return 0;
+}

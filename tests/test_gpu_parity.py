@@ -1,0 +1,96 @@
+"""-m gpu: the CUDA path, called through the C ABI, against the oracle on the same seeded inputs.
+Bar: bit-exact for every integer field, the k-mer histogram, the whole index, and the divergence float bits."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+import parity_util as pu
+
+pytestmark = pytest.mark.gpu
+RAW = os.path.join(pu.CFG_DIR, "raw_reads.cfg")
+HIFI = os.path.join(pu.CFG_DIR, "hifi.cfg")
+
+
+def _std_sort(keys, vals, seg):
+    lib = ctypes.CDLL(os.path.join(pu.ROOT, "tests", "cpu_models", "_bin", "libstdsort.so"))
+    k, v = keys.copy(), vals.copy()
+    lib.std_sort_segments(k.ctypes.data_as(ctypes.c_void_p), v.ctypes.data_as(ctypes.c_void_p),
+                          seg.ctypes.data_as(ctypes.c_void_p), ctypes.c_uint32(len(seg) - 1))
+    return k, v
+
+
+def test_device_introsort_matches_std_sort(engine):
+    """The warp introsort must reproduce libstdc++ std::sort's permutation, ties included."""
+    rng = np.random.default_rng(5)
+    sizes = [0, 1, 2, 16, 17, 18, 31, 32, 33, 34, 47, 48, 49, 50, 63, 64, 65, 66, 96, 97, 127, 128, 129, 1000, 4097]
+    sizes += list(rng.integers(1, 300, 300)) + list(rng.integers(300, 6000, 60)) + [70000, 150001]
+    keys, seg = [], [0]
+    for i, n in enumerate(sizes):
+        mode = i % 6
+        if mode == 0:
+            k = rng.integers(0, max(2, n // 3 + 1), n)
+        elif mode == 1:
+            k = rng.integers(0, 4, n)
+        elif mode == 2:
+            k = np.arange(n) // 2
+        elif mode == 3:
+            k = (n - np.arange(n)) // 3
+        elif mode == 4:
+            k = np.full(n, 9)
+        else:
+            k = rng.integers(0, 1 << 40, n)
+        keys.append(k.astype(np.uint64))
+        seg.append(seg[-1] + n)
+    keys = np.concatenate(keys)
+    vals = np.arange(len(keys), dtype=np.uint32)
+    seg = np.array(seg, dtype=np.uint64)
+    gk, gv = engine.debug_warp_sort(keys, vals, seg)
+    sk, sv = _std_sort(keys, vals, seg)
+    assert np.array_equal(gk, sk)
+    bad = np.nonzero(gv != sv)[0]
+    assert len(bad) == 0, "first mismatch at %d (segment %d)" % (bad[0], np.searchsorted(seg, bad[0], side="right") - 1)
+
+
+def _compare(tmp, name, exts):
+    res = {}
+    for e in exts:
+        n, sample = pu.diff_files(os.path.join(tmp, "ref." + e), os.path.join(tmp, "gpu." + e))
+        res[e] = n
+        if n:
+            print("%s .%s: %d differing lines; first: %s" % (name, e, n, sample[:4]))
+    return res
+
+
+def test_clr_small_full_parity(engine, tmp_path):
+    tmp = str(tmp_path)
+    reads = pu.simulate(os.path.join(tmp, "r.fasta"), genome_len=200000, coverage=20, seed=7)
+    ref = pu.run_oracle(reads, RAW, os.path.join(tmp, "ref"), k=15, extra=["--dump-index"])
+    _, info = pu.gpu_pipeline(reads, RAW, os.path.join(tmp, "gpu"), k=15, dump_index=True, engine=engine)
+    print(info)
+    res = _compare(tmp, "clr_small", ["hist", "index", "ovlp"])
+    assert ref["overlaps"] > 1000
+    assert res == {"hist": 0, "index": 0, "ovlp": 0}
+
+
+def test_clr_options(engine, tmp_path):
+    """either strand as query, forceLocal, maxOverlaps, all primary overlaps per target"""
+    tmp = str(tmp_path)
+    reads = pu.simulate(os.path.join(tmp, "r.fasta"), genome_len=120000, coverage=15, seed=3)
+    for opts, kw in [(["--both-strands", "--force-local", "--max-overlaps", "5"], dict(both_strands=True, force_local=True, max_overlaps=5)),
+                     (["--all-ext"], dict(all_ext=True))]:
+        pu.run_oracle(reads, RAW, os.path.join(tmp, "ref"), k=15, extra=opts)
+        pu.gpu_pipeline(reads, RAW, os.path.join(tmp, "gpu"), k=15, engine=engine, **kw)
+        res = _compare(tmp, "clr_opts %s" % opts, ["ovlp"])
+        assert res == {"ovlp": 0}
+
+
+def test_clr_k17_parity(engine, tmp_path):
+    """k = 17 takes the 64-bit key path"""
+    tmp = str(tmp_path)
+    reads = pu.simulate(os.path.join(tmp, "r.fasta"), genome_len=150000, coverage=18, error=0.10, seed=21)
+    pu.run_oracle(reads, RAW, os.path.join(tmp, "ref"), extra=["--dump-index"])
+    pu.gpu_pipeline(reads, RAW, os.path.join(tmp, "gpu"), dump_index=True, engine=engine)
+    res = _compare(tmp, "clr_k17", ["hist", "index", "ovlp"])
+    assert res == {"hist": 0, "index": 0, "ovlp": 0}
