@@ -90,7 +90,7 @@ def test_clr_k17_parity(engine, tmp_path):
     """k = 17 takes the 64-bit key path"""
     tmp = str(tmp_path)
     reads = pu.simulate(os.path.join(tmp, "r.fasta"), genome_len=150000, coverage=18, error=0.10, seed=21)
-    pu.run_oracle(reads, RAW, os.path.join(tmp, "ref"), extra=["--dump-index"])
+    pu.run_oracle(reads, RAW, os.path.join(tmp, "ref"), binary=pu.RESTATE, extra=["--dump-index"])  # the reference's k=17 flat counter needs 8 GiB + a 17 G-entry scan
     pu.gpu_pipeline(reads, RAW, os.path.join(tmp, "gpu"), dump_index=True, engine=engine)
     res = _compare(tmp, "clr_k17", ["hist", "index", "ovlp"])
     assert res == {"hist": 0, "index": 0, "ovlp": 0}
