@@ -1,0 +1,303 @@
+#!/usr/bin/env python
+"""bench.py — reads/sec through k-mer index + overlap detection (BASELINE.json metric).
+
+One step = one pass of the hot path over the whole synthetic read set:
+    [H2D of the packed reads]  ->  k-mer counting (solid presets)  ->  VertexIndex build  ->
+    estimateOverlaperParameters (1000 random queries)  ->  getSeqOverlaps for every forward read  -> [D2H overlaps]
+`value`  = reads / step time with the reads already resident in HBM (upload outside the timed region);
+`e2e`    = the same through the C-ABI calls with HOST buffers: every step re-uploads the packed reads from
+           pinned host memory and brings every overlap record back.
+Workloads (BASELINE.json configs):
+    hifi : configs[1]  4.6 Mb genome, 30x HiFi-like reads (0.5 % error, ~15 kb), minimizers w=10 k=17, edlib+HPC
+    clr  : configs[0]  4.6 Mb genome, 50x CLR-like reads (12 % error, mean 7.5 kb), solid k-mers k=15
+--impl reference times the reference's own CPU implementation (oracle/_ref/flye_ref_harness, the unmodified
+reference sources; the CPU restatement if that binary is absent) on all host cores, on a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+WORKLOADS = {
+    "hifi": dict(name="configs[1]: simulated 4.6 Mb genome, 30x HiFi-like reads (0.5% error, ~15 kb), asm_hifi settings "
+                      "(k=17 minimizers w=10, HPC edit-distance divergence)",
+                 sim=dict(genome_len=4600000, coverage=30, mean_len=15000, shape=20, error=0.005, seed=2), cfg="hifi.cfg", k=17,
+                 cpu_queries=400),
+    "clr": dict(name="configs[0]: simulated 4.6 Mb genome, 50x CLR-like reads (12% error, mean 7.5 kb), asm_raw_reads settings, k=15",
+                sim=dict(genome_len=4600000, coverage=50, mean_len=7500, shape=2, error=0.12, seed=1), cfg="raw_reads.cfg", k=15,
+                cpu_queries=3000),
+}
+MIN_OVERLAP = 1000
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def make_reads(wl, scale):
+    import parity_util as pu
+    from flye_b200 import build
+    build.build_tools()
+    sim = dict(wl["sim"])
+    sim["genome_len"] = max(50000, int(sim["genome_len"] * scale))
+    tag = "_".join("%s%s" % (k[0], v) for k, v in sorted(sim.items()))
+    path = os.path.join("/tmp", "flye_b200_bench_%s.fasta" % tag)
+    if not os.path.exists(path):
+        pu.simulate(path + ".tmp", **sim)
+        os.replace(path + ".tmp", path)
+    return path
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def run_reference(args, wl, reads_path):
+    """The reference's own CPU path, bounded sample: full index over all reads + the estimate pass + the first
+    Q forward reads as overlap queries; overlap time is scaled to all reads."""
+    import parity_util as pu
+    binary, kind = pu.oracle_binary()
+    cores = os.cpu_count() or 1
+    cfg = os.path.join(pu.CFG_DIR, wl["cfg"])
+    q = wl["cpu_queries"]
+    vals = []
+    n_reads = None
+    for it in range(args.warmup + args.steps):
+        if kind == "port" and it > 0:
+            break
+        r = pu.run_oracle(reads_path, cfg, "/tmp/flye_b200_bench_ref", k=wl["k"], threads=cores, binary=binary,
+                          extra=["--max-queries", str(q)])
+        n_reads = r["reads"]
+        nq = max(1, r["queries"])
+        t = r["t_count"] + r["t_index"] + r["t_estimate"] + r["t_overlaps"] * (n_reads / nq)
+        log("reference step %d: count %.2fs index %.2fs estimate %.2fs overlaps(%d queries) %.2fs -> projected %.1fs" %
+            (it, r["t_count"], r["t_index"], r["t_estimate"], nq, r["t_overlaps"], t))
+        if it >= args.warmup or kind == "port":
+            vals.append(t)
+    t = sum(vals) / len(vals)
+    value = n_reads / t
+    sample = "index over all %d reads + estimateOverlaperParameters + getSeqOverlaps of the first %d forward reads; overlap time " \
+             "scaled by reads/queries" % (n_reads, q)
+    return value, t, n_reads, dict(value=value, unit="reads/s", cores=cores, kind=kind, sample=sample)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("FLYE_B200_WORKLOAD", "hifi"), choices=sorted(WORKLOADS))
+    ap.add_argument("--scale", type=float, default=float(os.environ.get("FLYE_B200_SCALE", "1.0")), help="genome scale (tests)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    config = {"workload": wl["name"], "reads": None, "bases": None, "kmer": wl["k"], "min_overlap": MIN_OVERLAP,
+              "cache": "inputs (packed reads >= 34 MB, index and hit arrays of several GB) exceed the 126 MB L2",
+              "scale": args.scale, "partition": "reads sharded across ranks, index replicated" if world > 1 else "single GPU"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        reads_path = make_reads(wl, args.scale)
+        value, t, n_reads, cb = run_reference(args, wl, reads_path)
+        config["reads"] = n_reads
+        print(json.dumps({"impl": "reference", "metric": "reads/sec through k-mer index + overlap detection", "value": value,
+                          "unit": "reads/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3,
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+                          "config": config, "cpu_baseline": cb,
+                          "e2e": {"value": value, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    import numpy as np
+    import torch
+    import flye_b200 as fb
+    import parity_util as pu
+
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    reads_path = make_reads(wl, args.scale)
+    cfg = pu.load_cfg(os.path.join(pu.CFG_DIR, wl["cfg"]))
+    k = wl["k"]
+    reads = fb.read_fasta(reads_path, MIN_OVERLAP)
+    packed, woff, lens = fb.pack_reads(reads)
+    n_reads, n_bases = len(reads), int(lens.sum())
+    config["reads"], config["bases"] = n_reads, n_bases
+    del reads
+    # host buffers in pinned memory (what the e2e arm uploads every step)
+    packed_t = torch.from_numpy(packed.view(np.int64)).pin_memory()
+    packed_pin = packed_t.numpy().view(np.uint64)
+    eng = fb.Engine(local_rank)
+    stream = torch.cuda.ExternalStream(eng.stream_ptr(), device=torch.device("cuda", local_rank))
+    common = dict(max_jump=int(cfg["maximum_jump"]), min_overlap=MIN_OVERLAP, max_overhang=int(cfg["maximum_overhang"]),
+                  only_max_ext=True, nucl_alignment=bool(cfg["reads_base_alignment"]), use_hpc=bool(cfg["hpc_scoring_on"]))
+    est_ids = pu.libc_rand_ids(2 * n_reads)
+    # this rank's queries (forward reads); index built from all reads on every rank (replicated)
+    lo, hi = (n_reads * rank) // world, (n_reads * (rank + 1)) // world
+    queries = np.arange(2 * lo, 2 * hi, 2, dtype=np.uint32)
+    phase_ms, phase_calls, ovl_stats, n_ovl = {}, {}, {}, 0
+
+    def step(upload):
+        nonlocal phase_ms, phase_calls, ovl_stats, n_ovl
+        phase_ms, phase_calls = {}, {}
+
+        def grab():
+            t = eng.timings()
+            for name, ms in t.items():
+                phase_ms[name] = phase_ms.get(name, 0.0) + ms
+                phase_calls[name] = phase_calls.get(name, 0) + eng.last_calls[name]
+        if upload:
+            eng.upload_packed(packed_pin, woff, lens)
+        if int(cfg["use_minimizers"]):
+            eng.build_index_minimizers(k, 1, int(cfg["minimizer_window"]), cfg["repeat_kmer_rate"])
+        else:
+            eng.count_kmers(k)
+            grab()
+            eng.build_index_solid(2, cfg["meta_read_top_kmer_rate"], int(cfg["meta_read_filter_kmer_freq"]), cfg["repeat_kmer_rate"],
+                                  float(int(cfg["assemble_kmer_sample"])))
+        grab()
+        offs, ov, _ = eng.overlaps(est_ids, max_divergence=1.0, **common)
+        divs = []
+        for i in range(len(est_ids)):
+            a, b = int(offs[i]), int(offs[i + 1])
+            if b > a:
+                rng = ov["cur_end"][a:b] - ov["cur_begin"][a:b]
+                divs.append(ov["seq_divergence"][a + int(np.argmax(rng))])
+        mean = pu.median_f32(divs) if divs else np.float32(0.5)
+        max_div = np.float32((mean if bool(cfg["assemble_divergence_relative"]) else np.float32(0.0)) + np.float32(cfg["assemble_ovlp_divergence"]))
+        offs, ov, ovl_stats = eng.overlaps(queries, max_divergence=float(max_div), **common)
+        grab()
+        n_ovl = int(offs[-1])
+        return n_ovl
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(upload, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            step(upload)
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1) / steps
+        if world > 1:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    eng.upload_packed(packed_pin, woff, lens)
+    for _ in range(args.warmup):
+        step(False)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = eng.launches()
+    ms_resident = timed(False, args.steps)
+    launches = (eng.launches() - launches0) // max(1, args.steps)
+    resident_phases, resident_calls, stats = dict(phase_ms), dict(phase_calls), dict(ovl_stats)
+    ms_e2e = timed(True, args.steps)
+    clocks = sampler.stop()
+
+    total_reads = n_reads   # all ranks together process every forward read exactly once
+    value = total_reads / (ms_resident / 1e3)
+    e2e_value = total_reads / (ms_e2e / 1e3)
+    h2d = int(packed.nbytes + woff.nbytes + lens.nbytes + 4 * (len(queries) + len(est_ids)))
+    d2h = int(72 * n_ovl + 8 * (len(queries) + 1))
+
+    # roofline of the dominant kernel phase (algorithmic bytes: SURVEY.md §8d, stated in DESIGN.md)
+    M, O = stats.get("n_hits", 0), n_ovl
+    w = 4 if 2 * k <= 32 else 8
+    n_k = n_bases - k * n_reads
+    alg = {"hit_sort": 24.0 * M, "chain": 12.0 * M + 40.0 * O, "gather": (w + 8.0) * n_k + 20.0 * M,
+           "count_sort": 3.0 * w * n_k, "index_sort": 0.0, "select": (w + 5.0) * n_k, "extract": 0.25 * n_bases + w * n_k}
+    kernel_phases = {p: ms for p, ms in resident_phases.items() if p in alg and alg[p] > 0}
+    peak, peak_src = measured_peak()
+    roofline = None
+    if kernel_phases:
+        dom = max(kernel_phases, key=kernel_phases.get)
+        calls = max(1, resident_calls.get(dom, 1))
+        per_launch_ms = kernel_phases[dom] / calls
+        achieved = (alg[dom] / calls) / (per_launch_ms / 1e3) / 1e9
+        roofline = {"bound": "hbm", "kernel": {"hit_sort": "sortHitsKernel", "chain": "chainKernel", "gather": "queryLookupKernel+expandKernel",
+                                               "count_sort": "cub radix sort (keys)", "select": "selectKernel",
+                                               "extract": "extractKeysKernel"}.get(dom, dom),
+                    "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                    "peak_source": peak_src, "launches": calls, "ms_per_launch": per_launch_ms,
+                    "algorithmic_bytes_per_launch": alg[dom] / calls}
+
+    line = {"metric": "reads/sec through k-mer index + overlap detection", "value": value, "unit": "reads/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_resident, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "int64", "data": "synthetic", "config": config, "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "reads/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches), "roofline": roofline,
+            "phases_ms": {p: round(v, 3) for p, v in resident_phases.items()},
+            "work": {"kmer_hits": int(M), "target_groups": int(stats.get("n_pairs", 0)), "dp_pairs": int(stats.get("n_dp_pairs", 0)),
+                     "dp_cells": int(stats.get("n_dp_cells", 0)), "overlaps": int(O)}}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            _, _, _, cb = run_reference(argparse.Namespace(warmup=0, steps=1), wl, reads_path)
+            line["cpu_baseline"] = cb
+        except Exception as e:   # the baseline is a reported number, never a reason to lose the GPU line
+            line["cpu_baseline"] = {"value": None, "unit": "reads/s", "cores": os.cpu_count(), "kind": "unavailable", "sample": str(e)}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

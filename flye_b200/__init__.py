@@ -18,11 +18,11 @@ ERR_NAMES = {-1: "FG_ERR_CUDA", -2: "FG_ERR_ARG", -3: "FG_ERR_KMER_SIZE", -4: "F
              -5: "FG_ERR_OVERFLOW", -6: "FG_ERR_NCCL", -7: "FG_ERR_INTERNAL"}
 
 # every symbol include/flye_b200.h declares
-SYMBOLS = ["fg_ctx_create", "fg_ctx_destroy", "fg_last_error", "fg_kernel_launches", "fg_last_timings",
+SYMBOLS = ["fg_ctx_create", "fg_ctx_destroy", "fg_last_error", "fg_stream", "fg_kernel_launches", "fg_last_timings",
            "fg_reads_upload", "fg_reads_upload_ascii", "fg_count_kmers", "fg_kmer_hist", "fg_kmer_freq",
            "fg_build_index_solid", "fg_build_index_minimizers", "fg_index_clear", "fg_index_lookup",
            "fg_index_positions", "fg_index_export", "fg_overlaps_batch", "fg_comm_unique_id", "fg_comm_init",
-           "fg_comm_set_shard", "fg_debug_warp_sort"]
+           "fg_comm_set_shard", "fg_debug_warp_sort", "fg_debug_edit_distance"]
 
 
 class IndexStats(C.Structure):
@@ -69,9 +69,11 @@ def load_lib():
     lib.fg_ctx_destroy.restype = None
     lib.fg_last_error.argtypes = [vp]
     lib.fg_last_error.restype = C.c_char_p
+    lib.fg_stream.argtypes = [vp]
+    lib.fg_stream.restype = C.c_void_p
     lib.fg_kernel_launches.argtypes = [vp]
     lib.fg_kernel_launches.restype = C.c_uint64
-    lib.fg_last_timings.argtypes = [vp, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.c_int]
+    lib.fg_last_timings.argtypes = [vp, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.POINTER(C.c_int), C.c_int]
     lib.fg_reads_upload.argtypes = [vp, u64p, u64p, u32p, C.c_uint32]
     lib.fg_reads_upload_ascii.argtypes = [vp, C.c_char_p, u64p, C.c_uint32]
     lib.fg_count_kmers.argtypes = [vp, C.c_int, u64p]
@@ -88,6 +90,7 @@ def load_lib():
     lib.fg_comm_init.argtypes = [vp, C.c_int, C.c_int, u8p]
     lib.fg_comm_set_shard.argtypes = [vp, C.c_uint32, C.c_uint32]
     lib.fg_debug_warp_sort.argtypes = [vp, u64p, u32p, u64p, C.c_uint32]
+    lib.fg_debug_edit_distance.argtypes = [vp, u8p, C.c_int, u8p, C.c_int, C.POINTER(C.c_int)]
     _lib = lib
     return lib
 
@@ -263,11 +266,23 @@ class Engine:
         self._check(self.lib.fg_debug_warp_sort(self.ctx, _ptr(keys, C.c_uint64), _ptr(vals, C.c_uint32), _ptr(seg, C.c_uint64), len(seg) - 1))
         return keys, vals
 
+    def debug_edit_distance(self, a, b):
+        a = np.ascontiguousarray(a, dtype=np.uint8)
+        b = np.ascontiguousarray(b, dtype=np.uint8)
+        d = C.c_int()
+        self._check(self.lib.fg_debug_edit_distance(self.ctx, _ptr(a, C.c_uint8), len(a), _ptr(b, C.c_uint8), len(b), C.byref(d)))
+        return d.value
+
     def timings(self):
         names = (C.c_char_p * 32)()
         ms = (C.c_float * 32)()
-        n = self.lib.fg_last_timings(self.ctx, names, ms, 32)
+        calls = (C.c_int * 32)()
+        n = self.lib.fg_last_timings(self.ctx, names, ms, calls, 32)
+        self.last_calls = {names[i].decode(): calls[i] for i in range(n)}
         return {names[i].decode(): ms[i] for i in range(n)}
+
+    def stream_ptr(self):
+        return int(self.lib.fg_stream(self.ctx) or 0)
 
     def launches(self):
         return int(self.lib.fg_kernel_launches(self.ctx))

@@ -106,12 +106,16 @@ void fg_ctx_destroy(fg_ctx* ctx) {
 }
 
 const char* fg_last_error(const fg_ctx* ctx) { return ctx ? ctx->lastError.c_str() : "null context"; }
+void* fg_stream(const fg_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 uint64_t fg_kernel_launches(const fg_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
-int fg_last_timings(const fg_ctx* ctx, const char** names, float* ms, int cap) {
+int fg_last_timings(const fg_ctx* ctx, const char** names, float* ms, int* calls, int cap) {
     if (!ctx) return 0;
     int n = 0;
-    for (const auto& t : ctx->timings) { if (n >= cap) break; names[n] = t.first.c_str(); ms[n] = t.second; ++n; }
+    for (size_t i = 0; i < ctx->timings.size() && n < cap; ++i, ++n) {
+        names[n] = ctx->timings[i].first.c_str(); ms[n] = ctx->timings[i].second;
+        if (calls) calls[n] = ctx->timingCalls[i];
+    }
     return n;
 }
 
@@ -284,6 +288,13 @@ int fg_overlaps_batch(fg_ctx* ctx, const uint32_t* queryIds, uint32_t n, const f
     return guarded(ctx, [&] {
         if (!params || !result || (n && !queryIds)) throw Error(FG_ERR_ARG, "null argument");
         fg::overlapsBatch(ctx, queryIds, n, *params, result);
+    });
+}
+
+int fg_debug_edit_distance(fg_ctx* ctx, const uint8_t* a, int n, const uint8_t* b, int m, int* distance) {
+    return guarded(ctx, [&] {
+        if (n < 0 || m < 0 || !distance) throw Error(FG_ERR_ARG, "bad argument");
+        *distance = fg::debugEditDistance(ctx, a, n, b, m);
     });
 }
 

@@ -222,7 +222,7 @@ static void countKmersT(fg_ctx* ctx) {
 void countKmers(fg_ctx* ctx, int k) {
     if (k > 17) throw Error(FG_ERR_KMER_SIZE, "Can't use flat counter for k-mer size > 17");   // vertex_index.cpp:504-507
     setKmerSize(ctx, k);
-    ctx->timings.clear();
+    ctx->timings.clear(); ctx->timingCalls.clear();
     if (2 * k <= 32) countKmersT<uint32_t>(ctx); else countKmersT<uint64_t>(ctx);
 }
 
@@ -713,7 +713,7 @@ static void buildFromSelection(fg_ctx* ctx, DevBuf<uint32_t>& rcBits, int minCov
 
 void buildIndexSolid(fg_ctx* ctx, int minFreq, float selectRate, int tandemFreq, float repeatRate, float sampleRate) {
     if (!ctx->counted) throw Error(FG_ERR_ARG, "fg_count_kmers must run before fg_build_index_solid");
-    ctx->timings.clear();
+    ctx->timings.clear(); ctx->timingCalls.clear();
     ctx->minimizerMode = false;
     const int k = ctx->k;
     const uint32_t firstRead = ctx->shardSet ? ctx->shardFirst : 0, nReadsShard = ctx->shardSet ? ctx->shardCount : ctx->nReads;
@@ -766,7 +766,7 @@ void buildIndexMinimizers(fg_ctx* ctx, int k, int minCov, int window, float repe
     if (window < 1) throw Error(FG_ERR_ARG, "wrong minimizer length");   // kmer.h:208
     if (window >= 64) throw Error(FG_ERR_ARG, "minimizer window must be < 64");
     setKmerSize(ctx, k);
-    ctx->timings.clear();
+    ctx->timings.clear(); ctx->timingCalls.clear();
     ctx->minimizerMode = true;
     const uint32_t firstRead = ctx->shardSet ? ctx->shardFirst : 0, nReadsShard = ctx->shardSet ? ctx->shardCount : ctx->nReads;
     const uint64_t nWords = ctx->nSlots / 32 + 1;

@@ -60,6 +60,7 @@ struct fg_ctx {
 
     // ---- timings of the last call ----
     std::vector<std::pair<std::string, float>> timings;
+    std::vector<int> timingCalls;         // launches of the phase's kernel (parallel to timings)
 
     // ---- overlap results (host, library owned) ----
     std::vector<uint64_t> resOffsets;
@@ -88,8 +89,9 @@ struct PhaseTimer {
         float ms = 0;
         cudaEventElapsedTime(&ms, a, b);
         bool found = false;
-        for (auto& t : ctx->timings) if (t.first == name) { t.second += ms; found = true; }
-        if (!found) ctx->timings.emplace_back(name, ms);
+        for (size_t i = 0; i < ctx->timings.size(); ++i)
+            if (ctx->timings[i].first == name) { ctx->timings[i].second += ms; ++ctx->timingCalls[i]; found = true; }
+        if (!found) { ctx->timings.emplace_back(name, ms); ctx->timingCalls.push_back(1); }
         cudaEventDestroy(a); cudaEventDestroy(b);
     }
 };
@@ -114,6 +116,8 @@ void buildIndexMinimizers(fg_ctx* ctx, int k, int minCov, int window, float repe
 void overlapsBatch(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQueries, const fg_overlap_params& p,
                    fg_overlap_result* result);
 
+void editDistances(fg_ctx* ctx, fg_overlap* dOv, const fg_overlap* hOv, uint32_t nOv, bool useHpc);
+int debugEditDistance(fg_ctx* ctx, const uint8_t* a, int n, const uint8_t* b, int m);
 void debugWarpSort(fg_ctx* ctx, uint64_t* keys, uint32_t* vals, const uint64_t* segOffsets, uint32_t nSegs);
 
 }  // namespace fg

@@ -472,8 +472,7 @@ static uint32_t selectFlagged(fg_ctx* ctx, const FlagT* flags, uint32_t n, DevBu
 void overlapsBatch(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, const fg_overlap_params& prm, fg_overlap_result* result) {
     if (!ctx->indexed) throw Error(FG_ERR_ARG, "no index: call fg_build_index_* first");
     if (prm.keep_alignment) throw Error(FG_ERR_ARG, "keep_alignment is not implemented on the device path yet");
-    if (prm.nucl_alignment) throw Error(FG_ERR_ARG, "nucl_alignment is not implemented on the device path yet");
-    ctx->timings.clear();
+    ctx->timings.clear(); ctx->timingCalls.clear();
     const int k = ctx->k;
     for (uint32_t i = 0; i < nQ; ++i)
         if (queryIds[i] >= 2 * ctx->nReads) throw Error(FG_ERR_ARG, "query id out of range");
@@ -615,6 +614,13 @@ void overlapsBatch(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, const fg_
                 pinned.ensure(nOut);
                 FG_CUDA(cudaMemcpyAsync(pinned.p, dOut.p, nOut * sizeof(fg_overlap), cudaMemcpyDeviceToHost, ctx->stream));
                 FG_CUDA(cudaStreamSynchronize(ctx->stream));
+                if (prm.nucl_alignment) {   // overlap.cpp:463-468
+                    if (nOut >= (1ULL << 31)) throw Error(FG_ERR_ARG, "too many overlaps in one sub-batch");
+                    PhaseTimer pe(ctx, "edit");
+                    editDistances(ctx, dOut.p, pinned.p, (uint32_t)nOut, prm.use_hpc != 0);
+                    FG_CUDA(cudaMemcpyAsync(pinned.p, dOut.p, nOut * sizeof(fg_overlap), cudaMemcpyDeviceToHost, ctx->stream));
+                    FG_CUDA(cudaStreamSynchronize(ctx->stream));
+                }
                 hOut.insert(hOut.end(), pinned.p, pinned.p + nOut);
             }
         }
@@ -642,6 +648,10 @@ void overlapsBatch(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, const fg_
                 volatile float inv = 1 / matchRate;
                 volatile float lg = std::log((float)inv);
                 o.seq_divergence = lg / k;
+                if (prm.nucl_alignment) {   // alignment.cpp:240-245: (float)editDistance / max(len, len)
+                    if (o.edit_distance < 0) o.seq_divergence = 1.0f;
+                    else { volatile float dv = (float)o.edit_distance / (size_t)o.aln_len; o.seq_divergence = dv; }
+                }
                 o.reserved = 0;
                 if (o.seq_divergence < prm.max_divergence) { ctx->resOverlaps.push_back(o); ++detected; }
             }

@@ -37,12 +37,15 @@ typedef struct fg_ctx fg_ctx;
 int         fg_ctx_create(int cuda_device, fg_ctx** out);
 void        fg_ctx_destroy(fg_ctx* ctx);
 const char* fg_last_error(const fg_ctx* ctx);
+/* the CUDA stream (cudaStream_t) every kernel of this context is launched on — for external event timing */
+void*       fg_stream(const fg_ctx* ctx);
 /* number of kernels this library has launched on the context since creation (bench.py "gpu_launches") */
 uint64_t    fg_kernel_launches(const fg_ctx* ctx);
 /* device time (ms, CUDA events on the context's stream) of the phases of the most recent call;
  * names: "extract","count_sort","count_reduce","select","emit","index_sort","index_table",
- *        "gather","hit_sort","group","chain","edit","d2h" — returns number written */
-int         fg_last_timings(const fg_ctx* ctx, const char** names, float* ms, int cap);
+ *        "gather","hit_sort","group","chain","edit","d2h"; calls[i] = how many times the phase ran (sub-batches);
+ *        returns number written */
+int         fg_last_timings(const fg_ctx* ctx, const char** names, float* ms, int* calls, int cap);
 
 /* ---- reads: replaces SequenceContainer's storage for the device side ----------------------------------
  * (sequence.h:54-69 packing; sequence_container.cpp:48-79 ids; :359-392 global offsets)
@@ -143,6 +146,7 @@ int fg_comm_init(fg_ctx* ctx, int n_ranks, int rank, const uint8_t id[FG_NCCL_ID
 int fg_comm_set_shard(fg_ctx* ctx, uint32_t first_read, uint32_t n_reads);
 
 /* ---- test hook: the std::sort-exact warp introsort on caller data (segments sorted independently) ---- */
+int fg_debug_edit_distance(fg_ctx* ctx, const uint8_t* a, int n, const uint8_t* b, int m, int* distance);
 int fg_debug_warp_sort(fg_ctx* ctx, uint64_t* keys, uint32_t* vals, const uint64_t* seg_offsets, uint32_t n_segments);
 
 #ifdef __cplusplus

@@ -94,3 +94,51 @@ def test_clr_k17_parity(engine, tmp_path):
     pu.gpu_pipeline(reads, RAW, os.path.join(tmp, "gpu"), dump_index=True, engine=engine)
     res = _compare(tmp, "clr_k17", ["hist", "index", "ovlp"])
     assert res == {"hist": 0, "index": 0, "ovlp": 0}
+
+
+def _edit_distance_np(a, b):
+    prev = np.arange(len(b) + 1)
+    for i in range(1, len(a) + 1):
+        cur = np.empty_like(prev)
+        cur[0] = i
+        sub = prev[:-1] + (b != a[i - 1])
+        best = np.minimum(sub, prev[1:] + 1)
+        # left dependency: cur[j] = min(best[j-1], cur[j-1]+1) -> prefix scan
+        cur[1:] = best
+        cur = np.minimum.accumulate(cur - np.arange(len(cur))) + np.arange(len(cur))
+        prev = cur
+    return int(prev[-1])
+
+
+def test_device_edit_distance_exact(engine):
+    """wavefront edit distance == textbook DP (global, unit costs), incl. empty / unequal / unrelated inputs"""
+    rng = np.random.default_rng(11)
+    cases = [(0, 0, 0.0), (0, 7, 0.0), (9, 0, 0.0), (1, 1, 0.5), (50, 50, 0.0), (300, 300, 0.02), (1500, 1500, 0.01),
+             (1200, 900, 0.3), (700, 700, 1.0), (2000, 2000, 0.1), (33, 64, 0.2)]
+    for n, m, err in cases:
+        a = rng.integers(0, 4, n).astype(np.uint8)
+        if err >= 1.0:
+            b = rng.integers(0, 4, m).astype(np.uint8)
+        else:
+            b = []
+            for c in a[:m] if m <= n else a:
+                u = rng.random()
+                if u < err / 3:
+                    continue
+                if u < 2 * err / 3:
+                    b.append(rng.integers(0, 4)); b.append(c); continue
+                b.append((c + 1) % 4 if u < err else c)
+            b = np.array(b, dtype=np.uint8) if len(b) else np.zeros(0, np.uint8)
+        assert engine.debug_edit_distance(a, b) == _edit_distance_np(a, b), (n, m, err)
+
+
+def test_hifi_small_full_parity(engine, tmp_path):
+    """minimizer index + homopolymer-compressed edit-distance divergence (BASELINE configs 2/5 code path)"""
+    tmp = str(tmp_path)
+    reads = pu.simulate(os.path.join(tmp, "r.fasta"), genome_len=150000, coverage=15, mean_len=8000, shape=20, error=0.005, seed=11)
+    ref = pu.run_oracle(reads, HIFI, os.path.join(tmp, "ref"), extra=["--dump-index", "--both-strands"])
+    _, info = pu.gpu_pipeline(reads, HIFI, os.path.join(tmp, "gpu"), dump_index=True, both_strands=True, engine=engine)
+    print(info)
+    res = _compare(tmp, "hifi_small", ["index", "ovlp"])
+    assert ref["overlaps"] > 1000
+    assert res == {"index": 0, "ovlp": 0}
