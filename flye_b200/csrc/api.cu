@@ -15,6 +15,7 @@ int guarded(fg_ctx* ctx, F&& body) {
     std::lock_guard<std::mutex> lock(ctx->mtx);
     try {
         FG_CUDA(cudaSetDevice(ctx->device));
+        fg::allocStream() = ctx->stream;
         body();
         return FG_OK;
     } catch (const Error& e) {
@@ -92,6 +93,11 @@ int fg_ctx_create(int device, fg_ctx** out) {
     fg_ctx* ctx = new fg_ctx();
     ctx->device = device;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return FG_ERR_CUDA; }
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        unsigned long long never = ~0ULL;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &never);
+    }
     *out = ctx;
     return FG_OK;
 }
@@ -102,6 +108,7 @@ void fg_ctx_destroy(fg_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     cudaStream_t s = ctx->stream;
     delete ctx;
+    cudaStreamSynchronize(s);
     cudaStreamDestroy(s);
 }
 
@@ -263,6 +270,7 @@ int fg_index_export(fg_ctx* ctx, uint64_t* keys, uint8_t* isRep, uint64_t* first
         const uint64_t S = ctx->nUKeys, E = ctx->nEntriesStored;
         if (nKeys) *nKeys = S;
         if (nEntries) *nEntries = E;
+        FG_CUDA(cudaStreamSynchronize(ctx->stream));
         if (keys && S) {
             std::vector<uint64_t> pl(S);
             // keys arrive in the device's canonical value; give them back in the reference's representation

@@ -30,29 +30,35 @@ struct Error : std::runtime_error {
     } while (0)
 
 // ---------------------------------------------------------------------------------------------
-// device buffers (plain cudaMalloc; phases free their temporaries when they return)
+// device buffers: stream-ordered allocations from the device's default memory pool, whose release
+// threshold fg_ctx_create raises to "never" — after the first step every buffer is a pool hit, so the
+// phases can allocate/free their temporaries freely without paying cudaMalloc/cudaFree.
 // ---------------------------------------------------------------------------------------------
+inline cudaStream_t& allocStream() { static thread_local cudaStream_t s = nullptr; return s; }
+
 template <class T>
 struct DevBuf {
     T* p = nullptr;
     size_t n = 0;
+    cudaStream_t owner = nullptr;
     DevBuf() = default;
     explicit DevBuf(size_t count) { alloc(count); }
     DevBuf(const DevBuf&) = delete;
     DevBuf& operator=(const DevBuf&) = delete;
-    DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+    DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n), owner(o.owner) { o.p = nullptr; o.n = 0; }
     DevBuf& operator=(DevBuf&& o) noexcept {
-        if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; }
+        if (this != &o) { release(); p = o.p; n = o.n; owner = o.owner; o.p = nullptr; o.n = 0; }
         return *this;
     }
     ~DevBuf() { release(); }
     void alloc(size_t count) {
         release();
         n = count;
-        if (count) FG_CUDA(cudaMalloc((void**)&p, count * sizeof(T)));
+        owner = allocStream();
+        if (count) FG_CUDA(cudaMallocAsync((void**)&p, count * sizeof(T), owner));
     }
     void ensure(size_t count) { if (count > n) alloc(count + count / 8); }
-    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    void release() { if (p) cudaFreeAsync(p, owner); p = nullptr; n = 0; }
     size_t bytes() const { return n * sizeof(T); }
 };
 

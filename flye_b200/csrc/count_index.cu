@@ -265,33 +265,53 @@ __global__ void __launch_bounds__(256) selectKernel(const uint64_t* __restrict__
     const uint64_t base = slotOff[r];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nWarps = blockDim.x >> 5;
 
+    __shared__ uint32_t hist[256];
+    __shared__ uint32_t sPrefix, sRemaining, sMaxF;
+    if (threadIdx.x == 0) sMaxF = 0;
+    __syncthreads();
+    uint32_t myMax = 0;
     for (uint32_t p0 = warp * 32; p0 < n; p0 += nWarps * 32) {
         const uint32_t p = p0 + lane;
         bool rc = false;
         if (p < n) {
             uint64_t key = canonFromWindow(windowAt(words, p, k), k, rc);
             uint64_t payload;
-            freq[base + p] = tableFind(countTable, key, payload) ? (uint32_t)payload : 1u;
+            const uint32_t f = tableFind(countTable, key, payload) ? (uint32_t)payload : 1u;
+            freq[base + p] = f;
+            myMax = max(myMax, f);
         }
         uint32_t m = __ballot_sync(0xffffffffu, p < n && rc);
         if (lane == 0) rcBits[(base + p0) >> 5] = m;
     }
+    myMax = __reduce_max_sync(0xffffffffu, myMax);
+    if (lane == 0) atomicMax(&sMaxF, myMax);
     __syncthreads();
+    const uint32_t maxF = sMaxF;
 
-    __shared__ uint32_t hist[256];
-    __shared__ uint32_t sPrefix, sRemaining;
     if (threadIdx.x == 0) {
         unsigned long long rank = __float2ull_rz(__fmul_rn(selectRate, (float)n));
         if (rank >= n) rank = n - 1;   // the reference would index out of bounds for selectRate >= 1
         sPrefix = 0; sRemaining = (uint32_t)rank;
     }
     for (int shift = 24; shift >= 0; shift -= 8) {
+        if (shift > 0 && (maxF >> shift) == 0) continue;   // every value has digit 0 here: nothing to decide
         for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
         __syncthreads();
         const uint32_t prefix = sPrefix;
-        for (uint32_t p = threadIdx.x; p < n; p += blockDim.x) {
-            uint32_t f = freq[base + p];
-            if (shift == 24 || (f >> (shift + 8)) == (prefix >> (shift + 8))) atomicAdd(&hist[(f >> shift) & 255u], 1u);
+        for (uint32_t p0 = warp * 32; p0 < n; p0 += nWarps * 32) {
+            const uint32_t p = p0 + lane;
+            bool take = false; uint32_t digit = 0;
+            if (p < n) {
+                const uint32_t f = freq[base + p];
+                take = shift == 24 || (f >> (shift + 8)) == (prefix >> (shift + 8));
+                digit = (f >> shift) & 255u;
+            }
+            // warp-aggregated histogram update: frequencies are tiny and repeat, so most lanes share a bin
+            const uint32_t act = __ballot_sync(0xffffffffu, take);
+            if (take) {
+                const uint32_t peers = __match_any_sync(act, digit);
+                if (lane == __ffs(peers) - 1) atomicAdd(&hist[digit], (uint32_t)__popc(peers));
+            }
         }
         __syncthreads();
         if (threadIdx.x == 0) {

@@ -66,6 +66,7 @@ struct fg_ctx {
     std::vector<uint64_t> resOffsets;
     std::vector<fg_overlap> resOverlaps;
     std::vector<int32_t> resAln;
+    fg::PinnedBuf<fg_overlap> pinnedOut;  // D2H staging, kept across calls
 
     // ---- NCCL ----
     void* ncclComm = nullptr;

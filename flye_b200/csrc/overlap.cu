@@ -539,7 +539,7 @@ void overlapsBatch(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, const fg_
     std::vector<fg_overlap> hOut;
     DevBuf<Elem> hits, ord; DevBuf<int32_t> curA, extA, score, back; DevBuf<Cand> cands; DevBuf<uint8_t> flags;
     DevBuf<uint32_t> gStart, candIds, pairIds;
-    PinnedBuf<fg_overlap> pinned;
+    PinnedBuf<fg_overlap>& pinned = ctx->pinnedOut;
     std::vector<std::vector<fg_overlap>> perQuery;   // not used; results are appended in query order
 
     uint32_t qa = 0;

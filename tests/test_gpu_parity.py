@@ -142,3 +142,32 @@ def test_hifi_small_full_parity(engine, tmp_path):
     res = _compare(tmp, "hifi_small", ["index", "ovlp"])
     assert ref["overlaps"] > 1000
     assert res == {"index": 0, "ovlp": 0}
+
+
+def test_clr_quarter_scale_parity(engine, tmp_path):
+    """BASELINE config 1 at a quarter of the genome (1.15 Mb, 50x, 12 % error): ~7.6 k reads, ~110 M k-mer hits,
+    several sub-batches; every overlap field identical to the unmodified reference."""
+    tmp = str(tmp_path)
+    reads = pu.simulate(os.path.join(tmp, "r.fasta"), genome_len=1150000, coverage=50, seed=1)
+    ref = pu.run_oracle(reads, RAW, os.path.join(tmp, "ref"), k=15)
+    os.environ["FG_HIT_BUDGET"] = str(24 << 20)   # force several sub-batches
+    try:
+        _, info = pu.gpu_pipeline(reads, RAW, os.path.join(tmp, "gpu"), k=15, engine=engine)
+    finally:
+        del os.environ["FG_HIT_BUDGET"]
+    print(info)
+    res = _compare(tmp, "clr_quarter", ["hist", "ovlp"])
+    assert ref["overlaps"] > 100000
+    assert res == {"hist": 0, "ovlp": 0}
+
+
+def test_hifi_1mb_parity(engine, tmp_path):
+    """BASELINE config 2 code path at 1 Mb / 30x / 15 kb reads against the unmodified reference (edlib)"""
+    tmp = str(tmp_path)
+    reads = pu.simulate(os.path.join(tmp, "r.fasta"), genome_len=1000000, coverage=30, mean_len=15000, shape=20, error=0.005, seed=2)
+    ref = pu.run_oracle(reads, HIFI, os.path.join(tmp, "ref"))
+    _, info = pu.gpu_pipeline(reads, HIFI, os.path.join(tmp, "gpu"), engine=engine)
+    print(info)
+    res = _compare(tmp, "hifi_1mb", ["ovlp"])
+    assert ref["overlaps"] > 20000
+    assert res == {"ovlp": 0}
