@@ -262,8 +262,8 @@ def main():
     M, O = stats.get("n_hits", 0), n_ovl
     w = 4 if 2 * k <= 32 else 8
     n_k = n_bases - k * n_reads
-    alg = {"hit_sort": 24.0 * M, "chain": 12.0 * M + 40.0 * O, "gather": (w + 8.0) * n_k + 20.0 * M,
-           "count_sort": 3.0 * w * n_k, "index_sort": 0.0, "select": (w + 5.0) * n_k, "extract": 0.25 * n_bases + w * n_k}
+    alg = {"hit_sort_top": 24.0 * M, "hit_sort_small": 24.0 * M, "chain_dp": 12.0 * M + 40.0 * O, "gather": (w + 8.0) * n_k + 20.0 * M,
+           "count_sort": 3.0 * w * n_k, "select": (w + 5.0) * n_k, "extract": 0.25 * n_bases + w * n_k}
     kernel_phases = {p: ms for p, ms in resident_phases.items() if p in alg and alg[p] > 0}
     peak, peak_src = measured_peak()
     roofline = None
@@ -272,7 +272,8 @@ def main():
         calls = max(1, resident_calls.get(dom, 1))
         per_launch_ms = kernel_phases[dom] / calls
         achieved = (alg[dom] / calls) / (per_launch_ms / 1e3) / 1e9
-        roofline = {"bound": "hbm", "kernel": {"hit_sort": "sortHitsKernel", "chain": "chainKernel", "gather": "queryLookupKernel+expandKernel",
+        roofline = {"bound": "hbm", "kernel": {"hit_sort_top": "sortTopKernel", "hit_sort_small": "sortSmallKernel", "chain_dp": "chainDpKernel",
+                                               "gather": "queryLookupKernel+expandKernel",
                                                "count_sort": "cub radix sort (keys)", "select": "selectKernel",
                                                "extract": "extractKeysKernel"}.get(dom, dom),
                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,

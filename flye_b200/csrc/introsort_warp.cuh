@@ -140,6 +140,41 @@ FG_DEV void seqHeapSort(Elem* first, long len) {
     }
 }
 
+// literal sequential introsort (one thread) for the rare small arrays sorted inside per-thread code
+FG_DEV long seqUnguardedPartition(Elem* a, long first, long last, long pivot) {   // stl_algo.h:1871-1889
+    const unsigned long long p = a[pivot].key;
+    for (;;) {
+        while (a[first].key < p) ++first;
+        --last;
+        while (p < a[last].key) --last;
+        if (!(first < last)) return first;
+        elemSwap(a, first, last);
+        ++first;
+    }
+}
+FG_DEV void seqIntrosort(Elem* a, long n) {
+    if (n < 2) return;
+    if (n > 16) {
+        long stF[64], stL[64]; int stD[64];
+        int sp = 0, lg = 0;
+        while ((n >> (lg + 1)) != 0) ++lg;
+        long f = 0, l = n; int d = 2 * lg;
+        for (;;) {
+            while (l - f > 16) {
+                if (d == 0) { seqHeapSort(a + f, l - f); break; }
+                --d;
+                seqMedianToFirst(a, f, f + 1, f + (l - f) / 2, l - 1);
+                const long cut = seqUnguardedPartition(a, f + 1, l, f);
+                if (l - cut > 16) { stF[sp] = cut; stL[sp] = l; stD[sp] = d; ++sp; }
+                l = cut;
+            }
+            if (sp == 0) break;
+            --sp; f = stF[sp]; l = stL[sp]; d = stD[sp];
+        }
+    }
+    seqInsertionSort(a, 0, n);   // __final_insertion_sort == stable insertion sort of the whole array
+}
+
 // ---- the data-parallel Hoare partition ---------------------------------------------------------------
 // Partitions arr[f,l) (l-f > 16) exactly like
 //     __move_median_to_first(f, f+1, f+(l-f)/2, l-1); return __unguarded_partition(f+1, l, f);
@@ -161,13 +196,26 @@ FG_DEV long warpPartition(Elem* arr, long f, long l) {
     bool haveR = false;
     FG_LANEVAR(Elem, eL);
     FG_LANEVAR(Elem, eR);
+    // Software prefetch: the next full chunk of each side is loaded one refill ahead.  Positions of the
+    // untouched middle are never written, so a prefetched chunk stays valid as long as the other side has
+    // not claimed any of its 32 positions (hi - lo >= 32 at the time it is used).
+    FG_LANEVAR(Elem, pfL);
+    FG_LANEVAR(Elem, pfR);
+    bool pfLok = false, pfRok = false;
+    if (hi - lo >= 64) {
+        FG_FOR_LANES FG_L(pfL) = arr[lo + lane]; FG_L(pfR) = arr[hi - 32 + lane]; FG_END_LANES
+        pfLok = pfRok = true;
+    }
 
     for (;;) {
         if (pendL == 0 && lo < hi) {
             Lb = lo;
             const long nL = (hi - lo < 32) ? (hi - lo) : 32;
+            if (pfLok && nL == 32) { FG_FOR_LANES FG_L(eL) = FG_L(pfL); FG_END_LANES }
+            else { FG_FOR_LANES if (lane < nL) FG_L(eL) = arr[Lb + lane]; FG_END_LANES }
             lo += nL;
-            FG_FOR_LANES if (lane < nL) FG_L(eL) = arr[Lb + lane]; FG_END_LANES
+            pfLok = hi - lo >= 32;
+            if (pfLok) { FG_FOR_LANES FG_L(pfL) = arr[lo + lane]; FG_END_LANES }
             FG_BALLOT(geL, lane < nL && FG_L(eL).key >= p);
             FG_BALLOT(leL, lane < nL && FG_L(eL).key <= p);
             pendL = geL;
@@ -176,8 +224,11 @@ FG_DEV long warpPartition(Elem* arr, long f, long l) {
             if (haveR && geR) firstGeAbove = Rb + FG_CTZ(geR);
             const long nR = (hi - lo < 32) ? (hi - lo) : 32;
             Rb = hi - nR;
+            if (pfRok && nR == 32) { FG_FOR_LANES FG_L(eR) = FG_L(pfR); FG_END_LANES }
+            else { FG_FOR_LANES if (lane < nR) FG_L(eR) = arr[Rb + lane]; FG_END_LANES }
             hi = Rb;
-            FG_FOR_LANES if (lane < nR) FG_L(eR) = arr[Rb + lane]; FG_END_LANES
+            pfRok = hi - lo >= 32;
+            if (pfRok) { FG_FOR_LANES FG_L(pfR) = arr[hi - 32 + lane]; FG_END_LANES }
             FG_BALLOT(geR, lane < nR && FG_L(eR).key >= p);
             FG_BALLOT(leR, lane < nR && FG_L(eR).key <= p);
             pendR = leR;
@@ -254,10 +305,19 @@ FG_DEV long warpPartition(Elem* arr, long f, long l) {
 }
 
 // ---- the whole sort -------------------------------------------------------------------------------------
-// Sorts arr[0,n) ascending by key with std::sort's exact permutation.  One warp; no shared memory: the
-// explicit recursion stack (<= 2*lg n entries) and the pending-leaf list live in lane registers.
-FG_DEV void warpIntrosort(Elem* arr, long n) {
-    if (n < 2) return;
+// The introsort loop (__introsort_loop, stl_algo.h:1918-1940) on arr[f0,l0) with depth budget d0, followed by the
+// leaf insertion sorts.  One warp; no shared memory: the explicit recursion stack (<= 2*lg n entries) and the
+// pending-leaf list live in lane registers.
+//
+// Two-level use: with small > 0, every range of at most `small` elements is NOT processed here but handed to
+// `sink(f, l, depthBudget)`; a second kernel finishes those ranges in shared memory (warpIntrosortRange with
+// small = 0 on the staged copy).  Ranges are disjoint, so the order in which they are finished is irrelevant
+// to the resulting permutation.
+struct NoSink { FG_DEV void operator()(long, long, int) const {} };
+
+template <class Sink>
+FG_DEV void warpIntrosortRange(Elem* arr, long f0, long l0, int d0, long small, Sink& sink) {
+    if (l0 - f0 < 2) return;
     FG_LANEVAR(long, stF0); FG_LANEVAR(long, stL0); FG_LANEVAR(int, stD0);   // stack entries 0..31
     FG_LANEVAR(long, stF1); FG_LANEVAR(long, stL1); FG_LANEVAR(int, stD1);   // stack entries 32..63
     FG_LANEVAR(long, lfF);  FG_LANEVAR(long, lfL);                           // pending leaves
@@ -270,20 +330,21 @@ FG_DEV void warpIntrosort(Elem* arr, long n) {
         FG_SYNCWARP();
         nLeaf = 0;
     };
-    auto addLeaf = [&](long f, long l) {
+    // a finished-partitioning range: leaf (<= 16) or, in two-level mode, a task for the second kernel
+    auto retire = [&](long f, long l, int d) {
         if (l - f < 2) return;
+        if (small > 0) { sink(f, l, d); return; }
         FG_FOR_LANES if (lane == nLeaf) { FG_L(lfF) = f; FG_L(lfL) = l; } FG_END_LANES
         if (++nLeaf == 32) flushLeaves();
     };
+    const long stopAt = small > 16 ? small : 16;   // ranges of at most this many elements are retired
 
-    int lg = 0;
-    while ((n >> (lg + 1)) != 0) ++lg;
-    long f = 0, l = n;
-    int d = 2 * lg;
+    long f = f0, l = l0;
+    int d = d0;
     bool have = true;
     while (have) {
         bool heapSorted = false;
-        while (l - f > 16) {
+        while (l - f > stopAt) {
             if (d == 0) {
 #ifndef FG_WARP_HOST
                 if (fg::laneId() == 0)
@@ -298,7 +359,7 @@ FG_DEV void warpIntrosort(Elem* arr, long n) {
             }
             --d;
             const long cut = warpPartition(arr, f, l);
-            if (l - cut > 16) {   // "recurse" on the right part: push
+            if (l - cut > stopAt) {   // "recurse" on the right part: push
                 FG_FOR_LANES
                     if (lane == (sp & 31)) {
                         if (sp < 32) { FG_L(stF0) = cut; FG_L(stL0) = l; FG_L(stD0) = d; }
@@ -306,10 +367,10 @@ FG_DEV void warpIntrosort(Elem* arr, long n) {
                     }
                 FG_END_LANES
                 ++sp;
-            } else addLeaf(cut, l);
+            } else retire(cut, l, d);
             l = cut;
         }
-        if (!heapSorted) addLeaf(f, l);
+        if (!heapSorted) retire(f, l, d);
         if (sp == 0) have = false;
         else {
             --sp;
@@ -326,6 +387,19 @@ FG_DEV void warpIntrosort(Elem* arr, long n) {
         }
     }
     if (nLeaf) flushLeaves();
+}
+
+FG_DEV int introsortDepth(long n) {   // std::__lg(n) * 2
+    int lg = 0;
+    while ((n >> (lg + 1)) != 0) ++lg;
+    return 2 * lg;
+}
+
+// std::sort(arr, arr + n) in one go
+FG_DEV void warpIntrosort(Elem* arr, long n) {
+    if (n < 2) return;
+    NoSink none;
+    warpIntrosortRange(arr, 0, n, introsortDepth(n), 0, none);
 }
 
 }  // namespace fg

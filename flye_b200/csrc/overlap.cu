@@ -6,12 +6,14 @@
 //   Q2 scans              hit offsets per slot / per query; prefix popcounts of the repetitive bitmap
 //   Q3 expandKernel       load-balanced expansion of the position lists into KmerMatch records in the
 //                         reference's emission order (query position ascending, list order) (:176-196)
-//   Q4 sortHitsKernel     one warp per query: std::sort-exact introsort by (extId,curPos) (:201-204)
+//   Q4 sortTop/SmallKernel std::sort-exact segmented introsort of every query's hits by (extId,curPos) (:201-204):
+//                         warp-parallel partitioning in global memory, then shared-memory tasks
 //   Q5 group kernels      target groups, uniqueMatches / bounding-box / overhang prefilters (:216-262)
-//   Q6 chainKernel        one warp per (query,target) pair: optional std::sort-exact re-sort by extPos
-//                         (:269-275), chaining DP with warp prefix-max emulating the sequential scan and its
-//                         two break rules (:277-323), std::sort-exact score ordering (:331-334), chain walk,
-//                         overlapTest, filtered-position count (:338-427), primary selection (:431-458)
+//   Q6 per (query,target) pair: pairPrepKernel + the same segmented sort for the optional re-sort by extPos
+//                         (:269-275); chainDpKernel = chaining DP, one warp per pair, warp prefix-max emulating the
+//                         sequential scan and its two break rules (:277-323); segmented sort of the score order
+//                         (:331-334); chainWalkKernel = chain walk, overlapTest, filtered-position count
+//                         (:338-427) and primary selection (:431-458), one thread per pair
 //   Q7 gather + host epilogue: seqDivergence with the reference's float expression and glibc logf (:417-423),
 //                         divergence filter (:470-473), maxOverlaps cut (:218-219).
 #include "ctx.cuh"
@@ -143,14 +145,67 @@ __global__ void __launch_bounds__(256) expandKernel(const uint32_t* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------------
-// Q4
+// Q4: segmented std::sort-exact sorting, two levels.
+//   sortTopKernel    one warp per segment, in global memory with software prefetch: partitions until every
+//                    range is <= SORT_SMALL elements and appends those ranges to a task list
+//   sortSmallKernel  persistent warps pull tasks, stage the range in shared memory (16 KB per warp), finish the
+//                    introsort there and write it back — most recursion levels run at shared-memory latency and
+//                    the tasks balance the load across the chip whatever the segment-length distribution is.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) sortHitsKernel(Elem* __restrict__ hits, const uint64_t* __restrict__ qHitOff, uint32_t qFirst,
-                                                      uint32_t nQ, uint64_t hitBase) {
+static constexpr int SORT_SMALL = 1024;
+struct Seg { uint32_t start, n; };
+struct SortTask { uint32_t start, n; int depth; };
+
+struct TaskSinkDev {
+    SortTask* tasks; uint32_t* counter; uint32_t cap; uint32_t base;
+    __device__ __forceinline__ void operator()(long f, long l, int d) const {
+        if (laneId() == 0) {
+            const uint32_t t = atomicAdd(counter, 1u);
+            if (t < cap) { SortTask k; k.start = base + (uint32_t)f; k.n = (uint32_t)(l - f); k.depth = d; tasks[t] = k; }
+        }
+    }
+};
+
+__global__ void __launch_bounds__(128) sortTopKernel(Elem* __restrict__ arr, const Seg* __restrict__ segs, const uint32_t* __restrict__ nSegsPtr,
+                                                     SortTask* __restrict__ tasks, uint32_t* __restrict__ taskCounter, uint32_t taskCap) {
     const uint32_t w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (w >= nQ) return;
-    const uint64_t a = qHitOff[qFirst + w], b = qHitOff[qFirst + w + 1];
-    warpIntrosort(hits + (a - hitBase), (long)(b - a));
+    if (w >= *nSegsPtr) return;
+    const Seg sg = segs[w];
+    if (sg.n < 2) return;
+    TaskSinkDev sink{tasks, taskCounter, taskCap, sg.start};
+    const int depth = introsortDepth((long)sg.n);
+    if (sg.n <= (uint32_t)SORT_SMALL) { sink(0, (long)sg.n, depth); return; }
+    warpIntrosortRange(arr + sg.start, 0, (long)sg.n, depth, (long)SORT_SMALL, sink);
+}
+
+__global__ void __launch_bounds__(128) sortSmallKernel(Elem* __restrict__ arr, const SortTask* __restrict__ tasks,
+                                                       const uint32_t* __restrict__ taskCounter, uint32_t taskCap, uint32_t* __restrict__ next) {
+    extern __shared__ __align__(16) unsigned char smemRaw[];
+    Elem* sm = reinterpret_cast<Elem*>(smemRaw) + (threadIdx.x >> 5) * SORT_SMALL;
+    const int lane = threadIdx.x & 31;
+    const uint32_t nTasks = min(*taskCounter, taskCap);
+    for (;;) {
+        uint32_t t = 0;
+        if (lane == 0) t = atomicAdd(next, 1u);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if (t >= nTasks) return;
+        const SortTask k = tasks[t];
+        Elem* g = arr + k.start;
+        for (uint32_t i = lane; i < k.n; i += 32) sm[i] = g[i];
+        __syncwarp();
+        NoSink none;
+        warpIntrosortRange(sm, 0, (long)k.n, k.depth, 0, none);
+        __syncwarp();
+        for (uint32_t i = lane; i < k.n; i += 32) g[i] = sm[i];
+        __syncwarp();
+    }
+}
+
+__global__ void querySegsKernel(const uint64_t* __restrict__ qHitOff, uint32_t qFirst, uint32_t nQ, uint64_t hitBase, Seg* __restrict__ segs) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nQ) return;
+    Seg s; s.start = (uint32_t)(qHitOff[qFirst + i] - hitBase); s.n = (uint32_t)(qHitOff[qFirst + i + 1] - qHitOff[qFirst + i]);
+    segs[i] = s;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -250,56 +305,88 @@ __device__ __forceinline__ uint32_t filtRank(const uint32_t* __restrict__ filtBi
     return filtPrefix[w] + __popc(filtBits[w] & ((1u << (x & 31)) - 1u));
 }
 
-__global__ void __launch_bounds__(128) chainKernel(Elem* __restrict__ hits, const PairInfo* __restrict__ pairs, const uint32_t* __restrict__ pairIds,
-                                                   uint32_t nPairs, const uint32_t* __restrict__ qIds, const uint64_t* __restrict__ qSlotOff,
-                                                   const uint32_t* __restrict__ len, const uint32_t* __restrict__ filtBits,
-                                                   const uint32_t* __restrict__ filtPrefix, OvParams P,
-                                                   int32_t* __restrict__ curA, int32_t* __restrict__ extA, int32_t* __restrict__ score,
-                                                   int32_t* __restrict__ back, Elem* __restrict__ ord, Cand* __restrict__ cands,
-                                                   uint32_t* __restrict__ nCandOut, uint32_t* __restrict__ nKeptOut,
-                                                   unsigned long long* __restrict__ cellCount) {
+// pair flags
+static constexpr uint32_t PAIR_EXTSORTED = 1u;
+
+// (a) per pair: decide the DP axis (overlap.cpp:269), re-key the elements of ext-sorted pairs by extPos and
+// append them to the list of segments that need the std::sort-exact re-sort (:272-274)
+__global__ void __launch_bounds__(256) pairPrepKernel(Elem* __restrict__ hits, const PairInfo* __restrict__ pairs, const uint32_t* __restrict__ pairIds,
+                                                      uint32_t nPairs, const uint32_t* __restrict__ qIds, const uint32_t* __restrict__ len,
+                                                      uint32_t* __restrict__ pairFlags, Seg* __restrict__ extSegs, uint32_t* __restrict__ nExtSegs,
+                                                      Seg* __restrict__ allSegs) {
     const uint32_t w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (w >= nPairs) return;
     const int lane = threadIdx.x & 31;
     const PairInfo pi = pairs[pairIds[w]];
-    const uint32_t s0 = pi.start;
-    const int32_t n = (int32_t)pi.n;
-    const uint32_t curId = qIds[pi.qi], extId = pi.extId;
-    const int32_t curLen = (int32_t)len[curId >> 1], extLen = (int32_t)len[extId >> 1];
-    const int k = P.k;
-    Elem* h = hits + s0;
-    int32_t* cA = curA + s0; int32_t* eA = extA + s0; int32_t* sc = score + s0; int32_t* bk = back + s0;
-    Elem* od = ord + s0; Cand* cd = cands + s0;
-
-    // (a) optional re-sort by extPos (overlap.cpp:269-275), then split into position arrays
+    const int32_t curLen = (int32_t)len[qIds[pi.qi] >> 1], extLen = (int32_t)len[pi.extId >> 1];
     const bool extSorted = extLen > curLen;
+    if (lane == 0) {
+        pairFlags[w] = extSorted ? PAIR_EXTSORTED : 0u;
+        Seg sg; sg.start = pi.start; sg.n = pi.n;
+        allSegs[w] = sg;
+        if (extSorted) extSegs[atomicAdd(nExtSegs, 1u)] = sg;
+    }
     if (extSorted) {
-        for (int32_t i = lane; i < n; i += 32) {
-            Elem e = h[i];
+        Elem* h = hits + pi.start;
+        for (uint32_t i = lane; i < pi.n; i += 32) {
+            const Elem e = h[i];
             Elem t; t.key = (unsigned long long)e.val; t.val = (unsigned int)e.key; t.aux = 0;
             h[i] = t;
         }
-        __syncwarp();
-        warpIntrosort(h, n);
-        __syncwarp();
-        for (int32_t i = lane; i < n; i += 32) { Elem e = h[i]; cA[i] = (int32_t)e.val; eA[i] = (int32_t)(uint32_t)e.key; sc[i] = 0; bk[i] = -1; }
-    } else {
-        for (int32_t i = lane; i < n; i += 32) { Elem e = h[i]; cA[i] = (int32_t)(uint32_t)e.key; eA[i] = (int32_t)e.val; sc[i] = 0; bk[i] = -1; }
     }
-    __syncwarp();
+}
 
-    // (b) chaining DP (overlap.cpp:277-323).  Lanes evaluate 32 predecessors j = i-1, i-2, ... per step in
-    // the reference's traversal order; an inclusive prefix max over lanes reproduces "nextScore > maxScore"
-    // for every j, which is what the first break rule needs; the first lane that breaks ends the scan.
+__device__ __forceinline__ int32_t elemCur(const Elem& e, bool extSorted) { return extSorted ? (int32_t)e.val : (int32_t)(uint32_t)e.key; }
+__device__ __forceinline__ int32_t elemExt(const Elem& e, bool extSorted) { return extSorted ? (int32_t)(uint32_t)e.key : (int32_t)e.val; }
+
+// (b) chaining DP (overlap.cpp:277-323), one warp per pair.  Lanes evaluate 32 predecessors j = i-1, i-2, ... per step
+// in the reference's traversal order; an inclusive prefix max over lanes reproduces "nextScore > maxScore" for
+// every j, which is what the first break rule needs; the first lane that breaks ends the scan.  The last 32
+// matches (cur, ext, score) live in lane registers (match j in lane j%32) and reach the lanes by shuffle, so the
+// common case never waits for memory; longer look-backs continue from global memory.
+__global__ void __launch_bounds__(128) chainDpKernel(const Elem* __restrict__ hits, const PairInfo* __restrict__ pairs, const uint32_t* __restrict__ pairIds,
+                                                     uint32_t nPairs, const uint32_t* __restrict__ pairFlags, OvParams P,
+                                                     int32_t* __restrict__ score, int32_t* __restrict__ back, Elem* __restrict__ ord,
+                                                     unsigned long long* __restrict__ cellCount) {
+    const uint32_t w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (w >= nPairs) return;
+    const int lane = threadIdx.x & 31;
+    const PairInfo pi = pairs[pairIds[w]];
+    const bool extSorted = pairFlags[w] & PAIR_EXTSORTED;
+    const int32_t n = (int32_t)pi.n;
+    const int k = P.k;
+    const Elem* h = hits + pi.start;
+    int32_t* sc = score + pi.start; int32_t* bk = back + pi.start; Elem* od = ord + pi.start;
+
+    // block b = matches [32b, 32b+32): nx* holds the current block, pf* the next one (loaded a block ahead)
+    int32_t nxC = 0, nxE = 0, pfC = 0, pfE = 0;
+    if (lane < n) { const Elem e = h[lane]; nxC = elemCur(e, extSorted); nxE = elemExt(e, extSorted); }
+    if (32 + lane < n) { const Elem e = h[32 + lane]; pfC = elemCur(e, extSorted); pfE = elemExt(e, extSorted); }
+    int32_t wC = nxC, wE = nxE, wS = 0;   // window registers: lane 0 holds match 0 (score 0); others not yet valid
+    if (lane == 0) { sc[0] = 0; bk[0] = -1; Elem t; t.key = 0x7fffffffULL; t.val = 0; t.aux = 0; od[0] = t; }
     unsigned long long cells = 0;
     for (int32_t i = 1; i < n; ++i) {
-        const int32_t curN = cA[i], extN = eA[i];
+        const int l0 = i & 31;
+        if (l0 == 0) {
+            nxC = pfC; nxE = pfE;
+            const int32_t nb = i + 32 + lane;
+            if (nb < n) { const Elem e = h[nb]; pfC = elemCur(e, extSorted); pfE = elemExt(e, extSorted); }
+        }
+        const int32_t curN = __shfl_sync(0xffffffffu, nxC, l0), extN = __shfl_sync(0xffffffffu, nxE, l0);
         int32_t best = 0, bestId = 0;
-        for (int32_t jb = i - 1; jb >= 0; jb -= 32) {
+        bool stop = false;
+        for (int32_t jb = i - 1; jb >= 0 && !stop; jb -= 32) {
             const int32_t j = jb - lane;
             const bool in = j >= 0;
-            int32_t cj = 0, ej = 0, sj = 0;
-            if (in) { cj = cA[j]; ej = eA[j]; sj = sc[j]; }
+            int32_t cj, ej, sj;
+            if (jb == i - 1) {   // the 32 most recent matches: registers
+                const int src = j & 31;
+                cj = __shfl_sync(0xffffffffu, wC, src); ej = __shfl_sync(0xffffffffu, wE, src); sj = __shfl_sync(0xffffffffu, wS, src);
+            } else {
+                if (jb == i - 33) __syncwarp();   // order lane 0's score stores before these loads
+                cj = 0; ej = 0; sj = 0;
+                if (in) { const Elem e = h[j]; cj = elemCur(e, extSorted); ej = elemExt(e, extSorted); sj = sc[j]; }
+            }
             const int32_t dc = curN - cj, de = extN - ej;
             const bool ok = in && 0 < dc && dc < P.maxJump && 0 < de && de < P.maxJump;
             const int32_t jd = abs(dc - de);
@@ -322,70 +409,80 @@ __global__ void __launch_bounds__(128) chainKernel(Elem* __restrict__ hits, cons
                 best = mx; bestId = jb - (__ffs(wm) - 1);
             }
             cells += min(jb + 1, stopLane + 1);
-            if (bm) break;
+            stop = bm != 0;
         }
-        if (lane == 0) { sc[i] = max(best, k); if (best > k) bk[i] = bestId; }
-        __syncwarp();
+        const int32_t sci = max(best, k);
+        if (lane == l0) { wC = curN; wE = extN; wS = sci; }   // match i replaces match i-32 in the window
+        if (lane == 0) {
+            sc[i] = sci; bk[i] = best > k ? bestId : -1;
+            Elem t; t.key = (unsigned long long)(0x7fffffff - sci); t.val = (unsigned int)i; t.aux = 0; od[i] = t;   // (c) input of the score sort
+        }
     }
     if (lane == 0 && cells) atomicAdd(cellCount, cells);
+}
 
-    // (c) chain starts in std::sort order of scoreTable descending (overlap.cpp:331-334)
-    for (int32_t i = lane; i < n; i += 32) { Elem t; t.key = (unsigned long long)(0x7fffffff - sc[i]); t.val = (unsigned int)i; t.aux = 0; od[i] = t; }
-    __syncwarp();
-    warpIntrosort(od, n);
-    __syncwarp();
-
-    // (d) chain walk, overlapTest, filtered positions (overlap.cpp:338-427) — sequential by construction
+// (d)+(e) chain walk in std::sort order of the scores (overlap.cpp:331-427), overlapTest, filtered positions, then
+// primary selection (:431-458).  Pointer chasing with no parallelism inside a pair: one THREAD per pair.
+__global__ void __launch_bounds__(128) chainWalkKernel(const Elem* __restrict__ hits, const PairInfo* __restrict__ pairs, const uint32_t* __restrict__ pairIds,
+                                                       uint32_t nPairs, const uint32_t* __restrict__ pairFlags, const uint32_t* __restrict__ qIds,
+                                                       const uint64_t* __restrict__ qSlotOff, const uint32_t* __restrict__ len,
+                                                       const uint32_t* __restrict__ filtBits, const uint32_t* __restrict__ filtPrefix, OvParams P,
+                                                       const int32_t* __restrict__ score, int32_t* __restrict__ back, Elem* __restrict__ ord,
+                                                       Cand* __restrict__ cands, uint32_t* __restrict__ nCandOut, uint32_t* __restrict__ nKeptOut) {
+    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= nPairs) return;
+    const PairInfo pi = pairs[pairIds[w]];
+    const bool extSorted = pairFlags[w] & PAIR_EXTSORTED;
+    const int32_t n = (int32_t)pi.n;
+    const int k = P.k;
+    const uint32_t curId = qIds[pi.qi], extId = pi.extId;
+    const int32_t curLen = (int32_t)len[curId >> 1], extLen = (int32_t)len[extId >> 1];
+    const Elem* h = hits + pi.start;
+    const int32_t* sc = score + pi.start; int32_t* bk = back + pi.start;
+    Elem* od = ord + pi.start; Cand* cd = cands + pi.start;
+    const uint64_t qbase = qSlotOff[pi.qi];
+    const uint32_t qn = (uint32_t)(curLen - k);
     uint32_t nCand = 0;
-    if (lane == 0) {
-        const uint64_t qbase = qSlotOff[pi.qi];
-        const uint32_t qn = (uint32_t)(curLen - k);
-        for (int32_t t = 0; t < n; ++t) {
-            const int32_t chainStart = (int32_t)od[t].val;
-            if (bk[chainStart] == -1) continue;
-            int32_t firstMatch = 0, chainLength = 0, pos = chainStart;
-            while (pos != -1) { firstMatch = pos; ++chainLength; const int32_t np = bk[pos]; bk[pos] = -1; pos = np; }
-            const int32_t curBegin = cA[firstMatch], extBegin = eA[firstMatch];
-            const int32_t curEnd = cA[chainStart] + k - 1, extEnd = eA[chainStart] + k - 1;
-            if (!overlapTestDev(P, curId, extId, curBegin, curEnd, extBegin, extEnd, curLen, extLen)) continue;
-            const uint32_t hiPos = min((uint32_t)curEnd + 1u, qn), loPos = min((uint32_t)curBegin, qn);
-            Cand c;
-            c.curBegin = curBegin; c.curEnd = curEnd; c.extBegin = extBegin; c.extEnd = extEnd;
-            c.score = sc[chainStart] - sc[firstMatch] + k - 1;
-            c.chainLength = chainLength;
-            c.filtered = (int32_t)(filtRank(filtBits, filtPrefix, qbase, hiPos) - filtRank(filtBits, filtPrefix, qbase, loPos));
-            c.pad = 0;
-            cd[nCand++] = c;
-        }
+    for (int32_t t = 0; t < n; ++t) {
+        const int32_t chainStart = (int32_t)od[t].val;
+        if (bk[chainStart] == -1) continue;
+        int32_t firstMatch = 0, chainLength = 0, pos = chainStart;
+        while (pos != -1) { firstMatch = pos; ++chainLength; const int32_t np = bk[pos]; bk[pos] = -1; pos = np; }
+        const Elem eF = h[firstMatch], eL = h[chainStart];
+        const int32_t curBegin = elemCur(eF, extSorted), extBegin = elemExt(eF, extSorted);
+        const int32_t curEnd = elemCur(eL, extSorted) + k - 1, extEnd = elemExt(eL, extSorted) + k - 1;
+        if (!overlapTestDev(P, curId, extId, curBegin, curEnd, extBegin, extEnd, curLen, extLen)) continue;
+        const uint32_t hiPos = min((uint32_t)curEnd + 1u, qn), loPos = min((uint32_t)curBegin, qn);
+        Cand c;
+        c.curBegin = curBegin; c.curEnd = curEnd; c.extBegin = extBegin; c.extEnd = extEnd;
+        c.score = sc[chainStart] - sc[firstMatch] + k - 1;
+        c.chainLength = chainLength;
+        c.filtered = (int32_t)(filtRank(filtBits, filtPrefix, qbase, hiPos) - filtRank(filtBits, filtPrefix, qbase, loPos));
+        c.pad = 0;
+        cd[nCand++] = c;
     }
-    nCand = __shfl_sync(0xffffffffu, nCand, 0);
-    __syncwarp();
-
-    // (e) primary selection (overlap.cpp:431-458): std::sort by score descending, then best / containment filter
-    for (uint32_t i = lane; i < nCand; i += 32) { Elem t; t.key = (unsigned long long)(0x7fffffff - cd[i].score); t.val = i; t.aux = 0; od[i] = t; }
-    __syncwarp();
-    warpIntrosort(od, (long)nCand);
-    __syncwarp();
-    if (lane == 0) {
-        uint32_t kept = 0;
-        if (P.onlyMaxExt) { if (nCand) { od[0].aux = 1; kept = 1; } }
-        else {
-            for (uint32_t i = 0; i < nCand; ++i) {
-                const Cand c = cd[od[i].val];
-                bool contained = false;
-                for (uint32_t j = 0; j < i && !contained; ++j) {
-                    if (!od[j].aux) continue;
-                    const Cand p = cd[od[j].val];
-                    contained = p.curBegin <= c.curBegin && c.curEnd <= p.curEnd && p.extBegin <= c.extBegin && c.extEnd <= p.extEnd &&
-                                p.score > c.score;
-                }
-                od[i].aux = contained ? 0u : 1u;
-                kept += !contained;
+    // primary selection: std::sort by score descending (the ord slots of this pair are free now), then best /
+    // containment filter
+    for (uint32_t i = 0; i < nCand; ++i) { Elem t; t.key = (unsigned long long)(0x7fffffff - cd[i].score); t.val = i; t.aux = 0; od[i] = t; }
+    seqIntrosort(od, (long)nCand);
+    uint32_t kept = 0;
+    if (P.onlyMaxExt) { if (nCand) { od[0].aux = 1; kept = 1; } }
+    else {
+        for (uint32_t i = 0; i < nCand; ++i) {
+            const Cand c = cd[od[i].val];
+            bool contained = false;
+            for (uint32_t j = 0; j < i && !contained; ++j) {
+                if (!od[j].aux) continue;
+                const Cand p = cd[od[j].val];
+                contained = p.curBegin <= c.curBegin && c.curEnd <= p.curEnd && p.extBegin <= c.extBegin && c.extEnd <= p.extEnd &&
+                            p.score > c.score;
             }
+            od[i].aux = contained ? 0u : 1u;
+            kept += !contained;
         }
-        nCandOut[w] = nCand;
-        nKeptOut[w] = kept;
     }
+    nCandOut[w] = nCand;
+    nKeptOut[w] = kept;
 }
 
 // Q7: compact the kept candidates of every pair into the output, in the reference's order
@@ -413,26 +510,52 @@ __global__ void __launch_bounds__(256) gatherOverlapsKernel(const PairInfo* __re
     }
 }
 
-// test hook: sort caller-provided segments with the device introsort
-__global__ void __launch_bounds__(128) debugSortKernel(Elem* __restrict__ elems, const uint64_t* __restrict__ segOff, uint32_t nSegs) {
-    const uint32_t w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (w >= nSegs) return;
-    warpIntrosort(elems + segOff[w], (long)(segOff[w + 1] - segOff[w]));
+// two-level segmented sort driver; counters = {nSegs, taskCounter, next} on the device (nSegs already set,
+// the other two zero)
+static void sortSegments(fg_ctx* ctx, Elem* arr, const Seg* dSegs, uint32_t* dCounters, uint32_t maxSegs, DevBuf<SortTask>& tasks,
+                         uint32_t taskCap, const char* topName, const char* smallName) {
+    static bool attrSet = false;
+    const int smemBytes = 4 * SORT_SMALL * (int)sizeof(Elem);
+    if (!attrSet) {
+        FG_CUDA(cudaFuncSetAttribute(sortSmallKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smemBytes));
+        attrSet = true;
+    }
+    if (!maxSegs) return;
+    {
+        PhaseTimer pt(ctx, topName);
+        sortTopKernel<<<(maxSegs + 3) / 4, 128, 0, ctx->stream>>>(arr, dSegs, dCounters, tasks.p, dCounters + 1, taskCap);
+        checkLaunch(ctx, "sortTopKernel");
+    }
+    {
+        PhaseTimer pt(ctx, smallName);
+        sortSmallKernel<<<148 * 3, 128, smemBytes, ctx->stream>>>(arr, tasks.p, dCounters + 1, taskCap, dCounters + 2);
+        checkLaunch(ctx, "sortSmallKernel");
+    }
 }
 
+// test hook: sort caller-provided segments with the device introsort
 void debugWarpSort(fg_ctx* ctx, uint64_t* keys, uint32_t* vals, const uint64_t* segOffsets, uint32_t nSegs) {
     if (!nSegs) return;
     const uint64_t n = segOffsets[nSegs];
+    if (n >= (1ULL << 31)) throw Error(FG_ERR_ARG, "too many elements");
     std::vector<Elem> h(n);
     for (uint64_t i = 0; i < n; ++i) { h[i].key = keys[i]; h[i].val = vals[i]; h[i].aux = 0; }
+    std::vector<Seg> hs(nSegs);
+    for (uint32_t i = 0; i < nSegs; ++i) { hs[i].start = (uint32_t)segOffsets[i]; hs[i].n = (uint32_t)(segOffsets[i + 1] - segOffsets[i]); }
     DevBuf<Elem> d(std::max<uint64_t>(n, 1));
-    DevBuf<uint64_t> dOff(nSegs + 1);
+    DevBuf<Seg> dSegs(nSegs);
+    DevBuf<uint32_t> counters(4);
+    const uint32_t cap = (uint32_t)(n / 8 + nSegs + 1024);
+    DevBuf<SortTask> tasks(cap);
+    uint32_t hc[4] = {nSegs, 0, 0, 0};
     FG_CUDA(cudaMemcpyAsync(d.p, h.data(), n * sizeof(Elem), cudaMemcpyHostToDevice, ctx->stream));
-    FG_CUDA(cudaMemcpyAsync(dOff.p, segOffsets, (nSegs + 1) * 8ULL, cudaMemcpyHostToDevice, ctx->stream));
-    debugSortKernel<<<(nSegs + 3) / 4, 128, 0, ctx->stream>>>(d.p, dOff.p, nSegs);
-    checkLaunch(ctx, "debugSortKernel");
+    FG_CUDA(cudaMemcpyAsync(dSegs.p, hs.data(), nSegs * sizeof(Seg), cudaMemcpyHostToDevice, ctx->stream));
+    FG_CUDA(cudaMemcpyAsync(counters.p, hc, sizeof hc, cudaMemcpyHostToDevice, ctx->stream));
+    sortSegments(ctx, d.p, dSegs.p, counters.p, nSegs, tasks, cap, "dbg_sort_top", "dbg_sort_small");
     FG_CUDA(cudaMemcpyAsync(h.data(), d.p, n * sizeof(Elem), cudaMemcpyDeviceToHost, ctx->stream));
+    FG_CUDA(cudaMemcpyAsync(hc, counters.p, sizeof hc, cudaMemcpyDeviceToHost, ctx->stream));
     FG_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (hc[1] > cap) throw Error(FG_ERR_INTERNAL, "sort task list overflow");
     for (uint64_t i = 0; i < n; ++i) { keys[i] = h[i].key; vals[i] = h[i].val; }
 }
 
@@ -537,8 +660,10 @@ void overlapsBatch(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, const fg_
     uint64_t budget = 64ULL << 20;
     if (const char* e = getenv("FG_HIT_BUDGET")) budget = std::max<uint64_t>(1024, strtoull(e, nullptr, 10));
     std::vector<fg_overlap> hOut;
-    DevBuf<Elem> hits, ord; DevBuf<int32_t> curA, extA, score, back; DevBuf<Cand> cands; DevBuf<uint8_t> flags;
+    DevBuf<Elem> hits, ord; DevBuf<int32_t> score, back; DevBuf<Cand> cands; DevBuf<uint8_t> flags;
     DevBuf<uint32_t> gStart, candIds, pairIds;
+    DevBuf<SortTask> tasks; DevBuf<Seg> segsQ;
+    DevBuf<uint32_t> counters(16);
     PinnedBuf<fg_overlap>& pinned = ctx->pinnedOut;
     std::vector<std::vector<fg_overlap>> perQuery;   // not used; results are appended in query order
 
@@ -550,7 +675,12 @@ void overlapsBatch(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, const fg_
         const uint32_t nq = qb - qa;
         if (M >= (1ULL << 31)) throw Error(FG_ERR_ARG, "a single query produced >= 2^31 k-mer hits");
         if (M == 0) { qa = qb; continue; }
-        hits.ensure(M); ord.ensure(M); curA.ensure(M); extA.ensure(M); score.ensure(M); back.ensure(M); cands.ensure(M); flags.ensure(M);
+        hits.ensure(M); ord.ensure(M); score.ensure(M); back.ensure(M); cands.ensure(M); flags.ensure(M);
+        const uint32_t taskCap = (uint32_t)(M / 8 + nq + 4096);
+        tasks.ensure(taskCap); segsQ.ensure(nq);
+        uint32_t hCounters[16] = {0};
+        hCounters[0] = nq;
+        FG_CUDA(cudaMemcpyAsync(counters.p, hCounters, sizeof hCounters, cudaMemcpyHostToDevice, ctx->stream));
         const size_t tA = qTileFirst[qa], tB = qTileFirst[qb];
         {
             PhaseTimer pt(ctx, "gather");
@@ -558,11 +688,9 @@ void overlapsBatch(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, const fg_
                                                                       hitOff.p, slotInfo.p, hitBase, hits.p);
             checkLaunch(ctx, "expandKernel");
         }
-        {
-            PhaseTimer pt(ctx, "hit_sort");
-            sortHitsKernel<<<(nq + 3) / 4, 128, 0, ctx->stream>>>(hits.p, dQHitOff.p, qa, nq, hitBase);
-            checkLaunch(ctx, "sortHitsKernel");
-        }
+        querySegsKernel<<<(nq + 255) / 256, 256, 0, ctx->stream>>>(dQHitOff.p, qa, nq, hitBase, segsQ.p);
+        checkLaunch(ctx, "querySegsKernel");
+        sortSegments(ctx, hits.p, segsQ.p, counters.p, nq, tasks, taskCap, "hit_sort_top", "hit_sort_small");
         uint32_t G = 0, C = 0, Pn = 0;
         DevBuf<PairInfo> pairInfo;
         DevBuf<uint8_t> candFlag, passFlag;
@@ -591,12 +719,35 @@ void overlapsBatch(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, const fg_
             DevBuf<uint64_t> outOff(Pn + 1);
             DevBuf<unsigned long long> dCells(1);
             FG_CUDA(cudaMemsetAsync(dCells.p, 0, 8, ctx->stream));
+            DevBuf<uint32_t> pairFlags(Pn);
+            DevBuf<Seg> extSegs(Pn), allSegs(Pn);
             {
-                PhaseTimer pt(ctx, "chain");
-                chainKernel<<<(Pn + 3) / 4, 128, 0, ctx->stream>>>(hits.p, pairInfo.p, pairIds.p, Pn, dQIds.p, dQSlotOff.p, ctx->dLen.p,
-                                                                  filtBits.p, filtPrefix.p, P, curA.p, extA.p, score.p, back.p, ord.p,
-                                                                  cands.p, nCand.p, nKept.p, dCells.p);
-                checkLaunch(ctx, "chainKernel");
+                PhaseTimer pt(ctx, "chain_prep");
+                pairPrepKernel<<<(Pn + 7) / 8, 256, 0, ctx->stream>>>(hits.p, pairInfo.p, pairIds.p, Pn, dQIds.p, ctx->dLen.p, pairFlags.p,
+                                                                     extSegs.p, counters.p + 3, allSegs.p);
+                checkLaunch(ctx, "pairPrepKernel");
+            }
+            sortSegments(ctx, hits.p, extSegs.p, counters.p + 3, Pn, tasks, taskCap, "chain_extsort_top", "chain_extsort_small");
+            {
+                PhaseTimer pt(ctx, "chain_dp");
+                chainDpKernel<<<(Pn + 3) / 4, 128, 0, ctx->stream>>>(hits.p, pairInfo.p, pairIds.p, Pn, pairFlags.p, P, score.p, back.p, ord.p,
+                                                                    dCells.p);
+                checkLaunch(ctx, "chainDpKernel");
+            }
+            FG_CUDA(cudaMemcpyAsync(counters.p + 6, &Pn, 4, cudaMemcpyHostToDevice, ctx->stream));
+            sortSegments(ctx, ord.p, allSegs.p, counters.p + 6, Pn, tasks, taskCap, "chain_ordsort_top", "chain_ordsort_small");
+            {
+                PhaseTimer pt(ctx, "chain_walk");
+                chainWalkKernel<<<(Pn + 127) / 128, 128, 0, ctx->stream>>>(hits.p, pairInfo.p, pairIds.p, Pn, pairFlags.p, dQIds.p, dQSlotOff.p,
+                                                                          ctx->dLen.p, filtBits.p, filtPrefix.p, P, score.p, back.p, ord.p,
+                                                                          cands.p, nCand.p, nKept.p);
+                checkLaunch(ctx, "chainWalkKernel");
+            }
+            {
+                uint32_t hc[9];
+                FG_CUDA(cudaMemcpyAsync(hc, counters.p, sizeof hc, cudaMemcpyDeviceToHost, ctx->stream));
+                FG_CUDA(cudaStreamSynchronize(ctx->stream));
+                if (hc[1] > taskCap || hc[4] > taskCap || hc[7] > taskCap) throw Error(FG_ERR_INTERNAL, "sort task list overflow");
             }
             PhaseTimer pt(ctx, "d2h");
             cub::TransformInputIterator<uint64_t, CastU64, const uint32_t*> it64(nKept.p, CastU64());

@@ -8,10 +8,31 @@
 #include <algorithm>
 #include <random>
 
+struct VecSink {
+    struct T { long f, l; int d; };
+    std::vector<T> tasks;
+    void operator()(long f, long l, int d) { tasks.push_back({f, l, d}); }
+};
+static long g_small = 0;   // > 0: two-level mode (top pass hands ranges <= g_small to a second pass)
+
 static bool checkOne(std::vector<fg::Elem> a, const char* what) {
     std::vector<fg::Elem> ref = a;
     std::sort(ref.begin(), ref.end(), [](const fg::Elem& x, const fg::Elem& y) { return x.key < y.key; });
-    fg::warpIntrosort(a.data(), (long)a.size());
+    if (g_small > 0 && a.size() > 1) {
+        VecSink sink;
+        fg::warpIntrosortRange(a.data(), 0, (long)a.size(), fg::introsortDepth((long)a.size()), g_small, sink);
+        // second pass on a staged copy of each task, in reverse order to show that the order is irrelevant
+        for (size_t t = sink.tasks.size(); t-- > 0;) {
+            auto& T = sink.tasks[t];
+            std::vector<fg::Elem> tmp(a.begin() + T.f, a.begin() + T.l);
+            fg::NoSink none;
+            fg::warpIntrosortRange(tmp.data(), 0, (long)tmp.size(), T.d, 0, none);
+            std::copy(tmp.begin(), tmp.end(), a.begin() + T.f);
+        }
+    } else if (g_small < 0)
+        fg::seqIntrosort(a.data(), (long)a.size());
+    else
+        fg::warpIntrosort(a.data(), (long)a.size());
     for (size_t i = 0; i < a.size(); ++i)
         if (a[i].key != ref[i].key || a[i].val != ref[i].val) {
             printf("MISMATCH %s n=%zu at %zu: got (%llu,%u) want (%llu,%u)\n", what, a.size(), i, a[i].key, a[i].val,
@@ -33,6 +54,7 @@ static std::vector<unsigned long long> killer(size_t n) {
 int main(int argc, char** argv) {
     int trials = argc > 1 ? atoi(argv[1]) : 3000;
     unsigned seed = argc > 2 ? atoi(argv[2]) : 12345;
+    g_small = argc > 3 ? atol(argv[3]) : 0;
     std::mt19937_64 rng(seed);
     size_t arrays = 0, elements = 0;
     auto mk = [&](size_t n, int mode, unsigned long long distinct) {
