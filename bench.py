@@ -185,11 +185,18 @@ def main():
     # this rank's queries (forward reads); index built from all reads on every rank (replicated)
     lo, hi = (n_reads * rank) // world, (n_reads * (rank + 1)) // world
     queries = np.arange(2 * lo, 2 * hi, 2, dtype=np.uint32)
-    phase_ms, phase_calls, ovl_stats, n_ovl = {}, {}, {}, 0
+    phase_ms, phase_calls, ovl_stats, n_ovl, wall = {}, {}, {}, 0, {}
+    n_raw = [0]
 
     def step(upload):
-        nonlocal phase_ms, phase_calls, ovl_stats, n_ovl
-        phase_ms, phase_calls = {}, {}
+        nonlocal phase_ms, phase_calls, ovl_stats, n_ovl, wall
+        phase_ms, phase_calls, wall = {}, {}, {}
+        t_prev = [time.perf_counter()]
+
+        def lap(name):
+            now = time.perf_counter()
+            wall[name] = wall.get(name, 0.0) + (now - t_prev[0]) * 1e3
+            t_prev[0] = now
 
         def grab():
             t = eng.timings()
@@ -198,26 +205,38 @@ def main():
                 phase_calls[name] = phase_calls.get(name, 0) + eng.last_calls[name]
         if upload:
             eng.upload_packed(packed_pin, woff, lens)
+            lap("upload")
         if int(cfg["use_minimizers"]):
             eng.build_index_minimizers(k, 1, int(cfg["minimizer_window"]), cfg["repeat_kmer_rate"])
         else:
             eng.count_kmers(k)
             grab()
+            lap("count")
             eng.build_index_solid(2, cfg["meta_read_top_kmer_rate"], int(cfg["meta_read_filter_kmer_freq"]), cfg["repeat_kmer_rate"],
                                   float(int(cfg["assemble_kmer_sample"])))
         grab()
-        offs, ov, _ = eng.overlaps(est_ids, max_divergence=1.0, **common)
+        lap("index")
+        # estimateOverlaperParameters' 1000 random queries and the all-reads pass share ONE device batch: the device
+        # work does not depend on the divergence threshold (it only gates the final host-side filter, overlap.cpp:470),
+        # so the threshold is computed from the first 1000 result vectors and applied to the rest on the host.
+        all_q = np.concatenate([np.asarray(est_ids, dtype=np.uint32), queries])
+        offs, ov, ovl_stats = eng.overlaps(all_q, max_divergence=1.0, copy=False, **common)
+        rng_all = ov["cur_end"] - ov["cur_begin"]
+        div_all = ov["seq_divergence"]
         divs = []
         for i in range(len(est_ids)):
             a, b = int(offs[i]), int(offs[i + 1])
             if b > a:
-                rng = ov["cur_end"][a:b] - ov["cur_begin"][a:b]
-                divs.append(ov["seq_divergence"][a + int(np.argmax(rng))])
+                divs.append(div_all[a + int(np.argmax(rng_all[a:b]))])
         mean = pu.median_f32(divs) if divs else np.float32(0.5)
         max_div = np.float32((mean if bool(cfg["assemble_divergence_relative"]) else np.float32(0.0)) + np.float32(cfg["assemble_ovlp_divergence"]))
-        offs, ov, ovl_stats = eng.overlaps(queries, max_divergence=float(max_div), **common)
+        first = int(offs[len(est_ids)])
+        keep = div_all[first:] < max_div
+        lap("overlaps")
         grab()
-        n_ovl = int(offs[-1])
+        n_ovl = int(np.count_nonzero(keep))
+        n_raw[0] = int(offs[-1])
+        lap("filter")
         return n_ovl
 
     def barrier():
@@ -248,15 +267,16 @@ def main():
     launches0 = eng.launches()
     ms_resident = timed(False, args.steps)
     launches = (eng.launches() - launches0) // max(1, args.steps)
-    resident_phases, resident_calls, stats = dict(phase_ms), dict(phase_calls), dict(ovl_stats)
+    resident_phases, resident_calls, stats, resident_wall = dict(phase_ms), dict(phase_calls), dict(ovl_stats), dict(wall)
     ms_e2e = timed(True, args.steps)
+    e2e_wall = dict(wall)
     clocks = sampler.stop()
 
     total_reads = n_reads   # all ranks together process every forward read exactly once
     value = total_reads / (ms_resident / 1e3)
     e2e_value = total_reads / (ms_e2e / 1e3)
     h2d = int(packed.nbytes + woff.nbytes + lens.nbytes + 4 * (len(queries) + len(est_ids)))
-    d2h = int(72 * n_ovl + 8 * (len(queries) + 1))
+    d2h = int(72 * n_raw[0] + 8 * (len(queries) + len(est_ids) + 1))
 
     # roofline of the dominant kernel phase (algorithmic bytes: SURVEY.md §8d, stated in DESIGN.md)
     M, O = stats.get("n_hits", 0), n_ovl
@@ -286,6 +306,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "reads/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches), "roofline": roofline,
             "phases_ms": {p: round(v, 3) for p, v in resident_phases.items()},
+            "api_wall_ms": {p: round(v, 2) for p, v in resident_wall.items()}, "e2e_api_wall_ms": {p: round(v, 2) for p, v in e2e_wall.items()},
             "work": {"kmer_hits": int(M), "target_groups": int(stats.get("n_pairs", 0)), "dp_pairs": int(stats.get("n_dp_pairs", 0)),
                      "dp_cells": int(stats.get("n_dp_cells", 0)), "overlaps": int(O)}}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

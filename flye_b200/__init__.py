@@ -243,17 +243,22 @@ class Engine:
 
     # ---- overlaps ----
     def overlaps(self, query_ids, max_jump=1500, min_overlap=1000, max_overhang=1500, max_overlaps=0, force_local=False,
-                 keep_alignment=False, only_max_ext=True, nucl_alignment=False, use_hpc=False, max_divergence=1.0):
+                 keep_alignment=False, only_max_ext=True, nucl_alignment=False, use_hpc=False, max_divergence=1.0, copy=True):
+        """copy=False returns views into library-owned memory, valid until the next overlaps() call"""
         q = np.ascontiguousarray(query_ids, dtype=np.uint32)
         p = OverlapParams(max_jump, min_overlap, max_overhang, max_overlaps, int(force_local), int(keep_alignment),
                           int(only_max_ext), int(nucl_alignment), int(use_hpc), max_divergence)
         res = OverlapResult()
         self._check(self.lib.fg_overlaps_batch(self.ctx, _ptr(q, C.c_uint32), len(q), C.byref(p), C.byref(res)))
-        offsets = np.ctypeslib.as_array(res.offsets, shape=(len(q) + 1,)).copy()
+        offsets = np.ctypeslib.as_array(res.offsets, shape=(len(q) + 1,))
+        if copy:
+            offsets = offsets.copy()
         n = int(offsets[-1])
         if n:
             buf = (C.c_char * (n * OVERLAP_DTYPE.itemsize)).from_address(res.overlaps)
-            ov = np.frombuffer(buf, dtype=OVERLAP_DTYPE, count=n).copy()
+            ov = np.frombuffer(buf, dtype=OVERLAP_DTYPE, count=n)
+            if copy:
+                ov = ov.copy()
         else:
             ov = np.zeros(0, dtype=OVERLAP_DTYPE)
         stats = dict(n_hits=res.n_hits, n_pairs=res.n_pairs, n_dp_pairs=res.n_dp_pairs, n_dp_cells=res.n_dp_cells)

@@ -15,7 +15,7 @@ int guarded(fg_ctx* ctx, F&& body) {
     std::lock_guard<std::mutex> lock(ctx->mtx);
     try {
         FG_CUDA(cudaSetDevice(ctx->device));
-        fg::allocStream() = ctx->stream;
+        fg::currentArena() = &ctx->arena;
         body();
         return FG_OK;
     } catch (const Error& e) {
@@ -93,11 +93,7 @@ int fg_ctx_create(int device, fg_ctx** out) {
     fg_ctx* ctx = new fg_ctx();
     ctx->device = device;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return FG_ERR_CUDA; }
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-        unsigned long long never = ~0ULL;
-        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &never);
-    }
+
     *out = ctx;
     return FG_OK;
 }
@@ -107,8 +103,10 @@ void fg_ctx_destroy(fg_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     cudaStream_t s = ctx->stream;
+    cudaDeviceSynchronize();
+    fg::currentArena() = &ctx->arena;
     delete ctx;
-    cudaStreamSynchronize(s);
+    fg::currentArena() = nullptr;
     cudaStreamDestroy(s);
 }
 

@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
+#include <algorithm>
+#include <chrono>
 #include <cstring>
 #include <mutex>
 #include <stdexcept>
@@ -30,17 +32,54 @@ struct Error : std::runtime_error {
     } while (0)
 
 // ---------------------------------------------------------------------------------------------
-// device buffers: stream-ordered allocations from the device's default memory pool, whose release
-// threshold fg_ctx_create raises to "never" — after the first step every buffer is a pool hit, so the
-// phases can allocate/free their temporaries freely without paying cudaMalloc/cudaFree.
+// device buffers: every context owns a caching arena.  A released block goes back to the arena's free list and
+// is handed out again to the next request it fits (best fit, at most 2x oversize); cudaMalloc / cudaFree are
+// only paid while the working set is still growing (first step) and at context destruction.  All work of a
+// context is ordered on its single stream, so a block may be reused as soon as the host has released it.
 // ---------------------------------------------------------------------------------------------
-inline cudaStream_t& allocStream() { static thread_local cudaStream_t s = nullptr; return s; }
+struct Arena {
+    struct Block { void* p; size_t bytes; bool used; };
+    std::vector<Block> blocks;
+    size_t totalBytes = 0;
+    void* alloc(size_t bytes) {
+        if (!bytes) return nullptr;
+        int best = -1;
+        for (int i = 0; i < (int)blocks.size(); ++i)
+            if (!blocks[i].used && blocks[i].bytes >= bytes && blocks[i].bytes <= 2 * bytes + (1u << 20) &&
+                (best < 0 || blocks[i].bytes < blocks[best].bytes)) best = i;
+        if (best >= 0) { blocks[best].used = true; return blocks[best].p; }
+        size_t want = (bytes + bytes / 8 + (1u << 21) - 1) & ~((size_t)(1u << 21) - 1);
+        void* p = nullptr;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {   // give cached blocks back and retry once
+            cudaGetLastError();
+            trim();
+            e = cudaMalloc(&p, want);
+            if (e != cudaSuccess)
+                throw Error(FG_ERR_CUDA, std::string("cudaMalloc of ") + std::to_string(want) + " bytes failed: " + cudaGetErrorString(e));
+        }
+        blocks.push_back({p, want, true});
+        totalBytes += want;
+        return p;
+    }
+    void release(void* p) {
+        for (auto& b : blocks) if (b.p == p) { b.used = false; return; }
+    }
+    void trim() {   // free every unused block (synchronises the device)
+        cudaDeviceSynchronize();
+        std::vector<Block> keep;
+        for (auto& b : blocks) { if (b.used) keep.push_back(b); else { cudaFree(b.p); totalBytes -= b.bytes; } }
+        blocks.swap(keep);
+    }
+    ~Arena() { for (auto& b : blocks) cudaFree(b.p); }
+};
+inline Arena*& currentArena() { static thread_local Arena* a = nullptr; return a; }
 
 template <class T>
 struct DevBuf {
     T* p = nullptr;
     size_t n = 0;
-    cudaStream_t owner = nullptr;
+    Arena* owner = nullptr;
     DevBuf() = default;
     explicit DevBuf(size_t count) { alloc(count); }
     DevBuf(const DevBuf&) = delete;
@@ -54,11 +93,12 @@ struct DevBuf {
     void alloc(size_t count) {
         release();
         n = count;
-        owner = allocStream();
-        if (count) FG_CUDA(cudaMallocAsync((void**)&p, count * sizeof(T), owner));
+        owner = currentArena();
+        if (!owner) throw Error(FG_ERR_INTERNAL, "device allocation outside a context call");
+        if (count) p = (T*)owner->alloc(count * sizeof(T));
     }
     void ensure(size_t count) { if (count > n) alloc(count + count / 8); }
-    void release() { if (p) cudaFreeAsync(p, owner); p = nullptr; n = 0; }
+    void release() { if (p && owner) owner->release(p); p = nullptr; n = 0; }
     size_t bytes() const { return n * sizeof(T); }
 };
 
@@ -75,6 +115,14 @@ struct PinnedBuf {
         release();
         n = count + count / 4 + 16;
         FG_CUDA(cudaMallocHost((void**)&p, n * sizeof(T)));
+    }
+    // grow, keeping the first `used` elements
+    void ensureKeep(size_t count, size_t used) {
+        if (count <= n) return;
+        T* old = p; size_t oldN = n;
+        p = nullptr; n = count + count / 2 + 16;
+        FG_CUDA(cudaMallocHost((void**)&p, n * sizeof(T)));
+        if (old) { if (used) memcpy(p, old, std::min(used, oldN) * sizeof(T)); cudaFreeHost(old); }
     }
     void release() { if (p) cudaFreeHost(p); p = nullptr; n = 0; }
 };

@@ -6,6 +6,7 @@
 #include <utility>
 
 struct fg_ctx {
+    fg::Arena arena;                      // first member: destroyed last, after every DevBuf below
     int device = 0;
     cudaStream_t stream = nullptr;
     mutable std::mutex mtx;
@@ -94,6 +95,18 @@ struct PhaseTimer {
             if (ctx->timings[i].first == name) { ctx->timings[i].second += ms; ++ctx->timingCalls[i]; found = true; }
         if (!found) { ctx->timings.emplace_back(name, ms); ctx->timingCalls.push_back(1); }
         cudaEventDestroy(a); cudaEventDestroy(b);
+    }
+};
+
+// host wall-clock of a host-side section, reported next to the device phases as "host_<name>"
+struct HostTimer {
+    fg_ctx* ctx; const char* name; std::chrono::steady_clock::time_point t0;
+    HostTimer(fg_ctx* c, const char* n) : ctx(c), name(n), t0(std::chrono::steady_clock::now()) {}
+    ~HostTimer() {
+        float ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        for (size_t i = 0; i < ctx->timings.size(); ++i)
+            if (ctx->timings[i].first == name) { ctx->timings[i].second += ms; ++ctx->timingCalls[i]; return; }
+        ctx->timings.emplace_back(name, ms); ctx->timingCalls.push_back(1);
     }
 };
 

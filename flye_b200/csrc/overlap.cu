@@ -146,8 +146,10 @@ __global__ void __launch_bounds__(256) expandKernel(const uint32_t* __restrict__
 
 // ------------------------------------------------------------------------------------------------
 // Q4: segmented std::sort-exact sorting, two levels.
-//   sortTopKernel    one warp per segment, in global memory with software prefetch: partitions until every
-//                    range is <= SORT_SMALL elements and appends those ranges to a task list
+//   sortSeedKernel / sortLevelKernel   level-synchronous introsort recursion in global memory: per level one warp
+//                    partitions one range (software-prefetched streaming Hoare partition) and emits the two halves as
+//                    tasks; ranges of <= SORT_SMALL elements go to the task list of the second kernel.  All ranges of
+//                    all segments of a level run concurrently, so a long read does not serialise behind one warp.
 //   sortSmallKernel  persistent warps pull tasks, stage the range in shared memory (16 KB per warp), finish the
 //                    introsort there and write it back — most recursion levels run at shared-memory latency and
 //                    the tasks balance the load across the chip whatever the segment-length distribution is.
@@ -156,26 +158,43 @@ static constexpr int SORT_SMALL = 1024;
 struct Seg { uint32_t start, n; };
 struct SortTask { uint32_t start, n; int depth; };
 
-struct TaskSinkDev {
-    SortTask* tasks; uint32_t* counter; uint32_t cap; uint32_t base;
-    __device__ __forceinline__ void operator()(long f, long l, int d) const {
-        if (laneId() == 0) {
-            const uint32_t t = atomicAdd(counter, 1u);
-            if (t < cap) { SortTask k; k.start = base + (uint32_t)f; k.n = (uint32_t)(l - f); k.depth = d; tasks[t] = k; }
-        }
-    }
-};
+// counters of one segmented sort: [0] nSegs (input)  [1] nSmall  [2] next small task  [3] nBig ping  [4] nBig pong
+__device__ __forceinline__ void emitRange(uint32_t start, uint32_t n, int depth, SortTask* big, uint32_t* nBig, uint32_t capBig,
+                                          SortTask* small, uint32_t* nSmall, uint32_t capSmall) {
+    if (n < 2) return;
+    SortTask k; k.start = start; k.n = n; k.depth = depth;
+    if (n > (uint32_t)SORT_SMALL) { const uint32_t t = atomicAdd(nBig, 1u); if (t < capBig) big[t] = k; }
+    else { const uint32_t t = atomicAdd(nSmall, 1u); if (t < capSmall) small[t] = k; }
+}
 
-__global__ void __launch_bounds__(128) sortTopKernel(Elem* __restrict__ arr, const Seg* __restrict__ segs, const uint32_t* __restrict__ nSegsPtr,
-                                                     SortTask* __restrict__ tasks, uint32_t* __restrict__ taskCounter, uint32_t taskCap) {
+// every segment becomes one task: a "big" one (partitioned level by level in global memory) or a "small" one
+__global__ void __launch_bounds__(256) sortSeedKernel(const Seg* __restrict__ segs, const uint32_t* __restrict__ nSegsPtr, SortTask* __restrict__ big,
+                                                      uint32_t* __restrict__ nBig, uint32_t capBig, SortTask* __restrict__ small,
+                                                      uint32_t* __restrict__ nSmall, uint32_t capSmall) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= *nSegsPtr) return;
+    const Seg sg = segs[i];
+    emitRange(sg.start, sg.n, introsortDepth((long)sg.n), big, nBig, capBig, small, nSmall, capSmall);
+}
+
+// one introsort level: every warp partitions one big range (or heap-sorts it when its depth budget is spent,
+// stl_algo.h:1925-1929) and emits the two halves as tasks of the next level / of the shared-memory kernel
+__global__ void __launch_bounds__(128) sortLevelKernel(Elem* __restrict__ arr, const SortTask* __restrict__ in, const uint32_t* __restrict__ nInPtr,
+                                                       uint32_t capBig, SortTask* __restrict__ out, uint32_t* __restrict__ nOut,
+                                                       SortTask* __restrict__ small, uint32_t* __restrict__ nSmall, uint32_t capSmall) {
     const uint32_t w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (w >= *nSegsPtr) return;
-    const Seg sg = segs[w];
-    if (sg.n < 2) return;
-    TaskSinkDev sink{tasks, taskCounter, taskCap, sg.start};
-    const int depth = introsortDepth((long)sg.n);
-    if (sg.n <= (uint32_t)SORT_SMALL) { sink(0, (long)sg.n, depth); return; }
-    warpIntrosortRange(arr + sg.start, 0, (long)sg.n, depth, (long)SORT_SMALL, sink);
+    if (w >= min(*nInPtr, capBig)) return;
+    const SortTask t = in[w];
+    Elem* a = arr + t.start;
+    if (t.depth == 0) {
+        if (laneId() == 0) seqHeapSort(a, (long)t.n);
+        return;
+    }
+    const long cut = warpPartition(a, 0, (long)t.n);
+    if (laneId() == 0) {
+        emitRange(t.start, (uint32_t)cut, t.depth - 1, out, nOut, capBig, small, nSmall, capSmall);
+        emitRange(t.start + (uint32_t)cut, t.n - (uint32_t)cut, t.depth - 1, out, nOut, capBig, small, nSmall, capSmall);
+    }
 }
 
 __global__ void __launch_bounds__(128) sortSmallKernel(Elem* __restrict__ arr, const SortTask* __restrict__ tasks,
@@ -422,15 +441,21 @@ __global__ void __launch_bounds__(128) chainDpKernel(const Elem* __restrict__ hi
 }
 
 // (d)+(e) chain walk in std::sort order of the scores (overlap.cpp:331-427), overlapTest, filtered positions, then
-// primary selection (:431-458).  Pointer chasing with no parallelism inside a pair: one THREAD per pair.
+// primary selection (:431-458).  One warp per pair: the back-pointer table is staged in shared memory (the walk is
+// pure pointer chasing, so its latency is what matters), the lanes test 32 chain starts at a time and lane 0
+// walks the chains in order, re-testing the remaining starts after every walk because a walk consumes pointers.
+static constexpr int WALK_CAP = 4096;   // back pointers per warp in shared memory (16 KB); larger pairs stay in global
+
 __global__ void __launch_bounds__(128) chainWalkKernel(const Elem* __restrict__ hits, const PairInfo* __restrict__ pairs, const uint32_t* __restrict__ pairIds,
                                                        uint32_t nPairs, const uint32_t* __restrict__ pairFlags, const uint32_t* __restrict__ qIds,
                                                        const uint64_t* __restrict__ qSlotOff, const uint32_t* __restrict__ len,
                                                        const uint32_t* __restrict__ filtBits, const uint32_t* __restrict__ filtPrefix, OvParams P,
                                                        const int32_t* __restrict__ score, int32_t* __restrict__ back, Elem* __restrict__ ord,
                                                        Cand* __restrict__ cands, uint32_t* __restrict__ nCandOut, uint32_t* __restrict__ nKeptOut) {
-    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    extern __shared__ __align__(16) unsigned char smemRaw[];
+    const uint32_t w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (w >= nPairs) return;
+    const int lane = threadIdx.x & 31;
     const PairInfo pi = pairs[pairIds[w]];
     const bool extSorted = pairFlags[w] & PAIR_EXTSORTED;
     const int32_t n = (int32_t)pi.n;
@@ -438,29 +463,50 @@ __global__ void __launch_bounds__(128) chainWalkKernel(const Elem* __restrict__ 
     const uint32_t curId = qIds[pi.qi], extId = pi.extId;
     const int32_t curLen = (int32_t)len[curId >> 1], extLen = (int32_t)len[extId >> 1];
     const Elem* h = hits + pi.start;
-    const int32_t* sc = score + pi.start; int32_t* bk = back + pi.start;
+    const int32_t* sc = score + pi.start;
     Elem* od = ord + pi.start; Cand* cd = cands + pi.start;
     const uint64_t qbase = qSlotOff[pi.qi];
     const uint32_t qn = (uint32_t)(curLen - k);
-    uint32_t nCand = 0;
-    for (int32_t t = 0; t < n; ++t) {
-        const int32_t chainStart = (int32_t)od[t].val;
-        if (bk[chainStart] == -1) continue;
-        int32_t firstMatch = 0, chainLength = 0, pos = chainStart;
-        while (pos != -1) { firstMatch = pos; ++chainLength; const int32_t np = bk[pos]; bk[pos] = -1; pos = np; }
-        const Elem eF = h[firstMatch], eL = h[chainStart];
-        const int32_t curBegin = elemCur(eF, extSorted), extBegin = elemExt(eF, extSorted);
-        const int32_t curEnd = elemCur(eL, extSorted) + k - 1, extEnd = elemExt(eL, extSorted) + k - 1;
-        if (!overlapTestDev(P, curId, extId, curBegin, curEnd, extBegin, extEnd, curLen, extLen)) continue;
-        const uint32_t hiPos = min((uint32_t)curEnd + 1u, qn), loPos = min((uint32_t)curBegin, qn);
-        Cand c;
-        c.curBegin = curBegin; c.curEnd = curEnd; c.extBegin = extBegin; c.extEnd = extEnd;
-        c.score = sc[chainStart] - sc[firstMatch] + k - 1;
-        c.chainLength = chainLength;
-        c.filtered = (int32_t)(filtRank(filtBits, filtPrefix, qbase, hiPos) - filtRank(filtBits, filtPrefix, qbase, loPos));
-        c.pad = 0;
-        cd[nCand++] = c;
+
+    int32_t* bk = back + pi.start;
+    if (n <= WALK_CAP) {
+        int32_t* sb = reinterpret_cast<int32_t*>(smemRaw) + (threadIdx.x >> 5) * WALK_CAP;
+        for (int32_t i = lane; i < n; i += 32) sb[i] = bk[i];
+        bk = sb;
     }
+    __syncwarp();
+
+    uint32_t nCand = 0;   // meaningful in lane 0
+    for (int32_t t0 = 0; t0 < n; t0 += 32) {
+        const int32_t t = t0 + lane;
+        const int32_t cs = t < n ? (int32_t)od[t].val : 0;
+        uint32_t m = __ballot_sync(0xffffffffu, t < n && bk[cs] != -1);
+        while (m) {
+            const int src = __ffs(m) - 1;
+            const int32_t chainStart = __shfl_sync(0xffffffffu, cs, src);
+            if (lane == 0) {
+                int32_t firstMatch = 0, chainLength = 0, pos = chainStart;
+                while (pos != -1) { firstMatch = pos; ++chainLength; const int32_t np = bk[pos]; bk[pos] = -1; pos = np; }
+                const Elem eF = h[firstMatch], eL = h[chainStart];
+                const int32_t curBegin = elemCur(eF, extSorted), extBegin = elemExt(eF, extSorted);
+                const int32_t curEnd = elemCur(eL, extSorted) + k - 1, extEnd = elemExt(eL, extSorted) + k - 1;
+                if (overlapTestDev(P, curId, extId, curBegin, curEnd, extBegin, extEnd, curLen, extLen)) {
+                    const uint32_t hiPos = min((uint32_t)curEnd + 1u, qn), loPos = min((uint32_t)curBegin, qn);
+                    Cand c;
+                    c.curBegin = curBegin; c.curEnd = curEnd; c.extBegin = extBegin; c.extEnd = extEnd;
+                    c.score = sc[chainStart] - sc[firstMatch] + k - 1;
+                    c.chainLength = chainLength;
+                    c.filtered = (int32_t)(filtRank(filtBits, filtPrefix, qbase, hiPos) - filtRank(filtBits, filtPrefix, qbase, loPos));
+                    c.pad = 0;
+                    cd[nCand++] = c;
+                }
+            }
+            __syncwarp();
+            m = __ballot_sync(0xffffffffu, lane > src && t < n && bk[cs] != -1);
+        }
+    }
+    __syncwarp();   // all lanes are done reading ord[] before lane 0 reuses its slots
+    if (lane != 0) return;
     // primary selection: std::sort by score descending (the ord slots of this pair are free now), then best /
     // containment filter
     for (uint32_t i = 0; i < nCand; ++i) { Elem t; t.key = (unsigned long long)(0x7fffffff - cd[i].score); t.val = i; t.aux = 0; od[i] = t; }
@@ -510,10 +556,19 @@ __global__ void __launch_bounds__(256) gatherOverlapsKernel(const PairInfo* __re
     }
 }
 
-// two-level segmented sort driver; counters = {nSegs, taskCounter, next} on the device (nSegs already set,
-// the other two zero)
-static void sortSegments(fg_ctx* ctx, Elem* arr, const Seg* dSegs, uint32_t* dCounters, uint32_t maxSegs, DevBuf<SortTask>& tasks,
-                         uint32_t taskCap, const char* topName, const char* smallName) {
+// segmented sort driver.  dCounters: 5 device words (layout above) with [0] = nSegs already set and the rest zero.
+struct SortWorkspace {
+    DevBuf<SortTask> small, bigA, bigB;
+    uint32_t capSmall = 0, capBig = 0;
+    void ensure(uint64_t totalElems, uint32_t maxSegs) {
+        capSmall = (uint32_t)(totalElems / 8 + maxSegs + 4096);
+        capBig = (uint32_t)(totalElems / SORT_SMALL + maxSegs + 64);
+        small.ensure(capSmall); bigA.ensure(capBig); bigB.ensure(capBig);
+    }
+};
+
+static void sortSegments(fg_ctx* ctx, Elem* arr, const Seg* dSegs, uint32_t* dCounters, uint32_t maxSegs, SortWorkspace& ws,
+                         const char* topName, const char* smallName) {
     static bool attrSet = false;
     const int smemBytes = 4 * SORT_SMALL * (int)sizeof(Elem);
     if (!attrSet) {
@@ -523,12 +578,26 @@ static void sortSegments(fg_ctx* ctx, Elem* arr, const Seg* dSegs, uint32_t* dCo
     if (!maxSegs) return;
     {
         PhaseTimer pt(ctx, topName);
-        sortTopKernel<<<(maxSegs + 3) / 4, 128, 0, ctx->stream>>>(arr, dSegs, dCounters, tasks.p, dCounters + 1, taskCap);
-        checkLaunch(ctx, "sortTopKernel");
+        sortSeedKernel<<<(maxSegs + 255) / 256, 256, 0, ctx->stream>>>(dSegs, dCounters, ws.bigA.p, dCounters + 3, ws.capBig, ws.small.p,
+                                                                      dCounters + 1, ws.capSmall);
+        checkLaunch(ctx, "sortSeedKernel");
+        SortTask* in = ws.bigA.p; SortTask* out = ws.bigB.p;
+        uint32_t* nIn = dCounters + 3; uint32_t* nOut = dCounters + 4;
+        for (int level = 0; level < 200; ++level) {
+            uint32_t hIn = 0;
+            FG_CUDA(cudaMemcpyAsync(&hIn, nIn, 4, cudaMemcpyDeviceToHost, ctx->stream));
+            FG_CUDA(cudaStreamSynchronize(ctx->stream));
+            if (hIn > ws.capBig) throw Error(FG_ERR_INTERNAL, "sort task list overflow");
+            if (!hIn) break;
+            FG_CUDA(cudaMemsetAsync(nOut, 0, 4, ctx->stream));
+            sortLevelKernel<<<(hIn + 3) / 4, 128, 0, ctx->stream>>>(arr, in, nIn, ws.capBig, out, nOut, ws.small.p, dCounters + 1, ws.capSmall);
+            checkLaunch(ctx, "sortLevelKernel");
+            std::swap(in, out); std::swap(nIn, nOut);
+        }
     }
     {
         PhaseTimer pt(ctx, smallName);
-        sortSmallKernel<<<148 * 3, 128, smemBytes, ctx->stream>>>(arr, tasks.p, dCounters + 1, taskCap, dCounters + 2);
+        sortSmallKernel<<<148 * 3, 128, smemBytes, ctx->stream>>>(arr, ws.small.p, dCounters + 1, ws.capSmall, dCounters + 2);
         checkLaunch(ctx, "sortSmallKernel");
     }
 }
@@ -544,14 +613,14 @@ void debugWarpSort(fg_ctx* ctx, uint64_t* keys, uint32_t* vals, const uint64_t* 
     for (uint32_t i = 0; i < nSegs; ++i) { hs[i].start = (uint32_t)segOffsets[i]; hs[i].n = (uint32_t)(segOffsets[i + 1] - segOffsets[i]); }
     DevBuf<Elem> d(std::max<uint64_t>(n, 1));
     DevBuf<Seg> dSegs(nSegs);
-    DevBuf<uint32_t> counters(4);
-    const uint32_t cap = (uint32_t)(n / 8 + nSegs + 1024);
-    DevBuf<SortTask> tasks(cap);
-    uint32_t hc[4] = {nSegs, 0, 0, 0};
+    DevBuf<uint32_t> counters(8);
+    SortWorkspace ws; ws.ensure(n, nSegs);
+    const uint32_t cap = ws.capSmall;
+    uint32_t hc[8] = {nSegs, 0, 0, 0, 0, 0, 0, 0};
     FG_CUDA(cudaMemcpyAsync(d.p, h.data(), n * sizeof(Elem), cudaMemcpyHostToDevice, ctx->stream));
     FG_CUDA(cudaMemcpyAsync(dSegs.p, hs.data(), nSegs * sizeof(Seg), cudaMemcpyHostToDevice, ctx->stream));
     FG_CUDA(cudaMemcpyAsync(counters.p, hc, sizeof hc, cudaMemcpyHostToDevice, ctx->stream));
-    sortSegments(ctx, d.p, dSegs.p, counters.p, nSegs, tasks, cap, "dbg_sort_top", "dbg_sort_small");
+    sortSegments(ctx, d.p, dSegs.p, counters.p, nSegs, ws, "dbg_sort_top", "dbg_sort_small");
     FG_CUDA(cudaMemcpyAsync(h.data(), d.p, n * sizeof(Elem), cudaMemcpyDeviceToHost, ctx->stream));
     FG_CUDA(cudaMemcpyAsync(hc, counters.p, sizeof hc, cudaMemcpyDeviceToHost, ctx->stream));
     FG_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -657,14 +726,15 @@ void overlapsBatch(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, const fg_
     totHits = hQHitOff[nQ];
 
     // sub-batches of consecutive queries with a bounded number of hits
-    uint64_t budget = 64ULL << 20;
+    uint64_t budget = 256ULL << 20;
     if (const char* e = getenv("FG_HIT_BUDGET")) budget = std::max<uint64_t>(1024, strtoull(e, nullptr, 10));
-    std::vector<fg_overlap> hOut;
+    PinnedBuf<fg_overlap>& pinned = ctx->pinnedOut;   // all sub-batches land here; the epilogue compacts in place
+    size_t nRaw = 0;
+    HostTimer hostAll(ctx, "host_total");
     DevBuf<Elem> hits, ord; DevBuf<int32_t> score, back; DevBuf<Cand> cands; DevBuf<uint8_t> flags;
     DevBuf<uint32_t> gStart, candIds, pairIds;
-    DevBuf<SortTask> tasks; DevBuf<Seg> segsQ;
+    SortWorkspace ws; DevBuf<Seg> segsQ;
     DevBuf<uint32_t> counters(16);
-    PinnedBuf<fg_overlap>& pinned = ctx->pinnedOut;
     std::vector<std::vector<fg_overlap>> perQuery;   // not used; results are appended in query order
 
     uint32_t qa = 0;
@@ -676,8 +746,9 @@ void overlapsBatch(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, const fg_
         if (M >= (1ULL << 31)) throw Error(FG_ERR_ARG, "a single query produced >= 2^31 k-mer hits");
         if (M == 0) { qa = qb; continue; }
         hits.ensure(M); ord.ensure(M); score.ensure(M); back.ensure(M); cands.ensure(M); flags.ensure(M);
-        const uint32_t taskCap = (uint32_t)(M / 8 + nq + 4096);
-        tasks.ensure(taskCap); segsQ.ensure(nq);
+        ws.ensure(M, nq);
+        const uint32_t taskCap = ws.capSmall;
+        segsQ.ensure(nq);
         uint32_t hCounters[16] = {0};
         hCounters[0] = nq;
         FG_CUDA(cudaMemcpyAsync(counters.p, hCounters, sizeof hCounters, cudaMemcpyHostToDevice, ctx->stream));
@@ -690,7 +761,7 @@ void overlapsBatch(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, const fg_
         }
         querySegsKernel<<<(nq + 255) / 256, 256, 0, ctx->stream>>>(dQHitOff.p, qa, nq, hitBase, segsQ.p);
         checkLaunch(ctx, "querySegsKernel");
-        sortSegments(ctx, hits.p, segsQ.p, counters.p, nq, tasks, taskCap, "hit_sort_top", "hit_sort_small");
+        sortSegments(ctx, hits.p, segsQ.p, counters.p, nq, ws, "hit_sort_top", "hit_sort_small");
         uint32_t G = 0, C = 0, Pn = 0;
         DevBuf<PairInfo> pairInfo;
         DevBuf<uint8_t> candFlag, passFlag;
@@ -724,30 +795,33 @@ void overlapsBatch(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, const fg_
             {
                 PhaseTimer pt(ctx, "chain_prep");
                 pairPrepKernel<<<(Pn + 7) / 8, 256, 0, ctx->stream>>>(hits.p, pairInfo.p, pairIds.p, Pn, dQIds.p, ctx->dLen.p, pairFlags.p,
-                                                                     extSegs.p, counters.p + 3, allSegs.p);
+                                                                     extSegs.p, counters.p + 5, allSegs.p);
                 checkLaunch(ctx, "pairPrepKernel");
             }
-            sortSegments(ctx, hits.p, extSegs.p, counters.p + 3, Pn, tasks, taskCap, "chain_extsort_top", "chain_extsort_small");
+            sortSegments(ctx, hits.p, extSegs.p, counters.p + 5, Pn, ws, "chain_extsort_top", "chain_extsort_small");
             {
                 PhaseTimer pt(ctx, "chain_dp");
                 chainDpKernel<<<(Pn + 3) / 4, 128, 0, ctx->stream>>>(hits.p, pairInfo.p, pairIds.p, Pn, pairFlags.p, P, score.p, back.p, ord.p,
                                                                     dCells.p);
                 checkLaunch(ctx, "chainDpKernel");
             }
-            FG_CUDA(cudaMemcpyAsync(counters.p + 6, &Pn, 4, cudaMemcpyHostToDevice, ctx->stream));
-            sortSegments(ctx, ord.p, allSegs.p, counters.p + 6, Pn, tasks, taskCap, "chain_ordsort_top", "chain_ordsort_small");
+            FG_CUDA(cudaMemcpyAsync(counters.p + 10, &Pn, 4, cudaMemcpyHostToDevice, ctx->stream));
+            sortSegments(ctx, ord.p, allSegs.p, counters.p + 10, Pn, ws, "chain_ordsort_top", "chain_ordsort_small");
             {
                 PhaseTimer pt(ctx, "chain_walk");
-                chainWalkKernel<<<(Pn + 127) / 128, 128, 0, ctx->stream>>>(hits.p, pairInfo.p, pairIds.p, Pn, pairFlags.p, dQIds.p, dQSlotOff.p,
+                static bool walkAttr = false;
+                const int walkSmem = 4 * WALK_CAP * (int)sizeof(int32_t);
+                if (!walkAttr) { FG_CUDA(cudaFuncSetAttribute(chainWalkKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, walkSmem)); walkAttr = true; }
+                chainWalkKernel<<<(Pn + 3) / 4, 128, walkSmem, ctx->stream>>>(hits.p, pairInfo.p, pairIds.p, Pn, pairFlags.p, dQIds.p, dQSlotOff.p,
                                                                           ctx->dLen.p, filtBits.p, filtPrefix.p, P, score.p, back.p, ord.p,
                                                                           cands.p, nCand.p, nKept.p);
                 checkLaunch(ctx, "chainWalkKernel");
             }
             {
-                uint32_t hc[9];
+                uint32_t hc[16];
                 FG_CUDA(cudaMemcpyAsync(hc, counters.p, sizeof hc, cudaMemcpyDeviceToHost, ctx->stream));
                 FG_CUDA(cudaStreamSynchronize(ctx->stream));
-                if (hc[1] > taskCap || hc[4] > taskCap || hc[7] > taskCap) throw Error(FG_ERR_INTERNAL, "sort task list overflow");
+                if (hc[1] > taskCap || hc[6] > taskCap || hc[11] > taskCap) throw Error(FG_ERR_INTERNAL, "sort task list overflow");
             }
             PhaseTimer pt(ctx, "d2h");
             cub::TransformInputIterator<uint64_t, CastU64, const uint32_t*> it64(nKept.p, CastU64());
@@ -762,32 +836,35 @@ void overlapsBatch(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, const fg_
                 gatherOverlapsKernel<<<(Pn + 255) / 256, 256, 0, ctx->stream>>>(pairInfo.p, pairIds.p, Pn, dQIds.p, ctx->dLen.p, ord.p, cands.p,
                                                                                nCand.p, outOff.p, 0, dOut.p);
                 checkLaunch(ctx, "gatherOverlapsKernel");
-                pinned.ensure(nOut);
-                FG_CUDA(cudaMemcpyAsync(pinned.p, dOut.p, nOut * sizeof(fg_overlap), cudaMemcpyDeviceToHost, ctx->stream));
+                pinned.ensureKeep(nRaw + nOut, nRaw);
+                fg_overlap* dst = pinned.p + nRaw;
+                FG_CUDA(cudaMemcpyAsync(dst, dOut.p, nOut * sizeof(fg_overlap), cudaMemcpyDeviceToHost, ctx->stream));
                 FG_CUDA(cudaStreamSynchronize(ctx->stream));
                 if (prm.nucl_alignment) {   // overlap.cpp:463-468
                     if (nOut >= (1ULL << 31)) throw Error(FG_ERR_ARG, "too many overlaps in one sub-batch");
                     PhaseTimer pe(ctx, "edit");
-                    editDistances(ctx, dOut.p, pinned.p, (uint32_t)nOut, prm.use_hpc != 0);
-                    FG_CUDA(cudaMemcpyAsync(pinned.p, dOut.p, nOut * sizeof(fg_overlap), cudaMemcpyDeviceToHost, ctx->stream));
+                    editDistances(ctx, dOut.p, dst, (uint32_t)nOut, prm.use_hpc != 0);
+                    FG_CUDA(cudaMemcpyAsync(dst, dOut.p, nOut * sizeof(fg_overlap), cudaMemcpyDeviceToHost, ctx->stream));
                     FG_CUDA(cudaStreamSynchronize(ctx->stream));
                 }
-                hOut.insert(hOut.end(), pinned.p, pinned.p + nOut);
+                nRaw += nOut;
             }
         }
         qa = qb;
     }
 
     // host epilogue: divergence (overlap.cpp:417-423), threshold (:470), maxOverlaps (:218-219)
+    HostTimer hostEpi(ctx, "host_epilogue");
     const float sampleRate = ctx->stats.sample_rate;
-    size_t pos = 0;
+    fg_overlap* hOut = pinned.p;
+    size_t pos = 0, wpos = 0;
     for (uint32_t qi = 0; qi < nQ; ++qi) {
-        ctx->resOffsets[qi] = ctx->resOverlaps.size();
+        ctx->resOffsets[qi] = wpos;
         size_t detected = 0;
-        while (pos < hOut.size() && hOut[pos].reserved == qi) {
+        while (pos < nRaw && hOut[pos].reserved == qi) {
             // one target group = run of equal ext_id
             size_t end = pos;
-            while (end < hOut.size() && hOut[end].reserved == qi && hOut[end].ext_id == hOut[pos].ext_id) ++end;
+            while (end < nRaw && hOut[end].reserved == qi && hOut[end].ext_id == hOut[pos].ext_id) ++end;
             const bool stop = prm.max_overlaps != 0 && detected >= (size_t)prm.max_overlaps;
             for (size_t i = pos; i < end && !stop; ++i) {
                 fg_overlap o = hOut[i];
@@ -804,17 +881,17 @@ void overlapsBatch(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, const fg_
                     else { volatile float dv = (float)o.edit_distance / (size_t)o.aln_len; o.seq_divergence = dv; }
                 }
                 o.reserved = 0;
-                if (o.seq_divergence < prm.max_divergence) { ctx->resOverlaps.push_back(o); ++detected; }
+                if (o.seq_divergence < prm.max_divergence) { hOut[wpos++] = o; ++detected; }   // wpos <= i: in place
             }
             pos = end;
         }
     }
-    ctx->resOffsets[nQ] = ctx->resOverlaps.size();
-    if (pos != hOut.size()) throw Error(FG_ERR_INTERNAL, "overlap records out of query order");
+    ctx->resOffsets[nQ] = wpos;
+    if (pos != nRaw) throw Error(FG_ERR_INTERNAL, "overlap records out of query order");
 
     result->n_queries = nQ;
     result->offsets = ctx->resOffsets.data();
-    result->overlaps = ctx->resOverlaps.data();
+    result->overlaps = hOut;
     result->aln_pairs = nullptr;
     result->n_aln_pairs = 0;
     result->n_hits = totHits; result->n_pairs = totPairs; result->n_dp_pairs = totDpPairs; result->n_dp_cells = totCells;
