@@ -41,16 +41,26 @@ struct Arena {
     struct Block { void* p; size_t bytes; bool used; };
     std::vector<Block> blocks;
     size_t totalBytes = 0;
+    uint64_t mallocCalls = 0;
+    // size classes {1, 1.25, 1.5, 1.75} * 2^k (>= 256 KiB): a request only ever reuses a block of its own class, so
+    // a phase that issues the same request sequence every step hits the cache on every request from step 2 on
+    static size_t sizeClass(size_t bytes) {
+        size_t c = 256u << 10;
+        while (c < bytes) {
+            const size_t q = c / 4;
+            for (int i = 1; i <= 4; ++i) if (c + i * q >= bytes) return c + i * q;
+            c *= 2;
+        }
+        return c;
+    }
     void* alloc(size_t bytes) {
         if (!bytes) return nullptr;
-        int best = -1;
-        for (int i = 0; i < (int)blocks.size(); ++i)
-            if (!blocks[i].used && blocks[i].bytes >= bytes && blocks[i].bytes <= 2 * bytes + (1u << 20) &&
-                (best < 0 || blocks[i].bytes < blocks[best].bytes)) best = i;
-        if (best >= 0) { blocks[best].used = true; return blocks[best].p; }
-        size_t want = (bytes + bytes / 8 + (1u << 21) - 1) & ~((size_t)(1u << 21) - 1);
+        const size_t want = sizeClass(bytes);
+        for (auto& b : blocks)
+            if (!b.used && b.bytes == want) { b.used = true; return b.p; }
         void* p = nullptr;
         cudaError_t e = cudaMalloc(&p, want);
+        ++mallocCalls;
         if (e != cudaSuccess) {   // give cached blocks back and retry once
             cudaGetLastError();
             trim();

@@ -731,6 +731,7 @@ void overlapsBatch(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, const fg_
     PinnedBuf<fg_overlap>& pinned = ctx->pinnedOut;   // all sub-batches land here; the epilogue compacts in place
     size_t nRaw = 0;
     HostTimer hostAll(ctx, "host_total");
+    const uint64_t mallocs0 = ctx->arena.mallocCalls;
     DevBuf<Elem> hits, ord; DevBuf<int32_t> score, back; DevBuf<Cand> cands; DevBuf<uint8_t> flags;
     DevBuf<uint32_t> gStart, candIds, pairIds;
     SortWorkspace ws; DevBuf<Seg> segsQ;
@@ -889,6 +890,8 @@ void overlapsBatch(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, const fg_
     ctx->resOffsets[nQ] = wpos;
     if (pos != nRaw) throw Error(FG_ERR_INTERNAL, "overlap records out of query order");
 
+    ctx->timings.emplace_back("arena_mallocs", (float)(ctx->arena.mallocCalls - mallocs0)); ctx->timingCalls.push_back(1);
+    ctx->timings.emplace_back("arena_gib", (float)(ctx->arena.totalBytes / 1073741824.0)); ctx->timingCalls.push_back(1);
     result->n_queries = nQ;
     result->offsets = ctx->resOffsets.data();
     result->overlaps = hOut;
