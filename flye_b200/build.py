@@ -78,10 +78,24 @@ def build_oracle():
         _run(["make", "-C", odir, "ref", "-j4"])
 
 
+def build_host_harness():
+    """oracle/harness.cpp (the driver of the reference's public API) compiled UNCHANGED against the C++ host mirror in
+    flye_b200/host and linked to libflye_b200.so: the drop-in demonstration (tests/test_gpu_host_mirror.py)."""
+    src = os.path.join(ROOT, "oracle", "harness.cpp")
+    exe = os.path.join(BUILD, "flye_b200_harness")
+    host = os.path.join(ROOT, "flye_b200", "host")
+    deps = [src, LIB] + [os.path.join(dp, f) for dp, _, fs in os.walk(host) for f in fs]
+    if _newer(exe, deps):
+        _run(["g++", "-std=c++17", "-O2", "-DFLYE_B200", "-I" + host, "-I" + os.path.join(ROOT, "include"), src, "-o", exe,
+              "-L" + os.path.join(ROOT, "flye_b200"), "-lflye_b200", "-lz", "-pthread", "-Wl,-rpath,$ORIGIN/../flye_b200"])
+    return exe
+
+
 def build_all(force=False):
     build_lib(force)
     build_tools()
     build_oracle()
+    build_host_harness()
 
 
 if __name__ == "__main__":

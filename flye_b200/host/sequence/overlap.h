@@ -1,0 +1,405 @@
+// flye_b200 host mirror — OverlapRange / OverlapDetector / OverlapContainer with the reference's interface
+// (src/sequence/overlap.h:20-523, overlap.cpp:510-927).  getSeqOverlaps runs on the device through
+// fg_overlaps_batch; the container keeps the reference's lazy cache semantics on top of batched device calls.
+#pragma once
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdlib>
+#include <memory>
+#include <mutex>
+#include <unordered_map>
+#include <vector>
+
+#include "vertex_index.h"
+#include "sequence_container.h"
+#include "../common/config.h"
+#include "../common/logger.h"
+
+#if __has_include("IntervalTree.h")
+#include "IntervalTree.h"
+#else
+template <class T> struct Interval {   // what lib/interval_tree provides, for stand-alone builds
+    Interval(int32_t s, int32_t e, const T& v) : start(s), stop(e), value(v) {}
+    int32_t start, stop;
+    T value;
+};
+template <class T> class IntervalTree {
+public:
+    IntervalTree() {}
+    explicit IntervalTree(std::vector<Interval<T>>& ivs) : _ivs(ivs) {}
+    std::vector<Interval<T>> findOverlapping(int32_t start, int32_t stop) const {
+        std::vector<Interval<T>> out;
+        for (const auto& iv : _ivs) if (iv.stop >= start && iv.start <= stop) out.push_back(iv);
+        return out;
+    }
+private:
+    std::vector<Interval<T>> _ivs;
+};
+#endif
+
+struct OverlapRange {
+    OverlapRange(FastaRecord::Id curId = FastaRecord::ID_NONE, FastaRecord::Id extId = FastaRecord::ID_NONE, int32_t curInit = 0,
+                 int32_t extInit = 0, int32_t curLen = 0, int32_t extLen = 0)
+        : curId(curId), curBegin(curInit), curEnd(curInit), curLen(curLen), extId(extId), extBegin(extInit), extEnd(extInit),
+          extLen(extLen), score(0), seqDivergence(0.0f), kmerMatches(nullptr) {}
+    ~OverlapRange() { delete kmerMatches; }
+    OverlapRange(const OverlapRange& o) : kmerMatches(nullptr) { assign(o); }
+    OverlapRange(OverlapRange&& o) : kmerMatches(nullptr) { assign(o, false); kmerMatches = o.kmerMatches; o.kmerMatches = nullptr; }
+    OverlapRange& operator=(const OverlapRange& o) { if (this != &o) assign(o); return *this; }
+
+    int32_t curRange() const { return curEnd - curBegin; }
+    int32_t extRange() const { return extEnd - extBegin; }
+    int32_t minRange() const { return std::min(curRange(), extRange()); }
+
+    OverlapRange reverse() const {   // swap the roles of the two sequences
+        OverlapRange r(*this);
+        std::swap(r.curId, r.extId); std::swap(r.curBegin, r.extBegin);
+        std::swap(r.curEnd, r.extEnd); std::swap(r.curLen, r.extLen);
+        if (r.kmerMatches) {
+            for (auto& p : *r.kmerMatches) std::swap(p.first, p.second);
+            std::sort(r.kmerMatches->begin(), r.kmerMatches->end(),
+                      [](const std::pair<int32_t, int32_t>& a, const std::pair<int32_t, int32_t>& b) { return a.first < b.first; });
+        }
+        return r;
+    }
+    OverlapRange complement() const {   // the same overlap seen from the opposite strands
+        OverlapRange c(*this);
+        c.curBegin = curLen - curEnd - 1; c.curEnd = curLen - curBegin - 1;
+        c.extBegin = extLen - extEnd - 1; c.extEnd = extLen - extBegin - 1;
+        c.curId = curId.rc(); c.extId = extId.rc();
+        if (c.kmerMatches) {
+            for (auto& p : *c.kmerMatches) { p.first = curLen - p.first - 1; p.second = extLen - p.second - 1; }
+            std::reverse(c.kmerMatches->begin(), c.kmerMatches->end());
+        }
+        return c;
+    }
+    int32_t project(int32_t curPos) const {
+        if (curPos <= curBegin) return extBegin;
+        if (curPos >= curEnd) return extEnd;
+        if (!kmerMatches) {
+            float ratio = (float)extRange() / curRange();
+            int32_t p = extBegin + float(curPos - curBegin) * ratio;
+            return std::max(extBegin, std::min(p, extEnd));
+        }
+        size_t i = std::lower_bound(kmerMatches->begin(), kmerMatches->end(), curPos,
+                                    [](const std::pair<int32_t, int32_t>& pr, int32_t v) { return pr.first < v; }) - kmerMatches->begin();
+        if (i == 0 || i == kmerMatches->size()) throw std::runtime_error("Error in overlap projection");
+        const auto &a = (*kmerMatches)[i - 1], &b = (*kmerMatches)[i];
+        float ratio = (float)(b.second - a.second) / (b.first - a.first);
+        int32_t p = a.second + float(curPos - a.first) * ratio;
+        return std::max(a.second, std::min(p, b.second));
+    }
+    int32_t leftShift() const { return curBegin - extBegin; }
+    int32_t rightShift() const { return (extLen - extEnd) - (curLen - curEnd); }
+    int32_t lrOverhang() const { return std::max(std::min(curBegin, extBegin), std::min(curLen - curEnd, extLen - extEnd)); }
+    bool contains(int32_t curPos, int32_t extPos) const {
+        return curBegin <= curPos && curPos <= curEnd && extBegin <= extPos && extPos <= extEnd;
+    }
+    bool containedBy(const OverlapRange& o) const {
+        if (curId != o.curId || extId != o.extId) return false;
+        return o.curBegin <= curBegin && curEnd <= o.curEnd && o.extBegin <= extBegin && extEnd <= o.extEnd;
+    }
+    int32_t curIntersect(const OverlapRange& o) const { return std::min(curEnd, o.curEnd) - std::max(curBegin, o.curBegin); }
+    int32_t extIntersect(const OverlapRange& o) const { return std::min(extEnd, o.extEnd) - std::max(extBegin, o.extBegin); }
+    void dump(std::ostream& os, const SequenceContainer& curContainer, const SequenceContainer& extContainer) {
+        os << curContainer.seqName(curId) << " " << curBegin << " " << curEnd << " " << curLen << " " << extContainer.seqName(extId)
+           << " " << extBegin << " " << extEnd << " " << extLen << " " << -1 << " " << -1 << " " << score << " " << seqDivergence;
+    }
+    void load(std::istream& is, const SequenceContainer& curContainer, const SequenceContainer& extContainer) {
+        int32_t pad1, pad2; std::string curName, extName;
+        is >> curName >> curBegin >> curEnd >> curLen >> extName >> extBegin >> extEnd >> extLen >> pad1 >> pad2 >> score >> seqDivergence;
+        curId = curContainer.recordByName(curName).id;
+        extId = extContainer.recordByName(extName).id;
+    }
+
+    FastaRecord::Id curId; int32_t curBegin, curEnd, curLen;
+    FastaRecord::Id extId; int32_t extBegin, extEnd, extLen;
+    int32_t score;
+    float seqDivergence;
+    std::vector<std::pair<int32_t, int32_t>>* kmerMatches;
+
+private:
+    void assign(const OverlapRange& o, bool deep = true) {
+        curId = o.curId; curBegin = o.curBegin; curEnd = o.curEnd; curLen = o.curLen;
+        extId = o.extId; extBegin = o.extBegin; extEnd = o.extEnd; extLen = o.extLen;
+        score = o.score; seqDivergence = o.seqDivergence;
+        if (!deep) return;
+        if (!o.kmerMatches) { delete kmerMatches; kmerMatches = nullptr; }
+        else { if (!kmerMatches) kmerMatches = new std::vector<std::pair<int32_t, int32_t>>(); *kmerMatches = *o.kmerMatches; }
+    }
+};
+
+struct OvlpDivStats {
+    static const size_t MAX_STATS = 1000000;
+    OvlpDivStats() : divVec(MAX_STATS), vecSize(0) {}
+    void add(float val) {
+        size_t slot = vecSize.fetch_add(1);
+        if (slot < MAX_STATS) divVec[slot] = val; else vecSize = MAX_STATS;
+    }
+    std::vector<float> divVec;
+    std::atomic<size_t> vecSize;
+};
+
+class OverlapDetector {
+public:
+    OverlapDetector(const SequenceContainer& seqContainer, const VertexIndex& vertexIndex, int maxJump, int minOverlap, int maxOverhang,
+                    bool keepAlignment, bool onlyMaxExt, float maxDivergence, bool nuclAlignment, bool partitionBadMappings, bool useHpc)
+        : _maxJump(maxJump), _minOverlap(minOverlap), _maxOverhang(maxOverhang), _maxCurOverlaps(0), _checkOverhang(maxOverhang > 0),
+          _keepAlignment(keepAlignment), _onlyMaxExt(onlyMaxExt), _nuclAlignment(nuclAlignment),
+          _partitionBadMappings(partitionBadMappings), _useHpc(useHpc), _maxDivergence(maxDivergence), _vertexIndex(vertexIndex),
+          _seqContainer(seqContainer) {
+        if (partitionBadMappings) throw std::runtime_error("flye_b200: partitionBadMappings (KSW2 trimming) is not on the device path yet");
+    }
+    friend class OverlapContainer;
+
+private:
+    // getSeqOverlaps for many query sequences in one device pass (reference: one call per read, overlap.cpp:99-508)
+    std::vector<std::vector<OverlapRange>> getSeqOverlapsBatch(const std::vector<FastaRecord::Id>& queries, bool forceLocal,
+                                                               OvlpDivStats& divStats, int maxOverlaps) const {
+        const auto& dev = _vertexIndex.device();
+        if (&_vertexIndex.container() != &_seqContainer) throw std::runtime_error("flye_b200: index and target containers differ");
+        const uint32_t base = (uint32_t)_seqContainer.idOffset();
+        std::vector<uint32_t> ids(queries.size());
+        for (size_t i = 0; i < queries.size(); ++i) ids[i] = queries[i].rawId() - base;
+        fg_overlap_params p;
+        p.max_jump = _maxJump; p.min_overlap = _minOverlap; p.max_overhang = _maxOverhang; p.max_overlaps = maxOverlaps;
+        p.force_local = forceLocal; p.keep_alignment = _keepAlignment; p.only_max_ext = _onlyMaxExt; p.nucl_alignment = _nuclAlignment;
+        p.use_hpc = _useHpc; p.max_divergence = _maxDivergence;
+        // results live in library memory until the next call: copy out under the lock
+        std::lock_guard<std::mutex> lock(batchMutex());
+        fg_overlap_result res;
+        dev->check(fg_overlaps_batch(dev->ctx, ids.data(), (uint32_t)ids.size(), &p, &res));
+        std::vector<std::vector<OverlapRange>> out(queries.size());
+        for (size_t q = 0; q < queries.size(); ++q) {
+            out[q].reserve(res.offsets[q + 1] - res.offsets[q]);
+            for (uint64_t i = res.offsets[q]; i < res.offsets[q + 1]; ++i) {
+                const fg_overlap& o = res.overlaps[i];
+                OverlapRange r(FastaRecord::Id(base + o.cur_id), FastaRecord::Id(base + o.ext_id), o.cur_begin, o.ext_begin, o.cur_len, o.ext_len);
+                r.curEnd = o.cur_end; r.extEnd = o.ext_end; r.score = o.score; r.seqDivergence = o.seq_divergence;
+                out[q].push_back(std::move(r));
+            }
+            // per-10kb-window divergence statistics (overlap.cpp:488-506)
+            const int STAT_WND = 10000;
+            if (!out[q].empty()) {
+                std::vector<const OverlapRange*> wnd(out[q].front().curLen / STAT_WND + 1, nullptr);
+                for (const auto& r : out[q]) { auto& w = wnd[r.curBegin / STAT_WND]; if (!w || r.curRange() > w->curRange()) w = &r; }
+                for (auto* w : wnd) if (w && w->curRange() > 0) divStats.add(w->seqDivergence);
+            }
+        }
+        return out;
+    }
+    std::vector<OverlapRange> getSeqOverlaps(const FastaRecord& rec, bool forceLocal, OvlpDivStats& stats, int maxOverlaps) const {
+        return std::move(getSeqOverlapsBatch({rec.id}, forceLocal, stats, maxOverlaps)[0]);
+    }
+    static std::mutex& batchMutex() { static std::mutex m; return m; }
+
+    const int _maxJump, _minOverlap, _maxOverhang, _maxCurOverlaps;
+    const bool _checkOverhang, _keepAlignment, _onlyMaxExt, _nuclAlignment, _partitionBadMappings, _useHpc;
+    mutable float _maxDivergence;
+    const VertexIndex& _vertexIndex;
+    const SequenceContainer& _seqContainer;
+};
+
+class OverlapContainer {
+public:
+    OverlapContainer(const OverlapDetector& ovlpDetect, const SequenceContainer& queryContainer)
+        : _ovlpDetect(ovlpDetect), _queryContainer(queryContainer), _indexSize(0), _meanTrueOvlpDiv(0) {
+        if (&queryContainer != &ovlpDetect._seqContainer)
+            throw std::runtime_error("flye_b200: queries from a second container (read-to-graph alignment) are not on the device path yet");
+    }
+    struct IndexVecWrapper {
+        IndexVecWrapper() : fwdOverlaps(new std::vector<OverlapRange>), revOverlaps(new std::vector<OverlapRange>), cached(false),
+                            suggestChimeric(false) {}
+        std::shared_ptr<std::vector<OverlapRange>> fwdOverlaps, revOverlaps;
+        bool cached, suggestChimeric;
+    };
+
+    // thread safe: computes (one device call) and caches on first use; both strands are stored (overlap.cpp:528-574)
+    const std::vector<OverlapRange>& lazySeqOverlaps(FastaRecord::Id readId) {
+        const bool flipped = !readId.strand();
+        if (flipped) readId = readId.rc();
+        {
+            std::lock_guard<std::mutex> lock(_cacheMutex);
+            auto it = _overlapIndex.find(readId);
+            if (it != _overlapIndex.end() && it->second.cached) return flipped ? *it->second.revOverlaps : *it->second.fwdOverlaps;
+        }
+        prefetch({readId});
+        std::lock_guard<std::mutex> lock(_cacheMutex);
+        const auto& w = _overlapIndex[readId];
+        return flipped ? *w.revOverlaps : *w.fwdOverlaps;
+    }
+    bool hasSelfOverlaps(FastaRecord::Id readId) {
+        this->lazySeqOverlaps(readId);
+        std::lock_guard<std::mutex> lock(_cacheMutex);
+        return _overlapIndex[readId.strand() ? readId : readId.rc()].suggestChimeric;
+    }
+    std::vector<OverlapRange> quickSeqOverlaps(FastaRecord::Id readId, int maxOverlaps = 0, bool forceLocal = false) {
+        return std::move(_ovlpDetect.getSeqOverlapsBatch({readId}, forceLocal, _divergenceStats, maxOverlaps)[0]);
+    }
+    // mirror extension: the same results as N quickSeqOverlaps calls from one device pass
+    std::vector<std::vector<OverlapRange>> quickSeqOverlapsBatch(const std::vector<FastaRecord::Id>& ids, int maxOverlaps = 0,
+                                                                 bool forceLocal = false) {
+        return _ovlpDetect.getSeqOverlapsBatch(ids, forceLocal, _divergenceStats, maxOverlaps);
+    }
+    // mirror extension: fill the lazy cache for many forward reads with one device pass
+    void prefetch(const std::vector<FastaRecord::Id>& fwdIds) {
+        std::vector<FastaRecord::Id> todo;
+        {
+            std::lock_guard<std::mutex> lock(_cacheMutex);
+            for (auto id : fwdIds) { auto it = _overlapIndex.find(id); if (it == _overlapIndex.end() || !it->second.cached) todo.push_back(id); }
+        }
+        if (todo.empty()) return;
+        auto res = _ovlpDetect.getSeqOverlapsBatch(todo, false, _divergenceStats, _ovlpDetect._maxCurOverlaps);
+        std::lock_guard<std::mutex> lock(_cacheMutex);
+        for (size_t i = 0; i < todo.size(); ++i) {
+            auto& w = _overlapIndex[todo[i]];
+            if (w.cached) continue;
+            w.revOverlaps->reserve(res[i].size());
+            for (const auto& o : res[i]) w.revOverlaps->push_back(o.complement());
+            _indexSize += res[i].size();
+            *w.fwdOverlaps = std::move(res[i]);
+            w.cached = true;
+        }
+    }
+    size_t indexSize() { return _indexSize; }
+
+    void estimateOverlaperParameters() {   // overlap.cpp:744-817: 1000 ids drawn with rand() % size, either strand
+        Logger::get().debug() << "Estimating k-mer identity bias";
+        const int MAX_SEQS = 1000;
+        std::vector<FastaRecord::Id> ids;
+        for (int i = 0; i < MAX_SEQS; ++i) ids.push_back(_queryContainer.iterSeqs()[rand() % _queryContainer.iterSeqs().size()].id);
+        auto res = _ovlpDetect.getSeqOverlapsBatch(ids, false, _divergenceStats, 0);
+        std::vector<float> divs;
+        for (const auto& ovs : res) {
+            const OverlapRange* best = nullptr;
+            for (const auto& o : ovs) if (!best || o.curRange() > best->curRange()) best = &o;
+            if (best) divs.push_back(best->seqDivergence);
+        }
+        if (!divs.empty()) {
+            std::sort(divs.begin(), divs.end());
+            _meanTrueOvlpDiv = divs[std::min(divs.size() * (size_t)50 / 100, divs.size() - 1)];
+            _divergenceStats.vecSize = 0;
+        } else {
+            Logger::get().warning() << "No overlaps found - unable to estimate parameters";
+            _meanTrueOvlpDiv = 0.5f;
+        }
+        Logger::get().debug() << "Initial divergence estimate : " << _meanTrueOvlpDiv;
+    }
+    void setDivergenceThreshold(float threshold, bool isRelative) {
+        _ovlpDetect._maxDivergence = (isRelative ? _meanTrueOvlpDiv : 0.0f) + threshold;
+        Logger::get().debug() << "Max divergence threshold set to " << _ovlpDetect._maxDivergence;
+    }
+
+    // the functions below are NOT thread safe (as in the reference)
+    void ensureTransitivity(bool onlyMaxExt) {   // overlap.cpp:576-627
+        std::vector<FastaRecord::Id> all;
+        for (const auto& kv : _overlapIndex) { all.push_back(kv.first); all.push_back(kv.first.rc()); }
+        for (auto seq : all) {
+            std::vector<OverlapRange> toAdd;
+            for (const auto& cur : unsafeSeqOverlaps(seq)) {
+                if (onlyMaxExt) {
+                    bool found = false;
+                    for (auto& ext : unsafeSeqOverlaps(cur.extId))
+                        if (ext.extId == cur.curId) { if (cur.score > ext.score) ext = cur.reverse(); found = true; break; }
+                    if (!found) toAdd.push_back(cur.reverse());
+                } else toAdd.push_back(cur.reverse());
+            }
+            for (const auto& o : toAdd) unsafeSeqOverlaps(o.curId).push_back(o);
+        }
+    }
+    void overlapDivergenceStats() { overlapDivergenceStats(_divergenceStats, _ovlpDetect._maxDivergence); }
+    void overlapDivergenceStats(const OvlpDivStats& stats, float divCutoff) {
+        std::vector<float> v(stats.divVec.begin(), stats.divVec.begin() + std::min<size_t>(stats.vecSize, OvlpDivStats::MAX_STATS));
+        if (v.empty()) return;
+        std::sort(v.begin(), v.end());
+        auto q = [&](int pct) { return v[std::min(v.size() * (size_t)pct / 100, v.size() - 1)]; };
+        Logger::get().info() << "Median overlap divergence: " << q(50);
+        Logger::get().debug() << "Sequence divergence distribution: Q25 = " << q(25) << ", Q50 = " << q(50) << ", Q75 = " << q(75)
+                              << " (cutoff " << divCutoff << ")";
+    }
+    void findAllOverlaps() {   // overlap.cpp:630-668: all forward reads in one device pass, then closure + de-duplication
+        std::vector<FastaRecord::Id> all;
+        for (const auto& seq : _queryContainer.iterSeqs()) if (seq.id.strand()) all.push_back(seq.id);
+        prefetch(all);
+        ensureTransitivity(false);
+        filterOverlaps();
+    }
+    void buildIntervalTree() {
+        for (auto& kv : _overlapIndex)
+            for (auto id : {kv.first, kv.first.rc()}) {
+                std::vector<Interval<const OverlapRange*>> ivs;
+                for (const auto& o : unsafeSeqOverlaps(id)) ivs.emplace_back(o.curBegin, o.curEnd, &o);
+                _ovlpTree[id] = IntervalTree<const OverlapRange*>(ivs);
+            }
+    }
+    std::vector<Interval<const OverlapRange*>> getCoveringOverlaps(FastaRecord::Id seqId, int32_t start, int32_t end) const {
+        return _ovlpTree.at(seqId).findOverlapping(start, end);
+    }
+
+private:
+    std::vector<OverlapRange>& unsafeSeqOverlaps(FastaRecord::Id id) {
+        auto& w = _overlapIndex[id.strand() ? id : id.rc()];
+        return id.strand() ? *w.fwdOverlaps : *w.revOverlaps;
+    }
+    void filterOverlaps() {   // overlap.cpp:681-741: cluster near-identical overlaps (ends within k), keep the best of each
+        const int MAX_ENDS_DIFF = (int)Parameters::get().kmerSize;
+        for (const auto& seq : _queryContainer.iterSeqs()) {
+            auto& ovs = unsafeSeqOverlaps(seq.id);
+            std::vector<size_t> parent(ovs.size());
+            for (size_t i = 0; i < parent.size(); ++i) parent[i] = i;
+            auto find = [&](size_t x) { while (parent[x] != x) x = parent[x] = parent[parent[x]]; return x; };
+            for (size_t i = 0; i < ovs.size(); ++i)
+                for (size_t j = 0; j < ovs.size(); ++j) {
+                    if (ovs[i].extId != ovs[j].extId) continue;
+                    if (ovs[i].curRange() - ovs[i].curIntersect(ovs[j]) < MAX_ENDS_DIFF &&
+                        ovs[i].extRange() - ovs[i].extIntersect(ovs[j]) < MAX_ENDS_DIFF) parent[find(i)] = find(j);
+                }
+            std::unordered_map<size_t, size_t> best;   // cluster -> index of the first maximum score
+            for (size_t i = 0; i < ovs.size(); ++i) {
+                auto it = best.find(find(i));
+                if (it == best.end()) best[find(i)] = i; else if (ovs[i].score > ovs[it->second].score) it->second = i;
+            }
+            std::vector<OverlapRange> kept;
+            for (const auto& kv : best) kept.push_back(ovs[kv.second]);
+            std::sort(kept.begin(), kept.end(), [](const OverlapRange& a, const OverlapRange& b) { return a.curBegin < b.curBegin; });
+            ovs = std::move(kept);
+        }
+    }
+
+    const OverlapDetector& _ovlpDetect;
+    const SequenceContainer& _queryContainer;
+    OvlpDivStats _divergenceStats;
+    std::mutex _cacheMutex;
+    std::unordered_map<FastaRecord::Id, IndexVecWrapper> _overlapIndex;
+    std::atomic<size_t> _indexSize;
+    std::unordered_map<FastaRecord::Id, IntervalTree<const OverlapRange*>> _ovlpTree;
+    float _meanTrueOvlpDiv;
+};
+
+// iterate overlaps without large overhangs (overlap.h:457-523)
+class OvlpIterator {
+public:
+    OvlpIterator(std::vector<OverlapRange>::const_iterator it, std::vector<OverlapRange>::const_iterator end, bool onlyNoOverhang)
+        : it(it), end(end), onlyNoOverhang(onlyNoOverhang) { skip(); }
+    bool operator==(const OvlpIterator& o) const { return it == o.it && onlyNoOverhang == o.onlyNoOverhang; }
+    bool operator!=(const OvlpIterator& o) const { return !(*this == o); }
+    const OverlapRange& operator*() const { return *it; }
+    OvlpIterator& operator++() { ++it; skip(); return *this; }
+private:
+    void skip() {
+        if (!onlyNoOverhang) return;
+        static const int MAX_OVERHANG = Config::get("maximum_overhang");
+        while (it != end && it->lrOverhang() > MAX_OVERHANG) ++it;
+    }
+    std::vector<OverlapRange>::const_iterator it, end;
+    bool onlyNoOverhang;
+};
+class IterNoOverhang {
+public:
+    IterNoOverhang(const std::vector<OverlapRange>& ovlps) : ovlps(ovlps) {}
+    OvlpIterator begin() { return OvlpIterator(ovlps.begin(), ovlps.end(), true); }
+    OvlpIterator end() { return OvlpIterator(ovlps.end(), ovlps.end(), true); }
+private:
+    const std::vector<OverlapRange>& ovlps;
+};

@@ -1,0 +1,40 @@
+"""-m gpu: the drop-in boundary.  oracle/harness.cpp — written against the reference's public C++ API — is compiled
+unchanged against the host mirror (flye_b200/host: SequenceContainer, VertexIndex, OverlapDetector, OverlapContainer,
+OverlapRange over the C ABI) and must produce the same dumps as the build against the unmodified reference."""
+import os
+import subprocess
+import json
+
+import pytest
+
+import parity_util as pu
+
+pytestmark = pytest.mark.gpu
+MIRROR = os.path.join(pu.ROOT, "build", "flye_b200_harness")
+RAW = os.path.join(pu.CFG_DIR, "raw_reads.cfg")
+HIFI = os.path.join(pu.CFG_DIR, "hifi.cfg")
+
+
+def run_mirror(reads, cfg, out, k=None, extra=()):
+    if not os.path.exists(MIRROR):
+        from flye_b200 import build
+        build.build_host_harness()
+    cmd = [MIRROR, "--reads", reads, "--cfg", cfg, "--out", out, "--threads", "4"] + (["--k", str(k)] if k else []) + list(extra)
+    r = subprocess.run(cmd, check=True, stdout=subprocess.PIPE, text=True)
+    return json.loads(r.stdout.strip().splitlines()[-1])
+
+
+@pytest.mark.parametrize("cfg,k,sim,opts,exts", [
+    (RAW, 15, dict(genome_len=80000, coverage=12, seed=41), ["--dump-index"], ["hist", "index", "ovlp"]),
+    (RAW, 15, dict(genome_len=80000, coverage=12, seed=42), ["--find-all"], ["ovlp"]),        # closure + cluster filter, multisets
+    (HIFI, None, dict(genome_len=60000, coverage=10, mean_len=8000, shape=20, error=0.005, seed=43), ["--both-strands"], ["ovlp"]),
+])
+def test_reference_harness_source_runs_on_the_mirror(built, tmp_path, cfg, k, sim, opts, exts):
+    tmp = str(tmp_path)
+    reads = pu.simulate(os.path.join(tmp, "r.fasta"), **sim)
+    ref = pu.run_oracle(reads, cfg, os.path.join(tmp, "ref"), k=k, extra=opts)
+    got = run_mirror(reads, cfg, os.path.join(tmp, "gpu"), k=k, extra=opts)
+    assert got["reads"] == ref["reads"] and got["overlaps"] == ref["overlaps"]
+    for ext in exts:
+        n, sample = pu.diff_files(os.path.join(tmp, "ref." + ext), os.path.join(tmp, "gpu." + ext))
+        assert n == 0, (ext, sample[:3])
