@@ -264,6 +264,23 @@ class Engine:
         stats = dict(n_hits=res.n_hits, n_pairs=res.n_pairs, n_dp_pairs=res.n_dp_pairs, n_dp_cells=res.n_dp_cells)
         return offsets, ov, stats
 
+    # ---- multi-GPU ----
+    @staticmethod
+    def comm_unique_id():
+        lib = load_lib()
+        buf = (C.c_uint8 * 128)()
+        rc = lib.fg_comm_unique_id(buf)
+        if rc != FG_OK:
+            raise FlyeB200Error("fg_comm_unique_id: %s (is libnccl available?)" % ERR_NAMES.get(rc, rc))
+        return bytes(buf)
+
+    def comm_init(self, n_ranks, rank, unique_id):
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        self._check(self.lib.fg_comm_init(self.ctx, n_ranks, rank, buf))
+
+    def set_shard(self, first_read, n_reads):
+        self._check(self.lib.fg_comm_set_shard(self.ctx, first_read, n_reads))
+
     def debug_warp_sort(self, keys, vals, seg_offsets):
         keys = np.ascontiguousarray(keys, dtype=np.uint64).copy()
         vals = np.ascontiguousarray(vals, dtype=np.uint32).copy()

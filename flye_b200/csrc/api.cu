@@ -104,6 +104,7 @@ void fg_ctx_destroy(fg_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     cudaStream_t s = ctx->stream;
     cudaDeviceSynchronize();
+    try { fg::commDestroy(ctx); } catch (...) {}
     fg::currentArena() = &ctx->arena;
     delete ctx;
     fg::currentArena() = nullptr;
@@ -309,13 +310,11 @@ int fg_debug_warp_sort(fg_ctx* ctx, uint64_t* keys, uint32_t* vals, const uint64
 }
 
 // ---- multi-GPU ------------------------------------------------------------------------------------------
-int fg_comm_unique_id(uint8_t id[FG_NCCL_ID_BYTES]) { (void)id; return FG_ERR_NCCL; }
+int fg_comm_unique_id(uint8_t id[FG_NCCL_ID_BYTES]) {
+    try { fg::commUniqueId(id); return FG_OK; } catch (const Error& e) { return e.code; }
+}
 int fg_comm_init(fg_ctx* ctx, int nRanks, int rank, const uint8_t id[FG_NCCL_ID_BYTES]) {
-    (void)id;
-    return guarded(ctx, [&] {
-        if (nRanks != 1 || rank != 0) throw Error(FG_ERR_NCCL, "NCCL communicator support is not built yet");
-        ctx->nRanks = 1; ctx->rank = 0;
-    });
+    return guarded(ctx, [&] { fg::commInit(ctx, nRanks, rank, id); });
 }
 int fg_comm_set_shard(fg_ctx* ctx, uint32_t firstRead, uint32_t nReads) {
     return guarded(ctx, [&] {

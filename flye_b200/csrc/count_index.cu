@@ -154,7 +154,10 @@ static void countKmersT(fg_ctx* ctx) {
     ctx->hist.clear();
     ctx->nDistinct = 0;
     ctx->dCountSlots.release();
-    if (N == 0) { ctx->countTable = makeTable(ctx, ctx->dCountSlots, 0); ctx->counted = true; return; }
+    if (N == 0) {
+        if (sharded(ctx)) throw Error(FG_ERR_ARG, "a rank's read shard has no k-mers");
+        ctx->countTable = makeTable(ctx, ctx->dCountSlots, 0); ctx->counted = true; return;
+    }
 
     DevBuf<uint64_t> dTileOut(nTiles + 1);
     FG_CUDA(cudaMemcpyAsync(dTileOut.p, hTileOut.data(), (nTiles + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
@@ -189,14 +192,61 @@ static void countKmersT(fg_ctx* ctx) {
         FG_CUDA(cudaMemcpyAsync(&nRuns, dRuns.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
         FG_CUDA(cudaStreamSynchronize(ctx->stream));
 
+        // multi-GPU: every rank counted its own shard of the reads; all-gather the (k-mer,count) runs over NCCL and
+        // reduce them by key, so that every rank ends up with the global counts (replicated count table)
+        DevBuf<char> allKeys, allCounts; DevBuf<KeyT> mKeysB, mUniq; DevBuf<uint32_t> mCountsB, mCounts;
+        if (sharded(ctx)) {
+            std::vector<uint64_t> offK, offC;
+            allGatherV(ctx, uniq, nRuns * sizeof(KeyT), allKeys, offK);
+            allGatherV(ctx, counts.p, nRuns * 4ULL, allCounts, offC);
+            const uint64_t T = offC.back() / 4;
+            if (T >= (1ULL << 31)) throw Error(FG_ERR_ARG, "more than 2^31 (k-mer,count) runs to merge");
+            mKeysB.alloc(T); mCountsB.alloc(T); mUniq.alloc(T); mCounts.alloc(T);
+            cub::DoubleBuffer<KeyT> mk((KeyT*)allKeys.p, mKeysB.p);
+            cub::DoubleBuffer<uint32_t> mv((uint32_t*)allCounts.p, mCountsB.p);
+            size_t tb = 0;
+            FG_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, mk, mv, (int)T, 0, 2 * k, ctx->stream));
+            DevBuf<char> t1(tb);
+            FG_CUDA(cub::DeviceRadixSort::SortPairs(t1.p, tb, mk, mv, (int)T, 0, 2 * k, ctx->stream));
+            tb = 0;
+            FG_CUDA(cub::DeviceReduce::ReduceByKey(nullptr, tb, mk.Current(), mUniq.p, mv.Current(), mCounts.p, dRuns.p, cub::Sum(), (int)T, ctx->stream));
+            DevBuf<char> t2(tb);
+            FG_CUDA(cub::DeviceReduce::ReduceByKey(t2.p, tb, mk.Current(), mUniq.p, mv.Current(), mCounts.p, dRuns.p, cub::Sum(), (int)T, ctx->stream));
+            ctx->launches += (2 * k + 7) / 8 + 3;
+            FG_CUDA(cudaMemcpyAsync(&nRuns, dRuns.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+            FG_CUDA(cudaStreamSynchronize(ctx->stream));
+        }
+        const KeyT* gUniq = sharded(ctx) ? mUniq.p : uniq;
+        const uint32_t* gCounts = sharded(ctx) ? mCounts.p : counts.p;
+
         // histogram (vertex_index.cpp:567-576)
         DevBuf<unsigned long long> dHist(HIST_GLOBAL_BINS);
         const uint32_t ovCap = 1u << 20;
         DevBuf<uint32_t> dOv(ovCap), dNOv(1);
         FG_CUDA(cudaMemsetAsync(dHist.p, 0, dHist.bytes(), ctx->stream));
         FG_CUDA(cudaMemsetAsync(dNOv.p, 0, 4, ctx->stream));
-        histKernel<<<gridFor(nRuns), 256, 0, ctx->stream>>>(counts.p, nRuns, dHist.p, dOv.p, dNOv.p, ovCap);
-        checkLaunch(ctx, "histKernel");
+        if (sharded(ctx)) {
+            // each rank histograms its slice of the merged runs; the freq -> #k-mers histogram is then reduced over NCCL
+            const uint64_t lo = nRuns * ctx->rank / ctx->nRanks, hi = nRuns * (ctx->rank + 1) / ctx->nRanks;
+            if (hi > lo) {
+                histKernel<<<gridFor(hi - lo), 256, 0, ctx->stream>>>(gCounts + lo, hi - lo, dHist.p, dOv.p, dNOv.p, ovCap);
+                checkLaunch(ctx, "histKernel");
+            }
+            allReduceSumU64(ctx, dHist.p, HIST_GLOBAL_BINS);
+            DevBuf<char> ovAll; std::vector<uint64_t> ovOff;
+            uint32_t myOv = 0;
+            FG_CUDA(cudaMemcpyAsync(&myOv, dNOv.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+            FG_CUDA(cudaStreamSynchronize(ctx->stream));
+            if (myOv > ovCap) throw Error(FG_ERR_INTERNAL, "k-mer histogram overflow list exhausted");
+            allGatherV(ctx, dOv.p, myOv * 4ULL, ovAll, ovOff);
+            const uint32_t totOv = (uint32_t)(ovOff.back() / 4);
+            if (totOv > ovCap) throw Error(FG_ERR_INTERNAL, "k-mer histogram overflow list exhausted");
+            if (totOv) FG_CUDA(cudaMemcpyAsync(dOv.p, ovAll.p, totOv * 4ULL, cudaMemcpyDeviceToDevice, ctx->stream));
+            FG_CUDA(cudaMemcpyAsync(dNOv.p, &totOv, 4, cudaMemcpyHostToDevice, ctx->stream));
+        } else {
+            histKernel<<<gridFor(nRuns), 256, 0, ctx->stream>>>(gCounts, nRuns, dHist.p, dOv.p, dNOv.p, ovCap);
+            checkLaunch(ctx, "histKernel");
+        }
         std::vector<unsigned long long> hHist(HIST_GLOBAL_BINS);
         uint32_t nOv = 0;
         FG_CUDA(cudaMemcpyAsync(hHist.data(), dHist.p, dHist.bytes(), cudaMemcpyDeviceToHost, ctx->stream));
@@ -212,7 +262,7 @@ static void countKmersT(fg_ctx* ctx) {
         ctx->nDistinct = nRuns;
         uint64_t n2 = nRuns - (ctx->hist.count(1) ? ctx->hist[1] : 0);
         ctx->countTable = makeTable(ctx, ctx->dCountSlots, n2);
-        buildCountTableKernel<KeyT><<<gridFor(nRuns), 256, 0, ctx->stream>>>(uniq, counts.p, nRuns, ctx->countTable);
+        buildCountTableKernel<KeyT><<<gridFor(nRuns), 256, 0, ctx->stream>>>(gUniq, gCounts, nRuns, ctx->countTable);
         checkLaunch(ctx, "buildCountTableKernel");
         FG_CUDA(cudaStreamSynchronize(ctx->stream));
     }
@@ -643,6 +693,40 @@ static void buildFromSelection(fg_ctx* ctx, DevBuf<uint32_t>& rcBits, int minCov
             checkLaunch(ctx, "emitWriteKernel");
             FG_CUDA(cudaStreamSynchronize(ctx->stream));
         }
+    }
+    if (sharded(ctx)) {
+        // shards are contiguous, ascending read ranges, so concatenating the ranks' entries in rank order keeps the
+        // global-position order the single stable sort below relies on
+        DevBuf<char> allK, allV; std::vector<uint64_t> offK, offV;
+        allGatherV(ctx, keysA.p, E * sizeof(KeyT), allK, offK);
+        allGatherV(ctx, valsA.p, E * 8ULL, allV, offV);
+        E = offV.back() / 8;
+        if (E >= (1ULL << 31)) throw Error(FG_ERR_ARG, "more than 2^31 index entries");
+        keysA.alloc(std::max<uint64_t>(E, 1)); keysB.alloc(std::max<uint64_t>(E, 1));
+        valsA.alloc(std::max<uint64_t>(E, 1)); valsB.alloc(std::max<uint64_t>(E, 1));
+        if (E) {
+            FG_CUDA(cudaMemcpyAsync(keysA.p, allK.p, E * sizeof(KeyT), cudaMemcpyDeviceToDevice, ctx->stream));
+            FG_CUDA(cudaMemcpyAsync(valsA.p, allV.p, E * 8ULL, cudaMemcpyDeviceToDevice, ctx->stream));
+        }
+        // the "selected" bitmap (needed for the self-hit test of every query) is replicated by one NCCL broadcast per
+        // owner; each rank owns the whole bitmap words of its reads
+        std::vector<uint32_t> firsts(ctx->nRanks + 1, 0);
+        {
+            DevBuf<char> all; std::vector<uint64_t> off;
+            DevBuf<uint32_t> mine(1);
+            FG_CUDA(cudaMemcpyAsync(mine.p, &firstRead, 4, cudaMemcpyHostToDevice, ctx->stream));
+            allGatherV(ctx, mine.p, 4, all, off);
+            FG_CUDA(cudaMemcpyAsync(firsts.data(), all.p, ctx->nRanks * 4ULL, cudaMemcpyDeviceToHost, ctx->stream));
+            FG_CUDA(cudaStreamSynchronize(ctx->stream));
+            firsts[ctx->nRanks] = ctx->nReads;
+        }
+        groupStart();
+        for (int r = 0; r < ctx->nRanks; ++r) {
+            const uint64_t w0 = ctx->hSlotOff[firsts[r]] / 32, w1 = ctx->hSlotOff[firsts[r + 1]] / 32;
+            broadcastBytes(ctx, ctx->dSelBits.p + w0, (w1 - w0) * 4, r);
+        }
+        groupEnd();
+        FG_CUDA(cudaStreamSynchronize(ctx->stream));
     }
     ctx->dEntries.release(); ctx->dIndexSlots.release(); ctx->dUKeys.release(); ctx->dUPayload.release();
     ctx->stats = fg_index_stats{};

@@ -130,6 +130,17 @@ void buildIndexMinimizers(fg_ctx* ctx, int k, int minCov, int window, float repe
 void overlapsBatch(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQueries, const fg_overlap_params& p,
                    fg_overlap_result* result);
 
+// NCCL plumbing (comm.cu)
+void commUniqueId(uint8_t* id);
+void commInit(fg_ctx* ctx, int nRanks, int rank, const uint8_t* id);
+void commDestroy(fg_ctx* ctx);
+void allGatherV(fg_ctx* ctx, const void* src, uint64_t bytes, DevBuf<char>& out, std::vector<uint64_t>& offs);
+void allReduceSumU64(fg_ctx* ctx, unsigned long long* buf, size_t count);
+void broadcastBytes(fg_ctx* ctx, void* buf, uint64_t bytes, int root);
+void groupStart();
+void groupEnd();
+inline bool sharded(const fg_ctx* ctx) { return ctx->nRanks > 1 && ctx->ncclComm && ctx->shardSet; }
+
 void editDistances(fg_ctx* ctx, fg_overlap* dOv, const fg_overlap* hOv, uint32_t nOv, bool useHpc);
 int debugEditDistance(fg_ctx* ctx, const uint8_t* a, int n, const uint8_t* b, int m);
 void debugWarpSort(fg_ctx* ctx, uint64_t* keys, uint32_t* vals, const uint64_t* segOffsets, uint32_t nSegs);
