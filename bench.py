@@ -50,8 +50,9 @@ def make_reads(wl, scale):
     tag = "_".join("%s%s" % (k[0], v) for k, v in sorted(sim.items()))
     path = os.path.join("/tmp", "flye_b200_bench_%s.fasta" % tag)
     if not os.path.exists(path):
-        pu.simulate(path + ".tmp", **sim)
-        os.replace(path + ".tmp", path)
+        tmp = "%s.%d.tmp" % (path, os.getpid())
+        pu.simulate(tmp, **sim)
+        os.replace(tmp, path)
     return path
 
 
@@ -166,6 +167,10 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
+    if world > 1:   # one rank simulates, the others read the file
+        if rank == 0:
+            make_reads(wl, args.scale)
+        dist.barrier()
     reads_path = make_reads(wl, args.scale)
     cfg = pu.load_cfg(os.path.join(pu.CFG_DIR, wl["cfg"]))
     k = wl["k"]
