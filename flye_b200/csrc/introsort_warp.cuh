@@ -178,8 +178,13 @@ FG_DEV void seqIntrosort(Elem* a, long n) {
 // ---- the data-parallel Hoare partition ---------------------------------------------------------------
 // Partitions arr[f,l) (l-f > 16) exactly like
 //     __move_median_to_first(f, f+1, f+(l-f)/2, l-1); return __unguarded_partition(f+1, l, f);
-// and returns the cut.  All control flow is warp-uniform.
-FG_DEV long warpPartition(Elem* arr, long f, long l) {
+// and returns the cut.  All control flow is warp-uniform.  `tab` is 64 bytes of per-warp scratch (shared memory on
+// the device): rank -> lane tables that let lane m find the partner of its stop without searching bit masks.
+typedef int idx_t;   // positions inside one sorted array (< 2^31 elements)
+
+FG_DEV idx_t warpPartition(Elem* arr, idx_t f, idx_t l, unsigned char* tab) {
+    unsigned char* tabL = tab;        // tabL[m] = lane of the m-th lowest pending ">= pivot" stop
+    unsigned char* tabR = tab + 32;   // tabR[m] = lane of the m-th highest pending "<= pivot" stop
 #ifndef FG_WARP_HOST
     if (fg::laneId() == 0)
 #endif
@@ -187,11 +192,11 @@ FG_DEV long warpPartition(Elem* arr, long f, long l) {
     FG_SYNCWARP();
     const unsigned long long p = arr[f].key;
 
-    long lo = f + 1, hi = l;        // untouched middle [lo,hi)
-    long s = 0;                     // pairs swapped so far
-    long lastR = -1;                // position of R_{s-1}
-    long firstGeAbove = l;          // lowest position with original value >= p in retired right chunks
-    long Lb = 0, Rb = 0;            // base position of the current left / right chunk
+    idx_t lo = f + 1, hi = l;        // untouched middle [lo,hi)
+    idx_t s = 0;                     // pairs swapped so far
+    idx_t lastR = -1;                // position of R_{s-1}
+    idx_t firstGeAbove = l;          // lowest position with original value >= p in retired right chunks
+    idx_t Lb = 0, Rb = 0;            // base position of the current left / right chunk
     uint32_t geL = 0, leL = 0, pendL = 0, geR = 0, leR = 0, pendR = 0;
     bool haveR = false;
     FG_LANEVAR(Elem, eL);
@@ -210,7 +215,7 @@ FG_DEV long warpPartition(Elem* arr, long f, long l) {
     for (;;) {
         if (pendL == 0 && lo < hi) {
             Lb = lo;
-            const long nL = (hi - lo < 32) ? (hi - lo) : 32;
+            const idx_t nL = (hi - lo < 32) ? (hi - lo) : 32;
             if (pfLok && nL == 32) { FG_FOR_LANES FG_L(eL) = FG_L(pfL); FG_END_LANES }
             else { FG_FOR_LANES if (lane < nL) FG_L(eL) = arr[Lb + lane]; FG_END_LANES }
             lo += nL;
@@ -222,7 +227,7 @@ FG_DEV long warpPartition(Elem* arr, long f, long l) {
         }
         if (pendR == 0 && lo < hi) {
             if (haveR && geR) firstGeAbove = Rb + FG_CTZ(geR);
-            const long nR = (hi - lo < 32) ? (hi - lo) : 32;
+            const idx_t nR = (hi - lo < 32) ? (hi - lo) : 32;
             Rb = hi - nR;
             if (pfRok && nR == 32) { FG_FOR_LANES FG_L(eR) = FG_L(pfR); FG_END_LANES }
             else { FG_FOR_LANES if (lane < nR) FG_L(eR) = arr[Rb + lane]; FG_END_LANES }
@@ -239,20 +244,22 @@ FG_DEV long warpPartition(Elem* arr, long f, long l) {
         if (c > 0) {
             // pair m: m-th lowest pending L  <->  m-th highest pending R   (every pending L < every pending R)
             FG_FOR_LANES
-                if (pendL >> lane & 1) {
-                    int m = FG_POPC(pendL & ((1u << lane) - 1u));
-                    if (m < c) arr[Rb + nthHighBit(pendR, m)] = FG_L(eL);
-                }
-                if (pendR >> lane & 1) {
-                    int m = FG_POPC(pendR & ~((2u << lane) - 1u));
-                    if (m < c) arr[Lb + nthLowBit(pendL, m)] = FG_L(eR);
-                }
+                if (pendL >> lane & 1) tabL[FG_POPC(pendL & ((1u << lane) - 1u))] = (unsigned char)lane;
+                if (pendR >> lane & 1) tabR[FG_POPC(pendR & ~((2u << lane) - 1u))] = (unsigned char)lane;
             FG_END_LANES
-            lastR = Rb + nthHighBit(pendR, c - 1);
-            // drop the c lowest bits of pendL and the c highest of pendR
-            if (c == cL) pendL = 0; else pendL &= ~((2u << nthLowBit(pendL, c - 1)) - 1u);
-            if (c == cR) pendR = 0; else pendR &= ((1u << nthHighBit(pendR, c - 1)) - 1u);
+            FG_SYNCWARP();
+            FG_FOR_LANES
+                if (pendL >> lane & 1) { const int m = FG_POPC(pendL & ((1u << lane) - 1u)); if (m < c) arr[Rb + tabR[m]] = FG_L(eL); }
+                if (pendR >> lane & 1) { const int m = FG_POPC(pendR & ~((2u << lane) - 1u)); if (m < c) arr[Lb + tabL[m]] = FG_L(eR); }
+            FG_END_LANES
+            lastR = Rb + tabR[c - 1];
+            // drop the c lowest stops of pendL and the c highest of pendR
+            uint32_t keepL, keepR;
+            FG_BALLOT(keepL, (pendL >> lane & 1) && FG_POPC(pendL & ((1u << lane) - 1u)) >= c);
+            FG_BALLOT(keepR, (pendR >> lane & 1) && FG_POPC(pendR & ~((2u << lane) - 1u)) >= c);
+            pendL = keepL; pendR = keepR;
             s += c;
+            FG_SYNCWARP();   // the tables are rewritten by the next round
         }
         if (lo < hi && (pendL == 0 || pendR == 0)) continue;
         break;
@@ -260,42 +267,33 @@ FG_DEV long warpPartition(Elem* arr, long f, long l) {
     FG_SYNCWARP();
 
     // The chunks have met (lo == hi).  Remaining pairs, if any, lie inside ONE chunk.
-    const long INF = l + 1;
-    long Ls;   // position of L_s, the first unpaired ">= pivot" stop in the original ordering
-    if (pendL != 0) {
-        // unpaired L stops remain in the current left chunk; the next R stops are that chunk's
-        // "<= pivot" positions, descending
-        const int nl = FG_POPC(pendL), nr = FG_POPC(leL);
+    const idx_t INF = l + 1;
+    idx_t Ls;   // position of L_s, the first unpaired ">= pivot" stop in the original ordering
+    if (pendL != 0 || pendR != 0) {
+        // case A (pendL): unpaired L stops remain in the current left chunk; the next R stops are that chunk's
+        //   "<= pivot" positions, descending.
+        // case B (pendR): unpaired R stops remain in the current right chunk; the next L stops are that chunk's
+        //   ">= pivot" positions, ascending, then those of the chunks above it.
+        const bool caseA = pendL != 0;
+        const uint32_t maskL = caseA ? pendL : geR, maskR = caseA ? leL : pendR;
+        const idx_t base = caseA ? Lb : Rb;
+        const int nl = FG_POPC(maskL), nr = FG_POPC(maskR);
+        FG_FOR_LANES
+            if (maskL >> lane & 1) tabL[FG_POPC(maskL & ((1u << lane) - 1u))] = (unsigned char)lane;
+            if (maskR >> lane & 1) tabR[FG_POPC(maskR & ~((2u << lane) - 1u))] = (unsigned char)lane;
+        FG_END_LANES
+        FG_SYNCWARP();
         uint32_t ok;
-        FG_BALLOT(ok, lane < nl && lane < nr && nthLowBit(pendL, lane) < nthHighBit(leL, lane));
+        FG_BALLOT(ok, lane < nl && lane < nr && tabL[lane] < tabR[lane]);
         const int e = FG_POPC(ok);
         FG_FOR_LANES
-            const bool isL = pendL >> lane & 1, isR = leL >> lane & 1;
-            const int mL = FG_POPC(pendL & ((1u << lane) - 1u));
-            const int mR = FG_POPC(leL & ~((2u << lane) - 1u));
-            if (isL && mL < e) arr[Lb + nthHighBit(leL, mL)] = FG_L(eL);
-            if (isR && mR < e) arr[Lb + nthLowBit(pendL, mR)] = FG_L(eL);
+            const Elem mine = caseA ? FG_L(eL) : FG_L(eR);
+            if (maskL >> lane & 1) { const int m = FG_POPC(maskL & ((1u << lane) - 1u)); if (m < e) arr[base + tabR[m]] = mine; }
+            if (maskR >> lane & 1) { const int m = FG_POPC(maskR & ~((2u << lane) - 1u)); if (m < e) arr[base + tabL[m]] = mine; }
         FG_END_LANES
         s += e;
-        if (e > 0) lastR = Lb + nthHighBit(leL, e - 1);
-        Ls = (e < nl) ? Lb + nthLowBit(pendL, e) : INF;
-    } else if (pendR != 0) {
-        // unpaired R stops remain in the current right chunk; the next L stops are that chunk's
-        // ">= pivot" positions, ascending, then those of the chunks above it
-        const int nr = FG_POPC(pendR), nl = FG_POPC(geR);
-        uint32_t ok;
-        FG_BALLOT(ok, lane < nl && lane < nr && nthLowBit(geR, lane) < nthHighBit(pendR, lane));
-        const int e = FG_POPC(ok);
-        FG_FOR_LANES
-            const bool isL = geR >> lane & 1, isR = pendR >> lane & 1;
-            const int mL = FG_POPC(geR & ((1u << lane) - 1u));
-            const int mR = FG_POPC(pendR & ~((2u << lane) - 1u));
-            if (isL && mL < e) arr[Rb + nthHighBit(pendR, mL)] = FG_L(eR);
-            if (isR && mR < e) arr[Rb + nthLowBit(geR, mR)] = FG_L(eR);
-        FG_END_LANES
-        s += e;
-        if (e > 0) lastR = Rb + nthHighBit(pendR, e - 1);
-        Ls = (e < nl) ? Rb + nthLowBit(geR, e) : firstGeAbove;
+        if (e > 0) lastR = base + tabR[e - 1];
+        Ls = (e < nl) ? base + tabL[e] : (caseA ? INF : firstGeAbove);
     } else {
         Ls = (haveR && geR) ? Rb + FG_CTZ(geR) : firstGeAbove;
     }
@@ -316,11 +314,11 @@ FG_DEV long warpPartition(Elem* arr, long f, long l) {
 struct NoSink { FG_DEV void operator()(long, long, int) const {} };
 
 template <class Sink>
-FG_DEV void warpIntrosortRange(Elem* arr, long f0, long l0, int d0, long small, Sink& sink) {
+FG_DEV void warpIntrosortRange(Elem* arr, idx_t f0, idx_t l0, int d0, idx_t small, Sink& sink, unsigned char* tab) {
     if (l0 - f0 < 2) return;
-    FG_LANEVAR(long, stF0); FG_LANEVAR(long, stL0); FG_LANEVAR(int, stD0);   // stack entries 0..31
-    FG_LANEVAR(long, stF1); FG_LANEVAR(long, stL1); FG_LANEVAR(int, stD1);   // stack entries 32..63
-    FG_LANEVAR(long, lfF);  FG_LANEVAR(long, lfL);                           // pending leaves
+    FG_LANEVAR(idx_t, stF0); FG_LANEVAR(idx_t, stL0); FG_LANEVAR(int, stD0);   // stack entries 0..31
+    FG_LANEVAR(idx_t, stF1); FG_LANEVAR(idx_t, stL1); FG_LANEVAR(int, stD1);   // stack entries 32..63
+    FG_LANEVAR(idx_t, lfF);  FG_LANEVAR(idx_t, lfL);                           // pending leaves
     int sp = 0, nLeaf = 0;
     FG_FOR_LANES FG_L(lfF) = 0; FG_L(lfL) = 0; FG_END_LANES
 
@@ -331,15 +329,15 @@ FG_DEV void warpIntrosortRange(Elem* arr, long f0, long l0, int d0, long small, 
         nLeaf = 0;
     };
     // a finished-partitioning range: leaf (<= 16) or, in two-level mode, a task for the second kernel
-    auto retire = [&](long f, long l, int d) {
+    auto retire = [&](idx_t f, idx_t l, int d) {
         if (l - f < 2) return;
         if (small > 0) { sink(f, l, d); return; }
         FG_FOR_LANES if (lane == nLeaf) { FG_L(lfF) = f; FG_L(lfL) = l; } FG_END_LANES
         if (++nLeaf == 32) flushLeaves();
     };
-    const long stopAt = small > 16 ? small : 16;   // ranges of at most this many elements are retired
+    const idx_t stopAt = small > 16 ? small : 16;   // ranges of at most this many elements are retired
 
-    long f = f0, l = l0;
+    idx_t f = f0, l = l0;
     int d = d0;
     bool have = true;
     while (have) {
@@ -358,7 +356,7 @@ FG_DEV void warpIntrosortRange(Elem* arr, long f0, long l0, int d0, long small, 
                 break;
             }
             --d;
-            const long cut = warpPartition(arr, f, l);
+            const idx_t cut = warpPartition(arr, f, l, tab);
             if (l - cut > stopAt) {   // "recurse" on the right part: push
                 FG_FOR_LANES
                     if (lane == (sp & 31)) {
@@ -375,7 +373,7 @@ FG_DEV void warpIntrosortRange(Elem* arr, long f0, long l0, int d0, long small, 
         else {
             --sp;
 #ifndef FG_WARP_HOST
-            long tf = sp < 32 ? stF0 : stF1, tl = sp < 32 ? stL0 : stL1; int td = sp < 32 ? stD0 : stD1;
+            idx_t tf = sp < 32 ? stF0 : stF1, tl = sp < 32 ? stL0 : stL1; int td = sp < 32 ? stD0 : stD1;
             f = __shfl_sync(0xffffffffu, tf, sp & 31);
             l = __shfl_sync(0xffffffffu, tl, sp & 31);
             d = __shfl_sync(0xffffffffu, td, sp & 31);
@@ -396,10 +394,10 @@ FG_DEV int introsortDepth(long n) {   // std::__lg(n) * 2
 }
 
 // std::sort(arr, arr + n) in one go
-FG_DEV void warpIntrosort(Elem* arr, long n) {
+FG_DEV void warpIntrosort(Elem* arr, idx_t n, unsigned char* tab) {
     if (n < 2) return;
     NoSink none;
-    warpIntrosortRange(arr, 0, n, introsortDepth(n), 0, none);
+    warpIntrosortRange(arr, 0, n, introsortDepth(n), 0, none, tab);
 }
 
 }  // namespace fg

@@ -182,6 +182,7 @@ __global__ void __launch_bounds__(256) sortSeedKernel(const Seg* __restrict__ se
 __global__ void __launch_bounds__(128) sortLevelKernel(Elem* __restrict__ arr, const SortTask* __restrict__ in, const uint32_t* __restrict__ nInPtr,
                                                        uint32_t capBig, SortTask* __restrict__ out, uint32_t* __restrict__ nOut,
                                                        SortTask* __restrict__ small, uint32_t* __restrict__ nSmall, uint32_t capSmall) {
+    __shared__ unsigned char tabs[4][64];
     const uint32_t w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (w >= min(*nInPtr, capBig)) return;
     const SortTask t = in[w];
@@ -190,7 +191,7 @@ __global__ void __launch_bounds__(128) sortLevelKernel(Elem* __restrict__ arr, c
         if (laneId() == 0) seqHeapSort(a, (long)t.n);
         return;
     }
-    const long cut = warpPartition(a, 0, (long)t.n);
+    const idx_t cut = warpPartition(a, 0, (idx_t)t.n, tabs[threadIdx.x >> 5]);
     if (laneId() == 0) {
         emitRange(t.start, (uint32_t)cut, t.depth - 1, out, nOut, capBig, small, nSmall, capSmall);
         emitRange(t.start + (uint32_t)cut, t.n - (uint32_t)cut, t.depth - 1, out, nOut, capBig, small, nSmall, capSmall);
@@ -200,7 +201,9 @@ __global__ void __launch_bounds__(128) sortLevelKernel(Elem* __restrict__ arr, c
 __global__ void __launch_bounds__(128) sortSmallKernel(Elem* __restrict__ arr, const SortTask* __restrict__ tasks,
                                                        const uint32_t* __restrict__ taskCounter, uint32_t taskCap, uint32_t* __restrict__ next) {
     extern __shared__ __align__(16) unsigned char smemRaw[];
+    __shared__ unsigned char tabs[4][64];
     Elem* sm = reinterpret_cast<Elem*>(smemRaw) + (threadIdx.x >> 5) * SORT_SMALL;
+    unsigned char* tab = tabs[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
     const uint32_t nTasks = min(*taskCounter, taskCap);
     for (;;) {
@@ -213,7 +216,7 @@ __global__ void __launch_bounds__(128) sortSmallKernel(Elem* __restrict__ arr, c
         for (uint32_t i = lane; i < k.n; i += 32) sm[i] = g[i];
         __syncwarp();
         NoSink none;
-        warpIntrosortRange(sm, 0, (long)k.n, k.depth, 0, none);
+        warpIntrosortRange(sm, 0, (idx_t)k.n, k.depth, 0, none, tab);
         __syncwarp();
         for (uint32_t i = lane; i < k.n; i += 32) g[i] = sm[i];
         __syncwarp();

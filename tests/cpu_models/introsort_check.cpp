@@ -18,21 +18,22 @@ static long g_small = 0;   // > 0: two-level mode (top pass hands ranges <= g_sm
 static bool checkOne(std::vector<fg::Elem> a, const char* what) {
     std::vector<fg::Elem> ref = a;
     std::sort(ref.begin(), ref.end(), [](const fg::Elem& x, const fg::Elem& y) { return x.key < y.key; });
+    unsigned char tab[64];
     if (g_small > 0 && a.size() > 1) {
         VecSink sink;
-        fg::warpIntrosortRange(a.data(), 0, (long)a.size(), fg::introsortDepth((long)a.size()), g_small, sink);
+        fg::warpIntrosortRange(a.data(), 0, (int)a.size(), fg::introsortDepth((long)a.size()), (int)g_small, sink, tab);
         // second pass on a staged copy of each task, in reverse order to show that the order is irrelevant
         for (size_t t = sink.tasks.size(); t-- > 0;) {
             auto& T = sink.tasks[t];
             std::vector<fg::Elem> tmp(a.begin() + T.f, a.begin() + T.l);
             fg::NoSink none;
-            fg::warpIntrosortRange(tmp.data(), 0, (long)tmp.size(), T.d, 0, none);
+            fg::warpIntrosortRange(tmp.data(), 0, (int)tmp.size(), T.d, 0, none, tab);
             std::copy(tmp.begin(), tmp.end(), a.begin() + T.f);
         }
     } else if (g_small < 0)
         fg::seqIntrosort(a.data(), (long)a.size());
     else
-        fg::warpIntrosort(a.data(), (long)a.size());
+        fg::warpIntrosort(a.data(), (int)a.size(), tab);
     for (size_t i = 0; i < a.size(); ++i)
         if (a[i].key != ref[i].key || a[i].val != ref[i].val) {
             printf("MISMATCH %s n=%zu at %zu: got (%llu,%u) want (%llu,%u)\n", what, a.size(), i, a[i].key, a[i].val,
