@@ -152,6 +152,29 @@ FG_DEV long seqUnguardedPartition(Elem* a, long first, long last, long pivot) { 
         ++first;
     }
 }
+// literal __introsort_loop + leaf insertion sorts on a[f,l) with an INHERITED depth budget (one thread).  STACK bounds the
+// number of pending right halves (> 16 elements each, pairwise disjoint): (l-f)/17 at most.
+template <int STACK>
+FG_DEV void seqIntrosortRange(Elem* a, long f0, long l0, int d0) {
+    if (l0 - f0 < 2) return;
+    long stF[STACK], stL[STACK]; int stD[STACK];
+    int sp = 0;
+    long f = f0, l = l0; int d = d0;
+    for (;;) {
+        while (l - f > 16) {
+            if (d == 0) { seqHeapSort(a + f, l - f); break; }
+            --d;
+            seqMedianToFirst(a, f, f + 1, f + (l - f) / 2, l - 1);
+            const long cut = seqUnguardedPartition(a, f + 1, l, f);
+            if (l - cut > 16) { stF[sp] = cut; stL[sp] = l; stD[sp] = d; ++sp; }
+            l = cut;
+        }
+        if (sp == 0) break;
+        --sp; f = stF[sp]; l = stL[sp]; d = stD[sp];
+    }
+    seqInsertionSort(a, f0, l0);   // stable; never moves an element across a cut
+}
+
 FG_DEV void seqIntrosort(Elem* a, long n) {
     if (n < 2) return;
     if (n > 16) {
@@ -312,19 +335,26 @@ FG_DEV idx_t warpPartition(Elem* arr, idx_t f, idx_t l, unsigned char* tab) {
 // small = 0 on the staged copy).  Ranges are disjoint, so the order in which they are finished is irrelevant
 // to the resulting permutation.
 struct NoSink { FG_DEV void operator()(long, long, int) const {} };
+#ifndef FG_WARP_MINI
+#define FG_WARP_MINI 48
+#endif
+static constexpr int WARP_MINI = FG_WARP_MINI;
 
 template <class Sink>
 FG_DEV void warpIntrosortRange(Elem* arr, idx_t f0, idx_t l0, int d0, idx_t small, Sink& sink, unsigned char* tab) {
     if (l0 - f0 < 2) return;
     FG_LANEVAR(idx_t, stF0); FG_LANEVAR(idx_t, stL0); FG_LANEVAR(int, stD0);   // stack entries 0..31
     FG_LANEVAR(idx_t, stF1); FG_LANEVAR(idx_t, stL1); FG_LANEVAR(int, stD1);   // stack entries 32..63
-    FG_LANEVAR(idx_t, lfF);  FG_LANEVAR(idx_t, lfL);                           // pending leaves
+    FG_LANEVAR(idx_t, lfF);  FG_LANEVAR(idx_t, lfL); FG_LANEVAR(int, lfD);    // pending mini ranges
     int sp = 0, nLeaf = 0;
-    FG_FOR_LANES FG_L(lfF) = 0; FG_L(lfL) = 0; FG_END_LANES
+    FG_FOR_LANES FG_L(lfF) = 0; FG_L(lfL) = 0; FG_L(lfD) = 0; FG_END_LANES
 
+    // Ranges of at most WARP_MINI elements are not worth a warp-wide partition (most lanes would idle): they are
+    // queued and finished 32 at a time, one LANE per range, by the literal sequential algorithm with the range's
+    // inherited depth budget.
     auto flushLeaves = [&]() {
         FG_SYNCWARP();
-        FG_FOR_LANES if (lane < nLeaf) seqInsertionSort(arr, FG_L(lfF), FG_L(lfL)); FG_END_LANES
+        FG_FOR_LANES if (lane < nLeaf) seqIntrosortRange<WARP_MINI / 17 + 1>(arr, FG_L(lfF), FG_L(lfL), FG_L(lfD)); FG_END_LANES
         FG_SYNCWARP();
         nLeaf = 0;
     };
@@ -332,10 +362,10 @@ FG_DEV void warpIntrosortRange(Elem* arr, idx_t f0, idx_t l0, int d0, idx_t smal
     auto retire = [&](idx_t f, idx_t l, int d) {
         if (l - f < 2) return;
         if (small > 0) { sink(f, l, d); return; }
-        FG_FOR_LANES if (lane == nLeaf) { FG_L(lfF) = f; FG_L(lfL) = l; } FG_END_LANES
+        FG_FOR_LANES if (lane == nLeaf) { FG_L(lfF) = f; FG_L(lfL) = l; FG_L(lfD) = d; } FG_END_LANES
         if (++nLeaf == 32) flushLeaves();
     };
-    const idx_t stopAt = small > 16 ? small : 16;   // ranges of at most this many elements are retired
+    const idx_t stopAt = small > WARP_MINI ? small : WARP_MINI;   // ranges of at most this many elements are retired
 
     idx_t f = f0, l = l0;
     int d = d0;

@@ -414,16 +414,20 @@ __global__ void __launch_bounds__(128) chainDpKernel(const Elem* __restrict__ hi
             const int32_t jd = abs(dc - de);
             const int32_t gap = jd > 100 ? 2 * jd : (jd >> 1);            // int32(float(LG_GAP|SM_GAP) * jd), :299
             const int32_t s = ok ? sj + min(min(dc, de), k) - gap : INT32_MIN;
-            int32_t pm = s;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { int32_t t = __shfl_up_sync(0xffffffffu, pm, d); if (lane >= d) pm = max(pm, t); }
-            int32_t excl = __shfl_up_sync(0xffffffffu, pm, 1);
-            if (lane == 0) excl = INT32_MIN;
-            excl = max(excl, best);
-            const bool improved = ok && s > excl;
-            const bool brk = (improved && jd == 0 && dc < k) || (in && (extSorted ? de : dc) > P.maxJump);
-            const uint32_t bm = __ballot_sync(0xffffffffu, brk);
-            const int stopLane = bm ? (__ffs(bm) - 1) : 31;
+            // second break rule (sorted-axis distance) first: nothing beyond its first lane is ever evaluated
+            const uint32_t far = __ballot_sync(0xffffffffu, in && (extSorted ? de : dc) > P.maxJump);
+            int stopLane = far ? (__ffs(far) - 1) : 31;
+            bool brk = far != 0;
+            // first break rule: a predecessor with jumpDiv == 0 and dc < k ends the scan IF it improves the running
+            // maximum.  Such predecessors are rare, so instead of a prefix-max scan over all lanes each candidate is
+            // tested with one warp reduction over the lanes before it.
+            uint32_t pot = __ballot_sync(0xffffffffu, ok && jd == 0 && dc < k) & ((2u << stopLane) - 1u);
+            while (pot) {
+                const int t = __ffs(pot) - 1;
+                const int32_t prior = max(best, __reduce_max_sync(0xffffffffu, lane < t ? s : INT32_MIN));
+                if (__shfl_sync(0xffffffffu, s, t) > prior) { stopLane = t; brk = true; break; }
+                pot &= pot - 1;
+            }
             const bool part = ok && lane <= stopLane;
             const int32_t mx = __reduce_max_sync(0xffffffffu, part ? s : INT32_MIN);
             if (mx > best) {
@@ -431,7 +435,7 @@ __global__ void __launch_bounds__(128) chainDpKernel(const Elem* __restrict__ hi
                 best = mx; bestId = jb - (__ffs(wm) - 1);
             }
             cells += min(jb + 1, stopLane + 1);
-            stop = bm != 0;
+            stop = brk;
         }
         const int32_t sci = max(best, k);
         if (lane == l0) { wC = curN; wE = extN; wS = sci; }   // match i replaces match i-32 in the window
