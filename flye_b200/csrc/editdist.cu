@@ -59,19 +59,24 @@ __global__ void __launch_bounds__(256) hpcKernel(const uint64_t* __restrict__ se
 // Exact global edit distance of a[0,n) and b[0,m).  fr[k] = furthest row i reached on diagonal k = j - i with
 // the current number of edits; -1 = unreachable.  One warp; the two wavefront arrays live in global scratch
 // (index k + n).
+static constexpr int WFA_SHORT = 8;
+
 __device__ int wfaEditDistance(const uint8_t* __restrict__ a, int n, const uint8_t* __restrict__ b, int m, int* __restrict__ wfA,
                                int* __restrict__ wfB) {
     const int lane = threadIdx.x & 31;
     if (n == 0) return m;
     if (m == 0) return n;
     int* prev = wfA; int* cur = wfB;
-    {   // s = 0
+    {   // s = 0: common prefix, 32 bases per step
+        const int lim = min(n, m);
         int i = 0;
-        if (lane == 0) {
-            while (i < n && i < m && a[i] == b[i]) ++i;
-            prev[n] = i;
+        for (;;) {
+            const int j = i + lane;
+            const uint32_t mm = __ballot_sync(0xffffffffu, j >= lim || a[j] != b[j]);
+            if (mm) { i += __ffs(mm) - 1; break; }
+            i += 32;
         }
-        i = __shfl_sync(0xffffffffu, i, 0);
+        if (lane == 0) prev[n] = i;
         if (m == n && i >= n) return 0;
     }
     __syncwarp();
@@ -82,18 +87,41 @@ __device__ int wfaEditDistance(const uint8_t* __restrict__ a, int n, const uint8
         bool done = false;
         for (int k0 = lo; k0 <= hi; k0 += 32) {
             const int k = k0 + lane;
+            int best = -1;
+            bool longRun = false;
             if (k <= hi) {
-                int best = -1;
                 if (k - 1 >= plo && k - 1 <= phi) { const int i = prev[k - 1 + n]; if (i >= 0 && i + k <= m) best = i; }
                 if (k >= plo && k <= phi) { const int i = prev[k + n]; if (i >= 0 && i + 1 <= n && i + k + 1 <= m) best = max(best, i + 1); }
                 if (k + 1 >= plo && k + 1 <= phi) { const int i = prev[k + 1 + n]; if (i >= 0 && i + 1 <= n) best = max(best, i + 1); }
-                if (best >= 0) {
+                if (best >= 0) {   // short extension by the lane itself (off-diagonals stop after ~1 base)
                     const uint8_t* pa = a + best; const uint8_t* pb = b + best + k;
-                    const int lim = min(n - best, m - best - k);
+                    const int lim = min(min(n - best, m - best - k), WFA_SHORT);
                     int e = 0;
                     while (e < lim && pa[e] == pb[e]) ++e;
                     best += e;
+                    longRun = e == WFA_SHORT;
                 }
+            }
+            // the few diagonals that keep matching (the true alignment path) are extended by the whole warp, 32 bases
+            // per step, instead of one lane crawling alone
+            uint32_t lm = __ballot_sync(0xffffffffu, longRun);
+            while (lm) {
+                const int src = __ffs(lm) - 1;
+                lm &= lm - 1;
+                int bb = __shfl_sync(0xffffffffu, best, src);
+                const int kk = k0 + src;
+                const int lim = min(n - bb, m - bb - kk);
+                int e = 0;
+                for (;;) {
+                    const int i = e + lane;
+                    const bool mismatch = i >= lim || a[bb + i] != b[bb + kk + i];
+                    const uint32_t mm = __ballot_sync(0xffffffffu, mismatch);
+                    if (mm) { e += __ffs(mm) - 1; break; }
+                    e += 32;
+                }
+                if (lane == src) best = bb + e;
+            }
+            if (k <= hi) {
                 cur[k + n] = best;
                 if (k == target && best >= n) done = true;
             }

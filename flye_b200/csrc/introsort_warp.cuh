@@ -37,6 +37,7 @@
 #define FG_SYNCWARP() __syncwarp()
 #define FG_POPC(x) __popc(x)
 #define FG_CTZ(x) (__ffs(x) - 1)
+#define FG_PREFETCH_L2(ptr) asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr))
 #else
 #include <algorithm>
 namespace fg {
@@ -58,6 +59,7 @@ inline int nthHighBit(uint32_t mask, int n) {
 #define FG_SYNCWARP() ((void)0)
 #define FG_POPC(x) __builtin_popcount(x)
 #define FG_CTZ(x) __builtin_ctz(x)
+#define FG_PREFETCH_L2(ptr) ((void)0)
 #endif
 
 namespace fg {
@@ -205,7 +207,10 @@ FG_DEV void seqIntrosort(Elem* a, long n) {
 // the device): rank -> lane tables that let lane m find the partner of its stop without searching bit masks.
 typedef int idx_t;   // positions inside one sorted array (< 2^31 elements)
 
-FG_DEV idx_t warpPartition(Elem* arr, idx_t f, idx_t l, unsigned char* tab) {
+// `inGlobal`: arr lives in global memory — lines a few chunks ahead of both cursors are pulled into L2 early.
+static constexpr idx_t PF_AHEAD = 4 * 32;   // elements (4 chunks = 2 KB) between the register prefetch and the L2 prefetch
+
+FG_DEV idx_t warpPartition(Elem* arr, idx_t f, idx_t l, unsigned char* tab, bool inGlobal = false) {
     unsigned char* tabL = tab;        // tabL[m] = lane of the m-th lowest pending ">= pivot" stop
     unsigned char* tabR = tab + 32;   // tabR[m] = lane of the m-th highest pending "<= pivot" stop
 #ifndef FG_WARP_HOST
@@ -234,6 +239,14 @@ FG_DEV idx_t warpPartition(Elem* arr, idx_t f, idx_t l, unsigned char* tab) {
         FG_FOR_LANES FG_L(pfL) = arr[lo + lane]; FG_L(pfR) = arr[hi - 32 + lane]; FG_END_LANES
         pfLok = pfRok = true;
     }
+    if (inGlobal) {
+        FG_FOR_LANES
+            for (idx_t a = 32; a <= PF_AHEAD; a += 32) {
+                if (lo + a + lane < hi) FG_PREFETCH_L2(arr + lo + a + lane);
+                if (hi - 32 - a + lane >= lo) FG_PREFETCH_L2(arr + hi - 32 - a + lane);
+            }
+        FG_END_LANES
+    }
 
     for (;;) {
         if (pendL == 0 && lo < hi) {
@@ -244,6 +257,7 @@ FG_DEV idx_t warpPartition(Elem* arr, idx_t f, idx_t l, unsigned char* tab) {
             lo += nL;
             pfLok = hi - lo >= 32;
             if (pfLok) { FG_FOR_LANES FG_L(pfL) = arr[lo + lane]; FG_END_LANES }
+            if (inGlobal) { FG_FOR_LANES if (lo + PF_AHEAD + lane < hi) FG_PREFETCH_L2(arr + lo + PF_AHEAD + lane); FG_END_LANES }
             FG_BALLOT(geL, lane < nL && FG_L(eL).key >= p);
             FG_BALLOT(leL, lane < nL && FG_L(eL).key <= p);
             pendL = geL;
@@ -257,6 +271,7 @@ FG_DEV idx_t warpPartition(Elem* arr, idx_t f, idx_t l, unsigned char* tab) {
             hi = Rb;
             pfRok = hi - lo >= 32;
             if (pfRok) { FG_FOR_LANES FG_L(pfR) = arr[hi - 32 + lane]; FG_END_LANES }
+            if (inGlobal) { FG_FOR_LANES if (hi - 32 - PF_AHEAD + lane >= lo) FG_PREFETCH_L2(arr + hi - 32 - PF_AHEAD + lane); FG_END_LANES }
             FG_BALLOT(geR, lane < nR && FG_L(eR).key >= p);
             FG_BALLOT(leR, lane < nR && FG_L(eR).key <= p);
             pendR = leR;

@@ -23,6 +23,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <thread>
 
 namespace fg {
 
@@ -154,34 +155,38 @@ __global__ void __launch_bounds__(256) expandKernel(const uint32_t* __restrict__
 //                    introsort there and write it back — most recursion levels run at shared-memory latency and
 //                    the tasks balance the load across the chip whatever the segment-length distribution is.
 // ------------------------------------------------------------------------------------------------
-static constexpr int SORT_SMALL = 1024;
+static constexpr int SORT_SMALL_MAX = 2048;
+static int sortSmallN() {   // elements per shared-memory task (FG_SORT_SMALL, default 512: 8 KB per warp, 24 resident warps per SM)
+    static int v = [] { const char* e = getenv("FG_SORT_SMALL"); int x = e ? atoi(e) : 512; return x < 64 ? 64 : (x > SORT_SMALL_MAX ? SORT_SMALL_MAX : x); }();
+    return v;
+}
 struct Seg { uint32_t start, n; };
 struct SortTask { uint32_t start, n; int depth; };
 
 // counters of one segmented sort: [0] nSegs (input)  [1] nSmall  [2] next small task  [3] nBig ping  [4] nBig pong
 __device__ __forceinline__ void emitRange(uint32_t start, uint32_t n, int depth, SortTask* big, uint32_t* nBig, uint32_t capBig,
-                                          SortTask* small, uint32_t* nSmall, uint32_t capSmall) {
+                                          SortTask* small, uint32_t* nSmall, uint32_t capSmall, uint32_t smallN) {
     if (n < 2) return;
     SortTask k; k.start = start; k.n = n; k.depth = depth;
-    if (n > (uint32_t)SORT_SMALL) { const uint32_t t = atomicAdd(nBig, 1u); if (t < capBig) big[t] = k; }
+    if (n > smallN) { const uint32_t t = atomicAdd(nBig, 1u); if (t < capBig) big[t] = k; }
     else { const uint32_t t = atomicAdd(nSmall, 1u); if (t < capSmall) small[t] = k; }
 }
 
 // every segment becomes one task: a "big" one (partitioned level by level in global memory) or a "small" one
 __global__ void __launch_bounds__(256) sortSeedKernel(const Seg* __restrict__ segs, const uint32_t* __restrict__ nSegsPtr, SortTask* __restrict__ big,
                                                       uint32_t* __restrict__ nBig, uint32_t capBig, SortTask* __restrict__ small,
-                                                      uint32_t* __restrict__ nSmall, uint32_t capSmall) {
+                                                      uint32_t* __restrict__ nSmall, uint32_t capSmall, uint32_t smallN) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= *nSegsPtr) return;
     const Seg sg = segs[i];
-    emitRange(sg.start, sg.n, introsortDepth((long)sg.n), big, nBig, capBig, small, nSmall, capSmall);
+    emitRange(sg.start, sg.n, introsortDepth((long)sg.n), big, nBig, capBig, small, nSmall, capSmall, smallN);
 }
 
 // one introsort level: every warp partitions one big range (or heap-sorts it when its depth budget is spent,
 // stl_algo.h:1925-1929) and emits the two halves as tasks of the next level / of the shared-memory kernel
 __global__ void __launch_bounds__(128) sortLevelKernel(Elem* __restrict__ arr, const SortTask* __restrict__ in, const uint32_t* __restrict__ nInPtr,
                                                        uint32_t capBig, SortTask* __restrict__ out, uint32_t* __restrict__ nOut,
-                                                       SortTask* __restrict__ small, uint32_t* __restrict__ nSmall, uint32_t capSmall) {
+                                                       SortTask* __restrict__ small, uint32_t* __restrict__ nSmall, uint32_t capSmall, uint32_t smallN) {
     __shared__ unsigned char tabs[4][64];
     const uint32_t w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (w >= min(*nInPtr, capBig)) return;
@@ -191,18 +196,19 @@ __global__ void __launch_bounds__(128) sortLevelKernel(Elem* __restrict__ arr, c
         if (laneId() == 0) seqHeapSort(a, (long)t.n);
         return;
     }
-    const idx_t cut = warpPartition(a, 0, (idx_t)t.n, tabs[threadIdx.x >> 5]);
+    const idx_t cut = warpPartition(a, 0, (idx_t)t.n, tabs[threadIdx.x >> 5], /*inGlobal*/ true);
     if (laneId() == 0) {
-        emitRange(t.start, (uint32_t)cut, t.depth - 1, out, nOut, capBig, small, nSmall, capSmall);
-        emitRange(t.start + (uint32_t)cut, t.n - (uint32_t)cut, t.depth - 1, out, nOut, capBig, small, nSmall, capSmall);
+        emitRange(t.start, (uint32_t)cut, t.depth - 1, out, nOut, capBig, small, nSmall, capSmall, smallN);
+        emitRange(t.start + (uint32_t)cut, t.n - (uint32_t)cut, t.depth - 1, out, nOut, capBig, small, nSmall, capSmall, smallN);
     }
 }
 
 __global__ void __launch_bounds__(128) sortSmallKernel(Elem* __restrict__ arr, const SortTask* __restrict__ tasks,
-                                                       const uint32_t* __restrict__ taskCounter, uint32_t taskCap, uint32_t* __restrict__ next) {
+                                                       const uint32_t* __restrict__ taskCounter, uint32_t taskCap, uint32_t* __restrict__ next,
+                                                       uint32_t smallN) {
     extern __shared__ __align__(16) unsigned char smemRaw[];
     __shared__ unsigned char tabs[4][64];
-    Elem* sm = reinterpret_cast<Elem*>(smemRaw) + (threadIdx.x >> 5) * SORT_SMALL;
+    Elem* sm = reinterpret_cast<Elem*>(smemRaw) + (threadIdx.x >> 5) * smallN;
     unsigned char* tab = tabs[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
     const uint32_t nTasks = min(*taskCounter, taskCap);
@@ -569,7 +575,8 @@ struct SortWorkspace {
     uint32_t capSmall = 0, capBig = 0;
     void ensure(uint64_t totalElems, uint32_t maxSegs) {
         capSmall = (uint32_t)(totalElems / 8 + maxSegs + 4096);
-        capBig = (uint32_t)(totalElems / SORT_SMALL + maxSegs + 64);
+        capBig = (uint32_t)(totalElems / sortSmallN() + maxSegs + 64);
+        capSmall = (uint32_t)(totalElems * (128.0 / sortSmallN()) / 8 + maxSegs + 4096);
         small.ensure(capSmall); bigA.ensure(capBig); bigB.ensure(capBig);
     }
 };
@@ -577,16 +584,18 @@ struct SortWorkspace {
 static void sortSegments(fg_ctx* ctx, Elem* arr, const Seg* dSegs, uint32_t* dCounters, uint32_t maxSegs, SortWorkspace& ws,
                          const char* topName, const char* smallName) {
     static bool attrSet = false;
-    const int smemBytes = 4 * SORT_SMALL * (int)sizeof(Elem);
+    const uint32_t smallN = (uint32_t)sortSmallN();
+    const int smemBytes = 4 * (int)smallN * (int)sizeof(Elem);
     if (!attrSet) {
         FG_CUDA(cudaFuncSetAttribute(sortSmallKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smemBytes));
         attrSet = true;
     }
+    const int blocksPerSm = std::max(1, std::min(8, (int)((220 * 1024) / (smemBytes + 1024))));
     if (!maxSegs) return;
     {
         PhaseTimer pt(ctx, topName);
         sortSeedKernel<<<(maxSegs + 255) / 256, 256, 0, ctx->stream>>>(dSegs, dCounters, ws.bigA.p, dCounters + 3, ws.capBig, ws.small.p,
-                                                                      dCounters + 1, ws.capSmall);
+                                                                      dCounters + 1, ws.capSmall, smallN);
         checkLaunch(ctx, "sortSeedKernel");
         SortTask* in = ws.bigA.p; SortTask* out = ws.bigB.p;
         uint32_t* nIn = dCounters + 3; uint32_t* nOut = dCounters + 4;
@@ -597,14 +606,14 @@ static void sortSegments(fg_ctx* ctx, Elem* arr, const Seg* dSegs, uint32_t* dCo
             if (hIn > ws.capBig) throw Error(FG_ERR_INTERNAL, "sort task list overflow");
             if (!hIn) break;
             FG_CUDA(cudaMemsetAsync(nOut, 0, 4, ctx->stream));
-            sortLevelKernel<<<(hIn + 3) / 4, 128, 0, ctx->stream>>>(arr, in, nIn, ws.capBig, out, nOut, ws.small.p, dCounters + 1, ws.capSmall);
+            sortLevelKernel<<<(hIn + 3) / 4, 128, 0, ctx->stream>>>(arr, in, nIn, ws.capBig, out, nOut, ws.small.p, dCounters + 1, ws.capSmall, smallN);
             checkLaunch(ctx, "sortLevelKernel");
             std::swap(in, out); std::swap(nIn, nOut);
         }
     }
     {
         PhaseTimer pt(ctx, smallName);
-        sortSmallKernel<<<148 * 3, 128, smemBytes, ctx->stream>>>(arr, ws.small.p, dCounters + 1, ws.capSmall, dCounters + 2);
+        sortSmallKernel<<<148 * blocksPerSm, 128, smemBytes, ctx->stream>>>(arr, ws.small.p, dCounters + 1, ws.capSmall, dCounters + 2, smallN);
         checkLaunch(ctx, "sortSmallKernel");
     }
 }
@@ -865,17 +874,12 @@ void overlapsBatch(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, const fg_
     HostTimer hostEpi(ctx, "host_epilogue");
     const float sampleRate = ctx->stats.sample_rate;
     fg_overlap* hOut = pinned.p;
-    size_t pos = 0, wpos = 0;
-    for (uint32_t qi = 0; qi < nQ; ++qi) {
-        ctx->resOffsets[qi] = wpos;
-        size_t detected = 0;
-        while (pos < nRaw && hOut[pos].reserved == qi) {
-            // one target group = run of equal ext_id
-            size_t end = pos;
-            while (end < nRaw && hOut[end].reserved == qi && hOut[end].ext_id == hOut[pos].ext_id) ++end;
-            const bool stop = prm.max_overlaps != 0 && detected >= (size_t)prm.max_overlaps;
-            for (size_t i = pos; i < end && !stop; ++i) {
-                fg_overlap o = hOut[i];
+    // (1) divergence of every record, in parallel over host threads (pure per-record arithmetic with glibc logf)
+    {
+        const unsigned nThreads = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+        auto work = [&](size_t a, size_t b) {
+            for (size_t i = a; i < b; ++i) {
+                fg_overlap& o = hOut[i];
                 const int32_t curRange = o.cur_end - o.cur_begin, extRange = o.ext_end - o.ext_begin;
                 volatile float normLen = std::max(curRange, extRange) - o.filtered_positions;
                 volatile float mr = (float)o.chain_length * sampleRate;
@@ -888,6 +892,27 @@ void overlapsBatch(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, const fg_
                     if (o.edit_distance < 0) o.seq_divergence = 1.0f;
                     else { volatile float dv = (float)o.edit_distance / (size_t)o.aln_len; o.seq_divergence = dv; }
                 }
+            }
+        };
+        if (nRaw < 20000 || nThreads == 1) work(0, nRaw);
+        else {
+            std::vector<std::thread> pool;
+            for (unsigned t = 0; t < nThreads; ++t) pool.emplace_back(work, nRaw * t / nThreads, nRaw * (t + 1) / nThreads);
+            for (auto& th : pool) th.join();
+        }
+    }
+    // (2) threshold and maxOverlaps replay, in place, in query order
+    size_t pos = 0, wpos = 0;
+    for (uint32_t qi = 0; qi < nQ; ++qi) {
+        ctx->resOffsets[qi] = wpos;
+        size_t detected = 0;
+        while (pos < nRaw && hOut[pos].reserved == qi) {
+            // one target group = run of equal ext_id
+            size_t end = pos;
+            while (end < nRaw && hOut[end].reserved == qi && hOut[end].ext_id == hOut[pos].ext_id) ++end;
+            const bool stop = prm.max_overlaps != 0 && detected >= (size_t)prm.max_overlaps;
+            for (size_t i = pos; i < end && !stop; ++i) {
+                fg_overlap o = hOut[i];
                 o.reserved = 0;
                 if (o.seq_divergence < prm.max_divergence) { hOut[wpos++] = o; ++detected; }   // wpos <= i: in place
             }
