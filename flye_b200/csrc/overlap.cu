@@ -367,18 +367,22 @@ __global__ void __launch_bounds__(256) pairPrepKernel(Elem* __restrict__ hits, c
 __device__ __forceinline__ int32_t elemCur(const Elem& e, bool extSorted) { return extSorted ? (int32_t)e.val : (int32_t)(uint32_t)e.key; }
 __device__ __forceinline__ int32_t elemExt(const Elem& e, bool extSorted) { return extSorted ? (int32_t)(uint32_t)e.key : (int32_t)e.val; }
 
-// (b) chaining DP (overlap.cpp:277-323), one warp per pair.  Lanes evaluate 32 predecessors j = i-1, i-2, ... per step
-// in the reference's traversal order; an inclusive prefix max over lanes reproduces "nextScore > maxScore" for
-// every j, which is what the first break rule needs; the first lane that breaks ends the scan.  The last 32
-// matches (cur, ext, score) live in lane registers (match j in lane j%32) and reach the lanes by shuffle, so the
-// common case never waits for memory; longer look-backs continue from global memory.
+// (b) chaining DP (overlap.cpp:277-323): one HALF-WARP (16 lanes) per pair, two pairs per warp.  The lanes of a half
+// evaluate 16 predecessors j = i-1, i-2, ... per step in the reference's traversal order; the first lane that breaks
+// ends the scan.  The last 16 matches (cur, ext, score) live in lane registers (match j in sub-lane j%16) and reach
+// the lanes by shuffle, so the common case (a look-back of ~10 matches) never waits for memory; longer look-backs
+// continue from global memory.  Break rule 1 (jumpDiv == 0 && dc < k on an IMPROVING predecessor) is tested with one
+// warp reduction per candidate instead of a prefix-max scan.  Pairs are visited in order of decreasing size
+// (pairOrder) so that the two halves of a warp finish together.
 __global__ void __launch_bounds__(128) chainDpKernel(const Elem* __restrict__ hits, const PairInfo* __restrict__ pairs, const uint32_t* __restrict__ pairIds,
-                                                     uint32_t nPairs, const uint32_t* __restrict__ pairFlags, OvParams P,
-                                                     int32_t* __restrict__ score, int32_t* __restrict__ back, Elem* __restrict__ ord,
+                                                     const uint32_t* __restrict__ pairOrder, uint32_t nPairs, const uint32_t* __restrict__ pairFlags,
+                                                     OvParams P, int32_t* __restrict__ score, int32_t* __restrict__ back, Elem* __restrict__ ord,
                                                      unsigned long long* __restrict__ cellCount) {
-    const uint32_t w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (w >= nPairs) return;
-    const int lane = threadIdx.x & 31;
+    const uint32_t slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;   // half-warp index
+    if (slot >= nPairs) return;
+    const uint32_t w = pairOrder[slot];
+    const int sl = threadIdx.x & 15;
+    const uint32_t hm = 0xffffu << (threadIdx.x & 16);                     // the lanes of this half
     const PairInfo pi = pairs[pairIds[w]];
     const bool extSorted = pairFlags[w] & PAIR_EXTSORTED;
     const int32_t n = (int32_t)pi.n;
@@ -386,32 +390,32 @@ __global__ void __launch_bounds__(128) chainDpKernel(const Elem* __restrict__ hi
     const Elem* h = hits + pi.start;
     int32_t* sc = score + pi.start; int32_t* bk = back + pi.start; Elem* od = ord + pi.start;
 
-    // block b = matches [32b, 32b+32): nx* holds the current block, pf* the next one (loaded a block ahead)
+    // block b = matches [16b, 16b+16): nx* holds the current block, pf* the next one (loaded a block ahead)
     int32_t nxC = 0, nxE = 0, pfC = 0, pfE = 0;
-    if (lane < n) { const Elem e = h[lane]; nxC = elemCur(e, extSorted); nxE = elemExt(e, extSorted); }
-    if (32 + lane < n) { const Elem e = h[32 + lane]; pfC = elemCur(e, extSorted); pfE = elemExt(e, extSorted); }
-    int32_t wC = nxC, wE = nxE, wS = 0;   // window registers: lane 0 holds match 0 (score 0); others not yet valid
-    if (lane == 0) { sc[0] = 0; bk[0] = -1; Elem t; t.key = 0x7fffffffULL; t.val = 0; t.aux = 0; od[0] = t; }
+    if (sl < n) { const Elem e = h[sl]; nxC = elemCur(e, extSorted); nxE = elemExt(e, extSorted); }
+    if (16 + sl < n) { const Elem e = h[16 + sl]; pfC = elemCur(e, extSorted); pfE = elemExt(e, extSorted); }
+    int32_t wC = nxC, wE = nxE, wS = 0;   // window registers: sub-lane 0 holds match 0 (score 0); others not yet valid
+    if (sl == 0) { sc[0] = 0; bk[0] = -1; Elem t; t.key = 0x7fffffffULL; t.val = 0; t.aux = 0; od[0] = t; }
     unsigned long long cells = 0;
     for (int32_t i = 1; i < n; ++i) {
-        const int l0 = i & 31;
+        const int l0 = i & 15;
         if (l0 == 0) {
             nxC = pfC; nxE = pfE;
-            const int32_t nb = i + 32 + lane;
+            const int32_t nb = i + 16 + sl;
             if (nb < n) { const Elem e = h[nb]; pfC = elemCur(e, extSorted); pfE = elemExt(e, extSorted); }
         }
-        const int32_t curN = __shfl_sync(0xffffffffu, nxC, l0), extN = __shfl_sync(0xffffffffu, nxE, l0);
+        const int32_t curN = __shfl_sync(hm, nxC, l0, 16), extN = __shfl_sync(hm, nxE, l0, 16);
         int32_t best = 0, bestId = 0;
         bool stop = false;
-        for (int32_t jb = i - 1; jb >= 0 && !stop; jb -= 32) {
-            const int32_t j = jb - lane;
+        for (int32_t jb = i - 1; jb >= 0 && !stop; jb -= 16) {
+            const int32_t j = jb - sl;
             const bool in = j >= 0;
             int32_t cj, ej, sj;
-            if (jb == i - 1) {   // the 32 most recent matches: registers
-                const int src = j & 31;
-                cj = __shfl_sync(0xffffffffu, wC, src); ej = __shfl_sync(0xffffffffu, wE, src); sj = __shfl_sync(0xffffffffu, wS, src);
+            if (jb == i - 1) {   // the 16 most recent matches: registers
+                const int src = j & 15;
+                cj = __shfl_sync(hm, wC, src, 16); ej = __shfl_sync(hm, wE, src, 16); sj = __shfl_sync(hm, wS, src, 16);
             } else {
-                if (jb == i - 33) __syncwarp();   // order lane 0's score stores before these loads
+                if (jb == i - 17) __syncwarp(hm);   // order sub-lane 0's score stores before these loads
                 cj = 0; ej = 0; sj = 0;
                 if (in) { const Elem e = h[j]; cj = elemCur(e, extSorted); ej = elemExt(e, extSorted); sj = sc[j]; }
             }
@@ -421,36 +425,42 @@ __global__ void __launch_bounds__(128) chainDpKernel(const Elem* __restrict__ hi
             const int32_t gap = jd > 100 ? 2 * jd : (jd >> 1);            // int32(float(LG_GAP|SM_GAP) * jd), :299
             const int32_t s = ok ? sj + min(min(dc, de), k) - gap : INT32_MIN;
             // second break rule (sorted-axis distance) first: nothing beyond its first lane is ever evaluated
-            const uint32_t far = __ballot_sync(0xffffffffu, in && (extSorted ? de : dc) > P.maxJump);
-            int stopLane = far ? (__ffs(far) - 1) : 31;
+            const uint32_t far = (__ballot_sync(hm, in && (extSorted ? de : dc) > P.maxJump) >> (threadIdx.x & 16)) & 0xffffu;
+            int stopLane = far ? (__ffs(far) - 1) : 15;
             bool brk = far != 0;
-            // first break rule: a predecessor with jumpDiv == 0 and dc < k ends the scan IF it improves the running
-            // maximum.  Such predecessors are rare, so instead of a prefix-max scan over all lanes each candidate is
-            // tested with one warp reduction over the lanes before it.
-            uint32_t pot = __ballot_sync(0xffffffffu, ok && jd == 0 && dc < k) & ((2u << stopLane) - 1u);
+            uint32_t pot = (__ballot_sync(hm, ok && jd == 0 && dc < k) >> (threadIdx.x & 16)) & ((2u << stopLane) - 1u);
             while (pot) {
                 const int t = __ffs(pot) - 1;
-                const int32_t prior = max(best, __reduce_max_sync(0xffffffffu, lane < t ? s : INT32_MIN));
-                if (__shfl_sync(0xffffffffu, s, t) > prior) { stopLane = t; brk = true; break; }
+                const int32_t prior = max(best, __reduce_max_sync(hm, sl < t ? s : INT32_MIN));
+                if (__shfl_sync(hm, s, t, 16) > prior) { stopLane = t; brk = true; break; }
                 pot &= pot - 1;
             }
-            const bool part = ok && lane <= stopLane;
-            const int32_t mx = __reduce_max_sync(0xffffffffu, part ? s : INT32_MIN);
+            const bool part = ok && sl <= stopLane;
+            const int32_t mx = __reduce_max_sync(hm, part ? s : INT32_MIN);
             if (mx > best) {
-                const uint32_t wm = __ballot_sync(0xffffffffu, part && s == mx);
+                const uint32_t wm = (__ballot_sync(hm, part && s == mx) >> (threadIdx.x & 16)) & 0xffffu;
                 best = mx; bestId = jb - (__ffs(wm) - 1);
             }
             cells += min(jb + 1, stopLane + 1);
             stop = brk;
         }
         const int32_t sci = max(best, k);
-        if (lane == l0) { wC = curN; wE = extN; wS = sci; }   // match i replaces match i-32 in the window
-        if (lane == 0) {
+        if (sl == l0) { wC = curN; wE = extN; wS = sci; }   // match i replaces match i-16 in the window
+        if (sl == 0) {
             sc[i] = sci; bk[i] = best > k ? bestId : -1;
             Elem t; t.key = (unsigned long long)(0x7fffffff - sci); t.val = (unsigned int)i; t.aux = 0; od[i] = t;   // (c) input of the score sort
         }
     }
-    if (lane == 0 && cells) atomicAdd(cellCount, cells);
+    if (sl == 0 && cells) atomicAdd(cellCount, cells);
+}
+
+// order in which chainDpKernel visits the pairs: decreasing number of matches
+__global__ void __launch_bounds__(256) pairSizeKeyKernel(const PairInfo* __restrict__ pairs, const uint32_t* __restrict__ pairIds, uint32_t nPairs,
+                                                         uint32_t* __restrict__ keys, uint32_t* __restrict__ idx) {
+    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= nPairs) return;
+    keys[w] = ~pairs[pairIds[w]].n;
+    idx[w] = w;
 }
 
 // (d)+(e) chain walk in std::sort order of the scores (overlap.cpp:331-427), overlapTest, filtered positions, then
@@ -818,8 +828,18 @@ void overlapsBatch(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, const fg_
             sortSegments(ctx, hits.p, extSegs.p, counters.p + 5, Pn, ws, "chain_extsort_top", "chain_extsort_small");
             {
                 PhaseTimer pt(ctx, "chain_dp");
-                chainDpKernel<<<(Pn + 3) / 4, 128, 0, ctx->stream>>>(hits.p, pairInfo.p, pairIds.p, Pn, pairFlags.p, P, score.p, back.p, ord.p,
-                                                                    dCells.p);
+                // visit the pairs by decreasing size: two pairs share a warp, 8 a block
+                DevBuf<uint32_t> szKeyA(Pn), szKeyB(Pn), ordA(Pn), ordB(Pn);
+                pairSizeKeyKernel<<<(Pn + 255) / 256, 256, 0, ctx->stream>>>(pairInfo.p, pairIds.p, Pn, szKeyA.p, ordA.p);
+                checkLaunch(ctx, "pairSizeKeyKernel");
+                cub::DoubleBuffer<uint32_t> dk(szKeyA.p, szKeyB.p), dv(ordA.p, ordB.p);
+                size_t tb = 0;
+                FG_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, dk, dv, (int)Pn, 0, 32, ctx->stream));
+                DevBuf<char> tmpS(tb);
+                FG_CUDA(cub::DeviceRadixSort::SortPairs(tmpS.p, tb, dk, dv, (int)Pn, 0, 32, ctx->stream));
+                ctx->launches += 5;
+                chainDpKernel<<<(Pn + 7) / 8, 128, 0, ctx->stream>>>(hits.p, pairInfo.p, pairIds.p, dv.Current(), Pn, pairFlags.p, P, score.p,
+                                                                    back.p, ord.p, dCells.p);
                 checkLaunch(ctx, "chainDpKernel");
             }
             FG_CUDA(cudaMemcpyAsync(counters.p + 10, &Pn, 4, cudaMemcpyHostToDevice, ctx->stream));
