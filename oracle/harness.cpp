@@ -139,7 +139,9 @@ int main(int argc, char** argv) {
             size_t freq = index.kmerFreq(km);
             if (!rep && !freq) continue;
             fprintf(f, "%" PRIx64 " %d %zu", key, (int)rep, freq);
-            for (const auto& rp : index.iterKmerPos(km)) fprintf(f, " %u:%d", idNum(rp.readId), rp.position);
+            // iterKmerPos on a k-mer that is not in the table throws in the reference (cuckoo find); getSeqOverlaps
+            // itself only calls it after kmerFreq() != 0 (overlap.cpp:183-186)
+            if (freq) for (const auto& rp : index.iterKmerPos(km)) fprintf(f, " %u:%d", idNum(rp.readId), rp.position);
             fputc('\n', f);
         }
         fclose(f);

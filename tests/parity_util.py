@@ -68,12 +68,12 @@ def median_f32(values):
 
 
 def gpu_pipeline(reads_path, cfg_path, out_prefix, k=None, min_overlap=1000, dump_index=False, both_strands=False,
-                 max_overlaps=0, force_local=False, all_ext=False, estimate=True, engine=None, max_queries=None):
+                 max_overlaps=0, force_local=False, all_ext=False, estimate=True, engine=None, max_queries=None, min_read_len=None):
     """Mirror of oracle/harness.cpp on the CUDA path; writes the same dump files.  Returns (engine, info)."""
     import flye_b200 as fb
     cfg = load_cfg(cfg_path)
     k = k or int(cfg["kmer_size"])
-    reads = fb.read_fasta(reads_path, min_overlap)
+    reads = fb.read_fasta(reads_path, min_overlap if min_read_len is None else min_read_len)
     eng = engine or fb.Engine(0)
     eng.upload_ascii(reads)
     info = {"reads": len(reads)}

@@ -1,0 +1,108 @@
+"""-m gpu: edge cases the reference handles implicitly — reads shorter than k, identical reads (every k-mer hit is a
+tie for std::sort), tandem repeats (tandem filter + repetitive k-mers), low-complexity sequence (minimizer tie quirk,
+homopolymer compression), empty / duplicated / reverse-strand query lists."""
+import os
+
+import numpy as np
+import pytest
+
+import parity_util as pu
+
+pytestmark = pytest.mark.gpu
+RAW = os.path.join(pu.CFG_DIR, "raw_reads.cfg")
+HIFI = os.path.join(pu.CFG_DIR, "hifi.cfg")
+
+
+def _rand(rng, n):
+    return "".join(rng.choice(list("ACGT"), n))
+
+
+def _mutate(rng, s, rate):
+    out = []
+    for c in s:
+        u = rng.random()
+        if u < rate / 3:
+            continue
+        if u < 2 * rate / 3:
+            out.append(rng.choice(list("ACGT")))
+        out.append(rng.choice(list("ACGT")) if u > 1 - rate / 3 else c)
+    return "".join(out)
+
+
+def _rc(s):
+    return s[::-1].translate(str.maketrans("ACGT", "TGCA"))
+
+
+def _write(path, seqs):
+    with open(path, "w") as f:
+        for i, s in enumerate(seqs):
+            f.write(">e%d\n%s\n" % (i, s))
+
+
+def _check(tmp, reads, cfg, k, engine, exts, ref_opts=(), **kw):
+    pu.run_oracle(reads, cfg, os.path.join(tmp, "ref"), k=k, extra=["--dump-index", "--min-read-len", "0"] + list(ref_opts))
+    pu.gpu_pipeline(reads, cfg, os.path.join(tmp, "gpu"), k=k, dump_index=True, engine=engine, min_read_len=0, **kw)
+    for ext in exts:
+        n, sample = pu.diff_files(os.path.join(tmp, "ref." + ext), os.path.join(tmp, "gpu." + ext))
+        assert n == 0, (ext, sample[:3])
+
+
+def test_identical_and_short_reads(engine, tmp_path):
+    rng = np.random.default_rng(1)
+    base = _rand(rng, 4000)
+    seqs = [base] * 4 + [_rc(base)] * 2 + [base[500:3500], "ACGTACGTAC", "A" * 15, _rand(rng, 16), _rand(rng, 17), _rand(rng, 40)]
+    seqs += [_mutate(rng, base, 0.08) for _ in range(6)]
+    reads = os.path.join(str(tmp_path), "r.fasta")
+    _write(reads, seqs)
+    _check(str(tmp_path), reads, RAW, 15, engine, ["hist", "index", "ovlp"], ref_opts=["--both-strands", "--no-estimate"],
+           both_strands=True, estimate=False)
+
+
+def test_tandem_repeats_and_repetitive_kmers(engine, tmp_path):
+    rng = np.random.default_rng(2)
+    unit = _rand(rng, 23)
+    genome = _rand(rng, 3000) + unit * 260 + _rand(rng, 3000) + unit * 150 + _rand(rng, 2500)
+    seqs = []
+    for _ in range(60):
+        a = rng.integers(0, len(genome) - 5000)
+        s = _mutate(rng, genome[a:a + rng.integers(3000, 5000)], 0.06)
+        seqs.append(s if rng.random() < 0.5 else _rc(s))
+    reads = os.path.join(str(tmp_path), "r.fasta")
+    _write(reads, seqs)
+    _check(str(tmp_path), reads, RAW, 15, engine, ["hist", "index", "ovlp"], ref_opts=["--no-estimate"], estimate=False)
+
+
+def test_low_complexity_hifi(engine, tmp_path):
+    rng = np.random.default_rng(3)
+    genome = _rand(rng, 2500) + "A" * 400 + _rand(rng, 2000) + "AC" * 300 + _rand(rng, 2500) + "GGGTTT" * 120 + _rand(rng, 2000)
+    seqs = []
+    for _ in range(50):
+        a = rng.integers(0, len(genome) - 4500)
+        s = _mutate(rng, genome[a:a + rng.integers(3000, 4500)], 0.006)
+        seqs.append(s if rng.random() < 0.5 else _rc(s))
+    reads = os.path.join(str(tmp_path), "r.fasta")
+    _write(reads, seqs)
+    _check(str(tmp_path), reads, HIFI, None, engine, ["index", "ovlp"], ref_opts=["--both-strands", "--no-estimate"],
+           both_strands=True, estimate=False)
+
+
+def test_query_list_shapes(engine, tmp_path):
+    """empty list, duplicates, reverse-strand ids, a read too short to have k-mers"""
+    import flye_b200 as fb
+    rng = np.random.default_rng(4)
+    base = _rand(rng, 6000)
+    seqs = [_mutate(rng, base[a:a + 3500], 0.05) for a in (0, 800, 1600, 2400)] + ["ACGT"]
+    engine.upload_ascii([s.encode() for s in seqs])
+    engine.count_kmers(15)
+    engine.build_index_solid()
+    offs, ov, _ = engine.overlaps([])
+    assert len(offs) == 1 and offs[0] == 0 and len(ov) == 0
+    q = [0, 0, 3, 8, 9, 2, 0]
+    offs, ov, _ = engine.overlaps(q)
+    per = [ov[int(offs[i]):int(offs[i + 1])] for i in range(len(q))]
+    assert len(per[0]) > 0
+    assert all(np.array_equal(per[0], per[j]) for j in (1, 6))          # the same query gives the same vector
+    assert len(per[3]) == 0 and len(per[4]) == 0                        # read 4 ("ACGT") has no k-mers, either strand
+    assert (per[2]["cur_id"] == 3).all() and (per[5]["cur_id"] == 2).all()
+    with pytest.raises(fb.FlyeB200Error):
+        engine.overlaps([10])                                           # id out of range -> FG_ERR_ARG
