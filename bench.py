@@ -305,8 +305,14 @@ def main():
     M, O = stats.get("n_hits", 0), n_ovl
     w = 4 if 2 * k <= 32 else 8
     n_k = n_bases - k * n_reads
-    alg = {"hit_sort_top": 24.0 * M, "hit_sort_small": 24.0 * M, "chain_dp": 12.0 * M + 40.0 * O, "gather": (w + 8.0) * n_k + 20.0 * M,
-           "count_sort": 3.0 * w * n_k, "select": (w + 5.0) * n_k, "extract": 0.25 * n_bases + w * n_k}
+    # single-kernel phases only (hit_sort_top is a sequence of per-level launches; its counters are in profiles/)
+    alg = {"hit_sort_small": 24.0 * M, "chain_dp": 12.0 * M + 40.0 * O, "chain_walk": 12.0 * M + 40.0 * O,
+           "select": (w + 5.0) * n_k, "extract": 0.25 * n_bases + w * n_k}
+    names = {"hit_sort_small": "sortSmallKernel", "chain_dp": "chainDpKernel", "chain_walk": "chainWalkKernel", "select": "selectKernel",
+             "extract": "extractKeysKernel"}
+    # DRAM bytes per k-mer hit from the `ncu --set full` captures of round 1 (profiles/README.md:
+    # dram__bytes_read.sum + dram__bytes_write.sum of one launch / hits of that launch)
+    traffic_per_hit = {"hit_sort_small": 32.2, "chain_dp": 40.5, "chain_walk": 20.3}
     kernel_phases = {p: ms for p, ms in resident_phases.items() if p in alg and alg[p] > 0}
     peak, peak_src = measured_peak()
     roofline = None
@@ -315,13 +321,13 @@ def main():
         calls = max(1, resident_calls.get(dom, 1))
         per_launch_ms = kernel_phases[dom] / calls
         achieved = (alg[dom] / calls) / (per_launch_ms / 1e3) / 1e9
-        roofline = {"bound": "hbm", "kernel": {"hit_sort_top": "sortTopKernel", "hit_sort_small": "sortSmallKernel", "chain_dp": "chainDpKernel",
-                                               "gather": "queryLookupKernel+expandKernel",
-                                               "count_sort": "cub radix sort (keys)", "select": "selectKernel",
-                                               "extract": "extractKeysKernel"}.get(dom, dom),
-                    "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        roofline = {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": traffic_per_hit[dom] * M / calls if dom in traffic_per_hit else None,
+                    "traffic_source": "bytes per hit measured with ncu --set full (profiles/), scaled to this launch's hits",
                     "peak_source": peak_src, "launches": calls, "ms_per_launch": per_launch_ms,
-                    "algorithmic_bytes_per_launch": alg[dom] / calls}
+                    "algorithmic_bytes_per_launch": alg[dom] / calls,
+                    "note": "issue-bound integer kernel (80% issue-slot utilisation in ncu); the HBM fraction is low by construction"
+                            if dom == "chain_dp" else None}
 
     line = {"metric": "reads/sec through k-mer index + overlap detection", "value": value, "unit": "reads/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_resident, "higher_is_better": True, "scaling": "strong",
