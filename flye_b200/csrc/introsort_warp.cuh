@@ -356,7 +356,7 @@ struct NoSink { FG_DEV void operator()(long, long, int) const {} };
 static constexpr int WARP_MINI = FG_WARP_MINI;
 
 template <class Sink>
-FG_DEV void warpIntrosortRange(Elem* arr, idx_t f0, idx_t l0, int d0, idx_t small, Sink& sink, unsigned char* tab) {
+FG_DEV void warpIntrosortRange(Elem* arr, idx_t f0, idx_t l0, int d0, idx_t small, Sink& sink, unsigned char* tab, bool inGlobal = false) {
     if (l0 - f0 < 2) return;
     FG_LANEVAR(idx_t, stF0); FG_LANEVAR(idx_t, stL0); FG_LANEVAR(int, stD0);   // stack entries 0..31
     FG_LANEVAR(idx_t, stF1); FG_LANEVAR(idx_t, stL1); FG_LANEVAR(int, stD1);   // stack entries 32..63
@@ -401,7 +401,7 @@ FG_DEV void warpIntrosortRange(Elem* arr, idx_t f0, idx_t l0, int d0, idx_t smal
                 break;
             }
             --d;
-            const idx_t cut = warpPartition(arr, f, l, tab);
+            const idx_t cut = warpPartition(arr, f, l, tab, inGlobal);
             if (l - cut > stopAt) {   // "recurse" on the right part: push
                 FG_FOR_LANES
                     if (lane == (sp & 31)) {

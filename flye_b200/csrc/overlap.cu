@@ -23,6 +23,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <functional>
 #include <thread>
 
 namespace fg {
@@ -163,12 +164,13 @@ static int sortSmallN() {   // elements per shared-memory task (FG_SORT_SMALL, d
 struct Seg { uint32_t start, n; };
 struct SortTask { uint32_t start, n; int depth; };
 
-// counters of one segmented sort: [0] nSegs (input)  [1] nSmall  [2] next small task  [3] nBig ping  [4] nBig pong
+// counters of one segmented sort (8 words): [0] nSegs (input)  [1] nSmall  [2] next small task  [3] nBig ping  [4] nBig pong
+//                                           [5] elements in the ping list  [6] elements in the pong list
 __device__ __forceinline__ void emitRange(uint32_t start, uint32_t n, int depth, SortTask* big, uint32_t* nBig, uint32_t capBig,
                                           SortTask* small, uint32_t* nSmall, uint32_t capSmall, uint32_t smallN) {
     if (n < 2) return;
     SortTask k; k.start = start; k.n = n; k.depth = depth;
-    if (n > smallN) { const uint32_t t = atomicAdd(nBig, 1u); if (t < capBig) big[t] = k; }
+    if (n > smallN) { const uint32_t t = atomicAdd(nBig, 1u); atomicAdd(nBig + 2, n); if (t < capBig) big[t] = k; }
     else { const uint32_t t = atomicAdd(nSmall, 1u); if (t < capSmall) small[t] = k; }
 }
 
@@ -201,6 +203,29 @@ __global__ void __launch_bounds__(128) sortLevelKernel(Elem* __restrict__ arr, c
         emitRange(t.start, (uint32_t)cut, t.depth - 1, out, nOut, capBig, small, nSmall, capSmall, smallN);
         emitRange(t.start + (uint32_t)cut, t.n - (uint32_t)cut, t.depth - 1, out, nOut, capBig, small, nSmall, capSmall, smallN);
     }
+}
+
+// the long tail of the recursion (few, unevenly split ranges left): one warp finishes one remaining range in global
+// memory, handing every sub-range of <= smallN elements to the shared-memory kernel
+struct TaskSinkDev {
+    SortTask* tasks; uint32_t* counter; uint32_t cap; uint32_t base;
+    __device__ __forceinline__ void operator()(long f, long l, int d) const {
+        if (laneId() == 0) {
+            const uint32_t t = atomicAdd(counter, 1u);
+            if (t < cap) { SortTask k; k.start = base + (uint32_t)f; k.n = (uint32_t)(l - f); k.depth = d; tasks[t] = k; }
+        }
+    }
+};
+
+__global__ void __launch_bounds__(128) sortTailKernel(Elem* __restrict__ arr, const SortTask* __restrict__ in, const uint32_t* __restrict__ nInPtr,
+                                                      uint32_t capBig, SortTask* __restrict__ small, uint32_t* __restrict__ nSmall,
+                                                      uint32_t capSmall, uint32_t smallN) {
+    __shared__ unsigned char tabs[4][64];
+    const uint32_t w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (w >= min(*nInPtr, capBig)) return;
+    const SortTask t = in[w];
+    TaskSinkDev sink{small, nSmall, capSmall, t.start};
+    warpIntrosortRange(arr + t.start, 0, (idx_t)t.n, t.depth, (idx_t)smallN, sink, tabs[threadIdx.x >> 5], /*inGlobal*/ true);
 }
 
 __global__ void __launch_bounds__(128) sortSmallKernel(Elem* __restrict__ arr, const SortTask* __restrict__ tasks,
@@ -467,7 +492,7 @@ __global__ void __launch_bounds__(256) pairSizeKeyKernel(const PairInfo* __restr
 // primary selection (:431-458).  One warp per pair: the back-pointer table is staged in shared memory (the walk is
 // pure pointer chasing, so its latency is what matters), the lanes test 32 chain starts at a time and lane 0
 // walks the chains in order, re-testing the remaining starts after every walk because a walk consumes pointers.
-static constexpr int WALK_CAP = 4096;   // back pointers per warp in shared memory (16 KB); larger pairs stay in global
+static constexpr int WALK_CAP = 4096;   // matches per warp whose back pointers are staged in shared memory as 16-bit deltas (8 KB)
 
 __global__ void __launch_bounds__(128) chainWalkKernel(const Elem* __restrict__ hits, const PairInfo* __restrict__ pairs, const uint32_t* __restrict__ pairIds,
                                                        uint32_t nPairs, const uint32_t* __restrict__ pairFlags, const uint32_t* __restrict__ qIds,
@@ -491,25 +516,30 @@ __global__ void __launch_bounds__(128) chainWalkKernel(const Elem* __restrict__ 
     const uint64_t qbase = qSlotOff[pi.qi];
     const uint32_t qn = (uint32_t)(curLen - k);
 
-    int32_t* bk = back + pi.start;
-    if (n <= WALK_CAP) {
-        int32_t* sb = reinterpret_cast<int32_t*>(smemRaw) + (threadIdx.x >> 5) * WALK_CAP;
-        for (int32_t i = lane; i < n; i += 32) sb[i] = bk[i];
-        bk = sb;
-    }
+    // back pointers: delta = pos - back[pos] (>= 1), 0 = none.  n <= WALK_CAP < 65536, so a delta fits 16 bits.
+    int32_t* bkG = back + pi.start;
+    unsigned short* sb = reinterpret_cast<unsigned short*>(smemRaw) + (threadIdx.x >> 5) * WALK_CAP;
+    const bool staged = n <= WALK_CAP;
+    if (staged)
+        for (int32_t i = lane; i < n; i += 32) { const int32_t b = bkG[i]; sb[i] = b < 0 ? 0 : (unsigned short)(i - b); }
     __syncwarp();
+    auto hasBack = [&](int32_t pos) { return staged ? sb[pos] != 0 : bkG[pos] != -1; };
 
     uint32_t nCand = 0;   // meaningful in lane 0
     for (int32_t t0 = 0; t0 < n; t0 += 32) {
         const int32_t t = t0 + lane;
         const int32_t cs = t < n ? (int32_t)od[t].val : 0;
-        uint32_t m = __ballot_sync(0xffffffffu, t < n && bk[cs] != -1);
+        uint32_t m = __ballot_sync(0xffffffffu, t < n && hasBack(cs));
         while (m) {
             const int src = __ffs(m) - 1;
             const int32_t chainStart = __shfl_sync(0xffffffffu, cs, src);
             if (lane == 0) {
                 int32_t firstMatch = 0, chainLength = 0, pos = chainStart;
-                while (pos != -1) { firstMatch = pos; ++chainLength; const int32_t np = bk[pos]; bk[pos] = -1; pos = np; }
+                if (staged) {
+                    for (;;) { firstMatch = pos; ++chainLength; const unsigned short d = sb[pos]; sb[pos] = 0; if (!d) break; pos -= d; }
+                } else {
+                    while (pos != -1) { firstMatch = pos; ++chainLength; const int32_t np = bkG[pos]; bkG[pos] = -1; pos = np; }
+                }
                 const Elem eF = h[firstMatch], eL = h[chainStart];
                 const int32_t curBegin = elemCur(eF, extSorted), extBegin = elemExt(eF, extSorted);
                 const int32_t curEnd = elemCur(eL, extSorted) + k - 1, extEnd = elemExt(eL, extSorted) + k - 1;
@@ -525,7 +555,7 @@ __global__ void __launch_bounds__(128) chainWalkKernel(const Elem* __restrict__ 
                 }
             }
             __syncwarp();
-            m = __ballot_sync(0xffffffffu, lane > src && t < n && bk[cs] != -1);
+            m = __ballot_sync(0xffffffffu, lane > src && t < n && hasBack(cs));
         }
     }
     __syncwarp();   // all lanes are done reading ord[] before lane 0 reuses its slots
@@ -609,14 +639,25 @@ static void sortSegments(fg_ctx* ctx, Elem* arr, const Seg* dSegs, uint32_t* dCo
         checkLaunch(ctx, "sortSeedKernel");
         SortTask* in = ws.bigA.p; SortTask* out = ws.bigB.p;
         uint32_t* nIn = dCounters + 3; uint32_t* nOut = dCounters + 4;
+        uint64_t firstElems = 0;
         for (int level = 0; level < 200; ++level) {
-            uint32_t hIn = 0;
-            FG_CUDA(cudaMemcpyAsync(&hIn, nIn, 4, cudaMemcpyDeviceToHost, ctx->stream));
+            uint32_t hIn[3] = {0, 0, 0};   // count, (other list), elements
+            FG_CUDA(cudaMemcpyAsync(hIn, nIn, 12, cudaMemcpyDeviceToHost, ctx->stream));
             FG_CUDA(cudaStreamSynchronize(ctx->stream));
-            if (hIn > ws.capBig) throw Error(FG_ERR_INTERNAL, "sort task list overflow");
-            if (!hIn) break;
+            const uint32_t cnt = hIn[0], elems = hIn[2];
+            if (cnt > ws.capBig) throw Error(FG_ERR_INTERNAL, "sort task list overflow");
+            if (!cnt) break;
+            if (level == 0) firstElems = elems;
+            // tail: little work left in unevenly split ranges -> finish each range with one warp instead of paying a
+            // launch + host round trip per remaining level
+            if (level >= 4 && ((uint64_t)elems * 16 < firstElems || level >= 48)) {
+                sortTailKernel<<<(cnt + 3) / 4, 128, 0, ctx->stream>>>(arr, in, nIn, ws.capBig, ws.small.p, dCounters + 1, ws.capSmall, smallN);
+                checkLaunch(ctx, "sortTailKernel");
+                break;
+            }
             FG_CUDA(cudaMemsetAsync(nOut, 0, 4, ctx->stream));
-            sortLevelKernel<<<(hIn + 3) / 4, 128, 0, ctx->stream>>>(arr, in, nIn, ws.capBig, out, nOut, ws.small.p, dCounters + 1, ws.capSmall, smallN);
+            FG_CUDA(cudaMemsetAsync(nOut + 2, 0, 4, ctx->stream));
+            sortLevelKernel<<<(cnt + 3) / 4, 128, 0, ctx->stream>>>(arr, in, nIn, ws.capBig, out, nOut, ws.small.p, dCounters + 1, ws.capSmall, smallN);
             checkLaunch(ctx, "sortLevelKernel");
             std::swap(in, out); std::swap(nIn, nOut);
         }
@@ -761,7 +802,7 @@ void overlapsBatch(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, const fg_
     DevBuf<Elem> hits, ord; DevBuf<int32_t> score, back; DevBuf<Cand> cands; DevBuf<uint8_t> flags;
     DevBuf<uint32_t> gStart, candIds, pairIds;
     SortWorkspace ws; DevBuf<Seg> segsQ;
-    DevBuf<uint32_t> counters(16);
+    DevBuf<uint32_t> counters(32);
     std::vector<std::vector<fg_overlap>> perQuery;   // not used; results are appended in query order
 
     uint32_t qa = 0;
@@ -776,7 +817,7 @@ void overlapsBatch(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, const fg_
         ws.ensure(M, nq);
         const uint32_t taskCap = ws.capSmall;
         segsQ.ensure(nq);
-        uint32_t hCounters[16] = {0};
+        uint32_t hCounters[32] = {0};
         hCounters[0] = nq;
         FG_CUDA(cudaMemcpyAsync(counters.p, hCounters, sizeof hCounters, cudaMemcpyHostToDevice, ctx->stream));
         const size_t tA = qTileFirst[qa], tB = qTileFirst[qb];
@@ -822,10 +863,10 @@ void overlapsBatch(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, const fg_
             {
                 PhaseTimer pt(ctx, "chain_prep");
                 pairPrepKernel<<<(Pn + 7) / 8, 256, 0, ctx->stream>>>(hits.p, pairInfo.p, pairIds.p, Pn, dQIds.p, ctx->dLen.p, pairFlags.p,
-                                                                     extSegs.p, counters.p + 5, allSegs.p);
+                                                                     extSegs.p, counters.p + 8, allSegs.p);
                 checkLaunch(ctx, "pairPrepKernel");
             }
-            sortSegments(ctx, hits.p, extSegs.p, counters.p + 5, Pn, ws, "chain_extsort_top", "chain_extsort_small");
+            sortSegments(ctx, hits.p, extSegs.p, counters.p + 8, Pn, ws, "chain_extsort_top", "chain_extsort_small");
             {
                 PhaseTimer pt(ctx, "chain_dp");
                 // visit the pairs by decreasing size: two pairs share a warp, 8 a block
@@ -842,12 +883,12 @@ void overlapsBatch(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, const fg_
                                                                     back.p, ord.p, dCells.p);
                 checkLaunch(ctx, "chainDpKernel");
             }
-            FG_CUDA(cudaMemcpyAsync(counters.p + 10, &Pn, 4, cudaMemcpyHostToDevice, ctx->stream));
-            sortSegments(ctx, ord.p, allSegs.p, counters.p + 10, Pn, ws, "chain_ordsort_top", "chain_ordsort_small");
+            FG_CUDA(cudaMemcpyAsync(counters.p + 16, &Pn, 4, cudaMemcpyHostToDevice, ctx->stream));
+            sortSegments(ctx, ord.p, allSegs.p, counters.p + 16, Pn, ws, "chain_ordsort_top", "chain_ordsort_small");
             {
                 PhaseTimer pt(ctx, "chain_walk");
                 static bool walkAttr = false;
-                const int walkSmem = 4 * WALK_CAP * (int)sizeof(int32_t);
+                const int walkSmem = 4 * WALK_CAP * (int)sizeof(unsigned short);
                 if (!walkAttr) { FG_CUDA(cudaFuncSetAttribute(chainWalkKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, walkSmem)); walkAttr = true; }
                 chainWalkKernel<<<(Pn + 3) / 4, 128, walkSmem, ctx->stream>>>(hits.p, pairInfo.p, pairIds.p, Pn, pairFlags.p, dQIds.p, dQSlotOff.p,
                                                                           ctx->dLen.p, filtBits.p, filtPrefix.p, P, score.p, back.p, ord.p,
@@ -855,10 +896,10 @@ void overlapsBatch(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, const fg_
                 checkLaunch(ctx, "chainWalkKernel");
             }
             {
-                uint32_t hc[16];
+                uint32_t hc[32];
                 FG_CUDA(cudaMemcpyAsync(hc, counters.p, sizeof hc, cudaMemcpyDeviceToHost, ctx->stream));
                 FG_CUDA(cudaStreamSynchronize(ctx->stream));
-                if (hc[1] > taskCap || hc[6] > taskCap || hc[11] > taskCap) throw Error(FG_ERR_INTERNAL, "sort task list overflow");
+                if (hc[1] > taskCap || hc[9] > taskCap || hc[17] > taskCap) throw Error(FG_ERR_INTERNAL, "sort task list overflow");
             }
             PhaseTimer pt(ctx, "d2h");
             cub::TransformInputIterator<uint64_t, CastU64, const uint32_t*> it64(nKept.p, CastU64());
@@ -894,51 +935,66 @@ void overlapsBatch(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, const fg_
     HostTimer hostEpi(ctx, "host_epilogue");
     const float sampleRate = ctx->stats.sample_rate;
     fg_overlap* hOut = pinned.p;
-    // (1) divergence of every record, in parallel over host threads (pure per-record arithmetic with glibc logf)
-    {
-        const unsigned nThreads = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
-        auto work = [&](size_t a, size_t b) {
-            for (size_t i = a; i < b; ++i) {
-                fg_overlap& o = hOut[i];
-                const int32_t curRange = o.cur_end - o.cur_begin, extRange = o.ext_end - o.ext_begin;
-                volatile float normLen = std::max(curRange, extRange) - o.filtered_positions;
-                volatile float mr = (float)o.chain_length * sampleRate;
-                volatile float matchRate = mr / normLen;
-                matchRate = std::min((float)matchRate, 1.0f);
-                volatile float inv = 1 / matchRate;
-                volatile float lg = std::log((float)inv);
-                o.seq_divergence = lg / k;
-                if (prm.nucl_alignment) {   // alignment.cpp:240-245: (float)editDistance / max(len, len)
-                    if (o.edit_distance < 0) o.seq_divergence = 1.0f;
-                    else { volatile float dv = (float)o.edit_distance / (size_t)o.aln_len; o.seq_divergence = dv; }
+    const unsigned nThreads = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    auto parallelFor = [&](size_t n, const std::function<void(size_t, size_t)>& fn) {
+        if (n < 20000 || nThreads == 1) { fn(0, n); return; }
+        std::vector<std::thread> pool;
+        for (unsigned t = 0; t < nThreads; ++t) pool.emplace_back(fn, n * t / nThreads, n * (t + 1) / nThreads);
+        for (auto& th : pool) th.join();
+    };
+    // (1) divergence of every record (pure per-record arithmetic with glibc logf) and the first record of every query
+    std::vector<size_t> qStart(nQ + 1, SIZE_MAX);
+    parallelFor(nRaw, [&](size_t a, size_t b) {
+        for (size_t i = a; i < b; ++i) {
+            fg_overlap& o = hOut[i];
+            const int32_t curRange = o.cur_end - o.cur_begin, extRange = o.ext_end - o.ext_begin;
+            volatile float normLen = std::max(curRange, extRange) - o.filtered_positions;
+            volatile float mr = (float)o.chain_length * sampleRate;
+            volatile float matchRate = mr / normLen;
+            matchRate = std::min((float)matchRate, 1.0f);
+            volatile float inv = 1 / matchRate;
+            volatile float lg = std::log((float)inv);
+            o.seq_divergence = lg / k;
+            if (prm.nucl_alignment) {   // alignment.cpp:240-245: (float)editDistance / max(len, len)
+                if (o.edit_distance < 0) o.seq_divergence = 1.0f;
+                else { volatile float dv = (float)o.edit_distance / (size_t)o.aln_len; o.seq_divergence = dv; }
+            }
+            if (i == 0 || hOut[i - 1].reserved != o.reserved) {
+                if (o.reserved >= nQ || (i && hOut[i - 1].reserved > o.reserved)) continue;   // reported below
+                qStart[o.reserved] = i;
+            }
+        }
+    });
+    qStart[nQ] = nRaw;
+    for (uint32_t q = nQ; q-- > 0;) if (qStart[q] == SIZE_MAX) qStart[q] = qStart[q + 1];   // queries without records
+    // (2) threshold (:470) and maxOverlaps (:218-219) replay per query, in parallel: dropped records are marked
+    std::vector<uint32_t> kept(nQ, 0);
+    parallelFor(nQ, [&](size_t qa, size_t qb) {
+        for (size_t q = qa; q < qb; ++q) {
+            size_t pos = qStart[q], detected = 0;
+            const size_t qEnd = qStart[q + 1];
+            while (pos < qEnd) {
+                size_t end = pos;   // one target group = run of equal ext_id
+                while (end < qEnd && hOut[end].ext_id == hOut[pos].ext_id) ++end;
+                const bool stop = prm.max_overlaps != 0 && detected >= (size_t)prm.max_overlaps;
+                for (size_t i = pos; i < end; ++i) {
+                    const bool keep = !stop && hOut[i].seq_divergence < prm.max_divergence;
+                    hOut[i].reserved = keep ? 0u : 0xffffffffu;
+                    detected += keep;
                 }
+                pos = end;
             }
-        };
-        if (nRaw < 20000 || nThreads == 1) work(0, nRaw);
-        else {
-            std::vector<std::thread> pool;
-            for (unsigned t = 0; t < nThreads; ++t) pool.emplace_back(work, nRaw * t / nThreads, nRaw * (t + 1) / nThreads);
-            for (auto& th : pool) th.join();
+            kept[q] = (uint32_t)detected;
         }
+    });
+    size_t wpos = 0;
+    for (uint32_t q = 0; q < nQ; ++q) { ctx->resOffsets[q] = wpos; wpos += kept[q]; }
+    if (wpos != nRaw) {   // compact in place (records only ever move towards the front)
+        size_t w2 = 0;
+        for (size_t i = 0; i < nRaw; ++i)
+            if (hOut[i].reserved == 0u) { if (w2 != i) hOut[w2] = hOut[i]; ++w2; }
     }
-    // (2) threshold and maxOverlaps replay, in place, in query order
-    size_t pos = 0, wpos = 0;
-    for (uint32_t qi = 0; qi < nQ; ++qi) {
-        ctx->resOffsets[qi] = wpos;
-        size_t detected = 0;
-        while (pos < nRaw && hOut[pos].reserved == qi) {
-            // one target group = run of equal ext_id
-            size_t end = pos;
-            while (end < nRaw && hOut[end].reserved == qi && hOut[end].ext_id == hOut[pos].ext_id) ++end;
-            const bool stop = prm.max_overlaps != 0 && detected >= (size_t)prm.max_overlaps;
-            for (size_t i = pos; i < end && !stop; ++i) {
-                fg_overlap o = hOut[i];
-                o.reserved = 0;
-                if (o.seq_divergence < prm.max_divergence) { hOut[wpos++] = o; ++detected; }   // wpos <= i: in place
-            }
-            pos = end;
-        }
-    }
+    size_t pos = nRaw;
     ctx->resOffsets[nQ] = wpos;
     if (pos != nRaw) throw Error(FG_ERR_INTERNAL, "overlap records out of query order");
 
