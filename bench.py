@@ -238,16 +238,16 @@ def main():
         # so the threshold is computed from the first 1000 result vectors and applied to the rest on the host.
         all_q = np.concatenate([np.asarray(est_ids, dtype=np.uint32), queries])
         offs, ov, ovl_stats = eng.overlaps(all_q, max_divergence=1.0, copy=False, **common)
-        rng_all = ov["cur_end"] - ov["cur_begin"]
+        first = int(offs[len(est_ids)])
+        rng_est = ov["cur_end"][:first] - ov["cur_begin"][:first]
         div_all = ov["seq_divergence"]
         divs = []
         for i in range(len(est_ids)):
             a, b = int(offs[i]), int(offs[i + 1])
             if b > a:
-                divs.append(div_all[a + int(np.argmax(rng_all[a:b]))])
+                divs.append(div_all[a + int(np.argmax(rng_est[a:b]))])
         mean = pu.median_f32(divs) if divs else np.float32(0.5)
         max_div = np.float32((mean if bool(cfg["assemble_divergence_relative"]) else np.float32(0.0)) + np.float32(cfg["assemble_ovlp_divergence"]))
-        first = int(offs[len(est_ids)])
         keep = div_all[first:] < max_div
         lap("overlaps")
         grab()
