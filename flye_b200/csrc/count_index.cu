@@ -445,60 +445,82 @@ __global__ void __launch_bounds__(256) finalizeSelectionKernel(const uint64_t* _
 }
 
 // ------------------------------------------------------------------------------------------------
-// yieldMinimizers (kmer.h:206-262): the monotone deque with its "skip equal hashes only after an expiry" quirk
-// is order dependent, so one thread walks one read; reads run in parallel.  Sets the selected / rc bitmaps.
+// yieldMinimizers (kmer.h:206-262).  The monotone deque with its "skip equal hashes only after an expiry" quirk is
+// order dependent, but it can be restarted EXACTLY at any position p whose hash is strictly below every hash still
+// in the deque: the pop-back loop then empties the deque, the state becomes {p} whatever happened before, and p is
+// emitted.  (If the walk started >= window positions before p, every element the true deque could still hold lies
+// inside the simulated stretch, and any of them the simulation lost to a tie skip had the hash of an element it
+// kept, so the true deque is emptied as well.)  So a read is cut into chunks of MIN_CHUNK positions; the thread of a
+// chunk starts MIN_WARM positions early in silent mode, locks onto the first such position and reports the
+// emissions of the steps of its own chunk.  A chunk that fails to lock before its first step retries with a 4x
+// longer warm-up (ultimately from position 0, which is exact by definition).
 // ------------------------------------------------------------------------------------------------
+static constexpr int MIN_CHUNK = 512;   // TILE_SLOTS / 4
+static constexpr int MIN_WARM = 128;
+
 __global__ void __launch_bounds__(128) minimizerKernel(const uint64_t* __restrict__ seq, const uint64_t* __restrict__ wordOff,
                                                        const uint32_t* __restrict__ len, const uint64_t* __restrict__ slotOff,
-                                                       int k, int window, uint32_t readFirst, uint32_t readCount,
+                                                       const uint2* __restrict__ tiles, uint32_t nChunks, int k, int window,
                                                        uint32_t* __restrict__ selBits, uint32_t* __restrict__ rcBits) {
-    const uint32_t ri = blockIdx.x * blockDim.x + threadIdx.x;
-    if (ri >= readCount) return;
-    const uint32_t r = readFirst + ri;
-    const uint32_t L = len[r];
-    if (L <= (uint32_t)k) return;
-    const int32_t n = (int32_t)(L - k);
+    const uint32_t ci = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ci >= nChunks) return;
+    const uint2 tile = tiles[ci >> 2];
+    const uint32_t r = tile.x;
+    const int32_t n = (int32_t)(len[r] - k);
+    const int32_t c0 = (int32_t)tile.y + (int32_t)(ci & 3) * MIN_CHUNK;
+    if (c0 >= n) return;
+    const int32_t c1 = min(n, c0 + MIN_CHUNK);
     const uint64_t* words = seq + wordOff[r];
     const uint64_t base = slotOff[r] >> 5;
     const uint64_t mask = kmerMask(k);
     constexpr int QCAP = 64;                 // window < 64
     int32_t qPos[QCAP]; uint64_t qHash[QCAP];
-    int head = 0, size = 0;                  // ring buffer
-    int32_t lastEmitted = -1;
-    uint32_t selWord = 0, rcWord = 0;
-    // rolling window value v (little endian): v = (v >> 2) | (base << (2k-2))
-    uint64_t v = windowAt(words, 0, k);
-    for (int32_t p = 0; p < n; ++p) {
-        if (p) {
-            uint32_t q = (uint32_t)p + k - 1;
-            uint64_t b = (words[q >> 5] >> ((q & 31) * 2)) & 3ULL;
-            v = (v >> 2) | (b << (2 * k - 2));
-        }
-        const uint64_t f = fwdFromWindow(v, k), rcv = (~v) & mask;
-        const bool isRc = rcv < f;
-        if (isRc) rcWord |= 1u << (p & 31);
-        int32_t emit;
-        if (window == 1) emit = p;
-        else {
-            const uint64_t h = splitmix64(isRc ? rcv : f);
-            while (size > 0 && qHash[(head + size - 1) & (QCAP - 1)] > h) --size;
-            qPos[(head + size) & (QCAP - 1)] = p; qHash[(head + size) & (QCAP - 1)] = h; ++size;
-            if (qPos[head] <= p - window) {
-                while (qPos[head] <= p - window) { head = (head + 1) & (QCAP - 1); --size; }
-                while (size >= 2 && qHash[head] == qHash[(head + 1) & (QCAP - 1)]) { head = (head + 1) & (QCAP - 1); --size; }
+
+    for (int32_t warm = MIN_WARM;; warm *= 4) {
+        const int32_t start = max(0, c0 - warm);
+        bool locked = start == 0 || window == 1;
+        int head = 0, size = 0;
+        int32_t lastEmitted = -1;
+        uint32_t selWord = 0, rcWord = 0;
+        uint64_t v = windowAt(words, (uint32_t)start, k);
+        bool failed = false;
+        for (int32_t p = start; p < c1; ++p) {
+            if (p > start) {
+                const uint32_t q = (uint32_t)p + k - 1;
+                const uint64_t b = (words[q >> 5] >> ((q & 31) * 2)) & 3ULL;
+                v = (v >> 2) | (b << (2 * k - 2));
             }
-            emit = qPos[head];
+            if (p == c0 && !locked) { failed = true; break; }
+            const uint64_t f = fwdFromWindow(v, k), rcv = (~v) & mask;
+            const bool isRc = rcv < f;
+            if (p >= c0 && isRc) rcWord |= 1u << (p & 31);
+            int32_t emit;
+            if (window == 1) emit = p;
+            else {
+                const uint64_t h = splitmix64(isRc ? rcv : f);
+                while (size > 0 && qHash[(head + size - 1) & (QCAP - 1)] > h) --size;
+                if (!locked && size == 0 && p - start >= window) { locked = true; lastEmitted = -1; }
+                qPos[(head + size) & (QCAP - 1)] = p; qHash[(head + size) & (QCAP - 1)] = h; ++size;
+                if (qPos[head] <= p - window) {
+                    while (qPos[head] <= p - window) { head = (head + 1) & (QCAP - 1); --size; }
+                    while (size >= 2 && qHash[head] == qHash[(head + 1) & (QCAP - 1)]) { head = (head + 1) & (QCAP - 1); --size; }
+                }
+                emit = qPos[head];
+            }
+            if (locked && emit != lastEmitted) {
+                lastEmitted = emit;
+                if (p >= c0) {   // the emissions of this chunk's steps are this thread's to report
+                    if ((emit >> 5) == (p >> 5)) selWord |= 1u << (emit & 31);
+                    else atomicOr(&selBits[base + (emit >> 5)], 1u << (emit & 31));
+                }
+            }
+            if (p >= c0 && ((p & 31) == 31 || p == c1 - 1)) {
+                if (selWord) atomicOr(&selBits[base + (p >> 5)], selWord);
+                rcBits[base + (p >> 5)] = rcWord;
+                selWord = 0; rcWord = 0;
+            }
         }
-        if (emit != lastEmitted) {
-            lastEmitted = emit;
-            // emit <= p and emit > p - 64: it lies in the current bitmap word or the previous one
-            if ((emit >> 5) == (p >> 5)) selWord |= 1u << (emit & 31);
-            else selBits[base + (emit >> 5)] |= 1u << (emit & 31);   // word already flushed by this thread
-        }
-        if ((p & 31) == 31 || p == n - 1) {
-            selBits[base + (p >> 5)] = selWord; rcBits[base + (p >> 5)] = rcWord;
-            selWord = 0; rcWord = 0;
-        }
+        if (!failed) break;
     }
 }
 
@@ -881,9 +903,14 @@ void buildIndexMinimizers(fg_ctx* ctx, int k, int minCov, int window, float repe
     {
         PhaseTimer pt(ctx, "select");
         if (nReadsShard) {
-            minimizerKernel<<<(nReadsShard + 127) / 128, 128, 0, ctx->stream>>>(ctx->dSeq.p, ctx->dWordOff.p, ctx->dLen.p, ctx->dSlotOff.p,
-                                                                               k, window, firstRead, nReadsShard, ctx->dSelBits.p, rcBits.p);
-            checkLaunch(ctx, "minimizerKernel");
+            size_t tLo, tHi;
+            tileRange(ctx, firstRead, nReadsShard, tLo, tHi);
+            const uint32_t nChunks = (uint32_t)(tHi - tLo) * (TILE_SLOTS / MIN_CHUNK);
+            if (nChunks) {
+                minimizerKernel<<<(nChunks + 127) / 128, 128, 0, ctx->stream>>>(ctx->dSeq.p, ctx->dWordOff.p, ctx->dLen.p, ctx->dSlotOff.p,
+                                                                               ctx->dTiles.p + tLo, nChunks, k, window, ctx->dSelBits.p, rcBits.p);
+                checkLaunch(ctx, "minimizerKernel");
+            }
         }
         FG_CUDA(cudaStreamSynchronize(ctx->stream));
     }
