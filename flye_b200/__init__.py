@@ -262,6 +262,9 @@ class Engine:
         else:
             ov = np.zeros(0, dtype=OVERLAP_DTYPE)
         stats = dict(n_hits=res.n_hits, n_pairs=res.n_pairs, n_dp_pairs=res.n_dp_pairs, n_dp_cells=res.n_dp_cells)
+        if keep_alignment:
+            npts = int(res.n_aln_pairs)
+            stats["aln_pairs"] = (np.ctypeslib.as_array(res.aln_pairs, shape=(npts, 2)).copy() if npts else np.zeros((0, 2), np.int32))
         return offsets, ov, stats
 
     # ---- multi-GPU ----
@@ -331,7 +334,7 @@ def dump_index(engine, stats, path):
             f.write("\n")
 
 
-def dump_overlaps(query_ids, offsets, ov, path):
+def dump_overlaps(query_ids, offsets, ov, path, aln_pairs=None):
     bits = ov["seq_divergence"].view(np.uint32)
     with open(path, "w") as f:
         for i, q in enumerate(query_ids):
@@ -341,3 +344,6 @@ def dump_overlaps(query_ids, offsets, ov, path):
                 o = ov[j]
                 f.write("%d %d %d %d %d %d %d %d %d %08x\n" % (o["cur_id"], o["cur_begin"], o["cur_end"], o["cur_len"], o["ext_id"],
                                                               o["ext_begin"], o["ext_end"], o["ext_len"], o["score"], bits[j]))
+                if aln_pairs is not None:
+                    a0, n = int(o["aln_first"]), int(o["aln_count"])
+                    f.write("  aln %d %s\n" % (n, " ".join("%d,%d" % (c, e) for c, e in aln_pairs[a0:a0 + n])))

@@ -523,7 +523,7 @@ __global__ void __launch_bounds__(128) chainWalkKernel(const Elem* __restrict__ 
     if (staged)
         for (int32_t i = lane; i < n; i += 32) { const int32_t b = bkG[i]; sb[i] = b < 0 ? 0 : (unsigned short)(i - b); }
     __syncwarp();
-    auto hasBack = [&](int32_t pos) { return staged ? sb[pos] != 0 : bkG[pos] != -1; };
+    auto hasBack = [&](int32_t pos) { return staged ? sb[pos] != 0 : bkG[pos] >= 0; };
 
     uint32_t nCand = 0;   // meaningful in lane 0
     for (int32_t t0 = 0; t0 < n; t0 += 32) {
@@ -538,7 +538,14 @@ __global__ void __launch_bounds__(128) chainWalkKernel(const Elem* __restrict__ 
                 if (staged) {
                     for (;;) { firstMatch = pos; ++chainLength; const unsigned short d = sb[pos]; sb[pos] = 0; if (!d) break; pos -= d; }
                 } else {
-                    while (pos != -1) { firstMatch = pos; ++chainLength; const int32_t np = bkG[pos]; bkG[pos] = -1; pos = np; }
+                    // consumed nodes keep their pointer recoverable (value -2-np) for the keepAlignment re-walk
+                    while (pos != -1) {
+                        firstMatch = pos; ++chainLength;
+                        const int32_t v = bkG[pos];
+                        const int32_t np = v >= 0 ? v : -1;
+                        if (v >= 0) bkG[pos] = -2 - v;
+                        pos = np;
+                    }
                 }
                 const Elem eF = h[firstMatch], eL = h[chainStart];
                 const int32_t curBegin = elemCur(eF, extSorted), extBegin = elemExt(eF, extSorted);
@@ -550,7 +557,7 @@ __global__ void __launch_bounds__(128) chainWalkKernel(const Elem* __restrict__ 
                     c.score = sc[chainStart] - sc[firstMatch] + k - 1;
                     c.chainLength = chainLength;
                     c.filtered = (int32_t)(filtRank(filtBits, filtPrefix, qbase, hiPos) - filtRank(filtBits, filtPrefix, qbase, loPos));
-                    c.pad = 0;
+                    c.pad = chainStart;
                     cd[nCand++] = c;
                 }
             }
@@ -589,10 +596,11 @@ __global__ void __launch_bounds__(256) gatherOverlapsKernel(const PairInfo* __re
                                                             const uint32_t* __restrict__ qIds, const uint32_t* __restrict__ len,
                                                             const Elem* __restrict__ ord, const Cand* __restrict__ cands,
                                                             const uint32_t* __restrict__ nCand, const uint64_t* __restrict__ outOff,
-                                                            uint32_t qiBase, fg_overlap* __restrict__ out) {
+                                                            uint32_t qiBase, const uint32_t* __restrict__ pairFlags, fg_overlap* __restrict__ out) {
     const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= nPairs) return;
     const PairInfo pi = pairs[pairIds[w]];
+    const unsigned long long extSortedBit = (pairFlags[w] & PAIR_EXTSORTED) ? (1ULL << 63) : 0ULL;
     const uint32_t curId = qIds[pi.qi];
     uint64_t o = outOff[w];
     const uint32_t nc = nCand[w];
@@ -604,9 +612,53 @@ __global__ void __launch_bounds__(256) gatherOverlapsKernel(const PairInfo* __re
         r.cur_id = curId; r.cur_begin = c.curBegin; r.cur_end = c.curEnd; r.cur_len = (int32_t)len[curId >> 1];
         r.ext_id = pi.extId; r.ext_begin = c.extBegin; r.ext_end = c.extEnd; r.ext_len = (int32_t)len[pi.extId >> 1];
         r.score = c.score; r.seq_divergence = 0.f; r.chain_length = c.chainLength; r.filtered_positions = c.filtered;
-        r.edit_distance = -1; r.aln_len = 0; r.aln_first = 0; r.aln_count = 0; r.reserved = pi.qi - qiBase;
+        r.edit_distance = -1; r.aln_len = 0; r.reserved = pi.qi - qiBase;
+        r.aln_first = (unsigned long long)pi.start | extSortedBit;   // scratch for alignKernel: where the pair's matches live ...
+        r.aln_count = (uint32_t)c.pad;                               // ... and the match its chain starts at
         out[o++] = r;
     }
+}
+
+// keepAlignment (overlap.cpp:368-377, 398-405): the (cur,ext) anchors of a kept chain, re-walked from its start through
+// the back pointers (a consumed pointer v < -1 stands for -2-v) down to its first match.  write == false: count only.
+__global__ void __launch_bounds__(256) alignKernel(fg_overlap* __restrict__ ov, uint32_t nOv, const Elem* __restrict__ hits,
+                                                   const int32_t* __restrict__ back, int k, bool write,
+                                                   const uint64_t* __restrict__ alnOff, uint32_t* __restrict__ alnCount,
+                                                   int32_t* __restrict__ alnPairs) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nOv) return;
+    fg_overlap o = ov[i];
+    const bool extSorted = o.aln_first >> 63;
+    const uint32_t start = (uint32_t)(o.aln_first & 0xffffffffULL);
+    const Elem* h = hits + start;
+    const int32_t* bk = back + start;
+    int32_t pos = (int32_t)o.aln_count, cnt = 0, lastCur = 0;
+    // pass 1 (count) or pass 2 (write in reversed order): list = begin, recorded anchors ascending, end
+    int32_t* out = write ? alnPairs + 2 * alnOff[i] : nullptr;
+    const int32_t total = write ? (int32_t)alnCount[i] : 0;
+    for (;;) {
+        const Elem e = h[pos];
+        const int32_t cur = elemCur(e, extSorted), ext = elemExt(e, extSorted);
+        if (cnt == 0 || lastCur - cur > k) {
+            if (write) { const int32_t at = total - 2 - cnt; out[2 * at] = cur; out[2 * at + 1] = ext; }
+            ++cnt; lastCur = cur;
+        }
+        if (cur == o.cur_begin && ext == o.ext_begin) break;
+        const int32_t v = bk[pos];
+        pos = v >= 0 ? v : -2 - v;
+        if (pos < 0) break;   // cannot happen: the chain ends at its first match
+    }
+    if (!write) { alnCount[i] = (uint32_t)cnt + 2u; return; }
+    out[0] = o.cur_begin; out[1] = o.ext_begin;
+    out[2 * (total - 1)] = o.cur_end; out[2 * (total - 1) + 1] = o.ext_end;
+}
+
+__global__ void __launch_bounds__(256) alignFinishKernel(fg_overlap* __restrict__ ov, uint32_t nOv, const uint64_t* __restrict__ alnOff,
+                                                         const uint32_t* __restrict__ alnCount, uint64_t base, bool keep) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nOv) return;
+    ov[i].aln_first = keep ? base + alnOff[i] : 0ULL;
+    ov[i].aln_count = keep ? alnCount[i] : 0u;
 }
 
 // segmented sort driver.  dCounters: 5 device words (layout above) with [0] = nSegs already set and the rest zero.
@@ -730,7 +782,6 @@ static uint32_t selectFlagged(fg_ctx* ctx, const FlagT* flags, uint32_t n, DevBu
 
 void overlapsBatch(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, const fg_overlap_params& prm, fg_overlap_result* result) {
     if (!ctx->indexed) throw Error(FG_ERR_ARG, "no index: call fg_build_index_* first");
-    if (prm.keep_alignment) throw Error(FG_ERR_ARG, "keep_alignment is not implemented on the device path yet");
     ctx->timings.clear(); ctx->timingCalls.clear();
     const int k = ctx->k;
     for (uint32_t i = 0; i < nQ; ++i)
@@ -912,8 +963,34 @@ void overlapsBatch(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, const fg_
             if (nOut) {
                 DevBuf<fg_overlap> dOut(nOut);
                 gatherOverlapsKernel<<<(Pn + 255) / 256, 256, 0, ctx->stream>>>(pairInfo.p, pairIds.p, Pn, dQIds.p, ctx->dLen.p, ord.p, cands.p,
-                                                                               nCand.p, outOff.p, 0, dOut.p);
+                                                                               nCand.p, outOff.p, 0, pairFlags.p, dOut.p);
                 checkLaunch(ctx, "gatherOverlapsKernel");
+                {   // kmerMatches of the kept overlaps, or just clearing the scratch the gather left in aln_first / aln_count
+                    if (nOut >= (1ULL << 31)) throw Error(FG_ERR_ARG, "too many overlaps in one sub-batch");
+                    const uint32_t nO = (uint32_t)nOut;
+                    DevBuf<uint32_t> alnCount(nO); DevBuf<uint64_t> alnOff(nO + 1);
+                    if (prm.keep_alignment) {
+                        alignKernel<<<(nO + 255) / 256, 256, 0, ctx->stream>>>(dOut.p, nO, hits.p, back.p, k, false, nullptr, alnCount.p, nullptr);
+                        checkLaunch(ctx, "alignKernel");
+                        cub::TransformInputIterator<uint64_t, CastU64, const uint32_t*> itc(alnCount.p, CastU64());
+                        exclusiveScanToPlus1(ctx, itc, alnOff.p, nO);
+                        uint64_t nPts = 0;
+                        FG_CUDA(cudaMemcpyAsync(&nPts, alnOff.p + nO, 8, cudaMemcpyDeviceToHost, ctx->stream));
+                        FG_CUDA(cudaStreamSynchronize(ctx->stream));
+                        DevBuf<int32_t> alnPairs(std::max<uint64_t>(2 * nPts, 2));
+                        alignKernel<<<(nO + 255) / 256, 256, 0, ctx->stream>>>(dOut.p, nO, hits.p, back.p, k, true, alnOff.p, alnCount.p, alnPairs.p);
+                        checkLaunch(ctx, "alignKernel");
+                        const uint64_t base = ctx->resAln.size() / 2;
+                        alignFinishKernel<<<(nO + 255) / 256, 256, 0, ctx->stream>>>(dOut.p, nO, alnOff.p, alnCount.p, base, true);
+                        checkLaunch(ctx, "alignFinishKernel");
+                        ctx->resAln.resize(ctx->resAln.size() + 2 * nPts);
+                        FG_CUDA(cudaMemcpyAsync(ctx->resAln.data() + 2 * base, alnPairs.p, 2 * nPts * 4, cudaMemcpyDeviceToHost, ctx->stream));
+                        FG_CUDA(cudaStreamSynchronize(ctx->stream));
+                    } else {
+                        alignFinishKernel<<<(nO + 255) / 256, 256, 0, ctx->stream>>>(dOut.p, nO, nullptr, nullptr, 0, false);
+                        checkLaunch(ctx, "alignFinishKernel");
+                    }
+                }
                 pinned.ensureKeep(nRaw + nOut, nRaw);
                 fg_overlap* dst = pinned.p + nRaw;
                 FG_CUDA(cudaMemcpyAsync(dst, dOut.p, nOut * sizeof(fg_overlap), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1003,8 +1080,8 @@ void overlapsBatch(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, const fg_
     result->n_queries = nQ;
     result->offsets = ctx->resOffsets.data();
     result->overlaps = hOut;
-    result->aln_pairs = nullptr;
-    result->n_aln_pairs = 0;
+    result->aln_pairs = ctx->resAln.empty() ? nullptr : ctx->resAln.data();
+    result->n_aln_pairs = ctx->resAln.size() / 2;
     result->n_hits = totHits; result->n_pairs = totPairs; result->n_dp_pairs = totDpPairs; result->n_dp_cells = totCells;
 }
 

@@ -177,6 +177,12 @@ private:
                 const fg_overlap& o = res.overlaps[i];
                 OverlapRange r(FastaRecord::Id(base + o.cur_id), FastaRecord::Id(base + o.ext_id), o.cur_begin, o.ext_begin, o.cur_len, o.ext_len);
                 r.curEnd = o.cur_end; r.extEnd = o.ext_end; r.score = o.score; r.seqDivergence = o.seq_divergence;
+                if (_keepAlignment && o.aln_count) {
+                    r.kmerMatches = new std::vector<std::pair<int32_t, int32_t>>();
+                    r.kmerMatches->reserve(o.aln_count);
+                    for (uint64_t a = o.aln_first; a < o.aln_first + o.aln_count; ++a)
+                        r.kmerMatches->emplace_back(res.aln_pairs[2 * a], res.aln_pairs[2 * a + 1]);
+                }
                 out[q].push_back(std::move(r));
             }
             // per-10kb-window divergence statistics (overlap.cpp:488-506)

@@ -68,7 +68,8 @@ def median_f32(values):
 
 
 def gpu_pipeline(reads_path, cfg_path, out_prefix, k=None, min_overlap=1000, dump_index=False, both_strands=False,
-                 max_overlaps=0, force_local=False, all_ext=False, estimate=True, engine=None, max_queries=None, min_read_len=None):
+                 max_overlaps=0, force_local=False, all_ext=False, estimate=True, engine=None, max_queries=None, min_read_len=None,
+                 keep_aln=False):
     """Mirror of oracle/harness.cpp on the CUDA path; writes the same dump files.  Returns (engine, info)."""
     import flye_b200 as fb
     cfg = load_cfg(cfg_path)
@@ -109,11 +110,12 @@ def gpu_pipeline(reads_path, cfg_path, out_prefix, k=None, min_overlap=1000, dum
     queries = list(range(0, 2 * len(reads), step))
     if max_queries is not None:
         queries = queries[:max_queries]
-    offs, ov, stats = eng.overlaps(queries, max_divergence=float(max_div), max_overlaps=max_overlaps, force_local=force_local, **common)
+    offs, ov, stats = eng.overlaps(queries, max_divergence=float(max_div), max_overlaps=max_overlaps, force_local=force_local,
+                                   keep_alignment=keep_aln, **common)
     info["t_overlaps"] = eng.timings()
     info["ovl_stats"] = stats
     info["n_overlaps"] = int(offs[-1])
-    fb.dump_overlaps(queries, offs, ov, out_prefix + ".ovlp")
+    fb.dump_overlaps(queries, offs, ov, out_prefix + ".ovlp", aln_pairs=stats.pop("aln_pairs", None))
     return eng, info
 
 

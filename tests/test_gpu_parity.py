@@ -79,7 +79,9 @@ def test_clr_options(engine, tmp_path):
     tmp = str(tmp_path)
     reads = pu.simulate(os.path.join(tmp, "r.fasta"), genome_len=120000, coverage=15, seed=3)
     for opts, kw in [(["--both-strands", "--force-local", "--max-overlaps", "5"], dict(both_strands=True, force_local=True, max_overlaps=5)),
-                     (["--all-ext"], dict(all_ext=True))]:
+                     (["--all-ext"], dict(all_ext=True)),
+                     (["--all-ext", "--keep-aln"], dict(all_ext=True, keep_aln=True)),
+                     (["--keep-aln", "--both-strands"], dict(keep_aln=True, both_strands=True))]:
         pu.run_oracle(reads, RAW, os.path.join(tmp, "ref"), k=15, extra=opts)
         pu.gpu_pipeline(reads, RAW, os.path.join(tmp, "gpu"), k=15, engine=engine, **kw)
         res = _compare(tmp, "clr_opts %s" % opts, ["ovlp"])
@@ -171,3 +173,27 @@ def test_hifi_1mb_parity(engine, tmp_path):
     res = _compare(tmp, "hifi_1mb", ["ovlp"])
     assert ref["overlaps"] > 20000
     assert res == {"ovlp": 0}
+
+
+def test_metagenome_uneven_coverage_parity(engine, tmp_path):
+    """BASELINE config 4 code path at small scale: several genomes with log-distributed coverage (4x .. 16x), k = 15;
+    the reference uses buildIndexUnevenCoverage for every solid-k-mer run"""
+    tmp = str(tmp_path)
+    reads = pu.simulate(os.path.join(tmp, "r.fasta"), coverage=0, mean_len=9000, error=0.10, seed=4,
+                        extra=["--meta", "6", "--meta-total", "600000"])
+    ref = pu.run_oracle(reads, RAW, os.path.join(tmp, "ref"), k=15, extra=["--dump-index"])
+    _, info = pu.gpu_pipeline(reads, RAW, os.path.join(tmp, "gpu"), k=15, dump_index=True, engine=engine)
+    res = _compare(tmp, "meta", ["hist", "index", "ovlp"])
+    assert ref["overlaps"] > 2000
+    assert res == {"hist": 0, "index": 0, "ovlp": 0}
+
+
+def test_ont_like_k17_parity(engine, tmp_path):
+    """BASELINE config 3 code path at small scale: ONT-like reads (10 % error, mean 19 kb), cfg default k = 17"""
+    tmp = str(tmp_path)
+    reads = pu.simulate(os.path.join(tmp, "r.fasta"), genome_len=300000, coverage=20, mean_len=19000, error=0.10, seed=3)
+    ref = pu.run_oracle(reads, RAW, os.path.join(tmp, "ref"), binary=pu.RESTATE, extra=["--dump-index"])
+    _, info = pu.gpu_pipeline(reads, RAW, os.path.join(tmp, "gpu"), dump_index=True, engine=engine)
+    res = _compare(tmp, "ont_k17", ["hist", "index", "ovlp"])
+    assert ref["overlaps"] > 2000
+    assert res == {"hist": 0, "index": 0, "ovlp": 0}
