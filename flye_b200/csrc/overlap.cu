@@ -780,22 +780,12 @@ static uint32_t selectFlagged(fg_ctx* ctx, const FlagT* flags, uint32_t n, DevBu
     return h;
 }
 
-void overlapsBatch(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, const fg_overlap_params& prm, fg_overlap_result* result) {
-    if (!ctx->indexed) throw Error(FG_ERR_ARG, "no index: call fg_build_index_* first");
-    ctx->timings.clear(); ctx->timingCalls.clear();
+// one chunk of queries (< 2^30 k-mer slots): lookup, expansion and the per-sub-batch pipeline; the raw overlap records are
+// appended to the context's pinned buffer with `reserved` = position of the query in the whole call
+static void overlapsChunk(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, uint32_t qOffset, const fg_overlap_params& prm, const OvParams& P,
+                          size_t& nRaw, uint64_t& totHits, uint64_t& totPairs, uint64_t& totDpPairs, uint64_t& totCells) {
     const int k = ctx->k;
-    for (uint32_t i = 0; i < nQ; ++i)
-        if (queryIds[i] >= 2 * ctx->nReads) throw Error(FG_ERR_ARG, "query id out of range");
-
-    OvParams P;
-    P.k = k; P.maxJump = prm.max_jump; P.minOverlap = prm.min_overlap; P.maxOverhang = prm.max_overhang;
-    P.checkOverhang = prm.max_overhang > 0; P.forceLocal = prm.force_local != 0; P.onlyMaxExt = prm.only_max_ext != 0;
-    { volatile float a = 0.01f; volatile float m = a * prm.min_overlap; P.minUniqueF = m; }   // minKmerSruvivalRate * _minOverlap
-
-    ctx->resOffsets.assign(nQ + 1, 0);
-    ctx->resOverlaps.clear();
-    ctx->resAln.clear();
-    uint64_t totHits = 0, totPairs = 0, totDpPairs = 0, totCells = 0;
+    PinnedBuf<fg_overlap>& pinned = ctx->pinnedOut;
 
     // query slot space and tiles
     std::vector<uint64_t> hQSlotOff(nQ + 1, 0);
@@ -841,15 +831,11 @@ void overlapsBatch(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, const fg_
             FG_CUDA(cudaStreamSynchronize(ctx->stream));
         }
     }
-    totHits = hQHitOff[nQ];
+    totHits += hQHitOff[nQ];
 
     // sub-batches of consecutive queries with a bounded number of hits
     uint64_t budget = 256ULL << 20;
     if (const char* e = getenv("FG_HIT_BUDGET")) budget = std::max<uint64_t>(1024, strtoull(e, nullptr, 10));
-    PinnedBuf<fg_overlap>& pinned = ctx->pinnedOut;   // all sub-batches land here; the epilogue compacts in place
-    size_t nRaw = 0;
-    HostTimer hostAll(ctx, "host_total");
-    const uint64_t mallocs0 = ctx->arena.mallocCalls;
     DevBuf<Elem> hits, ord; DevBuf<int32_t> score, back; DevBuf<Cand> cands; DevBuf<uint8_t> flags;
     DevBuf<uint32_t> gStart, candIds, pairIds;
     SortWorkspace ws; DevBuf<Seg> segsQ;
@@ -963,7 +949,7 @@ void overlapsBatch(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, const fg_
             if (nOut) {
                 DevBuf<fg_overlap> dOut(nOut);
                 gatherOverlapsKernel<<<(Pn + 255) / 256, 256, 0, ctx->stream>>>(pairInfo.p, pairIds.p, Pn, dQIds.p, ctx->dLen.p, ord.p, cands.p,
-                                                                               nCand.p, outOff.p, 0, pairFlags.p, dOut.p);
+                                                                               nCand.p, outOff.p, 0u - qOffset, pairFlags.p, dOut.p);
                 checkLaunch(ctx, "gatherOverlapsKernel");
                 {   // kmerMatches of the kept overlaps, or just clearing the scratch the gather left in aln_first / aln_count
                     if (nOut >= (1ULL << 31)) throw Error(FG_ERR_ARG, "too many overlaps in one sub-batch");
@@ -1006,6 +992,45 @@ void overlapsBatch(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, const fg_
             }
         }
         qa = qb;
+    }
+
+}
+
+void overlapsBatch(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, const fg_overlap_params& prm, fg_overlap_result* result) {
+    if (!ctx->indexed) throw Error(FG_ERR_ARG, "no index: call fg_build_index_* first");
+    ctx->timings.clear(); ctx->timingCalls.clear();
+    const int k = ctx->k;
+    for (uint32_t i = 0; i < nQ; ++i)
+        if (queryIds[i] >= 2 * ctx->nReads) throw Error(FG_ERR_ARG, "query id out of range");
+
+    OvParams P;
+    P.k = k; P.maxJump = prm.max_jump; P.minOverlap = prm.min_overlap; P.maxOverhang = prm.max_overhang;
+    P.checkOverhang = prm.max_overhang > 0; P.forceLocal = prm.force_local != 0; P.onlyMaxExt = prm.only_max_ext != 0;
+    { volatile float a = 0.01f; volatile float m = a * prm.min_overlap; P.minUniqueF = m; }   // minKmerSruvivalRate * _minOverlap
+
+    ctx->resOffsets.assign(nQ + 1, 0);
+    ctx->resOverlaps.clear();
+    ctx->resAln.clear();
+    uint64_t totHits = 0, totPairs = 0, totDpPairs = 0, totCells = 0;
+    PinnedBuf<fg_overlap>& pinned = ctx->pinnedOut;   // all chunks / sub-batches land here; the epilogue compacts in place
+    size_t nRaw = 0;
+    HostTimer hostAll(ctx, "host_total");
+    const uint64_t mallocs0 = ctx->arena.mallocCalls;
+
+    // chunks of consecutive queries with < 2^30 k-mer slots each (device arrays are indexed with 32-bit counts)
+    uint64_t chunkSlots = 1ULL << 30;
+    if (const char* e = getenv("FG_CHUNK_SLOTS")) chunkSlots = std::max<uint64_t>(4096, std::min<uint64_t>(chunkSlots, strtoull(e, nullptr, 10)));
+    for (uint32_t q0 = 0; q0 < nQ;) {
+        uint64_t slots = 0;
+        uint32_t q1 = q0;
+        while (q1 < nQ) {
+            const uint32_t L = ctx->hLen[queryIds[q1] >> 1];
+            const uint64_t add = L > (uint32_t)k ? ((uint64_t)(L - k) + 31u) & ~31ULL : 0;
+            if (q1 > q0 && slots + add >= chunkSlots) break;
+            slots += add; ++q1;
+        }
+        overlapsChunk(ctx, queryIds + q0, q1 - q0, q0, prm, P, nRaw, totHits, totPairs, totDpPairs, totCells);
+        q0 = q1;
     }
 
     // host epilogue: divergence (overlap.cpp:417-423), threshold (:470), maxOverlaps (:218-219)

@@ -27,6 +27,7 @@ def run_mirror(reads, cfg, out, k=None, extra=()):
 @pytest.mark.parametrize("cfg,k,sim,opts,exts", [
     (RAW, 15, dict(genome_len=80000, coverage=12, seed=41), ["--dump-index"], ["hist", "index", "ovlp"]),
     (RAW, 15, dict(genome_len=80000, coverage=12, seed=42), ["--find-all"], ["ovlp"]),        # closure + cluster filter, multisets
+    (RAW, 15, dict(genome_len=60000, coverage=12, seed=44), ["--all-ext", "--keep-aln"], ["ovlp"]),   # kmerMatches through the mirror
     (HIFI, None, dict(genome_len=60000, coverage=10, mean_len=8000, shape=20, error=0.005, seed=43), ["--both-strands"], ["ovlp"]),
 ])
 def test_reference_harness_source_runs_on_the_mirror(built, tmp_path, cfg, k, sim, opts, exts):

@@ -152,11 +152,13 @@ def test_clr_quarter_scale_parity(engine, tmp_path):
     tmp = str(tmp_path)
     reads = pu.simulate(os.path.join(tmp, "r.fasta"), genome_len=1150000, coverage=50, seed=1)
     ref = pu.run_oracle(reads, RAW, os.path.join(tmp, "ref"), k=15)
-    os.environ["FG_HIT_BUDGET"] = str(24 << 20)   # force several sub-batches
+    os.environ["FG_HIT_BUDGET"] = str(24 << 20)     # force several sub-batches ...
+    os.environ["FG_CHUNK_SLOTS"] = str(20 << 20)    # ... inside several query chunks
     try:
         _, info = pu.gpu_pipeline(reads, RAW, os.path.join(tmp, "gpu"), k=15, engine=engine)
     finally:
         del os.environ["FG_HIT_BUDGET"]
+        del os.environ["FG_CHUNK_SLOTS"]
     print(info)
     res = _compare(tmp, "clr_quarter", ["hist", "ovlp"])
     assert ref["overlaps"] > 100000
