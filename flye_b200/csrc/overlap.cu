@@ -392,25 +392,35 @@ __global__ void __launch_bounds__(256) pairPrepKernel(Elem* __restrict__ hits, c
 __device__ __forceinline__ int32_t elemCur(const Elem& e, bool extSorted) { return extSorted ? (int32_t)e.val : (int32_t)(uint32_t)e.key; }
 __device__ __forceinline__ int32_t elemExt(const Elem& e, bool extSorted) { return extSorted ? (int32_t)(uint32_t)e.key : (int32_t)e.val; }
 
-// (b) chaining DP (overlap.cpp:277-323): one HALF-WARP (16 lanes) per pair, two pairs per warp.  The lanes of a half
-// evaluate 16 predecessors j = i-1, i-2, ... per step in the reference's traversal order; the first lane that breaks
-// ends the scan.  The last 16 matches (cur, ext, score) live in lane registers (match j in sub-lane j%16) and reach
-// the lanes by shuffle, so the common case (a look-back of ~10 matches) never waits for memory; longer look-backs
-// continue from global memory.  Break rule 1 (jumpDiv == 0 && dc < k on an IMPROVING predecessor) is tested with one
-// warp reduction per candidate instead of a prefix-max scan.  Pairs are visited in order of decreasing size
-// (pairOrder) so that the two halves of a warp finish together.
+// (b) chaining DP (overlap.cpp:277-323): one HALF-WARP (16 lanes) per pair, two pairs per warp, both halves in lock
+// step so that every collective uses the full-warp mask (partial masks compile to a slow WARPSYNC/COLLECTIVE path).  The
+// lanes of a half evaluate 16 predecessors j = i-1, i-2, ... per step in the reference's traversal order; the first
+// lane that breaks ends the scan.  The last 16 matches (cur, ext, score) live in lane registers (match j in sub-lane
+// j%16) and reach the lanes by shuffle, so the common case (a look-back of ~10 matches) never waits for memory; longer
+// look-backs continue from global memory.  Break rule 1 (jumpDiv == 0 && dc < k on an IMPROVING predecessor) is tested
+// with warp reductions per candidate instead of a prefix-max scan.  Pairs are visited in order of decreasing size
+// (pairOrder) so that the two halves of a warp have the same number of matches to go through.
+__device__ __forceinline__ int32_t halfMax(int32_t v, bool upper) {   // max over the 16 lanes of the caller's half
+    const int32_t a = __reduce_max_sync(0xffffffffu, upper ? INT32_MIN : v);
+    const int32_t b = __reduce_max_sync(0xffffffffu, upper ? v : INT32_MIN);
+    return upper ? b : a;
+}
+
 __global__ void __launch_bounds__(128) chainDpKernel(const Elem* __restrict__ hits, const PairInfo* __restrict__ pairs, const uint32_t* __restrict__ pairIds,
                                                      const uint32_t* __restrict__ pairOrder, uint32_t nPairs, const uint32_t* __restrict__ pairFlags,
                                                      OvParams P, int32_t* __restrict__ score, int32_t* __restrict__ back, Elem* __restrict__ ord,
                                                      unsigned long long* __restrict__ cellCount) {
     const uint32_t slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;   // half-warp index
-    if (slot >= nPairs) return;
-    const uint32_t w = pairOrder[slot];
     const int sl = threadIdx.x & 15;
-    const uint32_t hm = 0xffffu << (threadIdx.x & 16);                     // the lanes of this half
-    const PairInfo pi = pairs[pairIds[w]];
-    const bool extSorted = pairFlags[w] & PAIR_EXTSORTED;
+    const bool upper = threadIdx.x & 16;
+    const int hs = threadIdx.x & 16;                                       // bit offset of this half in a ballot
+    const bool valid = slot < nPairs;
+    const uint32_t w = valid ? pairOrder[slot] : 0u;
+    PairInfo pi; pi.start = 0; pi.n = 0; pi.qi = 0; pi.extId = 0;
+    if (valid) pi = pairs[pairIds[w]];
+    const bool extSorted = valid && (pairFlags[w] & PAIR_EXTSORTED);
     const int32_t n = (int32_t)pi.n;
+    const int32_t nMax = max(n, __shfl_xor_sync(0xffffffffu, n, 16));
     const int k = P.k;
     const Elem* h = hits + pi.start;
     int32_t* sc = score + pi.start; int32_t* bk = back + pi.start; Elem* od = ord + pi.start;
@@ -420,27 +430,30 @@ __global__ void __launch_bounds__(128) chainDpKernel(const Elem* __restrict__ hi
     if (sl < n) { const Elem e = h[sl]; nxC = elemCur(e, extSorted); nxE = elemExt(e, extSorted); }
     if (16 + sl < n) { const Elem e = h[16 + sl]; pfC = elemCur(e, extSorted); pfE = elemExt(e, extSorted); }
     int32_t wC = nxC, wE = nxE, wS = 0;   // window registers: sub-lane 0 holds match 0 (score 0); others not yet valid
-    if (sl == 0) { sc[0] = 0; bk[0] = -1; Elem t; t.key = 0x7fffffffULL; t.val = 0; t.aux = 0; od[0] = t; }
+    if (sl == 0 && n > 0) { sc[0] = 0; bk[0] = -1; Elem t; t.key = 0x7fffffffULL; t.val = 0; t.aux = 0; od[0] = t; }
     unsigned long long cells = 0;
-    for (int32_t i = 1; i < n; ++i) {
+    for (int32_t i = 1; i < nMax; ++i) {
+        const bool act = i < n;
         const int l0 = i & 15;
         if (l0 == 0) {
             nxC = pfC; nxE = pfE;
             const int32_t nb = i + 16 + sl;
             if (nb < n) { const Elem e = h[nb]; pfC = elemCur(e, extSorted); pfE = elemExt(e, extSorted); }
         }
-        const int32_t curN = __shfl_sync(hm, nxC, l0, 16), extN = __shfl_sync(hm, nxE, l0, 16);
+        const int32_t curN = __shfl_sync(0xffffffffu, nxC, l0, 16), extN = __shfl_sync(0xffffffffu, nxE, l0, 16);
         int32_t best = 0, bestId = 0;
-        bool stop = false;
-        for (int32_t jb = i - 1; jb >= 0 && !stop; jb -= 16) {
+        bool stop = !act;
+        for (int32_t jb = i - 1;; jb -= 16) {
+            const bool live = !stop && jb >= 0;                            // uniform inside a half
+            if (!__any_sync(0xffffffffu, live)) break;
             const int32_t j = jb - sl;
-            const bool in = j >= 0;
+            const bool in = live && j >= 0;
             int32_t cj, ej, sj;
             if (jb == i - 1) {   // the 16 most recent matches: registers
                 const int src = j & 15;
-                cj = __shfl_sync(hm, wC, src, 16); ej = __shfl_sync(hm, wE, src, 16); sj = __shfl_sync(hm, wS, src, 16);
+                cj = __shfl_sync(0xffffffffu, wC, src, 16); ej = __shfl_sync(0xffffffffu, wE, src, 16); sj = __shfl_sync(0xffffffffu, wS, src, 16);
             } else {
-                if (jb == i - 17) __syncwarp(hm);   // order sub-lane 0's score stores before these loads
+                if (jb == i - 17) __syncwarp();   // order sub-lane 0's score stores before these loads
                 cj = 0; ej = 0; sj = 0;
                 if (in) { const Elem e = h[j]; cj = elemCur(e, extSorted); ej = elemExt(e, extSorted); sj = sc[j]; }
             }
@@ -450,30 +463,35 @@ __global__ void __launch_bounds__(128) chainDpKernel(const Elem* __restrict__ hi
             const int32_t gap = jd > 100 ? 2 * jd : (jd >> 1);            // int32(float(LG_GAP|SM_GAP) * jd), :299
             const int32_t s = ok ? sj + min(min(dc, de), k) - gap : INT32_MIN;
             // second break rule (sorted-axis distance) first: nothing beyond its first lane is ever evaluated
-            const uint32_t far = (__ballot_sync(hm, in && (extSorted ? de : dc) > P.maxJump) >> (threadIdx.x & 16)) & 0xffffu;
+            const uint32_t far = (__ballot_sync(0xffffffffu, in && (extSorted ? de : dc) > P.maxJump) >> hs) & 0xffffu;
             int stopLane = far ? (__ffs(far) - 1) : 15;
             bool brk = far != 0;
-            uint32_t pot = (__ballot_sync(hm, ok && jd == 0 && dc < k) >> (threadIdx.x & 16)) & ((2u << stopLane) - 1u);
-            while (pot) {
-                const int t = __ffs(pot) - 1;
-                const int32_t prior = max(best, __reduce_max_sync(hm, sl < t ? s : INT32_MIN));
-                if (__shfl_sync(hm, s, t, 16) > prior) { stopLane = t; brk = true; break; }
-                pot &= pot - 1;
+            uint32_t pot = (__ballot_sync(0xffffffffu, ok && jd == 0 && dc < k) >> hs) & ((2u << stopLane) - 1u);
+            while (__any_sync(0xffffffffu, pot != 0)) {
+                const int t = pot ? (__ffs(pot) - 1) : 0;
+                const int32_t prior = max(best, halfMax((pot && sl < t) ? s : INT32_MIN, upper));
+                const int32_t st = __shfl_sync(0xffffffffu, s, t, 16);
+                if (pot) {
+                    if (st > prior) { stopLane = t; brk = true; pot = 0; }
+                    else pot &= pot - 1;
+                }
             }
             const bool part = ok && sl <= stopLane;
-            const int32_t mx = __reduce_max_sync(hm, part ? s : INT32_MIN);
-            if (mx > best) {
-                const uint32_t wm = (__ballot_sync(hm, part && s == mx) >> (threadIdx.x & 16)) & 0xffffu;
-                best = mx; bestId = jb - (__ffs(wm) - 1);
+            const int32_t mx = halfMax(part ? s : INT32_MIN, upper);
+            const uint32_t wm = (__ballot_sync(0xffffffffu, part && s == mx) >> hs) & 0xffffu;
+            if (live) {
+                if (mx > best) { best = mx; bestId = jb - (__ffs(wm) - 1); }
+                cells += min(jb + 1, stopLane + 1);
+                stop = brk;
             }
-            cells += min(jb + 1, stopLane + 1);
-            stop = brk;
         }
-        const int32_t sci = max(best, k);
-        if (sl == l0) { wC = curN; wE = extN; wS = sci; }   // match i replaces match i-16 in the window
-        if (sl == 0) {
-            sc[i] = sci; bk[i] = best > k ? bestId : -1;
-            Elem t; t.key = (unsigned long long)(0x7fffffff - sci); t.val = (unsigned int)i; t.aux = 0; od[i] = t;   // (c) input of the score sort
+        if (act) {
+            const int32_t sci = max(best, k);
+            if (sl == l0) { wC = curN; wE = extN; wS = sci; }   // match i replaces match i-16 in the window
+            if (sl == 0) {
+                sc[i] = sci; bk[i] = best > k ? bestId : -1;
+                Elem t; t.key = (unsigned long long)(0x7fffffff - sci); t.val = (unsigned int)i; t.aux = 0; od[i] = t;   // (c) input of the score sort
+            }
         }
     }
     if (sl == 0 && cells) atomicAdd(cellCount, cells);
@@ -917,7 +935,7 @@ static void overlapsChunk(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, ui
                 FG_CUDA(cub::DeviceRadixSort::SortPairs(tmpS.p, tb, dk, dv, (int)Pn, 0, 32, ctx->stream));
                 ctx->launches += 5;
                 chainDpKernel<<<(Pn + 7) / 8, 128, 0, ctx->stream>>>(hits.p, pairInfo.p, pairIds.p, dv.Current(), Pn, pairFlags.p, P, score.p,
-                                                                    back.p, ord.p, dCells.p);
+                                                                    back.p, ord.p, dCells.p);   // whole warps: no early exit inside
                 checkLaunch(ctx, "chainDpKernel");
             }
             FG_CUDA(cudaMemcpyAsync(counters.p + 16, &Pn, 4, cudaMemcpyHostToDevice, ctx->stream));
