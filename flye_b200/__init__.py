@@ -19,7 +19,7 @@ ERR_NAMES = {-1: "FG_ERR_CUDA", -2: "FG_ERR_ARG", -3: "FG_ERR_KMER_SIZE", -4: "F
 
 # every symbol include/flye_b200.h declares
 SYMBOLS = ["fg_ctx_create", "fg_ctx_destroy", "fg_last_error", "fg_stream", "fg_kernel_launches", "fg_last_timings",
-           "fg_reads_upload", "fg_reads_upload_ascii", "fg_count_kmers", "fg_kmer_hist", "fg_kmer_freq",
+           "fg_reads_upload", "fg_reads_upload_ascii", "fg_queries_upload", "fg_count_kmers", "fg_kmer_hist", "fg_kmer_freq",
            "fg_build_index_solid", "fg_build_index_minimizers", "fg_index_clear", "fg_index_lookup",
            "fg_index_positions", "fg_index_export", "fg_overlaps_batch", "fg_comm_unique_id", "fg_comm_init",
            "fg_comm_set_shard", "fg_debug_warp_sort", "fg_debug_edit_distance"]
@@ -34,7 +34,7 @@ class OverlapParams(C.Structure):
     _fields_ = [("max_jump", C.c_int32), ("min_overlap", C.c_int32), ("max_overhang", C.c_int32),
                 ("max_overlaps", C.c_int32), ("force_local", C.c_int32), ("keep_alignment", C.c_int32),
                 ("only_max_ext", C.c_int32), ("nucl_alignment", C.c_int32), ("use_hpc", C.c_int32),
-                ("max_divergence", C.c_float)]
+                ("max_divergence", C.c_float), ("query_set", C.c_int32)]
 
 
 OVERLAP_DTYPE = np.dtype([("cur_id", "<u4"), ("cur_begin", "<i4"), ("cur_end", "<i4"), ("cur_len", "<i4"),
@@ -76,6 +76,7 @@ def load_lib():
     lib.fg_last_timings.argtypes = [vp, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.POINTER(C.c_int), C.c_int]
     lib.fg_reads_upload.argtypes = [vp, u64p, u64p, u32p, C.c_uint32]
     lib.fg_reads_upload_ascii.argtypes = [vp, C.c_char_p, u64p, C.c_uint32]
+    lib.fg_queries_upload.argtypes = [vp, u64p, u64p, u32p, C.c_uint32]
     lib.fg_count_kmers.argtypes = [vp, C.c_int, u64p]
     lib.fg_kmer_hist.argtypes = [vp, u64p, u64p, u64p]
     lib.fg_kmer_freq.argtypes = [vp, u64p, C.c_uint32, u32p]
@@ -194,6 +195,11 @@ class Engine:
                                              _ptr(lengths, C.c_uint32), len(lengths)))
         self.n_reads, self.lengths = len(lengths), lengths.copy()
 
+    def upload_queries(self, reads):
+        """second sequence set (list of ASCII reads) for query_set=1 calls"""
+        packed, offs, lens = pack_reads(reads)
+        self._check(self.lib.fg_queries_upload(self.ctx, _ptr(packed, C.c_uint64), _ptr(offs, C.c_uint64), _ptr(lens, C.c_uint32), len(lens)))
+
     def upload_ascii(self, reads):
         buf = b"".join(reads)
         offs = np.zeros(len(reads) + 1, dtype=np.uint64)
@@ -243,11 +249,12 @@ class Engine:
 
     # ---- overlaps ----
     def overlaps(self, query_ids, max_jump=1500, min_overlap=1000, max_overhang=1500, max_overlaps=0, force_local=False,
-                 keep_alignment=False, only_max_ext=True, nucl_alignment=False, use_hpc=False, max_divergence=1.0, copy=True):
+                 keep_alignment=False, only_max_ext=True, nucl_alignment=False, use_hpc=False, max_divergence=1.0, copy=True,
+                 query_set=0):
         """copy=False returns views into library-owned memory, valid until the next overlaps() call"""
         q = np.ascontiguousarray(query_ids, dtype=np.uint32)
         p = OverlapParams(max_jump, min_overlap, max_overhang, max_overlaps, int(force_local), int(keep_alignment),
-                          int(only_max_ext), int(nucl_alignment), int(use_hpc), max_divergence)
+                          int(only_max_ext), int(nucl_alignment), int(use_hpc), max_divergence, int(query_set))
         res = OverlapResult()
         self._check(self.lib.fg_overlaps_batch(self.ctx, _ptr(q, C.c_uint32), len(q), C.byref(p), C.byref(res)))
         offsets = np.ctypeslib.as_array(res.offsets, shape=(len(q) + 1,))

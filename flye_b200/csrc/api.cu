@@ -148,6 +148,27 @@ int fg_reads_upload(fg_ctx* ctx, const uint64_t* packed, const uint64_t* wordOff
     });
 }
 
+int fg_queries_upload(fg_ctx* ctx, const uint64_t* packed, const uint64_t* wordOffsets, const uint32_t* lengths, uint32_t n) {
+    return guarded(ctx, [&] {
+        if (n && (!packed || !wordOffsets || !lengths)) throw Error(FG_ERR_ARG, "null input");
+        ctx->hQsLen.assign(lengths, lengths + n);
+        std::vector<uint64_t> off(n + 1, 0);
+        for (uint32_t i = 0; i < n; ++i) off[i + 1] = off[i] + (lengths[i] + 31) / 32;
+        ctx->dQsSeq.alloc(off[n] + 4);
+        ctx->dQsWordOff.alloc(n + 1);
+        ctx->dQsLen.alloc(std::max<uint32_t>(n, 1));
+        FG_CUDA(cudaMemsetAsync(ctx->dQsSeq.p + off[n], 0, 4 * 8, ctx->stream));
+        for (uint32_t i = 0; i < n; ++i)
+            if (off[i + 1] > off[i])
+                FG_CUDA(cudaMemcpyAsync(ctx->dQsSeq.p + off[i], packed + wordOffsets[i], (off[i + 1] - off[i]) * 8, cudaMemcpyHostToDevice,
+                                        ctx->stream));
+        FG_CUDA(cudaMemcpyAsync(ctx->dQsWordOff.p, off.data(), (n + 1) * 8ULL, cudaMemcpyHostToDevice, ctx->stream));
+        if (n) FG_CUDA(cudaMemcpyAsync(ctx->dQsLen.p, lengths, n * 4ULL, cudaMemcpyHostToDevice, ctx->stream));
+        FG_CUDA(cudaStreamSynchronize(ctx->stream));
+        ctx->nQsReads = n;
+    });
+}
+
 int fg_reads_upload_ascii(fg_ctx* ctx, const char* bases, const uint64_t* baseOffsets, uint32_t n) {
     return guarded(ctx, [&] {
         if (n && (!bases || !baseOffsets)) throw Error(FG_ERR_ARG, "null input");

@@ -23,6 +23,13 @@ struct fg_ctx {
     fg::DevBuf<uint64_t> dWordOff;        // nReads+1
     fg::DevBuf<uint32_t> dLen;            // nReads
 
+    // ---- optional second sequence set: queries that are not part of the indexed reads (read-to-graph alignment,
+    //      reference: OverlapContainer(detector, queryContainer) with queryContainer != the indexed container) ----
+    uint32_t nQsReads = 0;
+    std::vector<uint32_t> hQsLen;
+    fg::DevBuf<uint64_t> dQsSeq, dQsWordOff;
+    fg::DevBuf<uint32_t> dQsLen;
+
     // ---- k-mer slot space: read i owns slots [slotOff[i], slotOff[i]+n_i), n_i = max(L_i-k,0) (kmer.h:185-198),
     //      slotOff is a prefix of roundup32(n_i) so that every read owns whole 32-bit bitmap words ----
     int k = 0;
@@ -141,7 +148,8 @@ void groupStart();
 void groupEnd();
 inline bool sharded(const fg_ctx* ctx) { return ctx->nRanks > 1 && ctx->ncclComm && ctx->shardSet; }
 
-void editDistances(fg_ctx* ctx, fg_overlap* dOv, const fg_overlap* hOv, uint32_t nOv, bool useHpc);
+void editDistances(fg_ctx* ctx, fg_overlap* dOv, const fg_overlap* hOv, uint32_t nOv, bool useHpc, const uint64_t* qSeq,
+                   const uint64_t* qWordOff, const uint32_t* qLen);
 int debugEditDistance(fg_ctx* ctx, const uint8_t* a, int n, const uint8_t* b, int m);
 void debugWarpSort(fg_ctx* ctx, uint64_t* keys, uint32_t* vals, const uint64_t* segOffsets, uint32_t nSegs);
 

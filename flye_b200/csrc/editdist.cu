@@ -25,7 +25,9 @@ __device__ __forceinline__ uint32_t baseOf(const uint64_t* __restrict__ words, u
 struct EdJob { uint64_t offA, offB; };   // byte offsets of the two compressed sequences in the scratch
 
 __global__ void __launch_bounds__(256) hpcKernel(const uint64_t* __restrict__ seq, const uint64_t* __restrict__ wordOff,
-                                                 const uint32_t* __restrict__ len, const fg_overlap* __restrict__ ov, uint32_t nOv,
+                                                 const uint32_t* __restrict__ len, const uint64_t* __restrict__ qseq,
+                                                 const uint64_t* __restrict__ qWordOff, const uint32_t* __restrict__ qlen,
+                                                 const fg_overlap* __restrict__ ov, uint32_t nOv,
                                                  const EdJob* __restrict__ jobs, bool compress, uint8_t* __restrict__ scratch,
                                                  uint32_t* __restrict__ outLen) {
     const uint32_t w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -36,9 +38,9 @@ __global__ void __launch_bounds__(256) hpcKernel(const uint64_t* __restrict__ se
     const uint32_t id = side ? o.ext_id : o.cur_id;
     const uint32_t start = (uint32_t)(side ? o.ext_begin : o.cur_begin);
     const uint32_t n = (uint32_t)(side ? (o.ext_end - o.ext_begin) : (o.cur_end - o.cur_begin));
-    const uint32_t r = id >> 1, L = len[r];
+    const uint32_t r = id >> 1, L = side ? len[r] : qlen[r];   // side 0 = the query ("cur"), possibly from the second set
     const bool strand = id & 1;
-    const uint64_t* words = seq + wordOff[r];
+    const uint64_t* words = side ? seq + wordOff[r] : qseq + qWordOff[r];
     uint8_t* dst = scratch + (side ? jobs[w >> 1].offB : jobs[w >> 1].offA);
     uint32_t out = 0;
     for (uint32_t i0 = 0; i0 < n; i0 += 32) {
@@ -153,7 +155,8 @@ __global__ void __launch_bounds__(128) wfaKernel(fg_overlap* __restrict__ ov, ui
 }
 
 // device overlaps (already gathered) -> edit_distance / aln_len filled in
-void editDistances(fg_ctx* ctx, fg_overlap* dOv, const fg_overlap* hOv, uint32_t nOv, bool useHpc) {
+void editDistances(fg_ctx* ctx, fg_overlap* dOv, const fg_overlap* hOv, uint32_t nOv, bool useHpc, const uint64_t* qSeq,
+                   const uint64_t* qWordOff, const uint32_t* qLen) {
     if (!nOv) return;
     std::vector<EdJob> jobs(nOv);
     uint64_t off = 0; uint32_t maxLen = 0;
@@ -168,7 +171,8 @@ void editDistances(fg_ctx* ctx, fg_overlap* dOv, const fg_overlap* hOv, uint32_t
     DevBuf<uint32_t> hpcLen(2 * (size_t)nOv), nextJob(1);
     FG_CUDA(cudaMemcpyAsync(dJobs.p, jobs.data(), nOv * sizeof(EdJob), cudaMemcpyHostToDevice, ctx->stream));
     FG_CUDA(cudaMemsetAsync(nextJob.p, 0, 4, ctx->stream));
-    hpcKernel<<<(2 * nOv + 7) / 8, 256, 0, ctx->stream>>>(ctx->dSeq.p, ctx->dWordOff.p, ctx->dLen.p, dOv, nOv, dJobs.p, useHpc, scratch.p, hpcLen.p);
+    hpcKernel<<<(2 * nOv + 7) / 8, 256, 0, ctx->stream>>>(ctx->dSeq.p, ctx->dWordOff.p, ctx->dLen.p, qSeq, qWordOff, qLen, dOv, nOv, dJobs.p, useHpc,
+                                                          scratch.p, hpcLen.p);
     checkLaunch(ctx, "hpcKernel");
     const int blocks = 148 * 8, warps = blocks * 4;
     const uint64_t stride = 2ULL * maxLen + 8;

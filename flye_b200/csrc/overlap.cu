@@ -33,6 +33,7 @@ static constexpr int QTILE = 2048;
 struct OvParams {
     int k, maxJump, minOverlap, maxOverhang;
     bool checkOverhang, forceLocal, onlyMaxExt;
+    bool sameSet;       // queries come from the indexed read set (ids comparable, self hits possible)
     float minUniqueF;   // 0.01f * minOverlap (overlap.cpp:110,235)
 };
 
@@ -48,7 +49,7 @@ __global__ void __launch_bounds__(256) queryLookupKernel(const uint64_t* __restr
                                                          const uint32_t* __restrict__ len, const uint64_t* __restrict__ slotOff,
                                                          const uint32_t* __restrict__ selBits, const uint32_t* __restrict__ qIds,
                                                          const uint64_t* __restrict__ qSlotOff, const uint2* __restrict__ qTiles,
-                                                         int k, Table index, uint32_t* __restrict__ hitCnt,
+                                                         int k, bool sameSet, Table index, uint32_t* __restrict__ hitCnt,
                                                          uint64_t* __restrict__ slotInfo, uint32_t* __restrict__ filtBits) {
     const uint2 t = qTiles[blockIdx.x];
     const uint32_t id = qIds[t.x], r = id >> 1;
@@ -58,7 +59,7 @@ __global__ void __launch_bounds__(256) queryLookupKernel(const uint64_t* __restr
     const uint32_t cntPad = (cnt + 31u) & ~31u;
     const uint64_t* words = seq + wordOff[r];
     const uint64_t qbase = qSlotOff[t.x] + t.y;
-    const uint64_t fbase = slotOff[r];
+    const uint64_t fbase = sameSet ? slotOff[r] : 0;
     const uint64_t mask = kmerMask(k);
     const int lane = threadIdx.x & 31;
     for (uint32_t i0 = (threadIdx.x >> 5) * 32; i0 < cntPad; i0 += (blockDim.x >> 5) * 32) {
@@ -78,7 +79,7 @@ __global__ void __launch_bounds__(256) queryLookupKernel(const uint64_t* __restr
                 if (size == IDX_REPETITIVE) rep = true;
                 else {
                     bool self = false;
-                    if (q < n) self = (selBits[(fbase + q) >> 5] >> (q & 31)) & 1u;
+                    if (sameSet && q < n) self = (selBits[(fbase + q) >> 5] >> (q & 31)) & 1u;
                     c = (uint32_t)size - (self ? 1u : 0u);
                     info = (payload >> IDX_SIZE_BITS) | (fwdRc ? INFO_FWDRC : 0) | (self ? INFO_SELF : 0) | (flagQ ? INFO_QRC : 0);
                 }
@@ -110,7 +111,7 @@ __global__ void gatherQueryHitOffKernel(const uint64_t* __restrict__ hitOff, con
 // Q3: expansion.  One CTA per query tile; the tile's slot offsets are staged in shared memory and every
 // output record finds its slot with a shared-memory binary search, so global writes are coalesced.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) expandKernel(const uint32_t* __restrict__ len, const uint2* __restrict__ entries,
+__global__ void __launch_bounds__(256) expandKernel(const uint32_t* __restrict__ len, const uint32_t* __restrict__ qlen, const uint2* __restrict__ entries,
                                                     const uint32_t* __restrict__ qIds, const uint64_t* __restrict__ qSlotOff,
                                                     const uint2* __restrict__ qTiles, int k, const uint64_t* __restrict__ hitOff,
                                                     const uint64_t* __restrict__ slotInfo, uint64_t hitBase, Elem* __restrict__ hits) {
@@ -118,7 +119,7 @@ __global__ void __launch_bounds__(256) expandKernel(const uint32_t* __restrict__
     const uint2 t = qTiles[blockIdx.x];
     const uint32_t id = qIds[t.x], r = id >> 1;
     const bool strand = id & 1;
-    const uint32_t L = len[r], n = L - k;
+    const uint32_t L = qlen[r], n = L - k;
     const uint32_t cnt = min((uint32_t)QTILE, n - t.y);
     const uint64_t qbase = qSlotOff[t.x] + t.y;
     const uint64_t h0 = hitOff[qbase];
@@ -291,7 +292,8 @@ struct PairInfo { uint32_t start, n, qi, extId; };
 __global__ void __launch_bounds__(256) pairFilterKernel(const Elem* __restrict__ hits, const uint32_t* __restrict__ gStart, uint32_t G, uint64_t M,
                                                         const uint32_t* __restrict__ candIds, uint32_t C,
                                                         const uint64_t* __restrict__ qHitOff, uint32_t qFirst, uint32_t nQ, uint64_t hitBase,
-                                                        const uint32_t* __restrict__ qIds, const uint32_t* __restrict__ len, OvParams P,
+                                                        const uint32_t* __restrict__ qIds, const uint32_t* __restrict__ len,
+                                                        const uint32_t* __restrict__ qlen, OvParams P,
                                                         uint8_t* __restrict__ pass, PairInfo* __restrict__ info) {
     const uint32_t c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (c >= C) return;
@@ -315,7 +317,7 @@ __global__ void __launch_bounds__(256) pairFilterKernel(const Elem* __restrict__
     while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (qHitOff[qFirst + mid] - hitBase <= a) lo = mid; else hi = mid; }
     const uint32_t qi = qFirst + lo;
     const uint32_t extId = (uint32_t)(hits[a].key >> 32);
-    const int32_t curLen = (int32_t)len[qIds[qi] >> 1], extLen = (int32_t)len[extId >> 1];
+    const int32_t curLen = (int32_t)qlen[qIds[qi] >> 1], extLen = (int32_t)len[extId >> 1];
     const int32_t minCur = (int32_t)(uint32_t)hits[a].key, maxCur = (int32_t)(uint32_t)hits[b - 1].key;
     bool ok = !((float)uniq < P.minUniqueF);
     if (maxCur - minCur < P.minOverlap || maxExt - minExt < P.minOverlap) ok = false;
@@ -340,11 +342,11 @@ __device__ __forceinline__ bool overlapTestDev(const OvParams& P, uint32_t curId
     if (cr < P.minOverlap || er < P.minOverlap) return false;
     const float lengthDiff = (float)abs(cr - er);
     if (lengthDiff > __fmul_rn(0.5f, (float)min(cr, er))) return false;
-    if (curId == extId) {
+    if (P.sameSet && curId == extId) {
         const int32_t intersect = min(curEnd, extEnd) - max(curBegin, extBegin);
         if (intersect > cr / 2) return false;
     }
-    if (curId == (extId ^ 1u)) {
+    if (P.sameSet && curId == (extId ^ 1u)) {
         const int32_t intersect = min(curEnd, extLen - extBegin) - max(curBegin, extLen - extEnd);
         if (intersect > cr / 2) return false;
     }
@@ -365,13 +367,13 @@ static constexpr uint32_t PAIR_EXTSORTED = 1u;
 // append them to the list of segments that need the std::sort-exact re-sort (:272-274)
 __global__ void __launch_bounds__(256) pairPrepKernel(Elem* __restrict__ hits, const PairInfo* __restrict__ pairs, const uint32_t* __restrict__ pairIds,
                                                       uint32_t nPairs, const uint32_t* __restrict__ qIds, const uint32_t* __restrict__ len,
-                                                      uint32_t* __restrict__ pairFlags, Seg* __restrict__ extSegs, uint32_t* __restrict__ nExtSegs,
+                                                      const uint32_t* __restrict__ qlen, uint32_t* __restrict__ pairFlags, Seg* __restrict__ extSegs, uint32_t* __restrict__ nExtSegs,
                                                       Seg* __restrict__ allSegs) {
     const uint32_t w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (w >= nPairs) return;
     const int lane = threadIdx.x & 31;
     const PairInfo pi = pairs[pairIds[w]];
-    const int32_t curLen = (int32_t)len[qIds[pi.qi] >> 1], extLen = (int32_t)len[pi.extId >> 1];
+    const int32_t curLen = (int32_t)qlen[qIds[pi.qi] >> 1], extLen = (int32_t)len[pi.extId >> 1];
     const bool extSorted = extLen > curLen;
     if (lane == 0) {
         pairFlags[w] = extSorted ? PAIR_EXTSORTED : 0u;
@@ -515,7 +517,7 @@ static constexpr int WALK_CAP = 4096;   // matches per warp whose back pointers 
 __global__ void __launch_bounds__(128) chainWalkKernel(const Elem* __restrict__ hits, const PairInfo* __restrict__ pairs, const uint32_t* __restrict__ pairIds,
                                                        uint32_t nPairs, const uint32_t* __restrict__ pairFlags, const uint32_t* __restrict__ qIds,
                                                        const uint64_t* __restrict__ qSlotOff, const uint32_t* __restrict__ len,
-                                                       const uint32_t* __restrict__ filtBits, const uint32_t* __restrict__ filtPrefix, OvParams P,
+                                                       const uint32_t* __restrict__ qlen, const uint32_t* __restrict__ filtBits, const uint32_t* __restrict__ filtPrefix, OvParams P,
                                                        const int32_t* __restrict__ score, int32_t* __restrict__ back, Elem* __restrict__ ord,
                                                        Cand* __restrict__ cands, uint32_t* __restrict__ nCandOut, uint32_t* __restrict__ nKeptOut) {
     extern __shared__ __align__(16) unsigned char smemRaw[];
@@ -527,7 +529,7 @@ __global__ void __launch_bounds__(128) chainWalkKernel(const Elem* __restrict__ 
     const int32_t n = (int32_t)pi.n;
     const int k = P.k;
     const uint32_t curId = qIds[pi.qi], extId = pi.extId;
-    const int32_t curLen = (int32_t)len[curId >> 1], extLen = (int32_t)len[extId >> 1];
+    const int32_t curLen = (int32_t)qlen[curId >> 1], extLen = (int32_t)len[extId >> 1];
     const Elem* h = hits + pi.start;
     const int32_t* sc = score + pi.start;
     Elem* od = ord + pi.start; Cand* cd = cands + pi.start;
@@ -612,7 +614,7 @@ __global__ void __launch_bounds__(128) chainWalkKernel(const Elem* __restrict__ 
 // Q7: compact the kept candidates of every pair into the output, in the reference's order
 __global__ void __launch_bounds__(256) gatherOverlapsKernel(const PairInfo* __restrict__ pairs, const uint32_t* __restrict__ pairIds, uint32_t nPairs,
                                                             const uint32_t* __restrict__ qIds, const uint32_t* __restrict__ len,
-                                                            const Elem* __restrict__ ord, const Cand* __restrict__ cands,
+                                                            const uint32_t* __restrict__ qlen, const Elem* __restrict__ ord, const Cand* __restrict__ cands,
                                                             const uint32_t* __restrict__ nCand, const uint64_t* __restrict__ outOff,
                                                             uint32_t qiBase, const uint32_t* __restrict__ pairFlags, fg_overlap* __restrict__ out) {
     const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
@@ -627,7 +629,7 @@ __global__ void __launch_bounds__(256) gatherOverlapsKernel(const PairInfo* __re
         if (!e.aux) continue;
         const Cand c = cands[pi.start + e.val];
         fg_overlap r;
-        r.cur_id = curId; r.cur_begin = c.curBegin; r.cur_end = c.curEnd; r.cur_len = (int32_t)len[curId >> 1];
+        r.cur_id = curId; r.cur_begin = c.curBegin; r.cur_end = c.curEnd; r.cur_len = (int32_t)qlen[curId >> 1];
         r.ext_id = pi.extId; r.ext_begin = c.extBegin; r.ext_end = c.extEnd; r.ext_len = (int32_t)len[pi.extId >> 1];
         r.score = c.score; r.seq_divergence = 0.f; r.chain_length = c.chainLength; r.filtered_positions = c.filtered;
         r.edit_distance = -1; r.aln_len = 0; r.reserved = pi.qi - qiBase;
@@ -803,6 +805,11 @@ static uint32_t selectFlagged(fg_ctx* ctx, const FlagT* flags, uint32_t n, DevBu
 static void overlapsChunk(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, uint32_t qOffset, const fg_overlap_params& prm, const OvParams& P,
                           size_t& nRaw, uint64_t& totHits, uint64_t& totPairs, uint64_t& totDpPairs, uint64_t& totCells) {
     const int k = ctx->k;
+    // where the query sequences live: the indexed reads themselves, or the second set of fg_queries_upload
+    const std::vector<uint32_t>& qHLen = P.sameSet ? ctx->hLen : ctx->hQsLen;
+    const uint64_t* qSeq = P.sameSet ? ctx->dSeq.p : ctx->dQsSeq.p;
+    const uint64_t* qWordOff = P.sameSet ? ctx->dWordOff.p : ctx->dQsWordOff.p;
+    const uint32_t* qLen = P.sameSet ? ctx->dLen.p : ctx->dQsLen.p;
     PinnedBuf<fg_overlap>& pinned = ctx->pinnedOut;
 
     // query slot space and tiles
@@ -810,7 +817,7 @@ static void overlapsChunk(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, ui
     std::vector<uint2> hQTiles;
     std::vector<size_t> qTileFirst(nQ + 1, 0);
     for (uint32_t i = 0; i < nQ; ++i) {
-        const uint32_t L = ctx->hLen[queryIds[i] >> 1];
+        const uint32_t L = qHLen[queryIds[i] >> 1];
         const uint32_t n = L > (uint32_t)k ? L - k : 0;
         qTileFirst[i] = hQTiles.size();
         for (uint32_t t = 0; t < n; t += QTILE) hQTiles.push_back(make_uint2(i, t));
@@ -835,9 +842,9 @@ static void overlapsChunk(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, ui
         if (nQSlots >= (1ULL << 31)) throw Error(FG_ERR_ARG, "query batch too large (>= 2^31 k-mer slots); split the call");
         {
             PhaseTimer pt(ctx, "gather");
-            queryLookupKernel<<<(unsigned)hQTiles.size(), 256, 0, ctx->stream>>>(ctx->dSeq.p, ctx->dWordOff.p, ctx->dLen.p, ctx->dSlotOff.p,
+            queryLookupKernel<<<(unsigned)hQTiles.size(), 256, 0, ctx->stream>>>(qSeq, qWordOff, qLen, ctx->dSlotOff.p,
                                                                                 ctx->dSelBits.p, dQIds.p, dQSlotOff.p, dQTiles.p, k,
-                                                                                ctx->indexTable, hitCnt.p, slotInfo.p, filtBits.p);
+                                                                                P.sameSet, ctx->indexTable, hitCnt.p, slotInfo.p, filtBits.p);
             checkLaunch(ctx, "queryLookupKernel");
             cub::TransformInputIterator<uint64_t, CastU64, const uint32_t*> it64(hitCnt.p, CastU64());
             exclusiveScanToPlus1(ctx, it64, hitOff.p, nQSlots);
@@ -878,7 +885,7 @@ static void overlapsChunk(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, ui
         const size_t tA = qTileFirst[qa], tB = qTileFirst[qb];
         {
             PhaseTimer pt(ctx, "gather");
-            expandKernel<<<(unsigned)(tB - tA), 256, 0, ctx->stream>>>(ctx->dLen.p, ctx->dEntries.p, dQIds.p, dQSlotOff.p, dQTiles.p + tA, k,
+            expandKernel<<<(unsigned)(tB - tA), 256, 0, ctx->stream>>>(ctx->dLen.p, qLen, ctx->dEntries.p, dQIds.p, dQSlotOff.p, dQTiles.p + tA, k,
                                                                       hitOff.p, slotInfo.p, hitBase, hits.p);
             checkLaunch(ctx, "expandKernel");
         }
@@ -902,7 +909,7 @@ static void overlapsChunk(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, ui
             pairInfo.alloc(std::max<uint32_t>(C, 1)); passFlag.alloc(std::max<uint32_t>(C, 1));
             if (C) {
                 pairFilterKernel<<<(C + 7) / 8, 256, 0, ctx->stream>>>(hits.p, gStart.p, G, M, candIds.p, C, dQHitOff.p, qa, nq, hitBase,
-                                                                      dQIds.p, ctx->dLen.p, P, passFlag.p, pairInfo.p);
+                                                                      dQIds.p, ctx->dLen.p, qLen, P, passFlag.p, pairInfo.p);
                 checkLaunch(ctx, "pairFilterKernel");
                 Pn = selectFlagged(ctx, passFlag.p, C, pairIds);
             }
@@ -917,7 +924,7 @@ static void overlapsChunk(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, ui
             DevBuf<Seg> extSegs(Pn), allSegs(Pn);
             {
                 PhaseTimer pt(ctx, "chain_prep");
-                pairPrepKernel<<<(Pn + 7) / 8, 256, 0, ctx->stream>>>(hits.p, pairInfo.p, pairIds.p, Pn, dQIds.p, ctx->dLen.p, pairFlags.p,
+                pairPrepKernel<<<(Pn + 7) / 8, 256, 0, ctx->stream>>>(hits.p, pairInfo.p, pairIds.p, Pn, dQIds.p, ctx->dLen.p, qLen, pairFlags.p,
                                                                      extSegs.p, counters.p + 8, allSegs.p);
                 checkLaunch(ctx, "pairPrepKernel");
             }
@@ -946,7 +953,7 @@ static void overlapsChunk(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, ui
                 const int walkSmem = 4 * WALK_CAP * (int)sizeof(unsigned short);
                 if (!walkAttr) { FG_CUDA(cudaFuncSetAttribute(chainWalkKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, walkSmem)); walkAttr = true; }
                 chainWalkKernel<<<(Pn + 3) / 4, 128, walkSmem, ctx->stream>>>(hits.p, pairInfo.p, pairIds.p, Pn, pairFlags.p, dQIds.p, dQSlotOff.p,
-                                                                          ctx->dLen.p, filtBits.p, filtPrefix.p, P, score.p, back.p, ord.p,
+                                                                          ctx->dLen.p, qLen, filtBits.p, filtPrefix.p, P, score.p, back.p, ord.p,
                                                                           cands.p, nCand.p, nKept.p);
                 checkLaunch(ctx, "chainWalkKernel");
             }
@@ -966,7 +973,7 @@ static void overlapsChunk(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, ui
             totCells += cells;
             if (nOut) {
                 DevBuf<fg_overlap> dOut(nOut);
-                gatherOverlapsKernel<<<(Pn + 255) / 256, 256, 0, ctx->stream>>>(pairInfo.p, pairIds.p, Pn, dQIds.p, ctx->dLen.p, ord.p, cands.p,
+                gatherOverlapsKernel<<<(Pn + 255) / 256, 256, 0, ctx->stream>>>(pairInfo.p, pairIds.p, Pn, dQIds.p, ctx->dLen.p, qLen, ord.p, cands.p,
                                                                                nCand.p, outOff.p, 0u - qOffset, pairFlags.p, dOut.p);
                 checkLaunch(ctx, "gatherOverlapsKernel");
                 {   // kmerMatches of the kept overlaps, or just clearing the scratch the gather left in aln_first / aln_count
@@ -1002,7 +1009,7 @@ static void overlapsChunk(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, ui
                 if (prm.nucl_alignment) {   // overlap.cpp:463-468
                     if (nOut >= (1ULL << 31)) throw Error(FG_ERR_ARG, "too many overlaps in one sub-batch");
                     PhaseTimer pe(ctx, "edit");
-                    editDistances(ctx, dOut.p, dst, (uint32_t)nOut, prm.use_hpc != 0);
+                    editDistances(ctx, dOut.p, dst, (uint32_t)nOut, prm.use_hpc != 0, qSeq, qWordOff, qLen);
                     FG_CUDA(cudaMemcpyAsync(dst, dOut.p, nOut * sizeof(fg_overlap), cudaMemcpyDeviceToHost, ctx->stream));
                     FG_CUDA(cudaStreamSynchronize(ctx->stream));
                 }
@@ -1018,10 +1025,14 @@ void overlapsBatch(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, const fg_
     if (!ctx->indexed) throw Error(FG_ERR_ARG, "no index: call fg_build_index_* first");
     ctx->timings.clear(); ctx->timingCalls.clear();
     const int k = ctx->k;
+    const bool sameSet = prm.query_set == 0;
+    if (!sameSet && !ctx->dQsSeq.p) throw Error(FG_ERR_ARG, "query_set = 1 but fg_queries_upload has not been called");
+    const uint32_t nQuerySeqs = sameSet ? ctx->nReads : ctx->nQsReads;
     for (uint32_t i = 0; i < nQ; ++i)
-        if (queryIds[i] >= 2 * ctx->nReads) throw Error(FG_ERR_ARG, "query id out of range");
+        if (queryIds[i] >= 2 * nQuerySeqs) throw Error(FG_ERR_ARG, "query id out of range");
 
     OvParams P;
+    P.sameSet = sameSet;
     P.k = k; P.maxJump = prm.max_jump; P.minOverlap = prm.min_overlap; P.maxOverhang = prm.max_overhang;
     P.checkOverhang = prm.max_overhang > 0; P.forceLocal = prm.force_local != 0; P.onlyMaxExt = prm.only_max_ext != 0;
     { volatile float a = 0.01f; volatile float m = a * prm.min_overlap; P.minUniqueF = m; }   // minKmerSruvivalRate * _minOverlap
@@ -1042,7 +1053,7 @@ void overlapsBatch(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, const fg_
         uint64_t slots = 0;
         uint32_t q1 = q0;
         while (q1 < nQ) {
-            const uint32_t L = ctx->hLen[queryIds[q1] >> 1];
+            const uint32_t L = (sameSet ? ctx->hLen : ctx->hQsLen)[queryIds[q1] >> 1];
             const uint64_t add = L > (uint32_t)k ? ((uint64_t)(L - k) + 31u) & ~31ULL : 0;
             if (q1 > q0 && slots + add >= chunkSlots) break;
             slots += add; ++q1;

@@ -155,19 +155,27 @@ public:
 
 private:
     // getSeqOverlaps for many query sequences in one device pass (reference: one call per read, overlap.cpp:99-508)
+    // `queryContainer` may be a different container than the indexed one (read-to-graph alignment): its forward
+    // sequences are then uploaded once as the device's second sequence set
     std::vector<std::vector<OverlapRange>> getSeqOverlapsBatch(const std::vector<FastaRecord::Id>& queries, bool forceLocal,
-                                                               OvlpDivStats& divStats, int maxOverlaps) const {
+                                                               OvlpDivStats& divStats, int maxOverlaps,
+                                                               const SequenceContainer* queryContainer = nullptr) const {
         const auto& dev = _vertexIndex.device();
         if (&_vertexIndex.container() != &_seqContainer) throw std::runtime_error("flye_b200: index and target containers differ");
-        const uint32_t base = (uint32_t)_seqContainer.idOffset();
+        if (!queryContainer) queryContainer = &_seqContainer;
+        const bool sameSet = queryContainer == &_seqContainer;
+        const uint32_t base = (uint32_t)_seqContainer.idOffset();              // ids of the indexed (target) sequences
+        const uint32_t qbase = (uint32_t)queryContainer->idOffset();           // ids of the query sequences
         std::vector<uint32_t> ids(queries.size());
-        for (size_t i = 0; i < queries.size(); ++i) ids[i] = queries[i].rawId() - base;
-        fg_overlap_params p;
+        for (size_t i = 0; i < queries.size(); ++i) ids[i] = queries[i].rawId() - qbase;
+        fg_overlap_params p{};
+        p.query_set = sameSet ? 0 : 1;
         p.max_jump = _maxJump; p.min_overlap = _minOverlap; p.max_overhang = _maxOverhang; p.max_overlaps = maxOverlaps;
         p.force_local = forceLocal; p.keep_alignment = _keepAlignment; p.only_max_ext = _onlyMaxExt; p.nucl_alignment = _nuclAlignment;
         p.use_hpc = _useHpc; p.max_divergence = _maxDivergence;
         // results live in library memory until the next call: copy out under the lock
         std::lock_guard<std::mutex> lock(batchMutex());
+        if (!sameSet) dev->uploadQueries(*queryContainer);
         fg_overlap_result res;
         dev->check(fg_overlaps_batch(dev->ctx, ids.data(), (uint32_t)ids.size(), &p, &res));
         std::vector<std::vector<OverlapRange>> out(queries.size());
@@ -175,7 +183,7 @@ private:
             out[q].reserve(res.offsets[q + 1] - res.offsets[q]);
             for (uint64_t i = res.offsets[q]; i < res.offsets[q + 1]; ++i) {
                 const fg_overlap& o = res.overlaps[i];
-                OverlapRange r(FastaRecord::Id(base + o.cur_id), FastaRecord::Id(base + o.ext_id), o.cur_begin, o.ext_begin, o.cur_len, o.ext_len);
+                OverlapRange r(FastaRecord::Id(qbase + o.cur_id), FastaRecord::Id(base + o.ext_id), o.cur_begin, o.ext_begin, o.cur_len, o.ext_len);
                 r.curEnd = o.cur_end; r.extEnd = o.ext_end; r.score = o.score; r.seqDivergence = o.seq_divergence;
                 if (_keepAlignment && o.aln_count) {
                     r.kmerMatches = new std::vector<std::pair<int32_t, int32_t>>();
@@ -196,7 +204,7 @@ private:
         return out;
     }
     std::vector<OverlapRange> getSeqOverlaps(const FastaRecord& rec, bool forceLocal, OvlpDivStats& stats, int maxOverlaps) const {
-        return std::move(getSeqOverlapsBatch({rec.id}, forceLocal, stats, maxOverlaps)[0]);
+        return std::move(getSeqOverlapsBatch({rec.id}, forceLocal, stats, maxOverlaps)[0]);   // queries of the indexed container
     }
     static std::mutex& batchMutex() { static std::mutex m; return m; }
 
@@ -210,10 +218,7 @@ private:
 class OverlapContainer {
 public:
     OverlapContainer(const OverlapDetector& ovlpDetect, const SequenceContainer& queryContainer)
-        : _ovlpDetect(ovlpDetect), _queryContainer(queryContainer), _indexSize(0), _meanTrueOvlpDiv(0) {
-        if (&queryContainer != &ovlpDetect._seqContainer)
-            throw std::runtime_error("flye_b200: queries from a second container (read-to-graph alignment) are not on the device path yet");
-    }
+        : _ovlpDetect(ovlpDetect), _queryContainer(queryContainer), _indexSize(0), _meanTrueOvlpDiv(0) {}
     struct IndexVecWrapper {
         IndexVecWrapper() : fwdOverlaps(new std::vector<OverlapRange>), revOverlaps(new std::vector<OverlapRange>), cached(false),
                             suggestChimeric(false) {}
@@ -241,12 +246,12 @@ public:
         return _overlapIndex[readId.strand() ? readId : readId.rc()].suggestChimeric;
     }
     std::vector<OverlapRange> quickSeqOverlaps(FastaRecord::Id readId, int maxOverlaps = 0, bool forceLocal = false) {
-        return std::move(_ovlpDetect.getSeqOverlapsBatch({readId}, forceLocal, _divergenceStats, maxOverlaps)[0]);
+        return std::move(_ovlpDetect.getSeqOverlapsBatch({readId}, forceLocal, _divergenceStats, maxOverlaps, &_queryContainer)[0]);
     }
     // mirror extension: the same results as N quickSeqOverlaps calls from one device pass
     std::vector<std::vector<OverlapRange>> quickSeqOverlapsBatch(const std::vector<FastaRecord::Id>& ids, int maxOverlaps = 0,
                                                                  bool forceLocal = false) {
-        return _ovlpDetect.getSeqOverlapsBatch(ids, forceLocal, _divergenceStats, maxOverlaps);
+        return _ovlpDetect.getSeqOverlapsBatch(ids, forceLocal, _divergenceStats, maxOverlaps, &_queryContainer);
     }
     // mirror extension: fill the lazy cache for many forward reads with one device pass
     void prefetch(const std::vector<FastaRecord::Id>& fwdIds) {
@@ -256,7 +261,7 @@ public:
             for (auto id : fwdIds) { auto it = _overlapIndex.find(id); if (it == _overlapIndex.end() || !it->second.cached) todo.push_back(id); }
         }
         if (todo.empty()) return;
-        auto res = _ovlpDetect.getSeqOverlapsBatch(todo, false, _divergenceStats, _ovlpDetect._maxCurOverlaps);
+        auto res = _ovlpDetect.getSeqOverlapsBatch(todo, false, _divergenceStats, _ovlpDetect._maxCurOverlaps, &_queryContainer);
         std::lock_guard<std::mutex> lock(_cacheMutex);
         for (size_t i = 0; i < todo.size(); ++i) {
             auto& w = _overlapIndex[todo[i]];
@@ -275,7 +280,7 @@ public:
         const int MAX_SEQS = 1000;
         std::vector<FastaRecord::Id> ids;
         for (int i = 0; i < MAX_SEQS; ++i) ids.push_back(_queryContainer.iterSeqs()[rand() % _queryContainer.iterSeqs().size()].id);
-        auto res = _ovlpDetect.getSeqOverlapsBatch(ids, false, _divergenceStats, 0);
+        auto res = _ovlpDetect.getSeqOverlapsBatch(ids, false, _divergenceStats, 0, &_queryContainer);
         std::vector<float> divs;
         for (const auto& ovs : res) {
             const OverlapRange* best = nullptr;

@@ -41,6 +41,21 @@ struct DeviceContext {
         check(fg_reads_upload(ctx, words.data(), offsets.data(), lengths.data(), (uint32_t)lengths.size()));
         uploadedFrom = &sc;
     }
+    const void* queriesFrom = nullptr;    // the SequenceContainer uploaded as the second (query-only) set
+    void uploadQueries(const SequenceContainer& sc) {
+        if (queriesFrom == &sc) return;
+        std::vector<uint64_t> words, offsets{0};
+        std::vector<uint32_t> lengths;
+        for (const auto& rec : sc.iterSeqs()) {
+            if (!rec.id.strand()) continue;
+            words.insert(words.end(), rec.sequence.packedWords(), rec.sequence.packedWords() + rec.sequence.numWords());
+            offsets.push_back(words.size());
+            lengths.push_back((uint32_t)rec.sequence.length());
+        }
+        words.push_back(0);
+        check(fg_queries_upload(ctx, words.data(), offsets.data(), lengths.data(), (uint32_t)lengths.size()));
+        queriesFrom = &sc;
+    }
     static std::shared_ptr<DeviceContext> shared(int device = 0) {
         static std::shared_ptr<DeviceContext> inst;
         if (!inst) inst = std::make_shared<DeviceContext>(device);

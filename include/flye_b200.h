@@ -57,6 +57,12 @@ int fg_reads_upload(fg_ctx* ctx, const uint64_t* packed, const uint64_t* word_of
 /* Same, from ASCII letters (ACGT/acgt only) — the 2-bit packing runs on the device (K1). */
 int fg_reads_upload_ascii(fg_ctx* ctx, const char* bases, const uint64_t* base_offsets, uint32_t n_reads);
 
+/* Optional second sequence set for queries that are not among the indexed reads — OverlapContainer(detector,
+ * queryContainer) with a different container, as ReadAligner::alignReads does (read_aligner.cpp:178-217).  Same layout as
+ * fg_reads_upload; query ids 2i / 2i+1 then name sequence i of THIS set and its reverse complement. */
+int fg_queries_upload(fg_ctx* ctx, const uint64_t* packed, const uint64_t* word_offsets,
+                      const uint32_t* lengths, uint32_t n_seqs);
+
 /* ---- KmerCounter::count / getKmerHist (vertex_index.cpp:499-590) ----------------------------------- */
 int fg_count_kmers(fg_ctx* ctx, int k, uint64_t* n_distinct);
 /* histogram freq -> number of distinct canonical k-mers; call with NULLs to get the bin count */
@@ -107,6 +113,7 @@ typedef struct {
     int32_t nucl_alignment;       /* _nuclAlignment: divergence = edit distance of (HPC) substrings      */
     int32_t use_hpc;              /* _useHpc                                                             */
     float   max_divergence;       /* _maxDivergence                                                      */
+    int32_t query_set;            /* 0: query ids name the indexed reads; 1: the set of fg_queries_upload  */
 } fg_overlap_params;
 
 typedef struct {                  /* OverlapRange (overlap.h:20-279) plus what seqDivergence is made of  */

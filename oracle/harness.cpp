@@ -37,7 +37,7 @@ static double now() {
 }
 
 struct Args {
-    std::string reads, cfg, out;
+    std::string reads, cfg, out, queryReads;
     int k = -1, threads = 1, minOverlap = 1000, maxOverlaps = 0, minReadLen = -1;
     bool forceLocal = false, dumpIndex = false, bothStrands = false, noEstimate = false;
     bool findAll = false, noOverlaps = false, keepAln = false, allExt = false;
@@ -70,6 +70,7 @@ int main(int argc, char** argv) {
         auto nxt = [&]() { if (i + 1 >= argc) { usage(); exit(1); } return std::string(argv[++i]); };
         if (s == "--reads") a.reads = nxt(); else if (s == "--cfg") a.cfg = nxt();
         else if (s == "--out") a.out = nxt(); else if (s == "--k") a.k = atoi(nxt().c_str());
+        else if (s == "--query-reads") a.queryReads = nxt();
         else if (s == "--threads") a.threads = atoi(nxt().c_str());
         else if (s == "--min-overlap") a.minOverlap = atoi(nxt().c_str());
         else if (s == "--min-read-len") a.minReadLen = atoi(nxt().c_str());
@@ -154,7 +155,12 @@ int main(int argc, char** argv) {
                                  /*keepAlignment*/ a.keepAln, /*onlyMaxExt*/ !a.allExt, /*maxDivergence*/ 1.0f,
                                  (bool)Config::get("reads_base_alignment"), /*partitionBadMappings*/ false,
                                  (bool)Config::get("hpc_scoring_on"));
-        OverlapContainer container(detector, reads);
+        // queries from a SECOND container against the index of the first, as ReadAligner::alignReads does
+        // (read_aligner.cpp:178-217): ids keep running through the process-global counter
+        SequenceContainer queryReads;
+        if (!a.queryReads.empty()) queryReads.loadFromFile(a.queryReads, a.minReadLen >= 0 ? a.minReadLen : a.minOverlap);
+        const SequenceContainer& qc = a.queryReads.empty() ? reads : queryReads;
+        OverlapContainer container(detector, qc);
         if (!a.noEstimate) {
             t0 = now();
             container.estimateOverlaperParameters();
@@ -163,7 +169,7 @@ int main(int argc, char** argv) {
             tEstimate = now() - t0;
         }
         std::vector<FastaRecord::Id> queries;
-        for (const auto& rec : reads.iterSeqs())
+        for (const auto& rec : qc.iterSeqs())
             if (rec.id.strand() || a.bothStrands) queries.push_back(rec.id);
         if (a.maxQueries >= 0 && (size_t)a.maxQueries < queries.size()) queries.resize(a.maxQueries);
         nQueries = queries.size();

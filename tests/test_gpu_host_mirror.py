@@ -39,3 +39,18 @@ def test_reference_harness_source_runs_on_the_mirror(built, tmp_path, cfg, k, si
     for ext in exts:
         n, sample = pu.diff_files(os.path.join(tmp, "ref." + ext), os.path.join(tmp, "gpu." + ext))
         assert n == 0, (ext, sample[:3])
+
+
+def test_queries_from_a_second_container(built, tmp_path):
+    """read-to-graph style: index over container A, queries from container B (OverlapContainer(detector, B)); minimizer index,
+    all primary overlaps kept, local overlaps allowed (SMALL_ALN = 100 in the reference's ReadAligner)"""
+    tmp = str(tmp_path)
+    a = pu.simulate(os.path.join(tmp, "a.fasta"), genome_len=120000, coverage=6, mean_len=12000, shape=20, error=0.002, seed=51)
+    b = pu.simulate(os.path.join(tmp, "b.fasta"), genome_len=120000, coverage=8, mean_len=6000, shape=4, error=0.03, seed=51)
+    for cfg, k, opts in [(HIFI, None, ["--query-reads", b, "--all-ext", "--both-strands", "--no-estimate", "--min-overlap", "500"]),
+                         (RAW, 15, ["--query-reads", b, "--all-ext", "--keep-aln"])]:
+        ref = pu.run_oracle(a, cfg, os.path.join(tmp, "ref"), k=k, extra=opts)
+        got = run_mirror(a, cfg, os.path.join(tmp, "gpu"), k=k, extra=opts)
+        assert got["overlaps"] == ref["overlaps"] and ref["overlaps"] > 100
+        n, sample = pu.diff_files(os.path.join(tmp, "ref.ovlp"), os.path.join(tmp, "gpu.ovlp"))
+        assert n == 0, sample[:3]
