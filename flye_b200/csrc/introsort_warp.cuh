@@ -37,6 +37,8 @@
 #define FG_SYNCWARP() __syncwarp()
 #define FG_POPC(x) __popc(x)
 #define FG_CTZ(x) (__ffs(x) - 1)
+#define FG_POPCLL(x) __popcll(x)
+#define FG_CTZLL(x) (__ffsll((long long)(x)) - 1)
 #define FG_PREFETCH_L2(ptr) asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr))
 #else
 #include <algorithm>
@@ -59,6 +61,8 @@ inline int nthHighBit(uint32_t mask, int n) {
 #define FG_SYNCWARP() ((void)0)
 #define FG_POPC(x) __builtin_popcount(x)
 #define FG_CTZ(x) __builtin_ctz(x)
+#define FG_POPCLL(x) __builtin_popcountll(x)
+#define FG_CTZLL(x) __builtin_ctzll(x)
 #define FG_PREFETCH_L2(ptr) ((void)0)
 #endif
 
@@ -208,7 +212,8 @@ FG_DEV void seqIntrosort(Elem* a, long n) {
 typedef int idx_t;   // positions inside one sorted array (< 2^31 elements)
 
 // `inGlobal`: arr lives in global memory — lines a few chunks ahead of both cursors are pulled into L2 early.
-static constexpr idx_t PF_AHEAD = 4 * 32;   // elements (4 chunks = 2 KB) between the register prefetch and the L2 prefetch
+static constexpr idx_t PF_AHEAD = 4 * 32;
+static constexpr idx_t PF_AHEAD64 = 4 * 64;   // elements (4 chunks = 2 KB) between the register prefetch and the L2 prefetch
 
 FG_DEV idx_t warpPartition(Elem* arr, idx_t f, idx_t l, unsigned char* tab, bool inGlobal = false) {
     unsigned char* tabL = tab;        // tabL[m] = lane of the m-th lowest pending ">= pivot" stop
@@ -340,6 +345,172 @@ FG_DEV idx_t warpPartition(Elem* arr, idx_t f, idx_t l, unsigned char* tab, bool
     return Ls < lastR ? Ls : lastR;
 }
 
+// ---- the same partition with 64-position chunks (two elements per lane) --------------------------------------
+// Identical logic and result; every refill moves 1 KB per side, so the fixed cost of a round (ballots, rank tables,
+// mask updates) is spread over twice as many elements and twice as many bytes are in flight per warp.  Slot s of a
+// chunk (position base + s) lives in lane s%32, register s/32.  `tab` needs 128 bytes here.
+FG_DEV int rankBelow64(unsigned long long m, int s) { return FG_POPCLL(m & ((1ULL << s) - 1ULL)); }
+FG_DEV int rankAbove64(unsigned long long m, int s) { return s == 63 ? 0 : FG_POPCLL(m >> (s + 1)); }
+
+FG_DEV idx_t warpPartition64(Elem* arr, idx_t f, idx_t l, unsigned char* tab, bool inGlobal = false) {
+    unsigned char* tabL = tab;        // tabL[m] = slot of the m-th lowest pending ">= pivot" stop
+    unsigned char* tabR = tab + 64;   // tabR[m] = slot of the m-th highest pending "<= pivot" stop
+#ifndef FG_WARP_HOST
+    if (fg::laneId() == 0)
+#endif
+        seqMedianToFirst(arr, f, f + 1, f + (l - f) / 2, l - 1);
+    FG_SYNCWARP();
+    const unsigned long long p = arr[f].key;
+
+    idx_t lo = f + 1, hi = l;        // untouched middle [lo,hi)
+    idx_t s = 0, lastR = -1, firstGeAbove = l, Lb = 0, Rb = 0;
+    unsigned long long geL = 0, leL = 0, pendL = 0, geR = 0, leR = 0, pendR = 0;
+    bool haveR = false;
+    FG_LANEVAR(Elem, eL0); FG_LANEVAR(Elem, eL1); FG_LANEVAR(Elem, eR0); FG_LANEVAR(Elem, eR1);
+    FG_LANEVAR(Elem, pL0); FG_LANEVAR(Elem, pL1); FG_LANEVAR(Elem, pR0); FG_LANEVAR(Elem, pR1);   // register prefetch
+    bool pfLok = false, pfRok = false;
+    if (hi - lo >= 128) {
+        FG_FOR_LANES
+            FG_L(pL0) = arr[lo + lane]; FG_L(pL1) = arr[lo + 32 + lane];
+            FG_L(pR0) = arr[hi - 64 + lane]; FG_L(pR1) = arr[hi - 32 + lane];
+        FG_END_LANES
+        pfLok = pfRok = true;
+    }
+    if (inGlobal) {
+        FG_FOR_LANES
+            for (idx_t a = 64; a <= PF_AHEAD64; a += 32) {
+                if (lo + a + lane < hi) FG_PREFETCH_L2(arr + lo + a + lane);
+                if (hi - 32 - a + lane >= lo) FG_PREFETCH_L2(arr + hi - 32 - a + lane);
+            }
+        FG_END_LANES
+    }
+
+    for (;;) {
+        if (pendL == 0 && lo < hi) {
+            Lb = lo;
+            const idx_t nL = (hi - lo < 64) ? (hi - lo) : 64;
+            if (pfLok && nL == 64) { FG_FOR_LANES FG_L(eL0) = FG_L(pL0); FG_L(eL1) = FG_L(pL1); FG_END_LANES }
+            else { FG_FOR_LANES if (lane < nL) FG_L(eL0) = arr[Lb + lane]; if (32 + lane < nL) FG_L(eL1) = arr[Lb + 32 + lane]; FG_END_LANES }
+            lo += nL;
+            pfLok = hi - lo >= 64;
+            if (pfLok) { FG_FOR_LANES FG_L(pL0) = arr[lo + lane]; FG_L(pL1) = arr[lo + 32 + lane]; FG_END_LANES }
+            if (inGlobal) {
+                FG_FOR_LANES
+                    if (lo + PF_AHEAD64 + lane < hi) FG_PREFETCH_L2(arr + lo + PF_AHEAD64 + lane);
+                    if (lo + PF_AHEAD64 + 32 + lane < hi) FG_PREFETCH_L2(arr + lo + PF_AHEAD64 + 32 + lane);
+                FG_END_LANES
+            }
+            uint32_t a0, a1, b0, b1;
+            FG_BALLOT(a0, lane < nL && FG_L(eL0).key >= p); FG_BALLOT(a1, 32 + lane < nL && FG_L(eL1).key >= p);
+            FG_BALLOT(b0, lane < nL && FG_L(eL0).key <= p); FG_BALLOT(b1, 32 + lane < nL && FG_L(eL1).key <= p);
+            geL = a0 | ((unsigned long long)a1 << 32); leL = b0 | ((unsigned long long)b1 << 32);
+            pendL = geL;
+        }
+        if (pendR == 0 && lo < hi) {
+            if (haveR && geR) firstGeAbove = Rb + FG_CTZLL(geR);
+            const idx_t nR = (hi - lo < 64) ? (hi - lo) : 64;
+            Rb = hi - nR;
+            if (pfRok && nR == 64) { FG_FOR_LANES FG_L(eR0) = FG_L(pR0); FG_L(eR1) = FG_L(pR1); FG_END_LANES }
+            else { FG_FOR_LANES if (lane < nR) FG_L(eR0) = arr[Rb + lane]; if (32 + lane < nR) FG_L(eR1) = arr[Rb + 32 + lane]; FG_END_LANES }
+            hi = Rb;
+            pfRok = hi - lo >= 64;
+            if (pfRok) { FG_FOR_LANES FG_L(pR0) = arr[hi - 64 + lane]; FG_L(pR1) = arr[hi - 32 + lane]; FG_END_LANES }
+            if (inGlobal) {
+                FG_FOR_LANES
+                    if (hi - 32 - PF_AHEAD64 + lane >= lo) FG_PREFETCH_L2(arr + hi - 32 - PF_AHEAD64 + lane);
+                    if (hi - 64 - PF_AHEAD64 + lane >= lo) FG_PREFETCH_L2(arr + hi - 64 - PF_AHEAD64 + lane);
+                FG_END_LANES
+            }
+            uint32_t a0, a1, b0, b1;
+            FG_BALLOT(a0, lane < nR && FG_L(eR0).key >= p); FG_BALLOT(a1, 32 + lane < nR && FG_L(eR1).key >= p);
+            FG_BALLOT(b0, lane < nR && FG_L(eR0).key <= p); FG_BALLOT(b1, 32 + lane < nR && FG_L(eR1).key <= p);
+            geR = a0 | ((unsigned long long)a1 << 32); leR = b0 | ((unsigned long long)b1 << 32);
+            pendR = leR;
+            haveR = true;
+        }
+        const int cL = FG_POPCLL(pendL), cR = FG_POPCLL(pendR);
+        const int c = cL < cR ? cL : cR;
+        if (c > 0) {
+            FG_FOR_LANES
+                for (int r = 0; r < 2; ++r) {
+                    const int sl = lane + 32 * r;
+                    if (pendL >> sl & 1) tabL[rankBelow64(pendL, sl)] = (unsigned char)sl;
+                    if (pendR >> sl & 1) tabR[rankAbove64(pendR, sl)] = (unsigned char)sl;
+                }
+            FG_END_LANES
+            FG_SYNCWARP();
+            FG_FOR_LANES
+                for (int r = 0; r < 2; ++r) {
+                    const int sl = lane + 32 * r;
+                    if (pendL >> sl & 1) { const int m = rankBelow64(pendL, sl); if (m < c) arr[Rb + tabR[m]] = r ? FG_L(eL1) : FG_L(eL0); }
+                    if (pendR >> sl & 1) { const int m = rankAbove64(pendR, sl); if (m < c) arr[Lb + tabL[m]] = r ? FG_L(eR1) : FG_L(eR0); }
+                }
+            FG_END_LANES
+            lastR = Rb + tabR[c - 1];
+            uint32_t k0, k1, q0, q1;
+            FG_BALLOT(k0, (pendL >> lane & 1) && rankBelow64(pendL, lane) >= c);
+            FG_BALLOT(k1, (pendL >> (lane + 32) & 1) && rankBelow64(pendL, lane + 32) >= c);
+            FG_BALLOT(q0, (pendR >> lane & 1) && rankAbove64(pendR, lane) >= c);
+            FG_BALLOT(q1, (pendR >> (lane + 32) & 1) && rankAbove64(pendR, lane + 32) >= c);
+            pendL = k0 | ((unsigned long long)k1 << 32); pendR = q0 | ((unsigned long long)q1 << 32);
+            s += c;
+            FG_SYNCWARP();
+        }
+        if (lo < hi && (pendL == 0 || pendR == 0)) continue;
+        break;
+    }
+    FG_SYNCWARP();
+
+    const idx_t INF = l + 1;
+    idx_t Ls;
+    if (pendL != 0 || pendR != 0) {
+        const bool caseA = pendL != 0;
+        const unsigned long long maskL = caseA ? pendL : geR, maskR = caseA ? leL : pendR;
+        const idx_t base = caseA ? Lb : Rb;
+        const int nl = FG_POPCLL(maskL), nr = FG_POPCLL(maskR);
+        FG_FOR_LANES
+            for (int r = 0; r < 2; ++r) {
+                const int sl = lane + 32 * r;
+                if (maskL >> sl & 1) tabL[rankBelow64(maskL, sl)] = (unsigned char)sl;
+                if (maskR >> sl & 1) tabR[rankAbove64(maskR, sl)] = (unsigned char)sl;
+            }
+        FG_END_LANES
+        FG_SYNCWARP();
+        uint32_t ok0, ok1;
+        FG_BALLOT(ok0, lane < nl && lane < nr && tabL[lane] < tabR[lane]);
+        FG_BALLOT(ok1, lane + 32 < nl && lane + 32 < nr && tabL[lane + 32] < tabR[lane + 32]);
+        const int e = FG_POPC(ok0) + FG_POPC(ok1);
+        FG_FOR_LANES
+            for (int r = 0; r < 2; ++r) {
+                const int sl = lane + 32 * r;
+                const Elem mine = caseA ? (r ? FG_L(eL1) : FG_L(eL0)) : (r ? FG_L(eR1) : FG_L(eR0));
+                if (maskL >> sl & 1) { const int m = rankBelow64(maskL, sl); if (m < e) arr[base + tabR[m]] = mine; }
+                if (maskR >> sl & 1) { const int m = rankAbove64(maskR, sl); if (m < e) arr[base + tabL[m]] = mine; }
+            }
+        FG_END_LANES
+        s += e;
+        if (e > 0) lastR = base + tabR[e - 1];
+        Ls = (e < nl) ? base + tabL[e] : (caseA ? INF : firstGeAbove);
+    } else {
+        Ls = (haveR && geR) ? Rb + FG_CTZLL(geR) : firstGeAbove;
+    }
+    FG_SYNCWARP();
+    if (s == 0) return Ls;
+    return Ls < lastR ? Ls : lastR;
+}
+
+#ifndef FG_CHUNK64
+#define FG_CHUNK64 0   // measured on B200: the 64-wide variant needs 107-124 registers and loses more to occupancy than it gains
+#endif
+FG_DEV idx_t warpPartitionAny(Elem* arr, idx_t f, idx_t l, unsigned char* tab, bool inGlobal) {
+#if FG_CHUNK64
+    return warpPartition64(arr, f, l, tab, inGlobal);
+#else
+    return warpPartition(arr, f, l, tab, inGlobal);
+#endif
+}
+static constexpr int WARP_TAB_BYTES = 128;   // per-warp scratch of the partition
+
 // ---- the whole sort -------------------------------------------------------------------------------------
 // The introsort loop (__introsort_loop, stl_algo.h:1918-1940) on arr[f0,l0) with depth budget d0, followed by the
 // leaf insertion sorts.  One warp; no shared memory: the explicit recursion stack (<= 2*lg n entries) and the
@@ -401,7 +572,7 @@ FG_DEV void warpIntrosortRange(Elem* arr, idx_t f0, idx_t l0, int d0, idx_t smal
                 break;
             }
             --d;
-            const idx_t cut = warpPartition(arr, f, l, tab, inGlobal);
+            const idx_t cut = warpPartitionAny(arr, f, l, tab, inGlobal);
             if (l - cut > stopAt) {   // "recurse" on the right part: push
                 FG_FOR_LANES
                     if (lane == (sp & 31)) {

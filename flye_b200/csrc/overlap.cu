@@ -190,7 +190,7 @@ __global__ void __launch_bounds__(256) sortSeedKernel(const Seg* __restrict__ se
 __global__ void __launch_bounds__(128) sortLevelKernel(Elem* __restrict__ arr, const SortTask* __restrict__ in, const uint32_t* __restrict__ nInPtr,
                                                        uint32_t capBig, SortTask* __restrict__ out, uint32_t* __restrict__ nOut,
                                                        SortTask* __restrict__ small, uint32_t* __restrict__ nSmall, uint32_t capSmall, uint32_t smallN) {
-    __shared__ unsigned char tabs[4][64];
+    __shared__ unsigned char tabs[4][WARP_TAB_BYTES];
     const uint32_t w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (w >= min(*nInPtr, capBig)) return;
     const SortTask t = in[w];
@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(128) sortLevelKernel(Elem* __restrict__ arr, c
         if (laneId() == 0) seqHeapSort(a, (long)t.n);
         return;
     }
-    const idx_t cut = warpPartition(a, 0, (idx_t)t.n, tabs[threadIdx.x >> 5], /*inGlobal*/ true);
+    const idx_t cut = warpPartitionAny(a, 0, (idx_t)t.n, tabs[threadIdx.x >> 5], /*inGlobal*/ true);
     if (laneId() == 0) {
         emitRange(t.start, (uint32_t)cut, t.depth - 1, out, nOut, capBig, small, nSmall, capSmall, smallN);
         emitRange(t.start + (uint32_t)cut, t.n - (uint32_t)cut, t.depth - 1, out, nOut, capBig, small, nSmall, capSmall, smallN);
@@ -221,7 +221,7 @@ struct TaskSinkDev {
 __global__ void __launch_bounds__(128) sortTailKernel(Elem* __restrict__ arr, const SortTask* __restrict__ in, const uint32_t* __restrict__ nInPtr,
                                                       uint32_t capBig, SortTask* __restrict__ small, uint32_t* __restrict__ nSmall,
                                                       uint32_t capSmall, uint32_t smallN) {
-    __shared__ unsigned char tabs[4][64];
+    __shared__ unsigned char tabs[4][WARP_TAB_BYTES];
     const uint32_t w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (w >= min(*nInPtr, capBig)) return;
     const SortTask t = in[w];
@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(128) sortSmallKernel(Elem* __restrict__ arr, c
                                                        const uint32_t* __restrict__ taskCounter, uint32_t taskCap, uint32_t* __restrict__ next,
                                                        uint32_t smallN) {
     extern __shared__ __align__(16) unsigned char smemRaw[];
-    __shared__ unsigned char tabs[4][64];
+    __shared__ unsigned char tabs[4][WARP_TAB_BYTES];
     Elem* sm = reinterpret_cast<Elem*>(smemRaw) + (threadIdx.x >> 5) * smallN;
     unsigned char* tab = tabs[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;

@@ -18,7 +18,7 @@ static long g_small = 0;   // > 0: two-level mode (top pass hands ranges <= g_sm
 static bool checkOne(std::vector<fg::Elem> a, const char* what) {
     std::vector<fg::Elem> ref = a;
     std::sort(ref.begin(), ref.end(), [](const fg::Elem& x, const fg::Elem& y) { return x.key < y.key; });
-    unsigned char tab[64];
+    unsigned char tab[128];
     if (g_small > 0 && a.size() > 1) {
         VecSink sink;
         fg::warpIntrosortRange(a.data(), 0, (int)a.size(), fg::introsortDepth((long)a.size()), (int)g_small, sink, tab);
