@@ -241,16 +241,31 @@ def main():
         # estimateOverlaperParameters' 1000 random queries and the all-reads pass share ONE device batch: the device
         # work does not depend on the divergence threshold (it only gates the final host-side filter, overlap.cpp:470),
         # so the threshold is computed from the first 1000 result vectors and applied to the rest on the host.
-        all_q = np.concatenate([np.asarray(est_ids, dtype=np.uint32), queries])
+        # multi-GPU: the 1000 estimate queries are dealt round-robin to the ranks; the per-query divergences are
+        # all-gathered (a few KB) so that every rank derives the same threshold
+        my_est = np.asarray(est_ids[rank::world], dtype=np.uint32)
+        all_q = np.concatenate([my_est, queries])
         offs, ov, ovl_stats = eng.overlaps(all_q, max_divergence=1.0, copy=False, **common)
-        first = int(offs[len(est_ids)])
+        first = int(offs[len(my_est)])
         rng_est = ov["cur_end"][:first] - ov["cur_begin"][:first]
         div_all = ov["seq_divergence"]
         divs = []
-        for i in range(len(est_ids)):
+        for i in range(len(my_est)):
             a, b = int(offs[i]), int(offs[i + 1])
             if b > a:
                 divs.append(div_all[a + int(np.argmax(rng_est[a:b]))])
+        if world > 1:
+            cap = (len(est_ids) + world - 1) // world
+            buf = torch.full((cap + 1,), float("nan"), dtype=torch.float32, device="cuda")
+            buf[0] = len(divs)
+            if divs:
+                buf[1:1 + len(divs)] = torch.tensor(np.asarray(divs, dtype=np.float32), device="cuda")
+            gathered = [torch.empty_like(buf) for _ in range(world)]
+            dist.all_gather(gathered, buf)
+            divs = []
+            for g in gathered:
+                g = g.cpu().numpy()
+                divs.extend(g[1:1 + int(g[0])].tolist())
         mean = pu.median_f32(divs) if divs else np.float32(0.5)
         max_div = np.float32((mean if bool(cfg["assemble_divergence_relative"]) else np.float32(0.0)) + np.float32(cfg["assemble_ovlp_divergence"]))
         keep = div_all[first:] < max_div
