@@ -75,6 +75,11 @@ struct Arena {
     void release(void* p) {
         for (auto& b : blocks) if (b.p == p) { b.used = false; return; }
     }
+    size_t cachedFreeBytes() const {
+        size_t n = 0;
+        for (const auto& b : blocks) if (!b.used) n += b.bytes;
+        return n;
+    }
     void trim() {   // free every unused block (synchronises the device)
         cudaDeviceSynchronize();
         std::vector<Block> keep;

@@ -859,7 +859,16 @@ static void overlapsChunk(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, ui
     totHits += hQHitOff[nQ];
 
     // sub-batches of consecutive queries with a bounded number of hits
-    uint64_t budget = 256ULL << 20;
+    // k-mer hits per sub-batch: as many as comfortably fit (about 80 B of workspace per hit).  Fewer, larger
+    // sub-batches keep the first partition levels of the hit sort busy: they run one warp per read.
+    uint64_t budget = 768ULL << 20;
+    {
+        size_t freeB = 0, totalB = 0;
+        if (cudaMemGetInfo(&freeB, &totalB) == cudaSuccess) {
+            const uint64_t usable = (uint64_t)((freeB + ctx->arena.cachedFreeBytes()) * 0.55);
+            budget = std::max<uint64_t>(64ULL << 20, std::min<uint64_t>(budget, usable / 80));
+        }
+    }
     if (const char* e = getenv("FG_HIT_BUDGET")) budget = std::max<uint64_t>(1024, strtoull(e, nullptr, 10));
     DevBuf<Elem> hits, ord; DevBuf<int32_t> score, back; DevBuf<Cand> cands; DevBuf<uint8_t> flags;
     DevBuf<uint32_t> gStart, candIds, pairIds;
