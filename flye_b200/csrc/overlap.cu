@@ -464,6 +464,16 @@ __global__ void __launch_bounds__(128) chainDpKernel(const Elem* __restrict__ hi
             const int32_t jd = abs(dc - de);
             const int32_t gap = jd > 100 ? 2 * jd : (jd >> 1);            // int32(float(LG_GAP|SM_GAP) * jd), :299
             const int32_t s = ok ? sj + min(min(dc, de), k) - gap : INT32_MIN;
+            if (jb == i - 1) {
+                // fast path (the usual case on low-error reads): the nearest predecessor already improves and satisfies
+                // the first break rule, so the reference's scan ends after one step.  Taken when it holds for both halves.
+                const uint32_t fb = __ballot_sync(0xffffffffu, sl == 0 && (!act || (ok && jd == 0 && dc < k && s > 0)));
+                if (fb == 0x00010001u) {
+                    const int32_t s0 = __shfl_sync(0xffffffffu, s, 0, 16);
+                    if (act) { best = s0; bestId = i - 1; ++cells; }
+                    break;
+                }
+            }
             // second break rule (sorted-axis distance) first: nothing beyond its first lane is ever evaluated
             const uint32_t far = (__ballot_sync(0xffffffffu, in && (extSorted ? de : dc) > P.maxJump) >> hs) & 0xffffu;
             int stopLane = far ? (__ffs(far) - 1) : 15;
