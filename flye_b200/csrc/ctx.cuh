@@ -72,7 +72,6 @@ struct fg_ctx {
 
     // ---- overlap results (host, library owned) ----
     std::vector<uint64_t> resOffsets;
-    std::vector<fg_overlap> resOverlaps;
     std::vector<int32_t> resAln;
     fg::PinnedBuf<fg_overlap> pinnedOut;  // D2H staging, kept across calls
 

@@ -884,7 +884,6 @@ static void overlapsChunk(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, ui
     DevBuf<uint32_t> gStart, candIds, pairIds;
     SortWorkspace ws; DevBuf<Seg> segsQ;
     DevBuf<uint32_t> counters(32);
-    std::vector<std::vector<fg_overlap>> perQuery;   // not used; results are appended in query order
 
     uint32_t qa = 0;
     while (qa < nQ) {
@@ -1057,7 +1056,6 @@ void overlapsBatch(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, const fg_
     { volatile float a = 0.01f; volatile float m = a * prm.min_overlap; P.minUniqueF = m; }   // minKmerSruvivalRate * _minOverlap
 
     ctx->resOffsets.assign(nQ + 1, 0);
-    ctx->resOverlaps.clear();
     ctx->resAln.clear();
     uint64_t totHits = 0, totPairs = 0, totDpPairs = 0, totCells = 0;
     PinnedBuf<fg_overlap>& pinned = ctx->pinnedOut;   // all chunks / sub-batches land here; the epilogue compacts in place
@@ -1144,9 +1142,7 @@ void overlapsBatch(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, const fg_
         for (size_t i = 0; i < nRaw; ++i)
             if (hOut[i].reserved == 0u) { if (w2 != i) hOut[w2] = hOut[i]; ++w2; }
     }
-    size_t pos = nRaw;
     ctx->resOffsets[nQ] = wpos;
-    if (pos != nRaw) throw Error(FG_ERR_INTERNAL, "overlap records out of query order");
 
     ctx->timings.emplace_back("arena_mallocs", (float)(ctx->arena.mallocCalls - mallocs0)); ctx->timingCalls.push_back(1);
     ctx->timings.emplace_back("arena_gib", (float)(ctx->arena.totalBytes / 1073741824.0)); ctx->timingCalls.push_back(1);
