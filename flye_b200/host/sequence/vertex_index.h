@@ -2,6 +2,7 @@
 // Every method forwards to the C ABI (include/flye_b200.h); the k-mer counter, the per-read selection, the position
 // lists and the repetitive set all live in HBM.  Errors come back as std::runtime_error with the reference's texts.
 #pragma once
+#include <cstdlib>
 #include <map>
 #include <memory>
 #include <stdexcept>
@@ -16,7 +17,8 @@
 typedef std::map<size_t, size_t> KmerDistribution;
 
 namespace flye_b200 {
-// one device context per process and device, shared by VertexIndex / OverlapDetector
+// one device context per VertexIndex (reads + counts + index of ONE container), shared with the OverlapDetector /
+// OverlapContainer built on top of it; the CUDA device is taken from FLYE_B200_DEVICE (default 0)
 struct DeviceContext {
     fg_ctx* ctx = nullptr;
     const void* uploadedFrom = nullptr;   // the SequenceContainer whose reads are resident
@@ -56,10 +58,9 @@ struct DeviceContext {
         check(fg_queries_upload(ctx, words.data(), offsets.data(), lengths.data(), (uint32_t)lengths.size()));
         queriesFrom = &sc;
     }
-    static std::shared_ptr<DeviceContext> shared(int device = 0) {
-        static std::shared_ptr<DeviceContext> inst;
-        if (!inst) inst = std::make_shared<DeviceContext>(device);
-        return inst;
+    static std::shared_ptr<DeviceContext> create() {
+        const char* e = std::getenv("FLYE_B200_DEVICE");
+        return std::make_shared<DeviceContext>(e ? std::atoi(e) : 0);
     }
 };
 }  // namespace flye_b200
@@ -67,7 +68,7 @@ struct DeviceContext {
 class VertexIndex {
 public:
     VertexIndex(const SequenceContainer& seqContainer, float sampleRate)
-        : _seqContainer(seqContainer), _outputProgress(false), _sampleRate(sampleRate), _dev(flye_b200::DeviceContext::shared()) {}
+        : _seqContainer(seqContainer), _outputProgress(false), _sampleRate(sampleRate), _dev(flye_b200::DeviceContext::create()) {}
     ~VertexIndex() { this->clear(); }
     VertexIndex(const VertexIndex&) = delete;
     void operator=(const VertexIndex&) = delete;
