@@ -522,7 +522,7 @@ static constexpr int WARP_TAB_BYTES = 128;   // per-warp scratch of the partitio
 // to the resulting permutation.
 struct NoSink { FG_DEV void operator()(long, long, int) const {} };
 #ifndef FG_WARP_MINI
-#define FG_WARP_MINI 48
+#define FG_WARP_MINI 32
 #endif
 static constexpr int WARP_MINI = FG_WARP_MINI;
 
