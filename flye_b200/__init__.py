@@ -22,7 +22,7 @@ SYMBOLS = ["fg_ctx_create", "fg_ctx_destroy", "fg_last_error", "fg_stream", "fg_
            "fg_reads_upload", "fg_reads_upload_ascii", "fg_queries_upload", "fg_count_kmers", "fg_kmer_hist", "fg_kmer_freq",
            "fg_build_index_solid", "fg_build_index_minimizers", "fg_index_clear", "fg_index_lookup",
            "fg_index_positions", "fg_index_export", "fg_overlaps_batch", "fg_comm_unique_id", "fg_comm_init",
-           "fg_comm_set_shard", "fg_debug_warp_sort", "fg_debug_edit_distance"]
+           "fg_comm_set_shard", "fg_debug_warp_sort", "fg_debug_edit_distance", "fg_debug_edit_distance_rc"]
 
 
 class IndexStats(C.Structure):
@@ -92,6 +92,7 @@ def load_lib():
     lib.fg_comm_set_shard.argtypes = [vp, C.c_uint32, C.c_uint32]
     lib.fg_debug_warp_sort.argtypes = [vp, u64p, u32p, u64p, C.c_uint32]
     lib.fg_debug_edit_distance.argtypes = [vp, u8p, C.c_int, u8p, C.c_int, C.POINTER(C.c_int)]
+    lib.fg_debug_edit_distance_rc.argtypes = [vp, u8p, C.c_int, C.c_int, u8p, C.c_int, C.c_int, C.POINTER(C.c_int)]
     _lib = lib
     return lib
 
@@ -303,6 +304,14 @@ class Engine:
         b = np.ascontiguousarray(b, dtype=np.uint8)
         d = C.c_int()
         self._check(self.lib.fg_debug_edit_distance(self.ctx, _ptr(a, C.c_uint8), len(a), _ptr(b, C.c_uint8), len(b), C.byref(d)))
+        return d.value
+
+    def debug_edit_distance_rc(self, a, rc_a, b, rc_b):
+        a = np.ascontiguousarray(a, dtype=np.uint8)
+        b = np.ascontiguousarray(b, dtype=np.uint8)
+        d = C.c_int()
+        self._check(self.lib.fg_debug_edit_distance_rc(self.ctx, _ptr(a, C.c_uint8), len(a), int(rc_a), _ptr(b, C.c_uint8), len(b), int(rc_b),
+                                                       C.byref(d)))
         return d.value
 
     def timings(self):

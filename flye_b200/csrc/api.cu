@@ -48,6 +48,7 @@ __global__ void __launch_bounds__(256) packAsciiKernel(const char* __restrict__ 
 }
 
 void installReads(fg_ctx* ctx, uint32_t n) {
+    ctx->hpcReads.valid = false;
     ctx->nReads = n;
     ctx->hBasePrefix.assign(n + 1, 0);
     for (uint32_t i = 0; i < n; ++i) ctx->hBasePrefix[i + 1] = ctx->hBasePrefix[i] + ctx->hLen[i];
@@ -166,6 +167,8 @@ int fg_queries_upload(fg_ctx* ctx, const uint64_t* packed, const uint64_t* wordO
         if (n) FG_CUDA(cudaMemcpyAsync(ctx->dQsLen.p, lengths, n * 4ULL, cudaMemcpyHostToDevice, ctx->stream));
         FG_CUDA(cudaStreamSynchronize(ctx->stream));
         ctx->nQsReads = n;
+        ctx->nQsWords = off[n];
+        ctx->hpcQueries.valid = false;
     });
 }
 
@@ -322,7 +325,14 @@ int fg_overlaps_batch(fg_ctx* ctx, const uint32_t* queryIds, uint32_t n, const f
 int fg_debug_edit_distance(fg_ctx* ctx, const uint8_t* a, int n, const uint8_t* b, int m, int* distance) {
     return guarded(ctx, [&] {
         if (n < 0 || m < 0 || !distance) throw Error(FG_ERR_ARG, "bad argument");
-        *distance = fg::debugEditDistance(ctx, a, n, b, m);
+        *distance = fg::debugEditDistance(ctx, a, n, b, m, 0, 0);
+    });
+}
+
+int fg_debug_edit_distance_rc(fg_ctx* ctx, const uint8_t* a, int n, int rc_a, const uint8_t* b, int m, int rc_b, int* distance) {
+    return guarded(ctx, [&] {
+        if (n < 0 || m < 0 || !distance) throw Error(FG_ERR_ARG, "bad argument");
+        *distance = fg::debugEditDistance(ctx, a, n, b, m, rc_a, rc_b);
     });
 }
 

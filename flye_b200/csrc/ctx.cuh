@@ -29,6 +29,11 @@ struct fg_ctx {
     std::vector<uint32_t> hQsLen;
     fg::DevBuf<uint64_t> dQsSeq, dQsWordOff;
     fg::DevBuf<uint32_t> dQsLen;
+    uint64_t nQsWords = 0;
+
+    // ---- homopolymer-compressed copies of the two sequence sets (editdist.cu), built on first use, dropped on upload ----
+    struct HpcCache { fg::DevBuf<uint64_t> seq; fg::DevBuf<uint32_t> mask, prefix; bool valid = false; };
+    HpcCache hpcReads, hpcQueries;
 
     // ---- k-mer slot space: read i owns slots [slotOff[i], slotOff[i]+n_i), n_i = max(L_i-k,0) (kmer.h:185-198),
     //      slotOff is a prefix of roundup32(n_i) so that every read owns whole 32-bit bitmap words ----
@@ -147,9 +152,8 @@ void groupStart();
 void groupEnd();
 inline bool sharded(const fg_ctx* ctx) { return ctx->nRanks > 1 && ctx->ncclComm && ctx->shardSet; }
 
-void editDistances(fg_ctx* ctx, fg_overlap* dOv, const fg_overlap* hOv, uint32_t nOv, bool useHpc, const uint64_t* qSeq,
-                   const uint64_t* qWordOff, const uint32_t* qLen);
-int debugEditDistance(fg_ctx* ctx, const uint8_t* a, int n, const uint8_t* b, int m);
+void editDistances(fg_ctx* ctx, fg_overlap* dOv, const fg_overlap* hOv, uint32_t nOv, bool useHpc, bool querySet);
+int debugEditDistance(fg_ctx* ctx, const uint8_t* a, int n, const uint8_t* b, int m, int rcA, int rcB);
 void debugWarpSort(fg_ctx* ctx, uint64_t* keys, uint32_t* vals, const uint64_t* segOffsets, uint32_t nSegs);
 
 }  // namespace fg

@@ -5,126 +5,153 @@
 // edlibAlign(k=-1, EDLIB_MODE_NW, EDLIB_TASK_DISTANCE) returns (edlib.cpp:141-212).  The distance is a
 // unique integer, so any exact algorithm is bit-compatible; the float division stays on the host.
 //
-// K9a hpcKernel   one warp per overlap and side: ballot-compaction of "base != previous base" into a
-//                 byte-per-base scratch sequence (either strand of the read is read in place).
-// K9b wfaKernel   one warp per overlap: furthest-reaching wavefront (Ukkonen / Myers O(ND)) over the
-//                 diagonals, 32 diagonals per step, match extension by direct comparison.  Work is O(d^2 + n)
-//                 for distance d — HiFi overlaps have d of a few hundred on 10^4 bases, so this is ~50x less
-//                 work than the bit-vector band edlib uses, and it needs no band-doubling restarts.
+// K9a hpcReadsKernel  once per sequence set (cached until the next upload): every read is homopolymer-compressed as
+//                 a whole into a 2-bit packed sequence, with a run-start mask and a running count per 32-base word.
+//                 The compression of a SUBSTRING is the runs that intersect it, i.e. a contiguous slice
+//                 [rank(begin), rank(end-1)] of the read's compressed sequence, and the compression of a substring
+//                 of the reverse-complement strand is the reverse complement of a slice — so an overlap needs no
+//                 compaction pass of its own, only two rank look-ups.
+// K9b wfaKernel   one warp per overlap: furthest-reaching wavefront (Ukkonen / Myers O(ND)) over the diagonals,
+//                 32 diagonals per step.  Sequences are read through "views" (slice + strand) straight from the
+//                 packed words; a lane extends its diagonal 32 bases per compare (xor + count trailing zeros), the
+//                 few diagonals that keep matching (the true alignment path) are extended by the whole warp, 1024
+//                 bases per step.  Wavefronts live in shared memory up to WF_DMAX edits and continue in global
+//                 scratch beyond.  Work is O(d^2 + n) for distance d — HiFi overlaps have d ~ 10^2 on 10^4 bases.
 #include "ctx.cuh"
 
 namespace fg {
 
-__device__ __forceinline__ uint32_t baseOf(const uint64_t* __restrict__ words, uint32_t L, bool strand, uint32_t i) {
-    // DnaSequence::atRaw, sequence.h:120-129
-    const uint32_t idx = strand ? (L - 1 - i) : i;
-    const uint32_t c = (uint32_t)(words[idx >> 5] >> ((idx & 31) * 2)) & 3u;
-    return strand ? 3u - c : c;
+// ---- K9a ----------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t evenBits(uint64_t x) {   // bit 2t of x -> bit t
+    x &= 0x5555555555555555ULL;
+    x = (x | (x >> 1)) & 0x3333333333333333ULL;
+    x = (x | (x >> 2)) & 0x0f0f0f0f0f0f0f0fULL;
+    x = (x | (x >> 4)) & 0x00ff00ff00ff00ffULL;
+    x = (x | (x >> 8)) & 0x0000ffff0000ffffULL;
+    x = (x | (x >> 16)) & 0x00000000ffffffffULL;
+    return (uint32_t)x;
 }
 
-struct EdJob { uint64_t offA, offB; };   // byte offsets of the two compressed sequences in the scratch
-
-__global__ void __launch_bounds__(256) hpcKernel(const uint64_t* __restrict__ seq, const uint64_t* __restrict__ wordOff,
-                                                 const uint32_t* __restrict__ len, const uint64_t* __restrict__ qseq,
-                                                 const uint64_t* __restrict__ qWordOff, const uint32_t* __restrict__ qlen,
-                                                 const fg_overlap* __restrict__ ov, uint32_t nOv,
-                                                 const EdJob* __restrict__ jobs, bool compress, uint8_t* __restrict__ scratch,
-                                                 uint32_t* __restrict__ outLen) {
-    const uint32_t w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (w >= 2 * nOv) return;
+// one warp per read.  hpcSeq must be zero on entry (bases are OR-ed in).  For raw word w of the read:
+// startMask[w] bit t = base 32w+t starts a run (differs from its predecessor; base 0 always does),
+// startPrefix[w] = number of run starts in the words before w.
+__global__ void __launch_bounds__(128) hpcReadsKernel(const uint64_t* __restrict__ seq, const uint64_t* __restrict__ wordOff,
+                                                      const uint32_t* __restrict__ len, uint32_t nReads,
+                                                      unsigned long long* __restrict__ hpcSeq, uint32_t* __restrict__ startMask,
+                                                      uint32_t* __restrict__ startPrefix) {
+    const uint32_t r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= nReads) return;
     const int lane = threadIdx.x & 31;
-    const fg_overlap o = ov[w >> 1];
-    const bool side = w & 1;   // 0: cur, 1: ext
-    const uint32_t id = side ? o.ext_id : o.cur_id;
-    const uint32_t start = (uint32_t)(side ? o.ext_begin : o.cur_begin);
-    const uint32_t n = (uint32_t)(side ? (o.ext_end - o.ext_begin) : (o.cur_end - o.cur_begin));
-    const uint32_t r = id >> 1, L = side ? len[r] : qlen[r];   // side 0 = the query ("cur"), possibly from the second set
-    const bool strand = id & 1;
-    const uint64_t* words = side ? seq + wordOff[r] : qseq + qWordOff[r];
-    uint8_t* dst = scratch + (side ? jobs[w >> 1].offB : jobs[w >> 1].offA);
-    uint32_t out = 0;
-    for (uint32_t i0 = 0; i0 < n; i0 += 32) {
-        const uint32_t i = i0 + lane;
-        uint32_t c = 255, prev = 255;
-        if (i < n) {
-            c = baseOf(words, L, strand, start + i);
-            if (i > 0) prev = baseOf(words, L, strand, start + i - 1);
+    const uint64_t off = wordOff[r];
+    const uint32_t L = len[r], nWords = (L + 31) >> 5;
+    uint32_t tot = 0;
+    for (uint32_t w0 = 0; w0 < nWords; w0 += 32) {
+        const uint32_t wi = w0 + lane;
+        uint64_t word = 0; uint32_t mask = 0;
+        if (wi < nWords) {
+            word = seq[off + wi];
+            const uint64_t prevBase = wi ? seq[off + wi - 1] >> 62 : 0ULL;
+            const uint64_t x = word ^ ((word << 2) | prevBase);
+            mask = evenBits(x | (x >> 1));
+            if (wi == 0) mask |= 1u;
+            const uint32_t nb = min(32u, L - 32u * wi);
+            if (nb < 32) mask &= (1u << nb) - 1u;
         }
-        const bool keep = i < n && (!compress || i == 0 || c != prev);
-        const uint32_t m = __ballot_sync(0xffffffffu, keep);
-        if (keep) dst[out + __popc(m & ((1u << lane) - 1u))] = (uint8_t)c;
-        out += __popc(m);
+        const uint32_t cnt = __popc(mask);
+        uint32_t inc = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
+        const uint32_t o = tot + inc - cnt;
+        if (wi < nWords) {
+            startMask[off + wi] = mask; startPrefix[off + wi] = o;
+            unsigned long long v = 0; int c = 0;
+            for (uint32_t mm = mask; mm; mm &= mm - 1) { const int t = __ffs(mm) - 1; v |= ((word >> (2 * t)) & 3ULL) << (2 * c); ++c; }
+            if (cnt) {
+                const uint32_t sh = (o & 31) * 2;
+                atomicOr(hpcSeq + off + (o >> 5), v << sh);
+                if (sh && (o & 31) + cnt > 32) atomicOr(hpcSeq + off + (o >> 5) + 1, v >> (64 - sh));
+            }
+        }
+        tot += __shfl_sync(0xffffffffu, inc, 31);
     }
-    if (lane == 0) outLen[w] = out;
 }
 
-// Exact global edit distance of a[0,n) and b[0,m).  fr[k] = furthest row i reached on diagonal k = j - i with
-// the current number of edits; -1 = unreachable.  One warp; the two wavefront arrays live in global scratch
-// (index k + n).
-static constexpr int WFA_SHORT = 8;
+// ---- K9b ----------------------------------------------------------------------------------------------------
+// A sequence as the wavefront kernel sees it: n bases, base p = words[r0 + p] (forward strand) or the complement of
+// words[r1 - p] (reverse-complement strand), positions counted in 2-bit bases from `words`.
+struct SeqView { const uint64_t* words; int32_t r0, r1, n; bool rc; };
 
-__device__ int wfaEditDistance(const uint8_t* __restrict__ a, int n, const uint8_t* __restrict__ b, int m, int* __restrict__ wfA,
-                               int* __restrict__ wfB) {
-    const int lane = threadIdx.x & 31;
-    if (n == 0) return m;
-    if (m == 0) return n;
-    int* prev = wfA; int* cur = wfB;
-    {   // s = 0: common prefix, 32 bases per step
-        const int lim = min(n, m);
-        int i = 0;
-        for (;;) {
-            const int j = i + lane;
-            const uint32_t mm = __ballot_sync(0xffffffffu, j >= lim || a[j] != b[j]);
-            if (mm) { i += __ffs(mm) - 1; break; }
-            i += 32;
-        }
-        if (lane == 0) prev[n] = i;
-        if (m == n && i >= n) return 0;
+__device__ __forceinline__ uint64_t fetchFwd(const uint64_t* __restrict__ words, int32_t h) {   // 32 bases from base h >= 0
+    const uint64_t* w = words + (h >> 5);
+    const int sh = (h & 31) * 2;
+    return (w[0] >> sh) | ((w[1] << 1) << (63 - sh));
+}
+// 32 bases of the view starting at p (base t in bits 2t, 2t+1); bases at or beyond n are unspecified
+__device__ __forceinline__ uint64_t fetchView(const SeqView& v, int32_t p) {
+    if (!v.rc) return fetchFwd(v.words, v.r0 + p);
+    const int32_t h = v.r1 - p - 31;
+    const uint64_t x = h >= 0 ? fetchFwd(v.words, h) : fetchFwd(v.words, 0) << (2 * min(-h, 31));
+    return rev2(~x);
+}
+// number of matching bases from (pa, pb), at most min(lim, 32)
+__device__ __forceinline__ int matchLen32(const SeqView& a, int32_t pa, const SeqView& b, int32_t pb, int lim) {
+    const uint64_t x = fetchView(a, pa) ^ fetchView(b, pb);
+    const int e = x ? (__ffsll((long long)x) - 1) >> 1 : 32;
+    return min(e, lim);
+}
+// the same by the whole warp, 1024 bases per step (every lane returns the result)
+__device__ __forceinline__ int matchLenWarp(const SeqView& a, int32_t pa, const SeqView& b, int32_t pb, int lim, int lane) {
+    for (int base = 0;; base += 1024) {
+        const int o = base + 32 * lane;
+        const int l = max(0, min(32, lim - o));
+        const int e = l > 0 ? matchLen32(a, pa + o, b, pb + o, l) : 0;
+        const uint32_t stop = __ballot_sync(0xffffffffu, e < 32);
+        if (stop) { const int f = __ffs(stop) - 1; return base + 32 * f + __shfl_sync(0xffffffffu, e, f); }
     }
-    __syncwarp();
-    const int target = m - n;
-    for (int s = 1; s <= n + m; ++s) {
+}
+
+static constexpr int WF_DMAX = 254;                 // edits handled with the wavefronts in shared memory
+static constexpr int WF_SMEM_INTS = 2 * WF_DMAX + 5;   // diagonals -DMAX-2 .. DMAX+2
+static constexpr int WF_NEG = -(1 << 29);
+
+// Steps s = sFrom .. sTo of the wavefront recurrence.  fr[k + base] = furthest row i reached on diagonal k = j - i with
+// s edits (WF_NEG / -1 = unreachable); `prev` holds step sFrom-1 on entry.  Returns the distance when the end is
+// reached, else -1 with `prev` holding step sTo.
+__device__ int wfaSteps(const SeqView& A, const SeqView& B, int*& prev, int*& cur, int base, int sFrom, int sTo, int lane) {
+    const int n = A.n, m = B.n, target = m - n;
+    for (int s = sFrom; s <= sTo; ++s) {
         const int lo = max(-s, -n), hi = min(s, m);
         const int plo = max(-(s - 1), -n), phi = min(s - 1, m);
+        if (lane < 2) prev[plo - 1 - lane + base] = WF_NEG; else if (lane < 4) prev[phi - 1 + lane + base] = WF_NEG;   // guards
+        __syncwarp();
         bool done = false;
         for (int k0 = lo; k0 <= hi; k0 += 32) {
             const int k = k0 + lane;
             int best = -1;
             bool longRun = false;
             if (k <= hi) {
-                if (k - 1 >= plo && k - 1 <= phi) { const int i = prev[k - 1 + n]; if (i >= 0 && i + k <= m) best = i; }
-                if (k >= plo && k <= phi) { const int i = prev[k + n]; if (i >= 0 && i + 1 <= n && i + k + 1 <= m) best = max(best, i + 1); }
-                if (k + 1 >= plo && k + 1 <= phi) { const int i = prev[k + 1 + n]; if (i >= 0 && i + 1 <= n) best = max(best, i + 1); }
-                if (best >= 0) {   // short extension by the lane itself (off-diagonals stop after ~1 base)
-                    const uint8_t* pa = a + best; const uint8_t* pb = b + best + k;
-                    const int lim = min(min(n - best, m - best - k), WFA_SHORT);
-                    int e = 0;
-                    while (e < lim && pa[e] == pb[e]) ++e;
+                const int a = prev[k - 1 + base], b = prev[k + base], c = prev[k + 1 + base];
+                if (a >= 0 && a + k <= m) best = a;
+                if (b >= 0 && b + 1 <= n && b + k + 1 <= m) best = max(best, b + 1);
+                if (c >= 0 && c + 1 <= n) best = max(best, c + 1);
+                if (best >= 0) {
+                    const int lim = min(n - best, m - best - k);
+                    const int e = lim > 0 ? matchLen32(A, best, B, best + k, lim) : 0;
                     best += e;
-                    longRun = e == WFA_SHORT;
+                    longRun = e == 32 && lim > 32;
                 }
             }
-            // the few diagonals that keep matching (the true alignment path) are extended by the whole warp, 32 bases
-            // per step, instead of one lane crawling alone
             uint32_t lm = __ballot_sync(0xffffffffu, longRun);
             while (lm) {
                 const int src = __ffs(lm) - 1;
                 lm &= lm - 1;
-                int bb = __shfl_sync(0xffffffffu, best, src);
+                const int bb = __shfl_sync(0xffffffffu, best, src);
                 const int kk = k0 + src;
-                const int lim = min(n - bb, m - bb - kk);
-                int e = 0;
-                for (;;) {
-                    const int i = e + lane;
-                    const bool mismatch = i >= lim || a[bb + i] != b[bb + kk + i];
-                    const uint32_t mm = __ballot_sync(0xffffffffu, mismatch);
-                    if (mm) { e += __ffs(mm) - 1; break; }
-                    e += 32;
-                }
+                const int e = matchLenWarp(A, bb, B, bb + kk, min(n - bb, m - bb - kk), lane);
                 if (lane == src) best = bb + e;
             }
             if (k <= hi) {
-                cur[k + n] = best;
+                cur[k + base] = best;
                 if (k == target && best >= n) done = true;
             }
         }
@@ -132,69 +159,143 @@ __device__ int wfaEditDistance(const uint8_t* __restrict__ a, int n, const uint8
         __syncwarp();
         int* t = prev; prev = cur; cur = t;
     }
-    return -1;   // unreachable: the distance never exceeds max(n,m)
+    return -1;
 }
 
-__global__ void __launch_bounds__(128) wfaKernel(fg_overlap* __restrict__ ov, uint32_t nOv, const EdJob* __restrict__ jobs,
-                                                 const uint32_t* __restrict__ hpcLen, const uint8_t* __restrict__ scratch,
+// exact global edit distance of the two views; one warp.  smem: 2 * WF_SMEM_INTS ints; gA/gB: n + m + 8 ints each.
+__device__ int wfaEditDistance(const SeqView& A, const SeqView& B, int* smem, int* gA, int* gB) {
+    const int lane = threadIdx.x & 31;
+    const int n = A.n, m = B.n;
+    if (n == 0) return m;
+    if (m == 0) return n;
+    int* prev = smem; int* cur = smem + WF_SMEM_INTS;
+    const int base = WF_DMAX + 2;
+    const int i0 = matchLenWarp(A, 0, B, 0, min(n, m), lane);   // s = 0: common prefix
+    if (m == n && i0 >= n) return 0;
+    if (lane == 0) prev[base] = i0;
+    __syncwarp();
+    const int dCap = min(WF_DMAX, n + m);
+    int d = wfaSteps(A, B, prev, cur, base, 1, dCap, lane);
+    if (d >= 0 || dCap == n + m) return d;
+    // continue in global memory
+    const int gBase = n + 2;
+    const int plo = max(-dCap, -n), phi = min(dCap, m);
+    for (int k = plo + lane; k <= phi; k += 32) gA[k + gBase] = prev[k + base];
+    __syncwarp();
+    prev = gA; cur = gB;
+    return wfaSteps(A, B, prev, cur, gBase, dCap + 1, n + m, lane);
+}
+
+struct HpcSet { const uint64_t* seq; const uint64_t* hpc; const uint32_t* mask; const uint32_t* prefix; const uint64_t* wordOff; const uint32_t* len; };
+
+// run index of raw base i of a read
+__device__ __forceinline__ int32_t hpcRank(const HpcSet& S, uint64_t off, uint32_t i) {
+    const uint32_t w = i >> 5;
+    return (int32_t)(S.prefix[off + w] + __popc(S.mask[off + w] & (0xffffffffu >> (31 - (i & 31))))) - 1;
+}
+// the substring [begin, end) of sequence `id` (strand = id & 1), homopolymer-compressed or raw
+__device__ SeqView makeView(const HpcSet& S, uint32_t id, int32_t begin, int32_t end, bool compress) {
+    SeqView v;
+    const uint32_t r = id >> 1;
+    const uint64_t off = S.wordOff[r];
+    const int32_t L = (int32_t)S.len[r];
+    v.rc = id & 1;
+    v.words = (compress ? S.hpc : S.seq) + off;
+    if (end <= begin) { v.r0 = 0; v.r1 = -1; v.n = 0; return v; }
+    const int32_t fb = v.rc ? L - end : begin, fe = v.rc ? L - begin : end;   // forward-strand coordinates, fe exclusive
+    if (compress) { v.r0 = hpcRank(S, off, (uint32_t)fb); v.r1 = hpcRank(S, off, (uint32_t)(fe - 1)); }
+    else { v.r0 = fb; v.r1 = fe - 1; }
+    v.n = v.r1 - v.r0 + 1;
+    return v;
+}
+
+__global__ void __launch_bounds__(128) wfaKernel(fg_overlap* __restrict__ ov, uint32_t nOv, HpcSet cur, HpcSet ext, bool compress,
                                                  int* __restrict__ wfScratch, uint64_t wfStride, uint32_t* __restrict__ nextJob) {
+    __shared__ int wfSm[4][2 * WF_SMEM_INTS];
     const uint32_t warpGlobal = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
-    int* wfA = wfScratch + (uint64_t)warpGlobal * 2 * wfStride;
-    int* wfB = wfA + wfStride;
+    int* gA = wfScratch + (uint64_t)warpGlobal * 2 * wfStride;
+    int* gB = gA + wfStride;
     for (;;) {
         uint32_t j = 0;
         if (lane == 0) j = atomicAdd(nextJob, 1u);
         j = __shfl_sync(0xffffffffu, j, 0);
         if (j >= nOv) return;
-        const int n = (int)hpcLen[2 * j], m = (int)hpcLen[2 * j + 1];
-        const int d = wfaEditDistance(scratch + jobs[j].offA, n, scratch + jobs[j].offB, m, wfA, wfB);
-        if (lane == 0) { ov[j].edit_distance = d; ov[j].aln_len = max(n, m); }
+        const fg_overlap o = ov[j];
+        const SeqView A = makeView(cur, o.cur_id, o.cur_begin, o.cur_end, compress);
+        const SeqView B = makeView(ext, o.ext_id, o.ext_begin, o.ext_end, compress);
+        const int d = wfaEditDistance(A, B, wfSm[threadIdx.x >> 5], gA, gB);
+        if (lane == 0) { ov[j].edit_distance = d; ov[j].aln_len = max(A.n, B.n); }
         __syncwarp();
     }
 }
 
-// device overlaps (already gathered) -> edit_distance / aln_len filled in
-void editDistances(fg_ctx* ctx, fg_overlap* dOv, const fg_overlap* hOv, uint32_t nOv, bool useHpc, const uint64_t* qSeq,
-                   const uint64_t* qWordOff, const uint32_t* qLen) {
-    if (!nOv) return;
-    std::vector<EdJob> jobs(nOv);
-    uint64_t off = 0; uint32_t maxLen = 0;
-    for (uint32_t i = 0; i < nOv; ++i) {
-        const uint32_t la = (uint32_t)std::max(0, hOv[i].cur_end - hOv[i].cur_begin), lb = (uint32_t)std::max(0, hOv[i].ext_end - hOv[i].ext_begin);
-        jobs[i].offA = off; off += (la + 15u) & ~15u;
-        jobs[i].offB = off; off += (lb + 15u) & ~15u;
-        maxLen = std::max(maxLen, std::max(la, lb));
+// homopolymer-compressed copy of a sequence set (see K9a)
+static void buildHpc(fg_ctx* ctx, fg_ctx::HpcCache& c, const uint64_t* seq, const uint64_t* wordOff, const uint32_t* len, uint32_t nReads,
+                     uint64_t nWords) {
+    c.seq.alloc(nWords + 4); c.mask.alloc(nWords + 4); c.prefix.alloc(nWords + 4);
+    FG_CUDA(cudaMemsetAsync(c.seq.p, 0, (nWords + 4) * 8, ctx->stream));
+    if (nReads) {
+        hpcReadsKernel<<<(nReads + 3) / 4, 128, 0, ctx->stream>>>(seq, wordOff, len, nReads, reinterpret_cast<unsigned long long*>(c.seq.p), c.mask.p,
+                                                                  c.prefix.p);
+        checkLaunch(ctx, "hpcReadsKernel");
     }
-    DevBuf<EdJob> dJobs(nOv);
-    DevBuf<uint8_t> scratch(off + 16);
-    DevBuf<uint32_t> hpcLen(2 * (size_t)nOv), nextJob(1);
-    FG_CUDA(cudaMemcpyAsync(dJobs.p, jobs.data(), nOv * sizeof(EdJob), cudaMemcpyHostToDevice, ctx->stream));
+    c.valid = true;
+}
+
+// device overlaps (already gathered) -> edit_distance / aln_len filled in.  querySet: the "cur" side refers to the second
+// sequence set (fg_queries_upload).
+void editDistances(fg_ctx* ctx, fg_overlap* dOv, const fg_overlap* hOv, uint32_t nOv, bool useHpc, bool querySet) {
+    if (!nOv) return;
+    uint32_t maxLen = 0;
+    for (uint32_t i = 0; i < nOv; ++i)
+        maxLen = std::max(maxLen, (uint32_t)std::max(std::max(0, hOv[i].cur_end - hOv[i].cur_begin), std::max(0, hOv[i].ext_end - hOv[i].ext_begin)));
+    HpcSet ext{ctx->dSeq.p, nullptr, nullptr, nullptr, ctx->dWordOff.p, ctx->dLen.p};
+    HpcSet cur = ext;
+    if (querySet) cur = HpcSet{ctx->dQsSeq.p, nullptr, nullptr, nullptr, ctx->dQsWordOff.p, ctx->dQsLen.p};
+    if (useHpc) {
+        if (!ctx->hpcReads.valid) buildHpc(ctx, ctx->hpcReads, ctx->dSeq.p, ctx->dWordOff.p, ctx->dLen.p, ctx->nReads, ctx->hWordOff.back());
+        ext.hpc = ctx->hpcReads.seq.p; ext.mask = ctx->hpcReads.mask.p; ext.prefix = ctx->hpcReads.prefix.p;
+        if (querySet) {
+            if (!ctx->hpcQueries.valid)
+                buildHpc(ctx, ctx->hpcQueries, ctx->dQsSeq.p, ctx->dQsWordOff.p, ctx->dQsLen.p, ctx->nQsReads, ctx->nQsWords);
+            cur.hpc = ctx->hpcQueries.seq.p; cur.mask = ctx->hpcQueries.mask.p; cur.prefix = ctx->hpcQueries.prefix.p;
+        } else { cur.hpc = ext.hpc; cur.mask = ext.mask; cur.prefix = ext.prefix; }
+    }
+    DevBuf<uint32_t> nextJob(1);
     FG_CUDA(cudaMemsetAsync(nextJob.p, 0, 4, ctx->stream));
-    hpcKernel<<<(2 * nOv + 7) / 8, 256, 0, ctx->stream>>>(ctx->dSeq.p, ctx->dWordOff.p, ctx->dLen.p, qSeq, qWordOff, qLen, dOv, nOv, dJobs.p, useHpc,
-                                                          scratch.p, hpcLen.p);
-    checkLaunch(ctx, "hpcKernel");
     const int blocks = 148 * 8, warps = blocks * 4;
     const uint64_t stride = 2ULL * maxLen + 8;
-    DevBuf<int> wf((uint64_t)warps * 2 * stride);
-    wfaKernel<<<blocks, 128, 0, ctx->stream>>>(dOv, nOv, dJobs.p, hpcLen.p, scratch.p, wf.p, stride, nextJob.p);
+    DevBuf<int> wf((uint64_t)warps * 2 * stride);   // only touched by overlaps with more than WF_DMAX edits
+    wfaKernel<<<blocks, 128, 0, ctx->stream>>>(dOv, nOv, cur, ext, useHpc, wf.p, stride, nextJob.p);
     checkLaunch(ctx, "wfaKernel");
     FG_CUDA(cudaStreamSynchronize(ctx->stream));
 }
 
-// test hook: exact edit distance of byte strings (values are compared as they are)
-__global__ void debugEdKernel(const uint8_t* a, int n, const uint8_t* b, int m, int* wf, uint64_t stride, int* out) {
-    int d = wfaEditDistance(a, n, b, m, wf, wf + stride);
+// test hook: exact edit distance of two base strings (values 0..3), optionally seen as reverse complements
+__global__ void debugEdKernel(const uint64_t* a, int n, bool rcA, const uint64_t* b, int m, bool rcB, int* wf, uint64_t stride, int* out) {
+    __shared__ int sm[2 * WF_SMEM_INTS];
+    SeqView A{a, 0, n - 1, n, rcA}, B{b, 0, m - 1, m, rcB};
+    const int d = wfaEditDistance(A, B, sm, wf, wf + stride);
     if ((threadIdx.x & 31) == 0) *out = d;
 }
 
-int debugEditDistance(fg_ctx* ctx, const uint8_t* a, int n, const uint8_t* b, int m) {
-    DevBuf<uint8_t> dA(n + 1), dB(m + 1);
+int debugEditDistance(fg_ctx* ctx, const uint8_t* a, int n, const uint8_t* b, int m, int rcA, int rcB) {
+    auto pack = [](const uint8_t* s, int len) {
+        std::vector<uint64_t> w((size_t)len / 32 + 3, 0);
+        for (int i = 0; i < len; ++i) {
+            if (s[i] > 3) throw Error(FG_ERR_ARG, "bases must be 0..3");
+            w[i >> 5] |= (uint64_t)s[i] << ((i & 31) * 2);
+        }
+        return w;
+    };
+    const std::vector<uint64_t> pa = pack(a, n), pb = pack(b, m);
+    DevBuf<uint64_t> dA(pa.size()), dB(pb.size());
     const uint64_t stride = (uint64_t)n + m + 8;
     DevBuf<int> wf(2 * stride), dOut(1);
-    if (n) FG_CUDA(cudaMemcpyAsync(dA.p, a, n, cudaMemcpyHostToDevice, ctx->stream));
-    if (m) FG_CUDA(cudaMemcpyAsync(dB.p, b, m, cudaMemcpyHostToDevice, ctx->stream));
-    debugEdKernel<<<1, 32, 0, ctx->stream>>>(dA.p, n, dB.p, m, wf.p, stride, dOut.p);
+    FG_CUDA(cudaMemcpyAsync(dA.p, pa.data(), pa.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+    FG_CUDA(cudaMemcpyAsync(dB.p, pb.data(), pb.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+    debugEdKernel<<<1, 32, 0, ctx->stream>>>(dA.p, n, rcA != 0, dB.p, m, rcB != 0, wf.p, stride, dOut.p);
     checkLaunch(ctx, "debugEdKernel");
     int d = -1;
     FG_CUDA(cudaMemcpyAsync(&d, dOut.p, 4, cudaMemcpyDeviceToHost, ctx->stream));

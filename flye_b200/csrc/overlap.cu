@@ -158,10 +158,21 @@ __global__ void __launch_bounds__(256) expandKernel(const uint32_t* __restrict__
 //                    the tasks balance the load across the chip whatever the segment-length distribution is.
 // ------------------------------------------------------------------------------------------------
 static constexpr int SORT_SMALL_MAX = 2048;
-static int sortSmallN() {   // elements per shared-memory task (FG_SORT_SMALL, default 512: 8 KB per warp, 24 resident warps per SM)
-    static int v = [] { const char* e = getenv("FG_SORT_SMALL"); int x = e ? atoi(e) : 512; return x < 64 ? 64 : (x > SORT_SMALL_MAX ? SORT_SMALL_MAX : x); }();
-    return v;
+// How the shared-memory kernel finishes the tasks of one segmented sort: the largest task (elements) and the variant
+// of sortSmallKernel.  Measured on B200: the k-mer hits of a read arrive in no useful order -> rank-table partition +
+// stable leaf pass by ranking (variant 3), 384-element tasks (28 resident warps per SM); the two per-pair sorts get
+// nearly sorted input, where one lane per leaf is cheaper (variant 1), 512-element tasks.
+struct SortCfg { int smallN, variant; };
+static int envInt(const char* name, int dflt, int lo, int hi) { const char* e = getenv(name); const int x = e ? atoi(e) : dflt; return x < lo ? lo : (x > hi ? hi : x); }
+static SortCfg sortCfgHits() {
+    static const SortCfg c{envInt("FG_SORT_SMALL_HITS", 384, 64, SORT_SMALL_MAX), envInt("FG_SORT_VAR_HITS", 3, 0, 3)};
+    return c;
 }
+static SortCfg sortCfgPairs() {
+    static const SortCfg c{envInt("FG_SORT_SMALL", 512, 64, SORT_SMALL_MAX), envInt("FG_SORT_VAR", 1, 0, 3)};
+    return c;
+}
+static int sortSmallN() { return std::min(sortCfgHits().smallN, sortCfgPairs().smallN); }   // sizes the task lists
 struct Seg { uint32_t start, n; };
 struct SortTask { uint32_t start, n; int depth; };
 
@@ -229,13 +240,22 @@ __global__ void __launch_bounds__(128) sortTailKernel(Elem* __restrict__ arr, co
     warpIntrosortRange(arr + t.start, 0, (idx_t)t.n, t.depth, (idx_t)smallN, sink, tabs[threadIdx.x >> 5], /*inGlobal*/ true);
 }
 
+// VARIANT 0: streaming two-ended partition + one lane per mini range (the code path of the global-memory kernels);
+//         1: rank-table partition (warpPartitionTable), leaves as in 0;
+//         2: warpIntrosortSmem<16>: rank-table partition down to the 16-element leaves, stable leaf pass by ranking;
+//         3: warpIntrosortSmem<32>: as 2, ranges of 17..32 elements partitioned one lane per range.
+// Dynamic shared memory: 4 warps x smallN elements, then (VARIANT > 0) 4 x 2 rank tables of smallN 16-bit entries, then
+// (VARIANT > 1) 4 cut bitmaps of smallN / 32 + 2 words.
+template <int VARIANT>
 __global__ void __launch_bounds__(128) sortSmallKernel(Elem* __restrict__ arr, const SortTask* __restrict__ tasks,
                                                        const uint32_t* __restrict__ taskCounter, uint32_t taskCap, uint32_t* __restrict__ next,
                                                        uint32_t smallN) {
     extern __shared__ __align__(16) unsigned char smemRaw[];
     __shared__ unsigned char tabs[4][WARP_TAB_BYTES];
-    Elem* sm = reinterpret_cast<Elem*>(smemRaw) + (threadIdx.x >> 5) * smallN;
-    unsigned char* tab = tabs[threadIdx.x >> 5];
+    const int wid = threadIdx.x >> 5;
+    Elem* sm = reinterpret_cast<Elem*>(smemRaw) + wid * smallN;
+    unsigned char* tab = VARIANT ? smemRaw + 4 * smallN * sizeof(Elem) + wid * smallN * 4 : tabs[wid];
+    uint32_t* bits = reinterpret_cast<uint32_t*>(smemRaw + 4 * smallN * (sizeof(Elem) + 4)) + wid * (smallN / 32 + 2);
     const int lane = threadIdx.x & 31;
     const uint32_t nTasks = min(*taskCounter, taskCap);
     for (;;) {
@@ -248,7 +268,9 @@ __global__ void __launch_bounds__(128) sortSmallKernel(Elem* __restrict__ arr, c
         for (uint32_t i = lane; i < k.n; i += 32) sm[i] = g[i];
         __syncwarp();
         NoSink none;
-        warpIntrosortRange(sm, 0, (idx_t)k.n, k.depth, 0, none, tab);
+        if (VARIANT == 2) warpIntrosortSmem<16>(sm, (idx_t)k.n, k.depth, reinterpret_cast<unsigned short*>(tab), reinterpret_cast<unsigned short*>(tab) + smallN, bits);
+        else if (VARIANT == 3) warpIntrosortSmem<32>(sm, (idx_t)k.n, k.depth, reinterpret_cast<unsigned short*>(tab), reinterpret_cast<unsigned short*>(tab) + smallN, bits);
+        else warpIntrosortRange<VARIANT == 1>(sm, 0, (idx_t)k.n, k.depth, 0, none, tab, false, (int)smallN);
         __syncwarp();
         for (uint32_t i = lane; i < k.n; i += 32) g[i] = sm[i];
         __syncwarp();
@@ -509,6 +531,154 @@ __global__ void __launch_bounds__(128) chainDpKernel(const Elem* __restrict__ hi
     if (sl == 0 && cells) atomicAdd(cellCount, cells);
 }
 
+// The same DP with exact pruning of the look-back.  Most cells of a low-error data set are spent by matches that lie off
+// the chain's diagonal: no predecessor can improve them, yet the reference walks back through every match within
+// maxJump.  Here every completed block of 16 matches leaves a summary (maximum score, range of diagonals cur - ext,
+// sorted-axis coordinate of its first match) in the registers of its half-warp.  For a block of predecessors
+//     s(j) = score[j] + min(dc, de, k) - gap(|diag_i - diag_j|)  <=  maxScore + k - gap(dist(diag_i, [minDiag, maxDiag]))
+// (gap is monotone), so when that bound is <= the best score found so far no member of the block can improve — and a
+// predecessor that does not improve can neither become the back pointer (strict >, overlap.cpp:303) nor trigger the
+// first break rule (:307).  A block that also lies entirely within maxJump on the sorted axis (second break rule,
+// :314) is therefore skipped without looking at its matches; 16 blocks are tested per step, one per lane.  Blocks that
+// fail the test, that contain the maxJump boundary, or that are older than the 16 summaries kept in registers are
+// evaluated exactly as in chainDpKernel.  Scores, back pointers and the cell count (skipped cells are counted: the
+// reference evaluates them) are identical.
+__global__ void __launch_bounds__(128) chainDpPrunedKernel(const Elem* __restrict__ hits, const PairInfo* __restrict__ pairs,
+                                                           const uint32_t* __restrict__ pairIds, const uint32_t* __restrict__ pairOrder, uint32_t nPairs,
+                                                           const uint32_t* __restrict__ pairFlags, OvParams P, int32_t* __restrict__ score,
+                                                           int32_t* __restrict__ back, Elem* __restrict__ ord, unsigned long long* __restrict__ cellCount) {
+    const uint32_t slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;   // half-warp index
+    const int sl = threadIdx.x & 15;
+    const bool upper = threadIdx.x & 16;
+    const int hs = threadIdx.x & 16;                                       // bit offset of this half in a ballot
+    const bool valid = slot < nPairs;
+    const uint32_t w = valid ? pairOrder[slot] : 0u;
+    PairInfo pi; pi.start = 0; pi.n = 0; pi.qi = 0; pi.extId = 0;
+    if (valid) pi = pairs[pairIds[w]];
+    const bool extSorted = valid && (pairFlags[w] & PAIR_EXTSORTED);
+    const int32_t n = (int32_t)pi.n;
+    const int32_t nMax = max(n, __shfl_xor_sync(0xffffffffu, n, 16));
+    const int k = P.k;
+    const Elem* h = hits + pi.start;
+    int32_t* sc = score + pi.start; int32_t* bk = back + pi.start; Elem* od = ord + pi.start;
+
+    int32_t nxC = 0, nxE = 0, pfC = 0, pfE = 0;
+    if (sl < n) { const Elem e = h[sl]; nxC = elemCur(e, extSorted); nxE = elemExt(e, extSorted); }
+    if (16 + sl < n) { const Elem e = h[16 + sl]; pfC = elemCur(e, extSorted); pfE = elemExt(e, extSorted); }
+    int32_t wC = nxC, wE = nxE, wS = 0;   // window registers: match j of the last 16 in sub-lane j % 16
+    int32_t sumS = 0, sumLo = 0, sumHi = 0, sumFirst = 0;   // summary of the completed block b with b % 16 == sl
+    if (sl == 0 && n > 0) { sc[0] = 0; bk[0] = -1; Elem t; t.key = 0x7fffffffULL; t.val = 0; t.aux = 0; od[0] = t; }
+    unsigned long long cells = 0;
+    for (int32_t i = 1; i < nMax; ++i) {
+        const bool act = i < n;
+        const int l0 = i & 15;
+        if (l0 == 0) {
+            nxC = pfC; nxE = pfE;
+            const int32_t nb = i + 16 + sl;
+            if (nb < n) { const Elem e = h[nb]; pfC = elemCur(e, extSorted); pfE = elemExt(e, extSorted); }
+        }
+        const int32_t curN = __shfl_sync(0xffffffffu, nxC, l0, 16), extN = __shfl_sync(0xffffffffu, nxE, l0, 16);
+        int32_t best = 0, bestId = 0;
+        bool stop = !act;
+
+        // exact evaluation of the 16 predecessors jb, jb-1, ... (those with j <= jLim) for the halves with `want`
+        auto evalStep = [&](const int32_t jb, const int32_t jLim, const bool fromRegs, const bool want) {
+            const int32_t j = jb - sl;
+            const bool in = want && j >= 0 && j <= jLim;
+            int32_t cj = 0, ej = 0, sj = 0;
+            if (fromRegs) {
+                const int src = j & 15;
+                cj = __shfl_sync(0xffffffffu, wC, src, 16); ej = __shfl_sync(0xffffffffu, wE, src, 16); sj = __shfl_sync(0xffffffffu, wS, src, 16);
+            } else if (in) { const Elem e = h[j]; cj = elemCur(e, extSorted); ej = elemExt(e, extSorted); sj = sc[j]; }
+            const int32_t dc = curN - cj, de = extN - ej;
+            const bool ok = in && 0 < dc && dc < P.maxJump && 0 < de && de < P.maxJump;
+            const int32_t jd = abs(dc - de);
+            const int32_t gap = jd > 100 ? 2 * jd : (jd >> 1);            // int32(float(LG_GAP|SM_GAP) * jd), :299
+            const int32_t s = ok ? sj + min(min(dc, de), k) - gap : INT32_MIN;
+            if (fromRegs) {
+                // fast path (the usual case on low-error reads): the nearest predecessor already improves and satisfies
+                // the first break rule, so the reference's scan ends after one step.  Taken when it holds for both halves.
+                const uint32_t fb = __ballot_sync(0xffffffffu, sl == 0 && (!act || (ok && jd == 0 && dc < k && s > 0)));
+                if (fb == 0x00010001u) {
+                    const int32_t s0 = __shfl_sync(0xffffffffu, s, 0, 16);
+                    if (act) { best = s0; bestId = i - 1; ++cells; stop = true; }
+                    return;
+                }
+            }
+            // second break rule (sorted-axis distance) first: nothing beyond its first lane is ever evaluated
+            const uint32_t far = (__ballot_sync(0xffffffffu, in && (extSorted ? de : dc) > P.maxJump) >> hs) & 0xffffu;
+            int stopLane = far ? (__ffs(far) - 1) : 15;
+            bool brk = far != 0;
+            uint32_t pot = (__ballot_sync(0xffffffffu, ok && jd == 0 && dc < k) >> hs) & ((2u << stopLane) - 1u);
+            while (__any_sync(0xffffffffu, pot != 0)) {
+                const int t = pot ? (__ffs(pot) - 1) : 0;
+                const int32_t prior = max(best, halfMax((pot && sl < t) ? s : INT32_MIN, upper));
+                const int32_t st = __shfl_sync(0xffffffffu, s, t, 16);
+                if (pot) {
+                    if (st > prior) { stopLane = t; brk = true; pot = 0; }
+                    else pot &= pot - 1;
+                }
+            }
+            const bool part = ok && sl <= stopLane;
+            const int32_t mx = halfMax(part ? s : INT32_MIN, upper);
+            const uint32_t wm = (__ballot_sync(0xffffffffu, part && s == mx) >> hs) & 0xffffu;
+            if (want) {
+                if (mx > best) { best = mx; bestId = jb - (__ffs(wm) - 1); }
+                cells += max(0, min(jb + 1, stopLane + 1) - max(0, jb - jLim));
+                if (brk) stop = true;
+            }
+        };
+
+        evalStep(i - 1, i - 1, true, !stop);
+        // look-back beyond the 16 most recent matches: block by block, skipping what provably cannot matter
+        int32_t jLim = i - 17;                 // highest predecessor not looked at yet
+        int32_t nb = jLim >= 0 ? jLim >> 4 : -1;   // its block
+        if (nb < 0) stop = true;
+        const int32_t cb = i >> 4;             // blocks cb-16 .. cb-1 have their summaries in registers
+        const int32_t diagN = curN - extN, sortedN = extSorted ? extN : curN;
+        while (__any_sync(0xffffffffu, !stop)) {
+            __syncwarp();   // orders sub-lane 0's score stores before the loads below
+            const bool live = !stop;
+            const int32_t B = nb - sl;
+            const int src = B & 15;
+            const int32_t bS = __shfl_sync(0xffffffffu, sumS, src, 16), bLo = __shfl_sync(0xffffffffu, sumLo, src, 16);
+            const int32_t bHi = __shfl_sync(0xffffffffu, sumHi, src, 16), bFirst = __shfl_sync(0xffffffffu, sumFirst, src, 16);
+            const int32_t jdMin = diagN < bLo ? bLo - diagN : (diagN > bHi ? diagN - bHi : 0);
+            const int32_t gapMin = jdMin > 100 ? 2 * jdMin : (jdMin >> 1);
+            const bool skippable = live && B >= 0 && B >= cb - 16 && bS + k - gapMin <= best && sortedN - bFirst <= P.maxJump;
+            const uint32_t keep = (__ballot_sync(0xffffffffu, !skippable) >> hs) & 0xffffu;
+            const int nskip = keep ? __ffs(keep) - 1 : 16;
+            if (live && nskip > 0) {
+                cells += (unsigned long long)(jLim - 16 * nb + 1) + 16ULL * (nskip - 1);
+                nb -= nskip;
+                jLim = 16 * nb + 15;
+                if (nb < 0) stop = true;
+            }
+            const bool evalWant = live && !stop && nskip < 16;
+            if (__any_sync(0xffffffffu, evalWant)) evalStep(16 * nb + 15, jLim, false, evalWant);
+            if (evalWant) {
+                --nb; jLim = 16 * nb + 15;
+                if (nb < 0) stop = true;
+            }
+        }
+        if (act) {
+            const int32_t sci = max(best, k);
+            if (sl == l0) { wC = curN; wE = extN; wS = sci; }   // match i replaces match i-16 in the window
+            if (sl == 0) {
+                sc[i] = sci; bk[i] = best > k ? bestId : -1;
+                Elem t; t.key = (unsigned long long)(0x7fffffff - sci); t.val = (unsigned int)i; t.aux = 0; od[i] = t;   // (c) input of the score sort
+            }
+        }
+        if (l0 == 15) {   // block i >> 4 is complete: its summary goes to sub-lane (i >> 4) % 16
+            const int32_t dg = wC - wE;
+            const int32_t mS = halfMax(wS, upper), mHi = halfMax(dg, upper), mLo = -halfMax(-dg, upper);
+            const int32_t fst = __shfl_sync(0xffffffffu, extSorted ? wE : wC, 0, 16);
+            if (sl == (cb & 15)) { sumS = mS; sumLo = mLo; sumHi = mHi; sumFirst = fst; }
+        }
+    }
+    if (sl == 0 && cells) atomicAdd(cellCount, cells);
+}
+
 // order in which chainDpKernel visits the pairs: decreasing number of matches
 __global__ void __launch_bounds__(256) pairSizeKeyKernel(const PairInfo* __restrict__ pairs, const uint32_t* __restrict__ pairIds, uint32_t nPairs,
                                                          uint32_t* __restrict__ keys, uint32_t* __restrict__ idx) {
@@ -704,12 +874,18 @@ struct SortWorkspace {
 };
 
 static void sortSegments(fg_ctx* ctx, Elem* arr, const Seg* dSegs, uint32_t* dCounters, uint32_t maxSegs, SortWorkspace& ws,
-                         const char* topName, const char* smallName) {
+                         const char* topName, const char* smallName, SortCfg cfg) {
     static bool attrSet = false;
-    const uint32_t smallN = (uint32_t)sortSmallN();
-    const int smemBytes = 4 * (int)smallN * (int)sizeof(Elem);
+    const int variant = cfg.variant;
+    const uint32_t smallN = (uint32_t)cfg.smallN;
+    const int smemBytes = 4 * ((int)smallN * ((int)sizeof(Elem) + (variant ? 4 : 0)) + (variant > 1 ? ((int)smallN / 32 + 2) * 4 : 0));
+    auto smallKernel = variant == 0 ? sortSmallKernel<0> : variant == 1 ? sortSmallKernel<1> : variant == 2 ? sortSmallKernel<2> : sortSmallKernel<3>;
     if (!attrSet) {
-        FG_CUDA(cudaFuncSetAttribute(sortSmallKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smemBytes));
+        const int maxSmem = 4 * (SORT_SMALL_MAX * ((int)sizeof(Elem) + 4) + (SORT_SMALL_MAX / 32 + 2) * 4);
+        FG_CUDA(cudaFuncSetAttribute(sortSmallKernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
+        FG_CUDA(cudaFuncSetAttribute(sortSmallKernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
+        FG_CUDA(cudaFuncSetAttribute(sortSmallKernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
+        FG_CUDA(cudaFuncSetAttribute(sortSmallKernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
         attrSet = true;
     }
     const int blocksPerSm = std::max(1, std::min(8, (int)((220 * 1024) / (smemBytes + 1024))));
@@ -746,7 +922,7 @@ static void sortSegments(fg_ctx* ctx, Elem* arr, const Seg* dSegs, uint32_t* dCo
     }
     {
         PhaseTimer pt(ctx, smallName);
-        sortSmallKernel<<<148 * blocksPerSm, 128, smemBytes, ctx->stream>>>(arr, ws.small.p, dCounters + 1, ws.capSmall, dCounters + 2, smallN);
+        smallKernel<<<148 * blocksPerSm, 128, smemBytes, ctx->stream>>>(arr, ws.small.p, dCounters + 1, ws.capSmall, dCounters + 2, smallN);
         checkLaunch(ctx, "sortSmallKernel");
     }
 }
@@ -769,7 +945,7 @@ void debugWarpSort(fg_ctx* ctx, uint64_t* keys, uint32_t* vals, const uint64_t* 
     FG_CUDA(cudaMemcpyAsync(d.p, h.data(), n * sizeof(Elem), cudaMemcpyHostToDevice, ctx->stream));
     FG_CUDA(cudaMemcpyAsync(dSegs.p, hs.data(), nSegs * sizeof(Seg), cudaMemcpyHostToDevice, ctx->stream));
     FG_CUDA(cudaMemcpyAsync(counters.p, hc, sizeof hc, cudaMemcpyHostToDevice, ctx->stream));
-    sortSegments(ctx, d.p, dSegs.p, counters.p, nSegs, ws, "dbg_sort_top", "dbg_sort_small");
+    sortSegments(ctx, d.p, dSegs.p, counters.p, nSegs, ws, "dbg_sort_top", "dbg_sort_small", envInt("FG_DEBUG_SORT_PAIRS", 0, 0, 1) ? sortCfgPairs() : sortCfgHits());
     FG_CUDA(cudaMemcpyAsync(h.data(), d.p, n * sizeof(Elem), cudaMemcpyDeviceToHost, ctx->stream));
     FG_CUDA(cudaMemcpyAsync(hc, counters.p, sizeof hc, cudaMemcpyDeviceToHost, ctx->stream));
     FG_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -909,7 +1085,7 @@ static void overlapsChunk(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, ui
         }
         querySegsKernel<<<(nq + 255) / 256, 256, 0, ctx->stream>>>(dQHitOff.p, qa, nq, hitBase, segsQ.p);
         checkLaunch(ctx, "querySegsKernel");
-        sortSegments(ctx, hits.p, segsQ.p, counters.p, nq, ws, "hit_sort_top", "hit_sort_small");
+        sortSegments(ctx, hits.p, segsQ.p, counters.p, nq, ws, "hit_sort_top", "hit_sort_small", sortCfgHits());
         uint32_t G = 0, C = 0, Pn = 0;
         DevBuf<PairInfo> pairInfo;
         DevBuf<uint8_t> candFlag, passFlag;
@@ -946,7 +1122,7 @@ static void overlapsChunk(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, ui
                                                                      extSegs.p, counters.p + 8, allSegs.p);
                 checkLaunch(ctx, "pairPrepKernel");
             }
-            sortSegments(ctx, hits.p, extSegs.p, counters.p + 8, Pn, ws, "chain_extsort_top", "chain_extsort_small");
+            sortSegments(ctx, hits.p, extSegs.p, counters.p + 8, Pn, ws, "chain_extsort_top", "chain_extsort_small", sortCfgPairs());
             {
                 PhaseTimer pt(ctx, "chain_dp");
                 // visit the pairs by decreasing size: two pairs share a warp, 8 a block
@@ -959,12 +1135,14 @@ static void overlapsChunk(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, ui
                 DevBuf<char> tmpS(tb);
                 FG_CUDA(cub::DeviceRadixSort::SortPairs(tmpS.p, tb, dk, dv, (int)Pn, 0, 32, ctx->stream));
                 ctx->launches += 5;
-                chainDpKernel<<<(Pn + 7) / 8, 128, 0, ctx->stream>>>(hits.p, pairInfo.p, pairIds.p, dv.Current(), Pn, pairFlags.p, P, score.p,
-                                                                    back.p, ord.p, dCells.p);   // whole warps: no early exit inside
+                static const bool dpPrune = envInt("FG_DP_PRUNE", 0, 0, 1) != 0;
+                auto dp = dpPrune ? chainDpPrunedKernel : chainDpKernel;
+                dp<<<(Pn + 7) / 8, 128, 0, ctx->stream>>>(hits.p, pairInfo.p, pairIds.p, dv.Current(), Pn, pairFlags.p, P, score.p, back.p, ord.p,
+                                                         dCells.p);   // whole warps: no early exit inside
                 checkLaunch(ctx, "chainDpKernel");
             }
             FG_CUDA(cudaMemcpyAsync(counters.p + 16, &Pn, 4, cudaMemcpyHostToDevice, ctx->stream));
-            sortSegments(ctx, ord.p, allSegs.p, counters.p + 16, Pn, ws, "chain_ordsort_top", "chain_ordsort_small");
+            sortSegments(ctx, ord.p, allSegs.p, counters.p + 16, Pn, ws, "chain_ordsort_top", "chain_ordsort_small", sortCfgPairs());
             {
                 PhaseTimer pt(ctx, "chain_walk");
                 static bool walkAttr = false;
@@ -981,7 +1159,7 @@ static void overlapsChunk(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, ui
                 FG_CUDA(cudaStreamSynchronize(ctx->stream));
                 if (hc[1] > taskCap || hc[9] > taskCap || hc[17] > taskCap) throw Error(FG_ERR_INTERNAL, "sort task list overflow");
             }
-            PhaseTimer pt(ctx, "d2h");
+            HostTimer pt(ctx, "host_results");   // gather of the kept overlaps, device -> pinned host copies (includes "edit")
             cub::TransformInputIterator<uint64_t, CastU64, const uint32_t*> it64(nKept.p, CastU64());
             exclusiveScanToPlus1(ctx, it64, outOff.p, Pn);
             uint64_t nOut = 0; unsigned long long cells = 0;
@@ -1027,7 +1205,7 @@ static void overlapsChunk(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, ui
                 if (prm.nucl_alignment) {   // overlap.cpp:463-468
                     if (nOut >= (1ULL << 31)) throw Error(FG_ERR_ARG, "too many overlaps in one sub-batch");
                     PhaseTimer pe(ctx, "edit");
-                    editDistances(ctx, dOut.p, dst, (uint32_t)nOut, prm.use_hpc != 0, qSeq, qWordOff, qLen);
+                    editDistances(ctx, dOut.p, dst, (uint32_t)nOut, prm.use_hpc != 0, !P.sameSet);
                     FG_CUDA(cudaMemcpyAsync(dst, dOut.p, nOut * sizeof(fg_overlap), cudaMemcpyDeviceToHost, ctx->stream));
                     FG_CUDA(cudaStreamSynchronize(ctx->stream));
                 }

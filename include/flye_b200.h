@@ -154,6 +154,8 @@ int fg_comm_set_shard(fg_ctx* ctx, uint32_t first_read, uint32_t n_reads);
 
 /* ---- test hook: the std::sort-exact warp introsort on caller data (segments sorted independently) ---- */
 int fg_debug_edit_distance(fg_ctx* ctx, const uint8_t* a, int n, const uint8_t* b, int m, int* distance);
+/* the same with either string read as its reverse complement (base c -> 3 - c), as the kernel reads a reverse strand */
+int fg_debug_edit_distance_rc(fg_ctx* ctx, const uint8_t* a, int n, int rc_a, const uint8_t* b, int m, int rc_b, int* distance);
 int fg_debug_warp_sort(fg_ctx* ctx, uint64_t* keys, uint32_t* vals, const uint64_t* seg_offsets, uint32_t n_segments);
 
 #ifdef __cplusplus

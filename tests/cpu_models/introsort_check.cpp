@@ -14,6 +14,7 @@ struct VecSink {
     void operator()(long f, long l, int d) { tasks.push_back({f, l, d}); }
 };
 static long g_small = 0;   // > 0: two-level mode (top pass hands ranges <= g_small to a second pass)
+static int g_table = 0;     // second pass / one-pass sort uses the rank-table partition of the shared-memory kernel
 
 static bool checkOne(std::vector<fg::Elem> a, const char* what) {
     std::vector<fg::Elem> ref = a;
@@ -27,12 +28,27 @@ static bool checkOne(std::vector<fg::Elem> a, const char* what) {
             auto& T = sink.tasks[t];
             std::vector<fg::Elem> tmp(a.begin() + T.f, a.begin() + T.l);
             fg::NoSink none;
-            fg::warpIntrosortRange(tmp.data(), 0, (int)tmp.size(), T.d, 0, none, tab);
+            if (g_table) {
+                std::vector<unsigned short> t16(2 * tmp.size() + 2);
+                std::vector<uint32_t> bits(tmp.size() / 32 + 3);
+                if (g_table == 1) fg::warpIntrosortRange<true>(tmp.data(), 0, (int)tmp.size(), T.d, 0, none, (unsigned char*)t16.data(), false, (int)tmp.size());
+                else if (g_table == 2) fg::warpIntrosortSmem<16>(tmp.data(), (int)tmp.size(), T.d, t16.data(), t16.data() + tmp.size(), bits.data());
+                else fg::warpIntrosortSmem<32>(tmp.data(), (int)tmp.size(), T.d, t16.data(), t16.data() + tmp.size(), bits.data());
+            } else
+                fg::warpIntrosortRange(tmp.data(), 0, (int)tmp.size(), T.d, 0, none, tab);
             std::copy(tmp.begin(), tmp.end(), a.begin() + T.f);
         }
     } else if (g_small < 0)
         fg::seqIntrosort(a.data(), (long)a.size());
-    else
+    else if (g_table && a.size() < 65536) {
+        fg::NoSink none;
+        std::vector<unsigned short> t16(2 * a.size() + 2);
+        std::vector<uint32_t> bits(a.size() / 32 + 3);
+        const int d0 = fg::introsortDepth((long)a.size());
+        if (g_table == 1) fg::warpIntrosortRange<true>(a.data(), 0, (int)a.size(), d0, 0, none, (unsigned char*)t16.data(), false, (int)a.size());
+        else if (g_table == 2) fg::warpIntrosortSmem<16>(a.data(), (int)a.size(), d0, t16.data(), t16.data() + a.size(), bits.data());
+        else fg::warpIntrosortSmem<32>(a.data(), (int)a.size(), d0, t16.data(), t16.data() + a.size(), bits.data());
+    } else
         fg::warpIntrosort(a.data(), (int)a.size(), tab);
     for (size_t i = 0; i < a.size(); ++i)
         if (a[i].key != ref[i].key || a[i].val != ref[i].val) {
@@ -56,6 +72,7 @@ int main(int argc, char** argv) {
     int trials = argc > 1 ? atoi(argv[1]) : 3000;
     unsigned seed = argc > 2 ? atoi(argv[2]) : 12345;
     g_small = argc > 3 ? atol(argv[3]) : 0;
+    g_table = argc > 4 ? atoi(argv[4]) : 0;   // 1: table partition, 2/3: warpIntrosortSmem<16/32>
     std::mt19937_64 rng(seed);
     size_t arrays = 0, elements = 0;
     auto mk = [&](size_t n, int mode, unsigned long long distinct) {

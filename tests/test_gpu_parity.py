@@ -116,7 +116,8 @@ def test_device_edit_distance_exact(engine):
     """wavefront edit distance == textbook DP (global, unit costs), incl. empty / unequal / unrelated inputs"""
     rng = np.random.default_rng(11)
     cases = [(0, 0, 0.0), (0, 7, 0.0), (9, 0, 0.0), (1, 1, 0.5), (50, 50, 0.0), (300, 300, 0.02), (1500, 1500, 0.01),
-             (1200, 900, 0.3), (700, 700, 1.0), (2000, 2000, 0.1), (33, 64, 0.2)]
+             (1200, 900, 0.3), (700, 700, 1.0), (2000, 2000, 0.1), (33, 64, 0.2), (31, 32, 0.1), (64, 64, 0.0),
+             (4000, 4100, 0.002), (1025, 1024, 0.0)]
     for n, m, err in cases:
         a = rng.integers(0, 4, n).astype(np.uint8)
         if err >= 1.0:
@@ -131,7 +132,14 @@ def test_device_edit_distance_exact(engine):
                     b.append(rng.integers(0, 4)); b.append(c); continue
                 b.append((c + 1) % 4 if u < err else c)
             b = np.array(b, dtype=np.uint8) if len(b) else np.zeros(0, np.uint8)
-        assert engine.debug_edit_distance(a, b) == _edit_distance_np(a, b), (n, m, err)
+        want = _edit_distance_np(a, b)
+        assert engine.debug_edit_distance(a, b) == want, (n, m, err)
+        # strand views: d(rc(a), rc(b)) computed through the reverse-complement fetch path equals d(a', b') of the
+        # explicitly reverse-complemented strings
+        ra, rb = (3 - a[::-1]).astype(np.uint8), (3 - b[::-1]).astype(np.uint8)
+        assert engine.debug_edit_distance_rc(ra, True, rb, True) == want, (n, m, err, "rc/rc")
+        assert engine.debug_edit_distance_rc(ra, True, b, False) == want, (n, m, err, "rc/fwd")
+        assert engine.debug_edit_distance_rc(a, False, rb, True) == want, (n, m, err, "fwd/rc")
 
 
 def test_hifi_small_full_parity(engine, tmp_path):

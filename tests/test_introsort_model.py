@@ -18,3 +18,13 @@ def test_warp_introsort_host_build_equals_std_sort(built, small):
     assert r.stdout.startswith("OK")
     if small >= 0:
         assert "heapsorts=0" not in r.stdout   # the depth-limit fallback was exercised
+
+
+@pytest.mark.parametrize("variant", [1, 2, 3])
+@pytest.mark.parametrize("small", [0, 512, 64])
+def test_shared_memory_variants_equal_std_sort(built, small, variant):
+    """the shared-memory kernel's variants: rank-table partition (1), + stable leaf pass by ranking with 16- (2) or
+    32-element (3) warp-partition threshold"""
+    r = subprocess.run([BIN, "100", str(11 + small + variant), str(small), str(variant)], stdout=subprocess.PIPE, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout
+    assert r.stdout.startswith("OK")
