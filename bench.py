@@ -357,7 +357,9 @@ def main():
             "phases_ms": {p: round(v, 3) for p, v in resident_phases.items()},
             "api_wall_ms": {p: round(v, 2) for p, v in resident_wall.items()}, "e2e_api_wall_ms": {p: round(v, 2) for p, v in e2e_wall.items()},
             "work": {"kmer_hits": int(M), "target_groups": int(stats.get("n_pairs", 0)), "dp_pairs": int(stats.get("n_dp_pairs", 0)),
-                     "dp_cells": int(stats.get("n_dp_cells", 0)), "overlaps": int(O)}}
+                     "dp_cells": int(stats.get("n_dp_cells", 0)), "overlaps": int(O),
+                     "queries_with_hit_ties": int(resident_phases.get("tied_queries", 0)),
+                     "pairs_score_order_presorted": int(resident_phases.get("presorted_pairs", 0))}}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
             _, _, _, cb = run_reference(argparse.Namespace(warmup=0, steps=1), wl, reads_path)

@@ -111,12 +111,20 @@ __global__ void gatherQueryHitOffKernel(const uint64_t* __restrict__ hitOff, con
 // Q3: expansion.  One CTA per query tile; the tile's slot offsets are staged in shared memory and every
 // output record finds its slot with a shared-memory binary search, so global writes are coalesced.
 // ------------------------------------------------------------------------------------------------
+// SOA = false: Elem records (key = extId << 32 | curPos, val = extPos) into `hits`; with `onlyTied` set, only the tiles of
+//               queries whose flag is set are written (the re-expansion of the queries that need the exact sort).
+// SOA = true:  input of the stable radix sort of the tie-free fast path: keys[h] = (q - qFirst) << (32 + idBits) | extId << 32 | curPos,
+//               vals[h] = extPos.
+template <bool SOA>
 __global__ void __launch_bounds__(256) expandKernel(const uint32_t* __restrict__ len, const uint32_t* __restrict__ qlen, const uint2* __restrict__ entries,
                                                     const uint32_t* __restrict__ qIds, const uint64_t* __restrict__ qSlotOff,
                                                     const uint2* __restrict__ qTiles, int k, const uint64_t* __restrict__ hitOff,
-                                                    const uint64_t* __restrict__ slotInfo, uint64_t hitBase, Elem* __restrict__ hits) {
+                                                    const uint64_t* __restrict__ slotInfo, uint64_t hitBase, Elem* __restrict__ hits,
+                                                    unsigned long long* __restrict__ keys, uint32_t* __restrict__ vals, uint32_t qFirst, int idBits,
+                                                    const uint8_t* __restrict__ onlyTied) {
     __shared__ uint32_t rel[QTILE + 1];
     const uint2 t = qTiles[blockIdx.x];
+    if (!SOA && onlyTied && !onlyTied[t.x - qFirst]) return;
     const uint32_t id = qIds[t.x], r = id >> 1;
     const bool strand = id & 1;
     const uint32_t L = qlen[r], n = L - k;
@@ -142,8 +150,29 @@ __global__ void __launch_bounds__(256) expandKernel(const uint32_t* __restrict__
         }
         uint32_t extId = e.x; int32_t extPos = (int32_t)e.y;
         if (info & INFO_QRC) { extPos = (int32_t)len[extId >> 1] - extPos - k; extId ^= 1u; }   // vertex_index.h:166-173
-        Elem o; o.key = ((unsigned long long)extId << 32) | p; o.val = (unsigned int)extPos; o.aux = 0;
-        out[h] = o;
+        if (SOA) {
+            keys[(h0 - hitBase) + h] = ((unsigned long long)(t.x - qFirst) << (32 + idBits)) | ((unsigned long long)extId << 32) | p;
+            vals[(h0 - hitBase) + h] = (uint32_t)extPos;
+        } else {
+            Elem o; o.key = ((unsigned long long)extId << 32) | p; o.val = (unsigned int)extPos; o.aux = 0;
+            out[h] = o;
+        }
+    }
+}
+
+// Tie-free fast path of the hit sort (overlap.cpp:201-204).  std::sort's result is the unique sorted sequence whenever
+// no two elements compare equal, and the expansion emits a query's hits by ascending curPos — so for a query without an
+// (extId, curPos) tie a STABLE sort by extId alone reproduces libstdc++'s output.  This kernel turns the radix-sorted
+// (key, extPos) pairs back into Elem records and flags every query that does contain a tie (two adjacent equal keys):
+// those queries are expanded again and go through the exact introsort emulation.
+__global__ void __launch_bounds__(256) rebuildHitsKernel(const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ vals, uint64_t M,
+                                                         int idBits, Elem* __restrict__ hits, uint8_t* __restrict__ qTie) {
+    const unsigned long long idMask = (1ULL << idBits) - 1ULL;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < M; i += (uint64_t)gridDim.x * blockDim.x) {
+        const unsigned long long kk = keys[i];
+        Elem o; o.key = (((kk >> 32) & idMask) << 32) | (kk & 0xffffffffULL); o.val = vals[i]; o.aux = 0;
+        hits[i] = o;
+        if (i + 1 < M && keys[i + 1] == kk) qTie[kk >> (32 + idBits)] = 1;
     }
 }
 
@@ -277,10 +306,15 @@ __global__ void __launch_bounds__(128) sortSmallKernel(Elem* __restrict__ arr, c
     }
 }
 
-__global__ void querySegsKernel(const uint64_t* __restrict__ qHitOff, uint32_t qFirst, uint32_t nQ, uint64_t hitBase, Seg* __restrict__ segs) {
+__global__ void querySegsKernel(const uint64_t* __restrict__ qHitOff, uint32_t qFirst, uint32_t nQ, uint64_t hitBase, Seg* __restrict__ segs,
+                                const uint8_t* __restrict__ onlyTied, uint32_t* __restrict__ nTied) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nQ) return;
     Seg s; s.start = (uint32_t)(qHitOff[qFirst + i] - hitBase); s.n = (uint32_t)(qHitOff[qFirst + i + 1] - qHitOff[qFirst + i]);
+    if (onlyTied) {
+        if (!onlyTied[i]) s.n = 0;   // already in std::sort's order (segments of < 2 elements are never seeded)
+        else atomicAdd(nTied, 1u);
+    }
     segs[i] = s;
 }
 
@@ -397,19 +431,33 @@ __global__ void __launch_bounds__(256) pairPrepKernel(Elem* __restrict__ hits, c
     const PairInfo pi = pairs[pairIds[w]];
     const int32_t curLen = (int32_t)qlen[qIds[pi.qi] >> 1], extLen = (int32_t)len[pi.extId >> 1];
     const bool extSorted = extLen > curLen;
+    Seg sg; sg.start = pi.start; sg.n = pi.n;
     if (lane == 0) {
         pairFlags[w] = extSorted ? PAIR_EXTSORTED : 0u;
-        Seg sg; sg.start = pi.start; sg.n = pi.n;
         allSegs[w] = sg;
-        if (extSorted) extSegs[atomicAdd(nExtSegs, 1u)] = sg;
     }
     if (extSorted) {
+        // A pair whose extPos values already increase strictly along the curPos order is in the unique sorted order of
+        // distinct keys, i.e. in std::sort's output order: no re-sort (the usual case for a clean overlap).
         Elem* h = hits + pi.start;
-        for (uint32_t i = lane; i < pi.n; i += 32) {
-            const Elem e = h[i];
-            Elem t; t.key = (unsigned long long)e.val; t.val = (unsigned int)e.key; t.aux = 0;
-            h[i] = t;
+        bool sorted = true;
+        uint32_t carry = 0;
+        for (uint32_t i0 = 0; i0 < pi.n; i0 += 32) {
+            const uint32_t i = i0 + lane;
+            uint32_t x = 0xffffffffu;
+            if (i < pi.n) {
+                const Elem e = h[i];
+                Elem t; t.key = (unsigned long long)e.val; t.val = (unsigned int)e.key; t.aux = 0;
+                h[i] = t;
+                x = e.val;
+            }
+            uint32_t px = __shfl_up_sync(0xffffffffu, x, 1);
+            if (lane == 0) px = carry;
+            if (i < pi.n && i > 0 && !(px < x)) sorted = false;
+            carry = __shfl_sync(0xffffffffu, x, 31);
         }
+        sorted = __all_sync(0xffffffffu, sorted);
+        if (lane == 0 && !sorted) extSegs[atomicAdd(nExtSegs, 1u)] = sg;
     }
 }
 
@@ -677,6 +725,227 @@ __global__ void __launch_bounds__(128) chainDpPrunedKernel(const Elem* __restric
         }
     }
     if (sl == 0 && cells) atomicAdd(cellCount, cells);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Run-compressed chaining DP (default).  A RUN is a maximal sequence of consecutive matches i-1 -> i of a pair with
+// 0 < dc == de < k (same diagonal, closer than k).  For such an i the reference's scan (overlap.cpp:284-316) looks at
+// j = i-1 only: it is valid, scores score[i-1] + dc > 0, and satisfies the first break rule (:307) — so
+//     score[i] = score[i-1] + dc,  back[i] = i-1                      for every non-first match of a run (i >= 2),
+// and scores inside a run are score[a] + cur[i] - cur[a].  Only the first match of every run (its HEAD) needs a scan, and
+// the scan can go run by run instead of match by match: walking a run from its last match towards its first, dc and de
+// grow by the same amount the score shrinks, so score[j] + min(dc, de, k) never increases; the first VALID match of the
+// run is the only one that can pass the strict `>` of :303, and with it the only one that can trigger the break of :307.
+// The second break rule (:314-315) depends on the sorted-axis coordinate, which is monotone over the whole list, so it
+// cuts the scan at a run boundary or makes the rest of a run invalid.  Scores and back pointers are identical to the
+// match-by-match scan; the work drops from O(matches within maxJump) to O(runs within maxJump) per head and to O(1)
+// per other match (on low-error reads a run holds ~30 matches).
+//   chainRunsKernel   finds the runs of every pair (one warp per pair), writes their records and the run of every match
+//   chainRunDpKernel  the scan of the heads: half-warp per pair, 16 runs per step, the 16 most recent runs in registers
+//   chainFillKernel   scores / back pointers / score-sort input of all matches from the run records
+// ------------------------------------------------------------------------------------------------
+struct __align__(16) Run { int32_t a, curA, extA, backA; int32_t b, curB, extB, scoreB; };   // [a, b] = matches of the run
+static_assert(sizeof(Run) == sizeof(Cand), "run records live in the candidate array until the chain walk");
+
+__global__ void __launch_bounds__(256) chainRunsKernel(const Elem* __restrict__ hits, const PairInfo* __restrict__ pairs, const uint32_t* __restrict__ pairIds,
+                                                       uint32_t nPairs, const uint32_t* __restrict__ pairFlags, int k, Run* __restrict__ runs,
+                                                       int32_t* __restrict__ runOf, uint32_t* __restrict__ nRuns) {
+    const uint32_t w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (w >= nPairs) return;
+    const int lane = threadIdx.x & 31;
+    const PairInfo pi = pairs[pairIds[w]];
+    const bool extSorted = pairFlags[w] & PAIR_EXTSORTED;
+    const int32_t n = (int32_t)pi.n;
+    const Elem* h = hits + pi.start;
+    Run* rn = runs + pi.start;
+    int32_t* ro = runOf + pi.start;
+    int32_t base = 0, carryC = 0, carryE = 0;
+    for (int32_t i0 = 0; i0 < n; i0 += 32) {
+        const int32_t i = i0 + lane;
+        int32_t c = 0, x = 0;
+        if (i < n) { const Elem e = h[i]; c = elemCur(e, extSorted); x = elemExt(e, extSorted); }
+        int32_t pc = __shfl_up_sync(0xffffffffu, c, 1), px = __shfl_up_sync(0xffffffffu, x, 1);
+        if (lane == 0) { pc = carryC; px = carryE; }
+        const int32_t dc = c - pc, de = x - px;
+        // match 0 is its own run (score 0, :323); match 1 always starts one (its predecessor's score is not >= k)
+        const bool head = i < n && (i <= 1 || !(dc == de && 0 < dc && dc < k));
+        const uint32_t m = __ballot_sync(0xffffffffu, head);
+        const int32_t r = base + __popc(m & (0xffffffffu >> (31 - lane))) - 1;
+        if (i < n) ro[i] = r;
+        if (head) {
+            rn[r].a = i; rn[r].curA = c; rn[r].extA = x;
+            if (i > 0) { rn[r - 1].b = i - 1; rn[r - 1].curB = pc; rn[r - 1].extB = px; }
+        }
+        if (i == n - 1) { rn[r].b = i; rn[r].curB = c; rn[r].extB = x; }
+        base += __popc(m);
+        carryC = __shfl_sync(0xffffffffu, c, 31); carryE = __shfl_sync(0xffffffffu, x, 31);
+    }
+    if (lane == 0) nRuns[w] = (uint32_t)base;
+}
+
+__global__ void __launch_bounds__(128) chainRunDpKernel(const Elem* __restrict__ hits, const PairInfo* __restrict__ pairs, const uint32_t* __restrict__ pairIds,
+                                                        const uint32_t* __restrict__ pairOrder, uint32_t nPairs, const uint32_t* __restrict__ pairFlags,
+                                                        const uint32_t* __restrict__ nRuns, OvParams P, Run* runs, unsigned long long* __restrict__ cellCount) {
+    const uint32_t slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;   // half-warp index
+    const int sl = threadIdx.x & 15;
+    const bool upper = threadIdx.x & 16;
+    const int hs = threadIdx.x & 16;                                       // bit offset of this half in a ballot
+    const bool valid = slot < nPairs;
+    const uint32_t w = valid ? pairOrder[slot] : 0u;
+    PairInfo pi; pi.start = 0; pi.n = 0; pi.qi = 0; pi.extId = 0;
+    if (valid) pi = pairs[pairIds[w]];
+    const bool extSorted = valid && (pairFlags[w] & PAIR_EXTSORTED);
+    const int32_t R = valid ? (int32_t)nRuns[w] : 0;
+    const int32_t Rmax = max(R, __shfl_xor_sync(0xffffffffu, R, 16));
+    const int k = P.k;
+    const Elem* h = hits + pi.start;
+    Run* rn = runs + pi.start;
+    const int4* rn4 = reinterpret_cast<const int4*>(rn);   // [2r] = {a, curA, extA, backA}, [2r+1] = {b, curB, extB, scoreB}
+
+    // records of the runs [16b, 16b+16): nx* = current block, pf* = next block (loaded a block ahead; scoreB not used from these)
+    int4 nxH = make_int4(0, 0, 0, 0), nxT = nxH, pfH = nxH, pfT = nxH;
+    if (sl < R) { nxH = rn4[2 * sl]; nxT = rn4[2 * sl + 1]; }
+    if (16 + sl < R) { pfH = rn4[2 * (16 + sl)]; pfT = rn4[2 * (16 + sl) + 1]; }
+    // window registers: last match of run q (index, cur, ext, score) in sub-lane q % 16; run 0 = match 0 with score 0
+    int32_t wB = nxT.x, wC = nxT.y, wE = nxT.z, wS = 0;
+    if (sl == 0 && R > 0) { rn[0].scoreB = 0; rn[0].backA = -1; }
+    unsigned long long cells = 0;
+    for (int32_t r = 1; r < Rmax; ++r) {
+        const bool act = r < R;
+        const int l0 = r & 15;
+        if (l0 == 0) {
+            nxH = pfH; nxT = pfT;
+            const int32_t nb = r + 16 + sl;
+            if (nb < R) { pfH = rn4[2 * nb]; pfT = rn4[2 * nb + 1]; }
+        }
+        const int32_t curN = __shfl_sync(0xffffffffu, nxH.y, l0, 16), extN = __shfl_sync(0xffffffffu, nxH.z, l0, 16);
+        const int32_t sortedN = extSorted ? extN : curN;
+        int32_t best = 0, bestId = 0;
+        bool stop = !act;
+        for (int32_t rb = r - 1;; rb -= 16) {
+            const bool live = !stop && rb >= 0;                            // uniform inside a half
+            if (!__any_sync(0xffffffffu, live)) break;
+            const int32_t q = rb - sl;
+            const bool in = live && q >= 0;
+            int32_t jB, cj, ej, sj;
+            if (rb == r - 1) {   // the 16 most recent runs: registers
+                const int src = q & 15;
+                jB = __shfl_sync(0xffffffffu, wB, src, 16); cj = __shfl_sync(0xffffffffu, wC, src, 16);
+                ej = __shfl_sync(0xffffffffu, wE, src, 16); sj = __shfl_sync(0xffffffffu, wS, src, 16);
+            } else {
+                if (rb == r - 17) __syncwarp();   // order sub-lane 0's score stores before these loads
+                jB = 0; cj = 0; ej = 0; sj = 0;
+                if (in) { const int4 t = rn4[2 * q + 1]; jB = t.x; cj = t.y; ej = t.z; sj = t.w; }
+            }
+            const int32_t sortedB = extSorted ? ej : cj;   // the first match of this run the reference's scan visits
+            bool has = in;
+            if (in && !(cj < curN && ej < extN)) {
+                // the run's last match is not a predecessor of the head: its first valid match is the last one with
+                // cur < curN and ext < extN (ext = cur - diagonal inside a run)
+                const int32_t a = rn[q].a, cA = rn[q].curA;
+                const int32_t dg = cj - ej;
+                const int32_t X = min(curN, extN + dg);
+                if (a == jB || !(cA < X)) has = false;
+                else {
+                    int32_t lo = a, hi = jB, cLo = cA;   // cur[lo] < X <= cur[hi]
+                    while (hi - lo > 1) {
+                        const int32_t mid = (lo + hi) >> 1;
+                        const int32_t cm = elemCur(h[mid], extSorted);
+                        if (cm < X) { lo = mid; cLo = cm; } else hi = mid;
+                    }
+                    sj -= cj - cLo; cj = cLo; ej = cLo - dg; jB = lo;
+                }
+            }
+            const int32_t dc = curN - cj, de = extN - ej;
+            const bool ok = has && dc < P.maxJump && de < P.maxJump;   // dc > 0 and de > 0 by construction
+            const int32_t jd = abs(dc - de);
+            const int32_t gap = jd > 100 ? 2 * jd : (jd >> 1);            // int32(float(LG_GAP|SM_GAP) * jd), :299
+            const int32_t s = ok ? sj + min(min(dc, de), k) - gap : INT32_MIN;
+            // second break rule (sorted-axis distance): the scan ends at the first run whose last match is beyond maxJump
+            const uint32_t far = (__ballot_sync(0xffffffffu, in && sortedN - sortedB > P.maxJump) >> hs) & 0xffffu;
+            int stopLane = far ? (__ffs(far) - 1) : 15;
+            bool brk = far != 0;
+            uint32_t pot = (__ballot_sync(0xffffffffu, ok && jd == 0 && dc < k) >> hs) & ((2u << stopLane) - 1u);
+            while (__any_sync(0xffffffffu, pot != 0)) {
+                const int t = pot ? (__ffs(pot) - 1) : 0;
+                const int32_t prior = max(best, halfMax((pot && sl < t) ? s : INT32_MIN, upper));
+                const int32_t st = __shfl_sync(0xffffffffu, s, t, 16);
+                if (pot) {
+                    if (st > prior) { stopLane = t; brk = true; pot = 0; }
+                    else pot &= pot - 1;
+                }
+            }
+            const bool part = ok && sl <= stopLane;
+            const int32_t mx = halfMax(part ? s : INT32_MIN, upper);
+            const uint32_t wm = (__ballot_sync(0xffffffffu, part && s == mx) >> hs) & 0xffffu;
+            const int32_t jW = __shfl_sync(0xffffffffu, jB, wm ? (__ffs(wm) - 1) : 0, 16);
+            if (live) {
+                if (mx > best) { best = mx; bestId = jW; }
+                cells += min(rb + 1, stopLane + 1);
+                stop = brk;
+            }
+        }
+        const int32_t bIdx = __shfl_sync(0xffffffffu, nxT.x, l0, 16), curB = __shfl_sync(0xffffffffu, nxT.y, l0, 16);
+        const int32_t extB = __shfl_sync(0xffffffffu, nxT.z, l0, 16);
+        if (act) {
+            const int32_t sB = max(best, k) + (curB - curN);   // score of the run's last match
+            if (sl == l0) { wB = bIdx; wC = curB; wE = extB; wS = sB; }   // run r replaces run r-16 in the window
+            if (sl == 0) { rn[r].scoreB = sB; rn[r].backA = best > k ? bestId : -1; }
+        }
+    }
+    if (sl == 0 && cells) atomicAdd(cellCount, cells);
+}
+
+// scores, back pointers and the input of the score sort (:331-334) of every match.  When the scores of a pair increase
+// strictly with the match index, their descending order is the unique sorted sequence of distinct keys — std::sort's
+// output — so it is written directly (reversed) and the pair is taken off the list of segments to sort.
+__global__ void __launch_bounds__(256) chainFillKernel(const Elem* __restrict__ hits, const PairInfo* __restrict__ pairs, const uint32_t* __restrict__ pairIds,
+                                                       uint32_t nPairs, const uint32_t* __restrict__ pairFlags, const Run* __restrict__ runs,
+                                                       int32_t* __restrict__ score, int32_t* __restrict__ back, Elem* __restrict__ ord,
+                                                       Seg* __restrict__ allSegs, unsigned long long* __restrict__ nPresorted) {
+    const uint32_t w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (w >= nPairs) return;
+    const int lane = threadIdx.x & 31;
+    const PairInfo pi = pairs[pairIds[w]];
+    const bool extSorted = pairFlags[w] & PAIR_EXTSORTED;
+    const int32_t n = (int32_t)pi.n;
+    const Elem* h = hits + pi.start;
+    const int4* rn4 = reinterpret_cast<const int4*>(runs + pi.start);
+    int32_t* sc = score + pi.start; int32_t* bk = back + pi.start; Elem* od = ord + pi.start;
+    bool incr = true;
+    int32_t carry = INT32_MIN;
+    for (int32_t i0 = 0; i0 < n; i0 += 32) {
+        const int32_t i = i0 + lane;
+        int32_t s = INT32_MAX;
+        if (i < n) {
+            const int32_t r = bk[i];   // run of this match (chainRunsKernel)
+            const int4 H = rn4[2 * r], T = rn4[2 * r + 1];
+            s = T.w - (T.y - elemCur(h[i], extSorted));
+            sc[i] = s;
+            bk[i] = (i == H.x) ? H.w : i - 1;
+        }
+        int32_t ps = __shfl_up_sync(0xffffffffu, s, 1);
+        if (lane == 0) ps = carry;
+        if (i < n && !(ps < s)) incr = false;
+        carry = __shfl_sync(0xffffffffu, s, 31);
+    }
+    incr = __all_sync(0xffffffffu, incr);
+    for (int32_t i0 = 0; i0 < n; i0 += 32) {
+        const int32_t i = i0 + lane;
+        if (i < n) {
+            Elem t; t.key = (unsigned long long)(0x7fffffff - sc[i]); t.val = (unsigned int)i; t.aux = 0;
+            od[incr ? n - 1 - i : i] = t;
+        }
+    }
+    if (lane == 0 && incr) { allSegs[w].n = 0; atomicAdd(nPresorted, 1ULL); }
+}
+
+__global__ void __launch_bounds__(256) runCountKeyKernel(const uint32_t* __restrict__ nRuns, uint32_t nPairs, uint32_t* __restrict__ keys,
+                                                         uint32_t* __restrict__ idx) {
+    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= nPairs) return;
+    keys[w] = ~nRuns[w];
+    idx[w] = w;
 }
 
 // order in which chainDpKernel visits the pairs: decreasing number of matches
@@ -989,7 +1258,7 @@ static uint32_t selectFlagged(fg_ctx* ctx, const FlagT* flags, uint32_t n, DevBu
 // one chunk of queries (< 2^30 k-mer slots): lookup, expansion and the per-sub-batch pipeline; the raw overlap records are
 // appended to the context's pinned buffer with `reserved` = position of the query in the whole call
 static void overlapsChunk(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, uint32_t qOffset, const fg_overlap_params& prm, const OvParams& P,
-                          size_t& nRaw, uint64_t& totHits, uint64_t& totPairs, uint64_t& totDpPairs, uint64_t& totCells) {
+                          size_t& nRaw, uint64_t& totHits, uint64_t& totPairs, uint64_t& totDpPairs, uint64_t& totCells, uint64_t& totTied, uint64_t& totPresorted) {
     const int k = ctx->k;
     // where the query sequences live: the indexed reads themselves, or the second set of fg_queries_upload
     const std::vector<uint32_t>& qHLen = P.sameSet ? ctx->hLen : ctx->hQsLen;
@@ -1060,6 +1329,7 @@ static void overlapsChunk(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, ui
     DevBuf<uint32_t> gStart, candIds, pairIds;
     SortWorkspace ws; DevBuf<Seg> segsQ;
     DevBuf<uint32_t> counters(32);
+    DevBuf<uint8_t> qTie;
 
     uint32_t qa = 0;
     while (qa < nQ) {
@@ -1077,15 +1347,62 @@ static void overlapsChunk(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, ui
         hCounters[0] = nq;
         FG_CUDA(cudaMemcpyAsync(counters.p, hCounters, sizeof hCounters, cudaMemcpyHostToDevice, ctx->stream));
         const size_t tA = qTileFirst[qa], tB = qTileFirst[qb];
-        {
-            PhaseTimer pt(ctx, "gather");
-            expandKernel<<<(unsigned)(tB - tA), 256, 0, ctx->stream>>>(ctx->dLen.p, qLen, ctx->dEntries.p, dQIds.p, dQSlotOff.p, dQTiles.p + tA, k,
-                                                                      hitOff.p, slotInfo.p, hitBase, hits.p);
-            checkLaunch(ctx, "expandKernel");
+        // tie-free fast path: stable radix sort by (query, extId); needs both fields in 32 key bits
+        int idBits = 1, qBits = 1;
+        while ((2ULL * ctx->nReads) >> idBits) ++idBits;
+        while (((uint64_t)nq) >> qBits) ++qBits;
+        const bool radixPath = envInt("FG_HIT_RADIX", 1, 0, 1) != 0 && idBits + qBits <= 32;
+        if (radixPath) {
+            // scratch: the arrays of the later chaining stages (ord = 16 B, score / back = 4 B per hit) are free until the DP
+            unsigned long long* keyA = reinterpret_cast<unsigned long long*>(ord.p);
+            unsigned long long* keyB = keyA + M;
+            uint32_t* valA = reinterpret_cast<uint32_t*>(score.p);
+            uint32_t* valB = reinterpret_cast<uint32_t*>(back.p);
+            qTie.ensure(nq);
+            FG_CUDA(cudaMemsetAsync(qTie.p, 0, nq, ctx->stream));
+            {
+                PhaseTimer pt(ctx, "gather");
+                expandKernel<true><<<(unsigned)(tB - tA), 256, 0, ctx->stream>>>(ctx->dLen.p, qLen, ctx->dEntries.p, dQIds.p, dQSlotOff.p, dQTiles.p + tA, k,
+                                                                                hitOff.p, slotInfo.p, hitBase, nullptr, keyA, valA, qa, idBits, nullptr);
+                checkLaunch(ctx, "expandKernel");
+            }
+            {
+                PhaseTimer pt(ctx, "hit_sort_radix");
+                cub::DoubleBuffer<unsigned long long> dk(keyA, keyB);
+                cub::DoubleBuffer<uint32_t> dv(valA, valB);
+                size_t tb = 0;
+                FG_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, dk, dv, (int)M, 32, 32 + idBits + qBits, ctx->stream));
+                DevBuf<char> tmpS(tb);
+                FG_CUDA(cub::DeviceRadixSort::SortPairs(tmpS.p, tb, dk, dv, (int)M, 32, 32 + idBits + qBits, ctx->stream));
+                ctx->launches += 2 + (idBits + qBits + 7) / 8;
+                rebuildHitsKernel<<<gridFor(M, 256, 16), 256, 0, ctx->stream>>>(dk.Current(), dv.Current(), M, idBits, hits.p, qTie.p);
+                checkLaunch(ctx, "rebuildHitsKernel");
+            }
+            {
+                PhaseTimer pt(ctx, "gather");
+                expandKernel<false><<<(unsigned)(tB - tA), 256, 0, ctx->stream>>>(ctx->dLen.p, qLen, ctx->dEntries.p, dQIds.p, dQSlotOff.p, dQTiles.p + tA, k,
+                                                                                 hitOff.p, slotInfo.p, hitBase, hits.p, nullptr, nullptr, qa, 0, qTie.p);
+                checkLaunch(ctx, "expandKernel");
+            }
+            querySegsKernel<<<(nq + 255) / 256, 256, 0, ctx->stream>>>(dQHitOff.p, qa, nq, hitBase, segsQ.p, qTie.p, counters.p + 24);
+            checkLaunch(ctx, "querySegsKernel");
+        } else {
+            {
+                PhaseTimer pt(ctx, "gather");
+                expandKernel<false><<<(unsigned)(tB - tA), 256, 0, ctx->stream>>>(ctx->dLen.p, qLen, ctx->dEntries.p, dQIds.p, dQSlotOff.p, dQTiles.p + tA, k,
+                                                                                 hitOff.p, slotInfo.p, hitBase, hits.p, nullptr, nullptr, qa, 0, nullptr);
+                checkLaunch(ctx, "expandKernel");
+            }
+            querySegsKernel<<<(nq + 255) / 256, 256, 0, ctx->stream>>>(dQHitOff.p, qa, nq, hitBase, segsQ.p, nullptr, nullptr);
+            checkLaunch(ctx, "querySegsKernel");
         }
-        querySegsKernel<<<(nq + 255) / 256, 256, 0, ctx->stream>>>(dQHitOff.p, qa, nq, hitBase, segsQ.p);
-        checkLaunch(ctx, "querySegsKernel");
         sortSegments(ctx, hits.p, segsQ.p, counters.p, nq, ws, "hit_sort_top", "hit_sort_small", sortCfgHits());
+        if (radixPath) {
+            uint32_t hTied = 0;
+            FG_CUDA(cudaMemcpyAsync(&hTied, counters.p + 24, 4, cudaMemcpyDeviceToHost, ctx->stream));
+            FG_CUDA(cudaStreamSynchronize(ctx->stream));
+            totTied += hTied;
+        }
         uint32_t G = 0, C = 0, Pn = 0;
         DevBuf<PairInfo> pairInfo;
         DevBuf<uint8_t> candFlag, passFlag;
@@ -1112,8 +1429,8 @@ static void overlapsChunk(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, ui
         if (Pn) {
             DevBuf<uint32_t> nCand(Pn), nKept(Pn);
             DevBuf<uint64_t> outOff(Pn + 1);
-            DevBuf<unsigned long long> dCells(1);
-            FG_CUDA(cudaMemsetAsync(dCells.p, 0, 8, ctx->stream));
+            DevBuf<unsigned long long> dCells(2);   // [0] predecessor evaluations of the DP, [1] pairs whose score order needed no sort
+            FG_CUDA(cudaMemsetAsync(dCells.p, 0, 16, ctx->stream));
             DevBuf<uint32_t> pairFlags(Pn);
             DevBuf<Seg> extSegs(Pn), allSegs(Pn);
             {
@@ -1125,21 +1442,40 @@ static void overlapsChunk(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, ui
             sortSegments(ctx, hits.p, extSegs.p, counters.p + 8, Pn, ws, "chain_extsort_top", "chain_extsort_small", sortCfgPairs());
             {
                 PhaseTimer pt(ctx, "chain_dp");
+                // FG_DP_MODE: 2 = run-compressed DP (default), 1 = match-by-match with pruned look-back, 0 = match-by-match
+                static const int dpMode = envInt("FG_DP_MODE", 2, 0, 2);
                 // visit the pairs by decreasing size: two pairs share a warp, 8 a block
-                DevBuf<uint32_t> szKeyA(Pn), szKeyB(Pn), ordA(Pn), ordB(Pn);
-                pairSizeKeyKernel<<<(Pn + 255) / 256, 256, 0, ctx->stream>>>(pairInfo.p, pairIds.p, Pn, szKeyA.p, ordA.p);
-                checkLaunch(ctx, "pairSizeKeyKernel");
+                DevBuf<uint32_t> szKeyA(Pn), szKeyB(Pn), ordA(Pn), ordB(Pn), nRuns;
+                Run* runs = reinterpret_cast<Run*>(cands.p);
+                if (dpMode == 2) {
+                    nRuns.alloc(Pn);
+                    chainRunsKernel<<<(Pn + 7) / 8, 256, 0, ctx->stream>>>(hits.p, pairInfo.p, pairIds.p, Pn, pairFlags.p, k, runs, back.p, nRuns.p);
+                    checkLaunch(ctx, "chainRunsKernel");
+                    runCountKeyKernel<<<(Pn + 255) / 256, 256, 0, ctx->stream>>>(nRuns.p, Pn, szKeyA.p, ordA.p);
+                    checkLaunch(ctx, "runCountKeyKernel");
+                } else {
+                    pairSizeKeyKernel<<<(Pn + 255) / 256, 256, 0, ctx->stream>>>(pairInfo.p, pairIds.p, Pn, szKeyA.p, ordA.p);
+                    checkLaunch(ctx, "pairSizeKeyKernel");
+                }
                 cub::DoubleBuffer<uint32_t> dk(szKeyA.p, szKeyB.p), dv(ordA.p, ordB.p);
                 size_t tb = 0;
                 FG_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, dk, dv, (int)Pn, 0, 32, ctx->stream));
                 DevBuf<char> tmpS(tb);
                 FG_CUDA(cub::DeviceRadixSort::SortPairs(tmpS.p, tb, dk, dv, (int)Pn, 0, 32, ctx->stream));
                 ctx->launches += 5;
-                static const bool dpPrune = envInt("FG_DP_PRUNE", 0, 0, 1) != 0;
-                auto dp = dpPrune ? chainDpPrunedKernel : chainDpKernel;
-                dp<<<(Pn + 7) / 8, 128, 0, ctx->stream>>>(hits.p, pairInfo.p, pairIds.p, dv.Current(), Pn, pairFlags.p, P, score.p, back.p, ord.p,
-                                                         dCells.p);   // whole warps: no early exit inside
-                checkLaunch(ctx, "chainDpKernel");
+                if (dpMode == 2) {
+                    chainRunDpKernel<<<(Pn + 7) / 8, 128, 0, ctx->stream>>>(hits.p, pairInfo.p, pairIds.p, dv.Current(), Pn, pairFlags.p, nRuns.p, P, runs,
+                                                                           dCells.p);   // whole warps: no early exit inside
+                    checkLaunch(ctx, "chainRunDpKernel");
+                    chainFillKernel<<<(Pn + 7) / 8, 256, 0, ctx->stream>>>(hits.p, pairInfo.p, pairIds.p, Pn, pairFlags.p, runs, score.p, back.p, ord.p,
+                                                                          allSegs.p, dCells.p + 1);
+                    checkLaunch(ctx, "chainFillKernel");
+                } else {
+                    auto dp = dpMode == 1 ? chainDpPrunedKernel : chainDpKernel;
+                    dp<<<(Pn + 7) / 8, 128, 0, ctx->stream>>>(hits.p, pairInfo.p, pairIds.p, dv.Current(), Pn, pairFlags.p, P, score.p, back.p, ord.p,
+                                                             dCells.p);   // whole warps: no early exit inside
+                    checkLaunch(ctx, "chainDpKernel");
+                }
             }
             FG_CUDA(cudaMemcpyAsync(counters.p + 16, &Pn, 4, cudaMemcpyHostToDevice, ctx->stream));
             sortSegments(ctx, ord.p, allSegs.p, counters.p + 16, Pn, ws, "chain_ordsort_top", "chain_ordsort_small", sortCfgPairs());
@@ -1162,11 +1498,11 @@ static void overlapsChunk(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, ui
             HostTimer pt(ctx, "host_results");   // gather of the kept overlaps, device -> pinned host copies (includes "edit")
             cub::TransformInputIterator<uint64_t, CastU64, const uint32_t*> it64(nKept.p, CastU64());
             exclusiveScanToPlus1(ctx, it64, outOff.p, Pn);
-            uint64_t nOut = 0; unsigned long long cells = 0;
+            uint64_t nOut = 0; unsigned long long cells[2] = {0, 0};
             FG_CUDA(cudaMemcpyAsync(&nOut, outOff.p + Pn, 8, cudaMemcpyDeviceToHost, ctx->stream));
-            FG_CUDA(cudaMemcpyAsync(&cells, dCells.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+            FG_CUDA(cudaMemcpyAsync(cells, dCells.p, 16, cudaMemcpyDeviceToHost, ctx->stream));
             FG_CUDA(cudaStreamSynchronize(ctx->stream));
-            totCells += cells;
+            totCells += cells[0]; totPresorted += cells[1];
             if (nOut) {
                 DevBuf<fg_overlap> dOut(nOut);
                 gatherOverlapsKernel<<<(Pn + 255) / 256, 256, 0, ctx->stream>>>(pairInfo.p, pairIds.p, Pn, dQIds.p, ctx->dLen.p, qLen, ord.p, cands.p,
@@ -1235,7 +1571,7 @@ void overlapsBatch(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, const fg_
 
     ctx->resOffsets.assign(nQ + 1, 0);
     ctx->resAln.clear();
-    uint64_t totHits = 0, totPairs = 0, totDpPairs = 0, totCells = 0;
+    uint64_t totHits = 0, totPairs = 0, totDpPairs = 0, totCells = 0, totTied = 0, totPresorted = 0;
     PinnedBuf<fg_overlap>& pinned = ctx->pinnedOut;   // all chunks / sub-batches land here; the epilogue compacts in place
     size_t nRaw = 0;
     HostTimer hostAll(ctx, "host_total");
@@ -1253,7 +1589,7 @@ void overlapsBatch(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, const fg_
             if (q1 > q0 && slots + add >= chunkSlots) break;
             slots += add; ++q1;
         }
-        overlapsChunk(ctx, queryIds + q0, q1 - q0, q0, prm, P, nRaw, totHits, totPairs, totDpPairs, totCells);
+        overlapsChunk(ctx, queryIds + q0, q1 - q0, q0, prm, P, nRaw, totHits, totPairs, totDpPairs, totCells, totTied, totPresorted);
         q0 = q1;
     }
 
@@ -1324,6 +1660,8 @@ void overlapsBatch(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, const fg_
 
     ctx->timings.emplace_back("arena_mallocs", (float)(ctx->arena.mallocCalls - mallocs0)); ctx->timingCalls.push_back(1);
     ctx->timings.emplace_back("arena_gib", (float)(ctx->arena.totalBytes / 1073741824.0)); ctx->timingCalls.push_back(1);
+    ctx->timings.emplace_back("tied_queries", (float)totTied); ctx->timingCalls.push_back(1);   // queries that needed the exact hit sort
+    ctx->timings.emplace_back("presorted_pairs", (float)totPresorted); ctx->timingCalls.push_back(1);   // pairs whose score order needed no sort
     result->n_queries = nQ;
     result->offsets = ctx->resOffsets.data();
     result->overlaps = hOut;
