@@ -596,8 +596,9 @@ FG_DEV void warpIntrosortRange(Elem* arr, idx_t f0, idx_t l0, int d0, idx_t smal
     };
     // a finished-partitioning range: leaf (<= 16) or, in two-level mode, a task for the second kernel
     auto retire = [&](idx_t f, idx_t l, int d) {
+        if (l - f < 1) return;
+        if (small > 0) { sink(f, l, d); return; }   // single elements too: the tie-following sink has to deliver them
         if (l - f < 2) return;
-        if (small > 0) { sink(f, l, d); return; }
         FG_FOR_LANES if (lane == nLeaf) { FG_L(lfF) = f; FG_L(lfL) = l; FG_L(lfD) = d; } FG_END_LANES
         if (++nLeaf == 32) flushLeaves();
     };
@@ -619,6 +620,7 @@ FG_DEV void warpIntrosortRange(Elem* arr, idx_t f0, idx_t l0, int d0, idx_t smal
 #endif
                 FG_SYNCWARP();
                 heapSorted = true;
+                if (small > 0) sink(f, l, -1);   // two-level mode: tell the sink that this range is finished in place
                 break;
             }
             --d;

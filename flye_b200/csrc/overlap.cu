@@ -24,6 +24,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <functional>
+#include <memory>
 #include <thread>
 
 namespace fg {
@@ -93,6 +94,7 @@ __global__ void __launch_bounds__(256) queryLookupKernel(const uint64_t* __restr
 }
 
 struct CastU64 { __host__ __device__ uint64_t operator()(uint32_t x) const { return x; } };
+struct CastU8 { __host__ __device__ uint32_t operator()(uint8_t x) const { return x; } };
 struct PopcU32 { __host__ __device__ uint32_t operator()(uint32_t x) const {
 #ifdef __CUDA_ARCH__
     return __popc(x);
@@ -166,13 +168,15 @@ __global__ void __launch_bounds__(256) expandKernel(const uint32_t* __restrict__
 // (key, extPos) pairs back into Elem records and flags every query that does contain a tie (two adjacent equal keys):
 // those queries are expanded again and go through the exact introsort emulation.
 __global__ void __launch_bounds__(256) rebuildHitsKernel(const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ vals, uint64_t M,
-                                                         int idBits, Elem* __restrict__ hits, uint8_t* __restrict__ qTie) {
+                                                         int idBits, Elem* __restrict__ hits, uint8_t* __restrict__ qTie, uint8_t* __restrict__ tieFlag) {
     const unsigned long long idMask = (1ULL << idBits) - 1ULL;
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < M; i += (uint64_t)gridDim.x * blockDim.x) {
         const unsigned long long kk = keys[i];
         Elem o; o.key = (((kk >> 32) & idMask) << 32) | (kk & 0xffffffffULL); o.val = vals[i]; o.aux = 0;
         hits[i] = o;
-        if (i + 1 < M && keys[i + 1] == kk) qTie[kk >> (32 + idBits)] = 1;
+        const bool tie = i + 1 < M && keys[i + 1] == kk;
+        tieFlag[i] = tie;   // input of the prefix count that lets the exact sort skip tie-free ranges
+        if (tie) qTie[kk >> (32 + idBits)] = 1;
     }
 }
 
@@ -207,9 +211,18 @@ struct SortTask { uint32_t start, n; int depth; };
 
 // counters of one segmented sort (8 words): [0] nSegs (input)  [1] nSmall  [2] next small task  [3] nBig ping  [4] nBig pong
 //                                           [5] elements in the ping list  [6] elements in the pong list
+// tieP (optional): tieP[i] = number of positions j < i of the stably sorted array with key[j] == key[j+1].  A range of the
+// recursion holds the keys of the sorted ranks it covers; when none of them is duplicated (inside the range or across its
+// ends) the elements are determined by their keys and std::sort's result for these positions is the stable-sorted array
+// itself, which the output already holds — the emulation only has to follow the ranges that contain ties.
+__device__ __forceinline__ bool rangeIsTieFree(const uint32_t* __restrict__ tieP, uint32_t start, uint32_t n) {
+    return tieP && tieP[start + n] == tieP[start ? start - 1 : 0];
+}
 __device__ __forceinline__ void emitRange(uint32_t start, uint32_t n, int depth, SortTask* big, uint32_t* nBig, uint32_t capBig,
-                                          SortTask* small, uint32_t* nSmall, uint32_t capSmall, uint32_t smallN) {
-    if (n < 2) return;
+                                          SortTask* small, uint32_t* nSmall, uint32_t capSmall, uint32_t smallN, const uint32_t* __restrict__ tieP) {
+    // (a single element that is part of a tie still has to be delivered: which of the equal elements ended up here is
+    // exactly what the emulation decides)
+    if (n < (tieP ? 1u : 2u) || rangeIsTieFree(tieP, start, n)) return;
     SortTask k; k.start = start; k.n = n; k.depth = depth;
     if (n > smallN) { const uint32_t t = atomicAdd(nBig, 1u); atomicAdd(nBig + 2, n); if (t < capBig) big[t] = k; }
     else { const uint32_t t = atomicAdd(nSmall, 1u); if (t < capSmall) small[t] = k; }
@@ -218,18 +231,27 @@ __device__ __forceinline__ void emitRange(uint32_t start, uint32_t n, int depth,
 // every segment becomes one task: a "big" one (partitioned level by level in global memory) or a "small" one
 __global__ void __launch_bounds__(256) sortSeedKernel(const Seg* __restrict__ segs, const uint32_t* __restrict__ nSegsPtr, SortTask* __restrict__ big,
                                                       uint32_t* __restrict__ nBig, uint32_t capBig, SortTask* __restrict__ small,
-                                                      uint32_t* __restrict__ nSmall, uint32_t capSmall, uint32_t smallN) {
+                                                      uint32_t* __restrict__ nSmall, uint32_t capSmall, uint32_t smallN, const uint32_t* __restrict__ tieP) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= *nSegsPtr) return;
     const Seg sg = segs[i];
-    emitRange(sg.start, sg.n, introsortDepth((long)sg.n), big, nBig, capBig, small, nSmall, capSmall, smallN);
+    emitRange(sg.start, sg.n, introsortDepth((long)sg.n), big, nBig, capBig, small, nSmall, capSmall, smallN, tieP);
 }
 
 // one introsort level: every warp partitions one big range (or heap-sorts it when its depth budget is spent,
 // stl_algo.h:1925-1929) and emits the two halves as tasks of the next level / of the shared-memory kernel
+// `outArr`: where finished (fully sorted) ranges are delivered; equal to arr except in the tie-following mode, where arr is a
+// scratch copy in the original order and outArr already holds the stable-sorted elements.
+__device__ __forceinline__ void copyOutRange(const Elem* arr, Elem* outArr, uint32_t start, uint32_t n) {
+    if (outArr == arr) return;
+    __syncwarp();
+    for (uint32_t i = laneId(); i < n; i += 32) outArr[start + i] = arr[start + i];
+}
+
 __global__ void __launch_bounds__(128) sortLevelKernel(Elem* __restrict__ arr, const SortTask* __restrict__ in, const uint32_t* __restrict__ nInPtr,
                                                        uint32_t capBig, SortTask* __restrict__ out, uint32_t* __restrict__ nOut,
-                                                       SortTask* __restrict__ small, uint32_t* __restrict__ nSmall, uint32_t capSmall, uint32_t smallN) {
+                                                       SortTask* __restrict__ small, uint32_t* __restrict__ nSmall, uint32_t capSmall, uint32_t smallN,
+                                                       Elem* outArr, const uint32_t* __restrict__ tieP) {
     __shared__ unsigned char tabs[4][WARP_TAB_BYTES];
     const uint32_t w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (w >= min(*nInPtr, capBig)) return;
@@ -237,12 +259,13 @@ __global__ void __launch_bounds__(128) sortLevelKernel(Elem* __restrict__ arr, c
     Elem* a = arr + t.start;
     if (t.depth == 0) {
         if (laneId() == 0) seqHeapSort(a, (long)t.n);
+        copyOutRange(arr, outArr, t.start, t.n);
         return;
     }
     const idx_t cut = warpPartitionAny(a, 0, (idx_t)t.n, tabs[threadIdx.x >> 5], /*inGlobal*/ true);
     if (laneId() == 0) {
-        emitRange(t.start, (uint32_t)cut, t.depth - 1, out, nOut, capBig, small, nSmall, capSmall, smallN);
-        emitRange(t.start + (uint32_t)cut, t.n - (uint32_t)cut, t.depth - 1, out, nOut, capBig, small, nSmall, capSmall, smallN);
+        emitRange(t.start, (uint32_t)cut, t.depth - 1, out, nOut, capBig, small, nSmall, capSmall, smallN, tieP);
+        emitRange(t.start + (uint32_t)cut, t.n - (uint32_t)cut, t.depth - 1, out, nOut, capBig, small, nSmall, capSmall, smallN, tieP);
     }
 }
 
@@ -250,8 +273,11 @@ __global__ void __launch_bounds__(128) sortLevelKernel(Elem* __restrict__ arr, c
 // memory, handing every sub-range of <= smallN elements to the shared-memory kernel
 struct TaskSinkDev {
     SortTask* tasks; uint32_t* counter; uint32_t cap; uint32_t base;
+    const Elem* arr; Elem* outArr; const uint32_t* tieP;
     __device__ __forceinline__ void operator()(long f, long l, int d) const {
-        if (laneId() == 0) {
+        if (d < 0) { copyOutRange(arr, outArr, base + (uint32_t)f, (uint32_t)(l - f)); return; }   // heap-sorted in place: finished
+        if (l - f < (tieP ? 1 : 2)) return;
+        if (laneId() == 0 && !rangeIsTieFree(tieP, base + (uint32_t)f, (uint32_t)(l - f))) {
             const uint32_t t = atomicAdd(counter, 1u);
             if (t < cap) { SortTask k; k.start = base + (uint32_t)f; k.n = (uint32_t)(l - f); k.depth = d; tasks[t] = k; }
         }
@@ -260,12 +286,12 @@ struct TaskSinkDev {
 
 __global__ void __launch_bounds__(128) sortTailKernel(Elem* __restrict__ arr, const SortTask* __restrict__ in, const uint32_t* __restrict__ nInPtr,
                                                       uint32_t capBig, SortTask* __restrict__ small, uint32_t* __restrict__ nSmall,
-                                                      uint32_t capSmall, uint32_t smallN) {
+                                                      uint32_t capSmall, uint32_t smallN, Elem* outArr, const uint32_t* __restrict__ tieP) {
     __shared__ unsigned char tabs[4][WARP_TAB_BYTES];
     const uint32_t w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (w >= min(*nInPtr, capBig)) return;
     const SortTask t = in[w];
-    TaskSinkDev sink{small, nSmall, capSmall, t.start};
+    TaskSinkDev sink{small, nSmall, capSmall, t.start, arr, outArr, tieP};
     warpIntrosortRange(arr + t.start, 0, (idx_t)t.n, t.depth, (idx_t)smallN, sink, tabs[threadIdx.x >> 5], /*inGlobal*/ true);
 }
 
@@ -278,7 +304,7 @@ __global__ void __launch_bounds__(128) sortTailKernel(Elem* __restrict__ arr, co
 template <int VARIANT>
 __global__ void __launch_bounds__(128) sortSmallKernel(Elem* __restrict__ arr, const SortTask* __restrict__ tasks,
                                                        const uint32_t* __restrict__ taskCounter, uint32_t taskCap, uint32_t* __restrict__ next,
-                                                       uint32_t smallN) {
+                                                       uint32_t smallN, Elem* outArr) {
     extern __shared__ __align__(16) unsigned char smemRaw[];
     __shared__ unsigned char tabs[4][WARP_TAB_BYTES];
     const int wid = threadIdx.x >> 5;
@@ -301,7 +327,8 @@ __global__ void __launch_bounds__(128) sortSmallKernel(Elem* __restrict__ arr, c
         else if (VARIANT == 3) warpIntrosortSmem<32>(sm, (idx_t)k.n, k.depth, reinterpret_cast<unsigned short*>(tab), reinterpret_cast<unsigned short*>(tab) + smallN, bits);
         else warpIntrosortRange<VARIANT == 1>(sm, 0, (idx_t)k.n, k.depth, 0, none, tab, false, (int)smallN);
         __syncwarp();
-        for (uint32_t i = lane; i < k.n; i += 32) g[i] = sm[i];
+        Elem* go = outArr + k.start;
+        for (uint32_t i = lane; i < k.n; i += 32) go[i] = sm[i];
         __syncwarp();
     }
 }
@@ -800,7 +827,7 @@ __global__ void __launch_bounds__(128) chainRunDpKernel(const Elem* __restrict__
     const int k = P.k;
     const Elem* h = hits + pi.start;
     Run* rn = runs + pi.start;
-    const int4* rn4 = reinterpret_cast<const int4*>(rn);   // [2r] = {a, curA, extA, backA}, [2r+1] = {b, curB, extB, scoreB}
+    const int4* rn4 = reinterpret_cast<const int4*>(rn);   // [2r] = {a, curA, extA | run of backA, backA}, [2r+1] = {b, curB, extB, scoreB}
 
     // records of the runs [16b, 16b+16): nx* = current block, pf* = next block (loaded a block ahead; scoreB not used from these)
     int4 nxH = make_int4(0, 0, 0, 0), nxT = nxH, pfH = nxH, pfT = nxH;
@@ -820,7 +847,7 @@ __global__ void __launch_bounds__(128) chainRunDpKernel(const Elem* __restrict__
         }
         const int32_t curN = __shfl_sync(0xffffffffu, nxH.y, l0, 16), extN = __shfl_sync(0xffffffffu, nxH.z, l0, 16);
         const int32_t sortedN = extSorted ? extN : curN;
-        int32_t best = 0, bestId = 0;
+        int32_t best = 0, bestId = 0, bestRun = 0;
         bool stop = !act;
         for (int32_t rb = r - 1;; rb -= 16) {
             const bool live = !stop && rb >= 0;                            // uniform inside a half
@@ -880,7 +907,7 @@ __global__ void __launch_bounds__(128) chainRunDpKernel(const Elem* __restrict__
             const uint32_t wm = (__ballot_sync(0xffffffffu, part && s == mx) >> hs) & 0xffffu;
             const int32_t jW = __shfl_sync(0xffffffffu, jB, wm ? (__ffs(wm) - 1) : 0, 16);
             if (live) {
-                if (mx > best) { best = mx; bestId = jW; }
+                if (mx > best) { best = mx; bestId = jW; bestRun = rb - (__ffs(wm) - 1); }
                 cells += min(rb + 1, stopLane + 1);
                 stop = brk;
             }
@@ -890,7 +917,8 @@ __global__ void __launch_bounds__(128) chainRunDpKernel(const Elem* __restrict__
         if (act) {
             const int32_t sB = max(best, k) + (curB - curN);   // score of the run's last match
             if (sl == l0) { wB = bIdx; wC = curB; wE = extB; wS = sB; }   // run r replaces run r-16 in the window
-            if (sl == 0) { rn[r].scoreB = sB; rn[r].backA = best > k ? bestId : -1; }
+            // extA of a finished head is not read again: the slot keeps the run of the back pointer for the chain walk
+            if (sl == 0) { rn[r].scoreB = sB; rn[r].backA = best > k ? bestId : -1; rn[r].extA = bestRun; }
         }
     }
     if (sl == 0 && cells) atomicAdd(cellCount, cells);
@@ -963,12 +991,22 @@ __global__ void __launch_bounds__(256) pairSizeKeyKernel(const PairInfo* __restr
 // walks the chains in order, re-testing the remaining starts after every walk because a walk consumes pointers.
 static constexpr int WALK_CAP = 4096;   // matches per warp whose back pointers are staged in shared memory as 16-bit deltas (8 KB)
 
+// RUNS = true (after the run-compressed DP): the walk goes run by run.  Inside a run every match points to its
+// predecessor, and every walk that enters a run continues down to the run's head or to an already consumed match, so the
+// consumed matches of a run are always a prefix [a, ce) of it: one 16-bit watermark per run replaces the per-match
+// pointers, a walk costs one step per run instead of one per match, and each run can start at most one chain.  Run table
+// in shared memory (4 x 16 bit per run: first match, watermark, back pointer of the head and its run); pairs with more
+// than RUN_CAP runs or more than 65535 matches take the match-by-match path on the global back pointers.
+static constexpr int RUN_CAP = WALK_CAP / 4;
+
+template <bool RUNS>
 __global__ void __launch_bounds__(128) chainWalkKernel(const Elem* __restrict__ hits, const PairInfo* __restrict__ pairs, const uint32_t* __restrict__ pairIds,
                                                        uint32_t nPairs, const uint32_t* __restrict__ pairFlags, const uint32_t* __restrict__ qIds,
                                                        const uint64_t* __restrict__ qSlotOff, const uint32_t* __restrict__ len,
                                                        const uint32_t* __restrict__ qlen, const uint32_t* __restrict__ filtBits, const uint32_t* __restrict__ filtPrefix, OvParams P,
                                                        const int32_t* __restrict__ score, int32_t* __restrict__ back, Elem* __restrict__ ord,
-                                                       Cand* __restrict__ cands, uint32_t* __restrict__ nCandOut, uint32_t* __restrict__ nKeptOut) {
+                                                       Cand* __restrict__ cands, uint32_t* __restrict__ nCandOut, uint32_t* __restrict__ nKeptOut,
+                                                       const uint32_t* __restrict__ nRuns) {
     extern __shared__ __align__(16) unsigned char smemRaw[];
     const uint32_t w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (w >= nPairs) return;
@@ -988,23 +1026,56 @@ __global__ void __launch_bounds__(128) chainWalkKernel(const Elem* __restrict__ 
     // back pointers: delta = pos - back[pos] (>= 1), 0 = none.  n <= WALK_CAP < 65536, so a delta fits 16 bits.
     int32_t* bkG = back + pi.start;
     unsigned short* sb = reinterpret_cast<unsigned short*>(smemRaw) + (threadIdx.x >> 5) * WALK_CAP;
-    const bool staged = n <= WALK_CAP;
-    if (staged)
+    const int32_t R = RUNS ? (int32_t)nRuns[w] : 0;
+    const bool byRuns = RUNS && R <= RUN_CAP && n <= 65535;
+    const bool staged = !byRuns && n <= WALK_CAP;
+    // run table (byRuns); the candidates written below reuse the global run records, so everything needed is staged
+    unsigned short* sA = sb; unsigned short* sCe = sb + RUN_CAP; unsigned short* sBk = sb + 2 * RUN_CAP; unsigned short* sBr = sb + 3 * RUN_CAP;
+    if (byRuns) {
+        const int4* rn4 = reinterpret_cast<const int4*>(cands + pi.start);   // {a, curA, run of backA, backA}
+        for (int32_t r = lane; r < R; r += 32) {
+            const int4 H = rn4[2 * r];
+            sA[r] = (unsigned short)H.x; sCe[r] = (unsigned short)H.x;
+            sBk[r] = H.w < 0 ? (unsigned short)0xffff : (unsigned short)H.w; sBr[r] = (unsigned short)H.z;
+        }
+    } else if (staged)
         for (int32_t i = lane; i < n; i += 32) { const int32_t b = bkG[i]; sb[i] = b < 0 ? 0 : (unsigned short)(i - b); }
     __syncwarp();
-    auto hasBack = [&](int32_t pos) { return staged ? sb[pos] != 0 : bkG[pos] >= 0; };
+    auto runOf = [&](int32_t pos) {   // last run with first match <= pos
+        int32_t lo = 0, hi = R;
+        while (hi - lo > 1) { const int32_t mid = (lo + hi) >> 1; if ((int32_t)sA[mid] <= pos) lo = mid; else hi = mid; }
+        return lo;
+    };
+    auto hasBack = [&](int32_t pos, int32_t r) {
+        if (byRuns) return pos >= (int32_t)sCe[r] && (pos > (int32_t)sA[r] || sBk[r] != 0xffff);
+        return staged ? sb[pos] != 0 : bkG[pos] >= 0;
+    };
 
     uint32_t nCand = 0;   // meaningful in lane 0
     for (int32_t t0 = 0; t0 < n; t0 += 32) {
         const int32_t t = t0 + lane;
         const int32_t cs = t < n ? (int32_t)od[t].val : 0;
-        uint32_t m = __ballot_sync(0xffffffffu, t < n && hasBack(cs));
+        const int32_t cr = (byRuns && t < n) ? runOf(cs) : 0;
+        uint32_t m = __ballot_sync(0xffffffffu, t < n && hasBack(cs, cr));
         while (m) {
             const int src = __ffs(m) - 1;
             const int32_t chainStart = __shfl_sync(0xffffffffu, cs, src);
+            const int32_t startRun = __shfl_sync(0xffffffffu, cr, src);
             if (lane == 0) {
                 int32_t firstMatch = 0, chainLength = 0, pos = chainStart;
-                if (staged) {
+                if (byRuns) {
+                    int32_t r = startRun;
+                    for (;;) {
+                        const int32_t a = sA[r], ce = sCe[r];
+                        if (pos < ce) { firstMatch = pos; ++chainLength; break; }   // a consumed match ends the chain (it is still its first match)
+                        sCe[r] = (unsigned short)(pos + 1);
+                        if (ce > a) { firstMatch = ce - 1; chainLength += pos - ce + 2; break; }
+                        firstMatch = a; chainLength += pos - a + 1;
+                        const unsigned short nb = sBk[r];
+                        if (nb == 0xffff) break;
+                        pos = nb; r = sBr[r];
+                    }
+                } else if (staged) {
                     for (;;) { firstMatch = pos; ++chainLength; const unsigned short d = sb[pos]; sb[pos] = 0; if (!d) break; pos -= d; }
                 } else {
                     // consumed nodes keep their pointer recoverable (value -2-np) for the keepAlignment re-walk
@@ -1031,7 +1102,7 @@ __global__ void __launch_bounds__(128) chainWalkKernel(const Elem* __restrict__ 
                 }
             }
             __syncwarp();
-            m = __ballot_sync(0xffffffffu, lane > src && t < n && hasBack(cs));
+            m = __ballot_sync(0xffffffffu, lane > src && t < n && hasBack(cs, cr));
         }
     }
     __syncwarp();   // all lanes are done reading ord[] before lane 0 reuses its slots
@@ -1142,8 +1213,11 @@ struct SortWorkspace {
     }
 };
 
+// outArr / tieP: tie-following mode (see rangeIsTieFree): arr = scratch copy of the segments in their original order,
+// outArr = the stable-sorted elements; only ranges that contain ties are emulated and delivered to outArr.
 static void sortSegments(fg_ctx* ctx, Elem* arr, const Seg* dSegs, uint32_t* dCounters, uint32_t maxSegs, SortWorkspace& ws,
-                         const char* topName, const char* smallName, SortCfg cfg) {
+                         const char* topName, const char* smallName, SortCfg cfg, Elem* outArr = nullptr, const uint32_t* tieP = nullptr) {
+    if (!outArr) outArr = arr;
     static bool attrSet = false;
     const int variant = cfg.variant;
     const uint32_t smallN = (uint32_t)cfg.smallN;
@@ -1162,7 +1236,7 @@ static void sortSegments(fg_ctx* ctx, Elem* arr, const Seg* dSegs, uint32_t* dCo
     {
         PhaseTimer pt(ctx, topName);
         sortSeedKernel<<<(maxSegs + 255) / 256, 256, 0, ctx->stream>>>(dSegs, dCounters, ws.bigA.p, dCounters + 3, ws.capBig, ws.small.p,
-                                                                      dCounters + 1, ws.capSmall, smallN);
+                                                                      dCounters + 1, ws.capSmall, smallN, tieP);
         checkLaunch(ctx, "sortSeedKernel");
         SortTask* in = ws.bigA.p; SortTask* out = ws.bigB.p;
         uint32_t* nIn = dCounters + 3; uint32_t* nOut = dCounters + 4;
@@ -1178,20 +1252,20 @@ static void sortSegments(fg_ctx* ctx, Elem* arr, const Seg* dSegs, uint32_t* dCo
             // tail: little work left in unevenly split ranges -> finish each range with one warp instead of paying a
             // launch + host round trip per remaining level
             if (level >= 4 && ((uint64_t)elems * 16 < firstElems || level >= 48)) {
-                sortTailKernel<<<(cnt + 3) / 4, 128, 0, ctx->stream>>>(arr, in, nIn, ws.capBig, ws.small.p, dCounters + 1, ws.capSmall, smallN);
+                sortTailKernel<<<(cnt + 3) / 4, 128, 0, ctx->stream>>>(arr, in, nIn, ws.capBig, ws.small.p, dCounters + 1, ws.capSmall, smallN, outArr, tieP);
                 checkLaunch(ctx, "sortTailKernel");
                 break;
             }
             FG_CUDA(cudaMemsetAsync(nOut, 0, 4, ctx->stream));
             FG_CUDA(cudaMemsetAsync(nOut + 2, 0, 4, ctx->stream));
-            sortLevelKernel<<<(cnt + 3) / 4, 128, 0, ctx->stream>>>(arr, in, nIn, ws.capBig, out, nOut, ws.small.p, dCounters + 1, ws.capSmall, smallN);
+            sortLevelKernel<<<(cnt + 3) / 4, 128, 0, ctx->stream>>>(arr, in, nIn, ws.capBig, out, nOut, ws.small.p, dCounters + 1, ws.capSmall, smallN, outArr, tieP);
             checkLaunch(ctx, "sortLevelKernel");
             std::swap(in, out); std::swap(nIn, nOut);
         }
     }
     {
         PhaseTimer pt(ctx, smallName);
-        smallKernel<<<148 * blocksPerSm, 128, smemBytes, ctx->stream>>>(arr, ws.small.p, dCounters + 1, ws.capSmall, dCounters + 2, smallN);
+        smallKernel<<<148 * blocksPerSm, 128, smemBytes, ctx->stream>>>(arr, ws.small.p, dCounters + 1, ws.capSmall, dCounters + 2, smallN, outArr);
         checkLaunch(ctx, "sortSmallKernel");
     }
 }
@@ -1268,6 +1342,7 @@ static void overlapsChunk(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, ui
     PinnedBuf<fg_overlap>& pinned = ctx->pinnedOut;
 
     // query slot space and tiles
+    std::unique_ptr<HostTimer> hostPrep(new HostTimer(ctx, "host_chunk_prep"));   // wall clock up to the first sub-batch (incl. "gather" lookups)
     std::vector<uint64_t> hQSlotOff(nQ + 1, 0);
     std::vector<uint2> hQTiles;
     std::vector<size_t> qTileFirst(nQ + 1, 0);
@@ -1331,6 +1406,8 @@ static void overlapsChunk(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, ui
     DevBuf<uint32_t> counters(32);
     DevBuf<uint8_t> qTie;
 
+    hostPrep.reset();
+    HostTimer hostSub(ctx, "host_subbatches");   // wall clock of all sub-batches: minus the device phases = host gaps
     uint32_t qa = 0;
     while (qa < nQ) {
         uint32_t qb = qa + 1;
@@ -1339,7 +1416,7 @@ static void overlapsChunk(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, ui
         const uint32_t nq = qb - qa;
         if (M >= (1ULL << 31)) throw Error(FG_ERR_ARG, "a single query produced >= 2^31 k-mer hits");
         if (M == 0) { qa = qb; continue; }
-        hits.ensure(M); ord.ensure(M); score.ensure(M); back.ensure(M); cands.ensure(M); flags.ensure(M);
+        hits.ensure(M); ord.ensure(M); score.ensure(M + 1); back.ensure(M); cands.ensure(M); flags.ensure(M + 1);
         ws.ensure(M, nq);
         const uint32_t taskCap = ws.capSmall;
         segsQ.ensure(nq);
@@ -1375,17 +1452,38 @@ static void overlapsChunk(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, ui
                 DevBuf<char> tmpS(tb);
                 FG_CUDA(cub::DeviceRadixSort::SortPairs(tmpS.p, tb, dk, dv, (int)M, 32, 32 + idBits + qBits, ctx->stream));
                 ctx->launches += 2 + (idBits + qBits + 7) / 8;
-                rebuildHitsKernel<<<gridFor(M, 256, 16), 256, 0, ctx->stream>>>(dk.Current(), dv.Current(), M, idBits, hits.p, qTie.p);
+                rebuildHitsKernel<<<gridFor(M, 256, 16), 256, 0, ctx->stream>>>(dk.Current(), dv.Current(), M, idBits, hits.p, qTie.p, flags.p);
                 checkLaunch(ctx, "rebuildHitsKernel");
-            }
-            {
-                PhaseTimer pt(ctx, "gather");
-                expandKernel<false><<<(unsigned)(tB - tA), 256, 0, ctx->stream>>>(ctx->dLen.p, qLen, ctx->dEntries.p, dQIds.p, dQSlotOff.p, dQTiles.p + tA, k,
-                                                                                 hitOff.p, slotInfo.p, hitBase, hits.p, nullptr, nullptr, qa, 0, qTie.p);
-                checkLaunch(ctx, "expandKernel");
             }
             querySegsKernel<<<(nq + 255) / 256, 256, 0, ctx->stream>>>(dQHitOff.p, qa, nq, hitBase, segsQ.p, qTie.p, counters.p + 24);
             checkLaunch(ctx, "querySegsKernel");
+            uint32_t hTied = 0;
+            FG_CUDA(cudaMemcpyAsync(&hTied, counters.p + 24, 4, cudaMemcpyDeviceToHost, ctx->stream));
+            FG_CUDA(cudaStreamSynchronize(ctx->stream));
+            totTied += hTied;
+            if (hTied) {
+                // queries with ties: expanded again in the original order into a scratch array (the candidate array, free
+                // until the chain walk) and sorted by the exact introsort emulation, which only follows the ranges that
+                // contain ties; everything else of these queries keeps the stable-sorted order already in `hits`
+                Elem* scratch = reinterpret_cast<Elem*>(cands.p);
+                uint32_t* tieP = reinterpret_cast<uint32_t*>(score.p);
+                {
+                    PhaseTimer pt(ctx, "hit_sort_top");
+                    cub::TransformInputIterator<uint32_t, CastU8, const uint8_t*> itF(flags.p, CastU8());
+                    size_t tb = 0;
+                    FG_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, itF, tieP, (int)(M + 1), ctx->stream));
+                    DevBuf<char> tmpS(tb);
+                    FG_CUDA(cub::DeviceScan::ExclusiveSum(tmpS.p, tb, itF, tieP, (int)(M + 1), ctx->stream));
+                    ++ctx->launches;
+                }
+                {
+                    PhaseTimer pt(ctx, "gather");
+                    expandKernel<false><<<(unsigned)(tB - tA), 256, 0, ctx->stream>>>(ctx->dLen.p, qLen, ctx->dEntries.p, dQIds.p, dQSlotOff.p, dQTiles.p + tA, k,
+                                                                                     hitOff.p, slotInfo.p, hitBase, scratch, nullptr, nullptr, qa, 0, qTie.p);
+                    checkLaunch(ctx, "expandKernel");
+                }
+                sortSegments(ctx, scratch, segsQ.p, counters.p, nq, ws, "hit_sort_top", "hit_sort_small", sortCfgHits(), hits.p, tieP);
+            }
         } else {
             {
                 PhaseTimer pt(ctx, "gather");
@@ -1395,13 +1493,7 @@ static void overlapsChunk(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, ui
             }
             querySegsKernel<<<(nq + 255) / 256, 256, 0, ctx->stream>>>(dQHitOff.p, qa, nq, hitBase, segsQ.p, nullptr, nullptr);
             checkLaunch(ctx, "querySegsKernel");
-        }
-        sortSegments(ctx, hits.p, segsQ.p, counters.p, nq, ws, "hit_sort_top", "hit_sort_small", sortCfgHits());
-        if (radixPath) {
-            uint32_t hTied = 0;
-            FG_CUDA(cudaMemcpyAsync(&hTied, counters.p + 24, 4, cudaMemcpyDeviceToHost, ctx->stream));
-            FG_CUDA(cudaStreamSynchronize(ctx->stream));
-            totTied += hTied;
+            sortSegments(ctx, hits.p, segsQ.p, counters.p, nq, ws, "hit_sort_top", "hit_sort_small", sortCfgHits());
         }
         uint32_t G = 0, C = 0, Pn = 0;
         DevBuf<PairInfo> pairInfo;
@@ -1431,8 +1523,10 @@ static void overlapsChunk(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, ui
             DevBuf<uint64_t> outOff(Pn + 1);
             DevBuf<unsigned long long> dCells(2);   // [0] predecessor evaluations of the DP, [1] pairs whose score order needed no sort
             FG_CUDA(cudaMemsetAsync(dCells.p, 0, 16, ctx->stream));
-            DevBuf<uint32_t> pairFlags(Pn);
+            DevBuf<uint32_t> pairFlags(Pn), nRuns;
             DevBuf<Seg> extSegs(Pn), allSegs(Pn);
+            // FG_DP_MODE: 2 = run-compressed DP and chain walk (default), 1 = match-by-match with pruned look-back, 0 = match-by-match
+            const int dpMode = envInt("FG_DP_MODE", 2, 0, 2);   // read per call: the tests switch it
             {
                 PhaseTimer pt(ctx, "chain_prep");
                 pairPrepKernel<<<(Pn + 7) / 8, 256, 0, ctx->stream>>>(hits.p, pairInfo.p, pairIds.p, Pn, dQIds.p, ctx->dLen.p, qLen, pairFlags.p,
@@ -1443,9 +1537,8 @@ static void overlapsChunk(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, ui
             {
                 PhaseTimer pt(ctx, "chain_dp");
                 // FG_DP_MODE: 2 = run-compressed DP (default), 1 = match-by-match with pruned look-back, 0 = match-by-match
-                static const int dpMode = envInt("FG_DP_MODE", 2, 0, 2);
                 // visit the pairs by decreasing size: two pairs share a warp, 8 a block
-                DevBuf<uint32_t> szKeyA(Pn), szKeyB(Pn), ordA(Pn), ordB(Pn), nRuns;
+                DevBuf<uint32_t> szKeyA(Pn), szKeyB(Pn), ordA(Pn), ordB(Pn);
                 Run* runs = reinterpret_cast<Run*>(cands.p);
                 if (dpMode == 2) {
                     nRuns.alloc(Pn);
@@ -1483,10 +1576,15 @@ static void overlapsChunk(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, ui
                 PhaseTimer pt(ctx, "chain_walk");
                 static bool walkAttr = false;
                 const int walkSmem = 4 * WALK_CAP * (int)sizeof(unsigned short);
-                if (!walkAttr) { FG_CUDA(cudaFuncSetAttribute(chainWalkKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, walkSmem)); walkAttr = true; }
-                chainWalkKernel<<<(Pn + 3) / 4, 128, walkSmem, ctx->stream>>>(hits.p, pairInfo.p, pairIds.p, Pn, pairFlags.p, dQIds.p, dQSlotOff.p,
-                                                                          ctx->dLen.p, qLen, filtBits.p, filtPrefix.p, P, score.p, back.p, ord.p,
-                                                                          cands.p, nCand.p, nKept.p);
+                if (!walkAttr) {
+                    FG_CUDA(cudaFuncSetAttribute(chainWalkKernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, walkSmem));
+                    FG_CUDA(cudaFuncSetAttribute(chainWalkKernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, walkSmem));
+                    walkAttr = true;
+                }
+                auto walk = dpMode == 2 ? chainWalkKernel<true> : chainWalkKernel<false>;
+                walk<<<(Pn + 3) / 4, 128, walkSmem, ctx->stream>>>(hits.p, pairInfo.p, pairIds.p, Pn, pairFlags.p, dQIds.p, dQSlotOff.p,
+                                                               ctx->dLen.p, qLen, filtBits.p, filtPrefix.p, P, score.p, back.p, ord.p,
+                                                               cands.p, nCand.p, nKept.p, nRuns.p);
                 checkLaunch(ctx, "chainWalkKernel");
             }
             {

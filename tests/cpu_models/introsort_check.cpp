@@ -11,7 +11,7 @@
 struct VecSink {
     struct T { long f, l; int d; };
     std::vector<T> tasks;
-    void operator()(long f, long l, int d) { tasks.push_back({f, l, d}); }
+    void operator()(long f, long l, int d) { if (d >= 0) tasks.push_back({f, l, d}); }   // d < 0: finished in place (heap sort)
 };
 static long g_small = 0;   // > 0: two-level mode (top pass hands ranges <= g_small to a second pass)
 static int g_table = 0;     // second pass / one-pass sort uses the rank-table partition of the shared-memory kernel
@@ -59,6 +59,38 @@ static bool checkOne(std::vector<fg::Elem> a, const char* what) {
     return true;
 }
 
+// Model of the tie-following hit sort (overlap.cu: rangeIsTieFree): the recursion is only followed into ranges whose
+// sorted ranks contain a duplicated key (inside or across an end); every other range is taken from the STABLE-sorted array.
+// Must equal std::sort of the whole array.
+static long g_followed = 0, g_skipped = 0;
+static void tieFollow(std::vector<fg::Elem>& e, const std::vector<fg::Elem>& stab, const std::vector<unsigned>& tieP, long f, long l, int d) {
+    if (l - f < 2) { if (l - f == 1 && tieP[l] == tieP[f ? f - 1 : 0]) e[f] = stab[f]; return; }
+    if (tieP[l] == tieP[f ? f - 1 : 0]) { ++g_skipped; std::copy(stab.begin() + f, stab.begin() + l, e.begin() + f); return; }
+    ++g_followed;
+    if (l - f <= 16) { fg::seqInsertionSort(e.data(), f, l); return; }
+    if (d == 0) { fg::seqHeapSort(e.data() + f, l - f); return; }
+    --d;
+    fg::seqMedianToFirst(e.data(), f, f + 1, f + (l - f) / 2, l - 1);
+    const long cut = fg::seqUnguardedPartition(e.data(), f + 1, l, f);
+    tieFollow(e, stab, tieP, cut, l, d);
+    tieFollow(e, stab, tieP, f, cut, d);
+}
+static bool checkTieFollow(std::vector<fg::Elem> a, const char* what) {
+    std::vector<fg::Elem> ref = a, stab = a;
+    std::sort(ref.begin(), ref.end(), [](const fg::Elem& x, const fg::Elem& y) { return x.key < y.key; });
+    std::stable_sort(stab.begin(), stab.end(), [](const fg::Elem& x, const fg::Elem& y) { return x.key < y.key; });
+    const long n = (long)a.size();
+    std::vector<unsigned> tieP(n + 1, 0);
+    for (long i = 0; i < n; ++i) tieP[i + 1] = tieP[i] + ((i + 1 < n && stab[i].key == stab[i + 1].key) ? 1u : 0u);
+    tieFollow(a, stab, tieP, 0, n, fg::introsortDepth(n));
+    for (long i = 0; i < n; ++i)
+        if (a[i].key != ref[i].key || a[i].val != ref[i].val) {
+            printf("MISMATCH tie-follow %s n=%ld at %ld: got (%llu,%u) want (%llu,%u)\n", what, n, i, a[i].key, a[i].val, ref[i].key, ref[i].val);
+            return false;
+        }
+    return true;
+}
+
 // median-of-3 killer (Musser) to drive introsort into its heap-sort fallback
 static std::vector<unsigned long long> killer(size_t n) {
     std::vector<unsigned long long> v(n);
@@ -101,6 +133,13 @@ int main(int argc, char** argv) {
         auto a = mk(n, mode, distinct);
         ++arrays; elements += n;
         if (!checkOne(a, "random")) return 1;
+        if (g_small == 0 && g_table == 0) {
+            if (!checkTieFollow(a, "random")) return 1;
+            // mostly distinct keys with a few duplicated ones: the case the fast path is made for
+            auto b = mk(n, 6, 1);
+            for (int dup = 0; dup < 3 && n > 4; ++dup) { const size_t x = rng() % n, y = rng() % n; b[x].key = b[y].key; if (rng() % 2) b[rng() % n].key = b[y].key; }
+            if (!checkTieFollow(b, "few-ties")) return 1;
+        }
     }
     for (size_t n : {17u, 18u, 31u, 32u, 33u, 34u, 48u, 49u, 50u, 63u, 64u, 65u, 66u, 96u, 97u, 128u, 129u, 1000u, 4096u, 100000u}) {
         for (int mode = 0; mode < 7; ++mode) { auto a = mk(n, mode, 5); ++arrays; elements += n; if (!checkOne(a, "edge")) return 1; }
@@ -109,6 +148,7 @@ int main(int argc, char** argv) {
         for (size_t i = 0; i < n; ++i) a[i] = {kv[i], (unsigned)i, 0u};
         ++arrays; elements += n;
         if (!checkOne(a, "killer")) return 1;
+        if (g_small == 0 && g_table == 0) { a[n / 3].key = a[n / 2].key; if (!checkTieFollow(a, "killer+tie")) return 1; }
     }
     // exhaustive small alphabets around the chunk sizes: all arrays over {0,1,2} of length 17..20 is 3^20 -> sample
     for (int t = 0; t < trials * 5; ++t) {
@@ -118,6 +158,6 @@ int main(int argc, char** argv) {
         ++arrays; elements += n;
         if (!checkOne(a, "tiny-alphabet")) return 1;
     }
-    printf("OK %zu %zu heapsorts=%ld\n", arrays, elements, fg::g_heapSortCalls);
+    printf("OK %zu %zu heapsorts=%ld tie-follow ranges followed=%ld skipped=%ld\n", arrays, elements, fg::g_heapSortCalls, g_followed, g_skipped);
     return 0;
 }

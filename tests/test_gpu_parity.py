@@ -74,6 +74,24 @@ def test_clr_small_full_parity(engine, tmp_path):
     assert res == {"hist": 0, "index": 0, "ovlp": 0}
 
 
+@pytest.mark.parametrize("env", [{"FG_HIT_RADIX": "0"}, {"FG_DP_MODE": "0"}, {"FG_DP_MODE": "1"}, {"FG_HIT_RADIX": "0", "FG_DP_MODE": "0"}])
+def test_kernel_variants_agree_with_oracle(engine, tmp_path, monkeypatch, env):
+    """The alternative device paths stay exact: introsort emulation for every query (no radix fast path), match-by-match
+    DP with and without pruned look-back (the default is the run-compressed DP + run-wise chain walk).  CLR with all primary
+    overlaps + kmerMatches, and HiFi."""
+    for name, value in env.items():
+        monkeypatch.setenv(name, value)
+    tmp = str(tmp_path)
+    reads = pu.simulate(os.path.join(tmp, "r.fasta"), genome_len=150000, coverage=15, seed=11)
+    pu.run_oracle(reads, RAW, os.path.join(tmp, "ref"), k=15, extra=["--all-ext", "--keep-aln"])
+    pu.gpu_pipeline(reads, RAW, os.path.join(tmp, "gpu"), k=15, engine=engine, all_ext=True, keep_aln=True)
+    assert _compare(tmp, "variants clr %s" % env, ["ovlp"]) == {"ovlp": 0}
+    reads = pu.simulate(os.path.join(tmp, "h.fasta"), genome_len=150000, coverage=15, mean_len=12000, shape=20, error=0.005, seed=12)
+    pu.run_oracle(reads, HIFI, os.path.join(tmp, "ref"))
+    pu.gpu_pipeline(reads, HIFI, os.path.join(tmp, "gpu"), engine=engine)
+    assert _compare(tmp, "variants hifi %s" % env, ["ovlp"]) == {"ovlp": 0}
+
+
 def test_clr_options(engine, tmp_path):
     """either strand as query, forceLocal, maxOverlaps, all primary overlaps per target"""
     tmp = str(tmp_path)

@@ -28,3 +28,15 @@ def test_shared_memory_variants_equal_std_sort(built, small, variant):
     r = subprocess.run([BIN, "100", str(11 + small + variant), str(small), str(variant)], stdout=subprocess.PIPE, text=True, timeout=600)
     assert r.returncode == 0, r.stdout
     assert r.stdout.startswith("OK")
+
+
+def test_tie_following_emulation_equals_std_sort(built):
+    """The hit sort's fast path (overlap.cu: rangeIsTieFree): introsort is only emulated inside the ranges whose sorted ranks
+    contain a duplicated key; every other range is copied from the stable-sorted array.  The model in introsort_check (run for
+    small = 0) must reproduce std::sort on tie-heavy, few-tie and heap-sort-fallback inputs, and must actually skip ranges."""
+    r = subprocess.run([BIN, "400", "23", "0"], stdout=subprocess.PIPE, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout
+    assert r.stdout.startswith("OK")
+    skipped = int(r.stdout.split("skipped=")[1].split()[0])
+    followed = int(r.stdout.split("followed=")[1].split()[0])
+    assert skipped > 1000 and followed > 1000
