@@ -207,9 +207,10 @@ def main():
     queries = np.arange(2 * lo, 2 * hi, 2, dtype=np.uint32)
     phase_ms, phase_calls, ovl_stats, n_ovl, wall = {}, {}, {}, 0, {}
     n_raw = [0]
+    ovl_len_sample = np.zeros(0)
 
     def step(upload):
-        nonlocal phase_ms, phase_calls, ovl_stats, n_ovl, wall
+        nonlocal phase_ms, phase_calls, ovl_stats, n_ovl, wall, ovl_len_sample
         phase_ms, phase_calls, wall = {}, {}, {}
         t_prev = [time.perf_counter()]
 
@@ -273,6 +274,7 @@ def main():
         grab()
         n_ovl = int(np.count_nonzero(keep))
         n_raw[0] = int(offs[-1])
+        ovl_len_sample = (ov["cur_end"][first:first + 20000] - ov["cur_begin"][first:first + 20000]).astype(np.float64)
         lap("filter")
         return n_ovl
 
@@ -321,39 +323,56 @@ def main():
     h2d = int(packed.nbytes + woff.nbytes + lens.nbytes + 4 * (len(queries) + len(est_ids)))
     d2h = int(72 * n_raw[0] + 8 * (len(queries) + len(est_ids) + 1))
 
-    # roofline of the dominant kernel phase (algorithmic bytes: SURVEY.md §8d, stated in DESIGN.md)
+    # roofline (algorithmic bytes: SURVEY.md §8d stage formulas, assigned to kernels in DESIGN.md §4).  Only phases that
+    # consist of ONE launch of one of our kernels are listed; their durations are CUDA-event times on the library's stream.
     M, O = stats.get("n_hits", 0), n_ovl
     w = 4 if 2 * k <= 32 else 8
     n_k = n_bases - k * n_reads
-    # single-kernel phases only (hit_sort_top is a sequence of per-level launches; its counters are in profiles/)
-    alg = {"hit_sort_small": 24.0 * M, "chain_dp": 12.0 * M + 40.0 * O, "chain_walk": 12.0 * M + 40.0 * O,
+    raw_ovl = n_raw[0]
+    mean_ovl_len = float(np.mean(np.maximum(ovl_len_sample, 1))) if len(ovl_len_sample) else 0.0
+    alg = {"expand": 20.0 * M,                       # K6, per-hit part: 8 B index entry read + 12 B match written
+           "hit_sort_gather": 24.0 * M,              # K7: 12 B record read + 12 B record written, once
+           "hit_sort_small": 24.0 * M,               # K7 (exact path; only the ranges with ties since the radix fast path)
+           "chain_runs": 12.0 * M,                   # K8: one read of the matches
+           "chain_dp": 12.0 * M + 40.0 * O,          # K8
+           "chain_fill": 12.0 * M + 40.0 * O,        # K8: one read of the matches, scores / back pointers written
+           "chain_walk": 12.0 * M + 40.0 * O,        # K8
+           "edit": raw_ovl * 2.0 * mean_ovl_len / 4.0,   # K9: (len_q + len_t) / 4 bytes per overlap
            "select": (w + 5.0) * n_k, "extract": 0.25 * n_bases + w * n_k}
-    names = {"hit_sort_small": "sortSmallKernel", "chain_dp": "chainDpKernel", "chain_walk": "chainWalkKernel", "select": "selectKernel",
-             "extract": "extractKeysKernel"}
-    # DRAM bytes per k-mer hit from the `ncu --set full` captures of round 1 (profiles/README.md:
-    # dram__bytes_read.sum + dram__bytes_write.sum of one launch / hits of that launch)
-    traffic_per_hit = {"hit_sort_small": 32.2, "chain_dp": 40.5, "chain_walk": 20.3}
-    kernel_phases = {p: ms for p, ms in resident_phases.items() if p in alg and alg[p] > 0}
+    names = {"expand": "expandKernel", "hit_sort_gather": "gatherSortedHitsKernel", "hit_sort_small": "sortSmallKernel",
+             "chain_runs": "chainRunsKernel", "chain_dp": "chainRunDpKernel", "chain_fill": "chainFillKernel",
+             "chain_walk": "chainWalkKernel", "edit": "wfaKernel", "select": "selectKernel", "extract": "extractKeysKernel"}
+    bounds = {"edit": "integer issue (O(ND) wavefronts; bytes are negligible by construction)",
+              "chain_dp": "latency / integer issue (sequential scan over run heads)", "chain_walk": "latency (pointer chasing in shared memory)"}
+    # DRAM bytes per k-mer hit from `ncu --set full` captures (profiles/README.md: dram__bytes_read.sum + dram__bytes_write.sum
+    # of one launch / hits of that launch)
+    traffic_per_hit = {"expand": 25.9}
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic_per_hit.json")) as f:
+            traffic_per_hit.update(json.load(f).get(args.workload, {}))
+    except Exception:
+        pass
+    kernel_phases = {p: ms for p, ms in resident_phases.items() if p in alg and alg[p] > 0 and resident_calls.get(p, 1) == 1}
     peak, peak_src = measured_peak()
-    roofline = None
-    if kernel_phases:
-        dom = max(kernel_phases, key=kernel_phases.get)
-        calls = max(1, resident_calls.get(dom, 1))
-        per_launch_ms = kernel_phases[dom] / calls
-        achieved = (alg[dom] / calls) / (per_launch_ms / 1e3) / 1e9
-        roofline = {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": traffic_per_hit[dom] * M / calls if dom in traffic_per_hit else None,
-                    "traffic_source": "bytes per hit measured with ncu --set full (profiles/), scaled to this launch's hits",
-                    "peak_source": peak_src, "launches": calls, "ms_per_launch": per_launch_ms,
-                    "algorithmic_bytes_per_launch": alg[dom] / calls,
-                    "note": "issue-bound integer kernel (80% issue-slot utilisation in ncu); the HBM fraction is low by construction"
-                            if dom == "chain_dp" else None}
+    roofline, roofline_kernels = None, []
+    for ph in sorted(kernel_phases, key=kernel_phases.get, reverse=True):
+        ms_l = kernel_phases[ph]
+        achieved = alg[ph] / (ms_l / 1e3) / 1e9
+        roofline_kernels.append({"bound": "hbm", "kernel": names[ph], "phase": ph, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                                 "frac": achieved / peak, "traffic": traffic_per_hit[ph] * M if ph in traffic_per_hit else None,
+                                 "peak_source": peak_src, "launches": 1, "ms_per_launch": ms_l, "algorithmic_bytes_per_launch": alg[ph],
+                                 "note": bounds.get(ph)})
+    if roofline_kernels:
+        roofline = dict(roofline_kernels[0])
+        roofline["traffic_source"] = "bytes per hit measured with ncu --set full (profiles/), scaled to this launch's hits"
+    lib_ms = resident_phases.get("hit_sort_radix", 0.0)
 
     line = {"metric": "reads/sec through k-mer index + overlap detection", "value": value, "unit": "reads/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_resident, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "int64", "data": "synthetic", "config": config, "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "reads/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": int(launches), "roofline": roofline,
+            "gpu_launches": int(launches), "roofline": roofline, "roofline_kernels": roofline_kernels,
+            "library_ms": {"cub_radix_sort_of_hits": round(lib_ms, 3)},
             "phases_ms": {p: round(v, 3) for p, v in resident_phases.items()},
             "api_wall_ms": {p: round(v, 2) for p, v in resident_wall.items()}, "e2e_api_wall_ms": {p: round(v, 2) for p, v in e2e_wall.items()},
             "work": {"kmer_hits": int(M), "target_groups": int(stats.get("n_pairs", 0)), "dp_pairs": int(stats.get("n_dp_pairs", 0)),

@@ -115,15 +115,16 @@ __global__ void gatherQueryHitOffKernel(const uint64_t* __restrict__ hitOff, con
 // ------------------------------------------------------------------------------------------------
 // SOA = false: Elem records (key = extId << 32 | curPos, val = extPos) into `hits`; with `onlyTied` set, only the tiles of
 //               queries whose flag is set are written (the re-expansion of the queries that need the exact sort).
-// SOA = true:  input of the stable radix sort of the tie-free fast path: keys[h] = (q - qFirst) << (32 + idBits) | extId << 32 | curPos,
-//               vals[h] = extPos.
+// SOA = true:  input of the stable radix sort of the tie-free fast path: keys[h] = (q - qFirst) << idBits | extId (32 bits),
+//               vals[h] = h, payload[h] = curPos << 32 | extPos (32-bit key / 32-bit value pairs are what the library's
+//               radix sort moves fastest; the payload is gathered once, after the sort).
 template <bool SOA>
 __global__ void __launch_bounds__(256) expandKernel(const uint32_t* __restrict__ len, const uint32_t* __restrict__ qlen, const uint2* __restrict__ entries,
                                                     const uint32_t* __restrict__ qIds, const uint64_t* __restrict__ qSlotOff,
                                                     const uint2* __restrict__ qTiles, int k, const uint64_t* __restrict__ hitOff,
                                                     const uint64_t* __restrict__ slotInfo, uint64_t hitBase, Elem* __restrict__ hits,
-                                                    unsigned long long* __restrict__ keys, uint32_t* __restrict__ vals, uint32_t qFirst, int idBits,
-                                                    const uint8_t* __restrict__ onlyTied) {
+                                                    uint32_t* __restrict__ keys, uint32_t* __restrict__ vals, unsigned long long* __restrict__ payload,
+                                                    uint32_t qFirst, int idBits, const uint8_t* __restrict__ onlyTied) {
     __shared__ uint32_t rel[QTILE + 1];
     const uint2 t = qTiles[blockIdx.x];
     if (!SOA && onlyTied && !onlyTied[t.x - qFirst]) return;
@@ -153,8 +154,10 @@ __global__ void __launch_bounds__(256) expandKernel(const uint32_t* __restrict__
         uint32_t extId = e.x; int32_t extPos = (int32_t)e.y;
         if (info & INFO_QRC) { extPos = (int32_t)len[extId >> 1] - extPos - k; extId ^= 1u; }   // vertex_index.h:166-173
         if (SOA) {
-            keys[(h0 - hitBase) + h] = ((unsigned long long)(t.x - qFirst) << (32 + idBits)) | ((unsigned long long)extId << 32) | p;
-            vals[(h0 - hitBase) + h] = (uint32_t)extPos;
+            const uint32_t g = (uint32_t)(h0 - hitBase) + h;
+            keys[g] = ((t.x - qFirst) << idBits) | extId;
+            vals[g] = g;
+            payload[g] = ((unsigned long long)p << 32) | (uint32_t)extPos;
         } else {
             Elem o; o.key = ((unsigned long long)extId << 32) | p; o.val = (unsigned int)extPos; o.aux = 0;
             out[h] = o;
@@ -164,19 +167,30 @@ __global__ void __launch_bounds__(256) expandKernel(const uint32_t* __restrict__
 
 // Tie-free fast path of the hit sort (overlap.cpp:201-204).  std::sort's result is the unique sorted sequence whenever
 // no two elements compare equal, and the expansion emits a query's hits by ascending curPos — so for a query without an
-// (extId, curPos) tie a STABLE sort by extId alone reproduces libstdc++'s output.  This kernel turns the radix-sorted
-// (key, extPos) pairs back into Elem records and flags every query that does contain a tie (two adjacent equal keys):
-// those queries are expanded again and go through the exact introsort emulation.
-__global__ void __launch_bounds__(256) rebuildHitsKernel(const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ vals, uint64_t M,
-                                                         int idBits, Elem* __restrict__ hits, uint8_t* __restrict__ qTie, uint8_t* __restrict__ tieFlag) {
-    const unsigned long long idMask = (1ULL << idBits) - 1ULL;
-    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < M; i += (uint64_t)gridDim.x * blockDim.x) {
-        const unsigned long long kk = keys[i];
-        Elem o; o.key = (((kk >> 32) & idMask) << 32) | (kk & 0xffffffffULL); o.val = vals[i]; o.aux = 0;
-        hits[i] = o;
-        const bool tie = i + 1 < M && keys[i + 1] == kk;
-        tieFlag[i] = tie;   // input of the prefix count that lets the exact sort skip tie-free ranges
-        if (tie) qTie[kk >> (32 + idBits)] = 1;
+// (extId, curPos) tie a STABLE sort by extId alone reproduces libstdc++'s output.  This kernel gathers the radix-sorted
+// hits into Elem records and flags the ties (two adjacent elements with equal query, extId and curPos): the queries that
+// contain one are expanded again and go through the exact introsort emulation.
+__global__ void __launch_bounds__(256) gatherSortedHitsKernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals,
+                                                              const unsigned long long* __restrict__ payload, uint64_t M, int idBits,
+                                                              Elem* __restrict__ hits, uint8_t* __restrict__ qTie, uint8_t* __restrict__ tieFlag) {
+    const uint32_t idMask = (1u << idBits) - 1u;
+    const int lane = threadIdx.x & 31;
+    // whole warps walk the array together (the tie test looks at the neighbouring lane)
+    const uint64_t warpStride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i0 = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) - lane; i0 < M; i0 += warpStride) {
+        const uint64_t i = i0 + lane;
+        uint32_t kk = 0; unsigned long long pl = 0;
+        if (i < M) { kk = keys[i]; pl = payload[vals[i]]; }
+        uint32_t nk = __shfl_down_sync(0xffffffffu, kk, 1);
+        uint32_t np = __shfl_down_sync(0xffffffffu, (uint32_t)(pl >> 32), 1);
+        if (lane == 31 && i + 1 < M) { nk = keys[i + 1]; np = (uint32_t)(payload[vals[i + 1]] >> 32); }
+        if (i < M) {
+            Elem o; o.key = ((unsigned long long)(kk & idMask) << 32) | (pl >> 32); o.val = (unsigned int)pl; o.aux = 0;
+            hits[i] = o;
+            const bool tie = i + 1 < M && nk == kk && np == (uint32_t)(pl >> 32);
+            tieFlag[i] = tie;   // input of the prefix count that lets the exact sort skip tie-free ranges
+            if (tie) qTie[kk >> idBits] = 1;
+        }
     }
 }
 
@@ -445,6 +459,7 @@ __device__ __forceinline__ uint32_t filtRank(const uint32_t* __restrict__ filtBi
 
 // pair flags
 static constexpr uint32_t PAIR_EXTSORTED = 1u;
+static constexpr uint32_t PAIR_PRESORTED = 2u;   // scores increase strictly with the match index: the score order is n-1, n-2, ..., 0
 
 // (a) per pair: decide the DP axis (overlap.cpp:269), re-key the elements of ext-sorted pairs by extPos and
 // append them to the list of segments that need the std::sort-exact re-sort (:272-274)
@@ -926,9 +941,9 @@ __global__ void __launch_bounds__(128) chainRunDpKernel(const Elem* __restrict__
 
 // scores, back pointers and the input of the score sort (:331-334) of every match.  When the scores of a pair increase
 // strictly with the match index, their descending order is the unique sorted sequence of distinct keys — std::sort's
-// output — so it is written directly (reversed) and the pair is taken off the list of segments to sort.
+// output is n-1, n-2, ..., 0 — so the pair is flagged PAIR_PRESORTED and taken off the list of segments to sort.
 __global__ void __launch_bounds__(256) chainFillKernel(const Elem* __restrict__ hits, const PairInfo* __restrict__ pairs, const uint32_t* __restrict__ pairIds,
-                                                       uint32_t nPairs, const uint32_t* __restrict__ pairFlags, const Run* __restrict__ runs,
+                                                       uint32_t nPairs, uint32_t* __restrict__ pairFlags, const Run* __restrict__ runs,
                                                        int32_t* __restrict__ score, int32_t* __restrict__ back, Elem* __restrict__ ord,
                                                        Seg* __restrict__ allSegs, unsigned long long* __restrict__ nPresorted) {
     const uint32_t w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -958,14 +973,14 @@ __global__ void __launch_bounds__(256) chainFillKernel(const Elem* __restrict__ 
         carry = __shfl_sync(0xffffffffu, s, 31);
     }
     incr = __all_sync(0xffffffffu, incr);
+    if (incr) {   // the chain walk takes the order n-1 .. 0 from the flag: nothing to write, nothing to sort
+        if (lane == 0) { pairFlags[w] |= PAIR_PRESORTED; allSegs[w].n = 0; atomicAdd(nPresorted, 1ULL); }
+        return;
+    }
     for (int32_t i0 = 0; i0 < n; i0 += 32) {
         const int32_t i = i0 + lane;
-        if (i < n) {
-            Elem t; t.key = (unsigned long long)(0x7fffffff - sc[i]); t.val = (unsigned int)i; t.aux = 0;
-            od[incr ? n - 1 - i : i] = t;
-        }
+        if (i < n) { Elem t; t.key = (unsigned long long)(0x7fffffff - sc[i]); t.val = (unsigned int)i; t.aux = 0; od[i] = t; }
     }
-    if (lane == 0 && incr) { allSegs[w].n = 0; atomicAdd(nPresorted, 1ULL); }
 }
 
 __global__ void __launch_bounds__(256) runCountKeyKernel(const uint32_t* __restrict__ nRuns, uint32_t nPairs, uint32_t* __restrict__ keys,
@@ -1026,6 +1041,7 @@ __global__ void __launch_bounds__(128) chainWalkKernel(const Elem* __restrict__ 
     // back pointers: delta = pos - back[pos] (>= 1), 0 = none.  n <= WALK_CAP < 65536, so a delta fits 16 bits.
     int32_t* bkG = back + pi.start;
     unsigned short* sb = reinterpret_cast<unsigned short*>(smemRaw) + (threadIdx.x >> 5) * WALK_CAP;
+    const bool presorted = RUNS && (pairFlags[w] & PAIR_PRESORTED);
     const int32_t R = RUNS ? (int32_t)nRuns[w] : 0;
     const bool byRuns = RUNS && R <= RUN_CAP && n <= 65535;
     const bool staged = !byRuns && n <= WALK_CAP;
@@ -1054,7 +1070,7 @@ __global__ void __launch_bounds__(128) chainWalkKernel(const Elem* __restrict__ 
     uint32_t nCand = 0;   // meaningful in lane 0
     for (int32_t t0 = 0; t0 < n; t0 += 32) {
         const int32_t t = t0 + lane;
-        const int32_t cs = t < n ? (int32_t)od[t].val : 0;
+        const int32_t cs = t < n ? (presorted ? n - 1 - t : (int32_t)od[t].val) : 0;
         const int32_t cr = (byRuns && t < n) ? runOf(cs) : 0;
         uint32_t m = __ballot_sync(0xffffffffu, t < n && hasBack(cs, cr));
         while (m) {
@@ -1251,7 +1267,9 @@ static void sortSegments(fg_ctx* ctx, Elem* arr, const Seg* dSegs, uint32_t* dCo
             if (level == 0) firstElems = elems;
             // tail: little work left in unevenly split ranges -> finish each range with one warp instead of paying a
             // launch + host round trip per remaining level
-            if (level >= 4 && ((uint64_t)elems * 16 < firstElems || level >= 48)) {
+            // ... and a handful of short ranges from the start (the few pairs whose matches are not presorted): the same
+            const bool fewShort = level == 0 && cnt <= 8192 && (uint64_t)elems <= (uint64_t)cnt * 4096;
+            if (fewShort || (level >= 4 && ((uint64_t)elems * 16 < firstElems || level >= 48))) {
                 sortTailKernel<<<(cnt + 3) / 4, 128, 0, ctx->stream>>>(arr, in, nIn, ws.capBig, ws.small.p, dCounters + 1, ws.capSmall, smallN, outArr, tieP);
                 checkLaunch(ctx, "sortTailKernel");
                 break;
@@ -1371,7 +1389,7 @@ static void overlapsChunk(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, ui
     if (!hQTiles.empty()) {
         if (nQSlots >= (1ULL << 31)) throw Error(FG_ERR_ARG, "query batch too large (>= 2^31 k-mer slots); split the call");
         {
-            PhaseTimer pt(ctx, "gather");
+            PhaseTimer pt(ctx, "lookup");
             queryLookupKernel<<<(unsigned)hQTiles.size(), 256, 0, ctx->stream>>>(qSeq, qWordOff, qLen, ctx->dSlotOff.p,
                                                                                 ctx->dSelBits.p, dQIds.p, dQSlotOff.p, dQTiles.p, k,
                                                                                 P.sameSet, ctx->indexTable, hitCnt.p, slotInfo.p, filtBits.p);
@@ -1430,30 +1448,34 @@ static void overlapsChunk(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, ui
         while (((uint64_t)nq) >> qBits) ++qBits;
         const bool radixPath = envInt("FG_HIT_RADIX", 1, 0, 1) != 0 && idBits + qBits <= 32;
         if (radixPath) {
-            // scratch: the arrays of the later chaining stages (ord = 16 B, score / back = 4 B per hit) are free until the DP
-            unsigned long long* keyA = reinterpret_cast<unsigned long long*>(ord.p);
-            unsigned long long* keyB = keyA + M;
-            uint32_t* valA = reinterpret_cast<uint32_t*>(score.p);
-            uint32_t* valB = reinterpret_cast<uint32_t*>(back.p);
+            // scratch: the arrays of the later chaining stages are free until the DP (ord = 16 B per hit: the two key and the two
+            // value buffers; the second half of the 32-B candidate slots: the payload; its first half is the scratch copy below)
+            uint32_t* keyA = reinterpret_cast<uint32_t*>(ord.p);
+            uint32_t* keyB = keyA + M;
+            uint32_t* valA = keyB + M;
+            uint32_t* valB = valA + M;
+            unsigned long long* payload = reinterpret_cast<unsigned long long*>(reinterpret_cast<Elem*>(cands.p) + M);
             qTie.ensure(nq);
             FG_CUDA(cudaMemsetAsync(qTie.p, 0, nq, ctx->stream));
             {
-                PhaseTimer pt(ctx, "gather");
+                PhaseTimer pt(ctx, "expand");
                 expandKernel<true><<<(unsigned)(tB - tA), 256, 0, ctx->stream>>>(ctx->dLen.p, qLen, ctx->dEntries.p, dQIds.p, dQSlotOff.p, dQTiles.p + tA, k,
-                                                                                hitOff.p, slotInfo.p, hitBase, nullptr, keyA, valA, qa, idBits, nullptr);
+                                                                                hitOff.p, slotInfo.p, hitBase, nullptr, keyA, valA, payload, qa, idBits, nullptr);
                 checkLaunch(ctx, "expandKernel");
             }
+            cub::DoubleBuffer<uint32_t> dk(keyA, keyB), dv(valA, valB);
             {
                 PhaseTimer pt(ctx, "hit_sort_radix");
-                cub::DoubleBuffer<unsigned long long> dk(keyA, keyB);
-                cub::DoubleBuffer<uint32_t> dv(valA, valB);
                 size_t tb = 0;
-                FG_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, dk, dv, (int)M, 32, 32 + idBits + qBits, ctx->stream));
+                FG_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, dk, dv, (int)M, 0, idBits + qBits, ctx->stream));
                 DevBuf<char> tmpS(tb);
-                FG_CUDA(cub::DeviceRadixSort::SortPairs(tmpS.p, tb, dk, dv, (int)M, 32, 32 + idBits + qBits, ctx->stream));
+                FG_CUDA(cub::DeviceRadixSort::SortPairs(tmpS.p, tb, dk, dv, (int)M, 0, idBits + qBits, ctx->stream));
                 ctx->launches += 2 + (idBits + qBits + 7) / 8;
-                rebuildHitsKernel<<<gridFor(M, 256, 16), 256, 0, ctx->stream>>>(dk.Current(), dv.Current(), M, idBits, hits.p, qTie.p, flags.p);
-                checkLaunch(ctx, "rebuildHitsKernel");
+            }
+            {
+                PhaseTimer pt(ctx, "hit_sort_gather");
+                gatherSortedHitsKernel<<<gridFor(M, 256, 16), 256, 0, ctx->stream>>>(dk.Current(), dv.Current(), payload, M, idBits, hits.p, qTie.p, flags.p);
+                checkLaunch(ctx, "gatherSortedHitsKernel");
             }
             querySegsKernel<<<(nq + 255) / 256, 256, 0, ctx->stream>>>(dQHitOff.p, qa, nq, hitBase, segsQ.p, qTie.p, counters.p + 24);
             checkLaunch(ctx, "querySegsKernel");
@@ -1477,18 +1499,18 @@ static void overlapsChunk(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, ui
                     ++ctx->launches;
                 }
                 {
-                    PhaseTimer pt(ctx, "gather");
+                    PhaseTimer pt(ctx, "hit_sort_top");   // re-expansion of the queries with ties
                     expandKernel<false><<<(unsigned)(tB - tA), 256, 0, ctx->stream>>>(ctx->dLen.p, qLen, ctx->dEntries.p, dQIds.p, dQSlotOff.p, dQTiles.p + tA, k,
-                                                                                     hitOff.p, slotInfo.p, hitBase, scratch, nullptr, nullptr, qa, 0, qTie.p);
+                                                                                     hitOff.p, slotInfo.p, hitBase, scratch, nullptr, nullptr, nullptr, qa, 0, qTie.p);
                     checkLaunch(ctx, "expandKernel");
                 }
                 sortSegments(ctx, scratch, segsQ.p, counters.p, nq, ws, "hit_sort_top", "hit_sort_small", sortCfgHits(), hits.p, tieP);
             }
         } else {
             {
-                PhaseTimer pt(ctx, "gather");
+                PhaseTimer pt(ctx, "expand");
                 expandKernel<false><<<(unsigned)(tB - tA), 256, 0, ctx->stream>>>(ctx->dLen.p, qLen, ctx->dEntries.p, dQIds.p, dQSlotOff.p, dQTiles.p + tA, k,
-                                                                                 hitOff.p, slotInfo.p, hitBase, hits.p, nullptr, nullptr, qa, 0, nullptr);
+                                                                                 hitOff.p, slotInfo.p, hitBase, hits.p, nullptr, nullptr, nullptr, qa, 0, nullptr);
                 checkLaunch(ctx, "expandKernel");
             }
             querySegsKernel<<<(nq + 255) / 256, 256, 0, ctx->stream>>>(dQHitOff.p, qa, nq, hitBase, segsQ.p, nullptr, nullptr);
@@ -1535,35 +1557,44 @@ static void overlapsChunk(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, ui
             }
             sortSegments(ctx, hits.p, extSegs.p, counters.p + 8, Pn, ws, "chain_extsort_top", "chain_extsort_small", sortCfgPairs());
             {
-                PhaseTimer pt(ctx, "chain_dp");
-                // FG_DP_MODE: 2 = run-compressed DP (default), 1 = match-by-match with pruned look-back, 0 = match-by-match
                 // visit the pairs by decreasing size: two pairs share a warp, 8 a block
                 DevBuf<uint32_t> szKeyA(Pn), szKeyB(Pn), ordA(Pn), ordB(Pn);
                 Run* runs = reinterpret_cast<Run*>(cands.p);
                 if (dpMode == 2) {
+                    PhaseTimer pt(ctx, "chain_runs");
                     nRuns.alloc(Pn);
                     chainRunsKernel<<<(Pn + 7) / 8, 256, 0, ctx->stream>>>(hits.p, pairInfo.p, pairIds.p, Pn, pairFlags.p, k, runs, back.p, nRuns.p);
                     checkLaunch(ctx, "chainRunsKernel");
-                    runCountKeyKernel<<<(Pn + 255) / 256, 256, 0, ctx->stream>>>(nRuns.p, Pn, szKeyA.p, ordA.p);
-                    checkLaunch(ctx, "runCountKeyKernel");
-                } else {
-                    pairSizeKeyKernel<<<(Pn + 255) / 256, 256, 0, ctx->stream>>>(pairInfo.p, pairIds.p, Pn, szKeyA.p, ordA.p);
-                    checkLaunch(ctx, "pairSizeKeyKernel");
                 }
                 cub::DoubleBuffer<uint32_t> dk(szKeyA.p, szKeyB.p), dv(ordA.p, ordB.p);
-                size_t tb = 0;
-                FG_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, dk, dv, (int)Pn, 0, 32, ctx->stream));
-                DevBuf<char> tmpS(tb);
-                FG_CUDA(cub::DeviceRadixSort::SortPairs(tmpS.p, tb, dk, dv, (int)Pn, 0, 32, ctx->stream));
-                ctx->launches += 5;
+                {
+                    PhaseTimer pt(ctx, "chain_order");
+                    if (dpMode == 2) {
+                        runCountKeyKernel<<<(Pn + 255) / 256, 256, 0, ctx->stream>>>(nRuns.p, Pn, szKeyA.p, ordA.p);
+                        checkLaunch(ctx, "runCountKeyKernel");
+                    } else {
+                        pairSizeKeyKernel<<<(Pn + 255) / 256, 256, 0, ctx->stream>>>(pairInfo.p, pairIds.p, Pn, szKeyA.p, ordA.p);
+                        checkLaunch(ctx, "pairSizeKeyKernel");
+                    }
+                    size_t tb = 0;
+                    FG_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, dk, dv, (int)Pn, 0, 32, ctx->stream));
+                    DevBuf<char> tmpS(tb);
+                    FG_CUDA(cub::DeviceRadixSort::SortPairs(tmpS.p, tb, dk, dv, (int)Pn, 0, 32, ctx->stream));
+                    ctx->launches += 5;
+                }
                 if (dpMode == 2) {
-                    chainRunDpKernel<<<(Pn + 7) / 8, 128, 0, ctx->stream>>>(hits.p, pairInfo.p, pairIds.p, dv.Current(), Pn, pairFlags.p, nRuns.p, P, runs,
-                                                                           dCells.p);   // whole warps: no early exit inside
-                    checkLaunch(ctx, "chainRunDpKernel");
+                    {
+                        PhaseTimer pt(ctx, "chain_dp");
+                        chainRunDpKernel<<<(Pn + 7) / 8, 128, 0, ctx->stream>>>(hits.p, pairInfo.p, pairIds.p, dv.Current(), Pn, pairFlags.p, nRuns.p, P, runs,
+                                                                               dCells.p);   // whole warps: no early exit inside
+                        checkLaunch(ctx, "chainRunDpKernel");
+                    }
+                    PhaseTimer pt(ctx, "chain_fill");
                     chainFillKernel<<<(Pn + 7) / 8, 256, 0, ctx->stream>>>(hits.p, pairInfo.p, pairIds.p, Pn, pairFlags.p, runs, score.p, back.p, ord.p,
                                                                           allSegs.p, dCells.p + 1);
                     checkLaunch(ctx, "chainFillKernel");
                 } else {
+                    PhaseTimer pt(ctx, "chain_dp");
                     auto dp = dpMode == 1 ? chainDpPrunedKernel : chainDpKernel;
                     dp<<<(Pn + 7) / 8, 128, 0, ctx->stream>>>(hits.p, pairInfo.p, pairIds.p, dv.Current(), Pn, pairFlags.p, P, score.p, back.p, ord.p,
                                                              dCells.p);   // whole warps: no early exit inside
