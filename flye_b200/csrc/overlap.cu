@@ -113,21 +113,23 @@ __global__ void gatherQueryHitOffKernel(const uint64_t* __restrict__ hitOff, con
 // Q3: expansion.  One CTA per query tile; the tile's slot offsets are staged in shared memory and every
 // output record finds its slot with a shared-memory binary search, so global writes are coalesced.
 // ------------------------------------------------------------------------------------------------
-// SOA = false: Elem records (key = extId << 32 | curPos, val = extPos) into `hits`; with `onlyTied` set, only the tiles of
-//               queries whose flag is set are written (the re-expansion of the queries that need the exact sort).
-// SOA = true:  input of the stable radix sort of the tie-free fast path: keys[h] = (q - qFirst) << idBits | extId (32 bits),
-//               vals[h] = h, payload[h] = curPos << 32 | extPos (32-bit key / 32-bit value pairs are what the library's
-//               radix sort moves fastest; the payload is gathered once, after the sort).
-template <bool SOA>
+// MODE 0: Elem records (key = extId << 32 | curPos, val = extPos) into `hits`; with `onlyTied` set, only the tiles of
+//         queries whose flag is set are written (the re-expansion of the queries that need the exact sort).
+// MODE 1: input of the library's radix sort (fallback of the tie-free fast path): keys[h] = (q - qFirst) << idBits | extId,
+//         vals[h] = h, payload[h] = curPos << 32 | extPos.
+// MODE 2: input of segRadixSortKernel: packed[h] = extId << 2*posBits | curPos << posBits | extPos, and the tie test: two hits
+//         of one query position on the same target (neighbours in the position list) flag the query in qTie.
+template <int MODE>
 __global__ void __launch_bounds__(256) expandKernel(const uint32_t* __restrict__ len, const uint32_t* __restrict__ qlen, const uint2* __restrict__ entries,
                                                     const uint32_t* __restrict__ qIds, const uint64_t* __restrict__ qSlotOff,
                                                     const uint2* __restrict__ qTiles, int k, const uint64_t* __restrict__ hitOff,
                                                     const uint64_t* __restrict__ slotInfo, uint64_t hitBase, Elem* __restrict__ hits,
                                                     uint32_t* __restrict__ keys, uint32_t* __restrict__ vals, unsigned long long* __restrict__ payload,
-                                                    uint32_t qFirst, int idBits, const uint8_t* __restrict__ onlyTied) {
+                                                    uint32_t qFirst, int idBits, const uint8_t* __restrict__ onlyTied, int posBits,
+                                                    uint8_t* __restrict__ qTie) {
     __shared__ uint32_t rel[QTILE + 1];
     const uint2 t = qTiles[blockIdx.x];
-    if (!SOA && onlyTied && !onlyTied[t.x - qFirst]) return;
+    if (MODE == 0 && onlyTied && !onlyTied[t.x - qFirst]) return;
     const uint32_t id = qIds[t.x], r = id >> 1;
     const bool strand = id & 1;
     const uint32_t L = qlen[r], n = L - k;
@@ -153,11 +155,22 @@ __global__ void __launch_bounds__(256) expandKernel(const uint32_t* __restrict__
         }
         uint32_t extId = e.x; int32_t extPos = (int32_t)e.y;
         if (info & INFO_QRC) { extPos = (int32_t)len[extId >> 1] - extPos - k; extId ^= 1u; }   // vertex_index.h:166-173
-        if (SOA) {
+        if (MODE == 1) {
             const uint32_t g = (uint32_t)(h0 - hitBase) + h;
             keys[g] = ((t.x - qFirst) << idBits) | extId;
             vals[g] = g;
             payload[g] = ((unsigned long long)p << 32) | (uint32_t)extPos;
+        } else if (MODE == 2) {
+            payload[(h0 - hitBase) + h] = ((unsigned long long)extId << (2 * posBits)) | ((unsigned long long)p << posBits) | (uint32_t)extPos;
+            if (h + 1 < rel[s + 1]) {   // the next hit comes from the same query position: same target = an (extId, curPos) tie
+                uint2 e2 = entries[first + j + 1];
+                if (info & INFO_SELF) {
+                    const uint32_t q = strand ? (L - k - p) : p;
+                    const uint64_t self = (info & INFO_FWDRC) ? (((uint64_t)(2 * r + 1) << 32) | (L - q - k)) : (((uint64_t)(2 * r) << 32) | q);
+                    if ((((uint64_t)e2.x << 32) | e2.y) >= self) e2 = entries[first + j + 2];
+                }
+                if (e2.x == e.x) qTie[t.x - qFirst] = 1;
+            }
         } else {
             Elem o; o.key = ((unsigned long long)extId << 32) | p; o.val = (unsigned int)extPos; o.aux = 0;
             out[h] = o;
@@ -192,6 +205,105 @@ __global__ void __launch_bounds__(256) gatherSortedHitsKernel(const uint32_t* __
             if (tie) qTie[kk >> idBits] = 1;
         }
     }
+}
+
+// Segmented stable LSD radix sort of the packed hits by extId, one CTA per query (its hits are one contiguous segment,
+// already in curPos order).  8-bit digits; every warp owns a contiguous chunk of the segment, so (warp, digit) counts turn
+// into private running offsets and the scatter needs no synchronisation between warps: a warp moves 32 consecutive
+// elements per step, ranks equal digits with match.any, and keeps the order of equal digits (stable).  The counts of the
+// next pass are accumulated while scattering (the destination tells the owning warp).  The segment ping-pongs between two
+// buffers (L2 resident for all but the longest reads); the last pass writes the Elem records.
+static constexpr int SEG_WARPS = 16;
+__global__ void __launch_bounds__(SEG_WARPS * 32, 3) segRadixSortKernel(unsigned long long* bufA, unsigned long long* bufB,
+                                                                         const uint64_t* __restrict__ qHitOff, uint32_t qFirst, uint64_t hitBase,
+                                                                         int posBits, int nPass, Elem* __restrict__ hits) {
+    __shared__ uint32_t hist[2][SEG_WARPS][256];
+    __shared__ uint32_t base[256];
+    const uint64_t start = qHitOff[qFirst + blockIdx.x] - hitBase;
+    const uint32_t n = (uint32_t)(qHitOff[qFirst + blockIdx.x + 1] - qHitOff[qFirst + blockIdx.x]);
+    if (n == 0) return;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t C = (((n + SEG_WARPS - 1) / SEG_WARPS) + 31u) & ~31u;   // elements per warp, whole steps
+    const uint32_t wBeg = min(n, w * C), wEnd = min(n, wBeg + C);
+    const unsigned long long* src = bufA + start;
+    unsigned long long* dst = bufB + start;
+    const int idShift = 2 * posBits;
+    const unsigned long long posMask = (1ULL << posBits) - 1ULL;
+    uint32_t (*cur)[256] = hist[0];
+    uint32_t (*nxt)[256] = hist[1];
+    for (int i = threadIdx.x; i < SEG_WARPS * 256; i += blockDim.x) (&cur[0][0])[i] = 0u;
+    __syncthreads();
+    for (uint32_t i0 = wBeg; i0 < wEnd; i0 += 32) {   // counts of the first pass
+        const uint32_t i = i0 + lane;
+        const bool act = i < wEnd;
+        const uint32_t am = __ballot_sync(0xffffffffu, act);
+        if (act) {
+            const uint32_t d = (uint32_t)(src[i] >> idShift) & 255u;
+            const uint32_t peers = __match_any_sync(am, d);
+            if ((peers & ((1u << lane) - 1u)) == 0u) cur[w][d] += __popc(peers);
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    for (int pass = 0; pass < nPass; ++pass) {
+        const bool last = pass == nPass - 1;
+        const int sh = idShift + 8 * pass;
+        // (warp, digit) counts -> offsets: exclusive over the warps of a digit, then over the digits
+        uint32_t tot = 0;
+        if (threadIdx.x < 256) {
+            for (int v = 0; v < SEG_WARPS; ++v) { const uint32_t c = cur[v][threadIdx.x]; cur[v][threadIdx.x] = tot; tot += c; }
+        }
+        if (threadIdx.x < 256) {   // warps 0..7: block-wide exclusive scan of the 256 digit totals
+            uint32_t inc = tot;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
+            base[threadIdx.x] = inc - tot;               // exclusive inside the warp
+            if (lane == 31) nxt[0][w] = inc;             // warp totals, parked in the other histogram for a moment
+        }
+        __syncthreads();
+        if (threadIdx.x < 256) {
+            uint32_t add = 0;
+            for (int v = 0; v < w; ++v) add += nxt[0][v];
+            base[threadIdx.x] += add;
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < SEG_WARPS * 256; i += blockDim.x) (&nxt[0][0])[i] = 0u;
+        __syncthreads();
+        for (uint32_t i0 = wBeg; i0 < wEnd; i0 += 32) {
+            const uint32_t i = i0 + lane;
+            const bool act = i < wEnd;
+            const uint32_t am = __ballot_sync(0xffffffffu, act);
+            if (act) {
+                const unsigned long long x = src[i];
+                const uint32_t d = (uint32_t)(x >> sh) & 255u;
+                const uint32_t peers = __match_any_sync(am, d);
+                const uint32_t o = base[d] + cur[w][d];
+                __syncwarp(am);
+                if ((peers & ((1u << lane) - 1u)) == 0u) cur[w][d] += __popc(peers);
+                const uint32_t pos = o + __popc(peers & ((1u << lane) - 1u));
+                if (!last) {
+                    dst[pos] = x;
+                    atomicAdd(&nxt[pos / C][(uint32_t)(x >> (sh + 8)) & 255u], 1u);
+                } else {
+                    Elem e; e.key = ((x >> idShift) << 32) | ((x >> posBits) & posMask); e.val = (unsigned int)(x & posMask); e.aux = 0;
+                    hits[start + pos] = e;
+                }
+            }
+            __syncwarp();
+        }
+        __syncthreads();
+        const unsigned long long* t = dst; dst = const_cast<unsigned long long*>(src); src = t;
+        uint32_t (*th)[256] = cur; cur = nxt; nxt = th;
+    }
+}
+
+// tie flags (input of the prefix count of rangeIsTieFree) for the queries that contain ties; all other flags stay 0
+__global__ void __launch_bounds__(256) tieFlagKernel(const Elem* __restrict__ hits, const uint64_t* __restrict__ qHitOff, uint32_t qFirst, uint64_t hitBase,
+                                                     const uint8_t* __restrict__ qTie, uint8_t* __restrict__ tieFlag) {
+    if (!qTie[blockIdx.x]) return;
+    const uint64_t start = qHitOff[qFirst + blockIdx.x] - hitBase;
+    const uint32_t n = (uint32_t)(qHitOff[qFirst + blockIdx.x + 1] - qHitOff[qFirst + blockIdx.x]);
+    for (uint32_t i = threadIdx.x; i + 1 < n; i += blockDim.x) tieFlag[start + i] = hits[start + i].key == hits[start + i + 1].key;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -245,10 +357,16 @@ __device__ __forceinline__ void emitRange(uint32_t start, uint32_t n, int depth,
 // every segment becomes one task: a "big" one (partitioned level by level in global memory) or a "small" one
 __global__ void __launch_bounds__(256) sortSeedKernel(const Seg* __restrict__ segs, const uint32_t* __restrict__ nSegsPtr, SortTask* __restrict__ big,
                                                       uint32_t* __restrict__ nBig, uint32_t capBig, SortTask* __restrict__ small,
-                                                      uint32_t* __restrict__ nSmall, uint32_t capSmall, uint32_t smallN, const uint32_t* __restrict__ tieP) {
+                                                      uint32_t* __restrict__ nSmall, uint32_t capSmall, uint32_t smallN, const uint32_t* __restrict__ tieP,
+                                                      SortTask* __restrict__ huge, uint32_t* __restrict__ nHuge, uint32_t capHuge, uint32_t hugeMin) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= *nSegsPtr) return;
     const Seg sg = segs[i];
+    if (huge && sg.n > hugeMin && !rangeIsTieFree(tieP, sg.start, sg.n)) {
+        const uint32_t q = atomicAdd(nHuge, 1u);
+        if (q < capHuge) { SortTask k; k.start = sg.start; k.n = sg.n; k.depth = introsortDepth((long)sg.n); huge[q] = k; }
+        return;
+    }
     emitRange(sg.start, sg.n, introsortDepth((long)sg.n), big, nBig, capBig, small, nSmall, capSmall, smallN, tieP);
 }
 
@@ -280,6 +398,120 @@ __global__ void __launch_bounds__(128) sortLevelKernel(Elem* __restrict__ arr, c
     if (laneId() == 0) {
         emitRange(t.start, (uint32_t)cut, t.depth - 1, out, nOut, capBig, small, nSmall, capSmall, smallN, tieP);
         emitRange(t.start + (uint32_t)cut, t.n - (uint32_t)cut, t.depth - 1, out, nOut, capBig, small, nSmall, capSmall, smallN, tieP);
+    }
+}
+
+// One partition step of a HUGE range by a whole CTA (16 warps).  A warp that streams a long range alone needs ~27 ns per
+// element (every 32-element chunk waits for its own loads and for the pairing of its stops), and the level-synchronous
+// recursion can only move on when the longest range of a level is done — with a few long reads to sort that is the whole
+// cost.  Here the same partition (see introsort_warp.cuh: L-stops ascending = positions with key >= pivot, R-stops
+// descending = positions with key <= pivot, swap the pairs (L_m, R_m) with L_m < R_m, cut = min(L_s, R_{s-1})) is done in
+// three data-parallel phases: (1) every warp lists the L- and R-stops of its slice (positions, into scratch), (2) the
+// number s of swapped pairs is found by a 512-way search over the monotone predicate L_m < R_m, (3) the s swaps are done
+// by all threads.  Result and permutation are identical to the sequential loop.
+static constexpr int HUGE_WARPS = 16;
+struct StopLists {
+    const uint32_t* Lpos; const uint32_t* Rpos; const uint32_t* geBefore; const uint32_t* leAfter; const uint32_t* leCnt;
+    uint32_t sliceLen;
+    // position (relative to the range) of the m-th L-stop / of the m-th R-stop counted from the right end
+    __device__ __forceinline__ uint32_t L(uint32_t m) const {
+        int w = 0;
+#pragma unroll
+        for (int v = 1; v < HUGE_WARPS; ++v) w += geBefore[v] <= m;
+        return Lpos[1u + w * sliceLen + (m - geBefore[w])];
+    }
+    __device__ __forceinline__ uint32_t R(uint32_t m) const {
+        int w = HUGE_WARPS - 1;
+#pragma unroll
+        for (int v = HUGE_WARPS - 2; v >= 0; --v) w -= leAfter[v] <= m;
+        return Rpos[1u + w * sliceLen + (leCnt[w] - 1u - (m - leAfter[w]))];
+    }
+};
+
+__global__ void __launch_bounds__(HUGE_WARPS * 32) sortHugeKernel(Elem* __restrict__ arr, const SortTask* __restrict__ in, const uint32_t* __restrict__ nInPtr,
+                                                                  uint32_t capHuge, SortTask* __restrict__ outHuge, uint32_t* __restrict__ nOutHuge, uint32_t hugeMin,
+                                                                  SortTask* __restrict__ big, uint32_t* __restrict__ nBig, uint32_t capBig,
+                                                                  SortTask* __restrict__ small, uint32_t* __restrict__ nSmall, uint32_t capSmall, uint32_t smallN,
+                                                                  Elem* outArr, const uint32_t* __restrict__ tieP, uint32_t* __restrict__ scratchL,
+                                                                  uint32_t* __restrict__ scratchR) {
+    __shared__ uint32_t geCnt[HUGE_WARPS], leCnt[HUGE_WARPS], geBefore[HUGE_WARPS + 1], leAfter[HUGE_WARPS + 1];
+    __shared__ uint32_t sLo, sHi, sS;
+    if (blockIdx.x >= min(*nInPtr, capHuge)) return;
+    const SortTask t = in[blockIdx.x];
+    Elem* a = arr + t.start;
+    const uint32_t n = t.n;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (t.depth == 0) {   // stl_algo.h:1925-1929 (not expected for ranges of this size)
+        if (threadIdx.x == 0) seqHeapSort(a, (long)n);
+        __syncthreads();
+        if (outArr != arr) for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) outArr[t.start + i] = a[i];
+        return;
+    }
+    if (threadIdx.x == 0) seqMedianToFirst(a, 0, 1, (long)(n / 2), (long)n - 1);
+    __syncthreads();
+    const unsigned long long p = a[0].key;
+    uint32_t* Lp = scratchL + t.start; uint32_t* Rp = scratchR + t.start;
+    const uint32_t sliceLen = (((n - 1 + HUGE_WARPS - 1) / HUGE_WARPS) + 31u) & ~31u;
+    const uint32_t b = min(n, 1u + w * sliceLen), e = min(n, b + sliceLen);
+    // (1) stops of this warp's slice [b, e), ascending positions
+    uint32_t cg = 0, cl = 0;
+    for (uint32_t i0 = b; i0 < e; i0 += 32) {
+        const uint32_t i = i0 + lane;
+        const unsigned long long key = i < e ? a[i].key : 0ULL;
+        const bool ge = i < e && key >= p, le = i < e && key <= p;
+        const uint32_t gm = __ballot_sync(0xffffffffu, ge), lm = __ballot_sync(0xffffffffu, le);
+        const uint32_t lt = (1u << lane) - 1u;
+        if (ge) Lp[b + cg + __popc(gm & lt)] = i;
+        if (le) Rp[b + cl + __popc(lm & lt)] = i;
+        cg += __popc(gm); cl += __popc(lm);
+    }
+    if (lane == 0) { geCnt[w] = cg; leCnt[w] = cl; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t g = 0;
+        for (int v = 0; v < HUGE_WARPS; ++v) { geBefore[v] = g; g += geCnt[v]; }
+        geBefore[HUGE_WARPS] = g;
+        uint32_t l = 0;
+        for (int v = HUGE_WARPS - 1; v >= 0; --v) { leAfter[v] = l; l += leCnt[v]; }
+        leAfter[HUGE_WARPS] = l;
+        sLo = 0; sHi = min(g, l);
+    }
+    __syncthreads();
+    const uint32_t GE = geBefore[HUGE_WARPS];
+    StopLists st{Lp, Rp, geBefore, leAfter, leCnt, sliceLen};
+    // (2) s = number of m with L_m < R_m (a prefix of the m): all m < lo hold, no m >= hi holds
+    for (;;) {
+        const uint32_t lo = sLo, hi = sHi;
+        if (lo >= hi) { if (threadIdx.x == 0) sS = lo; break; }
+        const uint32_t step = (hi - lo + blockDim.x - 1) / blockDim.x;
+        const uint32_t m = lo + threadIdx.x * step;
+        const bool pred = m < hi && st.L(m) < st.R(m);
+        const uint32_t c = (uint32_t)__syncthreads_count(pred);
+        if (threadIdx.x == 0) {
+            if (step == 1) { sLo = lo + c; sHi = lo + c; }
+            else if (c == 0) { sHi = lo; }
+            else { sLo = lo + (c - 1) * step + 1; sHi = min(hi, lo + c * step); }
+        }
+        __syncthreads();
+    }
+    __syncthreads();
+    const uint32_t s = sS;
+    // (3) the swaps (the two position sets are disjoint: every L_m with m < s lies below every R_m' with m' < s)
+    for (uint32_t m = threadIdx.x; m < s; m += blockDim.x) {
+        const uint32_t x = st.L(m), y = st.R(m);
+        const Elem ex = a[x], ey = a[y];
+        a[x] = ey; a[y] = ex;
+    }
+    if (threadIdx.x == 0) {
+        const uint32_t Ls = s < GE ? st.L(s) : n;
+        const uint32_t cut = s == 0 ? Ls : min(Ls, st.R(s - 1));
+        const uint32_t cs[2] = {t.start, t.start + cut}, cn[2] = {cut, n - cut};
+        for (int c = 0; c < 2; ++c) {
+            if (cn[c] > hugeMin && !rangeIsTieFree(tieP, cs[c], cn[c])) {
+                const uint32_t q = atomicAdd(nOutHuge, 1u);
+                if (q < capHuge) { SortTask k; k.start = cs[c]; k.n = cn[c]; k.depth = t.depth - 1; outHuge[q] = k; }
+            } else emitRange(cs[c], cn[c], t.depth - 1, big, nBig, capBig, small, nSmall, capSmall, smallN, tieP);
+        }
     }
 }
 
@@ -1218,22 +1450,29 @@ __global__ void __launch_bounds__(256) alignFinishKernel(fg_overlap* __restrict_
 }
 
 // segmented sort driver.  dCounters: 5 device words (layout above) with [0] = nSegs already set and the rest zero.
+static constexpr uint32_t SORT_HUGE_MIN = 8192;   // ranges above this size are partitioned by a whole CTA (sortHugeKernel)
 struct SortWorkspace {
-    DevBuf<SortTask> small, bigA, bigB;
-    uint32_t capSmall = 0, capBig = 0;
+    DevBuf<SortTask> small, bigA, bigB, hugeA, hugeB;
+    uint32_t capSmall = 0, capBig = 0, capHuge = 0;
     void ensure(uint64_t totalElems, uint32_t maxSegs) {
         capSmall = (uint32_t)(totalElems / 8 + maxSegs + 4096);
         capBig = (uint32_t)(totalElems / sortSmallN() + maxSegs + 64);
         capSmall = (uint32_t)(totalElems * (128.0 / sortSmallN()) / 8 + maxSegs + 4096);
         small.ensure(capSmall); bigA.ensure(capBig); bigB.ensure(capBig);
+        capHuge = (uint32_t)(totalElems / SORT_HUGE_MIN + maxSegs + 64);
+        hugeA.ensure(capHuge); hugeB.ensure(capHuge);
     }
 };
 
 // outArr / tieP: tie-following mode (see rangeIsTieFree): arr = scratch copy of the segments in their original order,
 // outArr = the stable-sorted elements; only ranges that contain ties are emulated and delivered to outArr.
+// hugeScratch (optional): two arrays of 32-bit words indexed like arr (stop lists of sortHugeKernel) and hugeCounters, two
+// zeroed device words; without them every range takes the warp-per-range path.
 static void sortSegments(fg_ctx* ctx, Elem* arr, const Seg* dSegs, uint32_t* dCounters, uint32_t maxSegs, SortWorkspace& ws,
-                         const char* topName, const char* smallName, SortCfg cfg, Elem* outArr = nullptr, const uint32_t* tieP = nullptr) {
+                         const char* topName, const char* smallName, SortCfg cfg, Elem* outArr = nullptr, const uint32_t* tieP = nullptr,
+                         uint32_t* hugeScratchL = nullptr, uint32_t* hugeScratchR = nullptr, uint32_t* hugeCounters = nullptr) {
     if (!outArr) outArr = arr;
+    const bool useHuge = hugeScratchL && hugeScratchR && hugeCounters && envInt("FG_SORT_HUGE", 1, 0, 1);
     static bool attrSet = false;
     const int variant = cfg.variant;
     const uint32_t smallN = (uint32_t)cfg.smallN;
@@ -1252,8 +1491,26 @@ static void sortSegments(fg_ctx* ctx, Elem* arr, const Seg* dSegs, uint32_t* dCo
     {
         PhaseTimer pt(ctx, topName);
         sortSeedKernel<<<(maxSegs + 255) / 256, 256, 0, ctx->stream>>>(dSegs, dCounters, ws.bigA.p, dCounters + 3, ws.capBig, ws.small.p,
-                                                                      dCounters + 1, ws.capSmall, smallN, tieP);
+                                                                      dCounters + 1, ws.capSmall, smallN, tieP,
+                                                                      useHuge ? ws.hugeA.p : nullptr, hugeCounters, ws.capHuge, SORT_HUGE_MIN);
         checkLaunch(ctx, "sortSeedKernel");
+        if (useHuge) {   // CTA-wide partition steps until no range is longer than SORT_HUGE_MIN
+            SortTask* hin = ws.hugeA.p; SortTask* hout = ws.hugeB.p;
+            uint32_t* nHin = hugeCounters; uint32_t* nHout = hugeCounters + 1;
+            for (int level = 0; level < 200; ++level) {
+                uint32_t hCnt = 0;
+                FG_CUDA(cudaMemcpyAsync(&hCnt, nHin, 4, cudaMemcpyDeviceToHost, ctx->stream));
+                FG_CUDA(cudaStreamSynchronize(ctx->stream));
+                if (hCnt > ws.capHuge) throw Error(FG_ERR_INTERNAL, "sort task list overflow");
+                if (!hCnt) break;
+                FG_CUDA(cudaMemsetAsync(nHout, 0, 4, ctx->stream));
+                sortHugeKernel<<<hCnt, HUGE_WARPS * 32, 0, ctx->stream>>>(arr, hin, nHin, ws.capHuge, hout, nHout, SORT_HUGE_MIN, ws.bigA.p, dCounters + 3,
+                                                                         ws.capBig, ws.small.p, dCounters + 1, ws.capSmall, smallN, outArr, tieP,
+                                                                         hugeScratchL, hugeScratchR);
+                checkLaunch(ctx, "sortHugeKernel");
+                std::swap(hin, hout); std::swap(nHin, nHout);
+            }
+        }
         SortTask* in = ws.bigA.p; SortTask* out = ws.bigB.p;
         uint32_t* nIn = dCounters + 3; uint32_t* nOut = dCounters + 4;
         uint64_t firstElems = 0;
@@ -1299,14 +1556,15 @@ void debugWarpSort(fg_ctx* ctx, uint64_t* keys, uint32_t* vals, const uint64_t* 
     for (uint32_t i = 0; i < nSegs; ++i) { hs[i].start = (uint32_t)segOffsets[i]; hs[i].n = (uint32_t)(segOffsets[i + 1] - segOffsets[i]); }
     DevBuf<Elem> d(std::max<uint64_t>(n, 1));
     DevBuf<Seg> dSegs(nSegs);
-    DevBuf<uint32_t> counters(8);
+    DevBuf<uint32_t> counters(16), hugeScratch(2 * std::max<uint64_t>(n, 1));
     SortWorkspace ws; ws.ensure(n, nSegs);
     const uint32_t cap = ws.capSmall;
-    uint32_t hc[8] = {nSegs, 0, 0, 0, 0, 0, 0, 0};
+    uint32_t hc[16] = {nSegs, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     FG_CUDA(cudaMemcpyAsync(d.p, h.data(), n * sizeof(Elem), cudaMemcpyHostToDevice, ctx->stream));
     FG_CUDA(cudaMemcpyAsync(dSegs.p, hs.data(), nSegs * sizeof(Seg), cudaMemcpyHostToDevice, ctx->stream));
     FG_CUDA(cudaMemcpyAsync(counters.p, hc, sizeof hc, cudaMemcpyHostToDevice, ctx->stream));
-    sortSegments(ctx, d.p, dSegs.p, counters.p, nSegs, ws, "dbg_sort_top", "dbg_sort_small", envInt("FG_DEBUG_SORT_PAIRS", 0, 0, 1) ? sortCfgPairs() : sortCfgHits());
+    sortSegments(ctx, d.p, dSegs.p, counters.p, nSegs, ws, "dbg_sort_top", "dbg_sort_small", envInt("FG_DEBUG_SORT_PAIRS", 0, 0, 1) ? sortCfgPairs() : sortCfgHits(),
+                 nullptr, nullptr, hugeScratch.p, hugeScratch.p + n, counters.p + 8);
     FG_CUDA(cudaMemcpyAsync(h.data(), d.p, n * sizeof(Elem), cudaMemcpyDeviceToHost, ctx->stream));
     FG_CUDA(cudaMemcpyAsync(hc, counters.p, sizeof hc, cudaMemcpyDeviceToHost, ctx->stream));
     FG_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -1358,6 +1616,9 @@ static void overlapsChunk(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, ui
     const uint64_t* qWordOff = P.sameSet ? ctx->dWordOff.p : ctx->dQsWordOff.p;
     const uint32_t* qLen = P.sameSet ? ctx->dLen.p : ctx->dQsLen.p;
     PinnedBuf<fg_overlap>& pinned = ctx->pinnedOut;
+    uint32_t maxSeqLen = 1;   // bounds curPos and extPos (packed hits of the segmented sort)
+    for (uint32_t L : ctx->hLen) maxSeqLen = std::max(maxSeqLen, L);
+    for (uint32_t L : qHLen) maxSeqLen = std::max(maxSeqLen, L);
 
     // query slot space and tiles
     std::unique_ptr<HostTimer> hostPrep(new HostTimer(ctx, "host_chunk_prep"));   // wall clock up to the first sub-batch (incl. "gather" lookups)
@@ -1442,12 +1703,37 @@ static void overlapsChunk(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, ui
         hCounters[0] = nq;
         FG_CUDA(cudaMemcpyAsync(counters.p, hCounters, sizeof hCounters, cudaMemcpyHostToDevice, ctx->stream));
         const size_t tA = qTileFirst[qa], tB = qTileFirst[qb];
-        // tie-free fast path: stable radix sort by (query, extId); needs both fields in 32 key bits
-        int idBits = 1, qBits = 1;
+        // tie-free fast path: stable radix sort by (query, extId).  FG_HIT_RADIX: 1 (default) = segmented sort of packed 64-bit
+        // hits, one CTA per query; 2 = the library's radix sort on 32-bit (query, extId) keys; 0 = exact emulation for every query
+        int idBits = 1, qBits = 1, posBits = 1;
         while ((2ULL * ctx->nReads) >> idBits) ++idBits;
         while (((uint64_t)nq) >> qBits) ++qBits;
-        const bool radixPath = envInt("FG_HIT_RADIX", 1, 0, 1) != 0 && idBits + qBits <= 32;
+        while (((uint64_t)maxSeqLen) >> posBits) ++posBits;
+        int radixMode = envInt("FG_HIT_RADIX", 1, 0, 2);
+        if (radixMode == 1 && (idBits > 24 || idBits + 2 * posBits > 64)) radixMode = 2;
+        if (radixMode == 2 && idBits + qBits > 32) radixMode = 0;
+        const bool radixPath = radixMode != 0;
         if (radixPath) {
+            qTie.ensure(nq);
+            FG_CUDA(cudaMemsetAsync(qTie.p, 0, nq, ctx->stream));
+        }
+        if (radixMode == 1) {
+            // scratch: ord (16 B per hit, free until the DP) holds the two 8-byte ping-pong buffers
+            unsigned long long* bufA = reinterpret_cast<unsigned long long*>(ord.p);
+            unsigned long long* bufB = bufA + M;
+            {
+                PhaseTimer pt(ctx, "expand");
+                expandKernel<2><<<(unsigned)(tB - tA), 256, 0, ctx->stream>>>(ctx->dLen.p, qLen, ctx->dEntries.p, dQIds.p, dQSlotOff.p, dQTiles.p + tA, k,
+                                                                             hitOff.p, slotInfo.p, hitBase, nullptr, nullptr, nullptr, bufA, qa, idBits, nullptr,
+                                                                             posBits, qTie.p);
+                checkLaunch(ctx, "expandKernel");
+            }
+            {
+                PhaseTimer pt(ctx, "hit_sort_radix");
+                segRadixSortKernel<<<nq, SEG_WARPS * 32, 0, ctx->stream>>>(bufA, bufB, dQHitOff.p, qa, hitBase, posBits, (idBits + 7) / 8, hits.p);
+                checkLaunch(ctx, "segRadixSortKernel");
+            }
+        } else if (radixMode == 2) {
             // scratch: the arrays of the later chaining stages are free until the DP (ord = 16 B per hit: the two key and the two
             // value buffers; the second half of the 32-B candidate slots: the payload; its first half is the scratch copy below)
             uint32_t* keyA = reinterpret_cast<uint32_t*>(ord.p);
@@ -1455,17 +1741,15 @@ static void overlapsChunk(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, ui
             uint32_t* valA = keyB + M;
             uint32_t* valB = valA + M;
             unsigned long long* payload = reinterpret_cast<unsigned long long*>(reinterpret_cast<Elem*>(cands.p) + M);
-            qTie.ensure(nq);
-            FG_CUDA(cudaMemsetAsync(qTie.p, 0, nq, ctx->stream));
             {
                 PhaseTimer pt(ctx, "expand");
-                expandKernel<true><<<(unsigned)(tB - tA), 256, 0, ctx->stream>>>(ctx->dLen.p, qLen, ctx->dEntries.p, dQIds.p, dQSlotOff.p, dQTiles.p + tA, k,
-                                                                                hitOff.p, slotInfo.p, hitBase, nullptr, keyA, valA, payload, qa, idBits, nullptr);
+                expandKernel<1><<<(unsigned)(tB - tA), 256, 0, ctx->stream>>>(ctx->dLen.p, qLen, ctx->dEntries.p, dQIds.p, dQSlotOff.p, dQTiles.p + tA, k,
+                                                                             hitOff.p, slotInfo.p, hitBase, nullptr, keyA, valA, payload, qa, idBits, nullptr, 0, nullptr);
                 checkLaunch(ctx, "expandKernel");
             }
             cub::DoubleBuffer<uint32_t> dk(keyA, keyB), dv(valA, valB);
             {
-                PhaseTimer pt(ctx, "hit_sort_radix");
+                PhaseTimer pt(ctx, "hit_sort_radix_lib");
                 size_t tb = 0;
                 FG_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, dk, dv, (int)M, 0, idBits + qBits, ctx->stream));
                 DevBuf<char> tmpS(tb);
@@ -1477,12 +1761,20 @@ static void overlapsChunk(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, ui
                 gatherSortedHitsKernel<<<gridFor(M, 256, 16), 256, 0, ctx->stream>>>(dk.Current(), dv.Current(), payload, M, idBits, hits.p, qTie.p, flags.p);
                 checkLaunch(ctx, "gatherSortedHitsKernel");
             }
+        }
+        if (radixPath) {
             querySegsKernel<<<(nq + 255) / 256, 256, 0, ctx->stream>>>(dQHitOff.p, qa, nq, hitBase, segsQ.p, qTie.p, counters.p + 24);
             checkLaunch(ctx, "querySegsKernel");
             uint32_t hTied = 0;
             FG_CUDA(cudaMemcpyAsync(&hTied, counters.p + 24, 4, cudaMemcpyDeviceToHost, ctx->stream));
             FG_CUDA(cudaStreamSynchronize(ctx->stream));
             totTied += hTied;
+            if (hTied && radixMode == 1) {
+                PhaseTimer pt(ctx, "hit_sort_top");
+                FG_CUDA(cudaMemsetAsync(flags.p, 0, M + 1, ctx->stream));
+                tieFlagKernel<<<nq, 256, 0, ctx->stream>>>(hits.p, dQHitOff.p, qa, hitBase, qTie.p, flags.p);
+                checkLaunch(ctx, "tieFlagKernel");
+            }
             if (hTied) {
                 // queries with ties: expanded again in the original order into a scratch array (the candidate array, free
                 // until the chain walk) and sorted by the exact introsort emulation, which only follows the ranges that
@@ -1500,22 +1792,24 @@ static void overlapsChunk(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, ui
                 }
                 {
                     PhaseTimer pt(ctx, "hit_sort_top");   // re-expansion of the queries with ties
-                    expandKernel<false><<<(unsigned)(tB - tA), 256, 0, ctx->stream>>>(ctx->dLen.p, qLen, ctx->dEntries.p, dQIds.p, dQSlotOff.p, dQTiles.p + tA, k,
-                                                                                     hitOff.p, slotInfo.p, hitBase, scratch, nullptr, nullptr, nullptr, qa, 0, qTie.p);
+                    expandKernel<0><<<(unsigned)(tB - tA), 256, 0, ctx->stream>>>(ctx->dLen.p, qLen, ctx->dEntries.p, dQIds.p, dQSlotOff.p, dQTiles.p + tA, k,
+                                                                                     hitOff.p, slotInfo.p, hitBase, scratch, nullptr, nullptr, nullptr, qa, 0, qTie.p, 0, nullptr);
                     checkLaunch(ctx, "expandKernel");
                 }
-                sortSegments(ctx, scratch, segsQ.p, counters.p, nq, ws, "hit_sort_top", "hit_sort_small", sortCfgHits(), hits.p, tieP);
+                sortSegments(ctx, scratch, segsQ.p, counters.p, nq, ws, "hit_sort_top", "hit_sort_small", sortCfgHits(), hits.p, tieP,
+                             reinterpret_cast<uint32_t*>(ord.p), reinterpret_cast<uint32_t*>(ord.p) + M, counters.p + 25);
             }
         } else {
             {
                 PhaseTimer pt(ctx, "expand");
-                expandKernel<false><<<(unsigned)(tB - tA), 256, 0, ctx->stream>>>(ctx->dLen.p, qLen, ctx->dEntries.p, dQIds.p, dQSlotOff.p, dQTiles.p + tA, k,
-                                                                                 hitOff.p, slotInfo.p, hitBase, hits.p, nullptr, nullptr, nullptr, qa, 0, nullptr);
+                expandKernel<0><<<(unsigned)(tB - tA), 256, 0, ctx->stream>>>(ctx->dLen.p, qLen, ctx->dEntries.p, dQIds.p, dQSlotOff.p, dQTiles.p + tA, k,
+                                                                                 hitOff.p, slotInfo.p, hitBase, hits.p, nullptr, nullptr, nullptr, qa, 0, nullptr, 0, nullptr);
                 checkLaunch(ctx, "expandKernel");
             }
             querySegsKernel<<<(nq + 255) / 256, 256, 0, ctx->stream>>>(dQHitOff.p, qa, nq, hitBase, segsQ.p, nullptr, nullptr);
             checkLaunch(ctx, "querySegsKernel");
-            sortSegments(ctx, hits.p, segsQ.p, counters.p, nq, ws, "hit_sort_top", "hit_sort_small", sortCfgHits());
+            sortSegments(ctx, hits.p, segsQ.p, counters.p, nq, ws, "hit_sort_top", "hit_sort_small", sortCfgHits(), nullptr, nullptr,
+                         reinterpret_cast<uint32_t*>(ord.p), reinterpret_cast<uint32_t*>(ord.p) + M, counters.p + 25);
         }
         uint32_t G = 0, C = 0, Pn = 0;
         DevBuf<PairInfo> pairInfo;

@@ -26,6 +26,8 @@ def test_device_introsort_matches_std_sort(engine):
     rng = np.random.default_rng(5)
     sizes = [0, 1, 2, 16, 17, 18, 31, 32, 33, 34, 47, 48, 49, 50, 63, 64, 65, 66, 96, 97, 127, 128, 129, 1000, 4097]
     sizes += list(rng.integers(1, 300, 300)) + list(rng.integers(300, 6000, 60)) + [70000, 150001]
+    # ranges above 8192 elements take the CTA-wide partition (sortHugeKernel): every key pattern at several sizes
+    sizes += [8193, 9000, 12345, 16384, 20001, 33333, 40000, 50000, 65537, 8200, 100000, 262145, 30000, 11111]
     keys, seg = [], [0]
     for i, n in enumerate(sizes):
         mode = i % 6
