@@ -208,6 +208,7 @@ def main():
     phase_ms, phase_calls, ovl_stats, n_ovl, wall = {}, {}, {}, 0, {}
     n_raw = [0]
     ovl_len_sample = np.zeros(0)
+    edit_sample = [None]
 
     def step(upload):
         nonlocal phase_ms, phase_calls, ovl_stats, n_ovl, wall, ovl_len_sample
@@ -275,6 +276,7 @@ def main():
         n_ovl = int(np.count_nonzero(keep))
         n_raw[0] = int(offs[-1])
         ovl_len_sample = (ov["cur_end"][first:first + 20000] - ov["cur_begin"][first:first + 20000]).astype(np.float64)
+        edit_sample[0] = float(np.mean(ov["edit_distance"][first:first + 20000])) if common["nucl_alignment"] and len(ov) > first else None
         lap("filter")
         return n_ovl
 
@@ -377,6 +379,7 @@ def main():
             "api_wall_ms": {p: round(v, 2) for p, v in resident_wall.items()}, "e2e_api_wall_ms": {p: round(v, 2) for p, v in e2e_wall.items()},
             "work": {"kmer_hits": int(M), "target_groups": int(stats.get("n_pairs", 0)), "dp_pairs": int(stats.get("n_dp_pairs", 0)),
                      "dp_cells": int(stats.get("n_dp_cells", 0)), "overlaps": int(O),
+                     "mean_edit_distance_first_20k_overlaps": edit_sample[0],
                      "queries_with_hit_ties": int(resident_phases.get("tied_queries", 0)),
                      "pairs_score_order_presorted": int(resident_phases.get("presorted_pairs", 0))}}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

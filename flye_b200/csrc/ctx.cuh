@@ -2,8 +2,57 @@
 #pragma once
 #include "common.cuh"
 #include <algorithm>
+#include <condition_variable>
+#include <functional>
 #include <map>
+#include <thread>
 #include <utility>
+
+namespace fg {
+// Persistent host worker threads of a context (the per-record epilogue of fg_overlaps_batch: divergence with glibc logf,
+// threshold / maxOverlaps replay).  Created on first use; creating 2 x 16 std::threads per call cost more than the work.
+class HostPool {
+    std::vector<std::thread> workers;
+    std::mutex m;
+    std::condition_variable cvStart, cvDone;
+    const std::function<void(size_t, size_t)>* job = nullptr;
+    size_t jobN = 0;
+    unsigned generation = 0, pending = 0;
+    bool stopping = false;
+    void run(unsigned t) {
+        unsigned seen = 0;
+        for (;;) {
+            const std::function<void(size_t, size_t)>* fn; size_t n; unsigned T;
+            {
+                std::unique_lock<std::mutex> lk(m);
+                cvStart.wait(lk, [&] { return stopping || generation != seen; });
+                if (stopping) return;
+                seen = generation; fn = job; n = jobN; T = (unsigned)workers.size();
+            }
+            (*fn)(n * t / T, n * (t + 1) / T);
+            std::lock_guard<std::mutex> lk(m);
+            if (--pending == 0) cvDone.notify_all();
+        }
+    }
+public:
+    // fn(a, b) over a partition of [0, n) into contiguous ranges, one per worker; returns when all are done
+    // (`work`: number of elementary items behind the n ranges, decides whether threads are worth it)
+    void parallelFor(size_t n, const std::function<void(size_t, size_t)>& fn, size_t work = 0) {
+        const unsigned T = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+        if (std::max(n, work) < 20000 || n < T || T == 1) { fn(0, n); return; }
+        if (workers.empty()) for (unsigned t = 0; t < T; ++t) workers.emplace_back(&HostPool::run, this, t);
+        std::unique_lock<std::mutex> lk(m);
+        job = &fn; jobN = n; pending = (unsigned)workers.size(); ++generation;
+        cvStart.notify_all();
+        cvDone.wait(lk, [&] { return pending == 0; });
+    }
+    ~HostPool() {
+        { std::lock_guard<std::mutex> lk(m); stopping = true; }
+        cvStart.notify_all();
+        for (auto& th : workers) th.join();
+    }
+};
+}  // namespace fg
 
 struct fg_ctx {
     fg::Arena arena;                      // first member: destroyed last, after every DevBuf below
@@ -79,6 +128,7 @@ struct fg_ctx {
     std::vector<uint64_t> resOffsets;
     std::vector<int32_t> resAln;
     fg::PinnedBuf<fg_overlap> pinnedOut;  // D2H staging, kept across calls
+    fg::HostPool hostPool;
 
     // ---- NCCL ----
     void* ncclComm = nullptr;

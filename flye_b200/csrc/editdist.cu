@@ -264,7 +264,7 @@ void editDistances(fg_ctx* ctx, fg_overlap* dOv, const fg_overlap* hOv, uint32_t
     }
     DevBuf<uint32_t> nextJob(1);
     FG_CUDA(cudaMemsetAsync(nextJob.p, 0, 4, ctx->stream));
-    const int blocks = 148 * 8, warps = blocks * 4;
+    const int blocks = 148 * 10, warps = blocks * 4;   // 48 registers / thread: 40 resident warps per SM
     const uint64_t stride = 2ULL * maxLen + 8;
     DevBuf<int> wf((uint64_t)warps * 2 * stride);   // only touched by overlaps with more than WF_DMAX edits
     wfaKernel<<<blocks, 128, 0, ctx->stream>>>(dOv, nOv, cur, ext, useHpc, wf.p, stride, nextJob.p);

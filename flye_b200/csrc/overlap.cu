@@ -2020,13 +2020,7 @@ void overlapsBatch(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, const fg_
     HostTimer hostEpi(ctx, "host_epilogue");
     const float sampleRate = ctx->stats.sample_rate;
     fg_overlap* hOut = pinned.p;
-    const unsigned nThreads = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
-    auto parallelFor = [&](size_t n, const std::function<void(size_t, size_t)>& fn) {
-        if (n < 20000 || nThreads == 1) { fn(0, n); return; }
-        std::vector<std::thread> pool;
-        for (unsigned t = 0; t < nThreads; ++t) pool.emplace_back(fn, n * t / nThreads, n * (t + 1) / nThreads);
-        for (auto& th : pool) th.join();
-    };
+    auto parallelFor = [&](size_t n, const std::function<void(size_t, size_t)>& fn) { ctx->hostPool.parallelFor(n, fn, nRaw); };
     // (1) divergence of every record (pure per-record arithmetic with glibc logf) and the first record of every query
     std::vector<size_t> qStart(nQ + 1, SIZE_MAX);
     parallelFor(nRaw, [&](size_t a, size_t b) {
