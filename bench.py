@@ -251,11 +251,15 @@ def main():
         first = int(offs[len(my_est)])
         rng_est = ov["cur_end"][:first] - ov["cur_begin"][:first]
         div_all = ov["seq_divergence"]
+        # divergence of the longest overlap of every estimate query (first one on ties, as np.argmax / overlap.cpp:768-783)
         divs = []
-        for i in range(len(my_est)):
-            a, b = int(offs[i]), int(offs[i + 1])
-            if b > a:
-                divs.append(div_all[a + int(np.argmax(rng_est[a:b]))])
+        if first:
+            o_est = np.asarray(offs[:len(my_est) + 1], dtype=np.int64)
+            starts = o_est[:-1][np.diff(o_est) > 0]
+            big = first + 1
+            keyv = rng_est.astype(np.int64) * big + (big - 1 - np.arange(first, dtype=np.int64))
+            best = np.maximum.reduceat(keyv, starts)
+            divs = div_all[big - 1 - (best % big)].tolist()
         if world > 1:
             cap = (len(est_ids) + world - 1) // world
             buf = torch.full((cap + 1,), float("nan"), dtype=torch.float32, device="cuda")

@@ -216,7 +216,7 @@ __global__ void __launch_bounds__(256) gatherSortedHitsKernel(const uint32_t* __
 static constexpr int SEG_WARPS = 16;
 __global__ void __launch_bounds__(SEG_WARPS * 32, 3) segRadixSortKernel(unsigned long long* bufA, unsigned long long* bufB,
                                                                          const uint64_t* __restrict__ qHitOff, uint32_t qFirst, uint64_t hitBase,
-                                                                         int posBits, int nPass, Elem* __restrict__ hits) {
+                                                                         int posBits, int nPass, Elem* __restrict__ hits, uint8_t* __restrict__ groupFlags) {
     __shared__ uint32_t hist[2][SEG_WARPS][256];
     __shared__ uint32_t base[256];
     const uint64_t start = qHitOff[qFirst + blockIdx.x] - hitBase;
@@ -295,6 +295,9 @@ __global__ void __launch_bounds__(SEG_WARPS * 32, 3) segRadixSortKernel(unsigned
         const unsigned long long* t = dst; dst = const_cast<unsigned long long*>(src); src = t;
         uint32_t (*th)[256] = cur; cur = nxt; nxt = th;
     }
+    // start flags of the target groups (overlap.cpp:216-221), while the sorted segment is still in L2
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x)
+        groupFlags[start + i] = i == 0 || (uint32_t)(hits[start + i].key >> 32) != (uint32_t)(hits[start + i - 1].key >> 32);
 }
 
 // tie flags (input of the prefix count of rangeIsTieFree) for the queries that contain ties; all other flags stay 0
@@ -663,6 +666,10 @@ __global__ void __launch_bounds__(256) pairFilterKernel(const Elem* __restrict__
 // Q6: chaining
 // ------------------------------------------------------------------------------------------------
 struct Cand { int32_t curBegin, curEnd, extBegin, extEnd, score, chainLength, filtered, pad; };
+// run of the run-compressed chaining DP (see chainRunDpKernel): [a, b] = its matches
+struct __align__(16) Run { int32_t a, curA, extA, backA; int32_t b, curB, extB, scoreB; };
+static_assert(sizeof(Run) == sizeof(Cand), "run records live in the candidate array until the chain walk");
+static constexpr uint32_t RUNS_PENDING = 0xffffffffu;   // nRuns of a pair whose matches still have to be re-sorted by extPos
 
 __device__ __forceinline__ bool overlapTestDev(const OvParams& P, uint32_t curId, uint32_t extId, int32_t curBegin, int32_t curEnd,
                                                int32_t extBegin, int32_t extEnd, int32_t curLen, int32_t extLen) {
@@ -695,10 +702,13 @@ static constexpr uint32_t PAIR_PRESORTED = 2u;   // scores increase strictly wit
 
 // (a) per pair: decide the DP axis (overlap.cpp:269), re-key the elements of ext-sorted pairs by extPos and
 // append them to the list of segments that need the std::sort-exact re-sort (:272-274)
+// `runs` != nullptr (run-compressed DP): the same pass also finds the runs of the pair (see chainRunsKernel, which then only
+// has to visit the pairs that were re-sorted in between).
 __global__ void __launch_bounds__(256) pairPrepKernel(Elem* __restrict__ hits, const PairInfo* __restrict__ pairs, const uint32_t* __restrict__ pairIds,
                                                       uint32_t nPairs, const uint32_t* __restrict__ qIds, const uint32_t* __restrict__ len,
                                                       const uint32_t* __restrict__ qlen, uint32_t* __restrict__ pairFlags, Seg* __restrict__ extSegs, uint32_t* __restrict__ nExtSegs,
-                                                      Seg* __restrict__ allSegs) {
+                                                      Seg* __restrict__ allSegs, int k, Run* __restrict__ runs, int32_t* __restrict__ runOf,
+                                                      uint32_t* __restrict__ nRuns) {
     const uint32_t w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (w >= nPairs) return;
     const int lane = threadIdx.x & 31;
@@ -710,28 +720,46 @@ __global__ void __launch_bounds__(256) pairPrepKernel(Elem* __restrict__ hits, c
         pairFlags[w] = extSorted ? PAIR_EXTSORTED : 0u;
         allSegs[w] = sg;
     }
-    if (extSorted) {
-        // A pair whose extPos values already increase strictly along the curPos order is in the unique sorted order of
-        // distinct keys, i.e. in std::sort's output order: no re-sort (the usual case for a clean overlap).
-        Elem* h = hits + pi.start;
-        bool sorted = true;
-        uint32_t carry = 0;
-        for (uint32_t i0 = 0; i0 < pi.n; i0 += 32) {
-            const uint32_t i = i0 + lane;
-            uint32_t x = 0xffffffffu;
-            if (i < pi.n) {
-                const Elem e = h[i];
-                Elem t; t.key = (unsigned long long)e.val; t.val = (unsigned int)e.key; t.aux = 0;
-                h[i] = t;
-                x = e.val;
-            }
-            uint32_t px = __shfl_up_sync(0xffffffffu, x, 1);
-            if (lane == 0) px = carry;
-            if (i < pi.n && i > 0 && !(px < x)) sorted = false;
-            carry = __shfl_sync(0xffffffffu, x, 31);
+    if (!extSorted && !runs) return;
+    // A pair whose extPos values already increase strictly along the curPos order is in the unique sorted order of
+    // distinct keys, i.e. in std::sort's output order: no re-sort (the usual case for a clean overlap).
+    Elem* h = hits + pi.start;
+    Run* rn = runs ? runs + pi.start : nullptr;
+    int32_t* ro = runs ? runOf + pi.start : nullptr;
+    const int32_t n = (int32_t)pi.n;
+    bool sorted = true;
+    int32_t base = 0, carryC = 0, carryE = 0;
+    for (int32_t i0 = 0; i0 < n; i0 += 32) {
+        const int32_t i = i0 + lane;
+        int32_t c = 0, x = 0;
+        if (i < n) {
+            const Elem e = h[i];
+            c = (int32_t)(uint32_t)e.key; x = (int32_t)e.val;
+            if (extSorted) { Elem t; t.key = (unsigned long long)e.val; t.val = (unsigned int)e.key; t.aux = 0; h[i] = t; }
         }
-        sorted = __all_sync(0xffffffffu, sorted);
-        if (lane == 0 && !sorted) extSegs[atomicAdd(nExtSegs, 1u)] = sg;
+        int32_t pc = __shfl_up_sync(0xffffffffu, c, 1), px = __shfl_up_sync(0xffffffffu, x, 1);
+        if (lane == 0) { pc = carryC; px = carryE; }
+        if (extSorted && i < n && i > 0 && !((uint32_t)px < (uint32_t)x)) sorted = false;
+        if (runs) {
+            const int32_t dc = c - pc, de = x - px;
+            // match 0 is its own run (score 0, :323); match 1 always starts one (its predecessor's score is not >= k)
+            const bool head = i < n && (i <= 1 || !(dc == de && 0 < dc && dc < k));
+            const uint32_t m = __ballot_sync(0xffffffffu, head);
+            const int32_t r = base + __popc(m & (0xffffffffu >> (31 - lane))) - 1;
+            if (i < n) ro[i] = r;
+            if (head) {
+                rn[r].a = i; rn[r].curA = c; rn[r].extA = x;
+                if (i > 0) { rn[r - 1].b = i - 1; rn[r - 1].curB = pc; rn[r - 1].extB = px; }
+            }
+            if (i == n - 1) { rn[r].b = i; rn[r].curB = c; rn[r].extB = x; }
+            base += __popc(m);
+        }
+        carryC = __shfl_sync(0xffffffffu, c, 31); carryE = __shfl_sync(0xffffffffu, x, 31);
+    }
+    sorted = __all_sync(0xffffffffu, sorted);
+    if (lane == 0) {
+        if (extSorted && !sorted) extSegs[atomicAdd(nExtSegs, 1u)] = sg;
+        if (runs) nRuns[w] = (extSorted && !sorted) ? RUNS_PENDING : (uint32_t)base;   // pending: chainRunsKernel after the re-sort
     }
 }
 
@@ -1014,12 +1042,11 @@ __global__ void __launch_bounds__(128) chainDpPrunedKernel(const Elem* __restric
 // cuts the scan at a run boundary or makes the rest of a run invalid.  Scores and back pointers are identical to the
 // match-by-match scan; the work drops from O(matches within maxJump) to O(runs within maxJump) per head and to O(1)
 // per other match (on low-error reads a run holds ~30 matches).
-//   chainRunsKernel   finds the runs of every pair (one warp per pair), writes their records and the run of every match
+//   chainRunsKernel   finds the runs of a pair (one warp per pair), writes their records and the run of every match; the pairs
+//                     that need no re-sort by extPos get this done by pairPrepKernel, which reads their matches anyway
 //   chainRunDpKernel  the scan of the heads: half-warp per pair, 16 runs per step, the 16 most recent runs in registers
 //   chainFillKernel   scores / back pointers / score-sort input of all matches from the run records
 // ------------------------------------------------------------------------------------------------
-struct __align__(16) Run { int32_t a, curA, extA, backA; int32_t b, curB, extB, scoreB; };   // [a, b] = matches of the run
-static_assert(sizeof(Run) == sizeof(Cand), "run records live in the candidate array until the chain walk");
 
 __global__ void __launch_bounds__(256) chainRunsKernel(const Elem* __restrict__ hits, const PairInfo* __restrict__ pairs, const uint32_t* __restrict__ pairIds,
                                                        uint32_t nPairs, const uint32_t* __restrict__ pairFlags, int k, Run* __restrict__ runs,
@@ -1027,6 +1054,7 @@ __global__ void __launch_bounds__(256) chainRunsKernel(const Elem* __restrict__ 
     const uint32_t w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (w >= nPairs) return;
     const int lane = threadIdx.x & 31;
+    if (nRuns[w] != RUNS_PENDING) return;   // pairPrepKernel already found the runs (no re-sort in between)
     const PairInfo pi = pairs[pairIds[w]];
     const bool extSorted = pairFlags[w] & PAIR_EXTSORTED;
     const int32_t n = (int32_t)pi.n;
@@ -1713,6 +1741,7 @@ static void overlapsChunk(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, ui
         if (radixMode == 1 && (idBits > 24 || idBits + 2 * posBits > 64)) radixMode = 2;
         if (radixMode == 2 && idBits + qBits > 32) radixMode = 0;
         const bool radixPath = radixMode != 0;
+        uint8_t* tieFlags = reinterpret_cast<uint8_t*>(back.p);   // M + 1 bytes of the back-pointer array (free until the chaining)
         if (radixPath) {
             qTie.ensure(nq);
             FG_CUDA(cudaMemsetAsync(qTie.p, 0, nq, ctx->stream));
@@ -1730,7 +1759,7 @@ static void overlapsChunk(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, ui
             }
             {
                 PhaseTimer pt(ctx, "hit_sort_radix");
-                segRadixSortKernel<<<nq, SEG_WARPS * 32, 0, ctx->stream>>>(bufA, bufB, dQHitOff.p, qa, hitBase, posBits, (idBits + 7) / 8, hits.p);
+                segRadixSortKernel<<<nq, SEG_WARPS * 32, 0, ctx->stream>>>(bufA, bufB, dQHitOff.p, qa, hitBase, posBits, (idBits + 7) / 8, hits.p, flags.p);
                 checkLaunch(ctx, "segRadixSortKernel");
             }
         } else if (radixMode == 2) {
@@ -1758,7 +1787,7 @@ static void overlapsChunk(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, ui
             }
             {
                 PhaseTimer pt(ctx, "hit_sort_gather");
-                gatherSortedHitsKernel<<<gridFor(M, 256, 16), 256, 0, ctx->stream>>>(dk.Current(), dv.Current(), payload, M, idBits, hits.p, qTie.p, flags.p);
+                gatherSortedHitsKernel<<<gridFor(M, 256, 16), 256, 0, ctx->stream>>>(dk.Current(), dv.Current(), payload, M, idBits, hits.p, qTie.p, tieFlags);
                 checkLaunch(ctx, "gatherSortedHitsKernel");
             }
         }
@@ -1771,8 +1800,8 @@ static void overlapsChunk(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, ui
             totTied += hTied;
             if (hTied && radixMode == 1) {
                 PhaseTimer pt(ctx, "hit_sort_top");
-                FG_CUDA(cudaMemsetAsync(flags.p, 0, M + 1, ctx->stream));
-                tieFlagKernel<<<nq, 256, 0, ctx->stream>>>(hits.p, dQHitOff.p, qa, hitBase, qTie.p, flags.p);
+                FG_CUDA(cudaMemsetAsync(tieFlags, 0, M + 1, ctx->stream));
+                tieFlagKernel<<<nq, 256, 0, ctx->stream>>>(hits.p, dQHitOff.p, qa, hitBase, qTie.p, tieFlags);
                 checkLaunch(ctx, "tieFlagKernel");
             }
             if (hTied) {
@@ -1783,7 +1812,7 @@ static void overlapsChunk(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, ui
                 uint32_t* tieP = reinterpret_cast<uint32_t*>(score.p);
                 {
                     PhaseTimer pt(ctx, "hit_sort_top");
-                    cub::TransformInputIterator<uint32_t, CastU8, const uint8_t*> itF(flags.p, CastU8());
+                    cub::TransformInputIterator<uint32_t, CastU8, const uint8_t*> itF(tieFlags, CastU8());
                     size_t tb = 0;
                     FG_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, itF, tieP, (int)(M + 1), ctx->stream));
                     DevBuf<char> tmpS(tb);
@@ -1816,8 +1845,10 @@ static void overlapsChunk(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, ui
         DevBuf<uint8_t> candFlag, passFlag;
         {
             PhaseTimer pt(ctx, "group");
-            groupFlagKernel<<<gridFor(M), 256, 0, ctx->stream>>>(hits.p, M, flags.p);
-            checkLaunch(ctx, "groupFlagKernel");
+            if (radixMode != 1) {   // (the segmented sort writes the flags itself)
+                groupFlagKernel<<<gridFor(M), 256, 0, ctx->stream>>>(hits.p, M, flags.p);
+                checkLaunch(ctx, "groupFlagKernel");
+            }
             queryStartFlagKernel<<<(nq + 255) / 256, 256, 0, ctx->stream>>>(dQHitOff.p, qa, nq, hitBase, M, flags.p);
             checkLaunch(ctx, "queryStartFlagKernel");
             G = selectFlagged(ctx, flags.p, (uint32_t)M, gStart);
@@ -1845,8 +1876,10 @@ static void overlapsChunk(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, ui
             const int dpMode = envInt("FG_DP_MODE", 2, 0, 2);   // read per call: the tests switch it
             {
                 PhaseTimer pt(ctx, "chain_prep");
+                if (dpMode == 2) nRuns.alloc(Pn);
                 pairPrepKernel<<<(Pn + 7) / 8, 256, 0, ctx->stream>>>(hits.p, pairInfo.p, pairIds.p, Pn, dQIds.p, ctx->dLen.p, qLen, pairFlags.p,
-                                                                     extSegs.p, counters.p + 8, allSegs.p);
+                                                                     extSegs.p, counters.p + 8, allSegs.p, k, dpMode == 2 ? reinterpret_cast<Run*>(cands.p) : nullptr,
+                                                                     back.p, nRuns.p);
                 checkLaunch(ctx, "pairPrepKernel");
             }
             sortSegments(ctx, hits.p, extSegs.p, counters.p + 8, Pn, ws, "chain_extsort_top", "chain_extsort_small", sortCfgPairs());
@@ -1856,7 +1889,6 @@ static void overlapsChunk(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, ui
                 Run* runs = reinterpret_cast<Run*>(cands.p);
                 if (dpMode == 2) {
                     PhaseTimer pt(ctx, "chain_runs");
-                    nRuns.alloc(Pn);
                     chainRunsKernel<<<(Pn + 7) / 8, 256, 0, ctx->stream>>>(hits.p, pairInfo.p, pairIds.p, Pn, pairFlags.p, k, runs, back.p, nRuns.p);
                     checkLaunch(ctx, "chainRunsKernel");
                 }

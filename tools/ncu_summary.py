@@ -41,7 +41,12 @@ def launches(path):
 
 
 def full(path):
-    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], stdout=subprocess.PIPE, text=True).stdout
+    """path: a .ncu-rep, or the CSV that `ncu -i rep --page raw --csv` printed on the GPU box (the report itself stays there:
+    gpurun only brings back 64 MiB)"""
+    if path.endswith(".csv"):
+        raw = open(path).read()
+    else:
+        raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], stdout=subprocess.PIPE, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units = rows[0], rows[1]
     idx = [(k, hdr.index(k)) for k in KEY if k in hdr]
@@ -50,7 +55,7 @@ def full(path):
     for r in rows[2:]:
         name = r[ni].split("(")[0]
         seen[name] += 1
-        if seen[name] > 2:
+        if seen[name] > (int(sys.argv[3]) if len(sys.argv) > 3 else 2):
             continue
         print("--- %s (launch %d)" % (name, seen[name]))
         for k, i in idx:
