@@ -524,6 +524,89 @@ __global__ void __launch_bounds__(128) minimizerKernel(const uint64_t* __restric
     }
 }
 
+// The same walk with the deque in REGISTERS (window < CAP): the generic kernel keeps 64 (position, hash) slots per thread
+// in local memory, 1.5 MB per SM at full occupancy — every deque access is an L2 round trip and the kernel is bound by
+// that latency (ncu: 54 warps stalled on the long scoreboard per issue, 17 % of the DRAM peak).  The deque's hashes are
+// non-decreasing from front to back and its positions increase, so "pop_back while back.hash > h" is a prefix count,
+// and pops from the front are shifts of a small array; with compile-time indices everything stays in registers.
+template <int CAP>
+__global__ void __launch_bounds__(128) minimizerRegKernel(const uint64_t* __restrict__ seq, const uint64_t* __restrict__ wordOff,
+                                                          const uint32_t* __restrict__ len, const uint64_t* __restrict__ slotOff,
+                                                          const uint2* __restrict__ tiles, uint32_t nChunks, int k, int window,
+                                                          uint32_t* __restrict__ selBits, uint32_t* __restrict__ rcBits) {
+    const uint32_t ci = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ci >= nChunks) return;
+    const uint2 tile = tiles[ci >> 2];
+    const uint32_t r = tile.x;
+    const int32_t n = (int32_t)(len[r] - k);
+    const int32_t c0 = (int32_t)tile.y + (int32_t)(ci & 3) * MIN_CHUNK;
+    if (c0 >= n) return;
+    const int32_t c1 = min(n, c0 + MIN_CHUNK);
+    const uint64_t* words = seq + wordOff[r];
+    const uint64_t base = slotOff[r] >> 5;
+    const uint64_t mask = kmerMask(k);
+    uint64_t qh[CAP]; int32_t qp[CAP];   // front = slot 0
+
+    for (int32_t warm = MIN_WARM;; warm *= 4) {
+        const int32_t start = max(0, c0 - warm);
+        bool locked = start == 0;
+        int size = 0;
+#pragma unroll
+        for (int j = 0; j < CAP; ++j) { qh[j] = 0; qp[j] = 0; }
+        int32_t lastEmitted = -1;
+        uint32_t selWord = 0, rcWord = 0;
+        uint64_t v = windowAt(words, (uint32_t)start, k);
+        uint64_t wcur = words[((uint32_t)start + k) >> 5];   // the word of the next base to shift in
+        bool failed = false;
+        for (int32_t p = start; p < c1; ++p) {
+            if (p > start) {
+                const uint32_t q = (uint32_t)p + k - 1;
+                if ((q & 31) == 0) wcur = words[q >> 5];
+                const uint64_t b = (wcur >> ((q & 31) * 2)) & 3ULL;
+                v = (v >> 2) | (b << (2 * k - 2));
+            }
+            if (p == c0 && !locked) { failed = true; break; }
+            const uint64_t f = fwdFromWindow(v, k), rcv = (~v) & mask;
+            const bool isRc = rcv < f;
+            if (p >= c0 && isRc) rcWord |= 1u << (p & 31);
+            const uint64_t h = splitmix64(isRc ? rcv : f);
+            int cnt = 0;   // pop_back while back.hash > h
+#pragma unroll
+            for (int j = 0; j < CAP; ++j) cnt += (j < size && qh[j] <= h) ? 1 : 0;
+            if (!locked && cnt == 0 && p - start >= window) { locked = true; lastEmitted = -1; }
+#pragma unroll
+            for (int j = 0; j < CAP; ++j) if (j == cnt) { qh[j] = h; qp[j] = p; }
+            size = cnt + 1;
+            if (qp[0] <= p - window) {
+                while (qp[0] <= p - window) {
+#pragma unroll
+                    for (int j = 0; j + 1 < CAP; ++j) { qh[j] = qh[j + 1]; qp[j] = qp[j + 1]; }
+                    --size;
+                }
+                while (size >= 2 && qh[0] == qh[1]) {
+#pragma unroll
+                    for (int j = 0; j + 1 < CAP; ++j) { qh[j] = qh[j + 1]; qp[j] = qp[j + 1]; }
+                    --size;
+                }
+            }
+            const int32_t emit = qp[0];
+            if (locked && emit != lastEmitted) {
+                lastEmitted = emit;
+                if (p >= c0) {   // the emissions of this chunk's steps are this thread's to report
+                    if ((emit >> 5) == (p >> 5)) selWord |= 1u << (emit & 31);
+                    else atomicOr(&selBits[base + (emit >> 5)], 1u << (emit & 31));
+                }
+            }
+            if (p >= c0 && ((p & 31) == 31 || p == c1 - 1)) {
+                if (selWord) atomicOr(&selBits[base + (p >> 5)], selWord);
+                rcBits[base + (p >> 5)] = rcWord;
+                selWord = 0; rcWord = 0;
+            }
+        }
+        if (!failed) break;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // K5: emission in global-position order.  An "etile" is (tile, strand).  For every read the forward-strand
 // etiles come first with positions ascending, then the reverse-strand etiles with positions descending, so the
@@ -907,8 +990,10 @@ void buildIndexMinimizers(fg_ctx* ctx, int k, int minCov, int window, float repe
             tileRange(ctx, firstRead, nReadsShard, tLo, tHi);
             const uint32_t nChunks = (uint32_t)(tHi - tLo) * (TILE_SLOTS / MIN_CHUNK);
             if (nChunks) {
-                minimizerKernel<<<(nChunks + 127) / 128, 128, 0, ctx->stream>>>(ctx->dSeq.p, ctx->dWordOff.p, ctx->dLen.p, ctx->dSlotOff.p,
-                                                                               ctx->dTiles.p + tLo, nChunks, k, window, ctx->dSelBits.p, rcBits.p);
+                static const bool regDeque = getenv("FG_MINIMIZER_GENERIC") == nullptr;
+                auto kern = (regDeque && window >= 2 && window < 15) ? minimizerRegKernel<16> : minimizerKernel;
+                kern<<<(nChunks + 127) / 128, 128, 0, ctx->stream>>>(ctx->dSeq.p, ctx->dWordOff.p, ctx->dLen.p, ctx->dSlotOff.p,
+                                                                    ctx->dTiles.p + tLo, nChunks, k, window, ctx->dSelBits.p, rcBits.p);
                 checkLaunch(ctx, "minimizerKernel");
             }
         }

@@ -233,12 +233,15 @@ __global__ void __launch_bounds__(SEG_WARPS * 32, 3) segRadixSortKernel(unsigned
     uint32_t (*nxt)[256] = hist[1];
     for (int i = threadIdx.x; i < SEG_WARPS * 256; i += blockDim.x) (&cur[0][0])[i] = 0u;
     __syncthreads();
+    unsigned long long xn = wBeg + lane < wEnd ? src[wBeg + lane] : 0ULL;   // register prefetch: the load of step t+1 overlaps step t
     for (uint32_t i0 = wBeg; i0 < wEnd; i0 += 32) {   // counts of the first pass
         const uint32_t i = i0 + lane;
         const bool act = i < wEnd;
         const uint32_t am = __ballot_sync(0xffffffffu, act);
+        const unsigned long long xc = xn;
+        if (i + 32 < wEnd) xn = src[i + 32];
         if (act) {
-            const uint32_t d = (uint32_t)(src[i] >> idShift) & 255u;
+            const uint32_t d = (uint32_t)(xc >> idShift) & 255u;
             const uint32_t peers = __match_any_sync(am, d);
             if ((peers & ((1u << lane) - 1u)) == 0u) cur[w][d] += __popc(peers);
         }
@@ -269,12 +272,14 @@ __global__ void __launch_bounds__(SEG_WARPS * 32, 3) segRadixSortKernel(unsigned
         __syncthreads();
         for (int i = threadIdx.x; i < SEG_WARPS * 256; i += blockDim.x) (&nxt[0][0])[i] = 0u;
         __syncthreads();
+        xn = wBeg + lane < wEnd ? src[wBeg + lane] : 0ULL;
         for (uint32_t i0 = wBeg; i0 < wEnd; i0 += 32) {
             const uint32_t i = i0 + lane;
             const bool act = i < wEnd;
             const uint32_t am = __ballot_sync(0xffffffffu, act);
+            const unsigned long long x = xn;
+            if (i + 32 < wEnd) xn = src[i + 32];
             if (act) {
-                const unsigned long long x = src[i];
                 const uint32_t d = (uint32_t)(x >> sh) & 255u;
                 const uint32_t peers = __match_any_sync(am, d);
                 const uint32_t o = base[d] + cur[w][d];
@@ -1264,7 +1269,7 @@ __global__ void __launch_bounds__(256) pairSizeKeyKernel(const PairInfo* __restr
 // primary selection (:431-458).  One warp per pair: the back-pointer table is staged in shared memory (the walk is
 // pure pointer chasing, so its latency is what matters), the lanes test 32 chain starts at a time and lane 0
 // walks the chains in order, re-testing the remaining starts after every walk because a walk consumes pointers.
-static constexpr int WALK_CAP = 4096;   // matches per warp whose back pointers are staged in shared memory as 16-bit deltas (8 KB)
+static constexpr int WALK_CAP = 2048;   // matches per warp whose back pointers are staged in shared memory as 16-bit deltas (4 KB)
 
 // RUNS = true (after the run-compressed DP): the walk goes run by run.  Inside a run every match points to its
 // predecessor, and every walk that enters a run continues down to the run's head or to an already consumed match, so the
