@@ -247,7 +247,14 @@ def main():
         # all-gathered (a few KB) so that every rank derives the same threshold
         my_est = np.asarray(est_ids[rank::world], dtype=np.uint32)
         all_q = np.concatenate([my_est, queries])
-        offs, ov, ovl_stats = eng.overlaps(all_q, max_divergence=1.0, copy=False, **common)
+        # Presets with an ABSOLUTE threshold (asm_hifi: assemble_divergence_relative = 0) know it before the estimate: the main
+        # queries carry it (per-query thresholds), so the library can stop the edit-distance work of an overlap as soon as
+        # it cannot pass; the estimate queries stay unfiltered (1.0) as in overlap.cpp:744-790.
+        relative = bool(cfg["assemble_divergence_relative"])
+        qthr = None
+        if not relative:
+            qthr = np.concatenate([np.full(len(my_est), 1.0, np.float32), np.full(len(queries), np.float32(cfg["assemble_ovlp_divergence"]), np.float32)])
+        offs, ov, ovl_stats = eng.overlaps(all_q, max_divergence=1.0, copy=False, query_max_divergence=qthr, **common)
         first = int(offs[len(my_est)])
         rng_est = ov["cur_end"][:first] - ov["cur_begin"][:first]
         div_all = ov["seq_divergence"]
@@ -273,7 +280,7 @@ def main():
                 g = g.cpu().numpy()
                 divs.extend(g[1:1 + int(g[0])].tolist())
         mean = pu.median_f32(divs) if divs else np.float32(0.5)
-        max_div = np.float32((mean if bool(cfg["assemble_divergence_relative"]) else np.float32(0.0)) + np.float32(cfg["assemble_ovlp_divergence"]))
+        max_div = np.float32((mean if relative else np.float32(0.0)) + np.float32(cfg["assemble_ovlp_divergence"]))
         keep = div_all[first:] < max_div
         lap("overlaps")
         grab()
@@ -327,27 +334,27 @@ def main():
     value = total_reads / (ms_resident / 1e3)
     e2e_value = total_reads / (ms_e2e / 1e3)
     h2d = int(packed.nbytes + woff.nbytes + lens.nbytes + 4 * (len(queries) + len(est_ids)))
-    d2h = int(72 * n_raw[0] + 8 * (len(queries) + len(est_ids) + 1))
+    raw_records = int(resident_phases.get("raw_overlaps", n_raw[0])) * world   # records the library copied back (before the threshold)
+    d2h = int(72 * max(raw_records, n_raw[0]) + 8 * (len(queries) + len(est_ids) + 1))
 
     # roofline (algorithmic bytes: SURVEY.md §8d stage formulas, assigned to kernels in DESIGN.md §4).  Only phases that
     # consist of ONE launch of one of our kernels are listed; their durations are CUDA-event times on the library's stream.
     M, O = stats.get("n_hits", 0), n_ovl
     w = 4 if 2 * k <= 32 else 8
     n_k = n_bases - k * n_reads
-    raw_ovl = n_raw[0]
+    raw_ovl = int(resident_phases.get("raw_overlaps", n_raw[0]))
     mean_ovl_len = float(np.mean(np.maximum(ovl_len_sample, 1))) if len(ovl_len_sample) else 0.0
     alg = {"expand": 20.0 * M,                       # K6, per-hit part: 8 B index entry read + 12 B match written
-           "hit_sort_gather": 24.0 * M,              # K7: 12 B record read + 12 B record written, once
-           "hit_sort_small": 24.0 * M,               # K7 (exact path; only the ranges with ties since the radix fast path)
-           "chain_runs": 12.0 * M,                   # K8: one read of the matches
+           "hit_sort_radix": 24.0 * M,               # K7: 12 B record read + 12 B record written, once
+           "chain_prep": 12.0 * M,                   # K8: one read of the matches (runs found on the way)
            "chain_dp": 12.0 * M + 40.0 * O,          # K8
            "chain_fill": 12.0 * M + 40.0 * O,        # K8: one read of the matches, scores / back pointers written
            "chain_walk": 12.0 * M + 40.0 * O,        # K8
            "edit": raw_ovl * 2.0 * mean_ovl_len / 4.0,   # K9: (len_q + len_t) / 4 bytes per overlap
            "select": (w + 5.0) * n_k, "extract": 0.25 * n_bases + w * n_k}
-    names = {"expand": "expandKernel", "hit_sort_gather": "gatherSortedHitsKernel", "hit_sort_small": "sortSmallKernel",
-             "chain_runs": "chainRunsKernel", "chain_dp": "chainRunDpKernel", "chain_fill": "chainFillKernel",
-             "chain_walk": "chainWalkKernel", "edit": "wfaKernel", "select": "selectKernel", "extract": "extractKeysKernel"}
+    names = {"expand": "expandKernel", "hit_sort_radix": "segRadixSortKernel", "chain_prep": "pairPrepKernel",
+             "chain_dp": "chainRunDpKernel", "chain_fill": "chainFillKernel", "chain_walk": "chainWalkKernel", "edit": "wfaKernel",
+             "select": "minimizerRegKernel" if int(cfg["use_minimizers"]) else "selectKernel", "extract": "extractKeysKernel"}
     bounds = {"edit": "integer issue (O(ND) wavefronts; bytes are negligible by construction)",
               "chain_dp": "latency / integer issue (sequential scan over run heads)", "chain_walk": "latency (pointer chasing in shared memory)"}
     # DRAM bytes per k-mer hit from `ncu --set full` captures (profiles/README.md: dram__bytes_read.sum + dram__bytes_write.sum
@@ -371,7 +378,7 @@ def main():
     if roofline_kernels:
         roofline = dict(roofline_kernels[0])
         roofline["traffic_source"] = "bytes per hit measured with ncu --set full (profiles/), scaled to this launch's hits"
-    lib_ms = resident_phases.get("hit_sort_radix", 0.0)
+    lib_ms = resident_phases.get("hit_sort_radix_lib", 0.0)
 
     line = {"metric": "reads/sec through k-mer index + overlap detection", "value": value, "unit": "reads/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_resident, "higher_is_better": True, "scaling": "strong",

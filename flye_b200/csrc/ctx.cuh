@@ -5,6 +5,7 @@
 #include <condition_variable>
 #include <functional>
 #include <map>
+#include <memory>
 #include <thread>
 #include <utility>
 
@@ -129,6 +130,8 @@ struct fg_ctx {
     std::vector<int32_t> resAln;
     fg::PinnedBuf<fg_overlap> pinnedOut;  // D2H staging, kept across calls
     fg::HostPool hostPool;
+    std::unique_ptr<fg_overlap[]> resCompact;   // results after the divergence / maxOverlaps filter (when it removed something)
+    size_t resCompactCap = 0;
 
     // ---- NCCL ----
     void* ncclComm = nullptr;
@@ -202,7 +205,8 @@ void groupStart();
 void groupEnd();
 inline bool sharded(const fg_ctx* ctx) { return ctx->nRanks > 1 && ctx->ncclComm && ctx->shardSet; }
 
-void editDistances(fg_ctx* ctx, fg_overlap* dOv, const fg_overlap* hOv, uint32_t nOv, bool useHpc, bool querySet);
+void editDistances(fg_ctx* ctx, fg_overlap* dOv, const fg_overlap* hOv, uint32_t nOv, bool useHpc, bool querySet, float maxDivergence,
+                   const float* dQueryMaxDivergence);
 int debugEditDistance(fg_ctx* ctx, const uint8_t* a, int n, const uint8_t* b, int m, int rcA, int rcB);
 void debugWarpSort(fg_ctx* ctx, uint64_t* keys, uint32_t* vals, const uint64_t* segOffsets, uint32_t nSegs);
 

@@ -162,10 +162,13 @@ __device__ int wfaSteps(const SeqView& A, const SeqView& B, int*& prev, int*& cu
     return -1;
 }
 
-// exact global edit distance of the two views; one warp.  smem: 2 * WF_SMEM_INTS ints; gA/gB: n + m + 8 ints each.
-__device__ int wfaEditDistance(const SeqView& A, const SeqView& B, int* smem, int* gA, int* gB) {
+// exact global edit distance of the two views, or `limit` as soon as the distance is known to be >= limit; one warp.
+// smem: 2 * WF_SMEM_INTS ints; gA/gB: n + m + 8 ints each.
+__device__ int wfaEditDistance(const SeqView& A, const SeqView& B, int* smem, int* gA, int* gB, int limit = 0x7fffffff) {
     const int lane = threadIdx.x & 31;
     const int n = A.n, m = B.n;
+    if (limit <= 0) return limit;
+    if (abs(n - m) >= limit) return limit;   // the length difference alone costs that many edits
     if (n == 0) return m;
     if (m == 0) return n;
     int* prev = smem; int* cur = smem + WF_SMEM_INTS;
@@ -174,16 +177,19 @@ __device__ int wfaEditDistance(const SeqView& A, const SeqView& B, int* smem, in
     if (m == n && i0 >= n) return 0;
     if (lane == 0) prev[base] = i0;
     __syncwarp();
-    const int dCap = min(WF_DMAX, n + m);
+    const int sMax = min(n + m, limit - 1);   // steps worth taking: beyond them the distance is >= limit
+    const int dCap = min(WF_DMAX, sMax);
     int d = wfaSteps(A, B, prev, cur, base, 1, dCap, lane);
-    if (d >= 0 || dCap == n + m) return d;
+    if (d >= 0) return d;
+    if (dCap == sMax) return sMax == n + m ? d : limit;
     // continue in global memory
     const int gBase = n + 2;
     const int plo = max(-dCap, -n), phi = min(dCap, m);
     for (int k = plo + lane; k <= phi; k += 32) gA[k + gBase] = prev[k + base];
     __syncwarp();
     prev = gA; cur = gB;
-    return wfaSteps(A, B, prev, cur, gBase, dCap + 1, n + m, lane);
+    d = wfaSteps(A, B, prev, cur, gBase, dCap + 1, sMax, lane);
+    return (d < 0 && sMax < n + m) ? limit : d;
 }
 
 struct HpcSet { const uint64_t* seq; const uint64_t* hpc; const uint32_t* mask; const uint32_t* prefix; const uint64_t* wordOff; const uint32_t* len; };
@@ -209,8 +215,24 @@ __device__ SeqView makeView(const HpcSet& S, uint32_t id, int32_t begin, int32_t
     return v;
 }
 
+// The divergence filter (overlap.cpp:470-473) keeps an overlap iff (float)editDistance / alnLen < maxDivergence, so an
+// overlap whose distance reaches T = the smallest integer with (float)T / alnLen >= maxDivergence is dropped whatever the
+// exact value is: the wavefronts stop there and T is reported.  (Most of the cost used to be spent on exactly those
+// overlaps — two thirds of the HiFi candidates fail the 1 % threshold, with distances far beyond it.)
+__device__ __forceinline__ int dropLimit(float maxDiv, int alnLen) {
+    if (alnLen <= 0) return 0x7fffffff;
+    if (!(maxDiv > 0.f)) return 0;   // nothing passes a threshold <= 0 (or NaN)
+    const float L = (float)alnLen;
+    long long T = (long long)ceilf(__fmul_rn(maxDiv, L));
+    if (T > 0x7ffffff0LL) return 0x7fffffff;
+    while (T > 0 && __fdiv_rn((float)(T - 1), L) >= maxDiv) --T;
+    while (T < 0x7ffffff0LL && __fdiv_rn((float)T, L) < maxDiv) ++T;
+    return (int)T;
+}
+
 __global__ void __launch_bounds__(128) wfaKernel(fg_overlap* __restrict__ ov, uint32_t nOv, HpcSet cur, HpcSet ext, bool compress,
-                                                 int* __restrict__ wfScratch, uint64_t wfStride, uint32_t* __restrict__ nextJob) {
+                                                 int* __restrict__ wfScratch, uint64_t wfStride, uint32_t* __restrict__ nextJob,
+                                                 float maxDiv, const float* __restrict__ queryMaxDiv) {
     __shared__ int wfSm[4][2 * WF_SMEM_INTS];
     const uint32_t warpGlobal = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
@@ -224,7 +246,8 @@ __global__ void __launch_bounds__(128) wfaKernel(fg_overlap* __restrict__ ov, ui
         const fg_overlap o = ov[j];
         const SeqView A = makeView(cur, o.cur_id, o.cur_begin, o.cur_end, compress);
         const SeqView B = makeView(ext, o.ext_id, o.ext_begin, o.ext_end, compress);
-        const int d = wfaEditDistance(A, B, wfSm[threadIdx.x >> 5], gA, gB);
+        const int limit = dropLimit(queryMaxDiv ? queryMaxDiv[o.reserved] : maxDiv, max(A.n, B.n));
+        const int d = wfaEditDistance(A, B, wfSm[threadIdx.x >> 5], gA, gB, limit);
         if (lane == 0) { ov[j].edit_distance = d; ov[j].aln_len = max(A.n, B.n); }
         __syncwarp();
     }
@@ -245,7 +268,8 @@ static void buildHpc(fg_ctx* ctx, fg_ctx::HpcCache& c, const uint64_t* seq, cons
 
 // device overlaps (already gathered) -> edit_distance / aln_len filled in.  querySet: the "cur" side refers to the second
 // sequence set (fg_queries_upload).
-void editDistances(fg_ctx* ctx, fg_overlap* dOv, const fg_overlap* hOv, uint32_t nOv, bool useHpc, bool querySet) {
+void editDistances(fg_ctx* ctx, fg_overlap* dOv, const fg_overlap* hOv, uint32_t nOv, bool useHpc, bool querySet, float maxDivergence,
+                   const float* dQueryMaxDivergence) {
     if (!nOv) return;
     uint32_t maxLen = 0;
     for (uint32_t i = 0; i < nOv; ++i)
@@ -267,7 +291,7 @@ void editDistances(fg_ctx* ctx, fg_overlap* dOv, const fg_overlap* hOv, uint32_t
     const int blocks = 148 * 10, warps = blocks * 4;   // 48 registers / thread: 40 resident warps per SM
     const uint64_t stride = 2ULL * maxLen + 8;
     DevBuf<int> wf((uint64_t)warps * 2 * stride);   // only touched by overlaps with more than WF_DMAX edits
-    wfaKernel<<<blocks, 128, 0, ctx->stream>>>(dOv, nOv, cur, ext, useHpc, wf.p, stride, nextJob.p);
+    wfaKernel<<<blocks, 128, 0, ctx->stream>>>(dOv, nOv, cur, ext, useHpc, wf.p, stride, nextJob.p, maxDivergence, dQueryMaxDivergence);
     checkLaunch(ctx, "wfaKernel");
     FG_CUDA(cudaStreamSynchronize(ctx->stream));
 }

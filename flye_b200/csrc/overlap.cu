@@ -1641,7 +1641,7 @@ static uint32_t selectFlagged(fg_ctx* ctx, const FlagT* flags, uint32_t n, DevBu
 // one chunk of queries (< 2^30 k-mer slots): lookup, expansion and the per-sub-batch pipeline; the raw overlap records are
 // appended to the context's pinned buffer with `reserved` = position of the query in the whole call
 static void overlapsChunk(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, uint32_t qOffset, const fg_overlap_params& prm, const OvParams& P,
-                          size_t& nRaw, uint64_t& totHits, uint64_t& totPairs, uint64_t& totDpPairs, uint64_t& totCells, uint64_t& totTied, uint64_t& totPresorted) {
+                          size_t& nRaw, uint64_t& totHits, uint64_t& totPairs, uint64_t& totDpPairs, uint64_t& totCells, uint64_t& totTied, uint64_t& totPresorted, const float* dQueryMaxDiv) {
     const int k = ctx->k;
     // where the query sequences live: the indexed reads themselves, or the second set of fg_queries_upload
     const std::vector<uint32_t>& qHLen = P.sameSet ? ctx->hLen : ctx->hQsLen;
@@ -2001,7 +2001,7 @@ static void overlapsChunk(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, ui
                 if (prm.nucl_alignment) {   // overlap.cpp:463-468
                     if (nOut >= (1ULL << 31)) throw Error(FG_ERR_ARG, "too many overlaps in one sub-batch");
                     PhaseTimer pe(ctx, "edit");
-                    editDistances(ctx, dOut.p, dst, (uint32_t)nOut, prm.use_hpc != 0, !P.sameSet);
+                    editDistances(ctx, dOut.p, dst, (uint32_t)nOut, prm.use_hpc != 0, !P.sameSet, prm.max_divergence, dQueryMaxDiv);
                     FG_CUDA(cudaMemcpyAsync(dst, dOut.p, nOut * sizeof(fg_overlap), cudaMemcpyDeviceToHost, ctx->stream));
                     FG_CUDA(cudaStreamSynchronize(ctx->stream));
                 }
@@ -2037,6 +2037,11 @@ void overlapsBatch(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, const fg_
     HostTimer hostAll(ctx, "host_total");
     const uint64_t mallocs0 = ctx->arena.mallocCalls;
 
+    DevBuf<float> dQueryMaxDiv;   // per-query divergence thresholds (optional), indexed like the records' `reserved`
+    if (prm.query_max_divergence && nQ) {
+        dQueryMaxDiv.alloc(nQ);
+        FG_CUDA(cudaMemcpyAsync(dQueryMaxDiv.p, prm.query_max_divergence, nQ * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    }
     // chunks of consecutive queries with < 2^30 k-mer slots each (device arrays are indexed with 32-bit counts)
     uint64_t chunkSlots = 1ULL << 30;
     if (const char* e = getenv("FG_CHUNK_SLOTS")) chunkSlots = std::max<uint64_t>(4096, std::min<uint64_t>(chunkSlots, strtoull(e, nullptr, 10)));
@@ -2049,7 +2054,7 @@ void overlapsBatch(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, const fg_
             if (q1 > q0 && slots + add >= chunkSlots) break;
             slots += add; ++q1;
         }
-        overlapsChunk(ctx, queryIds + q0, q1 - q0, q0, prm, P, nRaw, totHits, totPairs, totDpPairs, totCells, totTied, totPresorted);
+        overlapsChunk(ctx, queryIds + q0, q1 - q0, q0, prm, P, nRaw, totHits, totPairs, totDpPairs, totCells, totTied, totPresorted, dQueryMaxDiv.p);
         q0 = q1;
     }
 
@@ -2093,8 +2098,9 @@ void overlapsBatch(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, const fg_
                 size_t end = pos;   // one target group = run of equal ext_id
                 while (end < qEnd && hOut[end].ext_id == hOut[pos].ext_id) ++end;
                 const bool stop = prm.max_overlaps != 0 && detected >= (size_t)prm.max_overlaps;
+                const float maxDiv = prm.query_max_divergence ? prm.query_max_divergence[q] : prm.max_divergence;
                 for (size_t i = pos; i < end; ++i) {
-                    const bool keep = !stop && hOut[i].seq_divergence < prm.max_divergence;
+                    const bool keep = !stop && hOut[i].seq_divergence < maxDiv;
                     hOut[i].reserved = keep ? 0u : 0xffffffffu;
                     detected += keep;
                 }
@@ -2105,15 +2111,26 @@ void overlapsBatch(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, const fg_
     });
     size_t wpos = 0;
     for (uint32_t q = 0; q < nQ; ++q) { ctx->resOffsets[q] = wpos; wpos += kept[q]; }
-    if (wpos != nRaw) {   // compact in place (records only ever move towards the front)
-        size_t w2 = 0;
-        for (size_t i = 0; i < nRaw; ++i)
-            if (hOut[i].reserved == 0u) { if (w2 != i) hOut[w2] = hOut[i]; ++w2; }
-    }
     ctx->resOffsets[nQ] = wpos;
+    if (wpos != nRaw) {   // compact: the kept records of every query go to their final place in a second buffer, in parallel
+        if (ctx->resCompactCap < wpos) {
+            ctx->resCompactCap = wpos + wpos / 4 + 16;
+            ctx->resCompact.reset(new fg_overlap[ctx->resCompactCap]);
+        }
+        fg_overlap* dst = ctx->resCompact.get();
+        parallelFor(nQ, [&](size_t qa, size_t qb) {
+            for (size_t q = qa; q < qb; ++q) {
+                size_t w2 = ctx->resOffsets[q];
+                for (size_t i = qStart[q]; i < qStart[q + 1]; ++i)
+                    if (hOut[i].reserved == 0u) dst[w2++] = hOut[i];
+            }
+        });
+        hOut = dst;
+    }
 
     ctx->timings.emplace_back("arena_mallocs", (float)(ctx->arena.mallocCalls - mallocs0)); ctx->timingCalls.push_back(1);
     ctx->timings.emplace_back("arena_gib", (float)(ctx->arena.totalBytes / 1073741824.0)); ctx->timingCalls.push_back(1);
+    ctx->timings.emplace_back("raw_overlaps", (float)nRaw); ctx->timingCalls.push_back(1);   // records copied device -> host (before the divergence filter)
     ctx->timings.emplace_back("tied_queries", (float)totTied); ctx->timingCalls.push_back(1);   // queries that needed the exact hit sort
     ctx->timings.emplace_back("presorted_pairs", (float)totPresorted); ctx->timingCalls.push_back(1);   // pairs whose score order needed no sort
     result->n_queries = nQ;

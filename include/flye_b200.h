@@ -114,6 +114,11 @@ typedef struct {
     int32_t use_hpc;              /* _useHpc                                                             */
     float   max_divergence;       /* _maxDivergence                                                      */
     int32_t query_set;            /* 0: query ids name the indexed reads; 1: the set of fg_queries_upload  */
+    const float* query_max_divergence; /* optional (NULL = max_divergence for every query): n_queries thresholds, one per
+                                          query.  estimateOverlaperParameters' unfiltered sample (threshold 1.0,
+                                          overlap.cpp:744-790) can then share a batch with the thresholded main pass.  With
+                                          nucl_alignment the threshold also bounds the edit-distance work: an overlap that
+                                          cannot pass it (overlap.cpp:470-473) is dropped without finishing its alignment */
 } fg_overlap_params;
 
 typedef struct {                  /* OverlapRange (overlap.h:20-279) plus what seqDivergence is made of  */

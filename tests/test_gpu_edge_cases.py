@@ -106,3 +106,34 @@ def test_query_list_shapes(engine, tmp_path):
     assert (per[2]["cur_id"] == 3).all() and (per[5]["cur_id"] == 2).all()
     with pytest.raises(fb.FlyeB200Error):
         engine.overlaps([10])                                           # id out of range -> FG_ERR_ARG
+
+
+def test_per_query_divergence_thresholds(engine, tmp_path):
+    """fg_overlap_params.query_max_divergence: every query is filtered with its own threshold (estimate queries at 1.0 next to
+    thresholded ones in one batch), and the threshold-bounded edit distance never changes a kept record: the overlaps kept at
+    0.01 are exactly the records of the unfiltered run whose divergence is below 0.01."""
+    import flye_b200 as fb
+    cfg = pu.load_cfg(os.path.join(pu.CFG_DIR, "hifi.cfg"))
+    reads_path = pu.simulate(os.path.join(str(tmp_path), "h.fasta"), genome_len=120000, coverage=15, mean_len=12000, shape=20, error=0.01, seed=21)
+    reads = fb.read_fasta(reads_path, 1000)
+    engine.upload_ascii(reads)
+    engine.build_index_minimizers(17, 1, int(cfg["minimizer_window"]), cfg["repeat_kmer_rate"])
+    common = dict(max_jump=int(cfg["maximum_jump"]), min_overlap=1000, max_overhang=int(cfg["maximum_overhang"]), only_max_ext=True,
+                  nucl_alignment=True, use_hpc=True)
+    q = np.arange(0, min(2 * len(reads), 120), dtype=np.uint32)
+    thr = np.where(np.arange(len(q)) % 3 == 0, 1.0, 0.01).astype(np.float32)
+    off_a, ov_a, _ = engine.overlaps(q, max_divergence=1.0, **common)
+    off_b, ov_b, _ = engine.overlaps(q, max_divergence=0.01, **common)
+    off_m, ov_m, _ = engine.overlaps(q, max_divergence=0.5, query_max_divergence=thr, **common)
+    fields = ["cur_id", "cur_begin", "cur_end", "ext_id", "ext_begin", "ext_end", "score", "seq_divergence", "edit_distance", "aln_len"]
+    n_low = n_all = 0
+    for i in range(len(q)):
+        a = ov_a[int(off_a[i]):int(off_a[i + 1])]
+        b = ov_b[int(off_b[i]):int(off_b[i + 1])]
+        m = ov_m[int(off_m[i]):int(off_m[i + 1])]
+        want_b = a[a["seq_divergence"] < np.float32(0.01)]
+        for f in fields:
+            assert np.array_equal(b[f], want_b[f]), (i, f)
+            assert np.array_equal(m[f], (a if thr[i] == 1.0 else want_b)[f]), (i, f)
+        n_low += len(want_b); n_all += len(a)
+    assert 0 < n_low < n_all      # the threshold really removes overlaps on this input (1 % error per read)
