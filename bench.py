@@ -281,11 +281,14 @@ def main():
                 divs.extend(g[1:1 + int(g[0])].tolist())
         mean = pu.median_f32(divs) if divs else np.float32(0.5)
         max_div = np.float32((mean if relative else np.float32(0.0)) + np.float32(cfg["assemble_ovlp_divergence"]))
-        keep = div_all[first:] < max_div
         lap("overlaps")
         grab()
-        n_ovl = int(np.count_nonzero(keep))
         n_raw[0] = int(offs[-1])
+        if relative:   # setDivergenceThreshold (overlap.cpp:817-827): the library re-applies the threshold to the main queries
+            offs, ov = eng.refilter(len(my_est), float(max_div), len(all_q))
+            div_all = ov["seq_divergence"]
+            lap("refilter")
+        n_ovl = int(offs[-1]) - int(offs[len(my_est)])
         ovl_len_sample = (ov["cur_end"][first:first + 20000] - ov["cur_begin"][first:first + 20000]).astype(np.float64)
         edit_sample[0] = float(np.mean(ov["edit_distance"][first:first + 20000])) if common["nucl_alignment"] and len(ov) > first else None
         lap("filter")

@@ -21,7 +21,7 @@ ERR_NAMES = {-1: "FG_ERR_CUDA", -2: "FG_ERR_ARG", -3: "FG_ERR_KMER_SIZE", -4: "F
 SYMBOLS = ["fg_ctx_create", "fg_ctx_destroy", "fg_last_error", "fg_stream", "fg_kernel_launches", "fg_last_timings",
            "fg_reads_upload", "fg_reads_upload_ascii", "fg_queries_upload", "fg_count_kmers", "fg_kmer_hist", "fg_kmer_freq",
            "fg_build_index_solid", "fg_build_index_minimizers", "fg_index_clear", "fg_index_lookup",
-           "fg_index_positions", "fg_index_export", "fg_overlaps_batch", "fg_comm_unique_id", "fg_comm_init",
+           "fg_index_positions", "fg_index_export", "fg_overlaps_batch", "fg_overlaps_refilter", "fg_comm_unique_id", "fg_comm_init",
            "fg_comm_set_shard", "fg_debug_warp_sort", "fg_debug_edit_distance", "fg_debug_edit_distance_rc"]
 
 
@@ -87,6 +87,7 @@ def load_lib():
     lib.fg_index_positions.argtypes = [vp, C.c_uint64, C.c_uint32, C.c_int, u32p, i32p]
     lib.fg_index_export.argtypes = [vp, u64p, u8p, u64p, u32p, u64p, u32p, i32p, u64p]
     lib.fg_overlaps_batch.argtypes = [vp, u32p, C.c_uint32, C.POINTER(OverlapParams), C.POINTER(OverlapResult)]
+    lib.fg_overlaps_refilter.argtypes = [vp, C.c_uint32, C.c_float, C.POINTER(OverlapResult)]
     lib.fg_comm_unique_id.argtypes = [u8p]
     lib.fg_comm_init.argtypes = [vp, C.c_int, C.c_int, u8p]
     lib.fg_comm_set_shard.argtypes = [vp, C.c_uint32, C.c_uint32]
@@ -281,6 +282,20 @@ class Engine:
             npts = int(res.n_aln_pairs)
             stats["aln_pairs"] = (np.ctypeslib.as_array(res.aln_pairs, shape=(npts, 2)).copy() if npts else np.zeros((0, 2), np.int32))
         return offsets, ov, stats
+
+    def refilter(self, first_query, max_divergence, n_queries, copy=False):
+        """fg_overlaps_refilter: drop the overlaps with seq_divergence >= max_divergence of the queries from first_query on
+        (last overlaps() result); returns (offsets, overlaps) like overlaps()."""
+        res = OverlapResult()
+        self._check(self.lib.fg_overlaps_refilter(self.ctx, C.c_uint32(first_query), C.c_float(max_divergence), C.byref(res)))
+        offsets = np.ctypeslib.as_array(res.offsets, shape=(n_queries + 1,))
+        n = int(offsets[-1])
+        if n:
+            buf = (C.c_char * (n * OVERLAP_DTYPE.itemsize)).from_address(res.overlaps)
+            ov = np.frombuffer(buf, dtype=OVERLAP_DTYPE, count=n)
+        else:
+            ov = np.zeros(0, dtype=OVERLAP_DTYPE)
+        return (offsets.copy(), ov.copy()) if copy else (offsets, ov)
 
     # ---- multi-GPU ----
     @staticmethod

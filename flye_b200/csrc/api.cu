@@ -322,6 +322,13 @@ int fg_overlaps_batch(fg_ctx* ctx, const uint32_t* queryIds, uint32_t n, const f
     });
 }
 
+int fg_overlaps_refilter(fg_ctx* ctx, uint32_t firstQuery, float maxDivergence, fg_overlap_result* result) {
+    return guarded(ctx, [&] {
+        if (!result) throw Error(FG_ERR_ARG, "null argument");
+        fg::overlapsRefilter(ctx, firstQuery, maxDivergence, result);
+    });
+}
+
 int fg_debug_edit_distance(fg_ctx* ctx, const uint8_t* a, int n, const uint8_t* b, int m, int* distance) {
     return guarded(ctx, [&] {
         if (n < 0 || m < 0 || !distance) throw Error(FG_ERR_ARG, "bad argument");

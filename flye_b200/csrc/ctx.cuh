@@ -130,8 +130,15 @@ struct fg_ctx {
     std::vector<int32_t> resAln;
     fg::PinnedBuf<fg_overlap> pinnedOut;  // D2H staging, kept across calls
     fg::HostPool hostPool;
-    std::unique_ptr<fg_overlap[]> resCompact;   // results after the divergence / maxOverlaps filter (when it removed something)
-    size_t resCompactCap = 0;
+    // results after the divergence / maxOverlaps filter (when it removed something); two buffers: fg_overlaps_refilter
+    // compacts from the one that holds the last result into the other
+    std::unique_ptr<fg_overlap[]> resCompact[2];
+    size_t resCompactCap[2] = {0, 0};
+    fg_overlap_result lastResult{};             // what the last fg_overlaps_batch / fg_overlaps_refilter returned
+    fg_overlap* compactBuffer(int which, size_t n) {
+        if (resCompactCap[which] < n) { resCompactCap[which] = n + n / 4 + 16; resCompact[which].reset(new fg_overlap[resCompactCap[which]]); }
+        return resCompact[which].get();
+    }
 
     // ---- NCCL ----
     void* ncclComm = nullptr;
@@ -193,6 +200,7 @@ void buildIndexSolid(fg_ctx* ctx, int minFreq, float selectRate, int tandemFreq,
 void buildIndexMinimizers(fg_ctx* ctx, int k, int minCov, int window, float repeatRate);
 void overlapsBatch(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQueries, const fg_overlap_params& p,
                    fg_overlap_result* result);
+void overlapsRefilter(fg_ctx* ctx, uint32_t firstQuery, float maxDivergence, fg_overlap_result* result);
 
 // NCCL plumbing (comm.cu)
 void commUniqueId(uint8_t* id);

@@ -117,11 +117,18 @@ static constexpr int WF_NEG = -(1 << 29);
 // Steps s = sFrom .. sTo of the wavefront recurrence.  fr[k + base] = furthest row i reached on diagonal k = j - i with
 // s edits (WF_NEG / -1 = unreachable); `prev` holds step sFrom-1 on entry.  Returns the distance when the end is
 // reached, else -1 with `prev` holding step sTo.
-__device__ int wfaSteps(const SeqView& A, const SeqView& B, int*& prev, int*& cur, int base, int sFrom, int sTo, int lane) {
+// `band` (>= 1): only distances < band matter to the caller.  A path that ends on the target diagonal with fewer than `band`
+// edits is, after s edits, at most band-1-s diagonals away from it — every other diagonal of step s is left out (its value
+// reads as unreachable).  The optimal path of any distance < band lies inside this diamond, so such a distance is still found
+// exactly, at the same step; the diamond has about half the area of the full triangle of diagonals.
+__device__ __forceinline__ int bandLo(int s, int n, int target, int band) { return max(max(-s, -n), target - (band - 1 - s)); }
+__device__ __forceinline__ int bandHi(int s, int m, int target, int band) { return min(min(s, m), target + (band - 1 - s)); }
+
+__device__ int wfaSteps(const SeqView& A, const SeqView& B, int*& prev, int*& cur, int base, int sFrom, int sTo, int lane, int band) {
     const int n = A.n, m = B.n, target = m - n;
     for (int s = sFrom; s <= sTo; ++s) {
-        const int lo = max(-s, -n), hi = min(s, m);
-        const int plo = max(-(s - 1), -n), phi = min(s - 1, m);
+        const int lo = bandLo(s, n, target, band), hi = bandHi(s, m, target, band);
+        const int plo = bandLo(s - 1, n, target, band), phi = bandHi(s - 1, m, target, band);
         if (lane < 2) prev[plo - 1 - lane + base] = WF_NEG; else if (lane < 4) prev[phi - 1 + lane + base] = WF_NEG;   // guards
         __syncwarp();
         bool done = false;
@@ -178,17 +185,18 @@ __device__ int wfaEditDistance(const SeqView& A, const SeqView& B, int* smem, in
     if (lane == 0) prev[base] = i0;
     __syncwarp();
     const int sMax = min(n + m, limit - 1);   // steps worth taking: beyond them the distance is >= limit
+    const int band = min(limit, n + m + 1);   // distances of interest are < band (the distance never exceeds n + m)
     const int dCap = min(WF_DMAX, sMax);
-    int d = wfaSteps(A, B, prev, cur, base, 1, dCap, lane);
+    int d = wfaSteps(A, B, prev, cur, base, 1, dCap, lane, band);
     if (d >= 0) return d;
     if (dCap == sMax) return sMax == n + m ? d : limit;
     // continue in global memory
     const int gBase = n + 2;
-    const int plo = max(-dCap, -n), phi = min(dCap, m);
+    const int plo = bandLo(dCap, n, m - n, band), phi = bandHi(dCap, m, m - n, band);
     for (int k = plo + lane; k <= phi; k += 32) gA[k + gBase] = prev[k + base];
     __syncwarp();
     prev = gA; cur = gB;
-    d = wfaSteps(A, B, prev, cur, gBase, dCap + 1, sMax, lane);
+    d = wfaSteps(A, B, prev, cur, gBase, dCap + 1, sMax, lane, band);
     return (d < 0 && sMax < n + m) ? limit : d;
 }
 

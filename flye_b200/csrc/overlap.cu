@@ -2113,11 +2113,7 @@ void overlapsBatch(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, const fg_
     for (uint32_t q = 0; q < nQ; ++q) { ctx->resOffsets[q] = wpos; wpos += kept[q]; }
     ctx->resOffsets[nQ] = wpos;
     if (wpos != nRaw) {   // compact: the kept records of every query go to their final place in a second buffer, in parallel
-        if (ctx->resCompactCap < wpos) {
-            ctx->resCompactCap = wpos + wpos / 4 + 16;
-            ctx->resCompact.reset(new fg_overlap[ctx->resCompactCap]);
-        }
-        fg_overlap* dst = ctx->resCompact.get();
+        fg_overlap* dst = ctx->compactBuffer(0, wpos);
         parallelFor(nQ, [&](size_t qa, size_t qb) {
             for (size_t q = qa; q < qb; ++q) {
                 size_t w2 = ctx->resOffsets[q];
@@ -2139,6 +2135,43 @@ void overlapsBatch(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, const fg_
     result->aln_pairs = ctx->resAln.empty() ? nullptr : ctx->resAln.data();
     result->n_aln_pairs = ctx->resAln.size() / 2;
     result->n_hits = totHits; result->n_pairs = totPairs; result->n_dp_pairs = totDpPairs; result->n_dp_cells = totCells;
+    ctx->lastResult = *result;
+}
+
+void overlapsRefilter(fg_ctx* ctx, uint32_t firstQuery, float maxDivergence, fg_overlap_result* result) {
+    fg_overlap_result& last = ctx->lastResult;
+    const uint32_t nQ = last.n_queries;
+    if (!last.offsets || firstQuery > nQ) throw Error(FG_ERR_ARG, "fg_overlaps_refilter: no previous result / first_query out of range");
+    HostTimer ht(ctx, "host_refilter");
+    const fg_overlap* src = last.overlaps;
+    const size_t nRaw = ctx->resOffsets[nQ];
+    std::vector<uint64_t> oldOff(ctx->resOffsets.begin(), ctx->resOffsets.begin() + nQ + 1);
+    std::vector<uint32_t> kept(nQ, 0);
+    ctx->hostPool.parallelFor(nQ, [&](size_t qa, size_t qb) {
+        for (size_t q = qa; q < qb; ++q) {
+            uint32_t c = 0;
+            if (q < firstQuery) c = (uint32_t)(oldOff[q + 1] - oldOff[q]);
+            else for (uint64_t i = oldOff[q]; i < oldOff[q + 1]; ++i) c += src[i].seq_divergence < maxDivergence;
+            kept[q] = c;
+        }
+    }, nRaw);
+    size_t wpos = 0;
+    for (uint32_t q = 0; q < nQ; ++q) { ctx->resOffsets[q] = wpos; wpos += kept[q]; }
+    ctx->resOffsets[nQ] = wpos;
+    if (wpos != nRaw) {
+        const int which = (src == ctx->resCompact[0].get()) ? 1 : 0;
+        fg_overlap* dst = ctx->compactBuffer(which, wpos);
+        ctx->hostPool.parallelFor(nQ, [&](size_t qa, size_t qb) {
+            for (size_t q = qa; q < qb; ++q) {
+                size_t w2 = ctx->resOffsets[q];
+                for (uint64_t i = oldOff[q]; i < oldOff[q + 1]; ++i)
+                    if (q < firstQuery || src[i].seq_divergence < maxDivergence) dst[w2++] = src[i];
+            }
+        }, nRaw);
+        last.overlaps = dst;
+    }
+    last.offsets = ctx->resOffsets.data();
+    *result = last;
 }
 
 }  // namespace fg

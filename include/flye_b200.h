@@ -150,6 +150,13 @@ typedef struct {
 int fg_overlaps_batch(fg_ctx* ctx, const uint32_t* query_ids, uint32_t n_queries,
                       const fg_overlap_params* params, fg_overlap_result* result);
 
+/* OverlapContainer::setDivergenceThreshold after estimateOverlaperParameters (overlap.cpp:744-827): re-applies a (tighter)
+ * threshold to the overlaps of the LAST fg_overlaps_batch on this ctx — records of the queries [first_query, n_queries) with
+ * seq_divergence >= max_divergence are removed (queries before first_query, the estimate sample, stay as they are).
+ * `result` is refreshed (same lifetime rules).  Presets with a RELATIVE threshold (asm_raw_reads) only know it after the
+ * sample; this keeps the sample and the main pass in one device batch. */
+int fg_overlaps_refilter(fg_ctx* ctx, uint32_t first_query, float max_divergence, fg_overlap_result* result);
+
 /* ---- multi-GPU (one context per rank; reads are partitioned, the index replicated) ------- */
 #define FG_NCCL_ID_BYTES 128
 int fg_comm_unique_id(uint8_t id[FG_NCCL_ID_BYTES]);

@@ -137,3 +137,31 @@ def test_per_query_divergence_thresholds(engine, tmp_path):
             assert np.array_equal(m[f], (a if thr[i] == 1.0 else want_b)[f]), (i, f)
         n_low += len(want_b); n_all += len(a)
     assert 0 < n_low < n_all      # the threshold really removes overlaps on this input (1 % error per read)
+
+
+def test_refilter_equals_thresholded_run(engine, tmp_path):
+    """fg_overlaps_refilter (setDivergenceThreshold after the estimate): re-filtering the unthresholded result of the queries
+    from `first` on gives exactly what a thresholded run returns for them; the queries before `first` keep everything."""
+    import flye_b200 as fb
+    cfg = pu.load_cfg(os.path.join(pu.CFG_DIR, "raw_reads.cfg"))
+    reads_path = pu.simulate(os.path.join(str(tmp_path), "c.fasta"), genome_len=100000, coverage=15, seed=31)
+    reads = fb.read_fasta(reads_path, 1000)
+    engine.upload_ascii(reads)
+    engine.count_kmers(15)
+    engine.build_index_solid(2, cfg["meta_read_top_kmer_rate"], int(cfg["meta_read_filter_kmer_freq"]), cfg["repeat_kmer_rate"],
+                             float(int(cfg["assemble_kmer_sample"])))
+    common = dict(max_jump=int(cfg["maximum_jump"]), min_overlap=1000, max_overhang=int(cfg["maximum_overhang"]), only_max_ext=True)
+    q = np.arange(0, min(2 * len(reads), 200), dtype=np.uint32)
+    off_a, ov_a, _ = engine.overlaps(q, max_divergence=1.0, **common)
+    thr = float(np.median(ov_a["seq_divergence"]))           # removes about half of the records
+    off_b, ov_b, _ = engine.overlaps(q, max_divergence=thr, **common)
+    engine.overlaps(q, max_divergence=1.0, copy=False, **common)
+    first = 37
+    off_r, ov_r = engine.refilter(first, thr, len(q), copy=True)
+    assert 0 < len(ov_b) < len(ov_a)
+    for i in range(len(q)):
+        want = ov_a[int(off_a[i]):int(off_a[i + 1])] if i < first else ov_b[int(off_b[i]):int(off_b[i + 1])]
+        got = ov_r[int(off_r[i]):int(off_r[i + 1])]
+        assert np.array_equal(got, want), i
+    off_r2, ov_r2 = engine.refilter(0, thr, len(q), copy=True)     # a second refilter works on the refreshed result
+    assert np.array_equal(off_r2, off_b) and np.array_equal(ov_r2, ov_b)
