@@ -66,6 +66,10 @@ def build_tools():
         _run(["g++", "-O2", "-std=c++17", src, "-o", exe])
 
 
+    for name in ("rundp_check", "wfa_check"):   # CPU models of the run-compressed DP / chain walk and of the bounded wavefronts
+        src, exe = os.path.join(ROOT, "tests", "cpu_models", name + ".cpp"), os.path.join(out, name)
+        if _newer(exe, [src]):
+            _run(["g++", "-O2", "-std=c++17", src, "-o", exe])
     src, so = os.path.join(ROOT, "tests", "cpu_models", "stdsort_lib.cpp"), os.path.join(out, "libstdsort.so")
     if _newer(so, [src]):
         _run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", src, "-o", so])

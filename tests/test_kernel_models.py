@@ -1,0 +1,26 @@
+"""CPU: sequential models of the exact shortcuts the kernels take (DESIGN.md §2 "Exact shortcuts"), each checked against the
+literal algorithm of the reference on random inputs.  The GPU parity tests check the kernels against the oracle; these check
+the arithmetic of the shortcuts themselves, without a GPU."""
+import os
+import subprocess
+
+import parity_util as pu
+
+BIN = os.path.join(pu.ROOT, "tests", "cpu_models", "_bin")
+
+
+def test_run_compressed_dp_and_run_wise_walk_equal_the_literal_algorithm(built):
+    """chainRunDpKernel / chainFillKernel / chainWalkKernel<true> (overlap.cu) vs overlap.cpp:277-323 and :338-383: scores, back
+    pointers and the (start, first match, length) of every chain, on 60 k random pairs (diagonal runs, indels, jumps beyond
+    maxJump, noise, ties; either sort axis); the binary search for a run's first valid match and the presorted shortcut are hit."""
+    r = subprocess.run([os.path.join(BIN, "rundp_check"), "60000", "19"], stdout=subprocess.PIPE, text=True, timeout=600)
+    assert r.returncode == 0 and r.stdout.startswith("OK"), r.stdout
+    stats = dict(kv.split("=") for kv in r.stdout.split()[3:])
+    assert int(stats["walkBacks"]) > 1000 and int(stats["presorted"]) > 50 and int(stats["heads"]) > 100000
+
+
+def test_bounded_band_pruned_wavefronts_are_exact_below_the_limit(built):
+    """wfaSteps / wfaEditDistance / dropLimit (editdist.cu) vs the O(nm) edit distance: exact for distances below the limit,
+    '>= limit' otherwise, for limits around the true distance; dropLimit is the smallest distance failing the float test."""
+    r = subprocess.run([os.path.join(BIN, "wfa_check"), "12000", "23"], stdout=subprocess.PIPE, text=True, timeout=600)
+    assert r.returncode == 0 and r.stdout.startswith("OK"), r.stdout
