@@ -121,8 +121,23 @@ static constexpr int WF_NEG = -(1 << 29);
 // edits is, after s edits, at most band-1-s diagonals away from it — every other diagonal of step s is left out (its value
 // reads as unreachable).  The optimal path of any distance < band lies inside this diamond, so such a distance is still found
 // exactly, at the same step; the diamond has about half the area of the full triangle of diagonals.
-__device__ __forceinline__ int bandLo(int s, int n, int target, int band) { return max(max(-s, -n), target - (band - 1 - s)); }
-__device__ __forceinline__ int bandHi(int s, int m, int target, int band) { return min(min(s, m), target + (band - 1 - s)); }
+// (kept out of line and free of min / max chains on purpose: the one-line forms `max(max(-s, -n), …)`, inlined into the second
+// wfaSteps call site (global-memory phase), came out of nvcc 12.9 returning +n for s > WF_DMAX — caught by the host-mirror
+// parity test; tests/test_gpu_parity.py::test_device_edit_distance_long_and_bounded pins the phase)
+__device__ __noinline__ int bandLo(int s, int n, int target, int band) {
+    int lo = -s;
+    if (lo < -n) lo = -n;
+    const int b = target - (band - 1 - s);
+    if (lo < b) lo = b;
+    return lo;
+}
+__device__ __noinline__ int bandHi(int s, int m, int target, int band) {
+    int hi = s;
+    if (hi > m) hi = m;
+    const int b = target + (band - 1 - s);
+    if (hi > b) hi = b;
+    return hi;
+}
 
 __device__ int wfaSteps(const SeqView& A, const SeqView& B, int*& prev, int*& cur, int base, int sFrom, int sTo, int lane, int band) {
     const int n = A.n, m = B.n, target = m - n;
@@ -171,7 +186,7 @@ __device__ int wfaSteps(const SeqView& A, const SeqView& B, int*& prev, int*& cu
 
 // exact global edit distance of the two views, or `limit` as soon as the distance is known to be >= limit; one warp.
 // smem: 2 * WF_SMEM_INTS ints; gA/gB: n + m + 8 ints each.
-__device__ int wfaEditDistance(const SeqView& A, const SeqView& B, int* smem, int* gA, int* gB, int limit = 0x7fffffff) {
+__device__ int wfaEditDistance(const SeqView& A, const SeqView& B, int* smem, int* gA, int* gB, int limit = 0x7fffffff, bool bandOn = true) {
     const int lane = threadIdx.x & 31;
     const int n = A.n, m = B.n;
     if (limit <= 0) return limit;
@@ -185,7 +200,7 @@ __device__ int wfaEditDistance(const SeqView& A, const SeqView& B, int* smem, in
     if (lane == 0) prev[base] = i0;
     __syncwarp();
     const int sMax = min(n + m, limit - 1);   // steps worth taking: beyond them the distance is >= limit
-    const int band = min(limit, n + m + 1);   // distances of interest are < band (the distance never exceeds n + m)
+    const int band = bandOn ? min(limit, n + m + 1) : n + m + 1;   // distances of interest are < band (the distance never exceeds n + m)
     const int dCap = min(WF_DMAX, sMax);
     int d = wfaSteps(A, B, prev, cur, base, 1, dCap, lane, band);
     if (d >= 0) return d;
@@ -240,7 +255,7 @@ __device__ __forceinline__ int dropLimit(float maxDiv, int alnLen) {
 
 __global__ void __launch_bounds__(128) wfaKernel(fg_overlap* __restrict__ ov, uint32_t nOv, HpcSet cur, HpcSet ext, bool compress,
                                                  int* __restrict__ wfScratch, uint64_t wfStride, uint32_t* __restrict__ nextJob,
-                                                 float maxDiv, const float* __restrict__ queryMaxDiv) {
+                                                 float maxDiv, const float* __restrict__ queryMaxDiv, bool bandOn) {
     __shared__ int wfSm[4][2 * WF_SMEM_INTS];
     const uint32_t warpGlobal = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
@@ -255,7 +270,7 @@ __global__ void __launch_bounds__(128) wfaKernel(fg_overlap* __restrict__ ov, ui
         const SeqView A = makeView(cur, o.cur_id, o.cur_begin, o.cur_end, compress);
         const SeqView B = makeView(ext, o.ext_id, o.ext_begin, o.ext_end, compress);
         const int limit = dropLimit(queryMaxDiv ? queryMaxDiv[o.reserved] : maxDiv, max(A.n, B.n));
-        const int d = wfaEditDistance(A, B, wfSm[threadIdx.x >> 5], gA, gB, limit);
+        const int d = wfaEditDistance(A, B, wfSm[threadIdx.x >> 5], gA, gB, limit, bandOn);
         if (lane == 0) { ov[j].edit_distance = d; ov[j].aln_len = max(A.n, B.n); }
         __syncwarp();
     }
@@ -299,16 +314,17 @@ void editDistances(fg_ctx* ctx, fg_overlap* dOv, const fg_overlap* hOv, uint32_t
     const int blocks = 148 * 10, warps = blocks * 4;   // 48 registers / thread: 40 resident warps per SM
     const uint64_t stride = 2ULL * maxLen + 8;
     DevBuf<int> wf((uint64_t)warps * 2 * stride);   // only touched by overlaps with more than WF_DMAX edits
-    wfaKernel<<<blocks, 128, 0, ctx->stream>>>(dOv, nOv, cur, ext, useHpc, wf.p, stride, nextJob.p, maxDivergence, dQueryMaxDivergence);
+    wfaKernel<<<blocks, 128, 0, ctx->stream>>>(dOv, nOv, cur, ext, useHpc, wf.p, stride, nextJob.p, maxDivergence, dQueryMaxDivergence,
+                                               getenv("FG_WFA_BAND") == nullptr || atoi(getenv("FG_WFA_BAND")) != 0);
     checkLaunch(ctx, "wfaKernel");
     FG_CUDA(cudaStreamSynchronize(ctx->stream));
 }
 
 // test hook: exact edit distance of two base strings (values 0..3), optionally seen as reverse complements
-__global__ void debugEdKernel(const uint64_t* a, int n, bool rcA, const uint64_t* b, int m, bool rcB, int* wf, uint64_t stride, int* out) {
+__global__ void debugEdKernel(const uint64_t* a, int n, bool rcA, const uint64_t* b, int m, bool rcB, int* wf, uint64_t stride, int* out, int limit) {
     __shared__ int sm[2 * WF_SMEM_INTS];
     SeqView A{a, 0, n - 1, n, rcA}, B{b, 0, m - 1, m, rcB};
-    const int d = wfaEditDistance(A, B, sm, wf, wf + stride);
+    const int d = wfaEditDistance(A, B, sm, wf, wf + stride, limit);
     if ((threadIdx.x & 31) == 0) *out = d;
 }
 
@@ -327,7 +343,9 @@ int debugEditDistance(fg_ctx* ctx, const uint8_t* a, int n, const uint8_t* b, in
     DevBuf<int> wf(2 * stride), dOut(1);
     FG_CUDA(cudaMemcpyAsync(dA.p, pa.data(), pa.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
     FG_CUDA(cudaMemcpyAsync(dB.p, pb.data(), pb.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
-    debugEdKernel<<<1, 32, 0, ctx->stream>>>(dA.p, n, rcA != 0, dB.p, m, rcB != 0, wf.p, stride, dOut.p);
+    // test hook of the test hook: FG_DEBUG_ED_LIMIT bounds the distance like the divergence threshold does in wfaKernel
+    const char* lim = getenv("FG_DEBUG_ED_LIMIT");
+    debugEdKernel<<<1, 32, 0, ctx->stream>>>(dA.p, n, rcA != 0, dB.p, m, rcB != 0, wf.p, stride, dOut.p, lim ? atoi(lim) : 0x7fffffff);
     checkLaunch(ctx, "debugEdKernel");
     int d = -1;
     FG_CUDA(cudaMemcpyAsync(&d, dOut.p, 4, cudaMemcpyDeviceToHost, ctx->stream));

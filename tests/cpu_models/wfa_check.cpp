@@ -22,7 +22,7 @@ static int wfaModel(const std::string& A, const std::string& B, int limit) {
     if (n == 0) return m;
     if (m == 0) return n;
     const int target = m - n, off = n + 3;
-    std::vector<int> prev(n + m + 8, NEG), cur(n + m + 8, NEG);
+    std::vector<int> prev(n + m + 8, 12345), cur(n + m + 8, 54321);   // garbage: only the guards may make a diagonal unreachable
     int i0 = 0;
     while (i0 < n && i0 < m && A[i0] == B[i0]) ++i0;
     if (m == n && i0 >= n) return 0;

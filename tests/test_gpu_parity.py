@@ -164,6 +164,38 @@ def test_device_edit_distance_exact(engine):
         assert engine.debug_edit_distance_rc(a, False, rb, True) == want, (n, m, err, "fwd/rc")
 
 
+def test_device_edit_distance_long_and_bounded(engine, monkeypatch):
+    """Distances beyond WF_DMAX (254) continue in global memory; FG_DEBUG_ED_LIMIT bounds the distance the way the divergence
+    threshold does in wfaKernel (exact below the limit, '>= limit' otherwise; the wavefronts are pruned to the diamond the limit
+    allows)."""
+    rng = np.random.default_rng(3)
+    for t in range(5):
+        n = int(rng.integers(2500, 5000))
+        a = rng.integers(0, 4, n).astype(np.uint8)
+        err = [0.03, 0.07, 0.05, 0.02, 0.09][t]
+        b = []
+        for c in a:
+            u = rng.random()
+            if u < err / 3:
+                continue
+            if u < 2 * err / 3:
+                b.append(rng.integers(0, 4)); b.append(c); continue
+            b.append((c + 1) % 4 if u < err else c)
+        b = np.array(b, dtype=np.uint8)
+        d = _edit_distance_np(a, b)
+        for limit in (None, d + 1, d + 40, 3 * d, d, max(1, d - 10), 255, 256):
+            if limit is None:
+                monkeypatch.delenv("FG_DEBUG_ED_LIMIT", raising=False)
+            else:
+                monkeypatch.setenv("FG_DEBUG_ED_LIMIT", str(limit))
+            got = engine.debug_edit_distance(a, b)
+            if limit is None or d < limit:
+                assert got == d, (n, len(b), d, limit, got)
+            else:
+                assert got >= limit, (n, len(b), d, limit, got)
+    monkeypatch.delenv("FG_DEBUG_ED_LIMIT", raising=False)
+
+
 def test_hifi_small_full_parity(engine, tmp_path):
     """minimizer index + homopolymer-compressed edit-distance divergence (BASELINE configs 2/5 code path)"""
     tmp = str(tmp_path)
