@@ -76,9 +76,15 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([x.strip() for x in line.split(",")])
 
+    def mark(self):
+        """start of the timed region: only the samples from here on are reported (nvidia-smi itself is started before the warm-up
+        steps, so that its start-up — NVML initialisation holds the driver for tens of ms — does not land in a timed step)"""
+        self.first = len(self.rows)
+
     def stop(self):
         if self.proc:
             self.proc.terminate()
+        self.rows = self.rows[getattr(self, "first", 0):] or self.rows
         sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
         mx = [int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
         reasons = set()
@@ -139,7 +145,7 @@ def run_reference(args, wl, reads_path):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=os.environ.get("FLYE_B200_WORKLOAD", "hifi"), choices=sorted(WORKLOADS))
@@ -317,10 +323,11 @@ def main():
     eng.upload_packed(packed_pin, woff, lens)
     if world > 1:
         eng.set_shard(shard[0], shard[1])
-    for _ in range(args.warmup):
-        step(False)
     sampler = ClockSampler(local_rank)
     sampler.start()
+    for _ in range(args.warmup):
+        step(False)
+    sampler.mark()
     launches0 = eng.launches()
     ms_resident = timed(False, args.steps)
     launches = (eng.launches() - launches0) // max(1, args.steps)
