@@ -66,7 +66,7 @@ def build_tools():
         _run(["g++", "-O2", "-std=c++17", src, "-o", exe])
 
 
-    for name in ("rundp_check", "wfa_check"):   # CPU models of the run-compressed DP / chain walk and of the bounded wavefronts
+    for name in ("rundp_check", "wfa_check", "segsort_check"):   # CPU models: run-compressed DP / chain walk, bounded wavefronts, segmented radix sort
         src, exe = os.path.join(ROOT, "tests", "cpu_models", name + ".cpp"), os.path.join(out, name)
         if _newer(exe, [src]):
             _run(["g++", "-O2", "-std=c++17", src, "-o", exe])

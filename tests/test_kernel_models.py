@@ -24,3 +24,12 @@ def test_bounded_band_pruned_wavefronts_are_exact_below_the_limit(built):
     '>= limit' otherwise, for limits around the true distance; dropLimit is the smallest distance failing the float test."""
     r = subprocess.run([os.path.join(BIN, "wfa_check"), "12000", "23"], stdout=subprocess.PIPE, text=True, timeout=600)
     assert r.returncode == 0 and r.stdout.startswith("OK"), r.stdout
+
+
+def test_segmented_radix_sort_model_is_the_stable_sort_by_target(built):
+    """segRadixSortKernel (overlap.cu): per-warp chunks, (warp, digit) offsets, match.any ranking, next-pass counts gathered
+    while scattering == std::stable_sort by extId for 1..3 passes and every segment shape; and for segments without an
+    (extId, curPos) tie that order is what std::sort by (extId, curPos) returns from any input order."""
+    r = subprocess.run([os.path.join(BIN, "segsort_check"), "1200", "29"], stdout=subprocess.PIPE, text=True, timeout=600)
+    assert r.returncode == 0 and r.stdout.startswith("OK"), r.stdout
+    assert int(r.stdout.split("tieFree=")[1]) > 100
