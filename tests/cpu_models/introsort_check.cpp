@@ -91,6 +91,41 @@ static bool checkTieFollow(std::vector<fg::Elem> a, const char* what) {
     return true;
 }
 
+// Model of sortHugeKernel's partition step (overlap.cu): stop lists per slice, s = #{m : L_m < R_m} by a monotone search,
+// s parallel swaps, cut = min(L_s, R_{s-1}) — against the literal __move_median_to_first + __unguarded_partition.
+static bool checkHugePartition(std::vector<fg::Elem> a, const char* what) {
+    const long n = (long)a.size();
+    if (n <= 16) return true;
+    std::vector<fg::Elem> ref = a;
+    fg::seqMedianToFirst(ref.data(), 0, 1, n / 2, n - 1);
+    const long cutRef = fg::seqUnguardedPartition(ref.data(), 1, n, 0);
+    fg::seqMedianToFirst(a.data(), 0, 1, n / 2, n - 1);
+    const unsigned long long p = a[0].key;
+    const int W = 16;
+    const long sliceLen = (((n - 1 + W - 1) / W) + 31) & ~31L;
+    std::vector<long> L, R;   // concatenation of the slices' lists = all stops, ascending positions
+    for (int w = 0; w < W; ++w)
+        for (long i = std::min(n, 1 + w * sliceLen); i < std::min(n, 1 + (w + 1) * sliceLen); ++i) {
+            if (a[i].key >= p) L.push_back(i);
+            if (a[i].key <= p) R.push_back(i);
+        }
+    auto Lm = [&](long m) { return L[m]; };
+    auto Rm = [&](long m) { return R[(long)R.size() - 1 - m]; };
+    long lo = 0, hi = (long)std::min(L.size(), R.size());   // all m < lo hold, no m >= hi holds
+    while (lo < hi) {   // the kernel probes 512 values of m per round; any search over a monotone predicate gives the same s
+        const long mid = (lo + hi) / 2;
+        if (Lm(mid) < Rm(mid)) lo = mid + 1; else hi = mid;
+    }
+    const long s = lo;
+    for (long m = 0; m < s; ++m) std::swap(a[Lm(m)], a[Rm(m)]);
+    const long Ls = s < (long)L.size() ? Lm(s) : n;
+    const long cut = s == 0 ? Ls : std::min(Ls, Rm(s - 1));
+    if (cut != cutRef) { printf("MISMATCH huge partition cut %s n=%ld: %ld vs %ld\n", what, n, cut, cutRef); return false; }
+    for (long i = 0; i < n; ++i)
+        if (a[i].key != ref[i].key || a[i].val != ref[i].val) { printf("MISMATCH huge partition %s n=%ld at %ld\n", what, n, i); return false; }
+    return true;
+}
+
 // median-of-3 killer (Musser) to drive introsort into its heap-sort fallback
 static std::vector<unsigned long long> killer(size_t n) {
     std::vector<unsigned long long> v(n);
@@ -135,6 +170,7 @@ int main(int argc, char** argv) {
         if (!checkOne(a, "random")) return 1;
         if (g_small == 0 && g_table == 0) {
             if (!checkTieFollow(a, "random")) return 1;
+            if (!checkHugePartition(a, "random")) return 1;
             // mostly distinct keys with a few duplicated ones: the case the fast path is made for
             auto b = mk(n, 6, 1);
             for (int dup = 0; dup < 3 && n > 4; ++dup) { const size_t x = rng() % n, y = rng() % n; b[x].key = b[y].key; if (rng() % 2) b[rng() % n].key = b[y].key; }
@@ -148,7 +184,7 @@ int main(int argc, char** argv) {
         for (size_t i = 0; i < n; ++i) a[i] = {kv[i], (unsigned)i, 0u};
         ++arrays; elements += n;
         if (!checkOne(a, "killer")) return 1;
-        if (g_small == 0 && g_table == 0) { a[n / 3].key = a[n / 2].key; if (!checkTieFollow(a, "killer+tie")) return 1; }
+        if (g_small == 0 && g_table == 0) { if (!checkHugePartition(a, "killer")) return 1; a[n / 3].key = a[n / 2].key; if (!checkTieFollow(a, "killer+tie")) return 1; }
     }
     // exhaustive small alphabets around the chunk sizes: all arrays over {0,1,2} of length 17..20 is 3^20 -> sample
     for (int t = 0; t < trials * 5; ++t) {

@@ -33,7 +33,9 @@ def test_shared_memory_variants_equal_std_sort(built, small, variant):
 def test_tie_following_emulation_equals_std_sort(built):
     """The hit sort's fast path (overlap.cu: rangeIsTieFree): introsort is only emulated inside the ranges whose sorted ranks
     contain a duplicated key; every other range is copied from the stable-sorted array.  The model in introsort_check (run for
-    small = 0) must reproduce std::sort on tie-heavy, few-tie and heap-sort-fallback inputs, and must actually skip ranges."""
+    small = 0) must reproduce std::sort on tie-heavy, few-tie and heap-sort-fallback inputs, and must actually skip ranges.
+    The same run checks the model of sortHugeKernel's partition step (stop lists, s by a monotone search, parallel swaps, cut)
+    against the literal __move_median_to_first + __unguarded_partition on every random and killer array."""
     r = subprocess.run([BIN, "400", "23", "0"], stdout=subprocess.PIPE, text=True, timeout=600)
     assert r.returncode == 0, r.stdout
     assert r.stdout.startswith("OK")
