@@ -1,21 +1,30 @@
 // flye_b200 — OverlapDetector::getSeqOverlaps for a batch of query sequences on the device.
 //
-// Replaces src/sequence/overlap.cpp:99-508 (and overlapTest :29-69).  Pipeline per call:
+// Replaces src/sequence/overlap.cpp:99-508 (and overlapTest :29-69).  Pipeline per call (DESIGN.md §2 "Exact shortcuts" has the
+// arguments why the shortcuts below do not change a bit of the reference's output):
 //   Q1 queryLookupKernel  every query k-mer (either strand) -> index table probe -> hit count, list start,
 //                         repetitive bit (curFilteredPos, :178-182), self-hit bit (:189-190)
 //   Q2 scans              hit offsets per slot / per query; prefix popcounts of the repetitive bitmap
-//   Q3 expandKernel       load-balanced expansion of the position lists into KmerMatch records in the
-//                         reference's emission order (query position ascending, list order) (:176-196)
-//   Q4 sortTop/SmallKernel std::sort-exact segmented introsort of every query's hits by (extId,curPos) (:201-204):
-//                         warp-parallel partitioning in global memory, then shared-memory tasks
+//   Q3 expandKernel<2>    load-balanced expansion of the position lists into packed KmerMatch records in the reference's
+//                         emission order (query position ascending, list order) (:176-196); flags the queries that contain an
+//                         (extId, curPos) tie
+//   Q4 the hit sort (:201-204)
+//        segRadixSortKernel   every query: stable 8-bit LSD radix sort by extId, one CTA per query — std::sort's result for the
+//                             queries without ties; also writes the target-group start flags
+//        queries with ties    re-expanded into a scratch copy and sorted by the std::sort-exact introsort emulation
+//                             (sortHugeKernel = CTA-wide partition of long ranges, sortLevel/TailKernel = warp per range,
+//                             sortSmallKernel = shared-memory tasks), which only follows the ranges that contain ties
 //   Q5 group kernels      target groups, uniqueMatches / bounding-box / overhang prefilters (:216-262)
-//   Q6 per (query,target) pair: pairPrepKernel + the same segmented sort for the optional re-sort by extPos
-//                         (:269-275); chainDpKernel = chaining DP, one warp per pair, warp prefix-max emulating the
-//                         sequential scan and its two break rules (:277-323); segmented sort of the score order
-//                         (:331-334); chainWalkKernel = chain walk, overlapTest, filtered-position count
-//                         (:338-427) and primary selection (:431-458), one thread per pair
-//   Q7 gather + host epilogue: seqDivergence with the reference's float expression and glibc logf (:417-423),
-//                         divergence filter (:470-473), maxOverlaps cut (:218-219).
+//   Q6 per (query,target) pair: pairPrepKernel (DP axis, re-keying, run detection; pairs already sorted by extPos skip the
+//                         re-sort of :269-275, the others take the exact sort); chainRunDpKernel = chaining DP over runs of
+//                         matches, half-warp per pair (:277-323); chainFillKernel = scores / back pointers of all matches;
+//                         exact sort of the score order (:331-334) only for pairs whose scores are not strictly increasing;
+//                         chainWalkKernel<true> = chain walk run by run, overlapTest, filtered-position count (:338-427) and
+//                         primary selection (:431-458), one warp per pair
+//   Q7 gather, edit distance (editdist.cu, bounded by the divergence threshold) + host epilogue: seqDivergence with the
+//                         reference's float expression and glibc logf (:417-423), divergence filter (:470-473), maxOverlaps
+//                         cut (:218-219), parallel compaction; fg_overlaps_refilter = setDivergenceThreshold afterwards.
+// FG_HIT_RADIX / FG_DP_MODE / FG_SORT_HUGE select the older, slower device paths (kept as cross-checks, tests/test_gpu_parity.py).
 #include "ctx.cuh"
 #include "introsort_warp.cuh"
 
