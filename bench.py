@@ -8,12 +8,22 @@ One step = one pass of the hot path over the whole synthetic read set:
 `e2e`    = the same through the C-ABI calls with HOST buffers: every step re-uploads the packed reads from
            pinned host memory and brings every overlap record back.
 Workloads (BASELINE.json configs):
-    hifi : configs[1]  4.6 Mb genome, 30x HiFi-like reads (0.5 % error, ~15 kb), minimizers w=10 k=17, edlib+HPC
-    clr  : configs[0]  4.6 Mb genome, 50x CLR-like reads (12 % error, mean 7.5 kb), solid k-mers k=15
+    clr     : configs[0]  4.6 Mb genome, 50x CLR-like reads (12 % error, mean 7.5 kb), solid k-mers k=15       (default: the
+              configuration BASELINE.md / SURVEY §8 quote, and the full north-star path: count + solid index + overlaps)
+    hifi    : configs[1]  4.6 Mb genome, 30x HiFi-like reads (0.5 % error, ~15 kb), minimizers w=10 k=17, edlib+HPC
+    ont     : configs[2]  140 Mb genome, 30x ONT-like reads (10 % error, mean 19 kb), solid k-mers k=17
+    meta    : configs[3]  20 genomes, 65 Mb in total, log-distributed coverage, 10 % error, mean 9 kb, k=17
+    hifi250 : configs[4]  250 Mb genome, 30x HiFi-like reads
+After the timed steps the ordered overlap vectors of the last step are digested (tools/ovlpdigest.cpp: sha256 per query,
+folded in query order over all ranks) and compared with the digest of the UNMODIFIED REFERENCE's dump committed under
+tests/golden/full_scale/; a mismatch makes the process exit with status 3 — so a green run at N ranks is also the N-rank
+parity proof.
 --impl reference times the reference's own CPU implementation (oracle/_ref/flye_ref_harness, the unmodified
-reference sources; the CPU restatement if that binary is absent) on all host cores, on a bounded sample.
+reference sources; the CPU restatement if that binary is absent) on all host cores.
 """
 import argparse
+import ctypes
+import hashlib
 import json
 import os
 import subprocess
@@ -26,15 +36,26 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 WORKLOADS = {
+    "clr": dict(name="configs[0]: simulated 4.6 Mb genome, 50x CLR-like reads (12% error, mean 7.5 kb), asm_raw_reads settings, k=15",
+                sim=dict(genome_len=4600000, coverage=50, mean_len=7500, shape=2, error=0.12, seed=1), cfg="raw_reads.cfg", k=15,
+                cpu_queries=None),
     "hifi": dict(name="configs[1]: simulated 4.6 Mb genome, 30x HiFi-like reads (0.5% error, ~15 kb), asm_hifi settings "
                       "(k=17 minimizers w=10, HPC edit-distance divergence)",
                  sim=dict(genome_len=4600000, coverage=30, mean_len=15000, shape=20, error=0.005, seed=2), cfg="hifi.cfg", k=17,
                  cpu_queries=None),
-    "clr": dict(name="configs[0]: simulated 4.6 Mb genome, 50x CLR-like reads (12% error, mean 7.5 kb), asm_raw_reads settings, k=15",
-                sim=dict(genome_len=4600000, coverage=50, mean_len=7500, shape=2, error=0.12, seed=1), cfg="raw_reads.cfg", k=15,
-                cpu_queries=None),
+    "ont": dict(name="configs[2]: simulated 140 Mb genome, 30x ONT-like reads (10% error, mean 19 kb), asm_raw_reads settings, k=17",
+                sim=dict(genome_len=140000000, coverage=30, mean_len=19000, shape=2, error=0.10, seed=3), cfg="raw_reads.cfg", k=17,
+                cpu_queries=2000),
+    "meta": dict(name="configs[3]: simulated metagenome, 20 genomes of 65 Mb in total, coverage 4*2^(i/2.5) capped at 400, 10% error, "
+                      "mean 9 kb, asm_raw_reads settings, k=17 (buildIndexUnevenCoverage is the index path of every solid preset)",
+                 sim=dict(genome_len=65000000, coverage=0, mean_len=9000, shape=2, error=0.10, seed=4, meta=20), cfg="raw_reads.cfg", k=17,
+                 cpu_queries=2000),
+    "hifi250": dict(name="configs[4]: simulated 250 Mb genome, 30x HiFi-like reads (0.5% error, ~15 kb), asm_hifi settings",
+                    sim=dict(genome_len=250000000, coverage=30, mean_len=15000, shape=20, error=0.005, seed=5), cfg="hifi.cfg", k=17,
+                    cpu_queries=2000),
 }
 MIN_OVERLAP = 1000
+METRIC = "reads/sec through k-mer index + overlap detection"
 
 
 def log(*a):
@@ -51,9 +72,46 @@ def make_reads(wl, scale):
     path = os.path.join("/tmp", "flye_b200_bench_%s.fasta" % tag)
     if not os.path.exists(path):
         tmp = "%s.%d.tmp" % (path, os.getpid())
-        pu.simulate(tmp, **sim)
+        meta = sim.pop("meta", 0)
+        if meta:
+            sim.pop("coverage")
+            total = sim.pop("genome_len")
+            pu.simulate(tmp, genome_len=total, extra=["--meta", str(meta), "--meta-total", str(total)], **sim)
+        else:
+            pu.simulate(tmp, **sim)
         os.replace(tmp, path)
     return path
+
+
+def golden_path(workload):
+    return os.path.join(ROOT, "tests", "golden", "full_scale", workload + ".json")
+
+
+_digest_lib = None
+
+
+def digest_lib():
+    global _digest_lib
+    if _digest_lib is None:
+        _digest_lib = ctypes.CDLL(os.path.join(ROOT, "tools", "_bin", "libovlpdigest.so"))
+    return _digest_lib
+
+
+def query_digests(query_ids, offsets, ov):
+    """sha256 of every query's block of the ordered overlap dump (oracle/harness.cpp format) -> (n, 32) uint8"""
+    import numpy as np
+    q = np.ascontiguousarray(query_ids, dtype=np.uint32)
+    offs = np.ascontiguousarray(offsets, dtype=np.uint64)
+    ov = np.ascontiguousarray(ov)
+    out = np.zeros((len(q), 32), dtype=np.uint8)
+    digest_lib().fg_digest_queries(q.ctypes.data_as(ctypes.c_void_p), offs.ctypes.data_as(ctypes.c_void_p), ov.ctypes.data_as(ctypes.c_void_p),
+                                   ctypes.c_uint64(len(q)), out.ctypes.data_as(ctypes.c_void_p))
+    return out
+
+
+def fold_digests(dq, chunk=1000):
+    chunks = [hashlib.sha256(dq[a:a + chunk].tobytes()).digest() for a in range(0, len(dq), chunk)]
+    return hashlib.sha256(b"".join(chunks)).hexdigest(), [c.hex() for c in chunks]
 
 
 class ClockSampler:
@@ -104,30 +162,33 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def run_reference(args, wl, reads_path):
+def run_reference(args, wl, reads_path, budget_s=150.0):
     """The reference's own CPU path on all host cores.  cpu_queries = None: the whole workload (the unmodified reference
-    needs ~17 s for configs[1] and ~31 s for configs[0] on the 16-core GPU box); a number Q: full index over all reads +
-    the estimate pass + the first Q forward reads as overlap queries, overlap time scaled to all reads."""
+    needs ~17 s for configs[1] and ~31 s for configs[0] on the 16-core GPU box); a number Q: full count + index over all reads +
+    the estimate pass + the first Q forward reads as overlap queries, overlap time scaled to all reads.  At most `budget_s`
+    seconds of steps are run after the warm-up one; the number of steps actually timed is returned."""
     import parity_util as pu
     binary, kind = pu.oracle_binary()
     cores = os.cpu_count() or 1
     cfg = os.path.join(pu.CFG_DIR, wl["cfg"])
     q = wl["cpu_queries"]
     vals = []
-    n_reads = None
-    t_begin = time.time()
+    n_reads = n_bases = None
     warm = min(args.warmup, 1)          # a CPU run has nothing to warm beyond the page cache
+    t_begin = None
     for it in range(warm + args.steps):
         if kind == "port" and it > 0:
             break
-        if it > warm and time.time() - t_begin > 150:   # keep the whole arm within a few minutes
+        if it == warm:
+            t_begin = time.time()
+        if it > warm and time.time() - t_begin + (vals[-1] if vals else 0) > budget_s:   # keep the whole arm within a few minutes
             break
         r = pu.run_oracle(reads_path, cfg, "/tmp/flye_b200_bench_ref", k=wl["k"], threads=cores, binary=binary,
                           extra=["--max-queries", str(q)] if q is not None else [])
-        n_reads = r["reads"]
+        n_reads, n_bases = r["reads"], r.get("bases")
         nq = max(1, r["queries"])
         t = r["t_count"] + r["t_index"] + r["t_estimate"] + r["t_overlaps"] * (n_reads / nq)
-        log("reference step %d: count %.2fs index %.2fs estimate %.2fs overlaps(%d queries) %.2fs -> projected %.1fs" %
+        log("reference step %d: count %.2fs index %.2fs estimate %.2fs overlaps(%d queries) %.2fs -> %.1fs per pass" %
             (it, r["t_count"], r["t_index"], r["t_estimate"], nq, r["t_overlaps"], t))
         if it >= warm or kind == "port":
             vals.append(t)
@@ -135,11 +196,11 @@ def run_reference(args, wl, reads_path):
     value = n_reads / t
     if q is None:
         sample = "the whole workload: k-mer counting / index over all %d reads + estimateOverlaperParameters + getSeqOverlaps of " \
-                 "every forward read (no extrapolation)" % n_reads
+                 "every forward read (no extrapolation); %d timed passes" % (n_reads, len(vals))
     else:
-        sample = "index over all %d reads + estimateOverlaperParameters + getSeqOverlaps of the first %d forward reads; overlap " \
-                 "time scaled by reads/queries" % (n_reads, q)
-    return value, t, n_reads, dict(value=value, unit="reads/s", cores=cores, kind=kind, sample=sample)
+        sample = "count + index over all %d reads + estimateOverlaperParameters + getSeqOverlaps of the first %d forward reads; overlap " \
+                 "time scaled by reads/queries; %d timed passes" % (n_reads, q, len(vals))
+    return value, t, n_reads, n_bases, len(vals), dict(value=value, unit="reads/s", cores=cores, kind=kind, sample=sample)
 
 
 def main():
@@ -148,9 +209,11 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default=os.environ.get("FLYE_B200_WORKLOAD", "hifi"), choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default=os.environ.get("FLYE_B200_WORKLOAD", "clr"), choices=sorted(WORKLOADS))
     ap.add_argument("--scale", type=float, default=float(os.environ.get("FLYE_B200_SCALE", "1.0")), help="genome scale (tests)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the second timed region (host buffers re-uploaded every step)")
+    ap.add_argument("--write-golden", action="store_true", help="(development) print the digest record instead of comparing")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
@@ -164,10 +227,12 @@ def main():
         if rank != 0:
             return
         reads_path = make_reads(wl, args.scale)
-        value, t, n_reads, cb = run_reference(args, wl, reads_path)
-        config["reads"] = n_reads
-        print(json.dumps({"impl": "reference", "metric": "reads/sec through k-mer index + overlap detection", "value": value,
-                          "unit": "reads/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3,
+        value, t, n_reads, n_bases, steps_run, cb = run_reference(args, wl, reads_path)
+        config["reads"], config["bases"] = n_reads, n_bases
+        config["partition"] = "host CPU threads (the reference has no device path)"
+        print(json.dumps({"impl": "reference", "metric": METRIC, "value": value,
+                          "unit": "reads/s", "n_gpus": args.gpus, "steps": steps_run, "warmup": min(args.warmup, 1), "ms_per_step": t * 1e3,
+                          "steps_requested": args.steps, "warmup_requested": args.warmup,
                           "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
                           "config": config, "cpu_baseline": cb,
                           "e2e": {"value": value, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
@@ -214,7 +279,8 @@ def main():
     phase_ms, phase_calls, ovl_stats, n_ovl, wall = {}, {}, {}, 0, {}
     n_raw = [0]
     ovl_len_sample = np.zeros(0)
-    edit_sample = [None]
+    edit_sample = [None, 0.0]
+    last = {}
 
     def step(upload):
         nonlocal phase_ms, phase_calls, ovl_stats, n_ovl, wall, ovl_len_sample
@@ -296,8 +362,12 @@ def main():
             lap("refilter")
         n_ovl = int(offs[-1]) - int(offs[len(my_est)])
         ovl_len_sample = (ov["cur_end"][first:first + 20000] - ov["cur_begin"][first:first + 20000]).astype(np.float64)
-        edit_sample[0] = float(np.mean(ov["edit_distance"][first:first + 20000])) if common["nucl_alignment"] and len(ov) > first else None
+        if common["nucl_alignment"] and len(ov) > first:
+            ed, al = ov["edit_distance"][first:first + 20000].astype(np.float64), ov["aln_len"][first:first + 20000].astype(np.float64)
+            edit_sample[0] = float(np.mean(ed))
+            edit_sample[1] = float(np.mean(al * (np.ceil((2 * ed + 1) / 64.0) + 1)))   # Myers word updates of a band of 2d+1 (edlib's regime)
         lap("filter")
+        last["offs"], last["ov"], last["n_est"] = offs, ov, len(my_est)
         return n_ovl
 
     def barrier():
@@ -332,87 +402,134 @@ def main():
     ms_resident = timed(False, args.steps)
     launches = (eng.launches() - launches0) // max(1, args.steps)
     resident_phases, resident_calls, stats, resident_wall = dict(phase_ms), dict(phase_calls), dict(ovl_stats), dict(wall)
-    ms_e2e = timed(True, args.steps)
-    e2e_wall = dict(wall)
+    ms_e2e, e2e_wall = None, {}
+    if not args.no_e2e:
+        ms_e2e = timed(True, args.steps)
+        e2e_wall = dict(wall)
     clocks = sampler.stop()
+    int_peak = eng.int_peak() if hasattr(eng, "int_peak") else None
 
+    # ---- parity: digest of the ordered overlap vectors of the last step, all ranks, against the reference's digest ----
+    n_est = last["n_est"]
+    my_offs = np.asarray(last["offs"][n_est:], dtype=np.uint64)
+    dq = query_digests(queries, my_offs - my_offs[0], last["ov"][int(my_offs[0]):int(my_offs[-1])])
     if world > 1:
+        counts = [None] * world
+        dist.all_gather_object(counts, len(dq))
+        mx = max(counts)
+        pad = torch.zeros((mx, 32), dtype=torch.uint8, device="cuda")
+        if len(dq):
+            pad[:len(dq)] = torch.from_numpy(dq).cuda()
+        gathered = [torch.empty_like(pad) for _ in range(world)]
+        dist.all_gather(gathered, pad)
+        dq = np.concatenate([g[:c].cpu().numpy() for g, c in zip(gathered, counts)])
         t = torch.tensor([n_ovl, n_raw[0]], device="cuda", dtype=torch.int64)
         dist.all_reduce(t)
         n_ovl, n_raw[0] = int(t[0].item()), int(t[1].item())
+    final, chunks = fold_digests(dq)
+    parity = {"digest": final, "queries": int(len(dq)), "overlaps": int(n_ovl), "golden": None, "match": None,
+              "what": "sha256 per query of the ordered overlap dump (all integer fields + divergence bits), folded in query order over all ranks"}
+    gp = golden_path(args.workload)
+    if args.scale == 1.0 and os.path.exists(gp):
+        g = json.load(open(gp))
+        parity["golden"] = g["final"]
+        parity["golden_source"] = "tests/golden/full_scale/%s.json (dump of the unmodified reference, %d overlaps)" % (args.workload, g["overlaps"])
+        parity["match"] = bool(g["final"] == final and g["overlaps"] == n_ovl)
+        if not parity["match"]:
+            parity["first_bad_chunk"] = next((i for i, (a, b) in enumerate(zip(chunks, g["chunks"])) if a != b), min(len(chunks), len(g["chunks"])))
+    if args.write_golden and rank == 0:
+        print(json.dumps({"queries": len(dq), "overlaps": n_ovl, "chunk_queries": 1000, "final": final, "chunks": chunks}))
+
     total_reads = n_reads   # all ranks together process every forward read exactly once
     value = total_reads / (ms_resident / 1e3)
-    e2e_value = total_reads / (ms_e2e / 1e3)
     h2d = int(packed.nbytes + woff.nbytes + lens.nbytes + 4 * (len(queries) + len(est_ids)))
     raw_records = int(resident_phases.get("raw_overlaps", n_raw[0])) * world   # records the library copied back (before the threshold)
     d2h = int(72 * max(raw_records, n_raw[0]) + 8 * (len(queries) + len(est_ids) + 1))
 
     # roofline (algorithmic bytes: SURVEY.md §8d stage formulas, assigned to kernels in DESIGN.md §4).  Only phases that
-    # consist of ONE launch of one of our kernels are listed; their durations are CUDA-event times on the library's stream.
-    M, O = stats.get("n_hits", 0), n_ovl
+    # consist of ONE launch of one of our kernels are listed; their durations are CUDA-event times on the library's stream(s).
+    M, O = stats.get("n_hits", 0), n_ovl // max(world, 1)
     w = 4 if 2 * k <= 32 else 8
-    n_k = n_bases - k * n_reads
+    shard_bases = int(lens[lo:hi].sum())
+    n_k = shard_bases - k * (hi - lo)
     raw_ovl = int(resident_phases.get("raw_overlaps", n_raw[0]))
     mean_ovl_len = float(np.mean(np.maximum(ovl_len_sample, 1))) if len(ovl_len_sample) else 0.0
+    k8 = 12.0 * M + 40.0 * O                        # K8 as a whole; its four kernels share it evenly
     alg = {"expand": 20.0 * M,                       # K6, per-hit part: 8 B index entry read + 12 B match written
+           "lookup": (w + 8.0) * n_k,                # K6, per-position part
            "hit_sort_radix": 24.0 * M,               # K7: 12 B record read + 12 B record written, once
-           "chain_prep": 12.0 * M,                   # K8: one read of the matches (runs found on the way)
-           "chain_dp": 12.0 * M + 40.0 * O,          # K8
-           "chain_fill": 12.0 * M + 40.0 * O,        # K8: one read of the matches, scores / back pointers written
-           "chain_walk": 12.0 * M + 40.0 * O,        # K8
+           "chain_prep": k8 / 4, "chain_dp": k8 / 4, "chain_fill": k8 / 4, "chain_walk": k8 / 4,
            "edit": raw_ovl * 2.0 * mean_ovl_len / 4.0,   # K9: (len_q + len_t) / 4 bytes per overlap
-           "select": (w + 5.0) * n_k, "extract": 0.25 * n_bases + w * n_k}
-    names = {"expand": "expandKernel", "hit_sort_radix": "segRadixSortKernel", "chain_prep": "pairPrepKernel",
+           "select": (w + 5.0) * n_k,                # K4
+           "count": 0.25 * shard_bases + w * n_k + 2.0 * w * n_k}   # K2 + the counting part of K3 (3 w N_k without the (w+4) D of the table)
+    names = {"expand": "expandKernel", "lookup": "queryLookupKernel", "hit_sort_radix": "segRadixSortKernel", "chain_prep": "pairPrepKernel",
              "chain_dp": "chainRunDpKernel", "chain_fill": "chainFillKernel", "chain_walk": "chainWalkKernel", "edit": "wfaKernel",
-             "select": "minimizerRegKernel" if int(cfg["use_minimizers"]) else "selectKernel", "extract": "extractKeysKernel"}
-    bounds = {"edit": "integer issue (O(ND) wavefronts; bytes are negligible by construction)",
-              "chain_dp": "latency / integer issue (sequential scan over run heads)", "chain_walk": "latency (pointer chasing in shared memory)"}
-    # DRAM bytes per k-mer hit from `ncu --set full` captures (profiles/README.md: dram__bytes_read.sum + dram__bytes_write.sum
-    # of one launch / hits of that launch)
-    traffic_per_hit = {"expand": 25.9}
+             "select": "minimizerRegKernel" if int(cfg["use_minimizers"]) else "selectKernel", "count": "denseCountKernel"}
+    # integer-bound kernels: algorithmic integer operations (~15 int ops per DP cell of the reference's scan; Myers
+    # word update ~17 int ops per 64 cells of edlib's band) against the IMAD/LOP3/SHF issue rate measured in this run
+    int_alg = {"chain_dp": 15.0 * stats.get("n_dp_cells", 0), "edit": 17.0 * raw_ovl * edit_sample[1]}
+    notes = {"edit": "integer issue: O(ND) wavefronts instead of edlib's banded bit-vectors; algorithmic ops = the reference's Myers word updates",
+             "chain_dp": "integer issue: scan over run heads; algorithmic ops = 15 per DP cell the reference evaluates",
+             "chain_walk": "latency (pointer chasing in shared memory)"}
+    traffic_per_hit = {}
     try:
         with open(os.path.join(ROOT, "profiles", "traffic_per_hit.json")) as f:
             traffic_per_hit.update(json.load(f).get(args.workload, {}))
     except Exception:
         pass
-    kernel_phases = {p: ms for p, ms in resident_phases.items() if p in alg and alg[p] > 0 and resident_calls.get(p, 1) == 1}
+    kernel_phases = {p: ms for p, ms in resident_phases.items() if p in alg and alg[p] > 0 and resident_calls.get(p, 1) >= 1}
     peak, peak_src = measured_peak()
     roofline, roofline_kernels = None, []
     for ph in sorted(kernel_phases, key=kernel_phases.get, reverse=True):
-        ms_l = kernel_phases[ph]
-        achieved = alg[ph] / (ms_l / 1e3) / 1e9
+        n_l = max(1, resident_calls.get(ph, 1))
+        ms_l = kernel_phases[ph] / n_l
+        if ph in int_alg and int_peak:
+            achieved = int_alg[ph] / n_l / (ms_l / 1e3) / 1e9
+            roofline_kernels.append({"bound": "int", "kernel": names[ph], "phase": ph, "achieved": achieved, "peak": int_peak, "unit": "Gop/s",
+                                     "frac": achieved / int_peak, "traffic": traffic_per_hit[ph] * M / n_l if ph in traffic_per_hit else None,
+                                     "peak_source": "measured in this run (fg_debug_int_peak: IMAD/LOP3/SHF mix, all SMs)", "launches": n_l,
+                                     "ms_per_launch": ms_l, "algorithmic_ops_per_launch": int_alg[ph] / n_l, "note": notes.get(ph)})
+            continue
+        achieved = alg[ph] / n_l / (ms_l / 1e3) / 1e9
         roofline_kernels.append({"bound": "hbm", "kernel": names[ph], "phase": ph, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                                 "frac": achieved / peak, "traffic": traffic_per_hit[ph] * M if ph in traffic_per_hit else None,
-                                 "peak_source": peak_src, "launches": 1, "ms_per_launch": ms_l, "algorithmic_bytes_per_launch": alg[ph],
-                                 "note": bounds.get(ph)})
+                                 "frac": achieved / peak, "traffic": traffic_per_hit[ph] * M / n_l if ph in traffic_per_hit else None,
+                                 "peak_source": peak_src, "launches": n_l, "ms_per_launch": ms_l, "algorithmic_bytes_per_launch": alg[ph] / n_l,
+                                 "note": notes.get(ph)})
     if roofline_kernels:
         roofline = dict(roofline_kernels[0])
         roofline["traffic_source"] = "bytes per hit measured with ncu --set full (profiles/), scaled to this launch's hits"
-    lib_ms = resident_phases.get("hit_sort_radix_lib", 0.0)
-
-    line = {"metric": "reads/sec through k-mer index + overlap detection", "value": value, "unit": "reads/s", "n_gpus": world,
+    lib_phases = ("index_sort", "hit_sort_radix_lib", "chain_order")
+    line = {"metric": METRIC, "value": value, "unit": "reads/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_resident, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "int64", "data": "synthetic", "config": config, "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": "reads/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": int(launches), "roofline": roofline, "roofline_kernels": roofline_kernels,
-            "library_ms": {"cub_radix_sort_of_hits": round(lib_ms, 3)},
+            "e2e": None if ms_e2e is None else {"value": total_reads / (ms_e2e / 1e3), "unit": "reads/s", "ms_per_step": ms_e2e,
+                                                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches), "roofline": roofline, "roofline_kernels": roofline_kernels, "parity": parity,
+            "library_ms": {"cub_radix_sort_of_index_entries": round(resident_phases.get("index_sort", 0.0), 3),
+                           "cub_radix_sort_of_hits": round(resident_phases.get("hit_sort_radix_lib", 0.0), 3),
+                           "cub_radix_sort_of_pair_sizes": round(resident_phases.get("chain_order", 0.0), 3),
+                           "note": "cub::DeviceScan / DeviceSelect calls (prefix sums, compaction of flags) run inside the phases lookup, group, emit, index_table"},
             "phases_ms": {p: round(v, 3) for p, v in resident_phases.items()},
             "api_wall_ms": {p: round(v, 2) for p, v in resident_wall.items()}, "e2e_api_wall_ms": {p: round(v, 2) for p, v in e2e_wall.items()},
             "work": {"kmer_hits": int(M), "target_groups": int(stats.get("n_pairs", 0)), "dp_pairs": int(stats.get("n_dp_pairs", 0)),
-                     "dp_cells": int(stats.get("n_dp_cells", 0)), "overlaps": int(O),
+                     "dp_cells": int(stats.get("n_dp_cells", 0)), "overlaps": int(n_ovl),
                      "mean_edit_distance_first_20k_overlaps": edit_sample[0],
                      "queries_with_hit_ties": int(resident_phases.get("tied_queries", 0)),
                      "pairs_score_order_presorted": int(resident_phases.get("presorted_pairs", 0))}}
+    _ = lib_phases
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
-            _, _, _, cb = run_reference(argparse.Namespace(warmup=0, steps=1), wl, reads_path)
+            _, _, _, _, _, cb = run_reference(argparse.Namespace(warmup=0, steps=1), wl, reads_path)
             line["cpu_baseline"] = cb
         except Exception as e:   # the baseline is a reported number, never a reason to lose the GPU line
             line["cpu_baseline"] = {"value": None, "unit": "reads/s", "cores": os.cpu_count(), "kind": "unavailable", "sample": str(e)}
-    if rank == 0:
+    if rank == 0 and not args.write_golden:
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+    if parity["match"] is False:
+        log("PARITY FAILURE: digest %s != golden %s (first bad chunk of 1000 queries: %s)" % (final, parity["golden"], parity.get("first_bad_chunk")))
+        sys.exit(3)
 
 
 if __name__ == "__main__":

@@ -22,7 +22,7 @@ SYMBOLS = ["fg_ctx_create", "fg_ctx_destroy", "fg_last_error", "fg_stream", "fg_
            "fg_reads_upload", "fg_reads_upload_ascii", "fg_queries_upload", "fg_count_kmers", "fg_kmer_hist", "fg_kmer_freq",
            "fg_build_index_solid", "fg_build_index_minimizers", "fg_index_clear", "fg_index_lookup",
            "fg_index_positions", "fg_index_export", "fg_overlaps_batch", "fg_overlaps_refilter", "fg_comm_unique_id", "fg_comm_init",
-           "fg_comm_set_shard", "fg_debug_warp_sort", "fg_debug_edit_distance", "fg_debug_edit_distance_rc"]
+           "fg_comm_set_shard", "fg_debug_int_peak", "fg_debug_warp_sort", "fg_debug_edit_distance", "fg_debug_edit_distance_rc"]
 
 
 class IndexStats(C.Structure):
@@ -91,6 +91,7 @@ def load_lib():
     lib.fg_comm_unique_id.argtypes = [u8p]
     lib.fg_comm_init.argtypes = [vp, C.c_int, C.c_int, u8p]
     lib.fg_comm_set_shard.argtypes = [vp, C.c_uint32, C.c_uint32]
+    lib.fg_debug_int_peak.argtypes = [vp, C.POINTER(C.c_double)]
     lib.fg_debug_warp_sort.argtypes = [vp, u64p, u32p, u64p, C.c_uint32]
     lib.fg_debug_edit_distance.argtypes = [vp, u8p, C.c_int, u8p, C.c_int, C.POINTER(C.c_int)]
     lib.fg_debug_edit_distance_rc.argtypes = [vp, u8p, C.c_int, C.c_int, u8p, C.c_int, C.c_int, C.POINTER(C.c_int)]
@@ -336,11 +337,17 @@ class Engine:
                                                        C.byref(d)))
         return d.value
 
+    def int_peak(self):
+        """measured integer-issue ceiling of the device in Gop/s (IMAD / LOP3 / SHF mix)"""
+        g = C.c_double()
+        self._check(self.lib.fg_debug_int_peak(self.ctx, C.byref(g)))
+        return g.value
+
     def timings(self):
-        names = (C.c_char_p * 32)()
-        ms = (C.c_float * 32)()
-        calls = (C.c_int * 32)()
-        n = self.lib.fg_last_timings(self.ctx, names, ms, calls, 32)
+        names = (C.c_char_p * 64)()
+        ms = (C.c_float * 64)()
+        calls = (C.c_int * 64)()
+        n = self.lib.fg_last_timings(self.ctx, names, ms, calls, 64)
         self.last_calls = {names[i].decode(): calls[i] for i in range(n)}
         return {names[i].decode(): ms[i] for i in range(n)}
 

@@ -17,7 +17,7 @@ BUILD = os.path.join(ROOT, "build")
 LIB = os.path.join(ROOT, "flye_b200", "libflye_b200.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Wno-deprecated-declarations"]
-SOURCES = ["api.cu", "count_index.cu", "overlap.cu", "editdist.cu", "comm.cu"]
+SOURCES = ["api.cu", "count_index.cu", "overlap.cu", "editdist.cu", "comm.cu", "intpeak.cu"]
 
 
 def _run(cmd, **kw):
@@ -59,6 +59,13 @@ def build_tools():
     src, exe = os.path.join(ROOT, "tools", "simreads.cpp"), os.path.join(out, "simreads")
     if _newer(exe, [src]):
         _run(["g++", "-O2", "-std=c++17", src, "-o", exe])
+    # digest of ordered overlap dumps (full-scale parity against committed reference digests; bench.py's digest check)
+    src = os.path.join(ROOT, "tools", "ovlpdigest.cpp")
+    exe, so = os.path.join(out, "ovlpdigest"), os.path.join(out, "libovlpdigest.so")
+    if _newer(exe, [src]):
+        _run(["g++", "-O2", "-std=c++17", src, "-o", exe])
+    if _newer(so, [src]):
+        _run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-DOVLPDIGEST_LIB", src, "-o", so])
     out = os.path.join(ROOT, "tests", "cpu_models", "_bin")
     os.makedirs(out, exist_ok=True)
     src, exe = os.path.join(ROOT, "tests", "cpu_models", "introsort_check.cpp"), os.path.join(out, "introsort_check")

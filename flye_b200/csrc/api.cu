@@ -295,16 +295,21 @@ int fg_index_export(fg_ctx* ctx, uint64_t* keys, uint8_t* isRep, uint64_t* first
         if (nEntries) *nEntries = E;
         FG_CUDA(cudaStreamSynchronize(ctx->stream));
         if (keys && S) {
-            std::vector<uint64_t> pl(S);
-            // keys arrive in the device's canonical value; give them back in the reference's representation
-            FG_CUDA(cudaMemcpy(keys, ctx->dUKeys.p, S * 8, cudaMemcpyDeviceToHost));
+            std::vector<uint64_t> pl(S), ks(S);
+            FG_CUDA(cudaMemcpy(ks.data(), ctx->dUKeys.p, S * 8, cudaMemcpyDeviceToHost));
             FG_CUDA(cudaMemcpy(pl.data(), ctx->dUPayload.p, S * 8, cudaMemcpyDeviceToHost));
-            for (uint64_t i = 0; i < S; ++i) {
+            // keys ascending: already so on one GPU; with the index sorted in per-owner shares (multi-GPU) order them here
+            std::vector<uint64_t> order(S);
+            for (uint64_t i = 0; i < S; ++i) order[i] = i;
+            if (!std::is_sorted(ks.begin(), ks.end())) std::sort(order.begin(), order.end(), [&](uint64_t a, uint64_t b) { return ks[a] < ks[b]; });
+            for (uint64_t j = 0; j < S; ++j) {
+                const uint64_t i = order[j];
+                keys[j] = ks[i];
                 const bool absent = pl[i] == ~0ULL;
                 const uint64_t s = pl[i] & fg::IDX_SIZE_MASK;
-                if (isRep) isRep[i] = !absent && s == fg::IDX_REPETITIVE;
-                if (size) size[i] = (absent || s == fg::IDX_REPETITIVE) ? 0 : (uint32_t)s;
-                if (first) first[i] = (absent || s == fg::IDX_REPETITIVE) ? 0 : pl[i] >> fg::IDX_SIZE_BITS;
+                if (isRep) isRep[j] = !absent && s == fg::IDX_REPETITIVE;
+                if (size) size[j] = (absent || s == fg::IDX_REPETITIVE) ? 0 : (uint32_t)s;
+                if (first) first[j] = (absent || s == fg::IDX_REPETITIVE) ? 0 : pl[i] >> fg::IDX_SIZE_BITS;
             }
         }
         if (entrySeqIds && entryPos && E) {
@@ -340,6 +345,13 @@ int fg_debug_edit_distance_rc(fg_ctx* ctx, const uint8_t* a, int n, int rc_a, co
     return guarded(ctx, [&] {
         if (n < 0 || m < 0 || !distance) throw Error(FG_ERR_ARG, "bad argument");
         *distance = fg::debugEditDistance(ctx, a, n, b, m, rc_a, rc_b);
+    });
+}
+
+int fg_debug_int_peak(fg_ctx* ctx, double* gops) {
+    return guarded(ctx, [&] {
+        if (!gops) throw Error(FG_ERR_ARG, "null argument");
+        *gops = fg::intPeak(ctx);
     });
 }
 

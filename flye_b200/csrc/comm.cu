@@ -22,18 +22,25 @@ struct Nccl {
     int (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*Broadcast)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*GroupStart)() = nullptr;
     int (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
 
     static Nccl& get() {
         static Nccl n;
-        if (n.handle) return n;
-        for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
-            n.handle = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
-            if (n.handle) break;
-        }
+        static bool ready = false;
+        static std::mutex m;
+        std::lock_guard<std::mutex> lock(m);
+        if (ready) return n;
+        if (!n.handle)
+            for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
+                n.handle = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+                if (n.handle) break;
+            }
         if (!n.handle) throw Error(FG_ERR_NCCL, std::string("cannot load libnccl: ") + dlerror());
+        // (`ready` is only set once every symbol resolved: a failed attempt never leaves a half-filled table behind)
         auto sym = [&](const char* s) { void* p = dlsym(n.handle, s); if (!p) throw Error(FG_ERR_NCCL, std::string("missing NCCL symbol ") + s); return p; };
         n.GetUniqueId = (decltype(n.GetUniqueId))sym("ncclGetUniqueId");
         n.CommInitRank = (decltype(n.CommInitRank))sym("ncclCommInitRank");
@@ -44,6 +51,9 @@ struct Nccl {
         n.GroupStart = (decltype(n.GroupStart))sym("ncclGroupStart");
         n.GroupEnd = (decltype(n.GroupEnd))sym("ncclGroupEnd");
         n.GetErrorString = (decltype(n.GetErrorString))sym("ncclGetErrorString");
+        n.Send = (decltype(n.Send))sym("ncclSend");
+        n.Recv = (decltype(n.Recv))sym("ncclRecv");
+        ready = true;
         return n;
     }
 };
@@ -78,25 +88,87 @@ void commDestroy(fg_ctx* ctx) {
 }
 
 // variable-size all-gather: rank r contributes `bytes` bytes at `src`; every rank receives the concatenation in rank
-// order in `out`; offs[r] .. offs[r+1] is rank r's part.  Implemented as one ncclBroadcast per rank inside a group
-// (no padding, no staging copy).
-void allGatherV(fg_ctx* ctx, const void* src, uint64_t bytes, DevBuf<char>& out, std::vector<uint64_t>& offs) {
+// order; offs[r] .. offs[r+1] is rank r's part.  Two steps so that the caller can allocate the destination with its own type:
+// allGatherSizes (one tiny ncclAllGather + host sync), then allGatherVInto = one ncclBroadcast per rank inside a group
+// (no padding, no staging copy).  Ranks that contribute 0 bytes take part like every other rank.
+void allGatherSizes(fg_ctx* ctx, uint64_t bytes, std::vector<uint64_t>& offs) {
     Nccl& n = Nccl::get();
-    ncclComm_t comm = (ncclComm_t)ctx->ncclComm;
     const int R = ctx->nRanks;
     DevBuf<uint64_t> dSizes(R), dMine(1);
     FG_CUDA(cudaMemcpyAsync(dMine.p, &bytes, 8, cudaMemcpyHostToDevice, ctx->stream));
-    ncclCheck(n.AllGather(dMine.p, dSizes.p, 1, ncclUint64, comm, ctx->stream), "ncclAllGather(sizes)");
+    ncclCheck(n.AllGather(dMine.p, dSizes.p, 1, ncclUint64, (ncclComm_t)ctx->ncclComm, ctx->stream), "ncclAllGather(sizes)");
     std::vector<uint64_t> sizes(R);
     FG_CUDA(cudaMemcpyAsync(sizes.data(), dSizes.p, R * 8ULL, cudaMemcpyDeviceToHost, ctx->stream));
     FG_CUDA(cudaStreamSynchronize(ctx->stream));
     offs.assign(R + 1, 0);
     for (int r = 0; r < R; ++r) offs[r + 1] = offs[r] + sizes[r];
-    out.alloc(std::max<uint64_t>(offs[R], 1));
+}
+
+void allGatherVInto(fg_ctx* ctx, const void* src, const std::vector<uint64_t>& offs, void* dst) {
+    Nccl& n = Nccl::get();
+    ncclComm_t comm = (ncclComm_t)ctx->ncclComm;
     ncclCheck(n.GroupStart(), "ncclGroupStart");
-    for (int r = 0; r < R; ++r)
-        if (sizes[r]) ncclCheck(n.Broadcast(src, out.p + offs[r], sizes[r], ncclChar, r, comm, ctx->stream), "ncclBroadcast");
+    for (int r = 0; r < ctx->nRanks; ++r)
+        if (offs[r + 1] > offs[r])
+            ncclCheck(n.Broadcast(src, (char*)dst + offs[r], offs[r + 1] - offs[r], ncclChar, r, comm, ctx->stream), "ncclBroadcast");
     ncclCheck(n.GroupEnd(), "ncclGroupEnd");
+}
+
+void allGatherV(fg_ctx* ctx, const void* src, uint64_t bytes, DevBuf<char>& out, std::vector<uint64_t>& offs) {
+    allGatherSizes(ctx, bytes, offs);
+    out.alloc(std::max<uint64_t>(offs.back(), 1));
+    allGatherVInto(ctx, src, offs, out.p);
+}
+
+// all-to-all with per-destination sizes: this rank sends the bytes [sendOffs[d], sendOffs[d+1]) of sendBuf to rank d; on return
+// recvOffs[s] .. recvOffs[s+1] delimits what rank s sent here, in rank order.  exchangeSizes = one ncclAllGather of the size row;
+// allToAllVInto = grouped ncclSend / ncclRecv over NVLink (the part for this rank itself is a device copy).
+void exchangeSizes(fg_ctx* ctx, const std::vector<uint64_t>& sendOffs, std::vector<uint64_t>& recvOffs) {
+    Nccl& n = Nccl::get();
+    const int R = ctx->nRanks;
+    std::vector<uint64_t> row(R);
+    for (int d = 0; d < R; ++d) row[d] = sendOffs[d + 1] - sendOffs[d];
+    DevBuf<uint64_t> dRow(R), dAll((size_t)R * R);
+    FG_CUDA(cudaMemcpyAsync(dRow.p, row.data(), R * 8ULL, cudaMemcpyHostToDevice, ctx->stream));
+    ncclCheck(n.AllGather(dRow.p, dAll.p, R, ncclUint64, (ncclComm_t)ctx->ncclComm, ctx->stream), "ncclAllGather(size matrix)");
+    std::vector<uint64_t> all((size_t)R * R);
+    FG_CUDA(cudaMemcpyAsync(all.data(), dAll.p, all.size() * 8ULL, cudaMemcpyDeviceToHost, ctx->stream));
+    FG_CUDA(cudaStreamSynchronize(ctx->stream));
+    recvOffs.assign(R + 1, 0);
+    for (int s = 0; s < R; ++s) recvOffs[s + 1] = recvOffs[s] + all[(size_t)s * R + ctx->rank];
+}
+
+void allToAllVInto(fg_ctx* ctx, const void* sendBuf, const std::vector<uint64_t>& sendOffs, void* recvBuf, const std::vector<uint64_t>& recvOffs) {
+    Nccl& n = Nccl::get();
+    ncclComm_t comm = (ncclComm_t)ctx->ncclComm;
+    const int R = ctx->nRanks, me = ctx->rank;
+    if (sendOffs[me + 1] > sendOffs[me])
+        FG_CUDA(cudaMemcpyAsync((char*)recvBuf + recvOffs[me], (const char*)sendBuf + sendOffs[me], sendOffs[me + 1] - sendOffs[me],
+                                cudaMemcpyDeviceToDevice, ctx->stream));
+    ncclCheck(n.GroupStart(), "ncclGroupStart");
+    for (int p = 0; p < R; ++p) {
+        if (p == me) continue;
+        if (sendOffs[p + 1] > sendOffs[p])
+            ncclCheck(n.Send((const char*)sendBuf + sendOffs[p], sendOffs[p + 1] - sendOffs[p], ncclChar, p, comm, ctx->stream), "ncclSend");
+        if (recvOffs[p + 1] > recvOffs[p])
+            ncclCheck(n.Recv((char*)recvBuf + recvOffs[p], recvOffs[p + 1] - recvOffs[p], ncclChar, p, comm, ctx->stream), "ncclRecv");
+    }
+    ncclCheck(n.GroupEnd(), "ncclGroupEnd");
+}
+
+// Rank-local failures inside a sharded phase must not leave the peers blocked in the next collective: every rank brings its
+// status word here (0 = fine) and all of them throw together when any is non-zero.
+void agreeOrThrow(fg_ctx* ctx, int code, const std::string& msg) {
+    if (!sharded(ctx)) { if (code) throw Error(code, msg); return; }
+    DevBuf<unsigned long long> d(1);
+    const unsigned long long mine = code ? 1ULL : 0ULL;
+    unsigned long long sum = 0;
+    FG_CUDA(cudaMemcpyAsync(d.p, &mine, 8, cudaMemcpyHostToDevice, ctx->stream));
+    allReduceSumU64(ctx, d.p, 1);
+    FG_CUDA(cudaMemcpyAsync(&sum, d.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    FG_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (code) throw Error(code, msg);
+    if (sum) throw Error(FG_ERR_INTERNAL, "a peer rank failed in a sharded phase (see its fg_last_error)");
 }
 
 void allReduceSumU64(fg_ctx* ctx, unsigned long long* buf, size_t count) {

@@ -67,14 +67,59 @@ static void tileRange(const fg_ctx* ctx, uint32_t first, uint32_t count, size_t&
 }
 
 // ------------------------------------------------------------------------------------------------
-// K2: canonical k-mer extraction.  One CTA per tile of <=2048 positions of one read; the tile's packed
-// words are staged in shared memory, every thread then assembles its k-mers from two 64-bit words.
-// Writes are fully coalesced (thread t -> output t, t+256, ...).
+// K2 + K3: k-mer counting (KmerCounter::count, vertex_index.cpp:499-590) with a DENSE counter array in HBM.
+//
+// The reference counts in a flat array over all 4^k k-mers (4-bit saturating counters + an overflow map) and refuses
+// k > 17 for that reason (vertex_index.cpp:504-507).  The same idea maps well onto 180 GB of HBM3e: one 32-bit counter
+// per canonical k-mer class, incremented with a fire-and-forget RED.ADD per read position — no key array is ever
+// materialised, nothing is sorted, and the footprint does not depend on the number of reads.
+//
+// Dense index of the class {f, rc(f)}:
+//   odd k   exactly one of f / rc(f) has A or C as its MIDDLE base (the middle base of the reverse complement is the
+//           complement of the middle base); that one is the representative and the high bit of its middle base (always
+//           0) is squeezed out: 4^k / 2 counters (k = 15: 2.1 GB, k = 17: 34 GB)
+//   even k  min(f, rc(f)): 4^k counters (k = 16: 17 GB)
+// Multi-GPU: the class with dense index i is OWNED by rank i % N and counted there in slot i / N (< 2^32 for N >= 2), so
+// the array, its clearing and its scan all shrink with the rank count.  Every rank partitions the positions of its read
+// shard by owner (two passes over the packed reads: totals, then scatter of the 32-bit local slots), one grouped
+// ncclSend/ncclRecv all-to-all moves them over NVLink, and the owner counts what it receives.  The scan then yields, per
+// rank: its part of the freq -> #k-mers histogram (reduced with ncclAllReduce) and its k-mers with count >= 2, which are
+// all-gathered so that every rank holds the complete count table (absent == 1) that the per-read selection probes.
 // ------------------------------------------------------------------------------------------------
-template <class KeyT>
-__global__ void __launch_bounds__(256) extractKeysKernel(const uint64_t* __restrict__ seq, const uint64_t* __restrict__ wordOff,
-                                                         const uint32_t* __restrict__ len, const uint2* __restrict__ tiles,
-                                                         const uint64_t* __restrict__ tileOut, int k, KeyT* __restrict__ keys) {
+static constexpr int MAX_RANKS = 64;
+
+struct DenseMap {
+    int k;
+    uint32_t nOwners, owner;      // owner: this rank
+    uint32_t ownerShift;          // log2(nOwners) if it is a power of two, else 0xffffffff
+};
+static inline uint64_t denseSpace(int k) { return (k & 1) ? (1ULL << (2 * k - 1)) : (1ULL << (2 * k)); }
+
+__host__ __device__ inline uint64_t denseIndexFromWindow(uint64_t v, int k) {
+    const uint64_t f = fwdFromWindow(v, k), r = (~v) & kmerMask(k);
+    if (k & 1) {   // base j of f sits at bits 2(k-1-j), 2(k-1-j)+1; the middle one (j = (k-1)/2) at bits k-1, k
+        const uint64_t rep = ((f >> k) & 1ULL) ? r : f;
+        return (rep & ((1ULL << k) - 1ULL)) | ((rep >> (k + 1)) << k);
+    }
+    return f < r ? f : r;
+}
+// canonical k-mer (Kmer::standardForm, kmer.h:54-63) of a dense index
+__host__ __device__ inline uint64_t canonFromDenseIndex(uint64_t idx, int k) {
+    if (!(k & 1)) return idx;
+    const uint64_t rep = (idx & ((1ULL << k) - 1ULL)) | ((idx >> k) << (k + 1));
+    const uint64_t rc = (~rev2(rep << (64 - 2 * k))) & kmerMask(k);   // kmer.h:39-52
+    return rep < rc ? rep : rc;
+}
+__device__ __forceinline__ void ownerOf(const DenseMap& m, uint64_t idx, uint32_t& owner, uint64_t& local) {
+    if (m.ownerShift != 0xffffffffu) { owner = (uint32_t)(idx & (m.nOwners - 1u)); local = idx >> m.ownerShift; }
+    else { local = idx / m.nOwners; owner = (uint32_t)(idx - local * m.nOwners); }
+}
+
+// single GPU: one CTA per tile of <= 2048 positions of one read; the tile's packed words are staged in shared memory,
+// every position becomes one RED.ADD.U32 on its class counter
+__global__ void __launch_bounds__(256) denseCountKernel(const uint64_t* __restrict__ seq, const uint64_t* __restrict__ wordOff,
+                                                        const uint32_t* __restrict__ len, const uint2* __restrict__ tiles, int k,
+                                                        uint32_t* __restrict__ dense) {
     __shared__ uint64_t sw[TILE_SLOTS / 32 + 4];
     const uint2 t = tiles[blockIdx.x];
     const uint32_t L = len[t.x], n = L - k, p0 = t.y;
@@ -84,40 +129,153 @@ __global__ void __launch_bounds__(256) extractKeysKernel(const uint64_t* __restr
     for (uint32_t i = threadIdx.x; i < nw; i += blockDim.x) sw[i] = words[w0 + i];
     if (threadIdx.x == 0) sw[nw] = 0;
     __syncthreads();
-    KeyT* out = keys + tileOut[blockIdx.x];
-    for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) {
-        bool rc;
-        uint64_t key = canonFromWindow(windowAt(sw, (p0 & 31) + i, k), k, rc);
-        out[i] = (KeyT)key;
-    }
+    for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x)
+        atomicAdd(&dense[denseIndexFromWindow(windowAt(sw, (p0 & 31) + i, k), k)], 1u);
 }
 
-// freq -> #distinct histogram: shared-memory privatised low bins, global atomics above, overflow list
+// multi-GPU pass A: how many positions of this rank's tiles belong to every owner
+__global__ void __launch_bounds__(256) ownerTotalsKernel(const uint64_t* __restrict__ seq, const uint64_t* __restrict__ wordOff,
+                                                         const uint32_t* __restrict__ len, const uint2* __restrict__ tiles, DenseMap m,
+                                                         unsigned long long* __restrict__ totals) {
+    __shared__ uint64_t sw[TILE_SLOTS / 32 + 4];
+    __shared__ uint32_t cnt[MAX_RANKS];
+    const int k = m.k;
+    const uint2 t = tiles[blockIdx.x];
+    const uint32_t L = len[t.x], n = L - k, p0 = t.y;
+    const uint32_t c = min((uint32_t)TILE_SLOTS, n - p0);
+    const uint64_t* words = seq + wordOff[t.x];
+    const uint32_t w0 = p0 >> 5, nw = ((p0 + c + k - 1) >> 5) - w0 + 1;
+    for (uint32_t i = threadIdx.x; i < nw; i += blockDim.x) sw[i] = words[w0 + i];
+    if (threadIdx.x == 0) sw[nw] = 0;
+    if (threadIdx.x < MAX_RANKS) cnt[threadIdx.x] = 0;
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < c; i += blockDim.x) {
+        uint32_t o; uint64_t local;
+        ownerOf(m, denseIndexFromWindow(windowAt(sw, (p0 & 31) + i, k), k), o, local);
+        atomicAdd(&cnt[o], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < m.nOwners && cnt[threadIdx.x]) atomicAdd(&totals[threadIdx.x], (unsigned long long)cnt[threadIdx.x]);
+}
+
+// multi-GPU pass B: the local slots go to the send segment of their owner (order inside a segment is irrelevant: the
+// receiver only counts); a CTA reserves its share of every segment with one atomic per owner
+__global__ void __launch_bounds__(256) ownerScatterKernel(const uint64_t* __restrict__ seq, const uint64_t* __restrict__ wordOff,
+                                                          const uint32_t* __restrict__ len, const uint2* __restrict__ tiles, DenseMap m,
+                                                          const unsigned long long* __restrict__ segStart, unsigned long long* __restrict__ cursor,
+                                                          uint32_t* __restrict__ sendBuf) {
+    __shared__ uint64_t sw[TILE_SLOTS / 32 + 4];
+    __shared__ uint32_t cnt[MAX_RANKS];
+    __shared__ unsigned long long base[MAX_RANKS];
+    constexpr int PER = TILE_SLOTS / 256;
+    const int k = m.k;
+    const uint2 t = tiles[blockIdx.x];
+    const uint32_t L = len[t.x], n = L - k, p0 = t.y;
+    const uint32_t c = min((uint32_t)TILE_SLOTS, n - p0);
+    const uint64_t* words = seq + wordOff[t.x];
+    const uint32_t w0 = p0 >> 5, nw = ((p0 + c + k - 1) >> 5) - w0 + 1;
+    for (uint32_t i = threadIdx.x; i < nw; i += blockDim.x) sw[i] = words[w0 + i];
+    if (threadIdx.x == 0) sw[nw] = 0;
+    if (threadIdx.x < MAX_RANKS) cnt[threadIdx.x] = 0;
+    __syncthreads();
+    uint32_t own[PER], slot[PER], rk[PER];
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+        const uint32_t i = threadIdx.x + j * 256;
+        own[j] = 0xffffffffu;
+        if (i < c) {
+            uint64_t local;
+            ownerOf(m, denseIndexFromWindow(windowAt(sw, (p0 & 31) + i, k), k), own[j], local);
+            slot[j] = (uint32_t)local;
+            rk[j] = atomicAdd(&cnt[own[j]], 1u);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < m.nOwners && cnt[threadIdx.x])
+        base[threadIdx.x] = segStart[threadIdx.x] + atomicAdd(&cursor[threadIdx.x], (unsigned long long)cnt[threadIdx.x]);
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < PER; ++j)
+        if (own[j] != 0xffffffffu) sendBuf[base[own[j]] + rk[j]] = slot[j];
+}
+
+__global__ void __launch_bounds__(256) denseCountListKernel(const uint32_t* __restrict__ slots, uint64_t n, uint32_t* __restrict__ dense) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        atomicAdd(&dense[slots[i]], 1u);
+}
+
+// scan of the counters, pass 1: freq -> #k-mers histogram (vertex_index.cpp:567-576; shared-memory privatised low bins, global
+// atomics above, overflow list beyond 2^16), number of distinct k-mers (hist[0]) and of k-mers with count >= 2 (*nSolid)
 static constexpr int HIST_SMEM_BINS = 1024;
 static constexpr int HIST_GLOBAL_BINS = 1 << 16;
-__global__ void __launch_bounds__(256) histKernel(const uint32_t* __restrict__ counts, uint64_t n, unsigned long long* __restrict__ hist,
-                                                  uint32_t* __restrict__ overflow, uint32_t* __restrict__ nOverflow, uint32_t overflowCap) {
+__global__ void __launch_bounds__(256) denseHistKernel(const uint4* __restrict__ dense4, uint64_t n4, unsigned long long* __restrict__ hist,
+                                                       uint32_t* __restrict__ overflow, uint32_t* __restrict__ nOverflow, uint32_t overflowCap,
+                                                       unsigned long long* __restrict__ nSolid) {
     __shared__ uint32_t sh[HIST_SMEM_BINS];
     for (int i = threadIdx.x; i < HIST_SMEM_BINS; i += blockDim.x) sh[i] = 0;
     __syncthreads();
-    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-        uint32_t c = counts[i];
-        if (c < HIST_SMEM_BINS) atomicAdd(&sh[c], 1u);
-        else if (c < HIST_GLOBAL_BINS) atomicAdd(&hist[c], 1ULL);
-        else { uint32_t s = atomicAdd(nOverflow, 1u); if (s < overflowCap) overflow[s] = c; }
+    uint32_t distinct = 0, solid = 0;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n4; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint4 q = dense4[i];
+        if ((q.x | q.y | q.z | q.w) == 0u) continue;
+        const uint32_t cs[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t c = cs[j];
+            if (!c) continue;
+            ++distinct; solid += c >= 2u;
+            if (c == 1u) continue;            // counted below as distinct - everything else
+            if (c < HIST_SMEM_BINS) atomicAdd(&sh[c], 1u);
+            else if (c < HIST_GLOBAL_BINS) atomicAdd(&hist[c], 1ULL);
+            else { const uint32_t s = atomicAdd(nOverflow, 1u); if (s < overflowCap) overflow[s] = c; }
+        }
     }
     __syncthreads();
     for (int i = threadIdx.x; i < HIST_SMEM_BINS; i += blockDim.x)
         if (sh[i]) atomicAdd(&hist[i], (unsigned long long)sh[i]);
+    distinct = __reduce_add_sync(0xffffffffu, distinct);
+    solid = __reduce_add_sync(0xffffffffu, solid);
+    if ((threadIdx.x & 31) == 0) {
+        if (distinct) { atomicAdd(&hist[0], (unsigned long long)distinct); atomicAdd(&hist[1], (unsigned long long)(distinct - solid)); }
+        if (solid) atomicAdd(nSolid, (unsigned long long)solid);
+    }
 }
 
-template <class KeyT>
-__global__ void __launch_bounds__(256) buildCountTableKernel(const KeyT* __restrict__ ukeys, const uint32_t* __restrict__ counts,
-                                                             uint64_t n, Table table) {
-    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-        uint32_t c = counts[i];
-        if (c >= 2) tableInsertUnique(table, (uint64_t)ukeys[i], c);
+// pass 2: (canonical k-mer, count) of every class with count >= 2, appended in no particular order (they go into a hash table)
+__global__ void __launch_bounds__(256) denseEmitKernel(const uint4* __restrict__ dense4, uint64_t n4, DenseMap m, uint64_t* __restrict__ keys,
+                                                       uint32_t* __restrict__ counts, unsigned long long* __restrict__ cursor) {
+    const int lane = threadIdx.x & 31;
+    // whole warps step together (the append is warp aggregated)
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t nIter = (n4 + stride - 1) / stride;
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    for (uint64_t it = 0; it < nIter; ++it, i += stride) {
+        uint4 q = make_uint4(0, 0, 0, 0);
+        if (i < n4) q = dense4[i];
+        const uint32_t cs[4] = {q.x, q.y, q.z, q.w};
+        const uint32_t mine = (cs[0] >= 2u) + (cs[1] >= 2u) + (cs[2] >= 2u) + (cs[3] >= 2u);
+        if (!__any_sync(0xffffffffu, mine != 0u)) continue;
+        uint32_t incl = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += v; }
+        unsigned long long base = 0;
+        if (lane == 31) base = atomicAdd(cursor, (unsigned long long)incl);
+        base = __shfl_sync(0xffffffffu, base, 31) + (incl - mine);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (cs[j] >= 2u) {
+                const uint64_t local = 4ULL * i + j;
+                keys[base] = canonFromDenseIndex(local * m.nOwners + m.owner, m.k);
+                counts[base] = cs[j];
+                ++base;
+            }
     }
+}
+
+__global__ void __launch_bounds__(256) buildCountTableKernel(const uint64_t* __restrict__ ukeys, const uint32_t* __restrict__ counts,
+                                                             uint64_t n, Table table) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        tableInsertUnique(table, ukeys[i], counts[i]);
 }
 
 __global__ void fillSlotsKernel(ulonglong2* slots, uint64_t n) {
@@ -135,145 +293,145 @@ static Table makeTable(fg_ctx* ctx, DevBuf<ulonglong2>& buf, uint64_t nItems) {
     return t;
 }
 
-template <class KeyT>
-static void countKmersT(fg_ctx* ctx) {
-    const int k = ctx->k;
-    const uint32_t first = ctx->shardSet ? ctx->shardFirst : 0, count = ctx->shardSet ? ctx->shardCount : ctx->nReads;
-    size_t tLo, tHi;
-    tileRange(ctx, first, count, tLo, tHi);
-    const size_t nTiles = tHi - tLo;
-    // dense output offset of every tile
-    std::vector<uint64_t> hTileOut(nTiles + 1, 0);
-    for (size_t t = 0; t < nTiles; ++t) {
-        const uint2 tl = ctx->hTiles[tLo + t];
-        uint32_t n = ctx->hLen[tl.x] - k;
-        hTileOut[t + 1] = hTileOut[t] + std::min<uint32_t>(TILE_SLOTS, n - tl.y);
-    }
-    const uint64_t N = hTileOut[nTiles];
-    if (N >= (1ULL << 31)) throw Error(FG_ERR_ARG, "more than 2^31 k-mers in one counting shard; partition the reads over more GPUs");
-    ctx->hist.clear();
-    ctx->nDistinct = 0;
-    ctx->dCountSlots.release();
-    if (N == 0) {
-        if (sharded(ctx)) throw Error(FG_ERR_ARG, "a rank's read shard has no k-mers");
-        ctx->countTable = makeTable(ctx, ctx->dCountSlots, 0); ctx->counted = true; return;
-    }
-
-    DevBuf<uint64_t> dTileOut(nTiles + 1);
-    FG_CUDA(cudaMemcpyAsync(dTileOut.p, hTileOut.data(), (nTiles + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
-    DevBuf<KeyT> keysA(N), keysB(N);
-    {
-        PhaseTimer pt(ctx, "extract");
-        extractKeysKernel<KeyT><<<(unsigned)nTiles, 256, 0, ctx->stream>>>(ctx->dSeq.p, ctx->dWordOff.p, ctx->dLen.p,
-                                                                           ctx->dTiles.p + tLo, dTileOut.p, k, keysA.p);
-        checkLaunch(ctx, "extractKeysKernel");
-    }
-    cub::DoubleBuffer<KeyT> db(keysA.p, keysB.p);
-    {
-        PhaseTimer pt(ctx, "count_sort");
-        size_t tmpBytes = 0;
-        FG_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tmpBytes, db, (int)N, 0, 2 * k, ctx->stream));
-        DevBuf<char> tmp(tmpBytes);
-        FG_CUDA(cub::DeviceRadixSort::SortKeys(tmp.p, tmpBytes, db, (int)N, 0, 2 * k, ctx->stream));
-        ctx->launches += (2 * k + 7) / 8 + 1;
-    }
-    KeyT* sorted = db.Current();
-    KeyT* uniq = db.Alternate();   // the other buffer is free now
-    DevBuf<uint32_t> counts(N);
-    DevBuf<uint64_t> dRuns(1);
-    uint64_t nRuns = 0;
-    {
-        PhaseTimer pt(ctx, "count_reduce");
-        size_t tmpBytes = 0;
-        FG_CUDA(cub::DeviceRunLengthEncode::Encode(nullptr, tmpBytes, sorted, uniq, counts.p, dRuns.p, (int)N, ctx->stream));
-        DevBuf<char> tmp(tmpBytes);
-        FG_CUDA(cub::DeviceRunLengthEncode::Encode(tmp.p, tmpBytes, sorted, uniq, counts.p, dRuns.p, (int)N, ctx->stream));
-        ctx->launches += 2;
-        FG_CUDA(cudaMemcpyAsync(&nRuns, dRuns.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
-        FG_CUDA(cudaStreamSynchronize(ctx->stream));
-
-        // multi-GPU: every rank counted its own shard of the reads; all-gather the (k-mer,count) runs over NCCL and
-        // reduce them by key, so that every rank ends up with the global counts (replicated count table)
-        DevBuf<char> allKeys, allCounts; DevBuf<KeyT> mKeysB, mUniq; DevBuf<uint32_t> mCountsB, mCounts;
-        if (sharded(ctx)) {
-            std::vector<uint64_t> offK, offC;
-            allGatherV(ctx, uniq, nRuns * sizeof(KeyT), allKeys, offK);
-            allGatherV(ctx, counts.p, nRuns * 4ULL, allCounts, offC);
-            const uint64_t T = offC.back() / 4;
-            if (T >= (1ULL << 31)) throw Error(FG_ERR_ARG, "more than 2^31 (k-mer,count) runs to merge");
-            mKeysB.alloc(T); mCountsB.alloc(T); mUniq.alloc(T); mCounts.alloc(T);
-            cub::DoubleBuffer<KeyT> mk((KeyT*)allKeys.p, mKeysB.p);
-            cub::DoubleBuffer<uint32_t> mv((uint32_t*)allCounts.p, mCountsB.p);
-            size_t tb = 0;
-            FG_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, mk, mv, (int)T, 0, 2 * k, ctx->stream));
-            DevBuf<char> t1(tb);
-            FG_CUDA(cub::DeviceRadixSort::SortPairs(t1.p, tb, mk, mv, (int)T, 0, 2 * k, ctx->stream));
-            tb = 0;
-            FG_CUDA(cub::DeviceReduce::ReduceByKey(nullptr, tb, mk.Current(), mUniq.p, mv.Current(), mCounts.p, dRuns.p, cub::Sum(), (int)T, ctx->stream));
-            DevBuf<char> t2(tb);
-            FG_CUDA(cub::DeviceReduce::ReduceByKey(t2.p, tb, mk.Current(), mUniq.p, mv.Current(), mCounts.p, dRuns.p, cub::Sum(), (int)T, ctx->stream));
-            ctx->launches += (2 * k + 7) / 8 + 3;
-            FG_CUDA(cudaMemcpyAsync(&nRuns, dRuns.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
-            FG_CUDA(cudaStreamSynchronize(ctx->stream));
-        }
-        const KeyT* gUniq = sharded(ctx) ? mUniq.p : uniq;
-        const uint32_t* gCounts = sharded(ctx) ? mCounts.p : counts.p;
-
-        // histogram (vertex_index.cpp:567-576)
-        DevBuf<unsigned long long> dHist(HIST_GLOBAL_BINS);
-        const uint32_t ovCap = 1u << 20;
-        DevBuf<uint32_t> dOv(ovCap), dNOv(1);
-        FG_CUDA(cudaMemsetAsync(dHist.p, 0, dHist.bytes(), ctx->stream));
-        FG_CUDA(cudaMemsetAsync(dNOv.p, 0, 4, ctx->stream));
-        if (sharded(ctx)) {
-            // each rank histograms its slice of the merged runs; the freq -> #k-mers histogram is then reduced over NCCL
-            const uint64_t lo = nRuns * ctx->rank / ctx->nRanks, hi = nRuns * (ctx->rank + 1) / ctx->nRanks;
-            if (hi > lo) {
-                histKernel<<<gridFor(hi - lo), 256, 0, ctx->stream>>>(gCounts + lo, hi - lo, dHist.p, dOv.p, dNOv.p, ovCap);
-                checkLaunch(ctx, "histKernel");
-            }
-            allReduceSumU64(ctx, dHist.p, HIST_GLOBAL_BINS);
-            DevBuf<char> ovAll; std::vector<uint64_t> ovOff;
-            uint32_t myOv = 0;
-            FG_CUDA(cudaMemcpyAsync(&myOv, dNOv.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
-            FG_CUDA(cudaStreamSynchronize(ctx->stream));
-            if (myOv > ovCap) throw Error(FG_ERR_INTERNAL, "k-mer histogram overflow list exhausted");
-            allGatherV(ctx, dOv.p, myOv * 4ULL, ovAll, ovOff);
-            const uint32_t totOv = (uint32_t)(ovOff.back() / 4);
-            if (totOv > ovCap) throw Error(FG_ERR_INTERNAL, "k-mer histogram overflow list exhausted");
-            if (totOv) FG_CUDA(cudaMemcpyAsync(dOv.p, ovAll.p, totOv * 4ULL, cudaMemcpyDeviceToDevice, ctx->stream));
-            FG_CUDA(cudaMemcpyAsync(dNOv.p, &totOv, 4, cudaMemcpyHostToDevice, ctx->stream));
-        } else {
-            histKernel<<<gridFor(nRuns), 256, 0, ctx->stream>>>(gCounts, nRuns, dHist.p, dOv.p, dNOv.p, ovCap);
-            checkLaunch(ctx, "histKernel");
-        }
-        std::vector<unsigned long long> hHist(HIST_GLOBAL_BINS);
-        uint32_t nOv = 0;
-        FG_CUDA(cudaMemcpyAsync(hHist.data(), dHist.p, dHist.bytes(), cudaMemcpyDeviceToHost, ctx->stream));
-        FG_CUDA(cudaMemcpyAsync(&nOv, dNOv.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
-        FG_CUDA(cudaStreamSynchronize(ctx->stream));
-        if (nOv > ovCap) throw Error(FG_ERR_INTERNAL, "k-mer histogram overflow list exhausted");
-        for (int f = 1; f < HIST_GLOBAL_BINS; ++f) if (hHist[f]) ctx->hist[f] = hHist[f];
-        if (nOv) {
-            std::vector<uint32_t> ov(nOv);
-            FG_CUDA(cudaMemcpy(ov.data(), dOv.p, nOv * 4ULL, cudaMemcpyDeviceToHost));
-            for (uint32_t c : ov) ctx->hist[c] += 1;
-        }
-        ctx->nDistinct = nRuns;
-        uint64_t n2 = nRuns - (ctx->hist.count(1) ? ctx->hist[1] : 0);
-        ctx->countTable = makeTable(ctx, ctx->dCountSlots, n2);
-        buildCountTableKernel<KeyT><<<gridFor(nRuns), 256, 0, ctx->stream>>>(gUniq, gCounts, nRuns, ctx->countTable);
-        checkLaunch(ctx, "buildCountTableKernel");
-        FG_CUDA(cudaStreamSynchronize(ctx->stream));
-    }
-    ctx->counted = true;
-}
-
 void countKmers(fg_ctx* ctx, int k) {
     if (k > 17) throw Error(FG_ERR_KMER_SIZE, "Can't use flat counter for k-mer size > 17");   // vertex_index.cpp:504-507
     setKmerSize(ctx, k);
     ctx->timings.clear(); ctx->timingCalls.clear();
-    if (2 * k <= 32) countKmersT<uint32_t>(ctx); else countKmersT<uint64_t>(ctx);
+    const bool multi = sharded(ctx);
+    if (multi && ctx->nRanks > MAX_RANKS) throw Error(FG_ERR_ARG, "too many ranks");
+    const uint32_t first = ctx->shardSet ? ctx->shardFirst : 0, count = ctx->shardSet ? ctx->shardCount : ctx->nReads;
+    size_t tLo, tHi;
+    tileRange(ctx, first, count, tLo, tHi);
+    const size_t nTiles = tHi - tLo;
+    ctx->hist.clear();
+    ctx->nDistinct = 0;
+    ctx->dCountSlots.release();
+
+    DenseMap m; m.k = k; m.nOwners = multi ? (uint32_t)ctx->nRanks : 1u; m.owner = multi ? (uint32_t)ctx->rank : 0u;
+    m.ownerShift = 0xffffffffu;
+    for (uint32_t s = 0; s < 31; ++s) if ((1u << s) == m.nOwners) m.ownerShift = s;
+    // counters of this rank: slots of the classes i with i % nOwners == owner, padded to whole 16-byte groups
+    const uint64_t nLocal = ((denseSpace(k) + m.nOwners - 1) / m.nOwners + 3) & ~3ULL;
+    DevBuf<uint32_t> dense(nLocal);
+    {
+        PhaseTimer pt(ctx, "count_clear");
+        FG_CUDA(cudaMemsetAsync(dense.p, 0, nLocal * 4ULL, ctx->stream));
+    }
+    if (!multi) {
+        PhaseTimer pt(ctx, "count");
+        if (nTiles) {
+            denseCountKernel<<<(unsigned)nTiles, 256, 0, ctx->stream>>>(ctx->dSeq.p, ctx->dWordOff.p, ctx->dLen.p, ctx->dTiles.p + tLo, k, dense.p);
+            checkLaunch(ctx, "denseCountKernel");
+        }
+    } else {
+        const int R = ctx->nRanks;
+        if (nLocal >= (1ULL << 32)) throw Error(FG_ERR_ARG, "dense k-mer slots do not fit 32 bits");   // (cannot happen for k <= 17, N >= 2)
+        DevBuf<unsigned long long> dTot(3 * MAX_RANKS);   // totals, segment starts, cursors
+        std::vector<unsigned long long> hTot(R, 0), hStart(R, 0);
+        DevBuf<uint32_t> sendBuf, recvBuf;
+        std::vector<uint64_t> sendOffs(R + 1, 0), recvOffs;
+        {
+            PhaseTimer pt(ctx, "count_partition");
+            FG_CUDA(cudaMemsetAsync(dTot.p, 0, dTot.bytes(), ctx->stream));
+            if (nTiles) {
+                ownerTotalsKernel<<<(unsigned)nTiles, 256, 0, ctx->stream>>>(ctx->dSeq.p, ctx->dWordOff.p, ctx->dLen.p, ctx->dTiles.p + tLo, m, dTot.p);
+                checkLaunch(ctx, "ownerTotalsKernel");
+            }
+            FG_CUDA(cudaMemcpyAsync(hTot.data(), dTot.p, R * 8ULL, cudaMemcpyDeviceToHost, ctx->stream));
+            FG_CUDA(cudaStreamSynchronize(ctx->stream));
+            for (int r = 0; r < R; ++r) { hStart[r] = sendOffs[r] / 4; sendOffs[r + 1] = sendOffs[r] + hTot[r] * 4ULL; }
+            sendBuf.alloc(std::max<uint64_t>(sendOffs[R] / 4, 1));
+            FG_CUDA(cudaMemcpyAsync(dTot.p + MAX_RANKS, hStart.data(), R * 8ULL, cudaMemcpyHostToDevice, ctx->stream));
+            if (nTiles) {
+                ownerScatterKernel<<<(unsigned)nTiles, 256, 0, ctx->stream>>>(ctx->dSeq.p, ctx->dWordOff.p, ctx->dLen.p, ctx->dTiles.p + tLo, m,
+                                                                              dTot.p + MAX_RANKS, dTot.p + 2 * MAX_RANKS, sendBuf.p);
+                checkLaunch(ctx, "ownerScatterKernel");
+            }
+        }
+        {
+            PhaseTimer pt(ctx, "count_exchange");
+            exchangeSizes(ctx, sendOffs, recvOffs);
+            recvBuf.alloc(std::max<uint64_t>(recvOffs[R] / 4, 1));
+            allToAllVInto(ctx, sendBuf.p, sendOffs, recvBuf.p, recvOffs);
+        }
+        sendBuf.release();
+        PhaseTimer pt(ctx, "count");
+        const uint64_t nRecv = recvOffs[R] / 4;
+        if (nRecv) {
+            denseCountListKernel<<<gridFor(nRecv, 256, 16), 256, 0, ctx->stream>>>(recvBuf.p, nRecv, dense.p);
+            checkLaunch(ctx, "denseCountListKernel");
+        }
+    }
+
+    // histogram (vertex_index.cpp:567-576), distinct k-mers, k-mers with count >= 2
+    DevBuf<unsigned long long> dHist(HIST_GLOBAL_BINS), dSolid(2);
+    const uint32_t ovCap = 1u << 20;
+    DevBuf<uint32_t> dOv(ovCap), dNOv(1);
+    unsigned long long hSolid = 0;
+    uint32_t nOv = 0;
+    {
+        PhaseTimer pt(ctx, "count_hist");
+        FG_CUDA(cudaMemsetAsync(dHist.p, 0, dHist.bytes(), ctx->stream));
+        FG_CUDA(cudaMemsetAsync(dNOv.p, 0, 4, ctx->stream));
+        FG_CUDA(cudaMemsetAsync(dSolid.p, 0, 16, ctx->stream));
+        denseHistKernel<<<gridFor(nLocal / 4, 256, 16), 256, 0, ctx->stream>>>(reinterpret_cast<const uint4*>(dense.p), nLocal / 4, dHist.p, dOv.p, dNOv.p,
+                                                                              ovCap, dSolid.p);
+        checkLaunch(ctx, "denseHistKernel");
+        FG_CUDA(cudaMemcpyAsync(&hSolid, dSolid.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        FG_CUDA(cudaMemcpyAsync(&nOv, dNOv.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        FG_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    agreeOrThrow(ctx, nOv > ovCap ? FG_ERR_INTERNAL : 0, "k-mer histogram overflow list exhausted");
+    // this rank's k-mers with count >= 2
+    DevBuf<uint64_t> solidKeys(std::max<uint64_t>(hSolid, 1));
+    DevBuf<uint32_t> solidCounts(std::max<uint64_t>(hSolid, 1));
+    {
+        PhaseTimer pt(ctx, "count_emit");
+        if (hSolid) {
+            denseEmitKernel<<<gridFor(nLocal / 4, 256, 16), 256, 0, ctx->stream>>>(reinterpret_cast<const uint4*>(dense.p), nLocal / 4, m, solidKeys.p,
+                                                                                  solidCounts.p, dSolid.p + 1);
+            checkLaunch(ctx, "denseEmitKernel");
+        }
+    }
+    dense.release();
+    uint64_t nSolidAll = hSolid;
+    DevBuf<uint64_t> allKeys; DevBuf<uint32_t> allCounts;
+    std::vector<uint32_t> ov(nOv);
+    if (nOv) FG_CUDA(cudaMemcpyAsync(ov.data(), dOv.p, nOv * 4ULL, cudaMemcpyDeviceToHost, ctx->stream));
+    if (multi) {
+        PhaseTimer pt(ctx, "count_merge");
+        allReduceSumU64(ctx, dHist.p, HIST_GLOBAL_BINS);
+        std::vector<uint64_t> offs;
+        allGatherSizes(ctx, hSolid * 8ULL, offs);
+        nSolidAll = offs.back() / 8;
+        allKeys.alloc(std::max<uint64_t>(nSolidAll, 1)); allCounts.alloc(std::max<uint64_t>(nSolidAll, 1));
+        allGatherVInto(ctx, solidKeys.p, offs, allKeys.p);
+        for (auto& o : offs) o /= 2;
+        allGatherVInto(ctx, solidCounts.p, offs, allCounts.p);
+        // counts beyond the histogram's dense bins are rare: gather the few values
+        DevBuf<char> ovAll; std::vector<uint64_t> ovOff;
+        allGatherV(ctx, dOv.p, nOv * 4ULL, ovAll, ovOff);
+        ov.resize(ovOff.back() / 4);
+        if (!ov.empty()) FG_CUDA(cudaMemcpyAsync(ov.data(), ovAll.p, ov.size() * 4ULL, cudaMemcpyDeviceToHost, ctx->stream));
+        FG_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    std::vector<unsigned long long> hHist(HIST_GLOBAL_BINS);
+    FG_CUDA(cudaMemcpyAsync(hHist.data(), dHist.p, dHist.bytes(), cudaMemcpyDeviceToHost, ctx->stream));
+    FG_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->nDistinct = hHist[0];
+    for (int f = 1; f < HIST_GLOBAL_BINS; ++f) if (hHist[f]) ctx->hist[f] = hHist[f];
+    for (uint32_t c : ov) ctx->hist[c] += 1;
+    {
+        PhaseTimer pt(ctx, "count_table");
+        ctx->countTable = makeTable(ctx, ctx->dCountSlots, nSolidAll);
+        if (nSolidAll) {
+            buildCountTableKernel<<<gridFor(nSolidAll, 256, 16), 256, 0, ctx->stream>>>(multi ? allKeys.p : solidKeys.p, multi ? allCounts.p : solidCounts.p,
+                                                                                       nSolidAll, ctx->countTable);
+            checkLaunch(ctx, "buildCountTableKernel");
+        }
+        FG_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    ctx->counted = true;
 }
 
 // KmerCounter::getFreq for a batch (tests)
@@ -305,7 +463,7 @@ void kmerFreqQuery(fg_ctx* ctx, const uint64_t* kmers, uint32_t n, uint32_t* out
 __global__ void __launch_bounds__(256) selectKernel(const uint64_t* __restrict__ seq, const uint64_t* __restrict__ wordOff,
                                                     const uint32_t* __restrict__ len, const uint64_t* __restrict__ slotOff,
                                                     int k, Table countTable, float selectRate, int tandemFreq,
-                                                    uint32_t readFirst, uint32_t* __restrict__ freq, uint32_t* __restrict__ rcBits,
+                                                    uint32_t readFirst, uint64_t slotBase, uint32_t* __restrict__ freqShard, uint32_t* __restrict__ rcBits,
                                                     uint32_t* __restrict__ minFreqOut, unsigned long long* __restrict__ nTandemCand) {
     const uint32_t r = readFirst + blockIdx.x;
     const uint32_t L = len[r];
@@ -313,6 +471,7 @@ __global__ void __launch_bounds__(256) selectKernel(const uint64_t* __restrict__
     const uint32_t n = L - k;
     const uint64_t* words = seq + wordOff[r];
     const uint64_t base = slotOff[r];
+    uint32_t* freq = freqShard - slotBase;   // freq[] only covers the slots of this rank's read shard: indexed by global slot below
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nWarps = blockDim.x >> 5;
 
     __shared__ uint32_t hist[256];
@@ -391,9 +550,10 @@ __global__ void __launch_bounds__(256) selectKernel(const uint64_t* __restrict__
 // for: key (read, canonical k-mer) -> occurrences of that k-mer in that read.
 __global__ void __launch_bounds__(256) tandemCountKernel(const uint64_t* __restrict__ seq, const uint64_t* __restrict__ wordOff,
                                                          const uint32_t* __restrict__ len, const uint64_t* __restrict__ slotOff,
-                                                         const uint2* __restrict__ tiles, int k, int tandemFreq,
-                                                         const uint32_t* __restrict__ freq, const uint32_t* __restrict__ minFreq,
+                                                         const uint2* __restrict__ tiles, int k, int tandemFreq, uint64_t slotBase,
+                                                         const uint32_t* __restrict__ freqShard, const uint32_t* __restrict__ minFreq,
                                                          Table tandem) {
+    const uint32_t* freq = freqShard - slotBase;
     const uint2 t = tiles[blockIdx.x];
     const uint32_t r = t.x, n = len[r] - k;
     const uint32_t cnt = min((uint32_t)TILE_SLOTS, n - t.y);
@@ -415,9 +575,10 @@ __global__ void __launch_bounds__(256) tandemCountKernel(const uint64_t* __restr
 // pass 1 (vertex_index.cpp:51), not a tandem k-mer (:346-355)
 __global__ void __launch_bounds__(256) finalizeSelectionKernel(const uint64_t* __restrict__ seq, const uint64_t* __restrict__ wordOff,
                                                                const uint32_t* __restrict__ len, const uint64_t* __restrict__ slotOff,
-                                                               const uint2* __restrict__ tiles, int k, int minCov, int tandemFreq,
-                                                               const uint32_t* __restrict__ freq, const uint32_t* __restrict__ minFreq,
+                                                               const uint2* __restrict__ tiles, int k, int minCov, int tandemFreq, uint64_t slotBase,
+                                                               const uint32_t* __restrict__ freqShard, const uint32_t* __restrict__ minFreq,
                                                                Table tandem, bool haveTandem, uint32_t* __restrict__ selBits) {
+    const uint32_t* freq = freqShard - slotBase;
     const uint2 t = tiles[blockIdx.x];
     const uint32_t r = t.x, n = len[r] - k;
     const uint32_t cnt = min((uint32_t)TILE_SLOTS, n - t.y);
@@ -686,12 +847,59 @@ __global__ void __launch_bounds__(256) emitWriteKernel(const uint64_t* __restric
     }
 }
 
+// run-length encoding of the sorted keys in two passes over 2048-key tiles (any number of keys; the library's encoder takes an
+// int): head counts per tile, one scan of the tile counts, then every head writes its key and its start position.  The start
+// positions ARE the CSR offsets ("first" of every key); the capacity of key g is starts[g+1] - starts[g].
+static constexpr int RLE_PER = 8, RLE_TILE = 256 * RLE_PER;
+template <class KeyT>
+__global__ void __launch_bounds__(256) rleCountKernel(const KeyT* __restrict__ keys, uint64_t n, uint32_t* __restrict__ tileHeads) {
+    const uint64_t i0 = (uint64_t)blockIdx.x * RLE_TILE + (uint64_t)threadIdx.x * RLE_PER;
+    uint32_t c = 0;
+    if (i0 < n) {
+        KeyT prev = i0 ? keys[i0 - 1] : (KeyT)0;
+#pragma unroll
+        for (int j = 0; j < RLE_PER; ++j)
+            if (i0 + j < n) { const KeyT x = keys[i0 + j]; c += (i0 + j == 0) || x != prev; prev = x; }
+    }
+    c = __reduce_add_sync(0xffffffffu, c);
+    __shared__ uint32_t ws[8];
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) { uint32_t t = 0; for (int w = 0; w < 8; ++w) t += ws[w]; tileHeads[blockIdx.x] = t; }
+}
+template <class KeyT>
+__global__ void __launch_bounds__(256) rleWriteKernel(const KeyT* __restrict__ keys, uint64_t n, const uint64_t* __restrict__ tileBase,
+                                                      KeyT* __restrict__ ukeys, uint64_t* __restrict__ starts) {
+    const uint64_t i0 = (uint64_t)blockIdx.x * RLE_TILE + (uint64_t)threadIdx.x * RLE_PER;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    KeyT x[RLE_PER]; uint32_t heads = 0;
+    if (i0 < n) {
+        KeyT prev = i0 ? keys[i0 - 1] : (KeyT)0;
+#pragma unroll
+        for (int j = 0; j < RLE_PER; ++j)
+            if (i0 + j < n) { x[j] = keys[i0 + j]; if ((i0 + j == 0) || x[j] != prev) heads |= 1u << j; prev = x[j]; }
+    }
+    const uint32_t mine = __popc(heads);
+    uint32_t incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += v; }
+    __shared__ uint32_t ws[8];
+    if (lane == 31) ws[w] = incl;
+    __syncthreads();
+    uint32_t before = 0;
+    for (int v = 0; v < w; ++v) before += ws[v];
+    uint64_t g = tileBase[blockIdx.x] + before + (incl - mine);
+#pragma unroll
+    for (int j = 0; j < RLE_PER; ++j)
+        if (heads & (1u << j)) { ukeys[g] = x[j]; starts[g] = i0 + j; ++g; }
+}
+
 // totals for filterFrequentKmers (vertex_index.cpp:175-184)
-__global__ void __launch_bounds__(256) capacityTotalsKernel(const uint32_t* __restrict__ cap, uint64_t n, uint32_t minCov,
+__global__ void __launch_bounds__(256) capacityTotalsKernel(const uint64_t* __restrict__ starts, uint64_t n, uint32_t minCov,
                                                             unsigned long long* __restrict__ totals) {
     unsigned long long total = 0, uniq = 0;
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-        uint32_t c = cap[i];
+        const uint64_t c = starts[i + 1] - starts[i];
         if (c >= minCov) { total += c; ++uniq; }
     }
     for (int d = 16; d; d >>= 1) { total += __shfl_down_sync(0xffffffffu, total, d); uniq += __shfl_down_sync(0xffffffffu, uniq, d); }
@@ -700,27 +908,28 @@ __global__ void __launch_bounds__(256) capacityTotalsKernel(const uint32_t* __re
 
 // classification of every distinct emitted key (vertex_index.cpp:188-202 repetitive set; :73-74 frequency gate
 // of pass 2) + table payload.  stats: [0] repetitive keys, [1] valid entries, [2] valid-or-empty keys, [3] too-frequent flag
+// entryBase: position of this rank's first entry in the replicated entry array (multi-GPU), 0 otherwise
 template <class KeyT>
-__global__ void __launch_bounds__(256) classifyKernel(const KeyT* __restrict__ ukeys, const uint32_t* __restrict__ cap,
-                                                      const uint64_t* __restrict__ first, uint64_t n, uint64_t repFreq,
-                                                      bool minimizerMode, Table countTable, uint64_t* __restrict__ keys64,
-                                                      uint64_t* __restrict__ payload, unsigned long long* __restrict__ stats) {
+__global__ void __launch_bounds__(256) classifyKernel(const KeyT* __restrict__ ukeys, const uint64_t* __restrict__ starts, uint64_t n,
+                                                      uint64_t repFreq, uint64_t entryBase, bool minimizerMode, Table countTable,
+                                                      uint64_t* __restrict__ keys64, uint64_t* __restrict__ payload,
+                                                      unsigned long long* __restrict__ stats) {
     unsigned long long nRep = 0, nEnt = 0, nKeys = 0;
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         const uint64_t key = (uint64_t)ukeys[i];
-        const uint32_t c = cap[i];
+        const uint64_t c = starts[i + 1] - starts[i];
         uint64_t pl;
-        if ((uint64_t)c > repFreq) { pl = IDX_REPETITIVE; ++nRep; }
+        if (c > repFreq) { pl = IDX_REPETITIVE; ++nRep; }
         else {
             ++nKeys;
-            if ((uint64_t)c + 1 > MEM_CHUNK) atomicExch(&stats[3], 1ULL);   // allocateIndexMemory, vertex_index.cpp:372-375
+            if (c + 1 > MEM_CHUNK) atomicExch(&stats[3], 1ULL);   // allocateIndexMemory, vertex_index.cpp:372-375
             bool valid = true;
             if (!minimizerMode) {
                 uint64_t f = 1;
                 tableFind(countTable, key, f);
                 valid = f <= repFreq;
             }
-            if (valid) { pl = (first[i] << IDX_SIZE_BITS) | c; nEnt += c; }
+            if (valid) { pl = ((entryBase + starts[i]) << IDX_SIZE_BITS) | c; nEnt += c; }
             else pl = ~0ULL;   // key stays in the reference's table with size 0: behaves as absent
         }
         keys64[i] = key;
@@ -750,10 +959,98 @@ __global__ void __launch_bounds__(256) unpackEntriesKernel(const uint64_t* __res
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Multi-GPU: the index entries are sorted by the rank that OWNS their key (owner = multiply-shift of a hash of the key, so
+// the shares are even whatever the key distribution is).  A STABLE partition keeps the emission order — global position
+// ascending — inside every share; shards are ascending read ranges, so concatenating what the ranks send in rank order keeps
+// it across ranks too, and the owner's single stable sort by key yields position-sorted lists as on one GPU.
+// ------------------------------------------------------------------------------------------------
+static constexpr int PART_PER = 8, PART_TILE = 256 * PART_PER;
+// (explicit __umulhi: written as a 64-bit product shifted by 32, nvcc 12.9 folded the index arithmetic of partCountKernel's
+// shared-memory atomic into `hi * (nOwners >> 30)` — every key counted for owner 0; cuobjdump showed LEA.HI + IMAD)
+__device__ __forceinline__ uint32_t indexOwner(uint64_t key, uint32_t nOwners) {
+    return __umulhi((uint32_t)(mix64(key) >> 32), nOwners);
+}
+template <class KeyT>
+__global__ void __launch_bounds__(256) partCountKernel(const KeyT* __restrict__ keys, uint64_t n, uint32_t nOwners, uint32_t nTiles,
+                                                       uint32_t* __restrict__ cntT) {
+    __shared__ uint32_t cnt[MAX_RANKS];
+    if (threadIdx.x < MAX_RANKS) cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const uint64_t base = (uint64_t)blockIdx.x * PART_TILE;
+    for (uint32_t i = threadIdx.x; i < PART_TILE && base + i < n; i += 256) atomicAdd(&cnt[indexOwner((uint64_t)keys[base + i], nOwners)], 1u);
+    __syncthreads();
+    if (threadIdx.x < nOwners) cntT[(uint64_t)threadIdx.x * nTiles + blockIdx.x] = cnt[threadIdx.x];
+}
+template <class KeyT>
+__global__ void __launch_bounds__(256) partScatterKernel(const KeyT* __restrict__ keys, const uint64_t* __restrict__ vals, uint64_t n,
+                                                         uint32_t nOwners, uint32_t nTiles, const uint64_t* __restrict__ offT,
+                                                         KeyT* __restrict__ outK, uint64_t* __restrict__ outV) {
+    __shared__ uint32_t wc[8][MAX_RANKS];
+    __shared__ uint64_t wbase[8][MAX_RANKS];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < 8 * MAX_RANKS; i += 256) (&wc[0][0])[i] = 0;
+    __syncthreads();
+    // warp w owns the 256 consecutive items [base, base + 256) of the tile, 32 consecutive ones per round
+    const uint64_t base = (uint64_t)blockIdx.x * PART_TILE + (uint64_t)w * (32 * PART_PER);
+    KeyT key[PART_PER]; uint64_t val[PART_PER]; uint32_t own[PART_PER];
+#pragma unroll
+    for (int r = 0; r < PART_PER; ++r) {
+        const uint64_t i = base + r * 32 + lane;
+        const bool act = i < n;
+        own[r] = 0xffffffffu;
+        if (act) { key[r] = keys[i]; val[r] = vals[i]; own[r] = indexOwner((uint64_t)key[r], nOwners); }
+        const uint32_t am = __ballot_sync(0xffffffffu, act);
+        if (act) {
+            const uint32_t peers = __match_any_sync(am, own[r]);
+            if ((peers & ((1u << lane) - 1u)) == 0u) wc[w][own[r]] += __popc(peers);
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    if (threadIdx.x < nOwners) {
+        uint64_t run = offT[(uint64_t)threadIdx.x * nTiles + blockIdx.x];
+        for (int v = 0; v < 8; ++v) { wbase[v][threadIdx.x] = run; run += wc[v][threadIdx.x]; }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < PART_PER; ++r) {
+        const bool act = own[r] != 0xffffffffu;
+        const uint32_t am = __ballot_sync(0xffffffffu, act);
+        uint64_t pos = 0; uint32_t peers = 0;
+        if (act) {
+            peers = __match_any_sync(am, own[r]);
+            pos = wbase[w][own[r]] + __popc(peers & ((1u << lane) - 1u));
+        }
+        __syncwarp();
+        if (act) {
+            if ((peers & ((1u << lane) - 1u)) == 0u) wbase[w][own[r]] += __popc(peers);
+            outK[pos] = key[r]; outV[pos] = val[r];
+        }
+        __syncwarp();
+    }
+}
+
+struct CastU32ToU64 { __host__ __device__ uint64_t operator()(uint32_t x) const { return x; } };
+// out[0] = 0, out[i+1] = in[0] + ... + in[i] (64-bit sums of 32-bit counts)
+static void prefixU32(fg_ctx* ctx, const uint32_t* in, uint64_t n, uint64_t* out) {
+    FG_CUDA(cudaMemsetAsync(out, 0, 8, ctx->stream));
+    if (!n) return;
+    cub::TransformInputIterator<uint64_t, CastU32ToU64, const uint32_t*> it(in, CastU32ToU64());
+    size_t tmpBytes = 0;
+    FG_CUDA(cub::DeviceScan::InclusiveSum(nullptr, tmpBytes, it, out + 1, (uint64_t)n, ctx->stream));
+    DevBuf<char> tmp(tmpBytes);
+    FG_CUDA(cub::DeviceScan::InclusiveSum(tmp.p, tmpBytes, it, out + 1, (uint64_t)n, ctx->stream));
+    ++ctx->launches;
+}
+
 // shared tail of both index builders: selected/rc bitmaps -> entries -> CSR + table
 template <class KeyT>
 static void buildFromSelection(fg_ctx* ctx, DevBuf<uint32_t>& rcBits, int minCov, float repeatRate, float sampleRateIn) {
     const int k = ctx->k;
+    const bool multi = sharded(ctx);
+    const int R = multi ? ctx->nRanks : 1;
+    if (R > MAX_RANKS) throw Error(FG_ERR_ARG, "too many ranks");
     const uint32_t firstRead = ctx->shardSet ? ctx->shardFirst : 0, nReadsShard = ctx->shardSet ? ctx->shardCount : ctx->nReads;
     size_t tLo, tHi;
     tileRange(ctx, firstRead, nReadsShard, tLo, tHi);
@@ -781,52 +1078,56 @@ static void buildFromSelection(fg_ctx* ctx, DevBuf<uint32_t>& rcBits, int minCov
             emitCountKernel<<<grid, 256, 0, ctx->stream>>>(ctx->dSlotOff.p, ctx->dLen.p, ctx->dTiles.p, dEtiles.p, nEtiles, k,
                                                            ctx->dSelBits.p, rcBits.p, dCount.p);
             checkLaunch(ctx, "emitCountKernel");
-            size_t tmpBytes = 0;
-            FG_CUDA(cudaMemsetAsync(dOff.p, 0, 8, ctx->stream));
-            FG_CUDA(cub::DeviceScan::InclusiveSum(nullptr, tmpBytes, dCount.p, dOff.p + 1, (int)nEtiles, ctx->stream));
-            DevBuf<char> tmp(tmpBytes);
-            FG_CUDA(cub::DeviceScan::InclusiveSum(tmp.p, tmpBytes, dCount.p, dOff.p + 1, (int)nEtiles, ctx->stream));
-            ++ctx->launches;
+            prefixU32(ctx, dCount.p, nEtiles, dOff.p);
             FG_CUDA(cudaMemcpyAsync(&E, dOff.p + nEtiles, 8, cudaMemcpyDeviceToHost, ctx->stream));
             FG_CUDA(cudaStreamSynchronize(ctx->stream));
-            if (E >= (1ULL << 31)) throw Error(FG_ERR_ARG, "more than 2^31 index entries in one shard; partition the reads over more GPUs");
-            keysA.alloc(std::max<uint64_t>(E, 1)); keysB.alloc(std::max<uint64_t>(E, 1));
-            valsA.alloc(std::max<uint64_t>(E, 1)); valsB.alloc(std::max<uint64_t>(E, 1));
+            keysA.alloc(std::max<uint64_t>(E, 1)); valsA.alloc(std::max<uint64_t>(E, 1));
             emitWriteKernel<KeyT><<<grid, 256, 0, ctx->stream>>>(ctx->dSeq.p, ctx->dWordOff.p, ctx->dSlotOff.p, ctx->dLen.p,
                                                                  ctx->dTiles.p, dEtiles.p, nEtiles, k, ctx->dSelBits.p, rcBits.p,
                                                                  dOff.p, keysA.p, valsA.p);
             checkLaunch(ctx, "emitWriteKernel");
             FG_CUDA(cudaStreamSynchronize(ctx->stream));
-        }
+        } else { keysA.alloc(1); valsA.alloc(1); }
     }
-    if (sharded(ctx)) {
-        // shards are contiguous, ascending read ranges, so concatenating the ranks' entries in rank order keeps the
-        // global-position order the single stable sort below relies on
-        DevBuf<char> allK, allV; std::vector<uint64_t> offK, offV;
-        allGatherV(ctx, keysA.p, E * sizeof(KeyT), allK, offK);
-        allGatherV(ctx, valsA.p, E * 8ULL, allV, offV);
-        E = offV.back() / 8;
-        if (E >= (1ULL << 31)) throw Error(FG_ERR_ARG, "more than 2^31 index entries");
-        keysA.alloc(std::max<uint64_t>(E, 1)); keysB.alloc(std::max<uint64_t>(E, 1));
-        valsA.alloc(std::max<uint64_t>(E, 1)); valsB.alloc(std::max<uint64_t>(E, 1));
+    if (multi) {
+        PhaseTimer pt(ctx, "index_exchange");
+        // stable partition of this rank's entries by the owner of their key, then one all-to-all
+        const uint32_t nTiles = (uint32_t)((E + PART_TILE - 1) / PART_TILE);
+        DevBuf<KeyT> pk(std::max<uint64_t>(E, 1)); DevBuf<uint64_t> pv(std::max<uint64_t>(E, 1));
+        std::vector<uint64_t> items(R + 1, 0);
         if (E) {
-            FG_CUDA(cudaMemcpyAsync(keysA.p, allK.p, E * sizeof(KeyT), cudaMemcpyDeviceToDevice, ctx->stream));
-            FG_CUDA(cudaMemcpyAsync(valsA.p, allV.p, E * 8ULL, cudaMemcpyDeviceToDevice, ctx->stream));
+            DevBuf<uint32_t> cntT((uint64_t)R * nTiles);
+            DevBuf<uint64_t> offT((uint64_t)R * nTiles + 1);
+            partCountKernel<KeyT><<<nTiles, 256, 0, ctx->stream>>>(keysA.p, E, (uint32_t)R, nTiles, cntT.p);
+            checkLaunch(ctx, "partCountKernel");
+            prefixU32(ctx, cntT.p, (uint64_t)R * nTiles, offT.p);
+            partScatterKernel<KeyT><<<nTiles, 256, 0, ctx->stream>>>(keysA.p, valsA.p, E, (uint32_t)R, nTiles, offT.p, pk.p, pv.p);
+            checkLaunch(ctx, "partScatterKernel");
+            for (int r = 0; r <= R; ++r)
+                FG_CUDA(cudaMemcpyAsync(&items[r], offT.p + (uint64_t)r * nTiles, 8, cudaMemcpyDeviceToHost, ctx->stream));
+            FG_CUDA(cudaStreamSynchronize(ctx->stream));
         }
+        std::vector<uint64_t> recvItems, sOff(R + 1), rOff(R + 1);
+        exchangeSizes(ctx, items, recvItems);
+        E = recvItems[R];
+        keysA.alloc(std::max<uint64_t>(E, 1)); valsA.alloc(std::max<uint64_t>(E, 1));
+        for (int r = 0; r <= R; ++r) { sOff[r] = items[r] * sizeof(KeyT); rOff[r] = recvItems[r] * sizeof(KeyT); }
+        allToAllVInto(ctx, pk.p, sOff, keysA.p, rOff);
+        for (int r = 0; r <= R; ++r) { sOff[r] = items[r] * 8ULL; rOff[r] = recvItems[r] * 8ULL; }
+        allToAllVInto(ctx, pv.p, sOff, valsA.p, rOff);
         // the "selected" bitmap (needed for the self-hit test of every query) is replicated by one NCCL broadcast per
         // owner; each rank owns the whole bitmap words of its reads
-        std::vector<uint32_t> firsts(ctx->nRanks + 1, 0);
-        {
-            DevBuf<char> all; std::vector<uint64_t> off;
-            DevBuf<uint32_t> mine(1);
-            FG_CUDA(cudaMemcpyAsync(mine.p, &firstRead, 4, cudaMemcpyHostToDevice, ctx->stream));
-            allGatherV(ctx, mine.p, 4, all, off);
-            FG_CUDA(cudaMemcpyAsync(firsts.data(), all.p, ctx->nRanks * 4ULL, cudaMemcpyDeviceToHost, ctx->stream));
-            FG_CUDA(cudaStreamSynchronize(ctx->stream));
-            firsts[ctx->nRanks] = ctx->nReads;
-        }
+        std::vector<uint64_t> fOff;
+        DevBuf<uint32_t> mine(1), all(R);
+        FG_CUDA(cudaMemcpyAsync(mine.p, &firstRead, 4, cudaMemcpyHostToDevice, ctx->stream));
+        allGatherSizes(ctx, 4, fOff);
+        allGatherVInto(ctx, mine.p, fOff, all.p);
+        std::vector<uint32_t> firsts(R + 1, 0);
+        FG_CUDA(cudaMemcpyAsync(firsts.data(), all.p, R * 4ULL, cudaMemcpyDeviceToHost, ctx->stream));
+        FG_CUDA(cudaStreamSynchronize(ctx->stream));
+        firsts[R] = ctx->nReads;
         groupStart();
-        for (int r = 0; r < ctx->nRanks; ++r) {
+        for (int r = 0; r < R; ++r) {
             const uint64_t w0 = ctx->hSlotOff[firsts[r]] / 32, w1 = ctx->hSlotOff[firsts[r + 1]] / 32;
             broadcastBytes(ctx, ctx->dSelBits.p + w0, (w1 - w0) * 4, r);
         }
@@ -836,57 +1137,61 @@ static void buildFromSelection(fg_ctx* ctx, DevBuf<uint32_t>& rcBits, int minCov
     ctx->dEntries.release(); ctx->dIndexSlots.release(); ctx->dUKeys.release(); ctx->dUPayload.release();
     ctx->stats = fg_index_stats{};
     ctx->stats.sample_rate = sampleRateIn;
-    ctx->nEntriesStored = E; ctx->nUKeys = 0;
-    if (E == 0) {
-        ctx->indexTable = makeTable(ctx, ctx->dIndexSlots, 0);
-        ctx->dEntries.alloc(1);
-        FG_CUDA(cudaStreamSynchronize(ctx->stream));
-        ctx->indexed = true;
-        return;
-    }
+    ctx->nEntriesStored = 0; ctx->nUKeys = 0;
+
+    // this rank's entries sorted by (key, global position): one stable radix sort by key
+    keysB.alloc(std::max<uint64_t>(E, 1)); valsB.alloc(std::max<uint64_t>(E, 1));
     cub::DoubleBuffer<KeyT> dbK(keysA.p, keysB.p);
     cub::DoubleBuffer<uint64_t> dbV(valsA.p, valsB.p);
-    {
+    if (E) {
         PhaseTimer pt(ctx, "index_sort");
         size_t tmpBytes = 0;
-        FG_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmpBytes, dbK, dbV, (int)E, 0, 2 * k, ctx->stream));
+        FG_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmpBytes, dbK, dbV, (uint64_t)E, 0, 2 * k, ctx->stream));
         DevBuf<char> tmp(tmpBytes);
-        FG_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmpBytes, dbK, dbV, (int)E, 0, 2 * k, ctx->stream));
+        FG_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmpBytes, dbK, dbV, (uint64_t)E, 0, 2 * k, ctx->stream));
         ctx->launches += (2 * k + 7) / 8 + 1;
         FG_CUDA(cudaStreamSynchronize(ctx->stream));
     }
     PhaseTimer pt(ctx, "index_table");
-    // entries in their final (key, global position) order
-    ctx->dEntries.alloc(E);
-    unpackEntriesKernel<<<gridFor(E), 256, 0, ctx->stream>>>(dbV.Current(), E, ctx->dEntries.p);
-    checkLaunch(ctx, "unpackEntriesKernel");
     KeyT* sortedKeys = dbK.Current();
     KeyT* ukeys = dbK.Alternate();
-    DevBuf<uint32_t> cap(E);
-    DevBuf<uint64_t> dRuns(1);
     uint64_t S = 0;
+    DevBuf<uint64_t> starts;
     {
-        size_t tmpBytes = 0;
-        FG_CUDA(cub::DeviceRunLengthEncode::Encode(nullptr, tmpBytes, sortedKeys, ukeys, cap.p, dRuns.p, (int)E, ctx->stream));
-        DevBuf<char> tmp(tmpBytes);
-        FG_CUDA(cub::DeviceRunLengthEncode::Encode(tmp.p, tmpBytes, sortedKeys, ukeys, cap.p, dRuns.p, (int)E, ctx->stream));
-        ctx->launches += 2;
-        FG_CUDA(cudaMemcpyAsync(&S, dRuns.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        const uint32_t nTiles = (uint32_t)((E + RLE_TILE - 1) / RLE_TILE);
+        DevBuf<uint32_t> tileHeads(std::max<uint32_t>(nTiles, 1));
+        DevBuf<uint64_t> tileBase(nTiles + 1);
+        if (nTiles) {
+            rleCountKernel<KeyT><<<nTiles, 256, 0, ctx->stream>>>(sortedKeys, E, tileHeads.p);
+            checkLaunch(ctx, "rleCountKernel");
+        }
+        prefixU32(ctx, tileHeads.p, nTiles, tileBase.p);
+        FG_CUDA(cudaMemcpyAsync(&S, tileBase.p + nTiles, 8, cudaMemcpyDeviceToHost, ctx->stream));
         FG_CUDA(cudaStreamSynchronize(ctx->stream));
+        starts.alloc(S + 1);
+        if (nTiles) {
+            rleWriteKernel<KeyT><<<nTiles, 256, 0, ctx->stream>>>(sortedKeys, E, tileBase.p, ukeys, starts.p);
+            checkLaunch(ctx, "rleWriteKernel");
+        }
+        FG_CUDA(cudaMemcpyAsync(starts.p + S, &E, 8, cudaMemcpyHostToDevice, ctx->stream));
     }
-    DevBuf<uint64_t> first(S);
-    {
-        size_t tmpBytes = 0;
-        FG_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, cap.p, first.p, (int)S, ctx->stream));
-        DevBuf<char> tmp(tmpBytes);
-        FG_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmpBytes, cap.p, first.p, (int)S, ctx->stream));
-        ++ctx->launches;
-    }
-    DevBuf<unsigned long long> dTotals(2), dStats(4);
-    FG_CUDA(cudaMemsetAsync(dTotals.p, 0, 16, ctx->stream));
+    // totals of filterFrequentKmers (vertex_index.cpp:175-184) over ALL keys; entry / key counts of every rank
+    DevBuf<unsigned long long> dTotals(4), dStats(4);
+    FG_CUDA(cudaMemsetAsync(dTotals.p, 0, 32, ctx->stream));
     FG_CUDA(cudaMemsetAsync(dStats.p, 0, 32, ctx->stream));
-    capacityTotalsKernel<<<gridFor(S), 256, 0, ctx->stream>>>(cap.p, S, (uint32_t)minCov, dTotals.p);
-    checkLaunch(ctx, "capacityTotalsKernel");
+    if (S) {
+        capacityTotalsKernel<<<gridFor(S), 256, 0, ctx->stream>>>(starts.p, S, (uint32_t)minCov, dTotals.p);
+        checkLaunch(ctx, "capacityTotalsKernel");
+    }
+    std::vector<uint64_t> eOff(2, 0), sOffs(2, 0);
+    eOff[1] = E * sizeof(uint2); sOffs[1] = S * 8ULL;
+    if (multi) {
+        allReduceSumU64(ctx, dTotals.p, 2);
+        allGatherSizes(ctx, E * sizeof(uint2), eOff);
+        allGatherSizes(ctx, S * 8ULL, sOffs);
+    }
+    const int me = multi ? ctx->rank : 0;
+    const uint64_t Etotal = eOff.back() / sizeof(uint2), Stotal = sOffs.back() / 8, entryBase = eOff[me] / sizeof(uint2);
     unsigned long long hTotals[2];
     FG_CUDA(cudaMemcpyAsync(hTotals, dTotals.p, 16, cudaMemcpyDeviceToHost, ctx->stream));
     FG_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -895,19 +1200,41 @@ static void buildFromSelection(fg_ctx* ctx, DevBuf<uint32_t>& rcBits, int minCov
     volatile float meanFrequency = (float)totalKmers / (uniqueKmers + 1);
     volatile float repF = repeatRate * meanFrequency;
     const size_t repetitiveFrequency = (size_t)repF;
-    ctx->dUKeys.alloc(S); ctx->dUPayload.alloc(S);
-    classifyKernel<KeyT><<<gridFor(S), 256, 0, ctx->stream>>>(ukeys, cap.p, first.p, S, repetitiveFrequency, ctx->minimizerMode,
-                                                              ctx->countTable, ctx->dUKeys.p, ctx->dUPayload.p, dStats.p);
-    checkLaunch(ctx, "classifyKernel");
+    DevBuf<uint64_t> locKeys(std::max<uint64_t>(S, 1)), locPayload(std::max<uint64_t>(S, 1));
+    if (S) {
+        classifyKernel<KeyT><<<gridFor(S), 256, 0, ctx->stream>>>(ukeys, starts.p, S, repetitiveFrequency, entryBase, ctx->minimizerMode,
+                                                                  ctx->countTable, locKeys.p, locPayload.p, dStats.p);
+        checkLaunch(ctx, "classifyKernel");
+    }
+    if (multi) allReduceSumU64(ctx, dStats.p, 4);
     unsigned long long hStats[4];
     FG_CUDA(cudaMemcpyAsync(hStats, dStats.p, 32, cudaMemcpyDeviceToHost, ctx->stream));
     FG_CUDA(cudaStreamSynchronize(ctx->stream));
-    if (hStats[3]) throw Error(FG_ERR_TOO_FREQ, "k-mer is too frequent");
-    ctx->indexTable = makeTable(ctx, ctx->dIndexSlots, S);
-    insertIndexKernel<<<gridFor(S), 256, 0, ctx->stream>>>(ctx->dUKeys.p, ctx->dUPayload.p, S, ctx->indexTable);
-    checkLaunch(ctx, "insertIndexKernel");
+    if (hStats[3]) throw Error(FG_ERR_TOO_FREQ, "k-mer is too frequent");   // (all ranks see the reduced flag: they throw together)
+    // entries in their final (key, global position) order; replicated on every rank
+    ctx->dEntries.alloc(std::max<uint64_t>(Etotal, 1));
+    ctx->dUKeys.alloc(std::max<uint64_t>(Stotal, 1)); ctx->dUPayload.alloc(std::max<uint64_t>(Stotal, 1));
+    if (!multi) {
+        if (E) { unpackEntriesKernel<<<gridFor(E), 256, 0, ctx->stream>>>(dbV.Current(), E, ctx->dEntries.p); checkLaunch(ctx, "unpackEntriesKernel"); }
+        if (S) {
+            FG_CUDA(cudaMemcpyAsync(ctx->dUKeys.p, locKeys.p, S * 8ULL, cudaMemcpyDeviceToDevice, ctx->stream));
+            FG_CUDA(cudaMemcpyAsync(ctx->dUPayload.p, locPayload.p, S * 8ULL, cudaMemcpyDeviceToDevice, ctx->stream));
+        }
+    } else {
+        uint2* locEntries = reinterpret_cast<uint2*>(dbV.Alternate());   // the other value buffer is free now
+        if (E) { unpackEntriesKernel<<<gridFor(E), 256, 0, ctx->stream>>>(dbV.Current(), E, locEntries); checkLaunch(ctx, "unpackEntriesKernel"); }
+        allGatherVInto(ctx, locEntries, eOff, ctx->dEntries.p);
+        allGatherVInto(ctx, locKeys.p, sOffs, ctx->dUKeys.p);
+        allGatherVInto(ctx, locPayload.p, sOffs, ctx->dUPayload.p);
+    }
+    ctx->indexTable = makeTable(ctx, ctx->dIndexSlots, Stotal);
+    if (Stotal) {
+        insertIndexKernel<<<gridFor(Stotal, 256, 16), 256, 0, ctx->stream>>>(ctx->dUKeys.p, ctx->dUPayload.p, Stotal, ctx->indexTable);
+        checkLaunch(ctx, "insertIndexKernel");
+    }
     FG_CUDA(cudaStreamSynchronize(ctx->stream));
-    ctx->nUKeys = S;
+    ctx->nEntriesStored = Etotal;
+    ctx->nUKeys = Stotal;
     ctx->stats.n_repetitive = hStats[0];
     ctx->stats.n_entries = hStats[1];
     ctx->stats.n_keys = hStats[2];
@@ -935,14 +1262,15 @@ void buildIndexSolid(fg_ctx* ctx, int minFreq, float selectRate, int tandemFreq,
     tileRange(ctx, firstRead, nReadsShard, tLo, tHi);
     {
         PhaseTimer pt(ctx, "select");
-        DevBuf<uint32_t> freq(std::max<uint64_t>(ctx->nSlots, 1));
+        const uint64_t slotBase = ctx->hSlotOff[firstRead], shardSlots = ctx->hSlotOff[firstRead + nReadsShard] - slotBase;
+        DevBuf<uint32_t> freq(std::max<uint64_t>(shardSlots, 1));
         DevBuf<uint32_t> minFreqR(ctx->nReads);
         DevBuf<unsigned long long> dCand(1);
         FG_CUDA(cudaMemsetAsync(dCand.p, 0, 8, ctx->stream));
         FG_CUDA(cudaMemsetAsync(minFreqR.p, 0, ctx->nReads * 4ULL, ctx->stream));
         if (nReadsShard) {
             selectKernel<<<nReadsShard, 256, 0, ctx->stream>>>(ctx->dSeq.p, ctx->dWordOff.p, ctx->dLen.p, ctx->dSlotOff.p, k,
-                                                              ctx->countTable, selectRate, tandemFreq, firstRead, freq.p,
+                                                              ctx->countTable, selectRate, tandemFreq, firstRead, slotBase, freq.p,
                                                               rcBits.p, minFreqR.p, dCand.p);
             checkLaunch(ctx, "selectKernel");
         }
@@ -955,13 +1283,13 @@ void buildIndexSolid(fg_ctx* ctx, int minFreq, float selectRate, int tandemFreq,
             if ((uint64_t)ctx->nReads >= (1ULL << (64 - 2 * k))) throw Error(FG_ERR_ARG, "too many reads for the tandem-filter key");
             tandem = makeTable(ctx, tandemSlots, nCand);
             tandemCountKernel<<<(unsigned)(tHi - tLo), 256, 0, ctx->stream>>>(ctx->dSeq.p, ctx->dWordOff.p, ctx->dLen.p, ctx->dSlotOff.p,
-                                                                             ctx->dTiles.p + tLo, k, tandemFreq, freq.p, minFreqR.p, tandem);
+                                                                             ctx->dTiles.p + tLo, k, tandemFreq, slotBase, freq.p, minFreqR.p, tandem);
             checkLaunch(ctx, "tandemCountKernel");
         }
         if (tHi > tLo) {
             finalizeSelectionKernel<<<(unsigned)(tHi - tLo), 256, 0, ctx->stream>>>(ctx->dSeq.p, ctx->dWordOff.p, ctx->dLen.p,
                                                                                    ctx->dSlotOff.p, ctx->dTiles.p + tLo, k, minFreq,
-                                                                                   tandemFreq, freq.p, minFreqR.p, tandem, nCand != 0,
+                                                                                   tandemFreq, slotBase, freq.p, minFreqR.p, tandem, nCand != 0,
                                                                                    ctx->dSelBits.p);
             checkLaunch(ctx, "finalizeSelectionKernel");
         }

@@ -207,6 +207,11 @@ void commUniqueId(uint8_t* id);
 void commInit(fg_ctx* ctx, int nRanks, int rank, const uint8_t* id);
 void commDestroy(fg_ctx* ctx);
 void allGatherV(fg_ctx* ctx, const void* src, uint64_t bytes, DevBuf<char>& out, std::vector<uint64_t>& offs);
+void allGatherSizes(fg_ctx* ctx, uint64_t bytes, std::vector<uint64_t>& offs);
+void allGatherVInto(fg_ctx* ctx, const void* src, const std::vector<uint64_t>& offs, void* dst);
+void exchangeSizes(fg_ctx* ctx, const std::vector<uint64_t>& sendOffs, std::vector<uint64_t>& recvOffs);
+void allToAllVInto(fg_ctx* ctx, const void* sendBuf, const std::vector<uint64_t>& sendOffs, void* recvBuf, const std::vector<uint64_t>& recvOffs);
+void agreeOrThrow(fg_ctx* ctx, int code, const std::string& msg);
 void allReduceSumU64(fg_ctx* ctx, unsigned long long* buf, size_t count);
 void broadcastBytes(fg_ctx* ctx, void* buf, uint64_t bytes, int root);
 void groupStart();
@@ -215,6 +220,7 @@ inline bool sharded(const fg_ctx* ctx) { return ctx->nRanks > 1 && ctx->ncclComm
 
 void editDistances(fg_ctx* ctx, fg_overlap* dOv, const fg_overlap* hOv, uint32_t nOv, bool useHpc, bool querySet, float maxDivergence,
                    const float* dQueryMaxDivergence);
+double intPeak(fg_ctx* ctx);
 int debugEditDistance(fg_ctx* ctx, const uint8_t* a, int n, const uint8_t* b, int m, int rcA, int rcB);
 void debugWarpSort(fg_ctx* ctx, uint64_t* keys, uint32_t* vals, const uint64_t* segOffsets, uint32_t nSegs);
 

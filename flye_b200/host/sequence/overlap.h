@@ -8,13 +8,18 @@
 #include <cstdlib>
 #include <memory>
 #include <mutex>
+#include <sstream>
 #include <unordered_map>
+#include <unordered_set>
 #include <vector>
 
 #include "vertex_index.h"
 #include "sequence_container.h"
 #include "../common/config.h"
 #include "../common/logger.h"
+#if __has_include("../common/progress_bar.h")
+#include "../common/progress_bar.h"
+#endif
 
 #if __has_include("IntervalTree.h")
 #include "IntervalTree.h"

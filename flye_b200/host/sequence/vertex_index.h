@@ -2,8 +2,21 @@
 // Every method forwards to the C ABI (include/flye_b200.h); the k-mer counter, the per-read selection, the position
 // lists and the repetitive set all live in HBM.  Errors come back as std::runtime_error with the reference's texts.
 #pragma once
+#include <algorithm>
+#include <cassert>
 #include <cstdlib>
+#include <cstring>
+#include <iostream>
 #include <map>
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <unordered_set>
+// the reference's vertex_index.h / overlap.h pull libcuckoo in, and its callers (extender.h, chimera.h, main_*.cpp) rely on
+// getting it — and <thread>, <cassert> — through these headers
+#if __has_include(<cuckoohash_map.hh>)
+#include <cuckoohash_map.hh>
+#endif
 #include <memory>
 #include <stdexcept>
 #include <vector>
@@ -12,7 +25,7 @@
 #include "sequence_container.h"
 #include "../common/config.h"
 #include "../common/logger.h"
-#include "../../../include/flye_b200.h"
+#include "flye_b200.h"   // the C ABI: put <flye_b200 repo>/include on the include path (-I)
 
 typedef std::map<size_t, size_t> KmerDistribution;
 

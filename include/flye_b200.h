@@ -42,8 +42,9 @@ void*       fg_stream(const fg_ctx* ctx);
 /* number of kernels this library has launched on the context since creation (bench.py "gpu_launches") */
 uint64_t    fg_kernel_launches(const fg_ctx* ctx);
 /* device time (ms, CUDA events on the context's stream) of the phases of the most recent call;
- * names: "extract","count_sort","count_reduce","select","emit","index_sort","index_table",
- *        "gather","hit_sort","group","chain","edit","d2h"; calls[i] = how many times the phase ran (sub-batches);
+ * names e.g. "count_clear","count","count_hist","count_table","select","emit","index_sort","index_table","lookup","expand",
+ *        "hit_sort_radix","group","chain_dp","chain_fill","chain_walk","edit", host wall clocks as "host_*";
+ *        calls[i] = how many times the phase ran (sub-batches);
  *        returns number written */
 int         fg_last_timings(const fg_ctx* ctx, const char** names, float* ms, int* calls, int cap);
 
@@ -163,6 +164,10 @@ int fg_comm_unique_id(uint8_t id[FG_NCCL_ID_BYTES]);
 int fg_comm_init(fg_ctx* ctx, int n_ranks, int rank, const uint8_t id[FG_NCCL_ID_BYTES]);
 /* this rank's share of the forward reads for counting / index emission: [first_read, first_read+n) */
 int fg_comm_set_shard(fg_ctx* ctx, uint32_t first_read, uint32_t n_reads);
+
+/* ---- measurement hook: the chip's integer-issue ceiling, in Gop/s (one op = one IMAD / LOP3 / SHF thread
+ * instruction; all SMs, full occupancy, no memory traffic).  bench.py reports the integer-bound kernels against it. ---- */
+int fg_debug_int_peak(fg_ctx* ctx, double* gops);
 
 /* ---- test hook: the std::sort-exact warp introsort on caller data (segments sorted independently) ---- */
 int fg_debug_edit_distance(fg_ctx* ctx, const uint8_t* a, int n, const uint8_t* b, int m, int* distance);

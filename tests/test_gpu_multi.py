@@ -48,6 +48,19 @@ dist.destroy_process_group()
 '''
 
 
+def _index_diff(a, b):
+    """key-level summary of two index dumps (diagnostics of a failure)"""
+    da = {l.split(" ", 1)[0]: l for l in open(a).read().splitlines()[1:]}
+    db = {l.split(" ", 1)[0]: l for l in open(b).read().splitlines()[1:]}
+    only_a, only_b = sorted(set(da) - set(db)), sorted(set(db) - set(da))
+    changed = [k for k in da if k in db and da[k] != db[k]]
+    print("INDEXDIFF", a, b, "first entries differ?", open(a).readline(), open(b).readline())
+    out = {"keys_a": len(da), "keys_b": len(db), "only_a": len(only_a), "only_b": len(only_b), "changed": len(changed),
+            "ex_only_a": [da[k] for k in only_a[:3]], "ex_only_b": [db[k] for k in only_b[:3]], "ex_changed": [(da[k], db[k]) for k in changed[:3]]}
+    print("INDEXDIFF", json.dumps(out))
+    return out["keys_a"], out["keys_b"], out["changed"]
+
+
 def _n_gpus():
     try:
         import torch
@@ -74,7 +87,7 @@ def test_two_gpu_parity(built, engine, tmp_path, cfg, k, sim):
                         "--master-port", "29611", worker, reads, cfg_path, os.path.join(tmp, "two"), str(k)],
                        env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:]
-    for a, b in [("one.index", "two.index.rank0"), ("one.index", "two.index.rank1"), ("one.ovlp", "two.ovlp")] + \
-                ([("one.hist", "two.hist")] if cfg == "raw_reads.cfg" else []):
+    for a, b in ([("one.hist", "two.hist")] if cfg == "raw_reads.cfg" else []) + \
+                [("one.index", "two.index.rank0"), ("one.index", "two.index.rank1"), ("one.ovlp", "two.ovlp")]:
         n, sample = pu.diff_files(os.path.join(tmp, a), os.path.join(tmp, b))
-        assert n == 0, (a, b, sample[:3])
+        assert n == 0, (a, b, sample[:3], _index_diff(os.path.join(tmp, a), os.path.join(tmp, b)) if "index" in a else None)
