@@ -60,6 +60,7 @@ void installReads(fg_ctx* ctx, uint32_t n) {
     if (n) FG_CUDA(cudaMemcpyAsync(ctx->dLen.p, ctx->hLen.data(), n * 4ULL, cudaMemcpyHostToDevice, ctx->stream));
     FG_CUDA(cudaStreamSynchronize(ctx->stream));
     ctx->k = 0; ctx->counted = false; ctx->indexed = false;
+    ctx->hitBudget = 0;
     ctx->dSlotOff.release();
     ctx->shardSet = false;
 }
@@ -107,6 +108,7 @@ void fg_ctx_destroy(fg_ctx* ctx) {
     cudaDeviceSynchronize();
     try { fg::commDestroy(ctx); } catch (...) {}
     fg::currentArena() = &ctx->arena;
+    ctx->lanes.clear();   // (their buffers are all released by now; frees the lanes' cached blocks and streams)
     delete ctx;
     fg::currentArena() = nullptr;
     cudaStreamDestroy(s);
@@ -114,7 +116,7 @@ void fg_ctx_destroy(fg_ctx* ctx) {
 
 const char* fg_last_error(const fg_ctx* ctx) { return ctx ? ctx->lastError.c_str() : "null context"; }
 void* fg_stream(const fg_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
-uint64_t fg_kernel_launches(const fg_ctx* ctx) { return ctx ? ctx->launches : 0; }
+uint64_t fg_kernel_launches(const fg_ctx* ctx) { return ctx ? ctx->launches.load() : 0; }
 
 int fg_last_timings(const fg_ctx* ctx, const char** names, float* ms, int* calls, int cap) {
     if (!ctx) return 0;
@@ -249,7 +251,7 @@ int fg_build_index_minimizers(fg_ctx* ctx, int k, int minCov, int window, float 
 int fg_index_clear(fg_ctx* ctx) {
     return guarded(ctx, [&] {
         ctx->dEntries.release(); ctx->dIndexSlots.release(); ctx->dUKeys.release(); ctx->dUPayload.release();
-        ctx->dCountSlots.release(); ctx->dSelBits.release();
+        ctx->dCountSlots.release(); ctx->dDense.release(); ctx->counts = fg::CountView{}; ctx->dSelBits.release();
         ctx->indexed = false; ctx->counted = false;
     });
 }

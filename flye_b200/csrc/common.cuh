@@ -113,6 +113,13 @@ struct DevBuf {
         if (count) p = (T*)owner->alloc(count * sizeof(T));
     }
     void ensure(size_t count) { if (count > n) alloc(count + count / 8); }
+    // hands the block over under another element type (no copy, no allocation)
+    template <class U> DevBuf<U> reinterpretAs() {
+        DevBuf<U> o;
+        o.p = reinterpret_cast<U*>(p); o.n = n * sizeof(T) / sizeof(U); o.owner = owner;
+        p = nullptr; n = 0;
+        return o;
+    }
     void release() { if (p && owner) owner->release(p); p = nullptr; n = 0; }
     size_t bytes() const { return n * sizeof(T); }
 };
@@ -234,6 +241,38 @@ __device__ inline void tableAddOne(const Table& t, uint64_t key) {
         if (prev == EMPTY_KEY || prev == key) { atomicAdd((unsigned long long*)&t.slots[i].y, 1ULL); return; }
         i = (i + 1) & t.mask;
     }
+}
+
+// k-mer counts as the selection / classification kernels see them: on one GPU the dense counter array of the counting
+// phase itself (one 32-byte sector per lookup, no hashing, no probing); with the classes spread over several ranks the
+// replicated table of the k-mers with count >= 2 (absent == 1).  Dense index: see count_index.cu.
+struct CountView {
+    const uint32_t* dense = nullptr;
+    Table table;
+    int k = 0;
+};
+__host__ __device__ inline uint64_t denseIndexOfPair(uint64_t f, uint64_t r, int k) {   // f, r: a k-mer and its reverse complement
+    if (k & 1) {   // base j of f sits at bits 2(k-1-j), 2(k-1-j)+1; the middle one (j = (k-1)/2) at bits k-1, k
+        const uint64_t rep = ((f >> k) & 1ULL) ? r : f;
+        return (rep & ((1ULL << k) - 1ULL)) | ((rep >> (k + 1)) << k);
+    }
+    return f < r ? f : r;
+}
+__host__ __device__ inline uint64_t revCompKmer(uint64_t f, int k) { return (~rev2(f << (64 - 2 * k))) & kmerMask(k); }   // kmer.h:39-52
+// count of the class of the k-mer given as its 2k-bit window `v` (base p in the lowest bits) ...
+__device__ inline uint32_t countOfWindow(const CountView& c, uint64_t v) {
+    const uint64_t f = fwdFromWindow(v, c.k), r = (~v) & kmerMask(c.k);
+    if (c.dense) return c.dense[denseIndexOfPair(f, r, c.k)];
+    uint64_t payload;
+    return tableFind(c.table, f < r ? f : r, payload) ? (uint32_t)payload : 1u;
+}
+// ... or as a k-mer in the reference's representation (either orientation); a k-mer that never occurs reports 1 from the table
+// form and 0 from the dense form — callers only ask for k-mers that occur
+__device__ inline uint32_t countOfKmer(const CountView& c, uint64_t kmer) {
+    const uint64_t r = revCompKmer(kmer, c.k);
+    if (c.dense) return c.dense[denseIndexOfPair(kmer, r, c.k)];
+    uint64_t payload;
+    return tableFind(c.table, kmer < r ? kmer : r, payload) ? (uint32_t)payload : 1u;
 }
 
 // index payload: [63:24] first entry, [23:0] size; all-ones size = repetitive k-mer

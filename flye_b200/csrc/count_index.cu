@@ -96,18 +96,13 @@ struct DenseMap {
 static inline uint64_t denseSpace(int k) { return (k & 1) ? (1ULL << (2 * k - 1)) : (1ULL << (2 * k)); }
 
 __host__ __device__ inline uint64_t denseIndexFromWindow(uint64_t v, int k) {
-    const uint64_t f = fwdFromWindow(v, k), r = (~v) & kmerMask(k);
-    if (k & 1) {   // base j of f sits at bits 2(k-1-j), 2(k-1-j)+1; the middle one (j = (k-1)/2) at bits k-1, k
-        const uint64_t rep = ((f >> k) & 1ULL) ? r : f;
-        return (rep & ((1ULL << k) - 1ULL)) | ((rep >> (k + 1)) << k);
-    }
-    return f < r ? f : r;
+    return denseIndexOfPair(fwdFromWindow(v, k), (~v) & kmerMask(k), k);
 }
 // canonical k-mer (Kmer::standardForm, kmer.h:54-63) of a dense index
 __host__ __device__ inline uint64_t canonFromDenseIndex(uint64_t idx, int k) {
     if (!(k & 1)) return idx;
     const uint64_t rep = (idx & ((1ULL << k) - 1ULL)) | ((idx >> k) << (k + 1));
-    const uint64_t rc = (~rev2(rep << (64 - 2 * k))) & kmerMask(k);   // kmer.h:39-52
+    const uint64_t rc = revCompKmer(rep, k);
     return rep < rc ? rep : rc;
 }
 __device__ __forceinline__ void ownerOf(const DenseMap& m, uint64_t idx, uint32_t& owner, uint64_t& local) {
@@ -305,14 +300,18 @@ void countKmers(fg_ctx* ctx, int k) {
     const size_t nTiles = tHi - tLo;
     ctx->hist.clear();
     ctx->nDistinct = 0;
-    ctx->dCountSlots.release();
+    ctx->dCountSlots.release(); ctx->dDense.release();
+    ctx->counts = CountView{};
+    // counting invalidates the index (setKmerSize): give its memory back before the counters are allocated
+    ctx->dEntries.release(); ctx->dIndexSlots.release(); ctx->dUKeys.release(); ctx->dUPayload.release();
 
     DenseMap m; m.k = k; m.nOwners = multi ? (uint32_t)ctx->nRanks : 1u; m.owner = multi ? (uint32_t)ctx->rank : 0u;
     m.ownerShift = 0xffffffffu;
     for (uint32_t s = 0; s < 31; ++s) if ((1u << s) == m.nOwners) m.ownerShift = s;
     // counters of this rank: slots of the classes i with i % nOwners == owner, padded to whole 16-byte groups
     const uint64_t nLocal = ((denseSpace(k) + m.nOwners - 1) / m.nOwners + 3) & ~3ULL;
-    DevBuf<uint32_t> dense(nLocal);
+    DevBuf<uint32_t>& dense = ctx->dDense;
+    dense.alloc(nLocal);
     {
         PhaseTimer pt(ctx, "count_clear");
         FG_CUDA(cudaMemsetAsync(dense.p, 0, nLocal * 4ULL, ctx->stream));
@@ -382,37 +381,49 @@ void countKmers(fg_ctx* ctx, int k) {
         FG_CUDA(cudaStreamSynchronize(ctx->stream));
     }
     agreeOrThrow(ctx, nOv > ovCap ? FG_ERR_INTERNAL : 0, "k-mer histogram overflow list exhausted");
-    // this rank's k-mers with count >= 2
-    DevBuf<uint64_t> solidKeys(std::max<uint64_t>(hSolid, 1));
-    DevBuf<uint32_t> solidCounts(std::max<uint64_t>(hSolid, 1));
-    {
-        PhaseTimer pt(ctx, "count_emit");
-        if (hSolid) {
-            denseEmitKernel<<<gridFor(nLocal / 4, 256, 16), 256, 0, ctx->stream>>>(reinterpret_cast<const uint4*>(dense.p), nLocal / 4, m, solidKeys.p,
-                                                                                  solidCounts.p, dSolid.p + 1);
-            checkLaunch(ctx, "denseEmitKernel");
-        }
-    }
-    dense.release();
-    uint64_t nSolidAll = hSolid;
-    DevBuf<uint64_t> allKeys; DevBuf<uint32_t> allCounts;
     std::vector<uint32_t> ov(nOv);
     if (nOv) FG_CUDA(cudaMemcpyAsync(ov.data(), dOv.p, nOv * 4ULL, cudaMemcpyDeviceToHost, ctx->stream));
-    if (multi) {
-        PhaseTimer pt(ctx, "count_merge");
-        allReduceSumU64(ctx, dHist.p, HIST_GLOBAL_BINS);
-        std::vector<uint64_t> offs;
-        allGatherSizes(ctx, hSolid * 8ULL, offs);
-        nSolidAll = offs.back() / 8;
-        allKeys.alloc(std::max<uint64_t>(nSolidAll, 1)); allCounts.alloc(std::max<uint64_t>(nSolidAll, 1));
-        allGatherVInto(ctx, solidKeys.p, offs, allKeys.p);
-        for (auto& o : offs) o /= 2;
-        allGatherVInto(ctx, solidCounts.p, offs, allCounts.p);
-        // counts beyond the histogram's dense bins are rare: gather the few values
-        DevBuf<char> ovAll; std::vector<uint64_t> ovOff;
-        allGatherV(ctx, dOv.p, nOv * 4ULL, ovAll, ovOff);
-        ov.resize(ovOff.back() / 4);
-        if (!ov.empty()) FG_CUDA(cudaMemcpyAsync(ov.data(), ovAll.p, ov.size() * 4ULL, cudaMemcpyDeviceToHost, ctx->stream));
+    if (!multi) {
+        // one GPU: the counter array IS the count structure of the selection (no table, no second pass over the counters)
+        ctx->counts.dense = dense.p; ctx->counts.k = k;
+    } else {
+        // this rank's k-mers with count >= 2, all-gathered into the replicated table
+        DevBuf<uint64_t> solidKeys(std::max<uint64_t>(hSolid, 1));
+        DevBuf<uint32_t> solidCounts(std::max<uint64_t>(hSolid, 1));
+        {
+            PhaseTimer pt(ctx, "count_emit");
+            if (hSolid) {
+                denseEmitKernel<<<gridFor(nLocal / 4, 256, 16), 256, 0, ctx->stream>>>(reinterpret_cast<const uint4*>(dense.p), nLocal / 4, m, solidKeys.p,
+                                                                                      solidCounts.p, dSolid.p + 1);
+                checkLaunch(ctx, "denseEmitKernel");
+            }
+        }
+        dense.release();
+        uint64_t nSolidAll = 0;
+        DevBuf<uint64_t> allKeys; DevBuf<uint32_t> allCounts;
+        {
+            PhaseTimer pt(ctx, "count_merge");
+            allReduceSumU64(ctx, dHist.p, HIST_GLOBAL_BINS);
+            std::vector<uint64_t> offs;
+            allGatherSizes(ctx, hSolid * 8ULL, offs);
+            nSolidAll = offs.back() / 8;
+            allKeys.alloc(std::max<uint64_t>(nSolidAll, 1)); allCounts.alloc(std::max<uint64_t>(nSolidAll, 1));
+            allGatherVInto(ctx, solidKeys.p, offs, allKeys.p);
+            for (auto& o : offs) o /= 2;
+            allGatherVInto(ctx, solidCounts.p, offs, allCounts.p);
+            // counts beyond the histogram's dense bins are rare: gather the few values
+            DevBuf<char> ovAll; std::vector<uint64_t> ovOff;
+            allGatherV(ctx, dOv.p, nOv * 4ULL, ovAll, ovOff);
+            ov.resize(ovOff.back() / 4);
+            if (!ov.empty()) FG_CUDA(cudaMemcpyAsync(ov.data(), ovAll.p, ov.size() * 4ULL, cudaMemcpyDeviceToHost, ctx->stream));
+            FG_CUDA(cudaStreamSynchronize(ctx->stream));
+        }
+        PhaseTimer pt(ctx, "count_table");
+        ctx->counts.table = makeTable(ctx, ctx->dCountSlots, nSolidAll); ctx->counts.k = k;
+        if (nSolidAll) {
+            buildCountTableKernel<<<gridFor(nSolidAll, 256, 16), 256, 0, ctx->stream>>>(allKeys.p, allCounts.p, nSolidAll, ctx->counts.table);
+            checkLaunch(ctx, "buildCountTableKernel");
+        }
         FG_CUDA(cudaStreamSynchronize(ctx->stream));
     }
     std::vector<unsigned long long> hHist(HIST_GLOBAL_BINS);
@@ -421,33 +432,24 @@ void countKmers(fg_ctx* ctx, int k) {
     ctx->nDistinct = hHist[0];
     for (int f = 1; f < HIST_GLOBAL_BINS; ++f) if (hHist[f]) ctx->hist[f] = hHist[f];
     for (uint32_t c : ov) ctx->hist[c] += 1;
-    {
-        PhaseTimer pt(ctx, "count_table");
-        ctx->countTable = makeTable(ctx, ctx->dCountSlots, nSolidAll);
-        if (nSolidAll) {
-            buildCountTableKernel<<<gridFor(nSolidAll, 256, 16), 256, 0, ctx->stream>>>(multi ? allKeys.p : solidKeys.p, multi ? allCounts.p : solidCounts.p,
-                                                                                       nSolidAll, ctx->countTable);
-            checkLaunch(ctx, "buildCountTableKernel");
-        }
-        FG_CUDA(cudaStreamSynchronize(ctx->stream));
-    }
     ctx->counted = true;
 }
 
 // KmerCounter::getFreq for a batch (tests)
-__global__ void kmerFreqKernel(const uint64_t* kmers, uint32_t n, Table table, uint32_t* out) {
+__global__ void kmerFreqKernel(const uint64_t* kmers, uint32_t n, CountView counts, uint32_t* out) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    uint64_t payload;
-    out[i] = tableFind(table, kmers[i], payload) ? (uint32_t)payload : 0xFFFFFFFFu;   // ~0: count is 0 or 1
+    const uint32_t c = countOfKmer(counts, kmers[i] & kmerMask(counts.k));
+    out[i] = (counts.dense ? c >= 2u : c != 1u) ? c : 0xFFFFFFFFu;   // ~0: count is 0 or 1
 }
 
 void kmerFreqQuery(fg_ctx* ctx, const uint64_t* kmers, uint32_t n, uint32_t* out) {
     if (!ctx->counted) throw Error(FG_ERR_ARG, "fg_count_kmers has not run");
+    if (!ctx->counts.dense && !ctx->dCountSlots.p) throw Error(FG_ERR_ARG, "the k-mer counters were released when the index was built");
     if (!n) return;
     DevBuf<uint64_t> dK(n); DevBuf<uint32_t> dO(n);
     FG_CUDA(cudaMemcpyAsync(dK.p, kmers, n * 8ULL, cudaMemcpyHostToDevice, ctx->stream));
-    kmerFreqKernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(dK.p, n, ctx->countTable, dO.p);
+    kmerFreqKernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(dK.p, n, ctx->counts, dO.p);
     checkLaunch(ctx, "kmerFreqKernel");
     FG_CUDA(cudaMemcpyAsync(out, dO.p, n * 4ULL, cudaMemcpyDeviceToHost, ctx->stream));
     FG_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -462,7 +464,7 @@ void kmerFreqQuery(fg_ctx* ctx, const uint64_t* kmers, uint32_t n, uint32_t* out
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) selectKernel(const uint64_t* __restrict__ seq, const uint64_t* __restrict__ wordOff,
                                                     const uint32_t* __restrict__ len, const uint64_t* __restrict__ slotOff,
-                                                    int k, Table countTable, float selectRate, int tandemFreq,
+                                                    int k, CountView counts, float selectRate, int tandemFreq,
                                                     uint32_t readFirst, uint64_t slotBase, uint32_t* __restrict__ freqShard, uint32_t* __restrict__ rcBits,
                                                     uint32_t* __restrict__ minFreqOut, unsigned long long* __restrict__ nTandemCand) {
     const uint32_t r = readFirst + blockIdx.x;
@@ -483,9 +485,9 @@ __global__ void __launch_bounds__(256) selectKernel(const uint64_t* __restrict__
         const uint32_t p = p0 + lane;
         bool rc = false;
         if (p < n) {
-            uint64_t key = canonFromWindow(windowAt(words, p, k), k, rc);
-            uint64_t payload;
-            const uint32_t f = tableFind(countTable, key, payload) ? (uint32_t)payload : 1u;
+            const uint64_t v = windowAt(words, p, k);
+            canonFromWindow(v, k, rc);
+            const uint32_t f = countOfWindow(counts, v);
             freq[base + p] = f;
             myMax = max(myMax, f);
         }
@@ -911,7 +913,7 @@ __global__ void __launch_bounds__(256) capacityTotalsKernel(const uint64_t* __re
 // entryBase: position of this rank's first entry in the replicated entry array (multi-GPU), 0 otherwise
 template <class KeyT>
 __global__ void __launch_bounds__(256) classifyKernel(const KeyT* __restrict__ ukeys, const uint64_t* __restrict__ starts, uint64_t n,
-                                                      uint64_t repFreq, uint64_t entryBase, bool minimizerMode, Table countTable,
+                                                      uint64_t repFreq, uint64_t entryBase, bool minimizerMode, CountView counts,
                                                       uint64_t* __restrict__ keys64, uint64_t* __restrict__ payload,
                                                       unsigned long long* __restrict__ stats) {
     unsigned long long nRep = 0, nEnt = 0, nKeys = 0;
@@ -925,9 +927,7 @@ __global__ void __launch_bounds__(256) classifyKernel(const KeyT* __restrict__ u
             if (c + 1 > MEM_CHUNK) atomicExch(&stats[3], 1ULL);   // allocateIndexMemory, vertex_index.cpp:372-375
             bool valid = true;
             if (!minimizerMode) {
-                uint64_t f = 1;
-                tableFind(countTable, key, f);
-                valid = f <= repFreq;
+                valid = (uint64_t)countOfKmer(counts, key) <= repFreq;
             }
             if (valid) { pl = ((entryBase + starts[i]) << IDX_SIZE_BITS) | c; nEnt += c; }
             else pl = ~0ULL;   // key stays in the reference's table with size 0: behaves as absent
@@ -1175,6 +1175,8 @@ static void buildFromSelection(fg_ctx* ctx, DevBuf<uint32_t>& rcBits, int minCov
         }
         FG_CUDA(cudaMemcpyAsync(starts.p + S, &E, 8, cudaMemcpyHostToDevice, ctx->stream));
     }
+    // the sorted keys have done their job (the distinct ones are in `ukeys`): give the buffer back before the outputs are allocated
+    (sortedKeys == keysA.p ? keysA : keysB).release();
     // totals of filterFrequentKmers (vertex_index.cpp:175-184) over ALL keys; entry / key counts of every rank
     DevBuf<unsigned long long> dTotals(4), dStats(4);
     FG_CUDA(cudaMemsetAsync(dTotals.p, 0, 32, ctx->stream));
@@ -1200,32 +1202,40 @@ static void buildFromSelection(fg_ctx* ctx, DevBuf<uint32_t>& rcBits, int minCov
     volatile float meanFrequency = (float)totalKmers / (uniqueKmers + 1);
     volatile float repF = repeatRate * meanFrequency;
     const size_t repetitiveFrequency = (size_t)repF;
-    DevBuf<uint64_t> locKeys(std::max<uint64_t>(S, 1)), locPayload(std::max<uint64_t>(S, 1));
+    // keys + payloads: written in place on one GPU, gathered from the owners otherwise
+    ctx->dUKeys.alloc(std::max<uint64_t>(Stotal, 1)); ctx->dUPayload.alloc(std::max<uint64_t>(Stotal, 1));
+    DevBuf<uint64_t> locKeys, locPayload;
+    if (multi) { locKeys.alloc(std::max<uint64_t>(S, 1)); locPayload.alloc(std::max<uint64_t>(S, 1)); }
     if (S) {
         classifyKernel<KeyT><<<gridFor(S), 256, 0, ctx->stream>>>(ukeys, starts.p, S, repetitiveFrequency, entryBase, ctx->minimizerMode,
-                                                                  ctx->countTable, locKeys.p, locPayload.p, dStats.p);
+                                                                  ctx->counts, multi ? locKeys.p : ctx->dUKeys.p, multi ? locPayload.p : ctx->dUPayload.p, dStats.p);
         checkLaunch(ctx, "classifyKernel");
     }
     if (multi) allReduceSumU64(ctx, dStats.p, 4);
     unsigned long long hStats[4];
     FG_CUDA(cudaMemcpyAsync(hStats, dStats.p, 32, cudaMemcpyDeviceToHost, ctx->stream));
     FG_CUDA(cudaStreamSynchronize(ctx->stream));
+    // the k-mer counters were last needed by the classification: large ones (k >= 16: 17 / 34 GB) go back before the table is built
+    if (ctx->dDense.bytes() > (4ULL << 30)) { ctx->dDense.release(); ctx->counts = CountView{}; }
+    (ukeys == keysA.p ? keysA : keysB).release();
+    starts.release();
     if (hStats[3]) throw Error(FG_ERR_TOO_FREQ, "k-mer is too frequent");   // (all ranks see the reduced flag: they throw together)
     // entries in their final (key, global position) order; replicated on every rank
-    ctx->dEntries.alloc(std::max<uint64_t>(Etotal, 1));
-    ctx->dUKeys.alloc(std::max<uint64_t>(Stotal, 1)); ctx->dUPayload.alloc(std::max<uint64_t>(Stotal, 1));
-    if (!multi) {
-        if (E) { unpackEntriesKernel<<<gridFor(E), 256, 0, ctx->stream>>>(dbV.Current(), E, ctx->dEntries.p); checkLaunch(ctx, "unpackEntriesKernel"); }
-        if (S) {
-            FG_CUDA(cudaMemcpyAsync(ctx->dUKeys.p, locKeys.p, S * 8ULL, cudaMemcpyDeviceToDevice, ctx->stream));
-            FG_CUDA(cudaMemcpyAsync(ctx->dUPayload.p, locPayload.p, S * 8ULL, cudaMemcpyDeviceToDevice, ctx->stream));
+    {
+        DevBuf<uint64_t>& curV = dbV.Current() == valsA.p ? valsA : valsB;
+        DevBuf<uint64_t>& altV = dbV.Current() == valsA.p ? valsB : valsA;
+        uint2* locEntries = reinterpret_cast<uint2*>(altV.p);   // the other value buffer is free: the unpacked entries go there
+        if (E) { unpackEntriesKernel<<<gridFor(E), 256, 0, ctx->stream>>>(curV.p, E, locEntries); checkLaunch(ctx, "unpackEntriesKernel"); }
+        if (!multi) {
+            ctx->dEntries = altV.reinterpretAs<uint2>();   // ... and that buffer becomes the index's entry array
+        } else {
+            ctx->dEntries.alloc(std::max<uint64_t>(Etotal, 1));
+            allGatherVInto(ctx, locEntries, eOff, ctx->dEntries.p);
+            allGatherVInto(ctx, locKeys.p, sOffs, ctx->dUKeys.p);
+            allGatherVInto(ctx, locPayload.p, sOffs, ctx->dUPayload.p);
+            altV.release();
         }
-    } else {
-        uint2* locEntries = reinterpret_cast<uint2*>(dbV.Alternate());   // the other value buffer is free now
-        if (E) { unpackEntriesKernel<<<gridFor(E), 256, 0, ctx->stream>>>(dbV.Current(), E, locEntries); checkLaunch(ctx, "unpackEntriesKernel"); }
-        allGatherVInto(ctx, locEntries, eOff, ctx->dEntries.p);
-        allGatherVInto(ctx, locKeys.p, sOffs, ctx->dUKeys.p);
-        allGatherVInto(ctx, locPayload.p, sOffs, ctx->dUPayload.p);
+        curV.release();
     }
     ctx->indexTable = makeTable(ctx, ctx->dIndexSlots, Stotal);
     if (Stotal) {
@@ -1270,7 +1280,7 @@ void buildIndexSolid(fg_ctx* ctx, int minFreq, float selectRate, int tandemFreq,
         FG_CUDA(cudaMemsetAsync(minFreqR.p, 0, ctx->nReads * 4ULL, ctx->stream));
         if (nReadsShard) {
             selectKernel<<<nReadsShard, 256, 0, ctx->stream>>>(ctx->dSeq.p, ctx->dWordOff.p, ctx->dLen.p, ctx->dSlotOff.p, k,
-                                                              ctx->countTable, selectRate, tandemFreq, firstRead, slotBase, freq.p,
+                                                              ctx->counts, selectRate, tandemFreq, firstRead, slotBase, freq.p,
                                                               rcBits.p, minFreqR.p, dCand.p);
             checkLaunch(ctx, "selectKernel");
         }

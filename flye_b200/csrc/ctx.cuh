@@ -2,10 +2,12 @@
 #pragma once
 #include "common.cuh"
 #include <algorithm>
+#include <atomic>
 #include <condition_variable>
 #include <functional>
 #include <map>
 #include <memory>
+#include <shared_mutex>
 #include <thread>
 #include <utility>
 
@@ -55,13 +57,29 @@ public:
 };
 }  // namespace fg
 
+namespace fg {
+// One execution lane of fg_overlaps_batch: the sub-batches of a call are processed by a few host worker threads, each with its
+// own CUDA stream, its own caching arena (a block is only ever reused by work on the stream that released it) and its own
+// phase-timing list.  While one lane waits for a count to come back from the device or copies results to the host, the
+// kernels of the other lanes keep the SMs busy.  Outside fg_overlaps_batch there is one implicit lane: the context itself.
+struct Lane {
+    Arena arena;
+    cudaStream_t stream = nullptr;
+    std::vector<std::pair<std::string, float>> timings;
+    std::vector<int> timingCalls;
+    ~Lane() { if (stream) cudaStreamDestroy(stream); }
+};
+inline Lane*& currentLane() { static thread_local Lane* l = nullptr; return l; }
+}  // namespace fg
+
 struct fg_ctx {
     fg::Arena arena;                      // first member: destroyed last, after every DevBuf below
     int device = 0;
     cudaStream_t stream = nullptr;
     mutable std::mutex mtx;
     std::string lastError;
-    uint64_t launches = 0;
+    std::atomic<uint64_t> launches{0};
+    std::vector<std::unique_ptr<fg::Lane>> lanes;   // worker lanes of fg_overlaps_batch (streams and arenas are kept across calls)
 
     // ---- reads (forward strands, 2-bit packed, every read word aligned) ----
     uint32_t nReads = 0;
@@ -104,8 +122,9 @@ struct fg_ctx {
     bool counted = false;
     uint64_t nDistinct = 0;
     std::map<uint64_t, uint64_t> hist;    // freq -> #distinct canonical k-mers
-    fg::DevBuf<ulonglong2> dCountSlots;   // table: canonical k-mer -> count, only counts >= 2 (absent = 1)
-    fg::Table countTable;
+    fg::DevBuf<ulonglong2> dCountSlots;   // multi-GPU: replicated table canonical k-mer -> count, only counts >= 2 (absent = 1)
+    fg::DevBuf<uint32_t> dDense;          // one GPU: the dense counter array itself (count_index.cu), kept until the index is built
+    fg::CountView counts;
 
     // ---- index ----
     bool indexed = false;
@@ -128,8 +147,12 @@ struct fg_ctx {
     // ---- overlap results (host, library owned) ----
     std::vector<uint64_t> resOffsets;
     std::vector<int32_t> resAln;
+    std::mutex alnMutex;
     fg::PinnedBuf<fg_overlap> pinnedOut;  // D2H staging, kept across calls
+    std::shared_mutex pinnedMutex;        // lanes copy into / work on their slice under a shared lock; growing the buffer takes it exclusively
     fg::HostPool hostPool;
+    std::mutex hostPoolMutex;             // one parallelFor at a time (the lanes share the pool)
+    uint64_t hitBudget = 0;               // k-mer hits per sub-batch and lane, derived once from the free device memory
     // results after the divergence / maxOverlaps filter (when it removed something); two buffers: fg_overlaps_refilter
     // compacts from the one that holds the last result into the other
     std::unique_ptr<fg_overlap[]> resCompact[2];
@@ -147,24 +170,34 @@ struct fg_ctx {
 
 namespace fg {
 
-// RAII phase timer on the context stream (CUDA events; the phase list is what fg_last_timings reports)
+// the stream of the calling thread: its lane's inside a worker of fg_overlaps_batch, the context's otherwise
+inline cudaStream_t streamOf(const fg_ctx* ctx) { Lane* l = currentLane(); return l ? l->stream : ctx->stream; }
+
+inline void addTiming(fg_ctx* ctx, const char* name, float ms, int calls = 1) {
+    Lane* l = currentLane();
+    auto& t = l ? l->timings : ctx->timings;
+    auto& c = l ? l->timingCalls : ctx->timingCalls;
+    for (size_t i = 0; i < t.size(); ++i)
+        if (t[i].first == name) { t[i].second += ms; c[i] += calls; return; }
+    t.emplace_back(name, ms); c.push_back(calls);
+}
+
+// RAII phase timer on the calling thread's stream (CUDA events; the phase list is what fg_last_timings reports; with several
+// lanes at work the phases of different lanes overlap in time, so their sum can exceed the wall clock of the call)
 struct PhaseTimer {
     fg_ctx* ctx;
     const char* name;
     cudaEvent_t a{}, b{};
     PhaseTimer(fg_ctx* c, const char* n) : ctx(c), name(n) {
         cudaEventCreate(&a); cudaEventCreate(&b);
-        cudaEventRecord(a, ctx->stream);
+        cudaEventRecord(a, streamOf(ctx));
     }
     ~PhaseTimer() {
-        cudaEventRecord(b, ctx->stream);
+        cudaEventRecord(b, streamOf(ctx));
         cudaEventSynchronize(b);
         float ms = 0;
         cudaEventElapsedTime(&ms, a, b);
-        bool found = false;
-        for (size_t i = 0; i < ctx->timings.size(); ++i)
-            if (ctx->timings[i].first == name) { ctx->timings[i].second += ms; ++ctx->timingCalls[i]; found = true; }
-        if (!found) { ctx->timings.emplace_back(name, ms); ctx->timingCalls.push_back(1); }
+        addTiming(ctx, name, ms);
         cudaEventDestroy(a); cudaEventDestroy(b);
     }
 };
@@ -173,12 +206,7 @@ struct PhaseTimer {
 struct HostTimer {
     fg_ctx* ctx; const char* name; std::chrono::steady_clock::time_point t0;
     HostTimer(fg_ctx* c, const char* n) : ctx(c), name(n), t0(std::chrono::steady_clock::now()) {}
-    ~HostTimer() {
-        float ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
-        for (size_t i = 0; i < ctx->timings.size(); ++i)
-            if (ctx->timings[i].first == name) { ctx->timings[i].second += ms; ++ctx->timingCalls[i]; return; }
-        ctx->timings.emplace_back(name, ms); ctx->timingCalls.push_back(1);
-    }
+    ~HostTimer() { addTiming(ctx, name, std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count()); }
 };
 
 inline void checkLaunch(fg_ctx* ctx, const char* what) {
@@ -220,6 +248,7 @@ inline bool sharded(const fg_ctx* ctx) { return ctx->nRanks > 1 && ctx->ncclComm
 
 void editDistances(fg_ctx* ctx, fg_overlap* dOv, const fg_overlap* hOv, uint32_t nOv, bool useHpc, bool querySet, float maxDivergence,
                    const float* dQueryMaxDivergence);
+void prepareEditDistances(fg_ctx* ctx, bool useHpc, bool querySet);   // builds the HPC copies editDistances reads (main thread, before the lanes start)
 double intPeak(fg_ctx* ctx);
 int debugEditDistance(fg_ctx* ctx, const uint8_t* a, int n, const uint8_t* b, int m, int rcA, int rcB);
 void debugWarpSort(fg_ctx* ctx, uint64_t* keys, uint32_t* vals, const uint64_t* segOffsets, uint32_t nSegs);

@@ -280,13 +280,23 @@ __global__ void __launch_bounds__(128) wfaKernel(fg_overlap* __restrict__ ov, ui
 static void buildHpc(fg_ctx* ctx, fg_ctx::HpcCache& c, const uint64_t* seq, const uint64_t* wordOff, const uint32_t* len, uint32_t nReads,
                      uint64_t nWords) {
     c.seq.alloc(nWords + 4); c.mask.alloc(nWords + 4); c.prefix.alloc(nWords + 4);
-    FG_CUDA(cudaMemsetAsync(c.seq.p, 0, (nWords + 4) * 8, ctx->stream));
+    FG_CUDA(cudaMemsetAsync(c.seq.p, 0, (nWords + 4) * 8, streamOf(ctx)));
     if (nReads) {
-        hpcReadsKernel<<<(nReads + 3) / 4, 128, 0, ctx->stream>>>(seq, wordOff, len, nReads, reinterpret_cast<unsigned long long*>(c.seq.p), c.mask.p,
+        hpcReadsKernel<<<(nReads + 3) / 4, 128, 0, streamOf(ctx)>>>(seq, wordOff, len, nReads, reinterpret_cast<unsigned long long*>(c.seq.p), c.mask.p,
                                                                   c.prefix.p);
         checkLaunch(ctx, "hpcReadsKernel");
     }
     c.valid = true;
+}
+
+// the homopolymer-compressed copies are built once per uploaded sequence set, on the context's own stream, before the lanes of
+// fg_overlaps_batch start (they only read them)
+void prepareEditDistances(fg_ctx* ctx, bool useHpc, bool querySet) {
+    if (!useHpc) return;
+    if (!ctx->hpcReads.valid) buildHpc(ctx, ctx->hpcReads, ctx->dSeq.p, ctx->dWordOff.p, ctx->dLen.p, ctx->nReads, ctx->hWordOff.back());
+    if (querySet && !ctx->hpcQueries.valid)
+        buildHpc(ctx, ctx->hpcQueries, ctx->dQsSeq.p, ctx->dQsWordOff.p, ctx->dQsLen.p, ctx->nQsReads, ctx->nQsWords);
+    FG_CUDA(cudaStreamSynchronize(streamOf(ctx)));
 }
 
 // device overlaps (already gathered) -> edit_distance / aln_len filled in.  querySet: the "cur" side refers to the second
@@ -301,23 +311,21 @@ void editDistances(fg_ctx* ctx, fg_overlap* dOv, const fg_overlap* hOv, uint32_t
     HpcSet cur = ext;
     if (querySet) cur = HpcSet{ctx->dQsSeq.p, nullptr, nullptr, nullptr, ctx->dQsWordOff.p, ctx->dQsLen.p};
     if (useHpc) {
-        if (!ctx->hpcReads.valid) buildHpc(ctx, ctx->hpcReads, ctx->dSeq.p, ctx->dWordOff.p, ctx->dLen.p, ctx->nReads, ctx->hWordOff.back());
+        if (!ctx->hpcReads.valid || (querySet && !ctx->hpcQueries.valid)) throw Error(FG_ERR_INTERNAL, "prepareEditDistances has not run");
         ext.hpc = ctx->hpcReads.seq.p; ext.mask = ctx->hpcReads.mask.p; ext.prefix = ctx->hpcReads.prefix.p;
         if (querySet) {
-            if (!ctx->hpcQueries.valid)
-                buildHpc(ctx, ctx->hpcQueries, ctx->dQsSeq.p, ctx->dQsWordOff.p, ctx->dQsLen.p, ctx->nQsReads, ctx->nQsWords);
             cur.hpc = ctx->hpcQueries.seq.p; cur.mask = ctx->hpcQueries.mask.p; cur.prefix = ctx->hpcQueries.prefix.p;
         } else { cur.hpc = ext.hpc; cur.mask = ext.mask; cur.prefix = ext.prefix; }
     }
     DevBuf<uint32_t> nextJob(1);
-    FG_CUDA(cudaMemsetAsync(nextJob.p, 0, 4, ctx->stream));
+    FG_CUDA(cudaMemsetAsync(nextJob.p, 0, 4, streamOf(ctx)));
     const int blocks = 148 * 10, warps = blocks * 4;   // 48 registers / thread: 40 resident warps per SM
     const uint64_t stride = 2ULL * maxLen + 8;
     DevBuf<int> wf((uint64_t)warps * 2 * stride);   // only touched by overlaps with more than WF_DMAX edits
-    wfaKernel<<<blocks, 128, 0, ctx->stream>>>(dOv, nOv, cur, ext, useHpc, wf.p, stride, nextJob.p, maxDivergence, dQueryMaxDivergence,
+    wfaKernel<<<blocks, 128, 0, streamOf(ctx)>>>(dOv, nOv, cur, ext, useHpc, wf.p, stride, nextJob.p, maxDivergence, dQueryMaxDivergence,
                                                getenv("FG_WFA_BAND") == nullptr || atoi(getenv("FG_WFA_BAND")) != 0);
     checkLaunch(ctx, "wfaKernel");
-    FG_CUDA(cudaStreamSynchronize(ctx->stream));
+    FG_CUDA(cudaStreamSynchronize(streamOf(ctx)));
 }
 
 // test hook: exact edit distance of two base strings (values 0..3), optionally seen as reverse complements
@@ -341,15 +349,15 @@ int debugEditDistance(fg_ctx* ctx, const uint8_t* a, int n, const uint8_t* b, in
     DevBuf<uint64_t> dA(pa.size()), dB(pb.size());
     const uint64_t stride = (uint64_t)n + m + 8;
     DevBuf<int> wf(2 * stride), dOut(1);
-    FG_CUDA(cudaMemcpyAsync(dA.p, pa.data(), pa.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
-    FG_CUDA(cudaMemcpyAsync(dB.p, pb.data(), pb.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+    FG_CUDA(cudaMemcpyAsync(dA.p, pa.data(), pa.size() * 8, cudaMemcpyHostToDevice, streamOf(ctx)));
+    FG_CUDA(cudaMemcpyAsync(dB.p, pb.data(), pb.size() * 8, cudaMemcpyHostToDevice, streamOf(ctx)));
     // test hook of the test hook: FG_DEBUG_ED_LIMIT bounds the distance like the divergence threshold does in wfaKernel
     const char* lim = getenv("FG_DEBUG_ED_LIMIT");
-    debugEdKernel<<<1, 32, 0, ctx->stream>>>(dA.p, n, rcA != 0, dB.p, m, rcB != 0, wf.p, stride, dOut.p, lim ? atoi(lim) : 0x7fffffff);
+    debugEdKernel<<<1, 32, 0, streamOf(ctx)>>>(dA.p, n, rcA != 0, dB.p, m, rcB != 0, wf.p, stride, dOut.p, lim ? atoi(lim) : 0x7fffffff);
     checkLaunch(ctx, "debugEdKernel");
     int d = -1;
-    FG_CUDA(cudaMemcpyAsync(&d, dOut.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
-    FG_CUDA(cudaStreamSynchronize(ctx->stream));
+    FG_CUDA(cudaMemcpyAsync(&d, dOut.p, 4, cudaMemcpyDeviceToHost, streamOf(ctx)));
+    FG_CUDA(cudaStreamSynchronize(streamOf(ctx)));
     return d;
 }
 

@@ -1515,24 +1515,23 @@ static void sortSegments(fg_ctx* ctx, Elem* arr, const Seg* dSegs, uint32_t* dCo
                          uint32_t* hugeScratchL = nullptr, uint32_t* hugeScratchR = nullptr, uint32_t* hugeCounters = nullptr) {
     if (!outArr) outArr = arr;
     const bool useHuge = hugeScratchL && hugeScratchR && hugeCounters && envInt("FG_SORT_HUGE", 1, 0, 1);
-    static bool attrSet = false;
     const int variant = cfg.variant;
     const uint32_t smallN = (uint32_t)cfg.smallN;
     const int smemBytes = 4 * ((int)smallN * ((int)sizeof(Elem) + (variant ? 4 : 0)) + (variant > 1 ? ((int)smallN / 32 + 2) * 4 : 0));
     auto smallKernel = variant == 0 ? sortSmallKernel<0> : variant == 1 ? sortSmallKernel<1> : variant == 2 ? sortSmallKernel<2> : sortSmallKernel<3>;
-    if (!attrSet) {
+    static std::once_flag attrSet[64];   // function attributes are per device
+    std::call_once(attrSet[ctx->device & 63], [&] {
         const int maxSmem = 4 * (SORT_SMALL_MAX * ((int)sizeof(Elem) + 4) + (SORT_SMALL_MAX / 32 + 2) * 4);
         FG_CUDA(cudaFuncSetAttribute(sortSmallKernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
         FG_CUDA(cudaFuncSetAttribute(sortSmallKernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
         FG_CUDA(cudaFuncSetAttribute(sortSmallKernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
         FG_CUDA(cudaFuncSetAttribute(sortSmallKernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxSmem));
-        attrSet = true;
-    }
+    });
     const int blocksPerSm = std::max(1, std::min(8, (int)((220 * 1024) / (smemBytes + 1024))));
     if (!maxSegs) return;
     {
         PhaseTimer pt(ctx, topName);
-        sortSeedKernel<<<(maxSegs + 255) / 256, 256, 0, ctx->stream>>>(dSegs, dCounters, ws.bigA.p, dCounters + 3, ws.capBig, ws.small.p,
+        sortSeedKernel<<<(maxSegs + 255) / 256, 256, 0, streamOf(ctx)>>>(dSegs, dCounters, ws.bigA.p, dCounters + 3, ws.capBig, ws.small.p,
                                                                       dCounters + 1, ws.capSmall, smallN, tieP,
                                                                       useHuge ? ws.hugeA.p : nullptr, hugeCounters, ws.capHuge, SORT_HUGE_MIN);
         checkLaunch(ctx, "sortSeedKernel");
@@ -1541,12 +1540,12 @@ static void sortSegments(fg_ctx* ctx, Elem* arr, const Seg* dSegs, uint32_t* dCo
             uint32_t* nHin = hugeCounters; uint32_t* nHout = hugeCounters + 1;
             for (int level = 0; level < 200; ++level) {
                 uint32_t hCnt = 0;
-                FG_CUDA(cudaMemcpyAsync(&hCnt, nHin, 4, cudaMemcpyDeviceToHost, ctx->stream));
-                FG_CUDA(cudaStreamSynchronize(ctx->stream));
+                FG_CUDA(cudaMemcpyAsync(&hCnt, nHin, 4, cudaMemcpyDeviceToHost, streamOf(ctx)));
+                FG_CUDA(cudaStreamSynchronize(streamOf(ctx)));
                 if (hCnt > ws.capHuge) throw Error(FG_ERR_INTERNAL, "sort task list overflow");
                 if (!hCnt) break;
-                FG_CUDA(cudaMemsetAsync(nHout, 0, 4, ctx->stream));
-                sortHugeKernel<<<hCnt, HUGE_WARPS * 32, 0, ctx->stream>>>(arr, hin, nHin, ws.capHuge, hout, nHout, SORT_HUGE_MIN, ws.bigA.p, dCounters + 3,
+                FG_CUDA(cudaMemsetAsync(nHout, 0, 4, streamOf(ctx)));
+                sortHugeKernel<<<hCnt, HUGE_WARPS * 32, 0, streamOf(ctx)>>>(arr, hin, nHin, ws.capHuge, hout, nHout, SORT_HUGE_MIN, ws.bigA.p, dCounters + 3,
                                                                          ws.capBig, ws.small.p, dCounters + 1, ws.capSmall, smallN, outArr, tieP,
                                                                          hugeScratchL, hugeScratchR);
                 checkLaunch(ctx, "sortHugeKernel");
@@ -1558,8 +1557,8 @@ static void sortSegments(fg_ctx* ctx, Elem* arr, const Seg* dSegs, uint32_t* dCo
         uint64_t firstElems = 0;
         for (int level = 0; level < 200; ++level) {
             uint32_t hIn[3] = {0, 0, 0};   // count, (other list), elements
-            FG_CUDA(cudaMemcpyAsync(hIn, nIn, 12, cudaMemcpyDeviceToHost, ctx->stream));
-            FG_CUDA(cudaStreamSynchronize(ctx->stream));
+            FG_CUDA(cudaMemcpyAsync(hIn, nIn, 12, cudaMemcpyDeviceToHost, streamOf(ctx)));
+            FG_CUDA(cudaStreamSynchronize(streamOf(ctx)));
             const uint32_t cnt = hIn[0], elems = hIn[2];
             if (cnt > ws.capBig) throw Error(FG_ERR_INTERNAL, "sort task list overflow");
             if (!cnt) break;
@@ -1569,20 +1568,20 @@ static void sortSegments(fg_ctx* ctx, Elem* arr, const Seg* dSegs, uint32_t* dCo
             // ... and a handful of short ranges from the start (the few pairs whose matches are not presorted): the same
             const bool fewShort = level == 0 && cnt <= 8192 && (uint64_t)elems <= (uint64_t)cnt * 4096;
             if (fewShort || (level >= 4 && ((uint64_t)elems * 16 < firstElems || level >= 48))) {
-                sortTailKernel<<<(cnt + 3) / 4, 128, 0, ctx->stream>>>(arr, in, nIn, ws.capBig, ws.small.p, dCounters + 1, ws.capSmall, smallN, outArr, tieP);
+                sortTailKernel<<<(cnt + 3) / 4, 128, 0, streamOf(ctx)>>>(arr, in, nIn, ws.capBig, ws.small.p, dCounters + 1, ws.capSmall, smallN, outArr, tieP);
                 checkLaunch(ctx, "sortTailKernel");
                 break;
             }
-            FG_CUDA(cudaMemsetAsync(nOut, 0, 4, ctx->stream));
-            FG_CUDA(cudaMemsetAsync(nOut + 2, 0, 4, ctx->stream));
-            sortLevelKernel<<<(cnt + 3) / 4, 128, 0, ctx->stream>>>(arr, in, nIn, ws.capBig, out, nOut, ws.small.p, dCounters + 1, ws.capSmall, smallN, outArr, tieP);
+            FG_CUDA(cudaMemsetAsync(nOut, 0, 4, streamOf(ctx)));
+            FG_CUDA(cudaMemsetAsync(nOut + 2, 0, 4, streamOf(ctx)));
+            sortLevelKernel<<<(cnt + 3) / 4, 128, 0, streamOf(ctx)>>>(arr, in, nIn, ws.capBig, out, nOut, ws.small.p, dCounters + 1, ws.capSmall, smallN, outArr, tieP);
             checkLaunch(ctx, "sortLevelKernel");
             std::swap(in, out); std::swap(nIn, nOut);
         }
     }
     {
         PhaseTimer pt(ctx, smallName);
-        smallKernel<<<148 * blocksPerSm, 128, smemBytes, ctx->stream>>>(arr, ws.small.p, dCounters + 1, ws.capSmall, dCounters + 2, smallN, outArr);
+        smallKernel<<<148 * blocksPerSm, 128, smemBytes, streamOf(ctx)>>>(arr, ws.small.p, dCounters + 1, ws.capSmall, dCounters + 2, smallN, outArr);
         checkLaunch(ctx, "sortSmallKernel");
     }
 }
@@ -1602,14 +1601,14 @@ void debugWarpSort(fg_ctx* ctx, uint64_t* keys, uint32_t* vals, const uint64_t* 
     SortWorkspace ws; ws.ensure(n, nSegs);
     const uint32_t cap = ws.capSmall;
     uint32_t hc[16] = {nSegs, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-    FG_CUDA(cudaMemcpyAsync(d.p, h.data(), n * sizeof(Elem), cudaMemcpyHostToDevice, ctx->stream));
-    FG_CUDA(cudaMemcpyAsync(dSegs.p, hs.data(), nSegs * sizeof(Seg), cudaMemcpyHostToDevice, ctx->stream));
-    FG_CUDA(cudaMemcpyAsync(counters.p, hc, sizeof hc, cudaMemcpyHostToDevice, ctx->stream));
+    FG_CUDA(cudaMemcpyAsync(d.p, h.data(), n * sizeof(Elem), cudaMemcpyHostToDevice, streamOf(ctx)));
+    FG_CUDA(cudaMemcpyAsync(dSegs.p, hs.data(), nSegs * sizeof(Seg), cudaMemcpyHostToDevice, streamOf(ctx)));
+    FG_CUDA(cudaMemcpyAsync(counters.p, hc, sizeof hc, cudaMemcpyHostToDevice, streamOf(ctx)));
     sortSegments(ctx, d.p, dSegs.p, counters.p, nSegs, ws, "dbg_sort_top", "dbg_sort_small", envInt("FG_DEBUG_SORT_PAIRS", 0, 0, 1) ? sortCfgPairs() : sortCfgHits(),
                  nullptr, nullptr, hugeScratch.p, hugeScratch.p + n, counters.p + 8);
-    FG_CUDA(cudaMemcpyAsync(h.data(), d.p, n * sizeof(Elem), cudaMemcpyDeviceToHost, ctx->stream));
-    FG_CUDA(cudaMemcpyAsync(hc, counters.p, sizeof hc, cudaMemcpyDeviceToHost, ctx->stream));
-    FG_CUDA(cudaStreamSynchronize(ctx->stream));
+    FG_CUDA(cudaMemcpyAsync(h.data(), d.p, n * sizeof(Elem), cudaMemcpyDeviceToHost, streamOf(ctx)));
+    FG_CUDA(cudaMemcpyAsync(hc, counters.p, sizeof hc, cudaMemcpyDeviceToHost, streamOf(ctx)));
+    FG_CUDA(cudaStreamSynchronize(streamOf(ctx)));
     if (hc[1] > cap) throw Error(FG_ERR_INTERNAL, "sort task list overflow");
     for (uint64_t i = 0; i < n; ++i) { keys[i] = h[i].key; vals[i] = h[i].val; }
 }
@@ -1620,14 +1619,14 @@ void debugWarpSort(fg_ctx* ctx, uint64_t* keys, uint32_t* vals, const uint64_t* 
 template <class InIt, class OutT>
 static void exclusiveScanToPlus1(fg_ctx* ctx, InIt in, OutT* outPlus1Base, uint64_t n) {
     // outPlus1Base[0] = 0, outPlus1Base[i+1] = sum(in[0..i])
-    FG_CUDA(cudaMemsetAsync(outPlus1Base, 0, sizeof(OutT), ctx->stream));
+    FG_CUDA(cudaMemsetAsync(outPlus1Base, 0, sizeof(OutT), streamOf(ctx)));
     if (!n) return;
     size_t tmpBytes = 0;
-    FG_CUDA(cub::DeviceScan::InclusiveSum(nullptr, tmpBytes, in, outPlus1Base + 1, (int)n, ctx->stream));
+    FG_CUDA(cub::DeviceScan::InclusiveSum(nullptr, tmpBytes, in, outPlus1Base + 1, (int)n, streamOf(ctx)));
     DevBuf<char> tmp(tmpBytes);
-    FG_CUDA(cub::DeviceScan::InclusiveSum(tmp.p, tmpBytes, in, outPlus1Base + 1, (int)n, ctx->stream));
+    FG_CUDA(cub::DeviceScan::InclusiveSum(tmp.p, tmpBytes, in, outPlus1Base + 1, (int)n, streamOf(ctx)));
     ++ctx->launches;
-    FG_CUDA(cudaStreamSynchronize(ctx->stream));
+    FG_CUDA(cudaStreamSynchronize(streamOf(ctx)));
 }
 
 template <class FlagT>
@@ -1637,27 +1636,49 @@ static uint32_t selectFlagged(fg_ctx* ctx, const FlagT* flags, uint32_t n, DevBu
     DevBuf<uint32_t> dNum(1);
     cub::CountingInputIterator<uint32_t> it(0);
     size_t tmpBytes = 0;
-    FG_CUDA(cub::DeviceSelect::Flagged(nullptr, tmpBytes, it, flags, out.p, dNum.p, (int)n, ctx->stream));
+    FG_CUDA(cub::DeviceSelect::Flagged(nullptr, tmpBytes, it, flags, out.p, dNum.p, (int)n, streamOf(ctx)));
     DevBuf<char> tmp(tmpBytes);
-    FG_CUDA(cub::DeviceSelect::Flagged(tmp.p, tmpBytes, it, flags, out.p, dNum.p, (int)n, ctx->stream));
+    FG_CUDA(cub::DeviceSelect::Flagged(tmp.p, tmpBytes, it, flags, out.p, dNum.p, (int)n, streamOf(ctx)));
     ++ctx->launches;
     uint32_t h = 0;
-    FG_CUDA(cudaMemcpyAsync(&h, dNum.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
-    FG_CUDA(cudaStreamSynchronize(ctx->stream));
+    FG_CUDA(cudaMemcpyAsync(&h, dNum.p, 4, cudaMemcpyDeviceToHost, streamOf(ctx)));
+    FG_CUDA(cudaStreamSynchronize(streamOf(ctx)));
     return h;
 }
 
 // one chunk of queries (< 2^30 k-mer slots): lookup, expansion and the per-sub-batch pipeline; the raw overlap records are
 // appended to the context's pinned buffer with `reserved` = position of the query in the whole call
+// Work counters of a call, added up by the lanes.
+struct BatchTotals { std::atomic<uint64_t> pairs{0}, dpPairs{0}, cells{0}, tied{0}, presorted{0}; };
+// Sub-batches hand their raw records to the shared pinned buffer IN ORDER (sub-batch i directly behind sub-batch i-1), so the
+// buffer holds the records in query order whatever lane produced them: a sub-batch learns its offset when its predecessor has.
+struct OrderedCommit {
+    std::mutex m; std::condition_variable cv;
+    size_t next = 0;       // index of the sub-batch whose turn it is
+    size_t nRaw = 0;       // records reserved so far
+    bool failed = false;
+    size_t reserve(size_t index, size_t n) {
+        std::unique_lock<std::mutex> lk(m);
+        cv.wait(lk, [&] { return next == index || failed; });
+        if (failed) throw Error(FG_ERR_INTERNAL, "another lane failed");
+        const size_t off = nRaw;
+        nRaw += n; next = index + 1;
+        lk.unlock(); cv.notify_all();
+        return off;
+    }
+    void fail() { { std::lock_guard<std::mutex> lk(m); failed = true; } cv.notify_all(); }
+};
+
+static void recordDivergences(fg_ctx* ctx, fg_overlap* recs, size_t n, const fg_overlap_params& prm);
+
 static void overlapsChunk(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, uint32_t qOffset, const fg_overlap_params& prm, const OvParams& P,
-                          size_t& nRaw, uint64_t& totHits, uint64_t& totPairs, uint64_t& totDpPairs, uint64_t& totCells, uint64_t& totTied, uint64_t& totPresorted, const float* dQueryMaxDiv) {
+                          OrderedCommit& commit, size_t& subBase, uint64_t& totHits, BatchTotals& tot, const float* dQueryMaxDiv) {
     const int k = ctx->k;
     // where the query sequences live: the indexed reads themselves, or the second set of fg_queries_upload
     const std::vector<uint32_t>& qHLen = P.sameSet ? ctx->hLen : ctx->hQsLen;
     const uint64_t* qSeq = P.sameSet ? ctx->dSeq.p : ctx->dQsSeq.p;
     const uint64_t* qWordOff = P.sameSet ? ctx->dWordOff.p : ctx->dQsWordOff.p;
     const uint32_t* qLen = P.sameSet ? ctx->dLen.p : ctx->dQsLen.p;
-    PinnedBuf<fg_overlap>& pinned = ctx->pinnedOut;
     uint32_t maxSeqLen = 1;   // bounds curPos and extPos (packed hits of the segmented sort)
     for (uint32_t L : ctx->hLen) maxSeqLen = std::max(maxSeqLen, L);
     for (uint32_t L : qHLen) maxSeqLen = std::max(maxSeqLen, L);
@@ -1683,17 +1704,17 @@ static void overlapsChunk(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, ui
     DevBuf<uint2> dQTiles(std::max<size_t>(hQTiles.size(), 1));
     DevBuf<uint32_t> hitCnt(nQSlots + 1), filtBits(nQSlots / 32 + 2), filtPrefix(nQSlots / 32 + 2);
     DevBuf<uint64_t> slotInfo(nQSlots + 1), hitOff(nQSlots + 2), dQHitOff(nQ + 1);
-    if (nQ) FG_CUDA(cudaMemcpyAsync(dQIds.p, queryIds, nQ * 4ULL, cudaMemcpyHostToDevice, ctx->stream));
-    FG_CUDA(cudaMemcpyAsync(dQSlotOff.p, hQSlotOff.data(), (nQ + 1) * 8ULL, cudaMemcpyHostToDevice, ctx->stream));
-    if (!hQTiles.empty()) FG_CUDA(cudaMemcpyAsync(dQTiles.p, hQTiles.data(), hQTiles.size() * sizeof(uint2), cudaMemcpyHostToDevice, ctx->stream));
-    FG_CUDA(cudaMemsetAsync(filtBits.p, 0, filtBits.bytes(), ctx->stream));
-    FG_CUDA(cudaMemsetAsync(hitCnt.p, 0, hitCnt.bytes(), ctx->stream));
+    if (nQ) FG_CUDA(cudaMemcpyAsync(dQIds.p, queryIds, nQ * 4ULL, cudaMemcpyHostToDevice, streamOf(ctx)));
+    FG_CUDA(cudaMemcpyAsync(dQSlotOff.p, hQSlotOff.data(), (nQ + 1) * 8ULL, cudaMemcpyHostToDevice, streamOf(ctx)));
+    if (!hQTiles.empty()) FG_CUDA(cudaMemcpyAsync(dQTiles.p, hQTiles.data(), hQTiles.size() * sizeof(uint2), cudaMemcpyHostToDevice, streamOf(ctx)));
+    FG_CUDA(cudaMemsetAsync(filtBits.p, 0, filtBits.bytes(), streamOf(ctx)));
+    FG_CUDA(cudaMemsetAsync(hitCnt.p, 0, hitCnt.bytes(), streamOf(ctx)));
 
     if (!hQTiles.empty()) {
         if (nQSlots >= (1ULL << 31)) throw Error(FG_ERR_ARG, "query batch too large (>= 2^31 k-mer slots); split the call");
         {
             PhaseTimer pt(ctx, "lookup");
-            queryLookupKernel<<<(unsigned)hQTiles.size(), 256, 0, ctx->stream>>>(qSeq, qWordOff, qLen, ctx->dSlotOff.p,
+            queryLookupKernel<<<(unsigned)hQTiles.size(), 256, 0, streamOf(ctx)>>>(qSeq, qWordOff, qLen, ctx->dSlotOff.p,
                                                                                 ctx->dSelBits.p, dQIds.p, dQSlotOff.p, dQTiles.p, k,
                                                                                 P.sameSet, ctx->indexTable, hitCnt.p, slotInfo.p, filtBits.p);
             checkLaunch(ctx, "queryLookupKernel");
@@ -1701,49 +1722,64 @@ static void overlapsChunk(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, ui
             exclusiveScanToPlus1(ctx, it64, hitOff.p, nQSlots);
             cub::TransformInputIterator<uint32_t, PopcU32, const uint32_t*> itPop(filtBits.p, PopcU32());
             exclusiveScanToPlus1(ctx, itPop, filtPrefix.p, nQSlots / 32);
-            gatherQueryHitOffKernel<<<(nQ + 256) / 256, 256, 0, ctx->stream>>>(hitOff.p, dQSlotOff.p, nQ, dQHitOff.p);
+            gatherQueryHitOffKernel<<<(nQ + 256) / 256, 256, 0, streamOf(ctx)>>>(hitOff.p, dQSlotOff.p, nQ, dQHitOff.p);
             checkLaunch(ctx, "gatherQueryHitOffKernel");
-            FG_CUDA(cudaMemcpyAsync(hQHitOff.data(), dQHitOff.p, (nQ + 1) * 8ULL, cudaMemcpyDeviceToHost, ctx->stream));
-            FG_CUDA(cudaStreamSynchronize(ctx->stream));
+            FG_CUDA(cudaMemcpyAsync(hQHitOff.data(), dQHitOff.p, (nQ + 1) * 8ULL, cudaMemcpyDeviceToHost, streamOf(ctx)));
+            FG_CUDA(cudaStreamSynchronize(streamOf(ctx)));
         }
     }
     totHits += hQHitOff[nQ];
 
-    // sub-batches of consecutive queries with a bounded number of hits
-    // k-mer hits per sub-batch: as many as comfortably fit (about 80 B of workspace per hit).  Fewer, larger
-    // sub-batches keep the first partition levels of the hit sort busy: they run one warp per read.
-    uint64_t budget = 768ULL << 20;
-    {
+    // sub-batches of consecutive queries with a bounded number of hits, processed by a few lanes (host thread + stream +
+    // arena each).  Hits per sub-batch: as many as comfortably fit (about 80 B of workspace per hit and lane), but at least
+    // two sub-batches per lane when the call is big enough, so that the lanes can overlap each other's host work (counts
+    // coming back from the device, result copies, the per-record epilogue).
+    const int nLanes = envInt("FG_LANES", 2, 1, 8);
+    if (!ctx->hitBudget) {
+        uint64_t budget = 768ULL << 20;
         size_t freeB = 0, totalB = 0;
         if (cudaMemGetInfo(&freeB, &totalB) == cudaSuccess) {
-            const uint64_t usable = (uint64_t)((freeB + ctx->arena.cachedFreeBytes()) * 0.55);
+            uint64_t cached = ctx->arena.cachedFreeBytes();
+            for (auto& l : ctx->lanes) cached += l->arena.cachedFreeBytes();
+            const uint64_t usable = (uint64_t)((freeB + cached) * 0.55);
             budget = std::max<uint64_t>(64ULL << 20, std::min<uint64_t>(budget, usable / 80));
         }
+        ctx->hitBudget = budget;
     }
+    uint64_t budget = std::max<uint64_t>(32ULL << 20, ctx->hitBudget / nLanes);
+    budget = std::min<uint64_t>(budget, std::max<uint64_t>(48ULL << 20, hQHitOff[nQ] / ((uint64_t)envInt("FG_SUBS_PER_LANE", 2, 1, 16) * nLanes) + 1));
     if (const char* e = getenv("FG_HIT_BUDGET")) budget = std::max<uint64_t>(1024, strtoull(e, nullptr, 10));
-    DevBuf<Elem> hits, ord; DevBuf<int32_t> score, back; DevBuf<Cand> cands; DevBuf<uint8_t> flags;
-    DevBuf<uint32_t> gStart, candIds, pairIds;
-    SortWorkspace ws; DevBuf<Seg> segsQ;
-    DevBuf<uint32_t> counters(32);
-    DevBuf<uint8_t> qTie;
-
-    hostPrep.reset();
-    HostTimer hostSub(ctx, "host_subbatches");   // wall clock of all sub-batches: minus the device phases = host gaps
-    uint32_t qa = 0;
-    while (qa < nQ) {
+    struct Sub { uint32_t qa, qb; };
+    std::vector<Sub> subs;
+    for (uint32_t qa = 0; qa < nQ;) {
         uint32_t qb = qa + 1;
         while (qb < nQ && hQHitOff[qb + 1] - hQHitOff[qa] <= budget) ++qb;
+        subs.push_back({qa, qb});
+        qa = qb;
+    }
+    hostPrep.reset();
+    HostTimer hostSub(ctx, "host_subbatches");   // wall clock of all sub-batches
+    PinnedBuf<fg_overlap>& pinned = ctx->pinnedOut;
+
+    auto runSub = [&](const uint32_t qa, const uint32_t qb, const size_t subIndex) {
+        bool committed = false;
+        auto commitNone = [&] { if (!committed) { commit.reserve(subIndex, 0); committed = true; } };
         const uint64_t hitBase = hQHitOff[qa], M = hQHitOff[qb] - hitBase;
         const uint32_t nq = qb - qa;
+        if (M == 0) { commitNone(); return; }
+        DevBuf<Elem> hits, ord; DevBuf<int32_t> score, back; DevBuf<Cand> cands; DevBuf<uint8_t> flags;
+        DevBuf<uint32_t> gStart, candIds, pairIds;
+        SortWorkspace ws; DevBuf<Seg> segsQ;
+        DevBuf<uint32_t> counters(32);
+        DevBuf<uint8_t> qTie;
         if (M >= (1ULL << 31)) throw Error(FG_ERR_ARG, "a single query produced >= 2^31 k-mer hits");
-        if (M == 0) { qa = qb; continue; }
         hits.ensure(M); ord.ensure(M); score.ensure(M + 1); back.ensure(M); cands.ensure(M); flags.ensure(M + 1);
         ws.ensure(M, nq);
         const uint32_t taskCap = ws.capSmall;
         segsQ.ensure(nq);
         uint32_t hCounters[32] = {0};
         hCounters[0] = nq;
-        FG_CUDA(cudaMemcpyAsync(counters.p, hCounters, sizeof hCounters, cudaMemcpyHostToDevice, ctx->stream));
+        FG_CUDA(cudaMemcpyAsync(counters.p, hCounters, sizeof hCounters, cudaMemcpyHostToDevice, streamOf(ctx)));
         const size_t tA = qTileFirst[qa], tB = qTileFirst[qb];
         // tie-free fast path: stable radix sort by (query, extId).  FG_HIT_RADIX: 1 (default) = segmented sort of packed 64-bit
         // hits, one CTA per query; 2 = the library's radix sort on 32-bit (query, extId) keys; 0 = exact emulation for every query
@@ -1758,7 +1794,7 @@ static void overlapsChunk(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, ui
         uint8_t* tieFlags = reinterpret_cast<uint8_t*>(back.p);   // M + 1 bytes of the back-pointer array (free until the chaining)
         if (radixPath) {
             qTie.ensure(nq);
-            FG_CUDA(cudaMemsetAsync(qTie.p, 0, nq, ctx->stream));
+            FG_CUDA(cudaMemsetAsync(qTie.p, 0, nq, streamOf(ctx)));
         }
         if (radixMode == 1) {
             // scratch: ord (16 B per hit, free until the DP) holds the two 8-byte ping-pong buffers
@@ -1766,14 +1802,14 @@ static void overlapsChunk(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, ui
             unsigned long long* bufB = bufA + M;
             {
                 PhaseTimer pt(ctx, "expand");
-                expandKernel<2><<<(unsigned)(tB - tA), 256, 0, ctx->stream>>>(ctx->dLen.p, qLen, ctx->dEntries.p, dQIds.p, dQSlotOff.p, dQTiles.p + tA, k,
+                expandKernel<2><<<(unsigned)(tB - tA), 256, 0, streamOf(ctx)>>>(ctx->dLen.p, qLen, ctx->dEntries.p, dQIds.p, dQSlotOff.p, dQTiles.p + tA, k,
                                                                              hitOff.p, slotInfo.p, hitBase, nullptr, nullptr, nullptr, bufA, qa, idBits, nullptr,
                                                                              posBits, qTie.p);
                 checkLaunch(ctx, "expandKernel");
             }
             {
                 PhaseTimer pt(ctx, "hit_sort_radix");
-                segRadixSortKernel<<<nq, SEG_WARPS * 32, 0, ctx->stream>>>(bufA, bufB, dQHitOff.p, qa, hitBase, posBits, (idBits + 7) / 8, hits.p, flags.p);
+                segRadixSortKernel<<<nq, SEG_WARPS * 32, 0, streamOf(ctx)>>>(bufA, bufB, dQHitOff.p, qa, hitBase, posBits, (idBits + 7) / 8, hits.p, flags.p);
                 checkLaunch(ctx, "segRadixSortKernel");
             }
         } else if (radixMode == 2) {
@@ -1786,7 +1822,7 @@ static void overlapsChunk(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, ui
             unsigned long long* payload = reinterpret_cast<unsigned long long*>(reinterpret_cast<Elem*>(cands.p) + M);
             {
                 PhaseTimer pt(ctx, "expand");
-                expandKernel<1><<<(unsigned)(tB - tA), 256, 0, ctx->stream>>>(ctx->dLen.p, qLen, ctx->dEntries.p, dQIds.p, dQSlotOff.p, dQTiles.p + tA, k,
+                expandKernel<1><<<(unsigned)(tB - tA), 256, 0, streamOf(ctx)>>>(ctx->dLen.p, qLen, ctx->dEntries.p, dQIds.p, dQSlotOff.p, dQTiles.p + tA, k,
                                                                              hitOff.p, slotInfo.p, hitBase, nullptr, keyA, valA, payload, qa, idBits, nullptr, 0, nullptr);
                 checkLaunch(ctx, "expandKernel");
             }
@@ -1794,28 +1830,28 @@ static void overlapsChunk(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, ui
             {
                 PhaseTimer pt(ctx, "hit_sort_radix_lib");
                 size_t tb = 0;
-                FG_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, dk, dv, (int)M, 0, idBits + qBits, ctx->stream));
+                FG_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, dk, dv, (int)M, 0, idBits + qBits, streamOf(ctx)));
                 DevBuf<char> tmpS(tb);
-                FG_CUDA(cub::DeviceRadixSort::SortPairs(tmpS.p, tb, dk, dv, (int)M, 0, idBits + qBits, ctx->stream));
+                FG_CUDA(cub::DeviceRadixSort::SortPairs(tmpS.p, tb, dk, dv, (int)M, 0, idBits + qBits, streamOf(ctx)));
                 ctx->launches += 2 + (idBits + qBits + 7) / 8;
             }
             {
                 PhaseTimer pt(ctx, "hit_sort_gather");
-                gatherSortedHitsKernel<<<gridFor(M, 256, 16), 256, 0, ctx->stream>>>(dk.Current(), dv.Current(), payload, M, idBits, hits.p, qTie.p, tieFlags);
+                gatherSortedHitsKernel<<<gridFor(M, 256, 16), 256, 0, streamOf(ctx)>>>(dk.Current(), dv.Current(), payload, M, idBits, hits.p, qTie.p, tieFlags);
                 checkLaunch(ctx, "gatherSortedHitsKernel");
             }
         }
         if (radixPath) {
-            querySegsKernel<<<(nq + 255) / 256, 256, 0, ctx->stream>>>(dQHitOff.p, qa, nq, hitBase, segsQ.p, qTie.p, counters.p + 24);
+            querySegsKernel<<<(nq + 255) / 256, 256, 0, streamOf(ctx)>>>(dQHitOff.p, qa, nq, hitBase, segsQ.p, qTie.p, counters.p + 24);
             checkLaunch(ctx, "querySegsKernel");
             uint32_t hTied = 0;
-            FG_CUDA(cudaMemcpyAsync(&hTied, counters.p + 24, 4, cudaMemcpyDeviceToHost, ctx->stream));
-            FG_CUDA(cudaStreamSynchronize(ctx->stream));
-            totTied += hTied;
+            FG_CUDA(cudaMemcpyAsync(&hTied, counters.p + 24, 4, cudaMemcpyDeviceToHost, streamOf(ctx)));
+            FG_CUDA(cudaStreamSynchronize(streamOf(ctx)));
+            tot.tied += hTied;
             if (hTied && radixMode == 1) {
                 PhaseTimer pt(ctx, "hit_sort_top");
-                FG_CUDA(cudaMemsetAsync(tieFlags, 0, M + 1, ctx->stream));
-                tieFlagKernel<<<nq, 256, 0, ctx->stream>>>(hits.p, dQHitOff.p, qa, hitBase, qTie.p, tieFlags);
+                FG_CUDA(cudaMemsetAsync(tieFlags, 0, M + 1, streamOf(ctx)));
+                tieFlagKernel<<<nq, 256, 0, streamOf(ctx)>>>(hits.p, dQHitOff.p, qa, hitBase, qTie.p, tieFlags);
                 checkLaunch(ctx, "tieFlagKernel");
             }
             if (hTied) {
@@ -1828,14 +1864,14 @@ static void overlapsChunk(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, ui
                     PhaseTimer pt(ctx, "hit_sort_top");
                     cub::TransformInputIterator<uint32_t, CastU8, const uint8_t*> itF(tieFlags, CastU8());
                     size_t tb = 0;
-                    FG_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, itF, tieP, (int)(M + 1), ctx->stream));
+                    FG_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, itF, tieP, (int)(M + 1), streamOf(ctx)));
                     DevBuf<char> tmpS(tb);
-                    FG_CUDA(cub::DeviceScan::ExclusiveSum(tmpS.p, tb, itF, tieP, (int)(M + 1), ctx->stream));
+                    FG_CUDA(cub::DeviceScan::ExclusiveSum(tmpS.p, tb, itF, tieP, (int)(M + 1), streamOf(ctx)));
                     ++ctx->launches;
                 }
                 {
                     PhaseTimer pt(ctx, "hit_sort_top");   // re-expansion of the queries with ties
-                    expandKernel<0><<<(unsigned)(tB - tA), 256, 0, ctx->stream>>>(ctx->dLen.p, qLen, ctx->dEntries.p, dQIds.p, dQSlotOff.p, dQTiles.p + tA, k,
+                    expandKernel<0><<<(unsigned)(tB - tA), 256, 0, streamOf(ctx)>>>(ctx->dLen.p, qLen, ctx->dEntries.p, dQIds.p, dQSlotOff.p, dQTiles.p + tA, k,
                                                                                      hitOff.p, slotInfo.p, hitBase, scratch, nullptr, nullptr, nullptr, qa, 0, qTie.p, 0, nullptr);
                     checkLaunch(ctx, "expandKernel");
                 }
@@ -1845,11 +1881,11 @@ static void overlapsChunk(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, ui
         } else {
             {
                 PhaseTimer pt(ctx, "expand");
-                expandKernel<0><<<(unsigned)(tB - tA), 256, 0, ctx->stream>>>(ctx->dLen.p, qLen, ctx->dEntries.p, dQIds.p, dQSlotOff.p, dQTiles.p + tA, k,
+                expandKernel<0><<<(unsigned)(tB - tA), 256, 0, streamOf(ctx)>>>(ctx->dLen.p, qLen, ctx->dEntries.p, dQIds.p, dQSlotOff.p, dQTiles.p + tA, k,
                                                                                  hitOff.p, slotInfo.p, hitBase, hits.p, nullptr, nullptr, nullptr, qa, 0, nullptr, 0, nullptr);
                 checkLaunch(ctx, "expandKernel");
             }
-            querySegsKernel<<<(nq + 255) / 256, 256, 0, ctx->stream>>>(dQHitOff.p, qa, nq, hitBase, segsQ.p, nullptr, nullptr);
+            querySegsKernel<<<(nq + 255) / 256, 256, 0, streamOf(ctx)>>>(dQHitOff.p, qa, nq, hitBase, segsQ.p, nullptr, nullptr);
             checkLaunch(ctx, "querySegsKernel");
             sortSegments(ctx, hits.p, segsQ.p, counters.p, nq, ws, "hit_sort_top", "hit_sort_small", sortCfgHits(), nullptr, nullptr,
                          reinterpret_cast<uint32_t*>(ord.p), reinterpret_cast<uint32_t*>(ord.p) + M, counters.p + 25);
@@ -1860,30 +1896,30 @@ static void overlapsChunk(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, ui
         {
             PhaseTimer pt(ctx, "group");
             if (radixMode != 1) {   // (the segmented sort writes the flags itself)
-                groupFlagKernel<<<gridFor(M), 256, 0, ctx->stream>>>(hits.p, M, flags.p);
+                groupFlagKernel<<<gridFor(M), 256, 0, streamOf(ctx)>>>(hits.p, M, flags.p);
                 checkLaunch(ctx, "groupFlagKernel");
             }
-            queryStartFlagKernel<<<(nq + 255) / 256, 256, 0, ctx->stream>>>(dQHitOff.p, qa, nq, hitBase, M, flags.p);
+            queryStartFlagKernel<<<(nq + 255) / 256, 256, 0, streamOf(ctx)>>>(dQHitOff.p, qa, nq, hitBase, M, flags.p);
             checkLaunch(ctx, "queryStartFlagKernel");
             G = selectFlagged(ctx, flags.p, (uint32_t)M, gStart);
             candFlag.alloc(std::max<uint32_t>(G, 1));
-            groupCandidateKernel<<<(G + 255) / 256, 256, 0, ctx->stream>>>(gStart.p, G, M, P.minUniqueF, candFlag.p);
+            groupCandidateKernel<<<(G + 255) / 256, 256, 0, streamOf(ctx)>>>(gStart.p, G, M, P.minUniqueF, candFlag.p);
             checkLaunch(ctx, "groupCandidateKernel");
             C = selectFlagged(ctx, candFlag.p, G, candIds);
             pairInfo.alloc(std::max<uint32_t>(C, 1)); passFlag.alloc(std::max<uint32_t>(C, 1));
             if (C) {
-                pairFilterKernel<<<(C + 7) / 8, 256, 0, ctx->stream>>>(hits.p, gStart.p, G, M, candIds.p, C, dQHitOff.p, qa, nq, hitBase,
+                pairFilterKernel<<<(C + 7) / 8, 256, 0, streamOf(ctx)>>>(hits.p, gStart.p, G, M, candIds.p, C, dQHitOff.p, qa, nq, hitBase,
                                                                       dQIds.p, ctx->dLen.p, qLen, P, passFlag.p, pairInfo.p);
                 checkLaunch(ctx, "pairFilterKernel");
                 Pn = selectFlagged(ctx, passFlag.p, C, pairIds);
             }
         }
-        totPairs += G; totDpPairs += Pn;
+        tot.pairs += G; tot.dpPairs += Pn;
         if (Pn) {
             DevBuf<uint32_t> nCand(Pn), nKept(Pn);
             DevBuf<uint64_t> outOff(Pn + 1);
             DevBuf<unsigned long long> dCells(2);   // [0] predecessor evaluations of the DP, [1] pairs whose score order needed no sort
-            FG_CUDA(cudaMemsetAsync(dCells.p, 0, 16, ctx->stream));
+            FG_CUDA(cudaMemsetAsync(dCells.p, 0, 16, streamOf(ctx)));
             DevBuf<uint32_t> pairFlags(Pn), nRuns;
             DevBuf<Seg> extSegs(Pn), allSegs(Pn);
             // FG_DP_MODE: 2 = run-compressed DP and chain walk (default), 1 = match-by-match with pruned look-back, 0 = match-by-match
@@ -1891,7 +1927,7 @@ static void overlapsChunk(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, ui
             {
                 PhaseTimer pt(ctx, "chain_prep");
                 if (dpMode == 2) nRuns.alloc(Pn);
-                pairPrepKernel<<<(Pn + 7) / 8, 256, 0, ctx->stream>>>(hits.p, pairInfo.p, pairIds.p, Pn, dQIds.p, ctx->dLen.p, qLen, pairFlags.p,
+                pairPrepKernel<<<(Pn + 7) / 8, 256, 0, streamOf(ctx)>>>(hits.p, pairInfo.p, pairIds.p, Pn, dQIds.p, ctx->dLen.p, qLen, pairFlags.p,
                                                                      extSegs.p, counters.p + 8, allSegs.p, k, dpMode == 2 ? reinterpret_cast<Run*>(cands.p) : nullptr,
                                                                      back.p, nRuns.p);
                 checkLaunch(ctx, "pairPrepKernel");
@@ -1903,78 +1939,77 @@ static void overlapsChunk(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, ui
                 Run* runs = reinterpret_cast<Run*>(cands.p);
                 if (dpMode == 2) {
                     PhaseTimer pt(ctx, "chain_runs");
-                    chainRunsKernel<<<(Pn + 7) / 8, 256, 0, ctx->stream>>>(hits.p, pairInfo.p, pairIds.p, Pn, pairFlags.p, k, runs, back.p, nRuns.p);
+                    chainRunsKernel<<<(Pn + 7) / 8, 256, 0, streamOf(ctx)>>>(hits.p, pairInfo.p, pairIds.p, Pn, pairFlags.p, k, runs, back.p, nRuns.p);
                     checkLaunch(ctx, "chainRunsKernel");
                 }
                 cub::DoubleBuffer<uint32_t> dk(szKeyA.p, szKeyB.p), dv(ordA.p, ordB.p);
                 {
                     PhaseTimer pt(ctx, "chain_order");
                     if (dpMode == 2) {
-                        runCountKeyKernel<<<(Pn + 255) / 256, 256, 0, ctx->stream>>>(nRuns.p, Pn, szKeyA.p, ordA.p);
+                        runCountKeyKernel<<<(Pn + 255) / 256, 256, 0, streamOf(ctx)>>>(nRuns.p, Pn, szKeyA.p, ordA.p);
                         checkLaunch(ctx, "runCountKeyKernel");
                     } else {
-                        pairSizeKeyKernel<<<(Pn + 255) / 256, 256, 0, ctx->stream>>>(pairInfo.p, pairIds.p, Pn, szKeyA.p, ordA.p);
+                        pairSizeKeyKernel<<<(Pn + 255) / 256, 256, 0, streamOf(ctx)>>>(pairInfo.p, pairIds.p, Pn, szKeyA.p, ordA.p);
                         checkLaunch(ctx, "pairSizeKeyKernel");
                     }
                     size_t tb = 0;
-                    FG_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, dk, dv, (int)Pn, 0, 32, ctx->stream));
+                    FG_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, dk, dv, (int)Pn, 0, 32, streamOf(ctx)));
                     DevBuf<char> tmpS(tb);
-                    FG_CUDA(cub::DeviceRadixSort::SortPairs(tmpS.p, tb, dk, dv, (int)Pn, 0, 32, ctx->stream));
+                    FG_CUDA(cub::DeviceRadixSort::SortPairs(tmpS.p, tb, dk, dv, (int)Pn, 0, 32, streamOf(ctx)));
                     ctx->launches += 5;
                 }
                 if (dpMode == 2) {
                     {
                         PhaseTimer pt(ctx, "chain_dp");
-                        chainRunDpKernel<<<(Pn + 7) / 8, 128, 0, ctx->stream>>>(hits.p, pairInfo.p, pairIds.p, dv.Current(), Pn, pairFlags.p, nRuns.p, P, runs,
+                        chainRunDpKernel<<<(Pn + 7) / 8, 128, 0, streamOf(ctx)>>>(hits.p, pairInfo.p, pairIds.p, dv.Current(), Pn, pairFlags.p, nRuns.p, P, runs,
                                                                                dCells.p);   // whole warps: no early exit inside
                         checkLaunch(ctx, "chainRunDpKernel");
                     }
                     PhaseTimer pt(ctx, "chain_fill");
-                    chainFillKernel<<<(Pn + 7) / 8, 256, 0, ctx->stream>>>(hits.p, pairInfo.p, pairIds.p, Pn, pairFlags.p, runs, score.p, back.p, ord.p,
+                    chainFillKernel<<<(Pn + 7) / 8, 256, 0, streamOf(ctx)>>>(hits.p, pairInfo.p, pairIds.p, Pn, pairFlags.p, runs, score.p, back.p, ord.p,
                                                                           allSegs.p, dCells.p + 1);
                     checkLaunch(ctx, "chainFillKernel");
                 } else {
                     PhaseTimer pt(ctx, "chain_dp");
                     auto dp = dpMode == 1 ? chainDpPrunedKernel : chainDpKernel;
-                    dp<<<(Pn + 7) / 8, 128, 0, ctx->stream>>>(hits.p, pairInfo.p, pairIds.p, dv.Current(), Pn, pairFlags.p, P, score.p, back.p, ord.p,
+                    dp<<<(Pn + 7) / 8, 128, 0, streamOf(ctx)>>>(hits.p, pairInfo.p, pairIds.p, dv.Current(), Pn, pairFlags.p, P, score.p, back.p, ord.p,
                                                              dCells.p);   // whole warps: no early exit inside
                     checkLaunch(ctx, "chainDpKernel");
                 }
             }
-            FG_CUDA(cudaMemcpyAsync(counters.p + 16, &Pn, 4, cudaMemcpyHostToDevice, ctx->stream));
+            FG_CUDA(cudaMemcpyAsync(counters.p + 16, &Pn, 4, cudaMemcpyHostToDevice, streamOf(ctx)));
             sortSegments(ctx, ord.p, allSegs.p, counters.p + 16, Pn, ws, "chain_ordsort_top", "chain_ordsort_small", sortCfgPairs());
             {
                 PhaseTimer pt(ctx, "chain_walk");
-                static bool walkAttr = false;
                 const int walkSmem = 4 * WALK_CAP * (int)sizeof(unsigned short);
-                if (!walkAttr) {
+                static std::once_flag walkAttr[64];   // function attributes are per device
+                std::call_once(walkAttr[ctx->device & 63], [&] {
                     FG_CUDA(cudaFuncSetAttribute(chainWalkKernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, walkSmem));
                     FG_CUDA(cudaFuncSetAttribute(chainWalkKernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, walkSmem));
-                    walkAttr = true;
-                }
+                });
                 auto walk = dpMode == 2 ? chainWalkKernel<true> : chainWalkKernel<false>;
-                walk<<<(Pn + 3) / 4, 128, walkSmem, ctx->stream>>>(hits.p, pairInfo.p, pairIds.p, Pn, pairFlags.p, dQIds.p, dQSlotOff.p,
+                walk<<<(Pn + 3) / 4, 128, walkSmem, streamOf(ctx)>>>(hits.p, pairInfo.p, pairIds.p, Pn, pairFlags.p, dQIds.p, dQSlotOff.p,
                                                                ctx->dLen.p, qLen, filtBits.p, filtPrefix.p, P, score.p, back.p, ord.p,
                                                                cands.p, nCand.p, nKept.p, nRuns.p);
                 checkLaunch(ctx, "chainWalkKernel");
             }
             {
                 uint32_t hc[32];
-                FG_CUDA(cudaMemcpyAsync(hc, counters.p, sizeof hc, cudaMemcpyDeviceToHost, ctx->stream));
-                FG_CUDA(cudaStreamSynchronize(ctx->stream));
+                FG_CUDA(cudaMemcpyAsync(hc, counters.p, sizeof hc, cudaMemcpyDeviceToHost, streamOf(ctx)));
+                FG_CUDA(cudaStreamSynchronize(streamOf(ctx)));
                 if (hc[1] > taskCap || hc[9] > taskCap || hc[17] > taskCap) throw Error(FG_ERR_INTERNAL, "sort task list overflow");
             }
             HostTimer pt(ctx, "host_results");   // gather of the kept overlaps, device -> pinned host copies (includes "edit")
             cub::TransformInputIterator<uint64_t, CastU64, const uint32_t*> it64(nKept.p, CastU64());
             exclusiveScanToPlus1(ctx, it64, outOff.p, Pn);
             uint64_t nOut = 0; unsigned long long cells[2] = {0, 0};
-            FG_CUDA(cudaMemcpyAsync(&nOut, outOff.p + Pn, 8, cudaMemcpyDeviceToHost, ctx->stream));
-            FG_CUDA(cudaMemcpyAsync(cells, dCells.p, 16, cudaMemcpyDeviceToHost, ctx->stream));
-            FG_CUDA(cudaStreamSynchronize(ctx->stream));
-            totCells += cells[0]; totPresorted += cells[1];
+            FG_CUDA(cudaMemcpyAsync(&nOut, outOff.p + Pn, 8, cudaMemcpyDeviceToHost, streamOf(ctx)));
+            FG_CUDA(cudaMemcpyAsync(cells, dCells.p, 16, cudaMemcpyDeviceToHost, streamOf(ctx)));
+            FG_CUDA(cudaStreamSynchronize(streamOf(ctx)));
+            tot.cells += cells[0]; tot.presorted += cells[1];
             if (nOut) {
                 DevBuf<fg_overlap> dOut(nOut);
-                gatherOverlapsKernel<<<(Pn + 255) / 256, 256, 0, ctx->stream>>>(pairInfo.p, pairIds.p, Pn, dQIds.p, ctx->dLen.p, qLen, ord.p, cands.p,
+                gatherOverlapsKernel<<<(Pn + 255) / 256, 256, 0, streamOf(ctx)>>>(pairInfo.p, pairIds.p, Pn, dQIds.p, ctx->dLen.p, qLen, ord.p, cands.p,
                                                                                nCand.p, outOff.p, 0u - qOffset, pairFlags.p, dOut.p);
                 checkLaunch(ctx, "gatherOverlapsKernel");
                 {   // kmerMatches of the kept overlaps, or just clearing the scratch the gather left in aln_first / aln_count
@@ -1982,44 +2017,131 @@ static void overlapsChunk(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, ui
                     const uint32_t nO = (uint32_t)nOut;
                     DevBuf<uint32_t> alnCount(nO); DevBuf<uint64_t> alnOff(nO + 1);
                     if (prm.keep_alignment) {
-                        alignKernel<<<(nO + 255) / 256, 256, 0, ctx->stream>>>(dOut.p, nO, hits.p, back.p, k, false, nullptr, alnCount.p, nullptr);
+                        alignKernel<<<(nO + 255) / 256, 256, 0, streamOf(ctx)>>>(dOut.p, nO, hits.p, back.p, k, false, nullptr, alnCount.p, nullptr);
                         checkLaunch(ctx, "alignKernel");
                         cub::TransformInputIterator<uint64_t, CastU64, const uint32_t*> itc(alnCount.p, CastU64());
                         exclusiveScanToPlus1(ctx, itc, alnOff.p, nO);
                         uint64_t nPts = 0;
-                        FG_CUDA(cudaMemcpyAsync(&nPts, alnOff.p + nO, 8, cudaMemcpyDeviceToHost, ctx->stream));
-                        FG_CUDA(cudaStreamSynchronize(ctx->stream));
+                        FG_CUDA(cudaMemcpyAsync(&nPts, alnOff.p + nO, 8, cudaMemcpyDeviceToHost, streamOf(ctx)));
+                        FG_CUDA(cudaStreamSynchronize(streamOf(ctx)));
                         DevBuf<int32_t> alnPairs(std::max<uint64_t>(2 * nPts, 2));
-                        alignKernel<<<(nO + 255) / 256, 256, 0, ctx->stream>>>(dOut.p, nO, hits.p, back.p, k, true, alnOff.p, alnCount.p, alnPairs.p);
+                        alignKernel<<<(nO + 255) / 256, 256, 0, streamOf(ctx)>>>(dOut.p, nO, hits.p, back.p, k, true, alnOff.p, alnCount.p, alnPairs.p);
                         checkLaunch(ctx, "alignKernel");
+                        std::lock_guard<std::mutex> alnLock(ctx->alnMutex);   // the pair array is shared by the lanes: append under a lock
                         const uint64_t base = ctx->resAln.size() / 2;
-                        alignFinishKernel<<<(nO + 255) / 256, 256, 0, ctx->stream>>>(dOut.p, nO, alnOff.p, alnCount.p, base, true);
+                        alignFinishKernel<<<(nO + 255) / 256, 256, 0, streamOf(ctx)>>>(dOut.p, nO, alnOff.p, alnCount.p, base, true);
                         checkLaunch(ctx, "alignFinishKernel");
                         ctx->resAln.resize(ctx->resAln.size() + 2 * nPts);
-                        FG_CUDA(cudaMemcpyAsync(ctx->resAln.data() + 2 * base, alnPairs.p, 2 * nPts * 4, cudaMemcpyDeviceToHost, ctx->stream));
-                        FG_CUDA(cudaStreamSynchronize(ctx->stream));
+                        FG_CUDA(cudaMemcpyAsync(ctx->resAln.data() + 2 * base, alnPairs.p, 2 * nPts * 4, cudaMemcpyDeviceToHost, streamOf(ctx)));
+                        FG_CUDA(cudaStreamSynchronize(streamOf(ctx)));
                     } else {
-                        alignFinishKernel<<<(nO + 255) / 256, 256, 0, ctx->stream>>>(dOut.p, nO, nullptr, nullptr, 0, false);
+                        alignFinishKernel<<<(nO + 255) / 256, 256, 0, streamOf(ctx)>>>(dOut.p, nO, nullptr, nullptr, 0, false);
                         checkLaunch(ctx, "alignFinishKernel");
                     }
                 }
-                pinned.ensureKeep(nRaw + nOut, nRaw);
-                fg_overlap* dst = pinned.p + nRaw;
-                FG_CUDA(cudaMemcpyAsync(dst, dOut.p, nOut * sizeof(fg_overlap), cudaMemcpyDeviceToHost, ctx->stream));
-                FG_CUDA(cudaStreamSynchronize(ctx->stream));
-                if (prm.nucl_alignment) {   // overlap.cpp:463-468
-                    if (nOut >= (1ULL << 31)) throw Error(FG_ERR_ARG, "too many overlaps in one sub-batch");
-                    PhaseTimer pe(ctx, "edit");
-                    editDistances(ctx, dOut.p, dst, (uint32_t)nOut, prm.use_hpc != 0, !P.sameSet, prm.max_divergence, dQueryMaxDiv);
-                    FG_CUDA(cudaMemcpyAsync(dst, dOut.p, nOut * sizeof(fg_overlap), cudaMemcpyDeviceToHost, ctx->stream));
-                    FG_CUDA(cudaStreamSynchronize(ctx->stream));
+                // this sub-batch's slice of the shared pinned buffer: directly behind its predecessor's
+                const size_t myOff = commit.reserve(subIndex, nOut);
+                committed = true;
+                {
+                    std::shared_lock<std::shared_mutex> rd(ctx->pinnedMutex);
+                    if (pinned.n < myOff + nOut) {   // grow: exclusively, when no lane is copying into or working on the buffer
+                        rd.unlock();
+                        {
+                            std::unique_lock<std::shared_mutex> wr(ctx->pinnedMutex);
+                            size_t reserved;   // slices of later sub-batches may already hold records: keep everything reserved so far
+                            { std::lock_guard<std::mutex> lk(commit.m); reserved = commit.nRaw; }
+                            if (pinned.n < myOff + nOut) pinned.ensureKeep(std::max(myOff + nOut, reserved), std::min(reserved, pinned.n));
+                        }
+                        rd.lock();
+                    }
+                    fg_overlap* dst = pinned.p + myOff;
+                    FG_CUDA(cudaMemcpyAsync(dst, dOut.p, nOut * sizeof(fg_overlap), cudaMemcpyDeviceToHost, streamOf(ctx)));
+                    FG_CUDA(cudaStreamSynchronize(streamOf(ctx)));
+                    if (prm.nucl_alignment) {   // overlap.cpp:463-468
+                        PhaseTimer pe(ctx, "edit");
+                        editDistances(ctx, dOut.p, dst, (uint32_t)nOut, prm.use_hpc != 0, !P.sameSet, prm.max_divergence, dQueryMaxDiv);
+                        FG_CUDA(cudaMemcpyAsync(dst, dOut.p, nOut * sizeof(fg_overlap), cudaMemcpyDeviceToHost, streamOf(ctx)));
+                        FG_CUDA(cudaStreamSynchronize(streamOf(ctx)));
+                    }
+                    // seqDivergence of this slice's records (host arithmetic with glibc logf), while the other lanes keep the device busy
+                    HostTimer he(ctx, "host_divergence");
+                    recordDivergences(ctx, dst, nOut, prm);
                 }
-                nRaw += nOut;
             }
         }
-        qa = qb;
-    }
+        commitNone();
+    };
 
+    // lanes
+    while ((int)ctx->lanes.size() < nLanes) {
+        std::unique_ptr<Lane> l(new Lane());
+        FG_CUDA(cudaStreamCreateWithFlags(&l->stream, cudaStreamNonBlocking));
+        ctx->lanes.push_back(std::move(l));
+    }
+    std::atomic<size_t> nextSub{0};
+    std::atomic<bool> aborted{false};
+    std::exception_ptr firstError; std::mutex errM;
+    const int nWorkers = (int)std::min<size_t>(nLanes, std::max<size_t>(subs.size(), 1));
+    auto worker = [&](int li) {
+        Lane* lane = ctx->lanes[li].get();
+        cudaSetDevice(ctx->device);
+        currentArena() = &lane->arena; currentLane() = lane;
+        try {
+            for (;;) {
+                const size_t i = nextSub.fetch_add(1);
+                if (i >= subs.size() || aborted.load()) break;
+                runSub(subs[i].qa, subs[i].qb, subBase + i);
+            }
+        } catch (...) {
+            { std::lock_guard<std::mutex> lk(errM); if (!firstError) firstError = std::current_exception(); }
+            aborted = true;
+            commit.fail();
+            cudaGetLastError();
+        }
+        currentLane() = nullptr; currentArena() = nullptr;
+    };
+    for (auto& l : ctx->lanes) { l->timings.clear(); l->timingCalls.clear(); }
+    std::vector<std::thread> threads;
+    for (int li = 1; li < nWorkers; ++li) threads.emplace_back(worker, li);
+    {   // the calling thread is lane 0
+        Arena* mainArena = currentArena();
+        worker(0);
+        currentArena() = mainArena;
+    }
+    for (auto& th : threads) th.join();
+    subBase += subs.size();
+    for (auto& l : ctx->lanes) {   // the lanes' phase times join the call's list
+        for (size_t i = 0; i < l->timings.size(); ++i) addTiming(ctx, l->timings[i].first.c_str(), l->timings[i].second, l->timingCalls[i]);
+        l->timings.clear(); l->timingCalls.clear();
+    }
+    if (firstError) std::rethrow_exception(firstError);
+}
+
+// seqDivergence of raw records (overlap.cpp:409-423; alignment.cpp:240-245 with nucl_alignment): the reference's float
+// expression, evaluated on the host with glibc logf so that the bits agree.  Runs on the context's host pool.
+static void recordDivergences(fg_ctx* ctx, fg_overlap* recs, size_t n, const fg_overlap_params& prm) {
+    const float sampleRate = ctx->stats.sample_rate;
+    const int k = ctx->k;
+    auto body = [&](size_t a, size_t b) {
+        for (size_t i = a; i < b; ++i) {
+            fg_overlap& o = recs[i];
+            const int32_t curRange = o.cur_end - o.cur_begin, extRange = o.ext_end - o.ext_begin;
+            volatile float normLen = std::max(curRange, extRange) - o.filtered_positions;
+            volatile float mr = (float)o.chain_length * sampleRate;
+            volatile float matchRate = mr / normLen;
+            matchRate = std::min((float)matchRate, 1.0f);
+            volatile float inv = 1 / matchRate;
+            volatile float lg = std::log((float)inv);
+            o.seq_divergence = lg / k;
+            if (prm.nucl_alignment) {   // alignment.cpp:240-245: (float)editDistance / max(len, len)
+                if (o.edit_distance < 0) o.seq_divergence = 1.0f;
+                else { volatile float dv = (float)o.edit_distance / (size_t)o.aln_len; o.seq_divergence = dv; }
+            }
+        }
+    };
+    if (n < 4096) { body(0, n); return; }
+    std::lock_guard<std::mutex> lk(ctx->hostPoolMutex);
+    ctx->hostPool.parallelFor(n, body, n);
 }
 
 void overlapsBatch(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, const fg_overlap_params& prm, fg_overlap_result* result) {
@@ -2040,16 +2162,19 @@ void overlapsBatch(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, const fg_
 
     ctx->resOffsets.assign(nQ + 1, 0);
     ctx->resAln.clear();
-    uint64_t totHits = 0, totPairs = 0, totDpPairs = 0, totCells = 0, totTied = 0, totPresorted = 0;
-    PinnedBuf<fg_overlap>& pinned = ctx->pinnedOut;   // all chunks / sub-batches land here; the epilogue compacts in place
-    size_t nRaw = 0;
+    uint64_t totHits = 0;
+    BatchTotals tot;
+    OrderedCommit commit;
+    size_t subBase = 0;
+    PinnedBuf<fg_overlap>& pinned = ctx->pinnedOut;   // all chunks / sub-batches land here in query order; the epilogue compacts into a second buffer
     HostTimer hostAll(ctx, "host_total");
     const uint64_t mallocs0 = ctx->arena.mallocCalls;
 
+    if (prm.nucl_alignment) prepareEditDistances(ctx, prm.use_hpc != 0, !sameSet);
     DevBuf<float> dQueryMaxDiv;   // per-query divergence thresholds (optional), indexed like the records' `reserved`
     if (prm.query_max_divergence && nQ) {
         dQueryMaxDiv.alloc(nQ);
-        FG_CUDA(cudaMemcpyAsync(dQueryMaxDiv.p, prm.query_max_divergence, nQ * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+        FG_CUDA(cudaMemcpyAsync(dQueryMaxDiv.p, prm.query_max_divergence, nQ * sizeof(float), cudaMemcpyHostToDevice, streamOf(ctx)));
     }
     // chunks of consecutive queries with < 2^30 k-mer slots each (device arrays are indexed with 32-bit counts)
     uint64_t chunkSlots = 1ULL << 30;
@@ -2063,38 +2188,29 @@ void overlapsBatch(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, const fg_
             if (q1 > q0 && slots + add >= chunkSlots) break;
             slots += add; ++q1;
         }
-        overlapsChunk(ctx, queryIds + q0, q1 - q0, q0, prm, P, nRaw, totHits, totPairs, totDpPairs, totCells, totTied, totPresorted, dQueryMaxDiv.p);
+        overlapsChunk(ctx, queryIds + q0, q1 - q0, q0, prm, P, commit, subBase, totHits, tot, dQueryMaxDiv.p);
         q0 = q1;
     }
+    const size_t nRaw = commit.nRaw;
+    const uint64_t totPairs = tot.pairs, totDpPairs = tot.dpPairs, totCells = tot.cells, totTied = tot.tied, totPresorted = tot.presorted;
 
     // host epilogue: divergence (overlap.cpp:417-423), threshold (:470), maxOverlaps (:218-219)
     HostTimer hostEpi(ctx, "host_epilogue");
-    const float sampleRate = ctx->stats.sample_rate;
     fg_overlap* hOut = pinned.p;
     auto parallelFor = [&](size_t n, const std::function<void(size_t, size_t)>& fn) { ctx->hostPool.parallelFor(n, fn, nRaw); };
-    // (1) divergence of every record (pure per-record arithmetic with glibc logf) and the first record of every query
+    // (1) the first record of every query (the divergences were computed by the lanes, recordDivergences)
     std::vector<size_t> qStart(nQ + 1, SIZE_MAX);
+    std::atomic<bool> badOrder{false};
     parallelFor(nRaw, [&](size_t a, size_t b) {
         for (size_t i = a; i < b; ++i) {
-            fg_overlap& o = hOut[i];
-            const int32_t curRange = o.cur_end - o.cur_begin, extRange = o.ext_end - o.ext_begin;
-            volatile float normLen = std::max(curRange, extRange) - o.filtered_positions;
-            volatile float mr = (float)o.chain_length * sampleRate;
-            volatile float matchRate = mr / normLen;
-            matchRate = std::min((float)matchRate, 1.0f);
-            volatile float inv = 1 / matchRate;
-            volatile float lg = std::log((float)inv);
-            o.seq_divergence = lg / k;
-            if (prm.nucl_alignment) {   // alignment.cpp:240-245: (float)editDistance / max(len, len)
-                if (o.edit_distance < 0) o.seq_divergence = 1.0f;
-                else { volatile float dv = (float)o.edit_distance / (size_t)o.aln_len; o.seq_divergence = dv; }
-            }
+            const fg_overlap& o = hOut[i];
             if (i == 0 || hOut[i - 1].reserved != o.reserved) {
-                if (o.reserved >= nQ || (i && hOut[i - 1].reserved > o.reserved)) continue;   // reported below
+                if (o.reserved >= nQ || (i && hOut[i - 1].reserved > o.reserved)) { badOrder = true; continue; }
                 qStart[o.reserved] = i;
             }
         }
     });
+    if (badOrder) throw Error(FG_ERR_INTERNAL, "overlap records out of query order");
     qStart[nQ] = nRaw;
     for (uint32_t q = nQ; q-- > 0;) if (qStart[q] == SIZE_MAX) qStart[q] = qStart[q + 1];   // queries without records
     // (2) threshold (:470) and maxOverlaps (:218-219) replay per query, in parallel: dropped records are marked
