@@ -34,7 +34,8 @@ class OverlapParams(C.Structure):
     _fields_ = [("max_jump", C.c_int32), ("min_overlap", C.c_int32), ("max_overhang", C.c_int32),
                 ("max_overlaps", C.c_int32), ("force_local", C.c_int32), ("keep_alignment", C.c_int32),
                 ("only_max_ext", C.c_int32), ("nucl_alignment", C.c_int32), ("use_hpc", C.c_int32),
-                ("max_divergence", C.c_float), ("query_set", C.c_int32), ("query_max_divergence", C.POINTER(C.c_float))]
+                ("max_divergence", C.c_float), ("query_set", C.c_int32), ("query_max_divergence", C.POINTER(C.c_float)),
+                ("keep_rejected", C.c_int32), ("pad_", C.c_int32)]
 
 
 OVERLAP_DTYPE = np.dtype([("cur_id", "<u4"), ("cur_begin", "<i4"), ("cur_end", "<i4"), ("cur_len", "<i4"),
@@ -253,7 +254,7 @@ class Engine:
     # ---- overlaps ----
     def overlaps(self, query_ids, max_jump=1500, min_overlap=1000, max_overhang=1500, max_overlaps=0, force_local=False,
                  keep_alignment=False, only_max_ext=True, nucl_alignment=False, use_hpc=False, max_divergence=1.0, copy=True,
-                 query_set=0, query_max_divergence=None):
+                 query_set=0, query_max_divergence=None, keep_rejected=False):
         """copy=False returns views into library-owned memory, valid until the next overlaps() call.
         query_max_divergence: optional per-query thresholds (float32, one per query id) overriding max_divergence."""
         q = np.ascontiguousarray(query_ids, dtype=np.uint32)
@@ -264,7 +265,7 @@ class Engine:
                 raise ValueError("query_max_divergence needs one threshold per query")
         p = OverlapParams(max_jump, min_overlap, max_overhang, max_overlaps, int(force_local), int(keep_alignment),
                           int(only_max_ext), int(nucl_alignment), int(use_hpc), max_divergence, int(query_set),
-                          _ptr(qthr, C.c_float) if qthr is not None else None)
+                          _ptr(qthr, C.c_float) if qthr is not None else None, int(keep_rejected), 0)
         res = OverlapResult()
         self._check(self.lib.fg_overlaps_batch(self.ctx, _ptr(q, C.c_uint32), len(q), C.byref(p), C.byref(res)))
         offsets = np.ctypeslib.as_array(res.offsets, shape=(len(q) + 1,))

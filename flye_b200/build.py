@@ -73,9 +73,9 @@ def build_tools():
         _run(["g++", "-O2", "-std=c++17", src, "-o", exe])
 
 
-    for name in ("rundp_check", "wfa_check", "segsort_check"):   # CPU models: run-compressed DP / chain walk, bounded wavefronts, segmented radix sort
+    for name in ("rundp_check", "wfa_check", "segsort_check", "dense_check"):   # CPU models: run-compressed DP / chain walk, bounded wavefronts, segmented radix sort, dense k-mer class index
         src, exe = os.path.join(ROOT, "tests", "cpu_models", name + ".cpp"), os.path.join(out, name)
-        if _newer(exe, [src]):
+        if _newer(exe, [src, os.path.join(CSRC, "kmer_math.cuh")]):
             _run(["g++", "-O2", "-std=c++17", src, "-o", exe])
     src, so = os.path.join(ROOT, "tests", "cpu_models", "stdsort_lib.cpp"), os.path.join(out, "libstdsort.so")
     if _newer(so, [src]):
@@ -102,11 +102,23 @@ def build_host_harness():
     return exe
 
 
+def build_flye_modules():
+    """the reference's whole `flye-modules` twice — unmodified, and its callers on the host mirror (oracle/build_flye_modules.sh);
+    build container only (needs the reference sources); tests/test_gpu_flye_modules.py runs both on the GPU box"""
+    if not os.path.isdir("/root/reference/src/sequence"):
+        return
+    host = os.path.join(ROOT, "flye_b200", "host")
+    deps = [LIB, os.path.join(ROOT, "include", "flye_b200.h")] + [os.path.join(dp, f) for dp, _, fs in os.walk(host) for f in fs]
+    if _newer(os.path.join(ROOT, "oracle", "_ref", "flye-modules-b200"), deps) or not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "flye-modules-ref")):
+        _run([os.path.join(ROOT, "oracle", "build_flye_modules.sh")])
+
+
 def build_all(force=False):
     build_lib(force)
     build_tools()
     build_oracle()
     build_host_harness()
+    build_flye_modules()
 
 
 if __name__ == "__main__":

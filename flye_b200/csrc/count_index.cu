@@ -93,18 +93,8 @@ struct DenseMap {
     uint32_t nOwners, owner;      // owner: this rank
     uint32_t ownerShift;          // log2(nOwners) if it is a power of two, else 0xffffffff
 };
-static inline uint64_t denseSpace(int k) { return (k & 1) ? (1ULL << (2 * k - 1)) : (1ULL << (2 * k)); }
+static inline uint64_t denseSpace(int k) { return denseSpaceOf(k); }
 
-__host__ __device__ inline uint64_t denseIndexFromWindow(uint64_t v, int k) {
-    return denseIndexOfPair(fwdFromWindow(v, k), (~v) & kmerMask(k), k);
-}
-// canonical k-mer (Kmer::standardForm, kmer.h:54-63) of a dense index
-__host__ __device__ inline uint64_t canonFromDenseIndex(uint64_t idx, int k) {
-    if (!(k & 1)) return idx;
-    const uint64_t rep = (idx & ((1ULL << k) - 1ULL)) | ((idx >> k) << (k + 1));
-    const uint64_t rc = revCompKmer(rep, k);
-    return rep < rc ? rep : rc;
-}
 __device__ __forceinline__ void ownerOf(const DenseMap& m, uint64_t idx, uint32_t& owner, uint64_t& local) {
     if (m.ownerShift != 0xffffffffu) { owner = (uint32_t)(idx & (m.nOwners - 1u)); local = idx >> m.ownerShift; }
     else { local = idx / m.nOwners; owner = (uint32_t)(idx - local * m.nOwners); }

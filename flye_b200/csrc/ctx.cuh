@@ -158,6 +158,10 @@ struct fg_ctx {
     std::unique_ptr<fg_overlap[]> resCompact[2];
     size_t resCompactCap[2] = {0, 0};
     fg_overlap_result lastResult{};             // what the last fg_overlaps_batch / fg_overlaps_refilter returned
+    // what the last batch was computed under (fg_overlaps_refilter may only TIGHTEN that)
+    int32_t lastMaxOverlaps = 0;
+    float lastMaxDivergence = 0.f;
+    std::vector<float> lastQueryMaxDivergence;
     fg_overlap* compactBuffer(int which, size_t n) {
         if (resCompactCap[which] < n) { resCompactCap[which] = n + n / 4 + 16; resCompact[which].reset(new fg_overlap[resCompactCap[which]]); }
         return resCompact[which].get();

@@ -1747,7 +1747,7 @@ static void overlapsChunk(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, ui
         ctx->hitBudget = budget;
     }
     uint64_t budget = std::max<uint64_t>(32ULL << 20, ctx->hitBudget / nLanes);
-    budget = std::min<uint64_t>(budget, std::max<uint64_t>(48ULL << 20, hQHitOff[nQ] / ((uint64_t)envInt("FG_SUBS_PER_LANE", 2, 1, 16) * nLanes) + 1));
+    budget = std::min<uint64_t>(budget, std::max<uint64_t>(48ULL << 20, hQHitOff[nQ] / ((uint64_t)envInt("FG_SUBS_PER_LANE", 1, 1, 16) * nLanes) + 1));
     if (const char* e = getenv("FG_HIT_BUDGET")) budget = std::max<uint64_t>(1024, strtoull(e, nullptr, 10));
     struct Sub { uint32_t qa, qb; };
     std::vector<Sub> subs;
@@ -2146,6 +2146,7 @@ static void recordDivergences(fg_ctx* ctx, fg_overlap* recs, size_t n, const fg_
 
 void overlapsBatch(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, const fg_overlap_params& prm, fg_overlap_result* result) {
     if (!ctx->indexed) throw Error(FG_ERR_ARG, "no index: call fg_build_index_* first");
+    if (prm.keep_rejected && prm.max_overlaps != 0) throw Error(FG_ERR_ARG, "keep_rejected needs max_overlaps = 0");
     ctx->timings.clear(); ctx->timingCalls.clear();
     const int k = ctx->k;
     const bool sameSet = prm.query_set == 0;
@@ -2225,8 +2226,9 @@ void overlapsBatch(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, const fg_
                 const bool stop = prm.max_overlaps != 0 && detected >= (size_t)prm.max_overlaps;
                 const float maxDiv = prm.query_max_divergence ? prm.query_max_divergence[q] : prm.max_divergence;
                 for (size_t i = pos; i < end; ++i) {
-                    const bool keep = !stop && hOut[i].seq_divergence < maxDiv;
-                    hOut[i].reserved = keep ? 0u : 0xffffffffu;
+                    const bool pass = hOut[i].seq_divergence < maxDiv;
+                    const bool keep = !stop && (pass || prm.keep_rejected);
+                    hOut[i].reserved = keep ? (pass ? 0u : 1u) : 0xffffffffu;
                     detected += keep;
                 }
                 pos = end;
@@ -2243,7 +2245,7 @@ void overlapsBatch(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, const fg_
             for (size_t q = qa; q < qb; ++q) {
                 size_t w2 = ctx->resOffsets[q];
                 for (size_t i = qStart[q]; i < qStart[q + 1]; ++i)
-                    if (hOut[i].reserved == 0u) dst[w2++] = hOut[i];
+                    if (hOut[i].reserved != 0xffffffffu) dst[w2++] = hOut[i];
             }
         });
         hOut = dst;
@@ -2261,12 +2263,25 @@ void overlapsBatch(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, const fg_
     result->n_aln_pairs = ctx->resAln.size() / 2;
     result->n_hits = totHits; result->n_pairs = totPairs; result->n_dp_pairs = totDpPairs; result->n_dp_cells = totCells;
     ctx->lastResult = *result;
+    ctx->lastMaxOverlaps = prm.max_overlaps != 0 || prm.keep_rejected ? -1 : 0;
+    ctx->lastMaxDivergence = prm.max_divergence;
+    if (prm.query_max_divergence) ctx->lastQueryMaxDivergence.assign(prm.query_max_divergence, prm.query_max_divergence + nQ);
+    else ctx->lastQueryMaxDivergence.clear();
 }
 
 void overlapsRefilter(fg_ctx* ctx, uint32_t firstQuery, float maxDivergence, fg_overlap_result* result) {
     fg_overlap_result& last = ctx->lastResult;
     const uint32_t nQ = last.n_queries;
     if (!last.offsets || firstQuery > nQ) throw Error(FG_ERR_ARG, "fg_overlaps_refilter: no previous result / first_query out of range");
+    // The records at hand are those that survived the batch's own threshold and maxOverlaps replay (overlap.cpp:218-219, 470): a
+    // tighter threshold can be applied to them afterwards, a looser one cannot (the dropped records are gone, and with
+    // nucl_alignment their edit distance was never finished), and after a maxOverlaps cut the reference would have gone on
+    // into later target groups.
+    if (ctx->lastMaxOverlaps != 0) throw Error(FG_ERR_ARG, "fg_overlaps_refilter: the batch was cut with max_overlaps (or kept rejected records); run it again with the new threshold");
+    for (uint32_t q = firstQuery; q < nQ; ++q) {
+        const float used = ctx->lastQueryMaxDivergence.empty() ? ctx->lastMaxDivergence : ctx->lastQueryMaxDivergence[q];
+        if (maxDivergence > used) throw Error(FG_ERR_ARG, "fg_overlaps_refilter: the new threshold is looser than the one the batch was computed with");
+    }
     HostTimer ht(ctx, "host_refilter");
     const fg_overlap* src = last.overlaps;
     const size_t nRaw = ctx->resOffsets[nQ];
@@ -2297,6 +2312,9 @@ void overlapsRefilter(fg_ctx* ctx, uint32_t firstQuery, float maxDivergence, fg_
     }
     last.offsets = ctx->resOffsets.data();
     *result = last;
+    // from now on the queries from firstQuery on stand under the new threshold
+    if (ctx->lastQueryMaxDivergence.empty()) ctx->lastQueryMaxDivergence.assign(nQ, ctx->lastMaxDivergence);
+    for (uint32_t q = firstQuery; q < nQ; ++q) ctx->lastQueryMaxDivergence[q] = maxDivergence;
 }
 
 }  // namespace fg

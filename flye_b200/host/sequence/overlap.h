@@ -9,6 +9,7 @@
 #include <memory>
 #include <mutex>
 #include <sstream>
+#include <thread>
 #include <unordered_map>
 #include <unordered_set>
 #include <vector>
@@ -135,6 +136,12 @@ private:
     }
 };
 
+// KSW2 trimming of a primary overlap that failed the divergence test (_partitionBadMappings, overlap.cpp:475-485).  The
+// function is the reference's own (alignment.cpp:306-495, with lib/minimap2's ksw2): inside flye-modules it is linked in as
+// before; a stand-alone build that never sets partitionBadMappings does not need it (weak reference).
+std::vector<OverlapRange> checkIdyAndTrim(OverlapRange& ovlp, const DnaSequence& curSeq, const DnaSequence& extSeq, float maxDivergence,
+                                          int32_t minOverlap, bool useHpc) __attribute__((weak));
+
 struct OvlpDivStats {
     static const size_t MAX_STATS = 1000000;
     OvlpDivStats() : divVec(MAX_STATS), vecSize(0) {}
@@ -154,7 +161,8 @@ public:
           _keepAlignment(keepAlignment), _onlyMaxExt(onlyMaxExt), _nuclAlignment(nuclAlignment),
           _partitionBadMappings(partitionBadMappings), _useHpc(useHpc), _maxDivergence(maxDivergence), _vertexIndex(vertexIndex),
           _seqContainer(seqContainer) {
-        if (partitionBadMappings) throw std::runtime_error("flye_b200: partitionBadMappings (KSW2 trimming) is not on the device path yet");
+        if (partitionBadMappings && !checkIdyAndTrim)
+            throw std::runtime_error("flye_b200: partitionBadMappings needs the reference's alignment.cpp (checkIdyAndTrim) linked in");
     }
     friend class OverlapContainer;
 
@@ -178,12 +186,15 @@ private:
         p.max_jump = _maxJump; p.min_overlap = _minOverlap; p.max_overhang = _maxOverhang; p.max_overlaps = maxOverlaps;
         p.force_local = forceLocal; p.keep_alignment = _keepAlignment; p.only_max_ext = _onlyMaxExt; p.nucl_alignment = _nuclAlignment;
         p.use_hpc = _useHpc; p.max_divergence = _maxDivergence;
+        p.keep_rejected = _partitionBadMappings;   // the primary overlaps that fail the test come back flagged and are trimmed below
         // results live in library memory until the next call: copy out under the lock
         std::lock_guard<std::mutex> lock(batchMutex());
         if (!sameSet) dev->uploadQueries(*queryContainer);
         fg_overlap_result res;
         dev->check(fg_overlaps_batch(dev->ctx, ids.data(), (uint32_t)ids.size(), &p, &res));
         std::vector<std::vector<OverlapRange>> out(queries.size());
+        struct Rejected { size_t q, at; OverlapRange ovlp; Rejected(size_t q, size_t at, OverlapRange&& o) : q(q), at(at), ovlp(std::move(o)) {} };
+        std::vector<Rejected> rejected;
         for (size_t q = 0; q < queries.size(); ++q) {
             out[q].reserve(res.offsets[q + 1] - res.offsets[q]);
             for (uint64_t i = res.offsets[q]; i < res.offsets[q + 1]; ++i) {
@@ -196,15 +207,40 @@ private:
                     for (uint64_t a = o.aln_first; a < o.aln_first + o.aln_count; ++a)
                         r.kmerMatches->emplace_back(res.aln_pairs[2 * a], res.aln_pairs[2 * a + 1]);
                 }
+                if (o.reserved & 1u) {   // failed the divergence test: its parts may pass (overlap.cpp:475-485); host side, the reference's KSW2
+                    rejected.emplace_back(q, out[q].size(), std::move(r));
+                    continue;
+                }
                 out[q].push_back(std::move(r));
             }
-            // per-10kb-window divergence statistics (overlap.cpp:488-506)
+            // per-10kb-window divergence statistics (overlap.cpp:488-506).  The reference records every PRIMARY overlap before the
+            // divergence test; the device only returns the rejected ones when asked to (keep_rejected, i.e. partitionBadMappings),
+            // so otherwise the logged quantiles (overlapDivergenceStats) are those of the kept overlaps — results are unaffected
             const int STAT_WND = 10000;
             if (!out[q].empty()) {
                 std::vector<const OverlapRange*> wnd(out[q].front().curLen / STAT_WND + 1, nullptr);
                 for (const auto& r : out[q]) { auto& w = wnd[r.curBegin / STAT_WND]; if (!w || r.curRange() > w->curRange()) w = &r; }
                 for (auto* w : wnd) if (w && w->curRange() > 0) divStats.add(w->seqDivergence);
             }
+        }
+        if (!rejected.empty()) {
+            // KSW2 trimming on the host, in parallel; the pieces take the place of the rejected overlap in its query's list
+            std::vector<std::vector<OverlapRange>> pieces(rejected.size());
+            std::atomic<size_t> next(0);
+            auto work = [&]() {
+                for (size_t i; (i = next.fetch_add(1)) < rejected.size();) {
+                    Rejected& r = rejected[i];
+                    pieces[i] = checkIdyAndTrim(r.ovlp, queryContainer->getSeq(r.ovlp.curId), _seqContainer.getSeq(r.ovlp.extId), _maxDivergence,
+                                                _minOverlap, _useHpc);
+                }
+            };
+            std::vector<std::thread> pool;
+            const size_t nThreads = std::min<size_t>(std::max<size_t>(1, Parameters::get().numThreads), rejected.size());
+            for (size_t t = 1; t < nThreads; ++t) pool.emplace_back(work);
+            work();
+            for (auto& t : pool) t.join();
+            for (size_t i = rejected.size(); i-- > 0;)   // back to front: the insertion points of earlier ones stay valid
+                out[rejected[i].q].insert(out[rejected[i].q].begin() + rejected[i].at, pieces[i].begin(), pieces[i].end());
         }
         return out;
     }
@@ -231,7 +267,11 @@ public:
         bool cached, suggestChimeric;
     };
 
-    // thread safe: computes (one device call) and caches on first use; both strands are stored (overlap.cpp:528-574)
+    // thread safe: computes and caches on first use; both strands are stored (overlap.cpp:528-574).  The callers ask for one
+    // read at a time from many threads (extender.cpp:32,44,98,244,339; chimera.cpp:77), the device wants batches: the FIRST miss
+    // computes the overlaps of every forward read of the query container in one device pass (exactly what the reference's cache
+    // holds once every read has been asked for: getSeqOverlaps(read, forceLocal = false, maxOverlaps = 0) under the detector's
+    // current threshold), later calls are cache hits.  FLYE_B200_LAZY_PREFETCH=0 restores one device pass per miss.
     const std::vector<OverlapRange>& lazySeqOverlaps(FastaRecord::Id readId) {
         const bool flipped = !readId.strand();
         if (flipped) readId = readId.rc();
@@ -239,6 +279,16 @@ public:
             std::lock_guard<std::mutex> lock(_cacheMutex);
             auto it = _overlapIndex.find(readId);
             if (it != _overlapIndex.end() && it->second.cached) return flipped ? *it->second.revOverlaps : *it->second.fwdOverlaps;
+        }
+        static const bool prefetchAll = !(getenv("FLYE_B200_LAZY_PREFETCH") && atoi(getenv("FLYE_B200_LAZY_PREFETCH")) == 0);
+        if (prefetchAll) {
+            std::lock_guard<std::mutex> once(_prefetchMutex);   // the threads that missed meanwhile wait here and then find their read cached
+            if (!_prefetchedAll) {
+                std::vector<FastaRecord::Id> all;
+                for (const auto& seq : _queryContainer.iterSeqs()) if (seq.id.strand()) all.push_back(seq.id);
+                prefetch(all);
+                _prefetchedAll = true;
+            }
         }
         prefetch({readId});
         std::lock_guard<std::mutex> lock(_cacheMutex);
@@ -386,7 +436,8 @@ private:
     const OverlapDetector& _ovlpDetect;
     const SequenceContainer& _queryContainer;
     OvlpDivStats _divergenceStats;
-    std::mutex _cacheMutex;
+    std::mutex _cacheMutex, _prefetchMutex;
+    bool _prefetchedAll = false;
     std::unordered_map<FastaRecord::Id, IndexVecWrapper> _overlapIndex;
     std::atomic<size_t> _indexSize;
     std::unordered_map<FastaRecord::Id, IntervalTree<const OverlapRange*>> _ovlpTree;

@@ -120,6 +120,10 @@ typedef struct {
                                           overlap.cpp:744-790) can then share a batch with the thresholded main pass.  With
                                           nucl_alignment the threshold also bounds the edit-distance work: an overlap that
                                           cannot pass it (overlap.cpp:470-473) is dropped without finishing its alignment */
+    int32_t keep_rejected;        /* _partitionBadMappings support: primary overlaps that FAIL the divergence test are returned too,
+                                     in the reference's order, with fg_overlap.reserved = 1 — the caller hands them to
+                                     checkIdyAndTrim (overlap.cpp:475-485, alignment.cpp:306-495).  Needs max_overlaps = 0 */
+    int32_t pad_;
 } fg_overlap_params;
 
 typedef struct {                  /* OverlapRange (overlap.h:20-279) plus what seqDivergence is made of  */
@@ -133,7 +137,7 @@ typedef struct {                  /* OverlapRange (overlap.h:20-279) plus what s
     int32_t  aln_len;             /* max(len(HPC cur), len(HPC ext)), 0 unless nucl_alignment            */
     uint64_t aln_first;           /* keep_alignment: index of first kmerMatches pair, count in aln_count  */
     uint32_t aln_count;
-    uint32_t reserved;
+    uint32_t reserved;            /* 0; 1 = failed the divergence test, returned because keep_rejected was set */
 } fg_overlap;
 
 typedef struct {
@@ -155,7 +159,9 @@ int fg_overlaps_batch(fg_ctx* ctx, const uint32_t* query_ids, uint32_t n_queries
  * threshold to the overlaps of the LAST fg_overlaps_batch on this ctx — records of the queries [first_query, n_queries) with
  * seq_divergence >= max_divergence are removed (queries before first_query, the estimate sample, stay as they are).
  * `result` is refreshed (same lifetime rules).  Presets with a RELATIVE threshold (asm_raw_reads) only know it after the
- * sample; this keeps the sample and the main pass in one device batch. */
+ * sample; this keeps the sample and the main pass in one device batch.
+ * Only a threshold at most as large as the one the batch was computed with can be applied, and only to a batch run with
+ * max_overlaps = 0 (FG_ERR_ARG otherwise): records the batch dropped are gone. */
 int fg_overlaps_refilter(fg_ctx* ctx, uint32_t first_query, float max_divergence, fg_overlap_result* result);
 
 /* ---- multi-GPU (one context per rank; reads are partitioned, the index replicated) ------- */

@@ -41,6 +41,7 @@ struct Args {
     int k = -1, threads = 1, minOverlap = 1000, maxOverlaps = 0, minReadLen = -1;
     bool forceLocal = false, dumpIndex = false, bothStrands = false, noEstimate = false;
     bool findAll = false, noOverlaps = false, keepAln = false, allExt = false;
+    bool lazy = false, perRead = false;
     long maxQueries = -1;
 };
 
@@ -48,7 +49,7 @@ static void usage() {
     fprintf(stderr,
         "harness --reads F --cfg C --out PREFIX [--k K] [--threads T] [--min-overlap M]\n"
         "        [--max-overlaps N] [--force-local] [--dump-index] [--both-strands]\n"
-        "        [--no-estimate] [--find-all] [--no-overlaps] [--max-queries N] [--all-ext]\n");
+        "        [--no-estimate] [--find-all] [--no-overlaps] [--max-queries N] [--all-ext] [--lazy] [--per-read]\n");
 }
 
 static uint32_t idNum(FastaRecord::Id id) {
@@ -84,6 +85,8 @@ int main(int argc, char** argv) {
         else if (s == "--no-overlaps") a.noOverlaps = true;
         else if (s == "--keep-aln") a.keepAln = true;
         else if (s == "--all-ext") a.allExt = true;
+        else if (s == "--lazy") a.lazy = true;          // lazySeqOverlaps(id) from --threads worker threads (how extender.cpp calls it)
+        else if (s == "--per-read") a.perRead = true;   // one quickSeqOverlaps call per read from --threads threads, also on the mirror
         else { usage(); return 1; }
     }
     if (a.reads.empty() || a.cfg.empty() || a.out.empty()) { usage(); return 1; }
@@ -196,15 +199,18 @@ int main(int argc, char** argv) {
         } else {
             std::vector<std::vector<OverlapRange>> results(queries.size());
             t0 = now();
-#ifdef FLYE_B200
-            // the mirror's batch entry (same results as N quickSeqOverlaps calls, one device pass)
-            results = container.quickSeqOverlapsBatch(queries, a.maxOverlaps, a.forceLocal);
-#else
             std::vector<size_t> order(queries.size());
             for (size_t i = 0; i < order.size(); ++i) order[i] = i;
             std::function<void(const size_t&)> work = [&](const size_t& i) {
-                results[i] = container.quickSeqOverlaps(queries[i], a.maxOverlaps, a.forceLocal);
+                if (a.lazy) results[i] = container.lazySeqOverlaps(queries[i]);   // thread safe, cached (overlap.h:397-411)
+                else results[i] = container.quickSeqOverlaps(queries[i], a.maxOverlaps, a.forceLocal);
             };
+#ifdef FLYE_B200
+            // the mirror's batch entry (same results as N quickSeqOverlaps calls, one device pass) unless the per-read
+            // calling pattern itself is what is being tested
+            if (!a.lazy && !a.perRead) results = container.quickSeqOverlapsBatch(queries, a.maxOverlaps, a.forceLocal);
+            else processInParallel(order, work, Parameters::get().numThreads, false);
+#else
             processInParallel(order, work, Parameters::get().numThreads, false);
 #endif
             tOverlaps = now() - t0;

@@ -165,3 +165,9 @@ def test_refilter_equals_thresholded_run(engine, tmp_path):
         assert np.array_equal(got, want), i
     off_r2, ov_r2 = engine.refilter(0, thr, len(q), copy=True)     # a second refilter works on the refreshed result
     assert np.array_equal(off_r2, off_b) and np.array_equal(ov_r2, ov_b)
+    # only tightening is possible: the records a batch (or an earlier refilter) dropped are gone
+    with pytest.raises(fb.FlyeB200Error, match="looser"):
+        engine.refilter(0, 2 * thr, len(q))
+    engine.overlaps(q, max_divergence=1.0, max_overlaps=3, copy=False, **common)
+    with pytest.raises(fb.FlyeB200Error, match="max_overlaps"):
+        engine.refilter(0, thr, len(q))

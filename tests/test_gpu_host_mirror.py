@@ -15,11 +15,11 @@ RAW = os.path.join(pu.CFG_DIR, "raw_reads.cfg")
 HIFI = os.path.join(pu.CFG_DIR, "hifi.cfg")
 
 
-def run_mirror(reads, cfg, out, k=None, extra=()):
+def run_mirror(reads, cfg, out, k=None, extra=(), threads=4):
     if not os.path.exists(MIRROR):
         from flye_b200 import build
         build.build_host_harness()
-    cmd = [MIRROR, "--reads", reads, "--cfg", cfg, "--out", out, "--threads", "4"] + (["--k", str(k)] if k else []) + list(extra)
+    cmd = [MIRROR, "--reads", reads, "--cfg", cfg, "--out", out, "--threads", str(threads)] + (["--k", str(k)] if k else []) + list(extra)
     r = subprocess.run(cmd, check=True, stdout=subprocess.PIPE, text=True)
     return json.loads(r.stdout.strip().splitlines()[-1])
 
@@ -39,6 +39,20 @@ def test_reference_harness_source_runs_on_the_mirror(built, tmp_path, cfg, k, si
     for ext in exts:
         n, sample = pu.diff_files(os.path.join(tmp, "ref." + ext), os.path.join(tmp, "gpu." + ext))
         assert n == 0, (ext, sample[:3])
+
+
+@pytest.mark.parametrize("mode", ["--lazy", "--per-read"])
+def test_on_demand_calls_from_many_threads(built, tmp_path, mode):
+    """how extender.cpp / chimera.cpp really call the path: one read per call — lazySeqOverlaps (thread safe, cached; the mirror
+    fills its cache for all reads on the first miss) or quickSeqOverlaps — from 8 worker threads at once"""
+    tmp = str(tmp_path)
+    reads = pu.simulate(os.path.join(tmp, "r.fasta"), genome_len=70000, coverage=10, seed=45)
+    opts = [mode] + (["--both-strands"] if mode == "--lazy" else [])
+    ref = pu.run_oracle(reads, RAW, os.path.join(tmp, "ref"), k=15, threads=8, extra=opts)
+    got = run_mirror(reads, RAW, os.path.join(tmp, "gpu"), k=15, extra=opts, threads=8)
+    assert got["overlaps"] == ref["overlaps"] and ref["overlaps"] > 100
+    n, sample = pu.diff_files(os.path.join(tmp, "ref.ovlp"), os.path.join(tmp, "gpu.ovlp"))
+    assert n == 0, sample[:3]
 
 
 def test_queries_from_a_second_container(built, tmp_path):

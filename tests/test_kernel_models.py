@@ -33,3 +33,12 @@ def test_segmented_radix_sort_model_is_the_stable_sort_by_target(built):
     r = subprocess.run([os.path.join(BIN, "segsort_check"), "1200", "29"], stdout=subprocess.PIPE, text=True, timeout=600)
     assert r.returncode == 0 and r.stdout.startswith("OK"), r.stdout
     assert int(r.stdout.split("tieFree=")[1]) > 100
+
+
+def test_dense_kmer_class_index_is_a_bijection_onto_the_canonical_kmers(built):
+    """denseIndexFromWindow / denseIndexOfPair / canonFromDenseIndex (kmer_math.cuh), the addressing of the counting kernels
+    (count_index.cu): both strands of a k-mer share one index below the array size, the index maps back to Kmer::standardForm's
+    canonical k-mer, classes never collide (exhaustive for k <= 9, sampled up to k = 17), and the multi-GPU owner / slot split
+    (index % N, index / N) is a bijection with 32-bit slots."""
+    r = subprocess.run([os.path.join(BIN, "dense_check")], stdout=subprocess.PIPE, text=True, timeout=600)
+    assert r.returncode == 0 and r.stdout.strip() == "ok", r.stdout
