@@ -21,7 +21,7 @@ ERR_NAMES = {-1: "FG_ERR_CUDA", -2: "FG_ERR_ARG", -3: "FG_ERR_KMER_SIZE", -4: "F
 SYMBOLS = ["fg_ctx_create", "fg_ctx_destroy", "fg_last_error", "fg_stream", "fg_kernel_launches", "fg_last_timings",
            "fg_reads_upload", "fg_reads_upload_ascii", "fg_queries_upload", "fg_count_kmers", "fg_kmer_hist", "fg_kmer_freq",
            "fg_build_index_solid", "fg_build_index_minimizers", "fg_index_clear", "fg_index_lookup",
-           "fg_index_positions", "fg_index_export", "fg_overlaps_batch", "fg_overlaps_refilter", "fg_comm_unique_id", "fg_comm_init",
+           "fg_index_positions", "fg_index_export", "fg_overlaps_batch", "fg_overlaps_refilter", "fg_overlaps_closure", "fg_comm_unique_id", "fg_comm_init",
            "fg_comm_set_shard", "fg_debug_int_peak", "fg_debug_warp_sort", "fg_debug_edit_distance", "fg_debug_edit_distance_rc"]
 
 
@@ -89,6 +89,7 @@ def load_lib():
     lib.fg_index_export.argtypes = [vp, u64p, u8p, u64p, u32p, u64p, u32p, i32p, u64p]
     lib.fg_overlaps_batch.argtypes = [vp, u32p, C.c_uint32, C.POINTER(OverlapParams), C.POINTER(OverlapResult)]
     lib.fg_overlaps_refilter.argtypes = [vp, C.c_uint32, C.c_float, C.POINTER(OverlapResult)]
+    lib.fg_overlaps_closure.argtypes = [vp, C.c_void_p, C.c_uint64, C.c_uint32, C.c_int32, C.POINTER(OverlapResult)]
     lib.fg_comm_unique_id.argtypes = [u8p]
     lib.fg_comm_init.argtypes = [vp, C.c_int, C.c_int, u8p]
     lib.fg_comm_set_shard.argtypes = [vp, C.c_uint32, C.c_uint32]
@@ -298,6 +299,20 @@ class Engine:
         else:
             ov = np.zeros(0, dtype=OVERLAP_DTYPE)
         return (offsets.copy(), ov.copy()) if copy else (offsets, ov)
+
+    def closure(self, records, n_seqs, max_ends_diff):
+        """fg_overlaps_closure: symmetric closure + cluster filter of forward-sequence overlap records -> (offsets, records)"""
+        recs = np.ascontiguousarray(records, dtype=OVERLAP_DTYPE)
+        res = OverlapResult()
+        self._check(self.lib.fg_overlaps_closure(self.ctx, recs.ctypes.data_as(C.c_void_p), len(recs), n_seqs, max_ends_diff, C.byref(res)))
+        offsets = np.ctypeslib.as_array(res.offsets, shape=(n_seqs + 1,)).copy()
+        n = int(offsets[-1])
+        if n:
+            buf = (C.c_char * (n * OVERLAP_DTYPE.itemsize)).from_address(res.overlaps)
+            ov = np.frombuffer(buf, dtype=OVERLAP_DTYPE, count=n).copy()
+        else:
+            ov = np.zeros(0, dtype=OVERLAP_DTYPE)
+        return offsets, ov
 
     # ---- multi-GPU ----
     @staticmethod

@@ -17,7 +17,7 @@ BUILD = os.path.join(ROOT, "build")
 LIB = os.path.join(ROOT, "flye_b200", "libflye_b200.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Wno-deprecated-declarations"]
-SOURCES = ["api.cu", "count_index.cu", "overlap.cu", "editdist.cu", "comm.cu", "intpeak.cu"]
+SOURCES = ["api.cu", "count_index.cu", "overlap.cu", "editdist.cu", "comm.cu", "intpeak.cu", "closure.cu"]
 
 
 def _run(cmd, **kw):

@@ -92,10 +92,23 @@ int fg_ctx_create(int device, fg_ctx** out) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0 || device < 0 || device >= n) return FG_ERR_CUDA;   // no CPU fallback
     if (cudaSetDevice(device) != cudaSuccess) return FG_ERR_CUDA;
+    // FG_L2_FETCH=32|64|128: L2 fetch granularity hint
+    {
+        const char* e = getenv("FG_L2_FETCH");
+        const size_t g = e ? (size_t)atoi(e) : 0;   // (measured: no effect on these kernels on B200 — a DRAM access moves ~128 B either way; left as a switch)
+        if (g == 32 || g == 64 || g == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, g);
+        cudaGetLastError();
+    }
     fg_ctx* ctx = new fg_ctx();
     ctx->device = device;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return FG_ERR_CUDA; }
 
+    // an allocation of the context's own arena that fails makes the lanes give their cached workspaces back (they are idle
+    // outside fg_overlaps_batch)
+    ctx->arena.onPressure = [ctx] {
+        std::lock_guard<std::mutex> lk(ctx->pressureMutex);
+        for (auto& l : ctx->lanes) l->arena.trim();
+    };
     *out = ctx;
     return FG_OK;
 }
@@ -251,7 +264,7 @@ int fg_build_index_minimizers(fg_ctx* ctx, int k, int minCov, int window, float 
 int fg_index_clear(fg_ctx* ctx) {
     return guarded(ctx, [&] {
         ctx->dEntries.release(); ctx->dIndexSlots.release(); ctx->dUKeys.release(); ctx->dUPayload.release();
-        ctx->dCountSlots.release(); ctx->dDense.release(); ctx->counts = fg::CountView{}; ctx->dSelBits.release();
+        ctx->dCountSlots.release(); ctx->dDense.release(); ctx->dSolidBits.release(); ctx->dIdxBits.release(); ctx->counts = fg::CountView{}; ctx->dSelBits.release();
         ctx->indexed = false; ctx->counted = false;
     });
 }
@@ -333,6 +346,13 @@ int fg_overlaps_refilter(fg_ctx* ctx, uint32_t firstQuery, float maxDivergence, 
     return guarded(ctx, [&] {
         if (!result) throw Error(FG_ERR_ARG, "null argument");
         fg::overlapsRefilter(ctx, firstQuery, maxDivergence, result);
+    });
+}
+
+int fg_overlaps_closure(fg_ctx* ctx, const fg_overlap* records, uint64_t n, uint32_t nSeqs, int32_t maxEndsDiff, fg_overlap_result* result) {
+    return guarded(ctx, [&] {
+        if (!result || (n && !records)) throw Error(FG_ERR_ARG, "null argument");
+        fg::overlapsClosure(ctx, records, n, nSeqs, maxEndsDiff, result);
     });
 }
 

@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cstring>
+#include <functional>
 #include <mutex>
 #include <stdexcept>
 #include <string>
@@ -43,6 +44,7 @@ struct Arena {
     std::vector<Block> blocks;
     size_t totalBytes = 0;
     uint64_t mallocCalls = 0;
+    std::function<void()> onPressure;   // frees what OTHER arenas of the context have cached (set by the context)
     // size classes {1, 1.25, 1.5, 1.75} * 2^k (>= 256 KiB): a request only ever reuses a block of its own class, so
     // a phase that issues the same request sequence every step hits the cache on every request from step 2 on
     static size_t sizeClass(size_t bytes) {
@@ -62,10 +64,11 @@ struct Arena {
         void* p = nullptr;
         cudaError_t e = cudaMalloc(&p, want);
         ++mallocCalls;
-        if (e != cudaSuccess) {   // give cached blocks back and retry once
+        if (e != cudaSuccess) {   // give cached blocks back (this arena's, then the context's other arenas') and retry once
             cudaGetLastError();
             trim();
             e = cudaMalloc(&p, want);
+            if (e != cudaSuccess && onPressure) { cudaGetLastError(); onPressure(); e = cudaMalloc(&p, want); }
             if (e != cudaSuccess)
                 throw Error(FG_ERR_CUDA, std::string("cudaMalloc of ") + std::to_string(want) + " bytes failed: " + cudaGetErrorString(e));
         }
@@ -197,13 +200,19 @@ __device__ inline void tableAddOne(const Table& t, uint64_t key) {
 // replicated table of the k-mers with count >= 2 (absent == 1).  Dense index: see count_index.cu.
 struct CountView {
     const uint32_t* dense = nullptr;
+    const uint32_t* solidBits = nullptr;   // optional front of `dense`: bit i set <=> class i occurs at least twice; dense then holds count - 1
     Table table;
     int k = 0;
 };
+__device__ __forceinline__ bool testBit(const uint32_t* __restrict__ bits, uint64_t i) { return (__ldg(&bits[i >> 5]) >> (i & 31)) & 1u; }
 // count of the class of the k-mer given as its 2k-bit window `v` (base p in the lowest bits) ...
 __device__ inline uint32_t countOfWindow(const CountView& c, uint64_t v) {
     const uint64_t f = fwdFromWindow(v, c.k), r = (~v) & kmerMask(c.k);
-    if (c.dense) return c.dense[denseIndexOfPair(f, r, c.k)];
+    if (c.dense) {
+        const uint64_t i = denseIndexOfPair(f, r, c.k);
+        if (!c.solidBits) return c.dense[i];
+        return testBit(c.solidBits, i) ? c.dense[i] + 1u : 1u;   // most positions of noisy reads are singletons: answered from the L2-resident bitmap
+    }
     uint64_t payload;
     return tableFind(c.table, f < r ? f : r, payload) ? (uint32_t)payload : 1u;
 }
@@ -211,7 +220,11 @@ __device__ inline uint32_t countOfWindow(const CountView& c, uint64_t v) {
 // form and 0 from the dense form — callers only ask for k-mers that occur
 __device__ inline uint32_t countOfKmer(const CountView& c, uint64_t kmer) {
     const uint64_t r = revCompKmer(kmer, c.k);
-    if (c.dense) return c.dense[denseIndexOfPair(kmer, r, c.k)];
+    if (c.dense) {
+        const uint64_t i = denseIndexOfPair(kmer, r, c.k);
+        if (!c.solidBits) return c.dense[i];
+        return testBit(c.solidBits, i) ? c.dense[i] + 1u : 1u;
+    }
     uint64_t payload;
     return tableFind(c.table, kmer < r ? kmer : r, payload) ? (uint32_t)payload : 1u;
 }

@@ -87,6 +87,7 @@ static void tileRange(const fg_ctx* ctx, uint32_t first, uint32_t count, size_t&
 // all-gathered so that every rank holds the complete count table (absent == 1) that the per-read selection probes.
 // ------------------------------------------------------------------------------------------------
 static constexpr int MAX_RANKS = 64;
+static bool envInt01(const char* name, int dflt) { const char* e = getenv(name); return (e ? atoi(e) : dflt) != 0; }
 
 struct DenseMap {
     int k;
@@ -100,11 +101,22 @@ __device__ __forceinline__ void ownerOf(const DenseMap& m, uint64_t idx, uint32_
     else { local = idx / m.nOwners; owner = (uint32_t)(idx - local * m.nOwners); }
 }
 
+// One occurrence of class i.  With the "seen" bitmap (1 bit per class, L2-resident: 64 MB for k = 15) the FIRST occurrence only sets
+// its bit — an atomic that never leaves the L2 — and the counter array in HBM holds count - 1: the singletons, more than half of the
+// positions of a noisy read set, cost no DRAM traffic at all (a RED on a counter that misses the L2 moves ~100 B).
+__device__ __forceinline__ void countOne(uint64_t i, uint32_t* __restrict__ dense, uint32_t* __restrict__ seenBits) {
+    if (seenBits) {
+        const uint32_t bit = 1u << (i & 31);
+        if (!(atomicOr(&seenBits[i >> 5], bit) & bit)) return;
+    }
+    atomicAdd(&dense[i], 1u);
+}
+
 // single GPU: one CTA per tile of <= 2048 positions of one read; the tile's packed words are staged in shared memory,
 // every position becomes one RED.ADD.U32 on its class counter
 __global__ void __launch_bounds__(256) denseCountKernel(const uint64_t* __restrict__ seq, const uint64_t* __restrict__ wordOff,
                                                         const uint32_t* __restrict__ len, const uint2* __restrict__ tiles, int k,
-                                                        uint32_t* __restrict__ dense) {
+                                                        uint32_t* __restrict__ dense, uint32_t* __restrict__ seenBits) {
     __shared__ uint64_t sw[TILE_SLOTS / 32 + 4];
     const uint2 t = tiles[blockIdx.x];
     const uint32_t L = len[t.x], n = L - k, p0 = t.y;
@@ -114,8 +126,7 @@ __global__ void __launch_bounds__(256) denseCountKernel(const uint64_t* __restri
     for (uint32_t i = threadIdx.x; i < nw; i += blockDim.x) sw[i] = words[w0 + i];
     if (threadIdx.x == 0) sw[nw] = 0;
     __syncthreads();
-    for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x)
-        atomicAdd(&dense[denseIndexFromWindow(windowAt(sw, (p0 & 31) + i, k), k)], 1u);
+    for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) countOne(denseIndexFromWindow(windowAt(sw, (p0 & 31) + i, k), k), dense, seenBits);
 }
 
 // multi-GPU pass A: how many positions of this rank's tiles belong to every owner
@@ -184,36 +195,43 @@ __global__ void __launch_bounds__(256) ownerScatterKernel(const uint64_t* __rest
         if (own[j] != 0xffffffffu) sendBuf[base[own[j]] + rk[j]] = slot[j];
 }
 
-__global__ void __launch_bounds__(256) denseCountListKernel(const uint32_t* __restrict__ slots, uint64_t n, uint32_t* __restrict__ dense) {
+__global__ void __launch_bounds__(256) denseCountListKernel(const uint32_t* __restrict__ slots, uint64_t n, uint32_t* __restrict__ dense,
+                                                            uint32_t* __restrict__ seenBits) {
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
-        atomicAdd(&dense[slots[i]], 1u);
+        countOne(slots[i], dense, seenBits);
 }
 
 // scan of the counters, pass 1: freq -> #k-mers histogram (vertex_index.cpp:567-576; shared-memory privatised low bins, global
 // atomics above, overflow list beyond 2^16), number of distinct k-mers (hist[0]) and of k-mers with count >= 2 (*nSolid)
 static constexpr int HIST_SMEM_BINS = 1024;
 static constexpr int HIST_GLOBAL_BINS = 1 << 16;
-__global__ void __launch_bounds__(256) denseHistKernel(const uint4* __restrict__ dense4, uint64_t n4, unsigned long long* __restrict__ hist,
+__global__ void __launch_bounds__(256) denseHistKernel(const uint4* __restrict__ dense4, uint64_t n8, const uint8_t* __restrict__ seenBytes,
+                                                       uint8_t* __restrict__ solidBytes, unsigned long long* __restrict__ hist,
                                                        uint32_t* __restrict__ overflow, uint32_t* __restrict__ nOverflow, uint32_t overflowCap,
                                                        unsigned long long* __restrict__ nSolid) {
     __shared__ uint32_t sh[HIST_SMEM_BINS];
     for (int i = threadIdx.x; i < HIST_SMEM_BINS; i += blockDim.x) sh[i] = 0;
     __syncthreads();
     uint32_t distinct = 0, solid = 0;
-    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n4; i += (uint64_t)gridDim.x * blockDim.x) {
-        const uint4 q = dense4[i];
-        if ((q.x | q.y | q.z | q.w) == 0u) continue;
-        const uint32_t cs[4] = {q.x, q.y, q.z, q.w};
+    // one step = 8 consecutive counters = one byte of either bitmap
+    for (uint64_t g = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; g < n8; g += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t seen = seenBytes ? seenBytes[g] : 0u;
+        uint32_t solidByte = 0;
+        if (seenBytes && !seen) { if (solidBytes) solidBytes[g] = 0; continue; }   // (a counter is only ever touched after its bit)
+        const uint4 q0 = dense4[2 * g], q1 = dense4[2 * g + 1];
+        const uint32_t cs[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const uint32_t c = cs[j];
+        for (int j = 0; j < 8; ++j) {
+            const uint32_t c = cs[j] + ((seen >> j) & 1u);   // with the bitmap the array holds count - 1
             if (!c) continue;
-            ++distinct; solid += c >= 2u;
+            ++distinct;
             if (c == 1u) continue;            // counted below as distinct - everything else
+            ++solid; solidByte |= 1u << j;
             if (c < HIST_SMEM_BINS) atomicAdd(&sh[c], 1u);
             else if (c < HIST_GLOBAL_BINS) atomicAdd(&hist[c], 1ULL);
             else { const uint32_t s = atomicAdd(nOverflow, 1u); if (s < overflowCap) overflow[s] = c; }
         }
+        if (solidBytes) solidBytes[g] = (uint8_t)solidByte;
     }
     __syncthreads();
     for (int i = threadIdx.x; i < HIST_SMEM_BINS; i += blockDim.x)
@@ -227,8 +245,8 @@ __global__ void __launch_bounds__(256) denseHistKernel(const uint4* __restrict__
 }
 
 // pass 2: (canonical k-mer, count) of every class with count >= 2, appended in no particular order (they go into a hash table)
-__global__ void __launch_bounds__(256) denseEmitKernel(const uint4* __restrict__ dense4, uint64_t n4, DenseMap m, uint64_t* __restrict__ keys,
-                                                       uint32_t* __restrict__ counts, unsigned long long* __restrict__ cursor) {
+__global__ void __launch_bounds__(256) denseEmitKernel(const uint4* __restrict__ dense4, uint64_t n4, const uint8_t* __restrict__ seenBytes, DenseMap m,
+                                                       uint64_t* __restrict__ keys, uint32_t* __restrict__ counts, unsigned long long* __restrict__ cursor) {
     const int lane = threadIdx.x & 31;
     // whole warps step together (the append is warp aggregated)
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
@@ -236,8 +254,9 @@ __global__ void __launch_bounds__(256) denseEmitKernel(const uint4* __restrict__
     uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     for (uint64_t it = 0; it < nIter; ++it, i += stride) {
         uint4 q = make_uint4(0, 0, 0, 0);
-        if (i < n4) q = dense4[i];
-        const uint32_t cs[4] = {q.x, q.y, q.z, q.w};
+        uint32_t seen = 0;
+        if (i < n4) { q = dense4[i]; if (seenBytes) seen = (seenBytes[i >> 1] >> ((i & 1) * 4)) & 15u; }
+        const uint32_t cs[4] = {q.x + (seen & 1u), q.y + ((seen >> 1) & 1u), q.z + ((seen >> 2) & 1u), q.w + ((seen >> 3) & 1u)};
         const uint32_t mine = (cs[0] >= 2u) + (cs[1] >= 2u) + (cs[2] >= 2u) + (cs[3] >= 2u);
         if (!__any_sync(0xffffffffu, mine != 0u)) continue;
         uint32_t incl = mine;
@@ -290,7 +309,7 @@ void countKmers(fg_ctx* ctx, int k) {
     const size_t nTiles = tHi - tLo;
     ctx->hist.clear();
     ctx->nDistinct = 0;
-    ctx->dCountSlots.release(); ctx->dDense.release();
+    ctx->dCountSlots.release(); ctx->dDense.release(); ctx->dSolidBits.release();
     ctx->counts = CountView{};
     // counting invalidates the index (setKmerSize): give its memory back before the counters are allocated
     ctx->dEntries.release(); ctx->dIndexSlots.release(); ctx->dUKeys.release(); ctx->dUPayload.release();
@@ -299,17 +318,24 @@ void countKmers(fg_ctx* ctx, int k) {
     m.ownerShift = 0xffffffffu;
     for (uint32_t s = 0; s < 31; ++s) if ((1u << s) == m.nOwners) m.ownerShift = s;
     // counters of this rank: slots of the classes i with i % nOwners == owner, padded to whole 16-byte groups
-    const uint64_t nLocal = ((denseSpace(k) + m.nOwners - 1) / m.nOwners + 3) & ~3ULL;
+    const uint64_t nLocal = ((denseSpace(k) + m.nOwners - 1) / m.nOwners + 31) & ~31ULL;
     DevBuf<uint32_t>& dense = ctx->dDense;
     dense.alloc(nLocal);
+    // bitmap fronts (see countOne): only while a bitmap fits the L2 comfortably (2^29 classes = 64 MB: k <= 15, or more ranks)
+    const bool front = nLocal <= (1ULL << 29) && envInt01("FG_COUNT_FRONT", 1);
+    DevBuf<uint32_t> seenBits;
+    ctx->dSolidBits.release();
+    if (front) { seenBits.alloc(nLocal / 32); ctx->dSolidBits.alloc(nLocal / 32); }
     {
         PhaseTimer pt(ctx, "count_clear");
         FG_CUDA(cudaMemsetAsync(dense.p, 0, nLocal * 4ULL, ctx->stream));
+        if (front) FG_CUDA(cudaMemsetAsync(seenBits.p, 0, nLocal / 8, ctx->stream));
     }
+    std::unique_ptr<L2Pin> pinSeen(front ? new L2Pin(ctx, seenBits.p, nLocal / 8) : nullptr);
     if (!multi) {
         PhaseTimer pt(ctx, "count");
         if (nTiles) {
-            denseCountKernel<<<(unsigned)nTiles, 256, 0, ctx->stream>>>(ctx->dSeq.p, ctx->dWordOff.p, ctx->dLen.p, ctx->dTiles.p + tLo, k, dense.p);
+            denseCountKernel<<<(unsigned)nTiles, 256, 0, ctx->stream>>>(ctx->dSeq.p, ctx->dWordOff.p, ctx->dLen.p, ctx->dTiles.p + tLo, k, dense.p, seenBits.p);
             checkLaunch(ctx, "denseCountKernel");
         }
     } else {
@@ -347,7 +373,7 @@ void countKmers(fg_ctx* ctx, int k) {
         PhaseTimer pt(ctx, "count");
         const uint64_t nRecv = recvOffs[R] / 4;
         if (nRecv) {
-            denseCountListKernel<<<gridFor(nRecv, 256, 16), 256, 0, ctx->stream>>>(recvBuf.p, nRecv, dense.p);
+            denseCountListKernel<<<gridFor(nRecv, 256, 16), 256, 0, ctx->stream>>>(recvBuf.p, nRecv, dense.p, seenBits.p);
             checkLaunch(ctx, "denseCountListKernel");
         }
     }
@@ -363,7 +389,10 @@ void countKmers(fg_ctx* ctx, int k) {
         FG_CUDA(cudaMemsetAsync(dHist.p, 0, dHist.bytes(), ctx->stream));
         FG_CUDA(cudaMemsetAsync(dNOv.p, 0, 4, ctx->stream));
         FG_CUDA(cudaMemsetAsync(dSolid.p, 0, 16, ctx->stream));
-        denseHistKernel<<<gridFor(nLocal / 4, 256, 16), 256, 0, ctx->stream>>>(reinterpret_cast<const uint4*>(dense.p), nLocal / 4, dHist.p, dOv.p, dNOv.p,
+        pinSeen.reset();
+        denseHistKernel<<<gridFor(nLocal / 8, 256, 16), 256, 0, ctx->stream>>>(reinterpret_cast<const uint4*>(dense.p), nLocal / 8,
+                                                                              reinterpret_cast<const uint8_t*>(seenBits.p),
+                                                                              reinterpret_cast<uint8_t*>(ctx->dSolidBits.p), dHist.p, dOv.p, dNOv.p,
                                                                               ovCap, dSolid.p);
         checkLaunch(ctx, "denseHistKernel");
         FG_CUDA(cudaMemcpyAsync(&hSolid, dSolid.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -375,7 +404,7 @@ void countKmers(fg_ctx* ctx, int k) {
     if (nOv) FG_CUDA(cudaMemcpyAsync(ov.data(), dOv.p, nOv * 4ULL, cudaMemcpyDeviceToHost, ctx->stream));
     if (!multi) {
         // one GPU: the counter array IS the count structure of the selection (no table, no second pass over the counters)
-        ctx->counts.dense = dense.p; ctx->counts.k = k;
+        ctx->counts.dense = dense.p; ctx->counts.solidBits = ctx->dSolidBits.p; ctx->counts.k = k;
     } else {
         // this rank's k-mers with count >= 2, all-gathered into the replicated table
         DevBuf<uint64_t> solidKeys(std::max<uint64_t>(hSolid, 1));
@@ -383,12 +412,13 @@ void countKmers(fg_ctx* ctx, int k) {
         {
             PhaseTimer pt(ctx, "count_emit");
             if (hSolid) {
-                denseEmitKernel<<<gridFor(nLocal / 4, 256, 16), 256, 0, ctx->stream>>>(reinterpret_cast<const uint4*>(dense.p), nLocal / 4, m, solidKeys.p,
+                denseEmitKernel<<<gridFor(nLocal / 4, 256, 16), 256, 0, ctx->stream>>>(reinterpret_cast<const uint4*>(dense.p), nLocal / 4,
+                                                                                      reinterpret_cast<const uint8_t*>(seenBits.p), m, solidKeys.p,
                                                                                       solidCounts.p, dSolid.p + 1);
                 checkLaunch(ctx, "denseEmitKernel");
             }
         }
-        dense.release();
+        dense.release(); ctx->dSolidBits.release();
         uint64_t nSolidAll = 0;
         DevBuf<uint64_t> allKeys; DevBuf<uint32_t> allCounts;
         {
@@ -942,6 +972,18 @@ __global__ void __launch_bounds__(256) insertIndexKernel(const uint64_t* __restr
         if (payload[i] != ~0ULL) tableInsertUnique(table, keys[i], payload[i]);
 }
 
+// presence bitmap of the index over the k-mer classes (dense index, kmer_math.cuh): set for every key the table holds (valid or
+// repetitive).  The queries look up ALL their k-mers, and in a noisy read set most of those are erroneous and absent: the
+// L2-resident bitmap answers them without a table probe in HBM (queryLookupKernel).
+__global__ void __launch_bounds__(256) indexBitsKernel(const uint64_t* __restrict__ keys, const uint64_t* __restrict__ payload, uint64_t n, int k,
+                                                       uint32_t* __restrict__ bits) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        if (payload[i] != ~0ULL) {
+            const uint64_t key = keys[i], d = denseIndexOfPair(key, revCompKmer(key, k), k);
+            atomicOr(&bits[d >> 5], 1u << (d & 31));
+        }
+}
+
 __global__ void __launch_bounds__(256) unpackEntriesKernel(const uint64_t* __restrict__ vals, uint64_t n, uint2* __restrict__ out) {
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         uint64_t v = vals[i];
@@ -1124,7 +1166,7 @@ static void buildFromSelection(fg_ctx* ctx, DevBuf<uint32_t>& rcBits, int minCov
         groupEnd();
         FG_CUDA(cudaStreamSynchronize(ctx->stream));
     }
-    ctx->dEntries.release(); ctx->dIndexSlots.release(); ctx->dUKeys.release(); ctx->dUPayload.release();
+    ctx->dEntries.release(); ctx->dIndexSlots.release(); ctx->dUKeys.release(); ctx->dUPayload.release(); ctx->dIdxBits.release();
     ctx->stats = fg_index_stats{};
     ctx->stats.sample_rate = sampleRateIn;
     ctx->nEntriesStored = 0; ctx->nUKeys = 0;
@@ -1206,7 +1248,7 @@ static void buildFromSelection(fg_ctx* ctx, DevBuf<uint32_t>& rcBits, int minCov
     FG_CUDA(cudaMemcpyAsync(hStats, dStats.p, 32, cudaMemcpyDeviceToHost, ctx->stream));
     FG_CUDA(cudaStreamSynchronize(ctx->stream));
     // the k-mer counters were last needed by the classification: large ones (k >= 16: 17 / 34 GB) go back before the table is built
-    if (ctx->dDense.bytes() > (4ULL << 30)) { ctx->dDense.release(); ctx->counts = CountView{}; }
+    if (ctx->dDense.bytes() > (4ULL << 30)) { ctx->dDense.release(); ctx->dSolidBits.release(); ctx->counts = CountView{}; }
     (ukeys == keysA.p ? keysA : keysB).release();
     starts.release();
     if (hStats[3]) throw Error(FG_ERR_TOO_FREQ, "k-mer is too frequent");   // (all ranks see the reduced flag: they throw together)
@@ -1228,9 +1270,18 @@ static void buildFromSelection(fg_ctx* ctx, DevBuf<uint32_t>& rcBits, int minCov
         curV.release();
     }
     ctx->indexTable = makeTable(ctx, ctx->dIndexSlots, Stotal);
+    ctx->dIdxBits.release();
+    if (denseSpace(k) <= (1ULL << 29) && envInt01("FG_INDEX_BITS", 1)) {   // 64 MB at most: stays in the L2 during the lookups
+        ctx->dIdxBits.alloc(denseSpace(k) / 32 + 1);
+        FG_CUDA(cudaMemsetAsync(ctx->dIdxBits.p, 0, ctx->dIdxBits.bytes(), ctx->stream));
+    }
     if (Stotal) {
         insertIndexKernel<<<gridFor(Stotal, 256, 16), 256, 0, ctx->stream>>>(ctx->dUKeys.p, ctx->dUPayload.p, Stotal, ctx->indexTable);
         checkLaunch(ctx, "insertIndexKernel");
+        if (ctx->dIdxBits.p) {
+            indexBitsKernel<<<gridFor(Stotal, 256, 16), 256, 0, ctx->stream>>>(ctx->dUKeys.p, ctx->dUPayload.p, Stotal, k, ctx->dIdxBits.p);
+            checkLaunch(ctx, "indexBitsKernel");
+        }
     }
     FG_CUDA(cudaStreamSynchronize(ctx->stream));
     ctx->nEntriesStored = Etotal;
@@ -1261,6 +1312,7 @@ void buildIndexSolid(fg_ctx* ctx, int minFreq, float selectRate, int tandemFreq,
     size_t tLo, tHi;
     tileRange(ctx, firstRead, nReadsShard, tLo, tHi);
     {
+        L2Pin pinSolid(ctx, ctx->dSolidBits.p, ctx->dSolidBits.bytes());   // the "count >= 2" bitmap answers most lookups: keep it in the L2
         PhaseTimer pt(ctx, "select");
         const uint64_t slotBase = ctx->hSlotOff[firstRead], shardSlots = ctx->hSlotOff[firstRead + nReadsShard] - slotBase;
         DevBuf<uint32_t> freq(std::max<uint64_t>(shardSlots, 1));

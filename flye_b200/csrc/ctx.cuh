@@ -124,6 +124,7 @@ struct fg_ctx {
     std::map<uint64_t, uint64_t> hist;    // freq -> #distinct canonical k-mers
     fg::DevBuf<ulonglong2> dCountSlots;   // multi-GPU: replicated table canonical k-mer -> count, only counts >= 2 (absent = 1)
     fg::DevBuf<uint32_t> dDense;          // one GPU: the dense counter array itself (count_index.cu), kept until the index is built
+    fg::DevBuf<uint32_t> dSolidBits;      // 1 bit per class: occurs at least twice (only while the bitmap fits the L2, k <= 15)
     fg::CountView counts;
 
     // ---- index ----
@@ -135,6 +136,7 @@ struct fg_ctx {
     uint64_t nEntriesStored = 0;
     fg::DevBuf<ulonglong2> dIndexSlots;
     fg::Table indexTable;
+    fg::DevBuf<uint32_t> dIdxBits;        // 1 bit per k-mer class: has an index entry or is repetitive (only while the bitmap fits the L2)
     // sorted unique keys with their class, for export / tests
     fg::DevBuf<uint64_t> dUKeys;
     fg::DevBuf<uint64_t> dUPayload;       // same encoding as the table payload; ~0 = not in index
@@ -152,6 +154,7 @@ struct fg_ctx {
     std::shared_mutex pinnedMutex;        // lanes copy into / work on their slice under a shared lock; growing the buffer takes it exclusively
     fg::HostPool hostPool;
     std::mutex hostPoolMutex;             // one parallelFor at a time (the lanes share the pool)
+    std::mutex pressureMutex;             // one arena at a time asks the others to give cached blocks back
     uint64_t hitBudget = 0;               // k-mer hits per sub-batch and lane, derived once from the free device memory
     // results after the divergence / maxOverlaps filter (when it removed something); two buffers: fg_overlaps_refilter
     // compacts from the one that holds the last result into the other
@@ -213,6 +216,38 @@ struct HostTimer {
     ~HostTimer() { addTiming(ctx, name, std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count()); }
 };
 
+// Keeps a small, randomly accessed structure (a presence bitmap) resident in the L2 while the kernels of the enclosing scope
+// stream gigabytes past it: persisting-L2 access policy window on the calling thread's stream (sm_80+).  Best effort.
+struct L2Pin {
+    cudaStream_t st; bool on = false;
+    L2Pin(const fg_ctx* ctx, const void* p, size_t bytes) : st(streamOf(ctx)) {
+        if (!p || !bytes) return;
+        int dev = 0, maxWin = 0, maxPersist = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&maxWin, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+        cudaDeviceGetAttribute(&maxPersist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+        if (maxWin <= 0 || maxPersist <= 0) { cudaGetLastError(); return; }
+        const size_t carve = std::min<size_t>((size_t)maxPersist, bytes);
+        if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve) != cudaSuccess) { cudaGetLastError(); return; }
+        cudaStreamAttrValue a{};
+        a.accessPolicyWindow.base_ptr = const_cast<void*>(p);
+        a.accessPolicyWindow.num_bytes = std::min<size_t>(bytes, (size_t)maxWin);
+        a.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)carve / (double)a.accessPolicyWindow.num_bytes);
+        a.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        a.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        on = cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &a) == cudaSuccess;
+        cudaGetLastError();
+    }
+    ~L2Pin() {
+        if (!on) return;
+        cudaStreamAttrValue a{};
+        a.accessPolicyWindow.num_bytes = 0;
+        cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &a);
+        cudaCtxResetPersistingL2Cache();
+        cudaGetLastError();
+    }
+};
+
 inline void checkLaunch(fg_ctx* ctx, const char* what) {
     ++ctx->launches;
     cudaError_t e = cudaGetLastError();
@@ -233,6 +268,7 @@ void buildIndexMinimizers(fg_ctx* ctx, int k, int minCov, int window, float repe
 void overlapsBatch(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQueries, const fg_overlap_params& p,
                    fg_overlap_result* result);
 void overlapsRefilter(fg_ctx* ctx, uint32_t firstQuery, float maxDivergence, fg_overlap_result* result);
+void overlapsClosure(fg_ctx* ctx, const fg_overlap* records, uint64_t n, uint32_t nSeqs, int maxEndsDiff, fg_overlap_result* result);
 
 // NCCL plumbing (comm.cu)
 void commUniqueId(uint8_t* id);

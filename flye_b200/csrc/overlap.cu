@@ -59,8 +59,8 @@ __global__ void __launch_bounds__(256) queryLookupKernel(const uint64_t* __restr
                                                          const uint32_t* __restrict__ len, const uint64_t* __restrict__ slotOff,
                                                          const uint32_t* __restrict__ selBits, const uint32_t* __restrict__ qIds,
                                                          const uint64_t* __restrict__ qSlotOff, const uint2* __restrict__ qTiles,
-                                                         int k, bool sameSet, Table index, uint32_t* __restrict__ hitCnt,
-                                                         uint64_t* __restrict__ slotInfo, uint32_t* __restrict__ filtBits) {
+                                                         int k, bool sameSet, Table index, const uint32_t* __restrict__ idxBits,
+                                                         uint32_t* __restrict__ hitCnt, uint64_t* __restrict__ slotInfo, uint32_t* __restrict__ filtBits) {
     const uint2 t = qTiles[blockIdx.x];
     const uint32_t id = qIds[t.x], r = id >> 1;
     const bool strand = id & 1;
@@ -84,7 +84,8 @@ __global__ void __launch_bounds__(256) queryLookupKernel(const uint64_t* __restr
             const uint64_t canon = flagQ ? qrc : qk;
             const bool fwdRc = rcv < f;
             uint64_t payload;
-            if (tableFind(index, canon, payload)) {
+            // (absent k-mers — most of a noisy read's — are answered by the L2-resident presence bitmap, without a probe in HBM)
+            if ((!idxBits || testBit(idxBits, denseIndexOfPair(f, rcv, k))) && tableFind(index, canon, payload)) {
                 const uint64_t size = payload & IDX_SIZE_MASK;
                 if (size == IDX_REPETITIVE) rep = true;
                 else {
@@ -1713,10 +1714,11 @@ static void overlapsChunk(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, ui
     if (!hQTiles.empty()) {
         if (nQSlots >= (1ULL << 31)) throw Error(FG_ERR_ARG, "query batch too large (>= 2^31 k-mer slots); split the call");
         {
+            L2Pin pinBits(ctx, ctx->dIdxBits.p, ctx->dIdxBits.bytes());
             PhaseTimer pt(ctx, "lookup");
             queryLookupKernel<<<(unsigned)hQTiles.size(), 256, 0, streamOf(ctx)>>>(qSeq, qWordOff, qLen, ctx->dSlotOff.p,
                                                                                 ctx->dSelBits.p, dQIds.p, dQSlotOff.p, dQTiles.p, k,
-                                                                                P.sameSet, ctx->indexTable, hitCnt.p, slotInfo.p, filtBits.p);
+                                                                                P.sameSet, ctx->indexTable, ctx->dIdxBits.p, hitCnt.p, slotInfo.p, filtBits.p);
             checkLaunch(ctx, "queryLookupKernel");
             cub::TransformInputIterator<uint64_t, CastU64, const uint32_t*> it64(hitCnt.p, CastU64());
             exclusiveScanToPlus1(ctx, it64, hitOff.p, nQSlots);
@@ -2076,6 +2078,9 @@ static void overlapsChunk(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, ui
     while ((int)ctx->lanes.size() < nLanes) {
         std::unique_ptr<Lane> l(new Lane());
         FG_CUDA(cudaStreamCreateWithFlags(&l->stream, cudaStreamNonBlocking));
+        // a lane that runs out of memory asks the context's own arena for its cached blocks (its owner thread is inside
+        // fg_overlaps_batch, waiting for or working as a lane: nothing allocates from it meanwhile)
+        l->arena.onPressure = [ctx] { std::lock_guard<std::mutex> lk(ctx->pressureMutex); ctx->arena.trim(); };
         ctx->lanes.push_back(std::move(l));
     }
     std::atomic<size_t> nextSub{0};

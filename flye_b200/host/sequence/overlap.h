@@ -388,6 +388,8 @@ public:
         std::vector<FastaRecord::Id> all;
         for (const auto& seq : _queryContainer.iterSeqs()) if (seq.id.strand()) all.push_back(seq.id);
         prefetch(all);
+        static const bool hostClosure = getenv("FLYE_B200_HOST_CLOSURE") && atoi(getenv("FLYE_B200_HOST_CLOSURE")) != 0;
+        if (!hostClosure && &_queryContainer == &_ovlpDetect._seqContainer) { deviceClosure(all); return; }
         ensureTransitivity(false);
         filterOverlaps();
     }
@@ -404,6 +406,49 @@ public:
     }
 
 private:
+    // ensureTransitivity(false) + filterOverlaps() on the device (fg_overlaps_closure): the cached vectors of the forward
+    // sequences go down as flat records, the lists of every sequence (both strands) come back as (input record, variant)
+    // pairs; the variants are rebuilt with reverse() / complement(), which also carry kmerMatches along
+    void deviceClosure(const std::vector<FastaRecord::Id>& fwdIds) {
+        const auto& dev = _ovlpDetect._vertexIndex.device();
+        const uint32_t base = (uint32_t)_queryContainer.idOffset();
+        std::vector<fg_overlap> flat;
+        std::vector<const OverlapRange*> src;
+        for (auto id : fwdIds)
+            for (const auto& o : *_overlapIndex[id].fwdOverlaps) {
+                fg_overlap r{};
+                r.cur_id = o.curId.rawId() - base; r.cur_begin = o.curBegin; r.cur_end = o.curEnd; r.cur_len = o.curLen;
+                r.ext_id = o.extId.rawId() - base; r.ext_begin = o.extBegin; r.ext_end = o.extEnd; r.ext_len = o.extLen;
+                r.score = o.score; r.seq_divergence = o.seqDivergence;
+                flat.push_back(r); src.push_back(&o);
+            }
+        const uint32_t nSeqs = (uint32_t)_queryContainer.iterSeqs().size();
+        std::vector<std::vector<OverlapRange>> lists(nSeqs);
+        {
+            std::lock_guard<std::mutex> lock(OverlapDetector::batchMutex());   // results live in library memory until the next call
+            fg_overlap_result res;
+            dev->check(fg_overlaps_closure(dev->ctx, flat.data(), flat.size(), nSeqs, (int32_t)Parameters::get().kmerSize, &res));
+            for (uint32_t s = 0; s < nSeqs; ++s) {
+                lists[s].reserve(res.offsets[s + 1] - res.offsets[s]);
+                for (uint64_t i = res.offsets[s]; i < res.offsets[s + 1]; ++i) {
+                    const uint32_t code = res.overlaps[i].reserved;
+                    OverlapRange o = *src[code >> 2];
+                    if (code & 1u) o = o.complement();
+                    if (code & 2u) o = o.reverse();
+                    lists[s].push_back(std::move(o));
+                }
+            }
+        }
+        size_t total = 0;
+        for (uint32_t s = 0; s < nSeqs; ++s) {
+            const FastaRecord::Id id(base + s);
+            auto& w = _overlapIndex[id.strand() ? id : id.rc()];
+            w.cached = true;
+            total += lists[s].size();
+            *(id.strand() ? w.fwdOverlaps : w.revOverlaps) = std::move(lists[s]);
+        }
+        _indexSize = total;
+    }
     std::vector<OverlapRange>& unsafeSeqOverlaps(FastaRecord::Id id) {
         auto& w = _overlapIndex[id.strand() ? id : id.rc()];
         return id.strand() ? *w.fwdOverlaps : *w.revOverlaps;

@@ -164,6 +164,16 @@ int fg_overlaps_batch(fg_ctx* ctx, const uint32_t* query_ids, uint32_t n_queries
  * max_overlaps = 0 (FG_ERR_ARG otherwise): records the batch dropped are gone. */
 int fg_overlaps_refilter(fg_ctx* ctx, uint32_t first_query, float max_divergence, fg_overlap_result* result);
 
+/* The rest of OverlapContainer::findAllOverlaps (overlap.cpp:630-668) on the device: ensureTransitivity(false) (:576-627) and
+ * filterOverlaps() (:681-741).  `records`: the getSeqOverlaps vectors of the FORWARD sequences (any order; host memory).  Result:
+ * for every sequence id 0 .. n_seqs-1 (both strands) its overlaps after the symmetric closure, the clustering of near-identical
+ * overlaps (ends within max_ends_diff = Parameters::kmerSize on both sequences, best score stays) and the sort by cur_begin.
+ * Every result record is a variant of an input record: reserved = 4 * input index + variant, variant bit 0 = complement(),
+ * bit 1 = reverse() applied after it (overlap.h:95-147) — enough to rebuild kmerMatches on the host.  The order among equal
+ * cur_begin is unspecified, as in the reference.  Same result lifetime rules as fg_overlaps_batch. */
+int fg_overlaps_closure(fg_ctx* ctx, const fg_overlap* records, uint64_t n_records, uint32_t n_seqs, int32_t max_ends_diff,
+                        fg_overlap_result* result);
+
 /* ---- multi-GPU (one context per rank; reads are partitioned, the index replicated) ------- */
 #define FG_NCCL_ID_BYTES 128
 int fg_comm_unique_id(uint8_t id[FG_NCCL_ID_BYTES]);

@@ -43,13 +43,14 @@ struct Args {
     bool findAll = false, noOverlaps = false, keepAln = false, allExt = false;
     bool lazy = false, perRead = false;
     long maxQueries = -1;
+    long chunk = 0;          // --chunk N: answer and dump N queries at a time (bounds the memory of a 10^8-overlap run)
 };
 
 static void usage() {
     fprintf(stderr,
         "harness --reads F --cfg C --out PREFIX [--k K] [--threads T] [--min-overlap M]\n"
         "        [--max-overlaps N] [--force-local] [--dump-index] [--both-strands]\n"
-        "        [--no-estimate] [--find-all] [--no-overlaps] [--max-queries N] [--all-ext] [--lazy] [--per-read]\n");
+        "        [--no-estimate] [--find-all] [--no-overlaps] [--max-queries N] [--all-ext] [--lazy] [--per-read] [--chunk N]\n");
 }
 
 static uint32_t idNum(FastaRecord::Id id) {
@@ -77,6 +78,7 @@ int main(int argc, char** argv) {
         else if (s == "--min-read-len") a.minReadLen = atoi(nxt().c_str());
         else if (s == "--max-overlaps") a.maxOverlaps = atoi(nxt().c_str());
         else if (s == "--max-queries") a.maxQueries = atol(nxt().c_str());
+        else if (s == "--chunk") a.chunk = atol(nxt().c_str());
         else if (s == "--force-local") a.forceLocal = true;
         else if (s == "--dump-index") a.dumpIndex = true;
         else if (s == "--both-strands") a.bothStrands = true;
@@ -197,25 +199,30 @@ int main(int argc, char** argv) {
                 nOverlaps += lines.size();
             }
         } else {
-            std::vector<std::vector<OverlapRange>> results(queries.size());
+            const size_t step = a.chunk > 0 ? (size_t)a.chunk : std::max<size_t>(queries.size(), 1);
+            for (size_t base = 0; base < queries.size(); base += step) {
+            const size_t cnt = std::min(step, queries.size() - base);
+            std::vector<std::vector<OverlapRange>> results(cnt);
             t0 = now();
-            std::vector<size_t> order(queries.size());
+            std::vector<size_t> order(cnt);
             for (size_t i = 0; i < order.size(); ++i) order[i] = i;
             std::function<void(const size_t&)> work = [&](const size_t& i) {
-                if (a.lazy) results[i] = container.lazySeqOverlaps(queries[i]);   // thread safe, cached (overlap.h:397-411)
-                else results[i] = container.quickSeqOverlaps(queries[i], a.maxOverlaps, a.forceLocal);
+                if (a.lazy) results[i] = container.lazySeqOverlaps(queries[base + i]);   // thread safe, cached (overlap.h:397-411)
+                else results[i] = container.quickSeqOverlaps(queries[base + i], a.maxOverlaps, a.forceLocal);
             };
 #ifdef FLYE_B200
             // the mirror's batch entry (same results as N quickSeqOverlaps calls, one device pass) unless the per-read
             // calling pattern itself is what is being tested
-            if (!a.lazy && !a.perRead) results = container.quickSeqOverlapsBatch(queries, a.maxOverlaps, a.forceLocal);
+            if (!a.lazy && !a.perRead)
+                results = container.quickSeqOverlapsBatch(std::vector<FastaRecord::Id>(queries.begin() + base, queries.begin() + base + cnt),
+                                                          a.maxOverlaps, a.forceLocal);
             else processInParallel(order, work, Parameters::get().numThreads, false);
 #else
             processInParallel(order, work, Parameters::get().numThreads, false);
 #endif
-            tOverlaps = now() - t0;
-            for (size_t i = 0; i < queries.size(); ++i) {
-                fprintf(f, "# %u %zu\n", idNum(queries[i]), results[i].size());
+            tOverlaps += now() - t0;
+            for (size_t i = 0; i < cnt; ++i) {
+                fprintf(f, "# %u %zu\n", idNum(queries[base + i]), results[i].size());
                 for (const auto& o : results[i]) {
                     dumpOverlap(f, o);
                     if (a.keepAln && o.kmerMatches) {
@@ -225,6 +232,7 @@ int main(int argc, char** argv) {
                     }
                 }
                 nOverlaps += results[i].size();
+            }
             }
         }
         fclose(f);

@@ -64,4 +64,10 @@ def test_flye_modules_assemble_on_the_mirror(built, tmp_path, preset, k, sim):
     # the next stage on the same disjointigs: repeat graph + read-to-graph alignment, both builds, byte-identical outputs
     rep_ref = _repeat(REF_BIN, os.path.join(tmp, "ref.fasta"), reads, cfg, os.path.join(tmp, "rep_ref"), 1, k)
     rep_got = _repeat(B200_BIN, os.path.join(tmp, "ref.fasta"), reads, cfg, os.path.join(tmp, "rep_b200"), 1, k)
+    if rep_got != rep_ref and os.path.isdir(os.path.join(pu.ROOT, "gpurun_out")):   # keep the evidence of a mismatch
+        for f in rep_ref:
+            if rep_got[f] != rep_ref[f]:
+                for side in ("rep_ref", "rep_b200"):
+                    shutil.copy(os.path.join(tmp, side, f), os.path.join(pu.ROOT, "gpurun_out", "mismatch_%s_%s" % (side, f)))
+                    shutil.copy(os.path.join(tmp, side, "log"), os.path.join(pu.ROOT, "gpurun_out", "mismatch_%s_log" % side))
     assert rep_got == rep_ref, {f: (rep_got[f] == rep_ref[f]) for f in rep_ref}
