@@ -28,6 +28,45 @@ def _assemble(binary, reads, cfg, out, threads, k):
     return hashlib.sha256(open(out, "rb").read()).hexdigest(), os.path.getsize(out)
 
 
+def _canonical(name, data):
+    """The node numbers of repeat_graph_dump and of the .gv files come from iterating a std::unordered_set<GraphNode*>
+    (repeat_graph.h:445, output_generator.cpp): they depend on heap addresses, not on the graph, so two runs of the SAME binary
+    can number the nodes differently.  Edge ids are stable: a node is renamed to the sorted list of its (direction, edge id)
+    incidences, and the lines are sorted."""
+    import re
+    text = data.decode()
+    if name == "repeat_graph_dump":
+        inc = {}
+        for ln in text.splitlines():
+            f = ln.split("\t")
+            if f[0] == "Edge":
+                inc.setdefault(f[2], []).append("o" + f[1]); inc.setdefault(f[3], []).append("i" + f[1])
+        sig = {n: "<" + ",".join(sorted(v)) + ">" for n, v in inc.items()}
+        out, block = [], None
+        for ln in text.splitlines():
+            f = ln.split("\t")
+            if f[0] == "Edge":
+                f[2], f[3] = sig[f[2]], sig[f[3]]
+                block = ["\t".join(f)]; out.append(block)
+            elif block is not None and ln.startswith("\t"):
+                block.append(ln)
+            else:
+                block = None; out.append([ln])
+        return "\n".join(sorted("\n".join(b) for b in out)).encode()
+    if name.endswith(".gv"):
+        edge = re.compile(r'^"(\d+)" -> "(\d+)" \[label = "id (-?\d+)')
+        inc = {}
+        for ln in text.splitlines():
+            m = edge.match(ln)
+            if m:
+                inc.setdefault(m.group(1), []).append("o" + m.group(3)); inc.setdefault(m.group(2), []).append("i" + m.group(3))
+        sig = lambda n: "<" + ",".join(sorted(inc.get(n, []))) + ">"
+        lines = [re.sub(r'^"(\d+)"( -> )?(?:"(\d+)")?', lambda m: sig(m.group(1)) + (m.group(2) or "") + (sig(m.group(3)) if m.group(3) else ""), ln)
+                 for ln in text.splitlines()]
+        return "\n".join(sorted(lines)).encode()
+    return data
+
+
 def _repeat(binary, disjointigs, reads, cfg, out_dir, threads, k):
     """the repeat stage: RepeatGraph::build = findAllOverlaps on the disjointigs with keepAlignment, nuclAlignment and
     partitionBadMappings (KSW2 trimming) on a minimizer index (repeat_graph.cpp:74-97), then ReadAligner::alignReads = every read
@@ -37,7 +76,7 @@ def _repeat(binary, disjointigs, reads, cfg, out_dir, threads, k):
            os.path.join(out_dir, "log"), "--threads", str(threads), "--min-ovlp", "1000", "--kmer", str(k)]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=1500)
     assert r.returncode == 0, r.stdout[-3000:]
-    return {f: hashlib.sha256(open(os.path.join(out_dir, f), "rb").read()).hexdigest()
+    return {f: hashlib.sha256(_canonical(f, open(os.path.join(out_dir, f), "rb").read())).hexdigest()
             for f in ("repeat_graph_edges.fasta", "repeat_graph_dump", "read_alignment_dump", "graph_before_rr.gv", "graph_after_rr.gv")}
 
 
