@@ -406,6 +406,19 @@ def main():
     if not args.no_e2e:
         ms_e2e = timed(True, args.steps)
         e2e_wall = dict(wall)
+    # roofline pass: the same resident step with ONE lane, so that every kernel runs alone on the device and its CUDA-event
+    # duration is its own (with two lanes the kernels of two sub-batches share the SMs and each event interval also covers the
+    # other lane's work).  `value` / `e2e` above are NOT taken from this pass.
+    prev_lanes = os.environ.get("FG_LANES")
+    os.environ["FG_LANES"] = "1"
+    roof_steps = max(1, min(args.steps, 3))
+    step(False)
+    ms_roof = timed(False, roof_steps)
+    roof_phases, roof_calls = dict(phase_ms), dict(phase_calls)
+    if prev_lanes is None:
+        del os.environ["FG_LANES"]
+    else:
+        os.environ["FG_LANES"] = prev_lanes
     clocks = sampler.stop()
     int_peak = eng.int_peak() if hasattr(eng, "int_peak") else None
 
@@ -462,7 +475,8 @@ def main():
            "edit": raw_ovl * 2.0 * mean_ovl_len / 4.0,   # K9: (len_q + len_t) / 4 bytes per overlap
            "select": (w + 5.0) * n_k,                # K4
            "count": 0.25 * shard_bases + w * n_k + 2.0 * w * n_k}   # K2 + the counting part of K3 (3 w N_k without the (w+4) D of the table)
-    names = {"expand": "expandKernel", "lookup": "queryLookupKernel", "hit_sort_radix": "segRadixSortKernel", "chain_prep": "pairPrepKernel",
+    names = {"expand": "expandKernel", "lookup": "queryLookupKernel", "hit_sort_radix": "segRadixSortClusterKernel" if os.environ.get("FG_SEG_SORT", "0") != "0" else "segRadixSortKernel",
+             "chain_prep": "pairPrepKernel",
              "chain_dp": "chainRunDpKernel", "chain_fill": "chainFillKernel", "chain_walk": "chainWalkKernel", "edit": "wfaKernel",
              "select": "minimizerRegKernel" if int(cfg["use_minimizers"]) else "selectKernel", "count": "denseCountKernel"}
     # integer-bound kernels: algorithmic integer operations (~15 int ops per DP cell of the reference's scan; Myers
@@ -477,11 +491,11 @@ def main():
             traffic_per_hit.update(json.load(f).get(args.workload, {}))
     except Exception:
         pass
-    kernel_phases = {p: ms for p, ms in resident_phases.items() if p in alg and alg[p] > 0 and resident_calls.get(p, 1) >= 1}
+    kernel_phases = {p: ms for p, ms in roof_phases.items() if p in alg and alg[p] > 0 and roof_calls.get(p, 1) >= 1}
     peak, peak_src = measured_peak()
     roofline, roofline_kernels = None, []
     for ph in sorted(kernel_phases, key=kernel_phases.get, reverse=True):
-        n_l = max(1, resident_calls.get(ph, 1))
+        n_l = max(1, roof_calls.get(ph, 1))
         ms_l = kernel_phases[ph] / n_l
         if ph in int_alg and int_peak:
             achieved = int_alg[ph] / n_l / (ms_l / 1e3) / 1e9
@@ -509,7 +523,11 @@ def main():
                            "cub_radix_sort_of_hits": round(resident_phases.get("hit_sort_radix_lib", 0.0), 3),
                            "cub_radix_sort_of_pair_sizes": round(resident_phases.get("chain_order", 0.0), 3),
                            "note": "cub::DeviceScan / DeviceSelect calls (prefix sums, compaction of flags) run inside the phases lookup, group, emit, index_table"},
+            "roofline_pass": {"lanes": 1, "steps": roof_steps, "ms_per_step": ms_roof,
+                              "note": "kernel durations of `roofline` / `roofline_kernels` / `phases_ms_one_lane` are CUDA-event times of a pass with one "
+                                      "lane (each kernel alone on the device); `value`, `e2e` and `phases_ms` come from the two-lane passes"},
             "phases_ms": {p: round(v, 3) for p, v in resident_phases.items()},
+            "phases_ms_one_lane": {p: round(v, 3) for p, v in roof_phases.items()},
             "api_wall_ms": {p: round(v, 2) for p, v in resident_wall.items()}, "e2e_api_wall_ms": {p: round(v, 2) for p, v in e2e_wall.items()},
             "work": {"kmer_hits": int(M), "target_groups": int(stats.get("n_pairs", 0)), "dp_pairs": int(stats.get("n_dp_pairs", 0)),
                      "dp_cells": int(stats.get("n_dp_cells", 0)), "overlaps": int(n_ovl),

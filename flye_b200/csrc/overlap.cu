@@ -29,6 +29,7 @@
 #include "introsort_warp.cuh"
 
 #include <cub/cub.cuh>
+#include <cooperative_groups.h>
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
@@ -313,6 +314,147 @@ __global__ void __launch_bounds__(SEG_WARPS * 32, 3) segRadixSortKernel(unsigned
     // start flags of the target groups (overlap.cpp:216-221), while the sorted segment is still in L2
     for (uint32_t i = threadIdx.x; i < n; i += blockDim.x)
         groupFlags[start + i] = i == 0 || (uint32_t)(hits[start + i].key >> 32) != (uint32_t)(hits[start + i - 1].key >> 32);
+}
+
+// Cluster version of the segmented sort (FG_SEG_SORT=1; NOT the default — measured on B200, 1 lane, whole configs[0] / configs[1]
+// pass: 9.3 / 16.2 ms with clusters of 1 / 2 CTAs against 8.3 / 12.9 ms for the kernel above, and 20-29 ms with clusters of 4-8:
+// the sort is bound by the latency of its warp steps (load -> match.any -> shared-memory offsets -> scattered store), which
+// 444 independent CTAs hide better than 148 CTAs that meet at cluster barriers, not by the bytes it moves.  Kept as a tested
+// variant and as the record of that experiment.)  The kernel above keeps 444 segments in flight, each with its source, its
+// ping-pong copy and its 16-byte output: 100-500 MB, so every pass goes through HBM (59 B of DRAM traffic per hit measured where
+// 24 are compulsory).  Here the grid is PERSISTENT — one 1024-thread CTA per SM, grouped into thread-block clusters of 1, 2, 4 or
+// 8 CTAs that take one query at a time from a counter — and the intermediate copy lives in a scratch slot that belongs to the
+// cluster and is reused for every query it sorts: sources + scratch of all resident clusters stay inside the 126 MB L2 (the
+// host picks the cluster size from the segment sizes), so HBM only sees the packed hits once on the way in and the Elem records
+// on the way out.  A cluster splits a segment into one contiguous chunk per warp; the per-(warp, digit) counts of the CTAs are
+// combined through distributed shared memory (every CTA reads its peers' digit totals), the counts of the next pass are
+// accumulated while scattering with shared-memory atomics on the CTA that owns the destination chunk (remote for c > 1).
+static constexpr int SRS_WARPS = 32;
+struct SrsSmem {
+    uint32_t hist[2][SRS_WARPS][256];
+    uint32_t base[256];
+    uint32_t ctaTot[256];
+    uint32_t warpTot[8];
+    uint32_t query;
+};
+__global__ void __launch_bounds__(SRS_WARPS * 32, 1) segRadixSortClusterKernel(const unsigned long long* __restrict__ packed, unsigned long long* __restrict__ scratch,
+                                                                                uint64_t scratchStride, int nBufs, const uint64_t* __restrict__ qHitOff,
+                                                                                uint32_t qFirst, uint32_t nq, uint64_t hitBase, int posBits, int nPass, Elem* __restrict__ hits,
+                                                                                uint8_t* __restrict__ groupFlags, uint32_t* __restrict__ nextQuery) {
+    namespace cg = cooperative_groups;
+    extern __shared__ __align__(16) unsigned char srsRaw[];
+    SrsSmem& sm = *reinterpret_cast<SrsSmem*>(srsRaw);
+    cg::cluster_group cluster = cg::this_cluster();
+    const uint32_t cSize = cluster.num_blocks(), cRank = cluster.block_rank();
+    const uint32_t clusterId = blockIdx.x / cSize;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t gw = cRank * SRS_WARPS + w, nW = cSize * SRS_WARPS;
+    const int idShift = 2 * posBits;
+    const unsigned long long posMask = (1ULL << posBits) - 1ULL;
+    unsigned long long* const slot = scratch + (uint64_t)clusterId * (uint64_t)nBufs * scratchStride;   // nBufs = 2 when three passes ping-pong
+    const uint32_t* remoteQuery = cluster.map_shared_rank(&sm.query, 0);
+    for (;;) {
+        if (cRank == 0 && threadIdx.x == 0) sm.query = atomicAdd(nextQuery, 1u);
+        cluster.sync();
+        const uint32_t q = *remoteQuery;
+        cluster.sync();                                   // everybody has read it before rank 0 fetches the next one
+        if (q >= nq) break;
+        const uint64_t start = qHitOff[qFirst + q] - hitBase;
+        const uint32_t n = (uint32_t)(qHitOff[qFirst + q + 1] - qHitOff[qFirst + q]);
+        if (n == 0) continue;
+        const uint32_t C = (((n + nW - 1) / nW) + 31u) & ~31u;   // elements per warp, whole steps
+        const uint32_t wBeg = (uint32_t)min((uint64_t)n, (uint64_t)gw * C), wEnd = (uint32_t)min((uint64_t)n, (uint64_t)wBeg + C);
+        const unsigned long long* src = packed + start;
+        uint32_t (*cur)[256] = sm.hist[0];
+        uint32_t (*nxt)[256] = sm.hist[1];
+        for (int i = threadIdx.x; i < SRS_WARPS * 256; i += blockDim.x) (&cur[0][0])[i] = 0u;
+        __syncthreads();
+        {   // counts of the first pass
+            unsigned long long xn = wBeg + lane < wEnd ? __ldcg(src + wBeg + lane) : 0ULL;
+            for (uint32_t i0 = wBeg; i0 < wEnd; i0 += 32) {
+                const uint32_t i = i0 + lane;
+                const bool act = i < wEnd;
+                const uint32_t am = __ballot_sync(0xffffffffu, act);
+                const unsigned long long xc = xn;
+                if (i + 32 < wEnd) xn = __ldcg(src + i + 32);
+                if (act) {
+                    const uint32_t d = (uint32_t)(xc >> idShift) & 255u;
+                    const uint32_t peers = __match_any_sync(am, d);
+                    if ((peers & ((1u << lane) - 1u)) == 0u) cur[w][d] += __popc(peers);
+                }
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+        for (int pass = 0; pass < nPass; ++pass) {
+            const bool last = pass == nPass - 1;
+            const int sh = idShift + 8 * pass;
+            unsigned long long* dst = slot + (uint64_t)(pass & (nBufs - 1)) * scratchStride;
+            // (warp, digit) counts -> exclusive offsets over the warps of this CTA; the CTA's digit totals for the cluster
+            if (threadIdx.x < 256) {
+                uint32_t tot = 0;
+                for (int v = 0; v < SRS_WARPS; ++v) { const uint32_t c = cur[v][threadIdx.x]; cur[v][threadIdx.x] = tot; tot += c; }
+                sm.ctaTot[threadIdx.x] = tot;
+            }
+            for (int i = threadIdx.x; i < SRS_WARPS * 256; i += blockDim.x) (&nxt[0][0])[i] = 0u;
+            cluster.sync();                               // totals visible, next-pass counters cleared in every CTA
+            uint32_t below = 0, all = 0;
+            if (threadIdx.x < 256) {
+                for (uint32_t r = 0; r < cSize; ++r) {
+                    const uint32_t t = r == cRank ? sm.ctaTot[threadIdx.x] : cluster.map_shared_rank(sm.ctaTot, r)[threadIdx.x];
+                    all += t; if (r < cRank) below += t;
+                }
+                uint32_t inc = all;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
+                sm.base[threadIdx.x] = inc - all + below;   // exclusive inside the warp of digits, plus the peers in front of this CTA
+                if (lane == 31) sm.warpTot[w] = inc;
+            }
+            __syncthreads();
+            if (threadIdx.x < 256) {
+                uint32_t add = 0;
+                for (int v = 0; v < w; ++v) add += sm.warpTot[v];
+                sm.base[threadIdx.x] += add;
+            }
+            __syncthreads();
+            unsigned long long xn = wBeg + lane < wEnd ? __ldcg(src + wBeg + lane) : 0ULL;
+            for (uint32_t i0 = wBeg; i0 < wEnd; i0 += 32) {
+                const uint32_t i = i0 + lane;
+                const bool act = i < wEnd;
+                const uint32_t am = __ballot_sync(0xffffffffu, act);
+                const unsigned long long x = xn;
+                if (i + 32 < wEnd) xn = __ldcg(src + i + 32);
+                if (act) {
+                    const uint32_t d = (uint32_t)(x >> sh) & 255u;
+                    const uint32_t peers = __match_any_sync(am, d);
+                    const uint32_t o = sm.base[d] + cur[w][d];
+                    __syncwarp(am);
+                    if ((peers & ((1u << lane) - 1u)) == 0u) cur[w][d] += __popc(peers);
+                    const uint32_t pos = o + __popc(peers & ((1u << lane) - 1u));
+                    if (!last) {
+                        dst[pos] = x;
+                        const uint32_t g2 = pos / C, r2 = g2 / SRS_WARPS, d2 = (uint32_t)(x >> (sh + 8)) & 255u;
+                        uint32_t* cnt = &nxt[g2 % SRS_WARPS][d2];
+                        if (r2 == cRank) atomicAdd(cnt, 1u);                       // shared-memory atomic
+                        else atomicAdd(cluster.map_shared_rank(cnt, r2), 1u);      // the owner's shared memory, through the cluster
+                    } else {
+                        Elem e; e.key = ((x >> idShift) << 32) | ((x >> posBits) & posMask); e.val = (unsigned int)(x & posMask); e.aux = 0;
+                        hits[start + pos] = e;
+                    }
+                }
+                __syncwarp();
+            }
+            __threadfence();
+            cluster.sync();                               // the scattered copy and the remote counts are complete
+            src = dst;
+            uint32_t (*th)[256] = cur; cur = nxt; nxt = th;
+        }
+        // start flags of the target groups (overlap.cpp:216-221), while the sorted segment is still in the L2
+        const uint32_t per = (n + cSize - 1) / cSize, fBeg = min(n, cRank * per), fEnd = min(n, fBeg + per);
+        const uint32_t* ids = reinterpret_cast<const uint32_t*>(hits + start);   // high half of the key = word 1 of every 4-word record
+        for (uint32_t i = fBeg + threadIdx.x; i < fEnd; i += blockDim.x)
+            groupFlags[start + i] = i == 0 || __ldcg(ids + 4ULL * i + 1) != __ldcg(ids + 4ULL * (i - 1) + 1);
+    }
 }
 
 // tie flags (input of the prefix count of rangeIsTieFree) for the queries that contain ties; all other flags stay 0
@@ -1809,9 +1951,49 @@ static void overlapsChunk(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, ui
                                                                              posBits, qTie.p);
                 checkLaunch(ctx, "expandKernel");
             }
-            {
+            int nPass = (idBits + 7) / 8;
+            {   // (tests: more passes than the ids need exercise the three-pass ping-pong on small inputs; the extra digits are 0)
+                const int forced = envInt("FG_SRS_MIN_PASSES", 1, 1, 3);
+                if (forced > nPass && 2 * posBits + 8 * forced <= 64) nPass = forced;
+            }
+            if (envInt("FG_SEG_SORT", 0, 0, 1)) {   // 1 = segRadixSortClusterKernel (L2-resident; measured slower, see its comment)
+                // cluster size: sources, scratch copies and fresh output of all resident clusters should fit the L2 together.
+                // The typical hit lives in a segment of the hits-weighted mean size.
+                double sum2 = 0.0; uint64_t maxSeg = 1;
+                for (uint32_t q = qa; q < qb; ++q) { const uint64_t n = hQHitOff[q + 1] - hQHitOff[q]; sum2 += (double)n * (double)n; maxSeg = std::max(maxSeg, n); }
+                const double segW = sum2 / (double)M;
+                const double l2Budget = (double)envInt("FG_SRS_L2_MB", 64, 1, 4096) * 1048576.0;
+                int cSize = 1;
+                while (cSize < 8 && (148.0 / cSize) * segW * 32.0 > l2Budget) cSize *= 2;
+                if (const int forced = envInt("FG_SRS_CLUSTER", 0, 0, 8)) cSize = forced == 1 || forced == 2 || forced == 4 || forced == 8 ? forced : cSize;
+                static std::once_flag srsAttr[64];   // function attributes are per device
+                std::call_once(srsAttr[ctx->device & 63], [&] {
+                    FG_CUDA(cudaFuncSetAttribute(segRadixSortClusterKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SrsSmem)));
+                });
+                cudaLaunchConfig_t cfg{};
+                cudaLaunchAttribute attr[1];
+                attr[0].id = cudaLaunchAttributeClusterDimension;
+                attr[0].val.clusterDim.x = (unsigned)cSize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+                cfg.blockDim = dim3(SRS_WARPS * 32); cfg.dynamicSmemBytes = sizeof(SrsSmem); cfg.stream = streamOf(ctx);
+                cfg.attrs = attr; cfg.numAttrs = 1;
+                cfg.gridDim = dim3((unsigned)cSize);
+                int maxClusters = 0;
+                FG_CUDA(cudaOccupancyMaxActiveClusters(&maxClusters, segRadixSortClusterKernel, &cfg));
+                if (maxClusters < 1) throw Error(FG_ERR_CUDA, "segRadixSortClusterKernel: no cluster of the requested size fits the device");
+                const uint32_t nClusters = std::min<uint32_t>((uint32_t)maxClusters, nq);
+                cfg.gridDim = dim3(nClusters * (unsigned)cSize);
+                const uint64_t stride = (maxSeg + 31) & ~31ULL;
+                const int nBufs = nPass >= 3 ? 2 : 1;
+                DevBuf<unsigned long long> srsScratch((uint64_t)nClusters * nBufs * stride);
+                DevBuf<uint32_t> nextQuery(1);
+                FG_CUDA(cudaMemsetAsync(nextQuery.p, 0, 4, streamOf(ctx)));
                 PhaseTimer pt(ctx, "hit_sort_radix");
-                segRadixSortKernel<<<nq, SEG_WARPS * 32, 0, streamOf(ctx)>>>(bufA, bufB, dQHitOff.p, qa, hitBase, posBits, (idBits + 7) / 8, hits.p, flags.p);
+                FG_CUDA(cudaLaunchKernelEx(&cfg, segRadixSortClusterKernel, (const unsigned long long*)bufA, srsScratch.p, stride, nBufs, (const uint64_t*)dQHitOff.p, qa, nq,
+                                           hitBase, posBits, nPass, hits.p, flags.p, nextQuery.p));
+                checkLaunch(ctx, "segRadixSortClusterKernel");
+            } else {
+                PhaseTimer pt(ctx, "hit_sort_radix");
+                segRadixSortKernel<<<nq, SEG_WARPS * 32, 0, streamOf(ctx)>>>(bufA, bufB, dQHitOff.p, qa, hitBase, posBits, nPass, hits.p, flags.p);
                 checkLaunch(ctx, "segRadixSortKernel");
             }
         } else if (radixMode == 2) {
