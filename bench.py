@@ -375,6 +375,8 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    per_rank = []   # ms per step of every rank, one list per timed region (resident, e2e, roofline pass)
+
     def timed(upload, steps):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -384,10 +386,13 @@ def main():
         e1.record(stream)
         barrier()
         ms = e0.elapsed_time(e1) / steps
+        per_rank.append([round(ms, 3)])
         if world > 1:
             t = torch.tensor([ms], device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
+            g = [torch.empty_like(t) for _ in range(world)]
+            dist.all_gather(g, t)
+            per_rank[-1] = [round(float(x.item()), 3) for x in g]
+            ms = max(per_rank[-1])
         return ms
 
     eng.upload_packed(packed_pin, woff, lens)
@@ -402,10 +407,11 @@ def main():
     ms_resident = timed(False, args.steps)
     launches = (eng.launches() - launches0) // max(1, args.steps)
     resident_phases, resident_calls, stats, resident_wall = dict(phase_ms), dict(phase_calls), dict(ovl_stats), dict(wall)
-    ms_e2e, e2e_wall = None, {}
+    ms_e2e, e2e_wall, e2e_phases = None, {}, {}
     if not args.no_e2e:
         ms_e2e = timed(True, args.steps)
         e2e_wall = dict(wall)
+        e2e_phases = dict(phase_ms)
     # roofline pass: the same resident step with ONE lane, so that every kernel runs alone on the device and its CUDA-event
     # duration is its own (with two lanes the kernels of two sub-batches share the SMs and each event interval also covers the
     # other lane's work).  `value` / `e2e` above are NOT taken from this pass.
@@ -528,6 +534,7 @@ def main():
                                       "lane (each kernel alone on the device); `value`, `e2e` and `phases_ms` come from the two-lane passes"},
             "phases_ms": {p: round(v, 3) for p, v in resident_phases.items()},
             "phases_ms_one_lane": {p: round(v, 3) for p, v in roof_phases.items()},
+            "phases_ms_e2e": {p: round(v, 3) for p, v in e2e_phases.items()}, "ms_per_step_of_every_rank": per_rank,
             "api_wall_ms": {p: round(v, 2) for p, v in resident_wall.items()}, "e2e_api_wall_ms": {p: round(v, 2) for p, v in e2e_wall.items()},
             "work": {"kmer_hits": int(M), "target_groups": int(stats.get("n_pairs", 0)), "dp_pairs": int(stats.get("n_dp_pairs", 0)),
                      "dp_cells": int(stats.get("n_dp_cells", 0)), "overlaps": int(n_ovl),

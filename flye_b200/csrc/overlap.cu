@@ -2107,7 +2107,9 @@ static void overlapsChunk(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, ui
             DevBuf<uint32_t> pairFlags(Pn), nRuns;
             DevBuf<Seg> extSegs(Pn), allSegs(Pn);
             // FG_DP_MODE: 2 = run-compressed DP and chain walk (default), 1 = match-by-match with pruned look-back, 0 = match-by-match
-            const int dpMode = envInt("FG_DP_MODE", 2, 0, 2);   // read per call: the tests switch it
+            // (the run-compressed DP relies on every in-run step passing the jump test, i.e. on k < max_jump — overlap.cpp:289 tests
+            // dc < _maxJump; any other setting takes the literal match-by-match DP)
+            const int dpMode = P.maxJump > k ? envInt("FG_DP_MODE", 2, 0, 2) : 0;   // read per call: the tests switch it
             {
                 PhaseTimer pt(ctx, "chain_prep");
                 if (dpMode == 2) nRuns.alloc(Pn);
@@ -2338,6 +2340,9 @@ void overlapsBatch(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, const fg_
     const int k = ctx->k;
     const bool sameSet = prm.query_set == 0;
     if (!sameSet && !ctx->dQsSeq.p) throw Error(FG_ERR_ARG, "query_set = 1 but fg_queries_upload has not been called");
+    // the self-hit removal of the lookup / expansion identifies a query position with ONE index entry; a palindromic k-mer (its own
+    // reverse complement: only possible for even k) would have two.  Every preset of the reference uses an odd k.
+    if (sameSet && (k & 1) == 0) throw Error(FG_ERR_ARG, "the device overlap path needs an odd k-mer size (palindromic k-mers)");
     const uint32_t nQuerySeqs = sameSet ? ctx->nReads : ctx->nQsReads;
     for (uint32_t i = 0; i < nQ; ++i)
         if (queryIds[i] >= 2 * nQuerySeqs) throw Error(FG_ERR_ARG, "query id out of range");
