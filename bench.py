@@ -375,14 +375,19 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    step_walls = []   # host wall clock of every single step of this rank, one list per timed region
     per_rank = []   # ms per step of every rank, one list per timed region (resident, e2e, roofline pass)
 
     def timed(upload, steps):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
+        walls = []
         for _ in range(steps):
+            t0 = time.perf_counter()
             step(upload)
+            walls.append(round((time.perf_counter() - t0) * 1e3, 2))
+        step_walls.append(walls)
         e1.record(stream)
         barrier()
         ms = e0.elapsed_time(e1) / steps
@@ -534,7 +539,7 @@ def main():
                                       "lane (each kernel alone on the device); `value`, `e2e` and `phases_ms` come from the two-lane passes"},
             "phases_ms": {p: round(v, 3) for p, v in resident_phases.items()},
             "phases_ms_one_lane": {p: round(v, 3) for p, v in roof_phases.items()},
-            "phases_ms_e2e": {p: round(v, 3) for p, v in e2e_phases.items()}, "ms_per_step_of_every_rank": per_rank,
+            "phases_ms_e2e": {p: round(v, 3) for p, v in e2e_phases.items()}, "ms_per_step_of_every_rank": per_rank, "step_wall_ms_rank0": step_walls,
             "api_wall_ms": {p: round(v, 2) for p, v in resident_wall.items()}, "e2e_api_wall_ms": {p: round(v, 2) for p, v in e2e_wall.items()},
             "work": {"kmer_hits": int(M), "target_groups": int(stats.get("n_pairs", 0)), "dp_pairs": int(stats.get("n_dp_pairs", 0)),
                      "dp_cells": int(stats.get("n_dp_cells", 0)), "overlaps": int(n_ovl),

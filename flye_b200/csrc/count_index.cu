@@ -1312,7 +1312,7 @@ void buildIndexSolid(fg_ctx* ctx, int minFreq, float selectRate, int tandemFreq,
     size_t tLo, tHi;
     tileRange(ctx, firstRead, nReadsShard, tLo, tHi);
     {
-        L2Pin pinSolid(ctx, ctx->dSolidBits.p, ctx->dSolidBits.bytes());   // the "count >= 2" bitmap answers most lookups: keep it in the L2
+        L2Pin pinSolid(ctx, ctx->dSolidBits.p, ctx->dSolidBits.bytes(), 2);   // the "count >= 2" bitmap answers most lookups: keep it in the L2
         PhaseTimer pt(ctx, "select");
         const uint64_t slotBase = ctx->hSlotOff[firstRead], shardSlots = ctx->hSlotOff[firstRead + nReadsShard] - slotBase;
         DevBuf<uint32_t> freq(std::max<uint64_t>(shardSlots, 1));

@@ -220,9 +220,9 @@ struct HostTimer {
 // stream gigabytes past it: persisting-L2 access policy window on the calling thread's stream (sm_80+).  Best effort.
 struct L2Pin {
     cudaStream_t st; bool on = false, carved = false;
-    L2Pin(const fg_ctx* ctx, const void* p, size_t bytes) : st(streamOf(ctx)) {
+    L2Pin(const fg_ctx* ctx, const void* p, size_t bytes, int which = 1) : st(streamOf(ctx)) {
         if (!p || !bytes) return;
-        if (const char* e = getenv("FG_L2_PIN")) if (atoi(e) == 0) return;   // A/B switch
+        if (const char* e = getenv("FG_L2_PIN")) if (!(atoi(e) & which)) return;   // A/B switch: bit 0 count, bit 1 select, bit 2 lookup
         int dev = 0, maxWin = 0, maxPersist = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&maxWin, cudaDevAttrMaxAccessPolicyWindowSize, dev);

@@ -225,7 +225,8 @@ __global__ void __launch_bounds__(256) gatherSortedHitsKernel(const uint32_t* __
 // next pass are accumulated while scattering (the destination tells the owning warp).  The segment ping-pongs between two
 // buffers (L2 resident for all but the longest reads); the last pass writes the Elem records.
 static constexpr int SEG_WARPS = 16;
-__global__ void __launch_bounds__(SEG_WARPS * 32, 3) segRadixSortKernel(unsigned long long* bufA, unsigned long long* bufB,
+template <int MIN_CTAS>
+__global__ void __launch_bounds__(SEG_WARPS * 32, MIN_CTAS) segRadixSortKernel(unsigned long long* bufA, unsigned long long* bufB,
                                                                          const uint64_t* __restrict__ qHitOff, uint32_t qFirst, uint64_t hitBase,
                                                                          int posBits, int nPass, Elem* __restrict__ hits, uint8_t* __restrict__ groupFlags) {
     __shared__ uint32_t hist[2][SEG_WARPS][256];
@@ -244,21 +245,17 @@ __global__ void __launch_bounds__(SEG_WARPS * 32, 3) segRadixSortKernel(unsigned
     uint32_t (*nxt)[256] = hist[1];
     for (int i = threadIdx.x; i < SEG_WARPS * 256; i += blockDim.x) (&cur[0][0])[i] = 0u;
     __syncthreads();
-    unsigned long long xn = wBeg + lane < wEnd ? src[wBeg + lane] : 0ULL;   // register prefetch: the load of step t+1 overlaps step t
-    for (uint32_t i0 = wBeg; i0 < wEnd; i0 += 32) {   // counts of the first pass
-        const uint32_t i = i0 + lane;
-        const bool act = i < wEnd;
-        const uint32_t am = __ballot_sync(0xffffffffu, act);
-        const unsigned long long xc = xn;
-        if (i + 32 < wEnd) xn = src[i + 32];
-        if (act) {
-            const uint32_t d = (uint32_t)(xc >> idShift) & 255u;
-            const uint32_t peers = __match_any_sync(am, d);
-            if ((peers & ((1u << lane) - 1u)) == 0u) cur[w][d] += __popc(peers);
-        }
-        __syncwarp();
+    // counts of the first pass: order does not matter here, one shared-memory atomic per element (four independent loads in flight)
+    for (uint32_t i0 = wBeg; i0 < wEnd; i0 += 128) {
+        unsigned long long x[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { const uint32_t i = i0 + 32 * u + lane; x[u] = i < wEnd ? src[i] : ~0ULL; }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (i0 + 32 * u + lane < wEnd) atomicAdd(&cur[w][(uint32_t)(x[u] >> idShift) & 255u], 1u);
     }
     __syncthreads();
+    unsigned long long xn, xn2;   // register prefetch: the loads of steps t+1 and t+2 overlap step t
     for (int pass = 0; pass < nPass; ++pass) {
         const bool last = pass == nPass - 1;
         const int sh = idShift + 8 * pass;
@@ -284,12 +281,14 @@ __global__ void __launch_bounds__(SEG_WARPS * 32, 3) segRadixSortKernel(unsigned
         for (int i = threadIdx.x; i < SEG_WARPS * 256; i += blockDim.x) (&nxt[0][0])[i] = 0u;
         __syncthreads();
         xn = wBeg + lane < wEnd ? src[wBeg + lane] : 0ULL;
+        xn2 = wBeg + 32 + lane < wEnd ? src[wBeg + 32 + lane] : 0ULL;
         for (uint32_t i0 = wBeg; i0 < wEnd; i0 += 32) {
             const uint32_t i = i0 + lane;
             const bool act = i < wEnd;
             const uint32_t am = __ballot_sync(0xffffffffu, act);
             const unsigned long long x = xn;
-            if (i + 32 < wEnd) xn = src[i + 32];
+            xn = xn2;
+            if (i + 64 < wEnd) xn2 = src[i + 64];
             if (act) {
                 const uint32_t d = (uint32_t)(x >> sh) & 255u;
                 const uint32_t peers = __match_any_sync(am, d);
@@ -1800,6 +1799,9 @@ struct OrderedCommit {
     size_t next = 0;       // index of the sub-batch whose turn it is
     size_t nRaw = 0;       // records reserved so far
     bool failed = false;
+    // per query of the whole call, filled by the lanes (sliceEpilogue): first record in the pinned buffer, records kept
+    std::vector<size_t> qStart; std::vector<uint32_t> kept;
+    std::atomic<bool> badOrder{false};
     size_t reserve(size_t index, size_t n) {
         std::unique_lock<std::mutex> lk(m);
         cv.wait(lk, [&] { return next == index || failed; });
@@ -1813,6 +1815,7 @@ struct OrderedCommit {
 };
 
 static void recordDivergences(fg_ctx* ctx, fg_overlap* recs, size_t n, const fg_overlap_params& prm);
+static void sliceEpilogue(fg_ctx* ctx, fg_overlap* recs, size_t n, size_t sliceOff, const fg_overlap_params& prm, OrderedCommit& commit);
 
 static void overlapsChunk(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, uint32_t qOffset, const fg_overlap_params& prm, const OvParams& P,
                           OrderedCommit& commit, size_t& subBase, uint64_t& totHits, BatchTotals& tot, const float* dQueryMaxDiv) {
@@ -1842,6 +1845,7 @@ static void overlapsChunk(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, ui
     const uint64_t nQSlots = hQSlotOff[nQ];
     std::vector<uint64_t> hQHitOff(nQ + 1, 0);
 
+    std::unique_ptr<HostTimer> prepPart(new HostTimer(ctx, "prep_alloc_copy"));
     DevBuf<uint32_t> dQIds(std::max<uint32_t>(nQ, 1));
     DevBuf<uint64_t> dQSlotOff(nQ + 1);
     DevBuf<uint2> dQTiles(std::max<size_t>(hQTiles.size(), 1));
@@ -1853,10 +1857,11 @@ static void overlapsChunk(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, ui
     FG_CUDA(cudaMemsetAsync(filtBits.p, 0, filtBits.bytes(), streamOf(ctx)));
     FG_CUDA(cudaMemsetAsync(hitCnt.p, 0, hitCnt.bytes(), streamOf(ctx)));
 
+    prepPart.reset(new HostTimer(ctx, "prep_lookup_wall"));
     if (!hQTiles.empty()) {
         if (nQSlots >= (1ULL << 31)) throw Error(FG_ERR_ARG, "query batch too large (>= 2^31 k-mer slots); split the call");
         {
-            L2Pin pinBits(ctx, ctx->dIdxBits.p, ctx->dIdxBits.bytes());
+            L2Pin pinBits(ctx, ctx->dIdxBits.p, ctx->dIdxBits.bytes(), 4);
             PhaseTimer pt(ctx, "lookup");
             queryLookupKernel<<<(unsigned)hQTiles.size(), 256, 0, streamOf(ctx)>>>(qSeq, qWordOff, qLen, ctx->dSlotOff.p,
                                                                                 ctx->dSelBits.p, dQIds.p, dQSlotOff.p, dQTiles.p, k,
@@ -1873,6 +1878,7 @@ static void overlapsChunk(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, ui
         }
     }
     totHits += hQHitOff[nQ];
+    prepPart.reset(new HostTimer(ctx, "prep_budget"));
 
     // sub-batches of consecutive queries with a bounded number of hits, processed by a few lanes (host thread + stream +
     // arena each).  Hits per sub-batch: as many as comfortably fit (about 80 B of workspace per hit and lane), but at least
@@ -1901,6 +1907,7 @@ static void overlapsChunk(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, ui
         subs.push_back({qa, qb});
         qa = qb;
     }
+    prepPart.reset();
     hostPrep.reset();
     HostTimer hostSub(ctx, "host_subbatches");   // wall clock of all sub-batches
     PinnedBuf<fg_overlap>& pinned = ctx->pinnedOut;
@@ -1993,7 +2000,8 @@ static void overlapsChunk(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, ui
                 checkLaunch(ctx, "segRadixSortClusterKernel");
             } else {
                 PhaseTimer pt(ctx, "hit_sort_radix");
-                segRadixSortKernel<<<nq, SEG_WARPS * 32, 0, streamOf(ctx)>>>(bufA, bufB, dQHitOff.p, qa, hitBase, posBits, nPass, hits.p, flags.p);
+                auto sortK = envInt("FG_SEG_OCC", 3, 3, 4) == 4 ? segRadixSortKernel<4> : segRadixSortKernel<3>;   // resident CTAs per SM (32 / 40 registers)
+                sortK<<<nq, SEG_WARPS * 32, 0, streamOf(ctx)>>>(bufA, bufB, dQHitOff.p, qa, hitBase, posBits, nPass, hits.p, flags.p);
                 checkLaunch(ctx, "segRadixSortKernel");
             }
         } else if (radixMode == 2) {
@@ -2252,6 +2260,7 @@ static void overlapsChunk(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, ui
                     // seqDivergence of this slice's records (host arithmetic with glibc logf), while the other lanes keep the device busy
                     HostTimer he(ctx, "host_divergence");
                     recordDivergences(ctx, dst, nOut, prm);
+                    sliceEpilogue(ctx, dst, nOut, myOff, prm, commit);   // threshold / maxOverlaps replay of this slice's queries
                 }
             }
         }
@@ -2333,6 +2342,59 @@ static void recordDivergences(fg_ctx* ctx, fg_overlap* recs, size_t n, const fg_
     ctx->hostPool.parallelFor(n, body, n);
 }
 
+// Per-query part of the host epilogue for one sub-batch's slice of the pinned buffer (whole queries, in query order): where every
+// query's records start, then the replay of the divergence threshold (overlap.cpp:470) and of the maxOverlaps cut (:218-219),
+// which only depends on the query's own records.  Dropped records are marked in `reserved`; the call's tail only has to turn the
+// kept counts into offsets and compact if anything was dropped.  Runs on the host pool while the other lane keeps the device busy.
+static void sliceEpilogue(fg_ctx* ctx, fg_overlap* recs, size_t n, size_t sliceOff, const fg_overlap_params& prm, OrderedCommit& commit) {
+    if (!n) return;
+    const size_t nQ = commit.kept.size();
+    std::vector<size_t>& qStart = commit.qStart;
+    std::lock_guard<std::mutex> lk(ctx->hostPoolMutex);
+    // (1) first record of every query of the slice
+    std::vector<std::vector<uint32_t>> found(1);
+    std::mutex fm;
+    ctx->hostPool.parallelFor(n, [&](size_t a, size_t b) {
+        std::vector<uint32_t> mine;
+        for (size_t i = a; i < b; ++i) {
+            const fg_overlap& o = recs[i];
+            if (i == 0 || recs[i - 1].reserved != o.reserved) {
+                if (o.reserved >= nQ || (i && recs[i - 1].reserved > o.reserved)) { commit.badOrder = true; continue; }
+                qStart[o.reserved] = sliceOff + i;
+                mine.push_back(o.reserved);
+            }
+        }
+        std::lock_guard<std::mutex> g(fm);
+        found.emplace_back(std::move(mine));
+    }, n);
+    if (commit.badOrder) return;
+    std::vector<uint32_t> qs;
+    for (auto& v : found) qs.insert(qs.end(), v.begin(), v.end());
+    std::sort(qs.begin(), qs.end());
+    // (2) replay per query
+    ctx->hostPool.parallelFor(qs.size(), [&](size_t ja, size_t jb) {
+        for (size_t j = ja; j < jb; ++j) {
+            const uint32_t q = qs[j];
+            size_t pos = qStart[q] - sliceOff, detected = 0;
+            const size_t qEnd = j + 1 < qs.size() ? qStart[qs[j + 1]] - sliceOff : n;
+            const float maxDiv = prm.query_max_divergence ? prm.query_max_divergence[q] : prm.max_divergence;
+            while (pos < qEnd) {
+                size_t end = pos;   // one target group = run of equal ext_id
+                while (end < qEnd && recs[end].ext_id == recs[pos].ext_id) ++end;
+                const bool stop = prm.max_overlaps != 0 && detected >= (size_t)prm.max_overlaps;
+                for (size_t i = pos; i < end; ++i) {
+                    const bool pass = recs[i].seq_divergence < maxDiv;
+                    const bool keep = !stop && (pass || prm.keep_rejected);
+                    recs[i].reserved = keep ? (pass ? 0u : 1u) : 0xffffffffu;
+                    detected += keep;
+                }
+                pos = end;
+            }
+            commit.kept[q] = (uint32_t)detected;
+        }
+    }, n);
+}
+
 void overlapsBatch(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, const fg_overlap_params& prm, fg_overlap_result* result) {
     if (!ctx->indexed) throw Error(FG_ERR_ARG, "no index: call fg_build_index_* first");
     if (prm.keep_rejected && prm.max_overlaps != 0) throw Error(FG_ERR_ARG, "keep_rejected needs max_overlaps = 0");
@@ -2358,6 +2420,7 @@ void overlapsBatch(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, const fg_
     uint64_t totHits = 0;
     BatchTotals tot;
     OrderedCommit commit;
+    commit.qStart.assign((size_t)nQ + 1, SIZE_MAX); commit.kept.assign(nQ, 0);
     size_t subBase = 0;
     PinnedBuf<fg_overlap>& pinned = ctx->pinnedOut;   // all chunks / sub-batches land here in query order; the epilogue compacts into a second buffer
     HostTimer hostAll(ctx, "host_total");
@@ -2391,43 +2454,13 @@ void overlapsBatch(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, const fg_
     HostTimer hostEpi(ctx, "host_epilogue");
     fg_overlap* hOut = pinned.p;
     auto parallelFor = [&](size_t n, const std::function<void(size_t, size_t)>& fn) { ctx->hostPool.parallelFor(n, fn, nRaw); };
-    // (1) the first record of every query (the divergences were computed by the lanes, recordDivergences)
-    std::vector<size_t> qStart(nQ + 1, SIZE_MAX);
-    std::atomic<bool> badOrder{false};
-    parallelFor(nRaw, [&](size_t a, size_t b) {
-        for (size_t i = a; i < b; ++i) {
-            const fg_overlap& o = hOut[i];
-            if (i == 0 || hOut[i - 1].reserved != o.reserved) {
-                if (o.reserved >= nQ || (i && hOut[i - 1].reserved > o.reserved)) { badOrder = true; continue; }
-                qStart[o.reserved] = i;
-            }
-        }
-    });
-    if (badOrder) throw Error(FG_ERR_INTERNAL, "overlap records out of query order");
+    // the lanes have computed the divergences (recordDivergences), found the first record of every query and replayed the threshold
+    // and maxOverlaps per query (sliceEpilogue); dropped records carry reserved = ~0
+    if (commit.badOrder) throw Error(FG_ERR_INTERNAL, "overlap records out of query order");
+    std::vector<size_t>& qStart = commit.qStart;
+    std::vector<uint32_t>& kept = commit.kept;
     qStart[nQ] = nRaw;
     for (uint32_t q = nQ; q-- > 0;) if (qStart[q] == SIZE_MAX) qStart[q] = qStart[q + 1];   // queries without records
-    // (2) threshold (:470) and maxOverlaps (:218-219) replay per query, in parallel: dropped records are marked
-    std::vector<uint32_t> kept(nQ, 0);
-    parallelFor(nQ, [&](size_t qa, size_t qb) {
-        for (size_t q = qa; q < qb; ++q) {
-            size_t pos = qStart[q], detected = 0;
-            const size_t qEnd = qStart[q + 1];
-            while (pos < qEnd) {
-                size_t end = pos;   // one target group = run of equal ext_id
-                while (end < qEnd && hOut[end].ext_id == hOut[pos].ext_id) ++end;
-                const bool stop = prm.max_overlaps != 0 && detected >= (size_t)prm.max_overlaps;
-                const float maxDiv = prm.query_max_divergence ? prm.query_max_divergence[q] : prm.max_divergence;
-                for (size_t i = pos; i < end; ++i) {
-                    const bool pass = hOut[i].seq_divergence < maxDiv;
-                    const bool keep = !stop && (pass || prm.keep_rejected);
-                    hOut[i].reserved = keep ? (pass ? 0u : 1u) : 0xffffffffu;
-                    detected += keep;
-                }
-                pos = end;
-            }
-            kept[q] = (uint32_t)detected;
-        }
-    });
     size_t wpos = 0;
     for (uint32_t q = 0; q < nQ; ++q) { ctx->resOffsets[q] = wpos; wpos += kept[q]; }
     ctx->resOffsets[nQ] = wpos;
