@@ -375,6 +375,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    step_detail = []   # API wall clock and host-side phase times of every timed step of this rank
     step_walls = []   # host wall clock of every single step of this rank, one list per timed region
     per_rank = []   # ms per step of every rank, one list per timed region (resident, e2e, roofline pass)
 
@@ -387,6 +388,8 @@ def main():
             t0 = time.perf_counter()
             step(upload)
             walls.append(round((time.perf_counter() - t0) * 1e3, 2))
+            step_detail.append({"wall": {p: round(v, 2) for p, v in wall.items()},
+                                "host": {p: round(v, 2) for p, v in phase_ms.items() if p.startswith(("host_", "prep_"))}})
         step_walls.append(walls)
         e1.record(stream)
         barrier()
@@ -539,7 +542,7 @@ def main():
                                       "lane (each kernel alone on the device); `value`, `e2e` and `phases_ms` come from the two-lane passes"},
             "phases_ms": {p: round(v, 3) for p, v in resident_phases.items()},
             "phases_ms_one_lane": {p: round(v, 3) for p, v in roof_phases.items()},
-            "phases_ms_e2e": {p: round(v, 3) for p, v in e2e_phases.items()}, "ms_per_step_of_every_rank": per_rank, "step_wall_ms_rank0": step_walls,
+            "phases_ms_e2e": {p: round(v, 3) for p, v in e2e_phases.items()}, "ms_per_step_of_every_rank": per_rank, "step_wall_ms_rank0": step_walls, "step_detail_rank0": step_detail,
             "api_wall_ms": {p: round(v, 2) for p, v in resident_wall.items()}, "e2e_api_wall_ms": {p: round(v, 2) for p, v in e2e_wall.items()},
             "work": {"kmer_hits": int(M), "target_groups": int(stats.get("n_pairs", 0)), "dp_pairs": int(stats.get("n_dp_pairs", 0)),
                      "dp_cells": int(stats.get("n_dp_cells", 0)), "overlaps": int(n_ovl),

@@ -46,7 +46,7 @@ def build_lib(force=False):
         objs.append(obj)
         if force or _newer(obj, [src] + headers):
             jobs.append([nvcc] + NVCC_FLAGS + ["-c", src, "-o", obj])
-    with ThreadPoolExecutor(max_workers=4) as ex:
+    with ThreadPoolExecutor(max_workers=int(os.environ.get("FLYE_B200_BUILD_JOBS", "4"))) as ex:
         list(ex.map(_run, jobs))
     if jobs or not os.path.exists(LIB):
         _run([nvcc, "-shared", "-o", LIB] + objs + ["-ldl"])

@@ -60,7 +60,11 @@ void installReads(fg_ctx* ctx, uint32_t n) {
     if (n) FG_CUDA(cudaMemcpyAsync(ctx->dLen.p, ctx->hLen.data(), n * 4ULL, cudaMemcpyHostToDevice, ctx->stream));
     FG_CUDA(cudaStreamSynchronize(ctx->stream));
     ctx->k = 0; ctx->counted = false; ctx->indexed = false;
-    ctx->hitBudget = 0;
+    // the hit budget of fg_overlaps_batch comes from the free device memory (cudaMemGetInfo: up to a few ms): keep it while the
+    // read set keeps its size, recompute when a differently sized one arrives
+    if (ctx->budgetBases == 0 || ctx->totalBases > ctx->budgetBases + ctx->budgetBases / 4 || ctx->totalBases + ctx->totalBases / 4 < ctx->budgetBases) {
+        ctx->hitBudget = 0; ctx->budgetBases = ctx->totalBases;
+    }
     ctx->dSlotOff.release();
     ctx->shardSet = false;
 }
@@ -264,7 +268,7 @@ int fg_build_index_minimizers(fg_ctx* ctx, int k, int minCov, int window, float 
 int fg_index_clear(fg_ctx* ctx) {
     return guarded(ctx, [&] {
         ctx->dEntries.release(); ctx->dIndexSlots.release(); ctx->dUKeys.release(); ctx->dUPayload.release();
-        ctx->dCountSlots.release(); ctx->dDense.release(); ctx->dSolidBits.release(); ctx->dIdxBits.release(); ctx->counts = fg::CountView{}; ctx->dSelBits.release();
+        ctx->dCountSlots.release(); ctx->dCount16.release(); ctx->dSolidBitsAll.release(); ctx->dDense.release(); ctx->dSolidBits.release(); ctx->dIdxBits.release(); ctx->counts = fg::CountView{}; ctx->dSelBits.release();
         ctx->indexed = false; ctx->counted = false;
     });
 }

@@ -200,11 +200,28 @@ __device__ inline void tableAddOne(const Table& t, uint64_t key) {
 // replicated table of the k-mers with count >= 2 (absent == 1).  Dense index: see count_index.cu.
 struct CountView {
     const uint32_t* dense = nullptr;
-    const uint32_t* solidBits = nullptr;   // optional front of `dense`: bit i set <=> class i occurs at least twice; dense then holds count - 1
+    const uint32_t* solidBits = nullptr;   // optional front: bit set <=> the class occurs at least twice; `dense` then holds count - 1
+    // multi-GPU: every rank's 16-bit saturated counters, all-gathered.  Class i lives at slot (i % nOwners) * nLocal + i / nOwners
+    // (solidBits uses the same slot numbering); a value of 65535 continues in `table` (class index -> count).
+    const uint16_t* count16 = nullptr;
+    uint64_t nLocal = 0;
+    uint32_t nOwners = 1, ownerShift = 0;   // ownerShift = log2(nOwners) if it is a power of two, else 0xffffffff
     Table table;
     int k = 0;
 };
+__device__ __forceinline__ uint64_t countSlotOf(const CountView& c, uint64_t i) {
+    if (c.ownerShift != 0xffffffffu) return (i & (c.nOwners - 1u)) * c.nLocal + (i >> c.ownerShift);
+    const uint64_t local = i / c.nOwners;
+    return (i - local * c.nOwners) * c.nLocal + local;
+}
 __device__ __forceinline__ bool testBit(const uint32_t* __restrict__ bits, uint64_t i) { return (__ldg(&bits[i >> 5]) >> (i & 31)) & 1u; }
+__device__ inline uint32_t countOfClass16(const CountView& c, uint64_t i) {
+    const uint64_t slot = countSlotOf(c, i);
+    if (c.solidBits && !testBit(c.solidBits, slot)) return 1u;   // callers only ask for k-mers that occur
+    uint32_t v = c.count16[slot];
+    if (v == 65535u) { uint64_t payload; if (tableFind(c.table, i, payload)) v = (uint32_t)payload; }
+    return v;
+}
 // count of the class of the k-mer given as its 2k-bit window `v` (base p in the lowest bits) ...
 __device__ inline uint32_t countOfWindow(const CountView& c, uint64_t v) {
     const uint64_t f = fwdFromWindow(v, c.k), r = (~v) & kmerMask(c.k);
@@ -213,11 +230,10 @@ __device__ inline uint32_t countOfWindow(const CountView& c, uint64_t v) {
         if (!c.solidBits) return c.dense[i];
         return testBit(c.solidBits, i) ? c.dense[i] + 1u : 1u;   // most positions of noisy reads are singletons: answered from the L2-resident bitmap
     }
-    uint64_t payload;
-    return tableFind(c.table, f < r ? f : r, payload) ? (uint32_t)payload : 1u;
+    return countOfClass16(c, denseIndexOfPair(f, r, c.k));
 }
-// ... or as a k-mer in the reference's representation (either orientation); a k-mer that never occurs reports 1 from the table
-// form and 0 from the dense form — callers only ask for k-mers that occur
+// ... or as a k-mer in the reference's representation (either orientation); a k-mer that never occurs reports 0 (1 behind a
+// bitmap front) — callers only ask for k-mers that occur
 __device__ inline uint32_t countOfKmer(const CountView& c, uint64_t kmer) {
     const uint64_t r = revCompKmer(kmer, c.k);
     if (c.dense) {
@@ -225,8 +241,7 @@ __device__ inline uint32_t countOfKmer(const CountView& c, uint64_t kmer) {
         if (!c.solidBits) return c.dense[i];
         return testBit(c.solidBits, i) ? c.dense[i] + 1u : 1u;
     }
-    uint64_t payload;
-    return tableFind(c.table, kmer < r ? kmer : r, payload) ? (uint32_t)payload : 1u;
+    return countOfClass16(c, denseIndexOfPair(kmer, r, c.k));
 }
 
 // index payload: [63:24] first entry, [23:0] size; all-ones size = repetitive k-mer

@@ -83,8 +83,8 @@ static void tileRange(const fg_ctx* ctx, uint32_t first, uint32_t count, size_t&
 // the array, its clearing and its scan all shrink with the rank count.  Every rank partitions the positions of its read
 // shard by owner (two passes over the packed reads: totals, then scatter of the 32-bit local slots), one grouped
 // ncclSend/ncclRecv all-to-all moves them over NVLink, and the owner counts what it receives.  The scan then yields, per
-// rank: its part of the freq -> #k-mers histogram (reduced with ncclAllReduce) and its k-mers with count >= 2, which are
-// all-gathered so that every rank holds the complete count table (absent == 1) that the per-read selection probes.
+// rank: its part of the freq -> #k-mers histogram (reduced with ncclAllReduce) and a 16-bit saturated copy of its counters;
+// the copies are all-gathered, so that every rank can look up any class by direct indexing, as on one GPU (CountView::count16).
 // ------------------------------------------------------------------------------------------------
 static constexpr int MAX_RANKS = 64;
 static bool envInt01(const char* name, int dflt) { const char* e = getenv(name); return (e ? atoi(e) : dflt) != 0; }
@@ -208,7 +208,8 @@ static constexpr int HIST_GLOBAL_BINS = 1 << 16;
 __global__ void __launch_bounds__(256) denseHistKernel(const uint4* __restrict__ dense4, uint64_t n8, const uint8_t* __restrict__ seenBytes,
                                                        uint8_t* __restrict__ solidBytes, unsigned long long* __restrict__ hist,
                                                        uint32_t* __restrict__ overflow, uint32_t* __restrict__ nOverflow, uint32_t overflowCap,
-                                                       unsigned long long* __restrict__ nSolid) {
+                                                       unsigned long long* __restrict__ nSolid, uint4* __restrict__ count16,
+                                                       uint32_t* __restrict__ overflowSlot) {
     __shared__ uint32_t sh[HIST_SMEM_BINS];
     for (int i = threadIdx.x; i < HIST_SMEM_BINS; i += blockDim.x) sh[i] = 0;
     __syncthreads();
@@ -217,21 +218,28 @@ __global__ void __launch_bounds__(256) denseHistKernel(const uint4* __restrict__
     for (uint64_t g = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; g < n8; g += (uint64_t)gridDim.x * blockDim.x) {
         const uint32_t seen = seenBytes ? seenBytes[g] : 0u;
         uint32_t solidByte = 0;
-        if (seenBytes && !seen) { if (solidBytes) solidBytes[g] = 0; continue; }   // (a counter is only ever touched after its bit)
+        if (seenBytes && !seen) {   // (a counter is only ever touched after its bit)
+            if (solidBytes) solidBytes[g] = 0;
+            if (count16) count16[g] = make_uint4(0, 0, 0, 0);
+            continue;
+        }
         const uint4 q0 = dense4[2 * g], q1 = dense4[2 * g + 1];
         const uint32_t cs[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+        uint32_t h16[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const uint32_t c = cs[j] + ((seen >> j) & 1u);   // with the bitmap the array holds count - 1
+            h16[j] = min(c, 65535u);
             if (!c) continue;
             ++distinct;
             if (c == 1u) continue;            // counted below as distinct - everything else
             ++solid; solidByte |= 1u << j;
             if (c < HIST_SMEM_BINS) atomicAdd(&sh[c], 1u);
             else if (c < HIST_GLOBAL_BINS) atomicAdd(&hist[c], 1ULL);
-            else { const uint32_t s = atomicAdd(nOverflow, 1u); if (s < overflowCap) overflow[s] = c; }
+            else { const uint32_t s = atomicAdd(nOverflow, 1u); if (s < overflowCap) { overflow[s] = c; if (overflowSlot) overflowSlot[s] = (uint32_t)(8 * g + j); } }
         }
         if (solidBytes) solidBytes[g] = (uint8_t)solidByte;
+        if (count16) count16[g] = make_uint4(h16[0] | (h16[1] << 16), h16[2] | (h16[3] << 16), h16[4] | (h16[5] << 16), h16[6] | (h16[7] << 16));
     }
     __syncthreads();
     for (int i = threadIdx.x; i < HIST_SMEM_BINS; i += blockDim.x)
@@ -241,38 +249,6 @@ __global__ void __launch_bounds__(256) denseHistKernel(const uint4* __restrict__
     if ((threadIdx.x & 31) == 0) {
         if (distinct) { atomicAdd(&hist[0], (unsigned long long)distinct); atomicAdd(&hist[1], (unsigned long long)(distinct - solid)); }
         if (solid) atomicAdd(nSolid, (unsigned long long)solid);
-    }
-}
-
-// pass 2: (canonical k-mer, count) of every class with count >= 2, appended in no particular order (they go into a hash table)
-__global__ void __launch_bounds__(256) denseEmitKernel(const uint4* __restrict__ dense4, uint64_t n4, const uint8_t* __restrict__ seenBytes, DenseMap m,
-                                                       uint64_t* __restrict__ keys, uint32_t* __restrict__ counts, unsigned long long* __restrict__ cursor) {
-    const int lane = threadIdx.x & 31;
-    // whole warps step together (the append is warp aggregated)
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    const uint64_t nIter = (n4 + stride - 1) / stride;
-    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    for (uint64_t it = 0; it < nIter; ++it, i += stride) {
-        uint4 q = make_uint4(0, 0, 0, 0);
-        uint32_t seen = 0;
-        if (i < n4) { q = dense4[i]; if (seenBytes) seen = (seenBytes[i >> 1] >> ((i & 1) * 4)) & 15u; }
-        const uint32_t cs[4] = {q.x + (seen & 1u), q.y + ((seen >> 1) & 1u), q.z + ((seen >> 2) & 1u), q.w + ((seen >> 3) & 1u)};
-        const uint32_t mine = (cs[0] >= 2u) + (cs[1] >= 2u) + (cs[2] >= 2u) + (cs[3] >= 2u);
-        if (!__any_sync(0xffffffffu, mine != 0u)) continue;
-        uint32_t incl = mine;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += v; }
-        unsigned long long base = 0;
-        if (lane == 31) base = atomicAdd(cursor, (unsigned long long)incl);
-        base = __shfl_sync(0xffffffffu, base, 31) + (incl - mine);
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-            if (cs[j] >= 2u) {
-                const uint64_t local = 4ULL * i + j;
-                keys[base] = canonFromDenseIndex(local * m.nOwners + m.owner, m.k);
-                counts[base] = cs[j];
-                ++base;
-            }
     }
 }
 
@@ -309,7 +285,7 @@ void countKmers(fg_ctx* ctx, int k) {
     const size_t nTiles = tHi - tLo;
     ctx->hist.clear();
     ctx->nDistinct = 0;
-    ctx->dCountSlots.release(); ctx->dDense.release(); ctx->dSolidBits.release();
+    ctx->dCountSlots.release(); ctx->dCount16.release(); ctx->dSolidBitsAll.release(); ctx->dDense.release(); ctx->dSolidBits.release();
     ctx->counts = CountView{};
     // counting invalidates the index (setKmerSize): give its memory back before the counters are allocated
     ctx->dEntries.release(); ctx->dIndexSlots.release(); ctx->dUKeys.release(); ctx->dUPayload.release();
@@ -340,7 +316,7 @@ void countKmers(fg_ctx* ctx, int k) {
         }
     } else {
         const int R = ctx->nRanks;
-        if (nLocal >= (1ULL << 32)) throw Error(FG_ERR_ARG, "dense k-mer slots do not fit 32 bits");   // (cannot happen for k <= 17, N >= 2)
+        if (nLocal > (1ULL << 32)) throw Error(FG_ERR_ARG, "dense k-mer slots do not fit 32 bits");   // (cannot happen for k <= 17, N >= 2: k = 17 on two ranks uses exactly 2^32 slots)
         DevBuf<unsigned long long> dTot(3 * MAX_RANKS);   // totals, segment starts, cursors
         std::vector<unsigned long long> hTot(R, 0), hStart(R, 0);
         DevBuf<uint32_t> sendBuf, recvBuf;
@@ -381,7 +357,9 @@ void countKmers(fg_ctx* ctx, int k) {
     // histogram (vertex_index.cpp:567-576), distinct k-mers, k-mers with count >= 2
     DevBuf<unsigned long long> dHist(HIST_GLOBAL_BINS), dSolid(2);
     const uint32_t ovCap = 1u << 20;
-    DevBuf<uint32_t> dOv(ovCap), dNOv(1);
+    DevBuf<uint32_t> dOv(ovCap), dNOv(1), dOvSlot;
+    DevBuf<uint16_t> local16;   // multi-GPU: this rank's counters, saturated to 16 bits, for the all-gather below
+    if (multi) { local16.alloc(nLocal); dOvSlot.alloc(ovCap); }
     unsigned long long hSolid = 0;
     uint32_t nOv = 0;
     {
@@ -393,7 +371,7 @@ void countKmers(fg_ctx* ctx, int k) {
         denseHistKernel<<<gridFor(nLocal / 8, 256, 16), 256, 0, ctx->stream>>>(reinterpret_cast<const uint4*>(dense.p), nLocal / 8,
                                                                               reinterpret_cast<const uint8_t*>(seenBits.p),
                                                                               reinterpret_cast<uint8_t*>(ctx->dSolidBits.p), dHist.p, dOv.p, dNOv.p,
-                                                                              ovCap, dSolid.p);
+                                                                              ovCap, dSolid.p, reinterpret_cast<uint4*>(local16.p), dOvSlot.p);
         checkLaunch(ctx, "denseHistKernel");
         FG_CUDA(cudaMemcpyAsync(&hSolid, dSolid.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
         FG_CUDA(cudaMemcpyAsync(&nOv, dNOv.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -406,44 +384,57 @@ void countKmers(fg_ctx* ctx, int k) {
         // one GPU: the counter array IS the count structure of the selection (no table, no second pass over the counters)
         ctx->counts.dense = dense.p; ctx->counts.solidBits = ctx->dSolidBits.p; ctx->counts.k = k;
     } else {
-        // this rank's k-mers with count >= 2, all-gathered into the replicated table
-        DevBuf<uint64_t> solidKeys(std::max<uint64_t>(hSolid, 1));
-        DevBuf<uint32_t> solidCounts(std::max<uint64_t>(hSolid, 1));
-        {
-            PhaseTimer pt(ctx, "count_emit");
-            if (hSolid) {
-                denseEmitKernel<<<gridFor(nLocal / 4, 256, 16), 256, 0, ctx->stream>>>(reinterpret_cast<const uint4*>(dense.p), nLocal / 4,
-                                                                                      reinterpret_cast<const uint8_t*>(seenBits.p), m, solidKeys.p,
-                                                                                      solidCounts.p, dSolid.p + 1);
-                checkLaunch(ctx, "denseEmitKernel");
-            }
-        }
-        dense.release(); ctx->dSolidBits.release();
-        uint64_t nSolidAll = 0;
-        DevBuf<uint64_t> allKeys; DevBuf<uint32_t> allCounts;
+        // Every rank needs the count of every k-mer of its reads (selection) and of its index keys (classification).  The owners'
+        // counters, saturated to 16 bits, are all-gathered: 2 bytes per class (k = 15: 1 GB, k = 17: 17 GB per rank) moved once over
+        // NVLink, then every lookup is a direct index as on one GPU — no table of the solid k-mers is built, nothing is inserted
+        // on every rank.  The (rare) counts >= 65535 go to a small replicated table; the "at least twice" bitmaps are gathered too
+        // and stay in the L2 in front of the array.
+        dense.release();
+        const int R = ctx->nRanks;
         {
             PhaseTimer pt(ctx, "count_merge");
             allReduceSumU64(ctx, dHist.p, HIST_GLOBAL_BINS);
-            std::vector<uint64_t> offs;
-            allGatherSizes(ctx, hSolid * 8ULL, offs);
-            nSolidAll = offs.back() / 8;
-            allKeys.alloc(std::max<uint64_t>(nSolidAll, 1)); allCounts.alloc(std::max<uint64_t>(nSolidAll, 1));
-            allGatherVInto(ctx, solidKeys.p, offs, allKeys.p);
-            for (auto& o : offs) o /= 2;
-            allGatherVInto(ctx, solidCounts.p, offs, allCounts.p);
-            // counts beyond the histogram's dense bins are rare: gather the few values
-            DevBuf<char> ovAll; std::vector<uint64_t> ovOff;
-            allGatherV(ctx, dOv.p, nOv * 4ULL, ovAll, ovOff);
-            ov.resize(ovOff.back() / 4);
-            if (!ov.empty()) FG_CUDA(cudaMemcpyAsync(ov.data(), ovAll.p, ov.size() * 4ULL, cudaMemcpyDeviceToHost, ctx->stream));
+            std::vector<uint64_t> offs(R + 1);
+            for (int r = 0; r <= R; ++r) offs[r] = (uint64_t)r * nLocal * 2ULL;
+            ctx->dCount16.alloc((uint64_t)R * nLocal);
+            allGatherVInto(ctx, local16.p, offs, ctx->dCount16.p);
+            local16.release();
+            if (front) {
+                for (int r = 0; r <= R; ++r) offs[r] = (uint64_t)r * (nLocal / 8);
+                ctx->dSolidBitsAll.alloc((uint64_t)R * (nLocal / 32));
+                allGatherVInto(ctx, ctx->dSolidBits.p, offs, ctx->dSolidBitsAll.p);
+            }
+            ctx->dSolidBits.release();
+            // counters beyond 16 bits (also beyond the histogram's dense bins): (class index, count) of every rank
+            std::vector<uint32_t> slots(nOv);
+            if (nOv) FG_CUDA(cudaMemcpyAsync(slots.data(), dOvSlot.p, nOv * 4ULL, cudaMemcpyDeviceToHost, ctx->stream));
             FG_CUDA(cudaStreamSynchronize(ctx->stream));
+            std::vector<uint64_t> mine(2 * (size_t)nOv);
+            for (uint32_t i = 0; i < nOv; ++i) { mine[2 * i] = (uint64_t)slots[i] * m.nOwners + m.owner; mine[2 * i + 1] = ov[i]; }
+            DevBuf<uint64_t> dMine(std::max<size_t>(mine.size(), 1));
+            if (nOv) FG_CUDA(cudaMemcpyAsync(dMine.p, mine.data(), mine.size() * 8ULL, cudaMemcpyHostToDevice, ctx->stream));
+            DevBuf<char> ovAll; std::vector<uint64_t> ovOff;
+            allGatherV(ctx, dMine.p, nOv * 16ULL, ovAll, ovOff);
+            const size_t nBig = ovOff.back() / 16;
+            std::vector<uint64_t> big(2 * nBig);
+            if (nBig) FG_CUDA(cudaMemcpyAsync(big.data(), ovAll.p, nBig * 16ULL, cudaMemcpyDeviceToHost, ctx->stream));
+            FG_CUDA(cudaStreamSynchronize(ctx->stream));
+            ov.resize(nBig);
+            for (size_t i = 0; i < nBig; ++i) ov[i] = (uint32_t)big[2 * i + 1];
+            ctx->counts.table = makeTable(ctx, ctx->dCountSlots, nBig);
+            if (nBig) {
+                DevBuf<uint64_t> bk(nBig); DevBuf<uint32_t> bc(nBig);
+                std::vector<uint64_t> hk(nBig); std::vector<uint32_t> hc(nBig);
+                for (size_t i = 0; i < nBig; ++i) { hk[i] = big[2 * i]; hc[i] = (uint32_t)big[2 * i + 1]; }
+                FG_CUDA(cudaMemcpyAsync(bk.p, hk.data(), nBig * 8ULL, cudaMemcpyHostToDevice, ctx->stream));
+                FG_CUDA(cudaMemcpyAsync(bc.p, hc.data(), nBig * 4ULL, cudaMemcpyHostToDevice, ctx->stream));
+                buildCountTableKernel<<<gridFor(nBig, 256, 16), 256, 0, ctx->stream>>>(bk.p, bc.p, nBig, ctx->counts.table);
+                checkLaunch(ctx, "buildCountTableKernel");
+                FG_CUDA(cudaStreamSynchronize(ctx->stream));
+            }
         }
-        PhaseTimer pt(ctx, "count_table");
-        ctx->counts.table = makeTable(ctx, ctx->dCountSlots, nSolidAll); ctx->counts.k = k;
-        if (nSolidAll) {
-            buildCountTableKernel<<<gridFor(nSolidAll, 256, 16), 256, 0, ctx->stream>>>(allKeys.p, allCounts.p, nSolidAll, ctx->counts.table);
-            checkLaunch(ctx, "buildCountTableKernel");
-        }
+        ctx->counts.count16 = ctx->dCount16.p; ctx->counts.solidBits = ctx->dSolidBitsAll.p;
+        ctx->counts.nLocal = nLocal; ctx->counts.nOwners = m.nOwners; ctx->counts.ownerShift = m.ownerShift; ctx->counts.k = k;
         FG_CUDA(cudaStreamSynchronize(ctx->stream));
     }
     std::vector<unsigned long long> hHist(HIST_GLOBAL_BINS);
@@ -460,12 +451,12 @@ __global__ void kmerFreqKernel(const uint64_t* kmers, uint32_t n, CountView coun
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint32_t c = countOfKmer(counts, kmers[i] & kmerMask(counts.k));
-    out[i] = (counts.dense ? c >= 2u : c != 1u) ? c : 0xFFFFFFFFu;   // ~0: count is 0 or 1
+    out[i] = c >= 2u ? c : 0xFFFFFFFFu;   // ~0: count is 0 or 1
 }
 
 void kmerFreqQuery(fg_ctx* ctx, const uint64_t* kmers, uint32_t n, uint32_t* out) {
     if (!ctx->counted) throw Error(FG_ERR_ARG, "fg_count_kmers has not run");
-    if (!ctx->counts.dense && !ctx->dCountSlots.p) throw Error(FG_ERR_ARG, "the k-mer counters were released when the index was built");
+    if (!ctx->counts.dense && !ctx->counts.count16) throw Error(FG_ERR_ARG, "the k-mer counters were released when the index was built");
     if (!n) return;
     DevBuf<uint64_t> dK(n); DevBuf<uint32_t> dO(n);
     FG_CUDA(cudaMemcpyAsync(dK.p, kmers, n * 8ULL, cudaMemcpyHostToDevice, ctx->stream));
@@ -1248,7 +1239,10 @@ static void buildFromSelection(fg_ctx* ctx, DevBuf<uint32_t>& rcBits, int minCov
     FG_CUDA(cudaMemcpyAsync(hStats, dStats.p, 32, cudaMemcpyDeviceToHost, ctx->stream));
     FG_CUDA(cudaStreamSynchronize(ctx->stream));
     // the k-mer counters were last needed by the classification: large ones (k >= 16: 17 / 34 GB) go back before the table is built
-    if (ctx->dDense.bytes() > (4ULL << 30)) { ctx->dDense.release(); ctx->dSolidBits.release(); ctx->counts = CountView{}; }
+    if (ctx->dDense.bytes() > (4ULL << 30) || ctx->dCount16.bytes() > (4ULL << 30)) {
+        ctx->dDense.release(); ctx->dSolidBits.release(); ctx->dCount16.release(); ctx->dSolidBitsAll.release(); ctx->dCountSlots.release();
+        ctx->counts = CountView{};
+    }
     (ukeys == keysA.p ? keysA : keysB).release();
     starts.release();
     if (hStats[3]) throw Error(FG_ERR_TOO_FREQ, "k-mer is too frequent");   // (all ranks see the reduced flag: they throw together)
@@ -1312,7 +1306,7 @@ void buildIndexSolid(fg_ctx* ctx, int minFreq, float selectRate, int tandemFreq,
     size_t tLo, tHi;
     tileRange(ctx, firstRead, nReadsShard, tLo, tHi);
     {
-        L2Pin pinSolid(ctx, ctx->dSolidBits.p, ctx->dSolidBits.bytes(), 2);   // the "count >= 2" bitmap answers most lookups: keep it in the L2
+        L2Pin pinSolid(ctx, ctx->counts.solidBits, ctx->dSolidBits.p ? ctx->dSolidBits.bytes() : ctx->dSolidBitsAll.bytes(), 2);   // the "count >= 2" bitmap answers most lookups: keep it in the L2
         PhaseTimer pt(ctx, "select");
         const uint64_t slotBase = ctx->hSlotOff[firstRead], shardSlots = ctx->hSlotOff[firstRead + nReadsShard] - slotBase;
         DevBuf<uint32_t> freq(std::max<uint64_t>(shardSlots, 1));

@@ -122,7 +122,9 @@ struct fg_ctx {
     bool counted = false;
     uint64_t nDistinct = 0;
     std::map<uint64_t, uint64_t> hist;    // freq -> #distinct canonical k-mers
-    fg::DevBuf<ulonglong2> dCountSlots;   // multi-GPU: replicated table canonical k-mer -> count, only counts >= 2 (absent = 1)
+    fg::DevBuf<ulonglong2> dCountSlots;   // multi-GPU: replicated table class index -> count for the (rare) counts >= 65535
+    fg::DevBuf<uint16_t> dCount16;        // multi-GPU: every rank's saturated 16-bit counters, all-gathered (CountView::count16)
+    fg::DevBuf<uint32_t> dSolidBitsAll;   // multi-GPU: every rank's "occurs at least twice" bitmap, all-gathered
     fg::DevBuf<uint32_t> dDense;          // one GPU: the dense counter array itself (count_index.cu), kept until the index is built
     fg::DevBuf<uint32_t> dSolidBits;      // 1 bit per class: occurs at least twice (only while the bitmap fits the L2, k <= 15)
     fg::CountView counts;
@@ -156,6 +158,7 @@ struct fg_ctx {
     std::mutex hostPoolMutex;             // one parallelFor at a time (the lanes share the pool)
     std::mutex pressureMutex;             // one arena at a time asks the others to give cached blocks back
     uint64_t hitBudget = 0;               // k-mer hits per sub-batch and lane, derived once from the free device memory
+    uint64_t budgetBases = 0;          // totalBases of the read set hitBudget was computed for
     // results after the divergence / maxOverlaps filter (when it removed something); two buffers: fg_overlaps_refilter
     // compacts from the one that holds the last result into the other
     std::unique_ptr<fg_overlap[]> resCompact[2];
