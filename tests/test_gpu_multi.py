@@ -73,6 +73,8 @@ def _n_gpus():
 @pytest.mark.parametrize("cfg,k,sim", [
     ("raw_reads.cfg", 15, dict(genome_len=150000, coverage=15, seed=61)),
     ("hifi.cfg", 17, dict(genome_len=100000, coverage=12, mean_len=8000, shape=20, error=0.005, seed=62)),
+    # solid k-mers with k = 17 (configs[2] / [3]): 2^33 classes, exactly 2^32 counter slots per rank, 64-bit keys in the index
+    ("raw_reads.cfg", 17, dict(genome_len=120000, coverage=14, error=0.10, seed=63)),
 ])
 def test_two_gpu_parity(built, engine, tmp_path, cfg, k, sim):
     tmp = str(tmp_path)
