@@ -71,6 +71,12 @@ void commUniqueId(uint8_t* id) {
 }
 
 void commInit(fg_ctx* ctx, int nRanks, int rank, const uint8_t* id) {
+    // the ranks of one box share its host cores: size the per-context host pool accordingly (FG_HOST_THREADS overrides)
+    {
+        unsigned t = std::max(2u, std::min(16u, std::thread::hardware_concurrency() / (unsigned)std::max(1, nRanks)));
+        if (const char* e = getenv("FG_HOST_THREADS")) t = (unsigned)std::max(1, atoi(e));
+        ctx->hostPool.maxThreads = t;
+    }
     if (nRanks < 1 || rank < 0 || rank >= nRanks) throw Error(FG_ERR_ARG, "bad rank / world size");
     commDestroy(ctx);
     ctx->nRanks = nRanks; ctx->rank = rank;

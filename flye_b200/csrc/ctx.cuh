@@ -38,10 +38,11 @@ class HostPool {
         }
     }
 public:
+    unsigned maxThreads = 16;   // lowered when several ranks share the host (fg_comm_init: cores / ranks); fixed once the workers exist
     // fn(a, b) over a partition of [0, n) into contiguous ranges, one per worker; returns when all are done
     // (`work`: number of elementary items behind the n ranges, decides whether threads are worth it)
     void parallelFor(size_t n, const std::function<void(size_t, size_t)>& fn, size_t work = 0) {
-        const unsigned T = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+        const unsigned T = std::max(1u, std::min(maxThreads, std::thread::hardware_concurrency()));
         if (std::max(n, work) < 20000 || n < T || T == 1) { fn(0, n); return; }
         if (workers.empty()) for (unsigned t = 0; t < T; ++t) workers.emplace_back(&HostPool::run, this, t);
         std::unique_lock<std::mutex> lk(m);

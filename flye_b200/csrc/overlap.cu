@@ -1815,7 +1815,8 @@ struct OrderedCommit {
 };
 
 static void recordDivergences(fg_ctx* ctx, fg_overlap* recs, size_t n, const fg_overlap_params& prm);
-static void sliceEpilogue(fg_ctx* ctx, fg_overlap* recs, size_t n, size_t sliceOff, const fg_overlap_params& prm, OrderedCommit& commit);
+static void sliceEpilogue(fg_ctx* ctx, fg_overlap* recs, size_t n, size_t sliceOff, const fg_overlap_params& prm, OrderedCommit& commit,
+                          size_t qFirst, size_t qCount);
 
 static void overlapsChunk(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, uint32_t qOffset, const fg_overlap_params& prm, const OvParams& P,
                           OrderedCommit& commit, size_t& subBase, uint64_t& totHits, BatchTotals& tot, const float* dQueryMaxDiv) {
@@ -2260,7 +2261,7 @@ static void overlapsChunk(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, ui
                     // seqDivergence of this slice's records (host arithmetic with glibc logf), while the other lanes keep the device busy
                     HostTimer he(ctx, "host_divergence");
                     recordDivergences(ctx, dst, nOut, prm);
-                    sliceEpilogue(ctx, dst, nOut, myOff, prm, commit);   // threshold / maxOverlaps replay of this slice's queries
+                    sliceEpilogue(ctx, dst, nOut, myOff, prm, commit, (size_t)qOffset + qa, nq);   // threshold / maxOverlaps replay of this slice's queries
                 }
             }
         }
@@ -2346,37 +2347,34 @@ static void recordDivergences(fg_ctx* ctx, fg_overlap* recs, size_t n, const fg_
 // query's records start, then the replay of the divergence threshold (overlap.cpp:470) and of the maxOverlaps cut (:218-219),
 // which only depends on the query's own records.  Dropped records are marked in `reserved`; the call's tail only has to turn the
 // kept counts into offsets and compact if anything was dropped.  Runs on the host pool while the other lane keeps the device busy.
-static void sliceEpilogue(fg_ctx* ctx, fg_overlap* recs, size_t n, size_t sliceOff, const fg_overlap_params& prm, OrderedCommit& commit) {
+static void sliceEpilogue(fg_ctx* ctx, fg_overlap* recs, size_t n, size_t sliceOff, const fg_overlap_params& prm, OrderedCommit& commit,
+                          size_t qFirst, size_t qCount) {
     if (!n) return;
     const size_t nQ = commit.kept.size();
     std::vector<size_t>& qStart = commit.qStart;
     std::lock_guard<std::mutex> lk(ctx->hostPoolMutex);
-    // (1) first record of every query of the slice
-    std::vector<std::vector<uint32_t>> found(1);
-    std::mutex fm;
+    // (1) first record of every query of the slice (queries qFirst ... qFirst + qCount - 1 of the call, in order)
     ctx->hostPool.parallelFor(n, [&](size_t a, size_t b) {
-        std::vector<uint32_t> mine;
         for (size_t i = a; i < b; ++i) {
             const fg_overlap& o = recs[i];
             if (i == 0 || recs[i - 1].reserved != o.reserved) {
-                if (o.reserved >= nQ || (i && recs[i - 1].reserved > o.reserved)) { commit.badOrder = true; continue; }
+                if (o.reserved >= nQ || o.reserved < qFirst || o.reserved >= qFirst + qCount || (i && recs[i - 1].reserved > o.reserved)) { commit.badOrder = true; continue; }
                 qStart[o.reserved] = sliceOff + i;
-                mine.push_back(o.reserved);
             }
         }
-        std::lock_guard<std::mutex> g(fm);
-        found.emplace_back(std::move(mine));
     }, n);
     if (commit.badOrder) return;
-    std::vector<uint32_t> qs;
-    for (auto& v : found) qs.insert(qs.end(), v.begin(), v.end());
-    std::sort(qs.begin(), qs.end());
+    // end of every query's records = start of the next query that has any
+    std::vector<size_t> qEndOf(qCount);
+    size_t nextStart = sliceOff + n;
+    for (size_t j = qCount; j-- > 0;) { qEndOf[j] = nextStart; if (qStart[qFirst + j] != SIZE_MAX) nextStart = qStart[qFirst + j]; }
     // (2) replay per query
-    ctx->hostPool.parallelFor(qs.size(), [&](size_t ja, size_t jb) {
+    ctx->hostPool.parallelFor(qCount, [&](size_t ja, size_t jb) {
         for (size_t j = ja; j < jb; ++j) {
-            const uint32_t q = qs[j];
+            const size_t q = qFirst + j;
+            if (qStart[q] == SIZE_MAX) continue;
             size_t pos = qStart[q] - sliceOff, detected = 0;
-            const size_t qEnd = j + 1 < qs.size() ? qStart[qs[j + 1]] - sliceOff : n;
+            const size_t qEnd = qEndOf[j] - sliceOff;
             const float maxDiv = prm.query_max_divergence ? prm.query_max_divergence[q] : prm.max_divergence;
             while (pos < qEnd) {
                 size_t end = pos;   // one target group = run of equal ext_id
