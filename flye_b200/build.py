@@ -73,9 +73,10 @@ def build_tools():
         _run(["g++", "-O2", "-std=c++17", src, "-o", exe])
 
 
-    for name in ("rundp_check", "wfa_check", "segsort_check", "dense_check"):   # CPU models: run-compressed DP / chain walk, bounded wavefronts, segmented radix sort, dense k-mer class index
+    # CPU models: run-compressed DP / chain walk, bounded wavefronts, segmented radix sort, dense k-mer class index, glibc's logf
+    for name in ("rundp_check", "wfa_check", "segsort_check", "dense_check", "logf_check"):
         src, exe = os.path.join(ROOT, "tests", "cpu_models", name + ".cpp"), os.path.join(out, name)
-        if _newer(exe, [src, os.path.join(CSRC, "kmer_math.cuh")]):
+        if _newer(exe, [src, os.path.join(CSRC, "kmer_math.cuh"), os.path.join(CSRC, "glibc_logf.cuh")]):
             _run(["g++", "-O2", "-std=c++17", src, "-o", exe])
     src, so = os.path.join(ROOT, "tests", "cpu_models", "stdsort_lib.cpp"), os.path.join(out, "libstdsort.so")
     if _newer(so, [src]):

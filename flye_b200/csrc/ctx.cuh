@@ -158,6 +158,7 @@ struct fg_ctx {
     fg::HostPool hostPool;
     std::mutex hostPoolMutex;             // one parallelFor at a time (the lanes share the pool)
     std::mutex pressureMutex;             // one arena at a time asks the others to give cached blocks back
+    int devEpilogueState = 0;             // device epilogue of fg_overlaps_batch: 0 = not tested yet, 1 = the device's logf matched the host's, -1 = it did not
     uint64_t hitBudget = 0;               // k-mer hits per sub-batch and lane, derived once from the free device memory
     uint64_t budgetBases = 0;          // totalBases of the read set hitBudget was computed for
     // results after the divergence / maxOverlaps filter (when it removed something); two buffers: fg_overlaps_refilter

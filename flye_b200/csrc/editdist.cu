@@ -276,6 +276,15 @@ __global__ void __launch_bounds__(128) wfaKernel(fg_overlap* __restrict__ ov, ui
     }
 }
 
+// longest cur / ext range of a batch of overlaps (sizes the global wavefront scratch)
+__global__ void __launch_bounds__(256) maxRangeKernel(const fg_overlap* __restrict__ ov, uint32_t nOv, uint32_t* __restrict__ out) {
+    uint32_t m = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nOv; i += gridDim.x * blockDim.x)
+        m = max(m, (uint32_t)max(max(0, ov[i].cur_end - ov[i].cur_begin), max(0, ov[i].ext_end - ov[i].ext_begin)));
+    for (int d = 16; d; d >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, d));
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
+}
+
 // homopolymer-compressed copy of a sequence set (see K9a)
 static void buildHpc(fg_ctx* ctx, fg_ctx::HpcCache& c, const uint64_t* seq, const uint64_t* wordOff, const uint32_t* len, uint32_t nReads,
                      uint64_t nWords) {
@@ -305,8 +314,17 @@ void editDistances(fg_ctx* ctx, fg_overlap* dOv, const fg_overlap* hOv, uint32_t
                    const float* dQueryMaxDivergence) {
     if (!nOv) return;
     uint32_t maxLen = 0;
-    for (uint32_t i = 0; i < nOv; ++i)
-        maxLen = std::max(maxLen, (uint32_t)std::max(std::max(0, hOv[i].cur_end - hOv[i].cur_begin), std::max(0, hOv[i].ext_end - hOv[i].ext_begin)));
+    if (hOv) {
+        for (uint32_t i = 0; i < nOv; ++i)
+            maxLen = std::max(maxLen, (uint32_t)std::max(std::max(0, hOv[i].cur_end - hOv[i].cur_begin), std::max(0, hOv[i].ext_end - hOv[i].ext_begin)));
+    } else {   // no host copy of the records (device epilogue): the longest range comes from a reduction on the device
+        DevBuf<uint32_t> dMax(1);
+        FG_CUDA(cudaMemsetAsync(dMax.p, 0, 4, streamOf(ctx)));
+        maxRangeKernel<<<gridFor(nOv), 256, 0, streamOf(ctx)>>>(dOv, nOv, dMax.p);
+        checkLaunch(ctx, "maxRangeKernel");
+        FG_CUDA(cudaMemcpyAsync(&maxLen, dMax.p, 4, cudaMemcpyDeviceToHost, streamOf(ctx)));
+        FG_CUDA(cudaStreamSynchronize(streamOf(ctx)));
+    }
     HpcSet ext{ctx->dSeq.p, nullptr, nullptr, nullptr, ctx->dWordOff.p, ctx->dLen.p};
     HpcSet cur = ext;
     if (querySet) cur = HpcSet{ctx->dQsSeq.p, nullptr, nullptr, nullptr, ctx->dQsWordOff.p, ctx->dQsLen.p};

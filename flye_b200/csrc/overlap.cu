@@ -27,12 +27,15 @@
 // FG_HIT_RADIX / FG_DP_MODE / FG_SORT_HUGE select the older, slower device paths (kept as cross-checks, tests/test_gpu_parity.py).
 #include "ctx.cuh"
 #include "introsort_warp.cuh"
+#include "glibc_logf.cuh"
 
 #include <cub/cub.cuh>
 #include <cooperative_groups.h>
 #include <algorithm>
 #include <cmath>
+#include <cstddef>
 #include <cstdlib>
+#include <cstring>
 #include <functional>
 #include <memory>
 #include <thread>
@@ -225,7 +228,12 @@ __global__ void __launch_bounds__(256) gatherSortedHitsKernel(const uint32_t* __
 // next pass are accumulated while scattering (the destination tells the owning warp).  The segment ping-pongs between two
 // buffers (L2 resident for all but the longest reads); the last pass writes the Elem records.
 static constexpr int SEG_WARPS = 16;
-template <int MIN_CTAS>
+// DEEP = false: two-step register prefetch in the scatter passes, four loads in flight in the count pass, one pair of loads per
+// iteration of the flag loop (the kernel of rounds 1-2).  DEEP = true (default, FG_SRS_DEEP=0 switches back): the same algorithm with
+// more independent loads in flight per thread — eight in the count pass, a four-step prefetch ring in the scatter passes, four
+// positions per iteration of the flag loop.  The kernel is bound by load latency x bytes in flight (Little's law: 48 warps x 2 x
+// 256 B per SM sustain ~1.9 TB/s at the ~2 us a load takes here — exactly the DRAM read rate ncu reports), not by bytes or issue.
+template <int MIN_CTAS, bool DEEP>
 __global__ void __launch_bounds__(SEG_WARPS * 32, MIN_CTAS) segRadixSortKernel(unsigned long long* bufA, unsigned long long* bufB,
                                                                          const uint64_t* __restrict__ qHitOff, uint32_t qFirst, uint64_t hitBase,
                                                                          int posBits, int nPass, Elem* __restrict__ hits, uint8_t* __restrict__ groupFlags) {
@@ -246,12 +254,13 @@ __global__ void __launch_bounds__(SEG_WARPS * 32, MIN_CTAS) segRadixSortKernel(u
     for (int i = threadIdx.x; i < SEG_WARPS * 256; i += blockDim.x) (&cur[0][0])[i] = 0u;
     __syncthreads();
     // counts of the first pass: order does not matter here, one shared-memory atomic per element (four independent loads in flight)
-    for (uint32_t i0 = wBeg; i0 < wEnd; i0 += 128) {
-        unsigned long long x[4];
+    constexpr int CU = DEEP ? 8 : 4;
+    for (uint32_t i0 = wBeg; i0 < wEnd; i0 += 32 * CU) {
+        unsigned long long x[CU];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) { const uint32_t i = i0 + 32 * u + lane; x[u] = i < wEnd ? src[i] : ~0ULL; }
+        for (int u = 0; u < CU; ++u) { const uint32_t i = i0 + 32 * u + lane; x[u] = i < wEnd ? src[i] : ~0ULL; }
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
+        for (int u = 0; u < CU; ++u)
             if (i0 + 32 * u + lane < wEnd) atomicAdd(&cur[w][(uint32_t)(x[u] >> idShift) & 255u], 1u);
     }
     __syncthreads();
@@ -280,15 +289,10 @@ __global__ void __launch_bounds__(SEG_WARPS * 32, MIN_CTAS) segRadixSortKernel(u
         __syncthreads();
         for (int i = threadIdx.x; i < SEG_WARPS * 256; i += blockDim.x) (&nxt[0][0])[i] = 0u;
         __syncthreads();
-        xn = wBeg + lane < wEnd ? src[wBeg + lane] : 0ULL;
-        xn2 = wBeg + 32 + lane < wEnd ? src[wBeg + 32 + lane] : 0ULL;
-        for (uint32_t i0 = wBeg; i0 < wEnd; i0 += 32) {
-            const uint32_t i = i0 + lane;
-            const bool act = i < wEnd;
+        // one step: 32 consecutive elements of the warp's chunk, `x` = this lane's element
+        auto step = [&](const uint32_t i0, const unsigned long long x) {
+            const bool act = i0 + lane < wEnd;
             const uint32_t am = __ballot_sync(0xffffffffu, act);
-            const unsigned long long x = xn;
-            xn = xn2;
-            if (i + 64 < wEnd) xn2 = src[i + 64];
             if (act) {
                 const uint32_t d = (uint32_t)(x >> sh) & 255u;
                 const uint32_t peers = __match_any_sync(am, d);
@@ -305,12 +309,53 @@ __global__ void __launch_bounds__(SEG_WARPS * 32, MIN_CTAS) segRadixSortKernel(u
                 }
             }
             __syncwarp();
+        };
+        if (DEEP) {
+            unsigned long long ring[4];   // the elements of the next four steps (slot = step number mod 4, compile-time after unrolling)
+#pragma unroll
+            for (int u = 0; u < 4; ++u) ring[u] = wBeg + 32 * u + lane < wEnd ? src[wBeg + 32 * u + lane] : 0ULL;
+            for (uint32_t i0 = wBeg; i0 < wEnd; i0 += 128) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const uint32_t s0 = i0 + 32 * u;
+                    if (s0 < wEnd) {   // warp uniform
+                        const unsigned long long x = ring[u];
+                        if (s0 + 128 + lane < wEnd) ring[u] = src[s0 + 128 + lane];
+                        step(s0, x);
+                    }
+                }
+            }
+        } else {
+            xn = wBeg + lane < wEnd ? src[wBeg + lane] : 0ULL;
+            xn2 = wBeg + 32 + lane < wEnd ? src[wBeg + 32 + lane] : 0ULL;
+            for (uint32_t i0 = wBeg; i0 < wEnd; i0 += 32) {
+                const unsigned long long x = xn;
+                xn = xn2;
+                if (i0 + lane + 64 < wEnd) xn2 = src[i0 + lane + 64];
+                step(i0, x);
+            }
         }
         __syncthreads();
         const unsigned long long* t = dst; dst = const_cast<unsigned long long*>(src); src = t;
         uint32_t (*th)[256] = cur; cur = nxt; nxt = th;
     }
     // start flags of the target groups (overlap.cpp:216-221), while the sorted segment is still in L2
+    if (DEEP) {
+        // every thread owns four consecutive positions per iteration: five independent key loads, one 4-byte flag store
+        const Elem* h = hits + start;
+        for (uint32_t i = 4 * threadIdx.x; i < n; i += 4 * blockDim.x) {
+            uint32_t id[5];
+            id[0] = i ? (uint32_t)(h[i - 1].key >> 32) : 0u;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) id[u + 1] = i + u < n ? (uint32_t)(h[i + u].key >> 32) : 0u;
+            uint32_t f = 0;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) f |= (uint32_t)((i + u == 0) || id[u + 1] != id[u]) << (8 * u);
+            if (((start + i) & 3u) == 0 && i + 4 <= n) *reinterpret_cast<uint32_t*>(groupFlags + start + i) = f;
+            else for (int u = 0; u < 4 && i + u < n; ++u) groupFlags[start + i + u] = (uint8_t)(f >> (8 * u));
+        }
+        return;
+    }
     for (uint32_t i = threadIdx.x; i < n; i += blockDim.x)
         groupFlags[start + i] = i == 0 || (uint32_t)(hits[start + i].key >> 32) != (uint32_t)(hits[start + i - 1].key >> 32);
 }
@@ -1633,6 +1678,53 @@ __global__ void __launch_bounds__(256) alignFinishKernel(fg_overlap* __restrict_
     ov[i].aln_count = keep ? alnCount[i] : 0u;
 }
 
+// Q7 on the device (the default epilogue; DESIGN.md §2 "Exact shortcuts" 7).  seqDivergence of every gathered record with the
+// reference's float expression — glibc's logf evaluated bit for bit (glibc_logf.cuh) — or, with nuclAlignment, from the edit
+// distance (alignment.cpp:240-245); the divergence test (overlap.cpp:470-473) against the call's or the query's threshold; the
+// number of records every query keeps.  Records whose arithmetic leaves the domain the device handles (zero chain, empty
+// alignment: never seen on real input) are counted in kept[nQueriesOfSub]; the sub-batch then takes the host epilogue.
+static_assert(sizeof(fg_overlap) == 72 && offsetof(fg_overlap, reserved) == 68 && offsetof(fg_overlap, aln_count) == 64, "gatherKeptKernel copies 9 words per record");
+__global__ void __launch_bounds__(256) divergenceKernel(fg_overlap* __restrict__ ov, uint32_t nOv, float sampleRate, int k, bool nucl, float maxDiv,
+                                                        const float* __restrict__ queryMaxDiv, uint32_t qFirst, uint32_t nq,
+                                                        uint8_t* __restrict__ keep, uint32_t* __restrict__ kept) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nOv) return;
+    fg_overlap& o = ov[i];
+    bool ok = true;
+    float div;
+    if (nucl) {
+        const int32_t ed = o.edit_distance, al = o.aln_len;
+        if (ed < 0) div = 1.0f;
+        else if (al <= 0) { ok = false; div = 0.0f; }
+        else div = __fdiv_rn(__int2float_rn(ed), __ull2float_rn((unsigned long long)al));   // (float)editDistance / size_t
+    } else {
+        div = kmerDivergence(o.cur_end - o.cur_begin, o.ext_end - o.ext_begin, o.filtered_positions, o.chain_length, sampleRate, k, ok);
+    }
+    o.seq_divergence = div;
+    const uint32_t q = o.reserved;
+    const bool pass = div < (queryMaxDiv ? queryMaxDiv[q] : maxDiv);
+    keep[i] = pass;
+    if (pass) atomicAdd(&kept[q - qFirst], 1u);
+    if (!ok) atomicAdd(&kept[nq], 1u);
+}
+
+// the kept records, in order, into the buffer that goes to the host; `reserved` becomes 0 (= passed the divergence test)
+__global__ void __launch_bounds__(256) gatherKeptKernel(const unsigned long long* __restrict__ src, const uint32_t* __restrict__ idx, uint32_t nSel,
+                                                        unsigned long long* __restrict__ dst) {
+    const uint64_t total = 9ULL * nSel, stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; t < total; t += stride) {
+        const uint32_t j = (uint32_t)(t / 9), w = (uint32_t)(t - 9ULL * j);
+        unsigned long long v = src[9ULL * idx[j] + w];
+        if (w == 8) v &= 0xffffffffULL;
+        dst[t] = v;
+    }
+}
+
+__global__ void logfSelfTestKernel(const float* __restrict__ x, uint32_t n, float* __restrict__ y) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = glibcLogfInDomain(x[i]) ? glibcLogf(x[i]) : -1.0f;
+}
+
 // segmented sort driver.  dCounters: 5 device words (layout above) with [0] = nSegs already set and the rest zero.
 static constexpr uint32_t SORT_HUGE_MIN = 8192;   // ranges above this size are partitioned by a whole CTA (sortHugeKernel)
 struct SortWorkspace {
@@ -1788,6 +1880,39 @@ static uint32_t selectFlagged(fg_ctx* ctx, const FlagT* flags, uint32_t n, DevBu
     return h;
 }
 
+// The device epilogue (divergenceKernel) is only used on a context whose DEVICE logf has reproduced the HOST's logf — the function
+// the reference calls — on a sample of 2^16 arguments: every binade, dense around the values 1 / matchRate takes.  The arithmetic is
+// proven on the CPU (tests/cpu_models/logf_check.cpp); this guards against a host libm that is not the glibc the proof was run on.
+// FG_DEVICE_EPILOGUE=0 keeps the host epilogue (recordDivergences + sliceEpilogue).  Main thread, before the lanes start.
+static bool deviceEpilogueUsable(fg_ctx* ctx) {
+    if (const char* e = getenv("FG_DEVICE_EPILOGUE")) if (atoi(e) == 0) return false;   // read per call: the tests switch it
+    if (ctx->devEpilogueState) return ctx->devEpilogueState > 0;
+    const uint32_t n = 1u << 16;
+    std::vector<float> x(n), y(n);
+    uint64_t rs = 0x9E3779B97F4A7C15ULL;
+    for (uint32_t i = 0; i < n; ++i) {
+        rs = splitmix64(rs);
+        uint32_t bits;
+        if (i & 1) bits = 0x3f800000u + (uint32_t)(rs % 0x01800000u);                       // [1, 8)
+        else bits = 0x00800000u + (uint32_t)(rs % (0x7f800000u - 0x00800000u));             // any positive normal float
+        std::memcpy(&x[i], &bits, 4);
+    }
+    DevBuf<float> dX(n), dY(n);
+    FG_CUDA(cudaMemcpyAsync(dX.p, x.data(), n * 4, cudaMemcpyHostToDevice, streamOf(ctx)));
+    logfSelfTestKernel<<<n / 256, 256, 0, streamOf(ctx)>>>(dX.p, n, dY.p);
+    checkLaunch(ctx, "logfSelfTestKernel");
+    FG_CUDA(cudaMemcpyAsync(y.data(), dY.p, n * 4, cudaMemcpyDeviceToHost, streamOf(ctx)));
+    FG_CUDA(cudaStreamSynchronize(streamOf(ctx)));
+    bool same = true;
+    for (uint32_t i = 0; i < n && same; ++i) {
+        volatile float xv = x[i];
+        const float ref = std::log((float)xv);
+        same = std::memcmp(&ref, &y[i], 4) == 0;
+    }
+    ctx->devEpilogueState = same ? 1 : -1;
+    return same;
+}
+
 // one chunk of queries (< 2^30 k-mer slots): lookup, expansion and the per-sub-batch pipeline; the raw overlap records are
 // appended to the context's pinned buffer with `reserved` = position of the query in the whole call
 // Work counters of a call, added up by the lanes.
@@ -1819,7 +1944,7 @@ static void sliceEpilogue(fg_ctx* ctx, fg_overlap* recs, size_t n, size_t sliceO
                           size_t qFirst, size_t qCount);
 
 static void overlapsChunk(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, uint32_t qOffset, const fg_overlap_params& prm, const OvParams& P,
-                          OrderedCommit& commit, size_t& subBase, uint64_t& totHits, BatchTotals& tot, const float* dQueryMaxDiv) {
+                          OrderedCommit& commit, size_t& subBase, uint64_t& totHits, BatchTotals& tot, const float* dQueryMaxDiv, const bool devEpilogue) {
     const int k = ctx->k;
     // where the query sequences live: the indexed reads themselves, or the second set of fg_queries_upload
     const std::vector<uint32_t>& qHLen = P.sameSet ? ctx->hLen : ctx->hQsLen;
@@ -2001,7 +2126,9 @@ static void overlapsChunk(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, ui
                 checkLaunch(ctx, "segRadixSortClusterKernel");
             } else {
                 PhaseTimer pt(ctx, "hit_sort_radix");
-                auto sortK = envInt("FG_SEG_OCC", 3, 3, 4) == 4 ? segRadixSortKernel<4> : segRadixSortKernel<3>;   // resident CTAs per SM (32 / 40 registers)
+                const bool deep = envInt("FG_SRS_DEEP", 1, 0, 1) != 0;   // more loads in flight per thread (see the kernel's comment)
+                auto sortK = envInt("FG_SEG_OCC", 3, 3, 4) == 4 ? (deep ? segRadixSortKernel<4, true> : segRadixSortKernel<4, false>)
+                                                                : (deep ? segRadixSortKernel<3, true> : segRadixSortKernel<3, false>);   // resident CTAs per SM (32 / 40 registers)
                 sortK<<<nq, SEG_WARPS * 32, 0, streamOf(ctx)>>>(bufA, bufB, dQHitOff.p, qa, hitBase, posBits, nPass, hits.p, flags.p);
                 checkLaunch(ctx, "segRadixSortKernel");
             }
@@ -2234,21 +2361,74 @@ static void overlapsChunk(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, ui
                         checkLaunch(ctx, "alignFinishKernel");
                     }
                 }
+                // grows the shared pinned buffer to `need` records: exclusively, when no lane is copying into or working on it
+                auto growPinned = [&](std::shared_lock<std::shared_mutex>& rd, size_t need) {
+                    if (pinned.n >= need) return;
+                    rd.unlock();
+                    {
+                        std::unique_lock<std::shared_mutex> wr(ctx->pinnedMutex);
+                        size_t reserved;   // slices of later sub-batches may already hold records: keep everything reserved so far
+                        { std::lock_guard<std::mutex> lk(commit.m); reserved = commit.nRaw; }
+                        if (pinned.n < need) pinned.ensureKeep(std::max(need, reserved), std::min(reserved, pinned.n));
+                    }
+                    rd.lock();
+                };
+                if (devEpilogue) {
+                    // device epilogue: edit distances, seqDivergence (glibc's logf, bit for bit), the divergence test and the per-query
+                    // counts are computed where the records are; only the kept records travel, already compact and in order
+                    const uint32_t nO = (uint32_t)nOut;
+                    if (prm.nucl_alignment) {   // overlap.cpp:463-468
+                        PhaseTimer pe(ctx, "edit");
+                        editDistances(ctx, dOut.p, nullptr, nO, prm.use_hpc != 0, !P.sameSet, prm.max_divergence, dQueryMaxDiv);
+                    }
+                    DevBuf<uint8_t> keepFlag(nO);
+                    DevBuf<uint32_t> dKept(nq + 1), selIdx;   // [nq] = records the device does not handle
+                    FG_CUDA(cudaMemsetAsync(dKept.p, 0, (nq + 1) * 4ULL, streamOf(ctx)));
+                    uint32_t nSel = 0;
+                    {
+                        PhaseTimer pt(ctx, "epilogue_dev");
+                        divergenceKernel<<<(nO + 255) / 256, 256, 0, streamOf(ctx)>>>(dOut.p, nO, ctx->stats.sample_rate, k, prm.nucl_alignment != 0, prm.max_divergence,
+                                                                                  dQueryMaxDiv, qOffset + qa, nq, keepFlag.p, dKept.p);
+                        checkLaunch(ctx, "divergenceKernel");
+                        nSel = selectFlagged(ctx, keepFlag.p, nO, selIdx);
+                    }
+                    std::vector<uint32_t> hKept(nq + 1);
+                    FG_CUDA(cudaMemcpyAsync(hKept.data(), dKept.p, (nq + 1) * 4ULL, cudaMemcpyDeviceToHost, streamOf(ctx)));
+                    FG_CUDA(cudaStreamSynchronize(streamOf(ctx)));
+                    if (hKept[nq] == 0) {
+                        DevBuf<fg_overlap> dKeep(std::max<uint32_t>(nSel, 1));
+                        if (nSel) {
+                            PhaseTimer pt(ctx, "epilogue_dev");
+                            gatherKeptKernel<<<gridFor(9ULL * nSel, 256, 16), 256, 0, streamOf(ctx)>>>(reinterpret_cast<const unsigned long long*>(dOut.p), selIdx.p, nSel,
+                                                                                                  reinterpret_cast<unsigned long long*>(dKeep.p));
+                            checkLaunch(ctx, "gatherKeptKernel");
+                        }
+                        const size_t myOff = commit.reserve(subIndex, nSel);
+                        committed = true;
+                        std::shared_lock<std::shared_mutex> rd(ctx->pinnedMutex);
+                        growPinned(rd, myOff + nSel);
+                        if (nSel) {
+                            FG_CUDA(cudaMemcpyAsync(pinned.p + myOff, dKeep.p, nSel * sizeof(fg_overlap), cudaMemcpyDeviceToHost, streamOf(ctx)));
+                            FG_CUDA(cudaStreamSynchronize(streamOf(ctx)));
+                        }
+                        size_t run = myOff;   // where every query's records start, how many it keeps (what sliceEpilogue derives on the host path)
+                        for (uint32_t j = 0; j < nq; ++j) {
+                            const size_t q = (size_t)qOffset + qa + j;
+                            if (hKept[j]) commit.qStart[q] = run;
+                            commit.kept[q] = hKept[j];
+                            run += hKept[j];
+                        }
+                        if (run != myOff + nSel) throw Error(FG_ERR_INTERNAL, "device epilogue: per-query counts do not add up");
+                        return;
+                    }
+                    // (a record outside the device's domain: the whole sub-batch takes the host epilogue below)
+                }
                 // this sub-batch's slice of the shared pinned buffer: directly behind its predecessor's
                 const size_t myOff = commit.reserve(subIndex, nOut);
                 committed = true;
                 {
                     std::shared_lock<std::shared_mutex> rd(ctx->pinnedMutex);
-                    if (pinned.n < myOff + nOut) {   // grow: exclusively, when no lane is copying into or working on the buffer
-                        rd.unlock();
-                        {
-                            std::unique_lock<std::shared_mutex> wr(ctx->pinnedMutex);
-                            size_t reserved;   // slices of later sub-batches may already hold records: keep everything reserved so far
-                            { std::lock_guard<std::mutex> lk(commit.m); reserved = commit.nRaw; }
-                            if (pinned.n < myOff + nOut) pinned.ensureKeep(std::max(myOff + nOut, reserved), std::min(reserved, pinned.n));
-                        }
-                        rd.lock();
-                    }
+                    growPinned(rd, myOff + nOut);
                     fg_overlap* dst = pinned.p + myOff;
                     FG_CUDA(cudaMemcpyAsync(dst, dOut.p, nOut * sizeof(fg_overlap), cudaMemcpyDeviceToHost, streamOf(ctx)));
                     FG_CUDA(cudaStreamSynchronize(streamOf(ctx)));
@@ -2430,6 +2610,9 @@ void overlapsBatch(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, const fg_
         dQueryMaxDiv.alloc(nQ);
         FG_CUDA(cudaMemcpyAsync(dQueryMaxDiv.p, prm.query_max_divergence, nQ * sizeof(float), cudaMemcpyHostToDevice, streamOf(ctx)));
     }
+    // divergence, threshold and per-query counts on the device unless the call needs the sequential per-query replay (maxOverlaps),
+    // the rejected records (partitionBadMappings) or kmerMatches — those keep the host epilogue
+    const bool devEpilogue = prm.max_overlaps == 0 && !prm.keep_rejected && !prm.keep_alignment && deviceEpilogueUsable(ctx);
     // chunks of consecutive queries with < 2^30 k-mer slots each (device arrays are indexed with 32-bit counts)
     uint64_t chunkSlots = 1ULL << 30;
     if (const char* e = getenv("FG_CHUNK_SLOTS")) chunkSlots = std::max<uint64_t>(4096, std::min<uint64_t>(chunkSlots, strtoull(e, nullptr, 10)));
@@ -2442,7 +2625,7 @@ void overlapsBatch(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, const fg_
             if (q1 > q0 && slots + add >= chunkSlots) break;
             slots += add; ++q1;
         }
-        overlapsChunk(ctx, queryIds + q0, q1 - q0, q0, prm, P, commit, subBase, totHits, tot, dQueryMaxDiv.p);
+        overlapsChunk(ctx, queryIds + q0, q1 - q0, q0, prm, P, commit, subBase, totHits, tot, dQueryMaxDiv.p, devEpilogue);
         q0 = q1;
     }
     const size_t nRaw = commit.nRaw;

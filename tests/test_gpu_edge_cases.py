@@ -171,3 +171,49 @@ def test_refilter_equals_thresholded_run(engine, tmp_path):
     engine.overlaps(q, max_divergence=1.0, max_overlaps=3, copy=False, **common)
     with pytest.raises(fb.FlyeB200Error, match="max_overlaps"):
         engine.refilter(0, thr, len(q))
+
+
+def test_device_epilogue_equals_host_epilogue(engine, tmp_path, monkeypatch):
+    """The default epilogue (divergenceKernel: seqDivergence with glibc's logf evaluated on the device, divergence test, per-query
+    counts, compaction on the device) returns byte-identical records and offsets to the host epilogue (FG_DEVICE_EPILOGUE=0:
+    recordDivergences with the host's logf + sliceEpilogue), for k-mer divergences (CLR) and edit-distance divergences (HiFi),
+    with a threshold that removes records, with per-query thresholds, and with forced sub-batching."""
+    import flye_b200 as fb
+    tmp = str(tmp_path)
+    n_cmp = 0
+    for preset in ("raw_reads.cfg", "hifi.cfg"):
+        cfg = pu.load_cfg(os.path.join(pu.CFG_DIR, preset))
+        hifi = preset == "hifi.cfg"
+        sim = dict(genome_len=120000, coverage=15, mean_len=12000, shape=20, error=0.01, seed=41) if hifi else dict(genome_len=120000, coverage=15, seed=42)
+        reads = fb.read_fasta(pu.simulate(os.path.join(tmp, preset + ".fasta"), **sim), 1000)
+        engine.upload_ascii(reads)
+        if hifi:
+            engine.build_index_minimizers(17, 1, int(cfg["minimizer_window"]), cfg["repeat_kmer_rate"])
+        else:
+            engine.count_kmers(15)
+            engine.build_index_solid(2, cfg["meta_read_top_kmer_rate"], int(cfg["meta_read_filter_kmer_freq"]), cfg["repeat_kmer_rate"],
+                                     float(int(cfg["assemble_kmer_sample"])))
+        common = dict(max_jump=int(cfg["maximum_jump"]), min_overlap=1000, max_overhang=int(cfg["maximum_overhang"]), only_max_ext=True,
+                      nucl_alignment=hifi, use_hpc=hifi)
+        q = np.arange(0, 2 * len(reads), dtype=np.uint32)
+        monkeypatch.setenv("FG_DEVICE_EPILOGUE", "0")
+        _, ov_all, _ = engine.overlaps(q, max_divergence=1.0, **common)
+        thr = float(np.median(ov_all["seq_divergence"]))          # removes about half of the records
+        per_q = np.where(np.arange(len(q)) % 4 == 0, 1.0, thr).astype(np.float32)
+        for kw in (dict(max_divergence=1.0), dict(max_divergence=thr), dict(max_divergence=0.5, query_max_divergence=per_q)):
+            for budget in (None, "20000"):
+                if budget:
+                    monkeypatch.setenv("FG_HIT_BUDGET", budget)
+                else:
+                    monkeypatch.delenv("FG_HIT_BUDGET", raising=False)
+                monkeypatch.setenv("FG_DEVICE_EPILOGUE", "0")
+                off_h, ov_h, _ = engine.overlaps(q, **kw, **common)
+                assert "epilogue_dev" not in engine.timings()
+                monkeypatch.setenv("FG_DEVICE_EPILOGUE", "1")
+                off_d, ov_d, _ = engine.overlaps(q, **kw, **common)
+                assert "epilogue_dev" in engine.timings()        # the device path really ran (no silent fallback)
+                assert np.array_equal(off_h, off_d), (preset, kw.keys(), budget)
+                assert ov_h.tobytes() == ov_d.tobytes(), (preset, kw.keys(), budget)
+                n_cmp += len(ov_d)
+        assert 0 < len(ov_h) < len(ov_all)
+    assert n_cmp > 10000

@@ -42,3 +42,13 @@ def test_dense_kmer_class_index_is_a_bijection_onto_the_canonical_kmers(built):
     (index % N, index / N) is a bijection with 32-bit slots."""
     r = subprocess.run([os.path.join(BIN, "dense_check")], stdout=subprocess.PIPE, text=True, timeout=600)
     assert r.returncode == 0 and r.stdout.strip() == "ok", r.stdout
+
+
+def test_device_logf_is_glibc_logf_bit_for_bit(built):
+    """glibcLogf / kmerDivergence (glibc_logf.cuh, used by divergenceKernel in overlap.cu) vs the container's logf — the function
+    behind std::log(float) at overlap.cpp:423: identical bits for every 97th positive normal float, every float of [1, 4), and
+    for the whole seqDivergence expression on 4 M random records (`logf_check 1` compares all 2.13e9 positive normal floats)."""
+    r = subprocess.run([os.path.join(BIN, "logf_check"), "97"], stdout=subprocess.PIPE, text=True, timeout=600)
+    assert r.returncode == 0 and r.stdout.startswith("OK"), r.stdout
+    stats = dict(kv.split("=") for kv in r.stdout.split()[1:])
+    assert int(stats["n"]) > 30000000 and int(stats["degenerate"]) > 1000
