@@ -360,6 +360,149 @@ __global__ void __launch_bounds__(SEG_WARPS * 32, MIN_CTAS) segRadixSortKernel(u
         groupFlags[start + i] = i == 0 || (uint32_t)(hits[start + i].key >> 32) != (uint32_t)(hits[start + i - 1].key >> 32);
 }
 
+// Tile version of the segmented sort (FG_SEG_SORT=2).  The kernel above scatters straight from registers: the 32 elements of a
+// warp step go to up to 32 different sectors (ncu: 15 sectors per store request), partly written sectors are evicted from the L2
+// before their neighbours arrive, and DRAM sees 59 B per hit where 24 are compulsory — the run time did not move when the loads
+// were pipelined deeper, it is the scattered traffic that bounds it.  Here a CTA takes its segment tile by tile (4096 elements):
+// the tile is ranked stably by digit (per-warp counts with match.any, exclusive scan over the warps and the digits), reordered in
+// shared memory, and copied out in runs of equal digits — consecutive threads write consecutive addresses, whole sectors.  The
+// digit's position in the segment advances tile by tile, so equal digits keep their order (stable LSD passes, as above).
+static constexpr int TS_WARPS = 16, TS_E = 8, TS_TILE = TS_WARPS * 32 * TS_E;
+struct TsSmem {
+    unsigned long long stage[TS_TILE];
+    uint32_t warpCnt[TS_WARPS][256];   // in-tile counts per (warp, digit); after the scan: first rank of the warp inside the digit's run
+    uint32_t digitBase[256];           // where the digit's next element goes in the segment
+    uint32_t tileStart[256];           // where the digit's run starts in the staged tile
+    uint32_t nxtCnt[256];              // digit counts of the next pass, gathered while copying out
+    uint32_t warpTot[8];
+};
+template <int MIN_CTAS>
+__global__ void __launch_bounds__(TS_WARPS * 32, MIN_CTAS) segTileSortKernel(unsigned long long* bufA, unsigned long long* bufB,
+                                                                            const uint64_t* __restrict__ qHitOff, uint32_t qFirst, uint64_t hitBase,
+                                                                            int posBits, int nPass, Elem* __restrict__ hits, uint8_t* __restrict__ groupFlags) {
+    extern __shared__ __align__(16) unsigned char tsRaw[];
+    TsSmem& S = *reinterpret_cast<TsSmem*>(tsRaw);
+    const uint64_t start = qHitOff[qFirst + blockIdx.x] - hitBase;
+    const uint32_t n = (uint32_t)(qHitOff[qFirst + blockIdx.x + 1] - qHitOff[qFirst + blockIdx.x]);
+    if (n == 0) return;
+    const uint32_t tid = threadIdx.x;
+    const int w = tid >> 5, lane = tid & 31;
+    const unsigned long long* src = bufA + start;
+    unsigned long long* dst = bufB + start;
+    const int idShift = 2 * posBits;
+    const unsigned long long posMask = (1ULL << posBits) - 1ULL;
+    // exclusive prefix over the 256 values the threads 0..255 hold (the others pass 0); one barrier inside, and the caller has a
+    // barrier between two calls (warpTot is reused)
+    auto exclusive256 = [&](const uint32_t v) -> uint32_t {
+        uint32_t inc = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
+        if (tid < 256 && lane == 31) S.warpTot[w] = inc;
+        __syncthreads();
+        uint32_t add = 0;
+        if (tid < 256) for (int v2 = 0; v2 < w; ++v2) add += S.warpTot[v2];
+        return inc - v + add;
+    };
+    // digit counts of the first pass
+    if (tid < 256) S.nxtCnt[tid] = 0u;
+    __syncthreads();
+    for (uint32_t i0 = 0; i0 < n; i0 += 4 * TS_WARPS * 32) {
+        unsigned long long x[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { const uint32_t i = i0 + u * TS_WARPS * 32 + tid; x[u] = i < n ? src[i] : 0ULL; }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (i0 + u * TS_WARPS * 32 + tid < n) atomicAdd(&S.nxtCnt[(uint32_t)(x[u] >> idShift) & 255u], 1u);
+    }
+    __syncthreads();
+    for (int pass = 0; pass < nPass; ++pass) {
+        const bool last = pass == nPass - 1;
+        const int sh = idShift + 8 * pass;
+        {
+            const uint32_t c = tid < 256 ? S.nxtCnt[tid] : 0u;
+            const uint32_t ex = exclusive256(c);
+            if (tid < 256) { S.digitBase[tid] = ex; S.nxtCnt[tid] = 0u; }
+        }
+        uint32_t prevRun = 0;   // thread d < 256: elements of digit d in the previous tile (advances digitBase[d])
+        for (uint32_t t0 = 0; t0 < n; t0 += TS_TILE) {
+            const uint32_t tileN = min((uint32_t)TS_TILE, n - t0);
+            // (1) load, rank inside the warp: warp w owns the tile positions [256 w, 256 w + 256), step e its e-th 32 elements
+            for (int j = lane; j < 256; j += 32) S.warpCnt[w][j] = 0u;
+            __syncwarp();
+            const uint32_t wb = t0 + (uint32_t)w * 32u * TS_E;
+            unsigned long long x[TS_E];
+            uint32_t r[TS_E];
+#pragma unroll
+            for (int e = 0; e < TS_E; ++e) { const uint32_t i = wb + e * 32 + lane; x[e] = i < n ? src[i] : 0ULL; }
+#pragma unroll
+            for (int e = 0; e < TS_E; ++e) {
+                const bool valid = wb + e * 32 + lane < n;
+                const uint32_t am = __ballot_sync(0xffffffffu, valid);
+                r[e] = 0;
+                if (valid) {
+                    const uint32_t d = (uint32_t)(x[e] >> sh) & 255u;
+                    const uint32_t peers = __match_any_sync(am, d);
+                    const uint32_t lower = peers & ((1u << lane) - 1u);
+                    r[e] = S.warpCnt[w][d] + __popc(lower);
+                    __syncwarp(am);
+                    if (lower == 0u) S.warpCnt[w][d] += __popc(peers);
+                }
+                __syncwarp();
+            }
+            __syncthreads();   // A: every warp's counts are in; the previous tile is copied out
+            // (2) per digit: exclusive over the warps; the runs' starts in the tile; the digit's place in the segment moves on
+            uint32_t run = 0;
+            if (tid < 256) {
+                for (int v = 0; v < TS_WARPS; ++v) { const uint32_t c = S.warpCnt[v][tid]; S.warpCnt[v][tid] = run; run += c; }
+                S.digitBase[tid] += prevRun;
+                prevRun = run;
+            }
+            const uint32_t ts = exclusive256(run);   // B inside
+            if (tid < 256) S.tileStart[tid] = ts;
+            __syncthreads();   // C
+            // (3) reorder in shared memory
+#pragma unroll
+            for (int e = 0; e < TS_E; ++e) {
+                if (wb + e * 32 + lane < n) {
+                    const uint32_t d = (uint32_t)(x[e] >> sh) & 255u;
+                    S.stage[S.tileStart[d] + S.warpCnt[w][d] + r[e]] = x[e];
+                }
+            }
+            __syncthreads();   // D
+            // (4) copy out: consecutive threads, consecutive addresses inside a run
+            for (uint32_t s0 = tid; s0 < tileN; s0 += TS_WARPS * 32) {
+                const unsigned long long y = S.stage[s0];
+                const uint32_t d = (uint32_t)(y >> sh) & 255u;
+                const uint32_t g = S.digitBase[d] + (s0 - S.tileStart[d]);
+                if (!last) {
+                    dst[g] = y;
+                    atomicAdd(&S.nxtCnt[(uint32_t)(y >> (sh + 8)) & 255u], 1u);
+                } else {
+                    Elem o; o.key = ((y >> idShift) << 32) | ((y >> posBits) & posMask); o.val = (unsigned int)(y & posMask); o.aux = 0;
+                    hits[start + g] = o;
+                }
+            }
+            // (no barrier: the next tile's step (1) touches neither the stage nor the digit tables, and its barrier A comes before
+            // anything of this tile is overwritten)
+        }
+        __syncthreads();   // the pass is written before it is read back / before the counts of the next pass are scanned
+        const unsigned long long* t = dst; dst = const_cast<unsigned long long*>(src); src = t;
+    }
+    // start flags of the target groups (overlap.cpp:216-221), while the sorted segment is still in L2
+    const Elem* h = hits + start;
+    for (uint32_t i = 4 * tid; i < n; i += 4 * TS_WARPS * 32) {
+        uint32_t id[5];
+        id[0] = i ? (uint32_t)(h[i - 1].key >> 32) : 0u;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) id[u + 1] = i + u < n ? (uint32_t)(h[i + u].key >> 32) : 0u;
+        uint32_t f = 0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) f |= (uint32_t)((i + u == 0) || id[u + 1] != id[u]) << (8 * u);
+        if (((start + i) & 3u) == 0 && i + 4 <= n) *reinterpret_cast<uint32_t*>(groupFlags + start + i) = f;
+        else for (int u = 0; u < 4 && i + u < n; ++u) groupFlags[start + i + u] = (uint8_t)(f >> (8 * u));
+    }
+}
+
 // Cluster version of the segmented sort (FG_SEG_SORT=1; NOT the default — measured on B200, 1 lane, whole configs[0] / configs[1]
 // pass: 9.3 / 16.2 ms with clusters of 1 / 2 CTAs against 8.3 / 12.9 ms for the kernel above, and 20-29 ms with clusters of 4-8:
 // the sort is bound by the latency of its warp steps (load -> match.any -> shared-memory offsets -> scattered store), which
@@ -2089,7 +2232,18 @@ static void overlapsChunk(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, ui
                 const int forced = envInt("FG_SRS_MIN_PASSES", 1, 1, 3);
                 if (forced > nPass && 2 * posBits + 8 * forced <= 64) nPass = forced;
             }
-            if (envInt("FG_SEG_SORT", 0, 0, 1)) {   // 1 = segRadixSortClusterKernel (L2-resident; measured slower, see its comment)
+            const int segSort = envInt("FG_SEG_SORT", 0, 0, 2);   // 0 = segRadixSortKernel, 1 = segRadixSortClusterKernel, 2 = segTileSortKernel
+            if (segSort == 2) {
+                static std::once_flag tsAttr[64];   // function attributes are per device
+                std::call_once(tsAttr[ctx->device & 63], [&] {
+                    FG_CUDA(cudaFuncSetAttribute(segTileSortKernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TsSmem)));
+                    FG_CUDA(cudaFuncSetAttribute(segTileSortKernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TsSmem)));
+                });
+                PhaseTimer pt(ctx, "hit_sort_radix");
+                auto sortK = envInt("FG_SEG_OCC", 3, 3, 4) == 4 ? segTileSortKernel<4> : segTileSortKernel<3>;
+                sortK<<<nq, TS_WARPS * 32, sizeof(TsSmem), streamOf(ctx)>>>(bufA, bufB, dQHitOff.p, qa, hitBase, posBits, nPass, hits.p, flags.p);
+                checkLaunch(ctx, "segTileSortKernel");
+            } else if (segSort == 1) {   // 1 = segRadixSortClusterKernel (L2-resident; measured slower, see its comment)
                 // cluster size: sources, scratch copies and fresh output of all resident clusters should fit the L2 together.
                 // The typical hit lives in a segment of the hits-weighted mean size.
                 double sum2 = 0.0; uint64_t maxSeg = 1;
@@ -2444,6 +2598,11 @@ static void overlapsChunk(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, ui
                     sliceEpilogue(ctx, dst, nOut, myOff, prm, commit, (size_t)qOffset + qa, nq);   // threshold / maxOverlaps replay of this slice's queries
                 }
             }
+        } else {   // no pair survived the prefilters: the hit sort's task counter is still checked (a truncated task list means unsorted ranges)
+            uint32_t hSmall = 0;
+            FG_CUDA(cudaMemcpyAsync(&hSmall, counters.p + 1, 4, cudaMemcpyDeviceToHost, streamOf(ctx)));
+            FG_CUDA(cudaStreamSynchronize(streamOf(ctx)));
+            if (hSmall > taskCap) throw Error(FG_ERR_INTERNAL, "sort task list overflow");
         }
         commitNone();
     };

@@ -81,11 +81,13 @@ def test_clr_small_full_parity(engine, tmp_path):
                                  {"FG_SEG_SORT": "1", "FG_SRS_CLUSTER": "1"}, {"FG_SEG_SORT": "1", "FG_SRS_CLUSTER": "2"},
                                  {"FG_SEG_SORT": "1", "FG_SRS_CLUSTER": "4", "FG_SRS_MIN_PASSES": "3"}, {"FG_SEG_SORT": "1", "FG_SRS_CLUSTER": "8"},
                                  {"FG_SRS_MIN_PASSES": "3"}, {"FG_DEVICE_EPILOGUE": "0"}, {"FG_SRS_DEEP": "0"},
-                                 {"FG_SRS_DEEP": "0", "FG_SRS_MIN_PASSES": "3"}])
+                                 {"FG_SRS_DEEP": "0", "FG_SRS_MIN_PASSES": "3"}, {"FG_SEG_SORT": "2"}, {"FG_SEG_SORT": "2", "FG_SRS_MIN_PASSES": "3"},
+                                 {"FG_SEG_SORT": "2", "FG_SEG_OCC": "4"}, {"FG_SEG_SORT": "0"}])
 def test_kernel_variants_agree_with_oracle(engine, tmp_path, monkeypatch, env):
     """The alternative device paths stay exact: introsort emulation for every query (no radix fast path; with and without the
     CTA-wide partition of long ranges), the library radix sort instead of the segmented one, the thread-block-cluster version of the
-    segmented sort with every cluster size, three radix passes, the segmented sort with the shallow prefetch, match-by-match DP with and without
+    segmented sort with every cluster size, three radix passes, the segmented sort with the shallow prefetch, the tile version of
+    the segmented sort (staged in shared memory, coalesced copy-out) and the register-scatter version, match-by-match DP with and without
     pruned look-back (the default is the run-compressed DP + run-wise chain walk), the host epilogue (divergence with the host's
     logf and per-query replay on host threads; the default computes both on the device).  CLR with all primary overlaps +
     kmerMatches, and HiFi."""
