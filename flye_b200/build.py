@@ -48,7 +48,7 @@ def build_lib(force=False):
             jobs.append([nvcc] + NVCC_FLAGS + ["-c", src, "-o", obj])
     with ThreadPoolExecutor(max_workers=int(os.environ.get("FLYE_B200_BUILD_JOBS", "4"))) as ex:
         list(ex.map(_run, jobs))
-    if jobs or not os.path.exists(LIB):
+    if jobs or _newer(LIB, objs):   # (an object compiled by hand, e.g. with -Xptxas -v, is newer than the library too)
         _run([nvcc, "-shared", "-o", LIB] + objs + ["-ldl"])
     return LIB
 
