@@ -489,7 +489,7 @@ def main():
            "edit": raw_ovl * 2.0 * mean_ovl_len / 4.0,   # K9: (len_q + len_t) / 4 bytes per overlap
            "select": (w + 5.0) * n_k,                # K4
            "count": 0.25 * shard_bases + w * n_k + 2.0 * w * n_k}   # K2 + the counting part of K3 (3 w N_k without the (w+4) D of the table)
-    names = {"expand": "expandKernel", "lookup": "queryLookupKernel", "hit_sort_radix": {"0": "segRadixSortKernel", "1": "segRadixSortClusterKernel", "2": "segTileSortKernel"}.get(os.environ.get("FG_SEG_SORT", "0"), "segRadixSortKernel"),
+    names = {"expand": "expandKernel", "lookup": "queryLookupKernel", "hit_sort_radix": {"0": "segRadixSortKernel", "1": "segRadixSortClusterKernel", "2": "segTileSortKernel"}.get(os.environ.get("FG_SEG_SORT", "2"), "segTileSortKernel"),
              "chain_prep": "pairPrepKernel",
              "chain_dp": "chainRunDpKernel", "chain_fill": "chainFillKernel", "chain_walk": "chainWalkKernel", "edit": "wfaKernel",
              "select": "minimizerRegKernel" if int(cfg["use_minimizers"]) else "selectKernel", "count": "denseCountKernel"}

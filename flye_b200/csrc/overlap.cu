@@ -9,8 +9,10 @@
 //                         emission order (query position ascending, list order) (:176-196); flags the queries that contain an
 //                         (extId, curPos) tie
 //   Q4 the hit sort (:201-204)
-//        segRadixSortKernel   every query: stable 8-bit LSD radix sort by extId, one CTA per query — std::sort's result for the
-//                             queries without ties; also writes the target-group start flags
+//        segTileSortKernel    every query: stable 8-bit LSD radix sort by extId, one CTA per query, tile by tile through shared
+//                             memory with coalesced copy-out — std::sort's result for the queries without ties; the last pass also
+//                             writes the target-group start flags (segRadixSortKernel / ...ClusterKernel: earlier versions, kept
+//                             as tested variants)
 //        queries with ties    re-expanded into a scratch copy and sorted by the std::sort-exact introsort emulation
 //                             (sortHugeKernel = CTA-wide partition of long ranges, sortLevel/TailKernel = warp per range,
 //                             sortSmallKernel = shared-memory tasks), which only follows the ranges that contain ties
@@ -24,7 +26,7 @@
 //   Q7 gather, edit distance (editdist.cu, bounded by the divergence threshold) + host epilogue: seqDivergence with the
 //                         reference's float expression and glibc logf (:417-423), divergence filter (:470-473), maxOverlaps
 //                         cut (:218-219), parallel compaction; fg_overlaps_refilter = setDivergenceThreshold afterwards.
-// FG_HIT_RADIX / FG_DP_MODE / FG_SORT_HUGE select the older, slower device paths (kept as cross-checks, tests/test_gpu_parity.py).
+// FG_HIT_RADIX / FG_SEG_SORT / FG_DP_MODE / FG_SORT_HUGE / FG_DEVICE_EPILOGUE select the older, slower paths (kept as cross-checks, tests/test_gpu_parity.py).
 #include "ctx.cuh"
 #include "introsort_warp.cuh"
 #include "glibc_logf.cuh"
@@ -360,7 +362,7 @@ __global__ void __launch_bounds__(SEG_WARPS * 32, MIN_CTAS) segRadixSortKernel(u
         groupFlags[start + i] = i == 0 || (uint32_t)(hits[start + i].key >> 32) != (uint32_t)(hits[start + i - 1].key >> 32);
 }
 
-// Tile version of the segmented sort (FG_SEG_SORT=2).  The kernel above scatters straight from registers: the 32 elements of a
+// Tile version of the segmented sort (the default; FG_SEG_SORT=0 selects the kernel above).  The kernel above scatters straight from registers: the 32 elements of a
 // warp step go to up to 32 different sectors (ncu: 15 sectors per store request), partly written sectors are evicted from the L2
 // before their neighbours arrive, and DRAM sees 59 B per hit where 24 are compulsory — the run time did not move when the loads
 // were pipelined deeper, it is the scattered traffic that bounds it.  Here a CTA takes its segment tile by tile (4096 elements):
@@ -374,6 +376,7 @@ struct TsSmem {
     uint32_t digitBase[256];           // where the digit's next element goes in the segment
     uint32_t tileStart[256];           // where the digit's run starts in the staged tile
     uint32_t nxtCnt[256];              // digit counts of the next pass, gathered while copying out
+    uint32_t digitStart[256];          // where the digit's elements start in the segment (digitBase before the first tile)
     uint32_t warpTot[8];
 };
 template <int MIN_CTAS>
@@ -421,7 +424,7 @@ __global__ void __launch_bounds__(TS_WARPS * 32, MIN_CTAS) segTileSortKernel(uns
         {
             const uint32_t c = tid < 256 ? S.nxtCnt[tid] : 0u;
             const uint32_t ex = exclusive256(c);
-            if (tid < 256) { S.digitBase[tid] = ex; S.nxtCnt[tid] = 0u; }
+            if (tid < 256) { S.digitBase[tid] = ex; S.digitStart[tid] = ex; S.nxtCnt[tid] = 0u; }
         }
         uint32_t prevRun = 0;   // thread d < 256: elements of digit d in the previous tile (advances digitBase[d])
         for (uint32_t t0 = 0; t0 < n; t0 += TS_TILE) {
@@ -480,6 +483,14 @@ __global__ void __launch_bounds__(TS_WARPS * 32, MIN_CTAS) segTileSortKernel(uns
                 } else {
                     Elem o; o.key = ((y >> idShift) << 32) | ((y >> posBits) & posMask); o.val = (unsigned int)(y & posMask); o.aux = 0;
                     hits[start + g] = o;
+                    // start flag of the target group (overlap.cpp:216-221): the predecessor in the final order is the staged
+                    // neighbour inside a run; the last element of the digit's earlier tiles at a run's head (written before this
+                    // tile's barriers); an element with another leading digit — another target — at the digit's very first element
+                    const uint32_t id = (uint32_t)(y >> idShift);
+                    bool flag = true;
+                    if (s0 > S.tileStart[d]) flag = id != (uint32_t)(S.stage[s0 - 1] >> idShift);
+                    else if (g != S.digitStart[d]) flag = id != (uint32_t)(hits[start + g - 1].key >> 32);
+                    groupFlags[start + g] = flag;
                 }
             }
             // (no barrier: the next tile's step (1) touches neither the stage nor the digit tables, and its barrier A comes before
@@ -487,19 +498,6 @@ __global__ void __launch_bounds__(TS_WARPS * 32, MIN_CTAS) segTileSortKernel(uns
         }
         __syncthreads();   // the pass is written before it is read back / before the counts of the next pass are scanned
         const unsigned long long* t = dst; dst = const_cast<unsigned long long*>(src); src = t;
-    }
-    // start flags of the target groups (overlap.cpp:216-221), while the sorted segment is still in L2
-    const Elem* h = hits + start;
-    for (uint32_t i = 4 * tid; i < n; i += 4 * TS_WARPS * 32) {
-        uint32_t id[5];
-        id[0] = i ? (uint32_t)(h[i - 1].key >> 32) : 0u;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) id[u + 1] = i + u < n ? (uint32_t)(h[i + u].key >> 32) : 0u;
-        uint32_t f = 0;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) f |= (uint32_t)((i + u == 0) || id[u + 1] != id[u]) << (8 * u);
-        if (((start + i) & 3u) == 0 && i + 4 <= n) *reinterpret_cast<uint32_t*>(groupFlags + start + i) = f;
-        else for (int u = 0; u < 4 && i + u < n; ++u) groupFlags[start + i + u] = (uint8_t)(f >> (8 * u));
     }
 }
 
@@ -1546,6 +1544,9 @@ __global__ void __launch_bounds__(128) chainRunDpKernel(const Elem* __restrict__
 // scores, back pointers and the input of the score sort (:331-334) of every match.  When the scores of a pair increase
 // strictly with the match index, their descending order is the unique sorted sequence of distinct keys — std::sort's
 // output is n-1, n-2, ..., 0 — so the pair is flagged PAIR_PRESORTED and taken off the list of segments to sort.
+// PAIRED (default; FG_FILL_PAIRED=0 switches back): two 32-match blocks per iteration — the loads of the second block (run index ->
+// run record -> match) are issued next to the first block's, which halves the number of dependent round trips of a warp.
+template <bool PAIRED>
 __global__ void __launch_bounds__(256) chainFillKernel(const Elem* __restrict__ hits, const PairInfo* __restrict__ pairs, const uint32_t* __restrict__ pairIds,
                                                        uint32_t nPairs, uint32_t* __restrict__ pairFlags, const Run* __restrict__ runs,
                                                        int32_t* __restrict__ score, int32_t* __restrict__ back, Elem* __restrict__ ord,
@@ -1561,6 +1562,30 @@ __global__ void __launch_bounds__(256) chainFillKernel(const Elem* __restrict__ 
     int32_t* sc = score + pi.start; int32_t* bk = back + pi.start; Elem* od = ord + pi.start;
     bool incr = true;
     int32_t carry = INT32_MIN;
+    if (PAIRED) {
+        for (int32_t i0 = 0; i0 < n; i0 += 64) {
+            const int32_t iA = i0 + lane, iB = iA + 32;
+            const bool vA = iA < n, vB = iB < n;
+            int32_t rA = 0, rB = 0;
+            if (vA) rA = bk[iA];   // run of this match (chainRunsKernel)
+            if (vB) rB = bk[iB];
+            int4 HA = make_int4(0, 0, 0, 0), TA = HA, HB = HA, TB = HA;
+            Elem eA, eB; eA.key = 0; eA.val = 0; eA.aux = 0; eB = eA;
+            if (vA) { HA = rn4[2 * rA]; TA = rn4[2 * rA + 1]; eA = h[iA]; }
+            if (vB) { HB = rn4[2 * rB]; TB = rn4[2 * rB + 1]; eB = h[iB]; }
+            int32_t sA = INT32_MAX, sB = INT32_MAX;
+            if (vA) { sA = TA.w - (TA.y - elemCur(eA, extSorted)); sc[iA] = sA; bk[iA] = (iA == HA.x) ? HA.w : iA - 1; }
+            if (vB) { sB = TB.w - (TB.y - elemCur(eB, extSorted)); sc[iB] = sB; bk[iB] = (iB == HB.x) ? HB.w : iB - 1; }
+            int32_t ps = __shfl_up_sync(0xffffffffu, sA, 1);
+            if (lane == 0) ps = carry;
+            if (vA && !(ps < sA)) incr = false;
+            carry = __shfl_sync(0xffffffffu, sA, 31);
+            ps = __shfl_up_sync(0xffffffffu, sB, 1);
+            if (lane == 0) ps = carry;
+            if (vB && !(ps < sB)) incr = false;
+            carry = __shfl_sync(0xffffffffu, sB, 31);
+        }
+    } else {
     for (int32_t i0 = 0; i0 < n; i0 += 32) {
         const int32_t i = i0 + lane;
         int32_t s = INT32_MAX;
@@ -1575,6 +1600,7 @@ __global__ void __launch_bounds__(256) chainFillKernel(const Elem* __restrict__ 
         if (lane == 0) ps = carry;
         if (i < n && !(ps < s)) incr = false;
         carry = __shfl_sync(0xffffffffu, s, 31);
+    }
     }
     incr = __all_sync(0xffffffffu, incr);
     if (incr) {   // the chain walk takes the order n-1 .. 0 from the flag: nothing to write, nothing to sort
@@ -2232,7 +2258,7 @@ static void overlapsChunk(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, ui
                 const int forced = envInt("FG_SRS_MIN_PASSES", 1, 1, 3);
                 if (forced > nPass && 2 * posBits + 8 * forced <= 64) nPass = forced;
             }
-            const int segSort = envInt("FG_SEG_SORT", 0, 0, 2);   // 0 = segRadixSortKernel, 1 = segRadixSortClusterKernel, 2 = segTileSortKernel
+            const int segSort = envInt("FG_SEG_SORT", 2, 0, 2);   // 2 (default) = segTileSortKernel, 0 = segRadixSortKernel, 1 = segRadixSortClusterKernel
             if (segSort == 2) {
                 static std::once_flag tsAttr[64];   // function attributes are per device
                 std::call_once(tsAttr[ctx->device & 63], [&] {
@@ -2442,7 +2468,8 @@ static void overlapsChunk(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, ui
                         checkLaunch(ctx, "chainRunDpKernel");
                     }
                     PhaseTimer pt(ctx, "chain_fill");
-                    chainFillKernel<<<(Pn + 7) / 8, 256, 0, streamOf(ctx)>>>(hits.p, pairInfo.p, pairIds.p, Pn, pairFlags.p, runs, score.p, back.p, ord.p,
+                    auto fillK = envInt("FG_FILL_PAIRED", 1, 0, 1) ? chainFillKernel<true> : chainFillKernel<false>;
+                    fillK<<<(Pn + 7) / 8, 256, 0, streamOf(ctx)>>>(hits.p, pairInfo.p, pairIds.p, Pn, pairFlags.p, runs, score.p, back.p, ord.p,
                                                                           allSegs.p, dCells.p + 1);
                     checkLaunch(ctx, "chainFillKernel");
                 } else {
