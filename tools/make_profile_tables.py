@@ -9,7 +9,7 @@ NAMES = {"count_clear": "clear counters + bitmap", "count": "`denseCountKernel` 
          "count_partition": "`ownerTotals/ownerScatterKernel`", "count_exchange": "all-to-all of the slots (NCCL)", "count_merge": "histogram all-reduce + all-gather of the 16-bit counters",
          "select": "`selectKernel` / `minimizerRegKernel` (+ tandem, finalize)", "emit": "`emitCount/emitWriteKernel`", "index_exchange": "owner partition + all-to-all of the entries (NCCL)",
          "index_sort": "radix sort of the entries by key (CUB)", "index_table": "RLE, classify, table insert, presence bitmap (+ all-gathers)",
-         "lookup": "`queryLookupKernel` + scans", "expand": "`expandKernel<2>`", "hit_sort_radix": "`segRadixSortKernel`",
+         "lookup": "`queryLookupKernel` + scans", "expand": "`expandKernel<2>`", "hit_sort_radix": "`segTileSortKernel`", "epilogue_dev": "`divergenceKernel`, flag compaction, `gatherKeptKernel`",
          "hit_sort_top": "queries with ties: re-expansion, tie prefix, `sortHuge/Level/TailKernel`", "hit_sort_small": "queries with ties: `sortSmallKernel`",
          "group": "group starts, candidates, `pairFilterKernel`", "chain_prep": "`pairPrepKernel`", "chain_extsort_top": "extPos re-sort of non-monotone pairs (exact)",
          "chain_extsort_small": "... shared-memory part", "chain_runs": "`chainRunsKernel` (re-sorted pairs)", "chain_order": "pair order (CUB sort of run counts)",
@@ -31,7 +31,7 @@ def main():
         print("| %s (`%s`) | %.2f | %.1f %% |" % (NAMES.get(k, k), k, v, 100 * v / tot))
     dev = sum(v for _, v in rows)
     print("| **device phases together** | %.2f | %.1f %% |" % (dev, 100 * dev / tot))
-    print("| host: results D2H + divergence + per-query replay (`host_results` incl. waits), refilter, glue | %.2f | %.1f %% |" % (tot - dev, 100 * (tot - dev) / tot))
+    print("| host: results D2H (`host_results` incl. waits), refilter, glue | %.2f | %.1f %% |" % (tot - dev, 100 * (tot - dev) / tot))
     print("\n| kernel | bound | ms / launch | achieved | peak | frac |\n|---|---|---|---|---|---|")
     for r in d["roofline_kernels"]:
         print("| `%s` | %s | %.2f | %.0f %s | %.0f | %.3f |" % (r["kernel"], r["bound"], r["ms_per_launch"], r["achieved"], r["unit"], r["peak"], r["frac"]))
