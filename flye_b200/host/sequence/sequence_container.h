@@ -166,10 +166,15 @@ private:
         h = h.substr(1, end - 1);
         if (h.empty()) throw ParseException("empty header");
     }
-    static void cleanSequence(std::string& s) {   // non-ACGT letters become rand() bases (sequence_container.cpp:318-328)
+    // validateSequence (sequence_container.cpp:318-328) means to replace non-ACGT letters by rand() bases, but compares the
+    // size_t code with `-1U` (32 bits), which never matches where size_t has 64: the letter stays, rand() is NOT called (its sequence
+    // feeds estimateOverlaperParameters later), and DnaSequence's constructor ORs the all-ones code into the chunk — the letter
+    // and every later base of its 32-base chunk read as T.  Kept bit for bit (tests/test_host_ingest.py compares with the reference).
+    static void cleanSequence(std::string& s) {
         for (char& c : s)
-            if (DnaSequence::dnaToId(c) == (size_t)-1) c = "ACGT"[rand() % 4];
+            if (DnaSequence::dnaToId(c) == -1U) c = "ACGT"[rand() % 4];
     }
+    // one line without its '\n' (a trailing '\r' stays: the callers strip it after the emptiness test, as the reference does)
     static bool nextLine(gzFile fd, std::vector<char>& buf, std::string& line) {
         line.clear();
         bool got = false;
@@ -178,21 +183,24 @@ private:
             line += buf.data();
             if (!line.empty() && line.back() == '\n') { line.pop_back(); break; }
         }
-        if (!line.empty() && line.back() == '\r') line.pop_back();
         return got;
     }
+    // readFasta / readFastq (sequence_container.cpp:145-303).  The line number of an error message counts the non-empty lines
+    // consumed so far plus one, as the reference's does (blank lines are not counted; an error at the end of the file names the
+    // line after the last one).
     static void parse(const std::string& fileName, bool fasta, std::vector<FastaRecord>& out) {
         gzFile fd = gzopen(fileName.c_str(), "rb");
         if (!fd) throw ParseException("Can't open reads file");
         std::vector<char> buf(1 << 20);
         std::string line, header, seq;
-        int lineNo = 0, state = 0;
+        int lineNo = 1, state = 0;
         try {
             while (nextLine(fd, buf, line)) {
-                ++lineNo;
+                if (line.empty()) { if (!fasta) state = (state + 1) % 4; continue; }
+                if (line.back() == '\r') line.pop_back();
+                const char first = line.empty() ? '\0' : line[0];
                 if (fasta) {
-                    if (line.empty()) continue;
-                    if (line[0] == '>') {
+                    if (first == '>') {
                         if (!header.empty()) {
                             if (seq.empty()) throw ParseException("empty sequence");
                             out.emplace_back(DnaSequence(seq), header, FastaRecord::ID_NONE);
@@ -202,12 +210,12 @@ private:
                         cleanHeader(header);
                     } else { cleanSequence(line); seq += line; }
                 } else {
-                    if (line.empty()) { state = (state + 1) % 4; continue; }
-                    if (state == 0) { if (line[0] != '@') throw ParseException("Fastq format error"); header = line; cleanHeader(header); }
+                    if (state == 0) { if (first != '@') throw ParseException("Fastq format error"); header = line; cleanHeader(header); }
                     else if (state == 1) { cleanSequence(line); out.emplace_back(DnaSequence(line), header, FastaRecord::ID_NONE); }
-                    else if (state == 2 && line[0] != '+') throw ParseException("Fastq fromat error");
+                    else if (state == 2 && first != '+') throw ParseException("Fastq fromat error");
                     state = (state + 1) % 4;
                 }
+                ++lineNo;
             }
             if (fasta) {
                 if (seq.empty()) throw ParseException("empty sequence");
