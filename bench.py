@@ -479,7 +479,7 @@ def main():
     w = 4 if 2 * k <= 32 else 8
     shard_bases = int(lens[lo:hi].sum())
     n_k = shard_bases - k * (hi - lo)
-    raw_ovl = int(resident_phases.get("raw_overlaps", n_raw[0]))
+    raw_ovl = int(resident_phases.get("gathered_overlaps", resident_phases.get("raw_overlaps", n_raw[0])))   # records the edit-distance kernel aligned (before the divergence test)
     mean_ovl_len = float(np.mean(np.maximum(ovl_len_sample, 1))) if len(ovl_len_sample) else 0.0
     k8 = 12.0 * M + 40.0 * O                        # K8 as a whole; its four kernels share it evenly
     alg = {"expand": 20.0 * M,                       # K6, per-hit part: 8 B index entry read + 12 B match written

@@ -2085,7 +2085,7 @@ static bool deviceEpilogueUsable(fg_ctx* ctx) {
 // one chunk of queries (< 2^30 k-mer slots): lookup, expansion and the per-sub-batch pipeline; the raw overlap records are
 // appended to the context's pinned buffer with `reserved` = position of the query in the whole call
 // Work counters of a call, added up by the lanes.
-struct BatchTotals { std::atomic<uint64_t> pairs{0}, dpPairs{0}, cells{0}, tied{0}, presorted{0}; };
+struct BatchTotals { std::atomic<uint64_t> pairs{0}, dpPairs{0}, cells{0}, tied{0}, presorted{0}, gathered{0}; };
 // Sub-batches hand their raw records to the shared pinned buffer IN ORDER (sub-batch i directly behind sub-batch i-1), so the
 // buffer holds the records in query order whatever lane produced them: a sub-batch learns its offset when its predecessor has.
 struct OrderedCommit {
@@ -2509,7 +2509,7 @@ static void overlapsChunk(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, ui
             FG_CUDA(cudaMemcpyAsync(&nOut, outOff.p + Pn, 8, cudaMemcpyDeviceToHost, streamOf(ctx)));
             FG_CUDA(cudaMemcpyAsync(cells, dCells.p, 16, cudaMemcpyDeviceToHost, streamOf(ctx)));
             FG_CUDA(cudaStreamSynchronize(streamOf(ctx)));
-            tot.cells += cells[0]; tot.presorted += cells[1];
+            tot.cells += cells[0]; tot.presorted += cells[1]; tot.gathered += nOut;
             if (nOut) {
                 DevBuf<fg_overlap> dOut(nOut);
                 gatherOverlapsKernel<<<(Pn + 255) / 256, 256, 0, streamOf(ctx)>>>(pairInfo.p, pairIds.p, Pn, dQIds.p, ctx->dLen.p, qLen, ord.p, cands.p,
@@ -2845,7 +2845,8 @@ void overlapsBatch(fg_ctx* ctx, const uint32_t* queryIds, uint32_t nQ, const fg_
 
     ctx->timings.emplace_back("arena_mallocs", (float)(ctx->arena.mallocCalls - mallocs0)); ctx->timingCalls.push_back(1);
     ctx->timings.emplace_back("arena_gib", (float)(ctx->arena.totalBytes / 1073741824.0)); ctx->timingCalls.push_back(1);
-    ctx->timings.emplace_back("raw_overlaps", (float)nRaw); ctx->timingCalls.push_back(1);   // records copied device -> host (before the divergence filter)
+    ctx->timings.emplace_back("raw_overlaps", (float)nRaw); ctx->timingCalls.push_back(1);   // records copied device -> host (device epilogue: the kept ones)
+    ctx->timings.emplace_back("gathered_overlaps", (float)tot.gathered.load()); ctx->timingCalls.push_back(1);   // primary overlaps before the divergence test (what the edit-distance kernel aligns)
     ctx->timings.emplace_back("tied_queries", (float)totTied); ctx->timingCalls.push_back(1);   // queries that needed the exact hit sort
     ctx->timings.emplace_back("presorted_pairs", (float)totPresorted); ctx->timingCalls.push_back(1);   // pairs whose score order needed no sort
     result->n_queries = nQ;

@@ -14,6 +14,9 @@
 
 namespace restate {
 
+std::atomic<unsigned long long> dpCellsVisited{0};
+
+
 // ------------------------------------------------------------------------------------------------
 // reads
 // ------------------------------------------------------------------------------------------------
@@ -399,10 +402,12 @@ std::vector<Overlap> getSeqOverlaps(const Reads& r, const Index& idx, const Para
         if (extSorted)
             std::sort(matchesList.begin(), matchesList.end(),
                       [](const KmerMatch& k1, const KmerMatch& k2) { return k1.extPos < k2.extPos; });
+        unsigned long long cells = 0;   // predecessors the scan visits (the integer work of the stage)
         for (int32_t i = 1; i < (int32_t)scoreTable.size(); ++i) {
             int32_t maxScore = 0, maxId = 0;
             int32_t curNext = matchesList[i].curPos, extNext = matchesList[i].extPos;
             for (int32_t j = i - 1; j >= 0; --j) {
+                ++cells;
                 int32_t curPrev = matchesList[j].curPos, extPrev = matchesList[j].extPos;
                 if (0 < curNext - curPrev && curNext - curPrev < p.maxJump &&
                     0 < extNext - extPrev && extNext - extPrev < p.maxJump) {
@@ -421,6 +426,7 @@ std::vector<Overlap> getSeqOverlaps(const Reads& r, const Index& idx, const Para
             scoreTable[i] = std::max(maxScore, kmerSize);
             if (maxScore > kmerSize) backtrackTable[i] = maxId;
         }
+        dpCellsVisited += cells;
 
         std::vector<Overlap> extOverlaps;                 // :326-427 chain extraction
         std::vector<std::pair<int32_t, int32_t>> kmerMatches;

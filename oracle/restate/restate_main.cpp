@@ -167,8 +167,8 @@ int main(int argc, char** argv) {
     size_t nBases = 0; for (const auto& s : reads.fwd) nBases += s.size();
     printf("{\"reads\": %zu, \"bases\": %zu, \"k\": %d, \"threads\": %d, \"minimizers\": %d, "
            "\"t_load\": %.4f, \"t_count\": %.4f, \"t_index\": %.4f, \"t_estimate\": %.4f, \"t_overlaps\": %.4f, "
-           "\"queries\": %zu, \"overlaps\": %zu}\n",
+           "\"queries\": %zu, \"overlaps\": %zu, \"dp_cells\": %llu}\n",
            reads.fwd.size(), nBases, p.k, threads, (int)p.useMinimizers, tLoad, tCount, tIndex, tEstimate, tOverlaps,
-           nQueries, nOverlaps);
+           nQueries, nOverlaps, (unsigned long long)restate::dpCellsVisited.load());
     return 0;
 }

@@ -16,7 +16,7 @@ NAMES = {"count_clear": "clear counters + bitmap", "count": "`denseCountKernel` 
          "chain_dp": "`chainRunDpKernel`", "chain_fill": "`chainFillKernel`", "chain_ordsort_top": "score sort of non-presorted pairs (exact)",
          "chain_ordsort_small": "... shared-memory part", "chain_walk": "`chainWalkKernel<true>`", "edit": "`hpcReadsKernel` + `wfaKernel`"}
 SKIP_PREFIX = ("host_", "prep_", "arena_")
-SKIP = {"raw_overlaps", "tied_queries", "presorted_pairs"}
+SKIP = {"raw_overlaps", "gathered_overlaps", "tied_queries", "presorted_pairs"}
 
 
 def main():
