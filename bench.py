@@ -495,9 +495,17 @@ def main():
              "select": "minimizerRegKernel" if int(cfg["use_minimizers"]) else "selectKernel", "count": "denseCountKernel"}
     # integer-bound kernels: algorithmic integer operations (~15 int ops per DP cell of the reference's scan; Myers
     # word update ~17 int ops per 64 cells of edlib's band) against the IMAD/LOP3/SHF issue rate measured in this run
-    int_alg = {"chain_dp": 15.0 * stats.get("n_dp_cells", 0), "edit": 17.0 * raw_ovl * edit_sample[1]}
+    # chain_dp: the reference's scan visits `dp_cells_literal` predecessors on this read set (counted by the CPU restatement, recorded
+    # next to the reference's digest); the kernel reaches the same scores visiting `n_dp_cells` run heads.  Like the edit distance,
+    # the kernel is reported in units of the reference's algorithm; `work` has both counts.
+    dp_cells_literal = None
+    if args.scale == 1.0 and world == 1 and os.path.exists(gp):
+        dp_cells_literal = json.load(open(gp)).get("dp_cells_literal")
+    int_alg = {"chain_dp": 15.0 * (dp_cells_literal or stats.get("n_dp_cells", 0)), "edit": 17.0 * raw_ovl * edit_sample[1]}
     notes = {"edit": "integer issue: O(ND) wavefronts instead of edlib's banded bit-vectors; algorithmic ops = the reference's Myers word updates",
-             "chain_dp": "integer issue: scan over run heads; algorithmic ops = 15 per DP cell the reference evaluates",
+             "chain_dp": ("integer issue: scan over run heads; algorithmic ops = 15 per predecessor the reference's scan visits on this read set "
+                          "(tests/golden/full_scale: dp_cells_literal)") if dp_cells_literal else
+                         "integer issue: scan over run heads; algorithmic ops = 15 per run-head predecessor the kernel itself evaluates (no literal count recorded for this run)",
              "chain_walk": "latency (pointer chasing in shared memory)"}
     traffic_per_hit = {}
     try:
@@ -545,7 +553,7 @@ def main():
             "phases_ms_e2e": {p: round(v, 3) for p, v in e2e_phases.items()}, "ms_per_step_of_every_rank": per_rank, "step_wall_ms_rank0": step_walls, "step_detail_rank0": step_detail,
             "api_wall_ms": {p: round(v, 2) for p, v in resident_wall.items()}, "e2e_api_wall_ms": {p: round(v, 2) for p, v in e2e_wall.items()},
             "work": {"kmer_hits": int(M), "target_groups": int(stats.get("n_pairs", 0)), "dp_pairs": int(stats.get("n_dp_pairs", 0)),
-                     "dp_cells": int(stats.get("n_dp_cells", 0)), "overlaps": int(n_ovl),
+                     "dp_cells": int(stats.get("n_dp_cells", 0)), "dp_cells_literal": dp_cells_literal, "overlaps": int(n_ovl),
                      "mean_edit_distance_first_20k_overlaps": edit_sample[0],
                      "queries_with_hit_ties": int(resident_phases.get("tied_queries", 0)),
                      "pairs_score_order_presorted": int(resident_phases.get("presorted_pairs", 0))}}

@@ -100,10 +100,15 @@ def build_host_harness():
     if _newer(exe, deps):
         _run(["g++", "-std=c++17", "-O2", "-DFLYE_B200", "-I" + host, "-I" + os.path.join(ROOT, "include"), src, "-o", exe,
               "-L" + os.path.join(ROOT, "flye_b200"), "-lflye_b200", "-lz", "-pthread", "-Wl,-rpath,$ORIGIN/../flye_b200"])
-    # oracle/ingest_check.cpp on the mirror (the reference build of the same source is oracle/_ref/ingest_ref)
+    # oracle/ingest_check.cpp and oracle/host_api_check.cpp on the mirror (the reference builds of the same sources are
+    # oracle/_ref/ingest_ref and oracle/_ref/host_api_ref)
     src2, exe2 = os.path.join(ROOT, "oracle", "ingest_check.cpp"), os.path.join(BUILD, "flye_b200_ingest")
     if _newer(exe2, [src2] + deps[1:]):
         _run(["g++", "-std=c++17", "-O2", "-I" + host, "-I" + os.path.join(ROOT, "include"), src2, "-o", exe2,
+              "-L" + os.path.join(ROOT, "flye_b200"), "-lflye_b200", "-lz", "-pthread", "-Wl,-rpath,$ORIGIN/../flye_b200"])
+    src3, exe3 = os.path.join(ROOT, "oracle", "host_api_check.cpp"), os.path.join(BUILD, "flye_b200_host_api")
+    if _newer(exe3, [src3] + deps[1:]):
+        _run(["g++", "-std=c++17", "-O2", "-I" + host, "-I" + os.path.join(ROOT, "include"), src3, "-o", exe3,
               "-L" + os.path.join(ROOT, "flye_b200"), "-lflye_b200", "-lz", "-pthread", "-Wl,-rpath,$ORIGIN/../flye_b200"])
     return exe
 
