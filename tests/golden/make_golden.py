@@ -67,5 +67,37 @@ def main():
     shutil.rmtree(tmp)
 
 
+K17_PINS = {   # the read sets of tests/test_gpu_parity.py::test_clr_k17_parity and ::test_ont_like_k17_parity
+    "clr_k17": dict(genome_len=150000, coverage=18, error=0.10, seed=21),
+    "ont_k17": dict(genome_len=300000, coverage=20, mean_len=19000, error=0.10, seed=3),
+}
+
+
+def k17_pins():
+    """pins/k17_reference_pins.json: sha256 of the reference's dumps at k = 17 (8 GiB flat counter + 17 G-entry scan per run,
+    70-90 s each) on the read sets the GPU k = 17 tests simulate.  Only the digests are committed (the simulator is deterministic)."""
+    tmp = tempfile.mkdtemp(prefix="golden_k17_")
+    cfg = "raw_reads.cfg"
+    out = {"_comment": "sha256 of the dumps (.hist, .index, .ovlp) of the UNMODIFIED reference (oracle/_ref/flye_ref_harness, k = 17) on the "
+                       "simulated read sets of tests/test_gpu_parity.py::test_clr_k17_parity and ::test_ont_like_k17_parity (regenerated from "
+                       "`sim`); checked against the CPU restatement by tests/test_oracle_golden.py::test_restatement_k17_matches_reference_pins; "
+                       "made by tests/golden/make_golden.py --k17-pins"}
+    for name, sim in K17_PINS.items():
+        reads = pu.simulate(os.path.join(tmp, name + ".fasta"), **sim)
+        info = pu.run_oracle(reads, os.path.join(pu.CFG_DIR, cfg), os.path.join(tmp, name), binary=pu.REF_HARNESS, extra=["--dump-index"], threads=4)
+        rec = {"sim": sim, "cfg": cfg, "k": 17, "options": ["--dump-index"], "reads": info["reads"], "overlaps": info["overlaps"]}
+        for ext in ("hist", "index", "ovlp"):
+            rec[ext + "_sha256"] = hashlib.sha256(open(os.path.join(tmp, name + "." + ext), "rb").read()).hexdigest()
+        out[name] = rec
+        print(name, info["reads"], "reads", info["overlaps"], "overlaps")
+    os.makedirs(os.path.join(HERE, "pins"), exist_ok=True)
+    with open(os.path.join(HERE, "pins", "k17_reference_pins.json"), "w") as f:
+        json.dump(out, f, indent=1)
+    shutil.rmtree(tmp)
+
+
 if __name__ == "__main__":
-    main()
+    if "--k17-pins" in sys.argv:
+        k17_pins()
+    else:
+        main()

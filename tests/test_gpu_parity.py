@@ -119,7 +119,9 @@ def test_clr_options(engine, tmp_path):
 
 
 def test_clr_k17_parity(engine, tmp_path):
-    """k = 17 takes the 64-bit key path"""
+    """k = 17 takes the 64-bit key path.  The oracle here is the restatement (the reference's k = 17 flat counter needs 8 GiB and a
+    17 G-entry scan); its dumps of exactly this read set are pinned to the unmodified reference's by sha256
+    (tests/golden/pins/k17_reference_pins.json, checked by tests/test_oracle_golden.py)."""
     tmp = str(tmp_path)
     reads = pu.simulate(os.path.join(tmp, "r.fasta"), genome_len=150000, coverage=18, error=0.10, seed=21)
     pu.run_oracle(reads, RAW, os.path.join(tmp, "ref"), binary=pu.RESTATE, extra=["--dump-index"])  # the reference's k=17 flat counter needs 8 GiB + a 17 G-entry scan
@@ -261,7 +263,8 @@ def test_metagenome_uneven_coverage_parity(engine, tmp_path):
 
 
 def test_ont_like_k17_parity(engine, tmp_path):
-    """BASELINE config 3 code path at small scale: ONT-like reads (10 % error, mean 19 kb), cfg default k = 17"""
+    """BASELINE config 3 code path at small scale: ONT-like reads (10 % error, mean 19 kb), cfg default k = 17 (restatement as the
+    oracle, pinned to the reference on this read set: tests/golden/pins/k17_reference_pins.json)"""
     tmp = str(tmp_path)
     reads = pu.simulate(os.path.join(tmp, "r.fasta"), genome_len=300000, coverage=20, mean_len=19000, error=0.10, seed=3)
     ref = pu.run_oracle(reads, RAW, os.path.join(tmp, "ref"), binary=pu.RESTATE, extra=["--dump-index"])

@@ -36,3 +36,20 @@ def test_restatement_matches_golden(built, tmp_path, name):
             assert n == 0, (ext, sample[:3])
     digest = hashlib.sha256(open(out + ".index", "rb").read()).hexdigest()
     assert digest == open(os.path.join(GOLD, name + ".index.sha256")).read().strip()
+
+
+PINS = json.load(open(os.path.join(GOLD, "pins", "k17_reference_pins.json")))
+
+
+@pytest.mark.parametrize("name", [n for n in PINS if not n.startswith("_")])
+def test_restatement_k17_matches_reference_pins(built, tmp_path, name):
+    """k = 17 (64-bit keys): the reference's flat counter takes 8 GiB and a 17 G-entry scan, so the GPU k = 17 tests compare the
+    device path with the restatement; here the restatement's dumps of exactly those read sets must have the sha256 of the
+    unmodified reference's (tests/golden/pins/k17_reference_pins.json, made in the build container)."""
+    pin = PINS[name]
+    reads = pu.simulate(os.path.join(str(tmp_path), "r.fasta"), **pin["sim"])
+    out = os.path.join(str(tmp_path), "res")
+    info = pu.run_oracle(reads, os.path.join(pu.CFG_DIR, pin["cfg"]), out, binary=pu.RESTATE, extra=pin["options"])
+    assert info["reads"] == pin["reads"] and info["overlaps"] == pin["overlaps"] and info["k"] == 17
+    for ext in ("hist", "index", "ovlp"):
+        assert hashlib.sha256(open(out + "." + ext, "rb").read()).hexdigest() == pin[ext + "_sha256"], ext
