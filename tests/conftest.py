@@ -19,7 +19,7 @@ def built():
     if not os.path.exists(os.path.join(ROOT, "flye_b200", "libflye_b200.so")):
         build.build_lib()
     build.build_tools()
-    if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "flye_restate")):
+    if not all(os.path.exists(os.path.join(ROOT, "oracle", "_ref", f)) for f in ("flye_restate", "trim_restate")):
         build.build_oracle()
     return True
 

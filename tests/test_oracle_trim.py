@@ -1,0 +1,43 @@
+"""CPU: the oracle for the alignment-trimming branch of getSeqOverlaps (overlap.cpp:475-485) — the restatement of
+getAlignmentCigarKsw / checkIdyAndTrim (oracle/restate/ksw_restate.cpp: minimap2's banded ksw_extz2_sse restated at the level of its
+byte arrays, the traceback, the interval search with libstdc++'s std::sort permutation) against the unmodified reference.
+oracle/trim_check.cpp is one driver with two builds; their outputs — every CIGAR and every trimmed overlap with its divergence
+bits, on generated pairs with block-wise divergence, homopolymer runs, either strand, band doublings — must be identical.
+Where the reference binary is absent the restatement is held to the committed digests of the reference's output."""
+import hashlib
+import json
+import os
+import subprocess
+
+import pytest
+
+import parity_util as pu
+
+REF_BIN = os.path.join(pu.ROOT, "oracle", "_ref", "trim_ref")
+RESTATE_BIN = os.path.join(pu.ROOT, "oracle", "_ref", "trim_restate")
+PINS = json.load(open(os.path.join(pu.ROOT, "tests", "golden", "pins", "trim_reference_pins.json")))
+
+
+def _run(exe, cases, seed):
+    r = subprocess.run([exe, str(cases), str(seed)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    return r.stdout
+
+
+@pytest.mark.parametrize("run", PINS["runs"], ids=lambda r: "seed%d" % r["seed"])
+def test_trim_restatement_matches_reference_digests(built, run):
+    out = _run(RESTATE_BIN, run["cases"], run["seed"])
+    assert out.count(b"    cur [") == run["pieces"] > 100 and out.count(b"\n") == run["lines"]
+    assert hashlib.sha256(out).hexdigest() == run["sha256"]
+
+
+@pytest.mark.skipif(not os.path.exists(REF_BIN), reason="oracle/_ref/trim_ref is built where the reference sources are")
+def test_trim_restatement_equals_reference_on_fresh_cases(built):
+    seed = 20000 + os.getpid() % 10000          # a new seed every run: the two builds must agree on any input
+    ref, res = _run(REF_BIN, 500, seed), _run(RESTATE_BIN, 500, seed)
+    if ref != res:
+        a, b = ref.splitlines(), res.splitlines()
+        first = next((i for i, (x, y) in enumerate(zip(a, b)) if x != y), min(len(a), len(b)))
+        raise AssertionError("seed %d line %d: reference %r, restatement %r" % (seed, first, a[first:first + 1], b[first:first + 1]))
+    lens = [abs(int(l.split()[3].rstrip(b"+-")) - int(l.split()[5].rstrip(b"+-"))) for l in ref.splitlines() if l.startswith(b"case")]
+    assert sum(d > 64 for d in lens) > 50       # the first band (64) was too narrow: the doubling loop ran
