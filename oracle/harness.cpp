@@ -40,7 +40,7 @@ struct Args {
     std::string reads, cfg, out, queryReads;
     int k = -1, threads = 1, minOverlap = 1000, maxOverlaps = 0, minReadLen = -1;
     bool forceLocal = false, dumpIndex = false, bothStrands = false, noEstimate = false;
-    bool findAll = false, noOverlaps = false, keepAln = false, allExt = false;
+    bool findAll = false, noOverlaps = false, keepAln = false, allExt = false, partitionBad = false;
     bool lazy = false, perRead = false;
     long maxQueries = -1;
     long chunk = 0;          // --chunk N: answer and dump N queries at a time (bounds the memory of a 10^8-overlap run)
@@ -50,7 +50,7 @@ static void usage() {
     fprintf(stderr,
         "harness --reads F --cfg C --out PREFIX [--k K] [--threads T] [--min-overlap M]\n"
         "        [--max-overlaps N] [--force-local] [--dump-index] [--both-strands]\n"
-        "        [--no-estimate] [--find-all] [--no-overlaps] [--max-queries N] [--all-ext] [--lazy] [--per-read] [--chunk N]\n");
+        "        [--no-estimate] [--find-all] [--no-overlaps] [--max-queries N] [--all-ext] [--partition-bad] [--lazy] [--per-read] [--chunk N]\n");
 }
 
 static uint32_t idNum(FastaRecord::Id id) {
@@ -87,6 +87,7 @@ int main(int argc, char** argv) {
         else if (s == "--no-overlaps") a.noOverlaps = true;
         else if (s == "--keep-aln") a.keepAln = true;
         else if (s == "--all-ext") a.allExt = true;
+        else if (s == "--partition-bad") a.partitionBad = true;   // OverlapDetector(..., partitionBadMappings = true): the repeat stage's setting
         else if (s == "--lazy") a.lazy = true;          // lazySeqOverlaps(id) from --threads worker threads (how extender.cpp calls it)
         else if (s == "--per-read") a.perRead = true;   // one quickSeqOverlaps call per read from --threads threads, also on the mirror
         else { usage(); return 1; }
@@ -158,7 +159,7 @@ int main(int argc, char** argv) {
         OverlapDetector detector(reads, index, (int)Config::get("maximum_jump"),
                                  Parameters::get().minimumOverlap, (int)Config::get("maximum_overhang"),
                                  /*keepAlignment*/ a.keepAln, /*onlyMaxExt*/ !a.allExt, /*maxDivergence*/ 1.0f,
-                                 (bool)Config::get("reads_base_alignment"), /*partitionBadMappings*/ false,
+                                 (bool)Config::get("reads_base_alignment"), /*partitionBadMappings*/ a.partitionBad,
                                  (bool)Config::get("hpc_scoring_on"));
         // queries from a SECOND container against the index of the first, as ReadAligner::alignReads does
         // (read_aligner.cpp:178-217): ids keep running through the process-global counter

@@ -496,6 +496,8 @@ std::vector<Overlap> getSeqOverlaps(const Reads& r, const Index& idx, const Para
         for (auto& o : primary) {                         // :461-473
             if (p.nuclAlignment) o.seqDivergence = alignmentErrEdlib(r, o, p.useHpc);
             if (o.seqDivergence < maxDivergence) detected.push_back(o);
+            else if (p.partitionBadMappings)              // :475-485
+                for (const auto& piece : checkIdyAndTrim(r, o, maxDivergence, p.minOverlap, p.useHpc)) detected.push_back(piece);
         }
     }
     return detected;

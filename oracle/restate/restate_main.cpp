@@ -54,7 +54,7 @@ int main(int argc, char** argv) {
     std::string readsPath, cfgPath, out;
     int k = -1, threads = 1, minOverlap = 1000, maxOverlaps = 0, minReadLen = -1; long maxQueries = -1;
     bool forceLocal = false, dumpIndex = false, bothStrands = false, noEstimate = false, noOverlaps = false;
-    bool keepAln = false, allExt = false;
+    bool keepAln = false, allExt = false, partitionBad = false;
     for (int i = 1; i < argc; ++i) {
         std::string s = argv[i];
         auto nxt = [&]() { if (i + 1 >= argc) exit(1); return std::string(argv[++i]); };
@@ -72,6 +72,7 @@ int main(int argc, char** argv) {
         else if (s == "--no-overlaps") noOverlaps = true;
         else if (s == "--keep-aln") keepAln = true;
         else if (s == "--all-ext") allExt = true;
+        else if (s == "--partition-bad") partitionBad = true;
         else { fprintf(stderr, "unknown option %s\n", s.c_str()); return 1; }
     }
     std::map<std::string, float> cfg;
@@ -81,7 +82,7 @@ int main(int argc, char** argv) {
     p.minOverlap = minOverlap;
     p.maxJump = (int)cfg.at("maximum_jump");
     p.maxOverhang = (int)cfg.at("maximum_overhang");
-    p.keepAlignment = keepAln; p.onlyMaxExt = !allExt;
+    p.keepAlignment = keepAln; p.onlyMaxExt = !allExt; p.partitionBadMappings = partitionBad;
     p.nuclAlignment = (bool)cfg.at("reads_base_alignment");
     p.useHpc = (bool)cfg.at("hpc_scoring_on");
     p.maxDivergence = 1.0f;
