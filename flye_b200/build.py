@@ -17,7 +17,7 @@ BUILD = os.path.join(ROOT, "build")
 LIB = os.path.join(ROOT, "flye_b200", "libflye_b200.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Wno-deprecated-declarations"]
-SOURCES = ["api.cu", "count_index.cu", "overlap.cu", "editdist.cu", "comm.cu", "intpeak.cu", "closure.cu"]
+SOURCES = ["api.cu", "count_index.cu", "overlap.cu", "editdist.cu", "comm.cu", "intpeak.cu", "closure.cu", "ksw.cu"]
 
 
 def _run(cmd, **kw):
@@ -110,6 +110,12 @@ def build_host_harness():
     if _newer(exe3, [src3] + deps[1:]):
         _run(["g++", "-std=c++17", "-O2", "-I" + host, "-I" + os.path.join(ROOT, "include"), src3, "-o", exe3,
               "-L" + os.path.join(ROOT, "flye_b200"), "-lflye_b200", "-lz", "-pthread", "-Wl,-rpath,$ORIGIN/../flye_b200"])
+    # oracle/trim_check.cpp on the device build of the KSW2 routine (fg_debug_ksw_cigar); the reference / restatement / host builds of
+    # the same driver are oracle/_ref/trim_{ref,restate,core}
+    src4, exe4 = os.path.join(ROOT, "oracle", "trim_check.cpp"), os.path.join(BUILD, "flye_b200_trim_device")
+    if _newer(exe4, [src4, LIB, os.path.join(ROOT, "include", "flye_b200.h")]):
+        _run(["g++", "-std=c++17", "-O2", "-DTRIM_DEVICE", "-I" + os.path.join(ROOT, "include"), src4, "-o", exe4,
+              "-L" + os.path.join(ROOT, "flye_b200"), "-lflye_b200", "-pthread", "-Wl,-rpath,$ORIGIN/../flye_b200"])
     return exe
 
 

@@ -6,6 +6,9 @@
 // Cases: a target and a copy of it with block-wise varying divergence (clean blocks between noisy ones, so that the trimming
 // finds several pieces), homopolymer-rich stretches, length differences beyond the first band (the band is doubled), either
 // strand of either sequence, with and without homopolymer compression, three thresholds.
+// Two more builds print the CIGAR lines only (the trimming itself stays host code):
+//   (3) -DTRIM_CORE    the host build of flye_b200/csrc/ksw_core.cuh — the scalar routine the device kernel runs,
+//   (4) -DTRIM_DEVICE  the device build of the same routine through the C ABI (fg_debug_ksw_cigar, one batch for all cases).
 // Usage: trim_check N_CASES SEED      prints per case the CIGAR (digest + head) and the trimmed overlaps.
 #include <cinttypes>
 #include <cstdio>
@@ -14,11 +17,43 @@
 #include <string>
 #include <vector>
 
-#ifdef TRIM_REF
+#if defined(TRIM_REF)
 #include "sequence/sequence_container.h"
 #include "sequence/alignment.h"
+#elif defined(TRIM_CORE)
+#include "../flye_b200/csrc/ksw_core.cuh"
+#elif defined(TRIM_DEVICE)
+#include "flye_b200.h"
 #else
 #include "restate/restate.h"
+#endif
+
+#if defined(TRIM_CORE) || defined(TRIM_DEVICE)
+#define TRIM_CIGAR_ONLY 1
+static std::vector<uint8_t> baseCodes(const std::string& s) {
+    std::vector<uint8_t> v(s.size());
+    for (size_t i = 0; i < s.size(); ++i) v[i] = s[i] == 'A' ? 0 : s[i] == 'C' ? 1 : s[i] == 'G' ? 2 : 3;
+    return v;
+}
+// ksw-level CIGAR (len << 4 | op) -> the =, X, I, D runs of getAlignmentCigarKsw (alignment.cpp:172-211)
+static std::vector<std::pair<char, int>> decodeKsw(const uint32_t* cg, int n, const std::vector<uint8_t>& trg, const std::vector<uint8_t>& qry) {
+    std::vector<std::pair<char, int>> out;
+    size_t posQry = 0, posTrg = 0;
+    for (int c = 0; c < n; ++c) {
+        const int size = (int)(cg[c] >> 4);
+        const char op = "MID"[cg[c] & 0xf];
+        if (op == 'M') {
+            for (int k = 0; k < size; ++k) {
+                const char match = trg[posTrg + k] == qry[posQry + k] ? '=' : 'X';
+                if (k == 0 || match != out.back().first) out.emplace_back(match, 1);
+                else ++out.back().second;
+            }
+            posQry += size; posTrg += size;
+        } else if (op == 'I') { out.emplace_back('I', size); posQry += size; }
+        else { out.emplace_back('D', size); posTrg += size; }
+    }
+    return out;
+}
 #endif
 
 static uint32_t rngState = 88172645u;
@@ -65,27 +100,71 @@ static std::string revComp(const std::string& s) {
     return r;
 }
 
+struct Case {
+    std::string t, q;
+    bool curRc, extRc, useHpc; float maxDiv; int32_t minOverlap, curBegin, curEnd, extBegin, extEnd;
+};
+struct Piece { int32_t cb, ce, eb, ee; float div; };
+
 int main(int argc, char** argv) {
     const int nCases = argc > 1 ? atoi(argv[1]) : 60;
     if (argc > 2) rngState = (uint32_t)strtoul(argv[2], nullptr, 10) | 1u;
+    std::vector<Case> cases(nCases);
     for (int c = 0; c < nCases; ++c) {
+        Case& k = cases[c];
         const size_t n = c % 7 == 0 ? 2500 + rnd() % 4000 : 200 + rnd() % 1500;
-        const std::string t = makeTarget(n);
-        const std::string q = mutate(t, c % 5 == 0 ? 6 : 0);
-        const bool curRc = c % 4 == 1, extRc = c % 4 == 2;
-        const bool useHpc = c % 2 == 0;
-        const float maxDiv = c % 3 == 0 ? 0.05f : c % 3 == 1 ? 0.10f : 0.20f;
-        const int32_t minOverlap = c % 2 ? 50 : 150;
+        k.t = makeTarget(n);
+        k.q = mutate(k.t, c % 5 == 0 ? 6 : 0);
+        k.curRc = c % 4 == 1; k.extRc = c % 4 == 2;
+        k.useHpc = c % 2 == 0;
+        k.maxDiv = c % 3 == 0 ? 0.05f : c % 3 == 1 ? 0.10f : 0.20f;
+        k.minOverlap = c % 2 ? 50 : 150;
         // the overlap: most of both sequences (the stored sequence of a reverse strand is the reverse complement of what is aligned)
-        const int32_t curBegin = (int32_t)(rnd() % 10), curEnd = (int32_t)t.size() - (int32_t)(rnd() % 10);
-        const int32_t extBegin = (int32_t)(rnd() % 10), extEnd = (int32_t)q.size() - (int32_t)(rnd() % 10);
+        k.curBegin = (int32_t)(rnd() % 10); k.curEnd = (int32_t)k.t.size() - (int32_t)(rnd() % 10);
+        k.extBegin = (int32_t)(rnd() % 10); k.extEnd = (int32_t)k.q.size() - (int32_t)(rnd() % 10);
+    }
+    std::vector<std::vector<std::pair<char, int>>> cigars(nCases);
+    std::vector<std::vector<Piece>> pieces(nCases);
+#if defined(TRIM_DEVICE)
+    {   // one batch through the C ABI
+        std::vector<uint8_t> T, Q; std::vector<uint64_t> tOff{0}, qOff{0};
+        std::vector<std::vector<uint8_t>> trgs(nCases), qrys(nCases);
+        for (int c = 0; c < nCases; ++c) {
+            const Case& k = cases[c];
+            trgs[c] = baseCodes(k.t.substr(k.curBegin, k.curEnd - k.curBegin));
+            qrys[c] = baseCodes(k.q.substr(k.extBegin, k.extEnd - k.extBegin));
+            T.insert(T.end(), trgs[c].begin(), trgs[c].end()); tOff.push_back(T.size());
+            Q.insert(Q.end(), qrys[c].begin(), qrys[c].end()); qOff.push_back(Q.size());
+        }
+        fg_ctx* ctx = nullptr;
+        if (fg_ctx_create(0, &ctx) != FG_OK) { fprintf(stderr, "fg_ctx_create failed\n"); return 3; }
+        const uint32_t cap = 16384;
+        std::vector<uint32_t> cg((size_t)nCases * cap), nCg(nCases);
+        std::vector<int32_t> status(nCases);
+        if (fg_debug_ksw_cigar(ctx, T.data(), tOff.data(), Q.data(), qOff.data(), (uint32_t)nCases, cap, cg.data(), nCg.data(), status.data()) != FG_OK) {
+            fprintf(stderr, "fg_debug_ksw_cigar: %s\n", fg_last_error(ctx));
+            return 3;
+        }
+        for (int c = 0; c < nCases; ++c) {
+            if (status[c] == 2) { fprintf(stderr, "case %d: cigar capacity\n", c); return 3; }
+            cigars[c] = decodeKsw(cg.data() + (size_t)c * cap, (int)nCg[c], trgs[c], qrys[c]);
+        }
+        fg_ctx_destroy(ctx);
+    }
+#endif
+    for (int c = 0; c < nCases; ++c) {
+        const Case& k = cases[c];
+        const std::string& t = k.t; const std::string& q = k.q;
+        const bool curRc = k.curRc, extRc = k.extRc, useHpc = k.useHpc;
+        const float maxDiv = k.maxDiv;
+        const int32_t minOverlap = k.minOverlap, curBegin = k.curBegin, curEnd = k.curEnd, extBegin = k.extBegin, extEnd = k.extEnd;
         const std::string storedCur = curRc ? revComp(t) : t, storedExt = extRc ? revComp(q) : q;
+        (void)storedCur; (void)storedExt; (void)useHpc; (void)maxDiv; (void)minOverlap;
+        std::vector<std::pair<char, int>>& cigar = cigars[c];
+        std::vector<Piece>& pcs = pieces[c];
         printf("case %d cur %zu%s ext %zu%s hpc %d maxDiv %.2f minOvlp %d\n", c, t.size(), curRc ? "-" : "+", q.size(), extRc ? "-" : "+", (int)useHpc,
                (double)maxDiv, minOverlap);
-        std::vector<std::pair<char, int>> cigar;
-        struct Piece { int32_t cb, ce, eb, ee; float div; };
-        std::vector<Piece> pieces;
-#ifdef TRIM_REF
+#if defined(TRIM_REF)
         SequenceContainer sc;
         const FastaRecord& curRec = sc.addSequence(DnaSequence(storedCur), "cur");
         const FastaRecord::Id curFwd = curRec.id;
@@ -101,7 +180,26 @@ int main(int argc, char** argv) {
         ov.curId = curId; ov.curBegin = curBegin; ov.curEnd = curEnd; ov.curLen = (int32_t)t.size();
         ov.extId = extId; ov.extBegin = extBegin; ov.extEnd = extEnd; ov.extLen = (int32_t)q.size();
         ov.score = 1234; ov.seqDivergence = 0.5f;
-        for (auto& p : checkIdyAndTrim(ov, curSeq, extSeq, maxDiv, minOverlap, useHpc)) pieces.push_back({p.curBegin, p.curEnd, p.extBegin, p.extEnd, p.seqDivergence});
+        for (auto& p : checkIdyAndTrim(ov, curSeq, extSeq, maxDiv, minOverlap, useHpc)) pcs.push_back({p.curBegin, p.curEnd, p.extBegin, p.extEnd, p.seqDivergence});
+#elif defined(TRIM_CORE)
+        {   // getAlignmentCigarKsw's band loop around the shared scalar routine
+            const std::vector<uint8_t> trg = baseCodes(t.substr(curBegin, curEnd - curBegin)), qry = baseCodes(q.substr(extBegin, extEnd - extBegin));
+            std::vector<uint32_t> cg(16384);
+            int nCg = 0;
+            for (int band = 64;; band *= 2) {
+                const fg::KswSizes z = fg::kswSizes((int)qry.size(), (int)trg.size(), band);
+                std::vector<uint8_t> mem(z.memBytes, 0xAB), p(z.pBytes, 0xCD);   // (the routine must not depend on what the scratch held)
+                std::vector<int> off(2 * z.rounds);
+                const int rc = fg::kswExtz2Core(qry.data(), (int)qry.size(), trg.data(), (int)trg.size(), band, mem.data(), p.data(), off.data(),
+                                                off.data() + z.rounds, cg.data(), (int)cg.size(), &nCg);
+                if (rc == fg::KSW_CIGAR_OVERFLOW) { fprintf(stderr, "case %d: cigar capacity\n", c); return 3; }
+                if (rc != fg::KSW_BAND_TOO_NARROW) break;
+                if (band > (int)std::max(qry.size(), trg.size())) { nCg = 0; break; }
+            }
+            cigar = decodeKsw(cg.data(), nCg, trg, qry);
+        }
+#elif defined(TRIM_DEVICE)
+        // (computed above)
 #else
         restate::Reads reads;
         auto codes = [](const std::string& s) { std::vector<uint8_t> v(s.size()); for (size_t i = 0; i < s.size(); ++i) v[i] = s[i] == 'A' ? 0 : s[i] == 'C' ? 1 : s[i] == 'G' ? 2 : 3; return v; };
@@ -116,14 +214,18 @@ int main(int argc, char** argv) {
         ov.curId = curId; ov.curBegin = curBegin; ov.curEnd = curEnd; ov.curLen = (int32_t)t.size();
         ov.extId = extId; ov.extBegin = extBegin; ov.extEnd = extEnd; ov.extLen = (int32_t)q.size();
         ov.score = 1234; ov.seqDivergence = 0.5f;
-        for (auto& p : restate::checkIdyAndTrim(reads, ov, maxDiv, minOverlap, useHpc)) pieces.push_back({p.curBegin, p.curEnd, p.extBegin, p.extEnd, p.seqDivergence});
+        for (auto& p : restate::checkIdyAndTrim(reads, ov, maxDiv, minOverlap, useHpc)) pcs.push_back({p.curBegin, p.curEnd, p.extBegin, p.extEnd, p.seqDivergence});
 #endif
         uint64_t h = 1469598103934665603ULL;
         for (auto& o : cigar) { h = fnv(h, (uint64_t)o.first); h = fnv(h, (uint64_t)o.second); }
         printf("  cigar ops %zu digest %016" PRIx64 " head", cigar.size(), h);
         for (size_t i = 0; i < cigar.size() && i < 12; ++i) printf(" %d%c", cigar[i].second, cigar[i].first);
-        printf("\n  pieces %zu\n", pieces.size());
-        for (auto& p : pieces) { uint32_t bits; memcpy(&bits, &p.div, 4); printf("    cur [%d,%d) ext [%d,%d) div %08x\n", p.cb, p.ce, p.eb, p.ee, bits); }
+#ifdef TRIM_CIGAR_ONLY
+        printf("\n");
+#else
+        printf("\n  pieces %zu\n", pcs.size());
+        for (auto& p : pcs) { uint32_t bits; memcpy(&bits, &p.div, 4); printf("    cur [%d,%d) ext [%d,%d) div %08x\n", p.cb, p.ce, p.eb, p.ee, bits); }
+#endif
     }
     return 0;
 }

@@ -15,6 +15,7 @@ import parity_util as pu
 
 REF_BIN = os.path.join(pu.ROOT, "oracle", "_ref", "trim_ref")
 RESTATE_BIN = os.path.join(pu.ROOT, "oracle", "_ref", "trim_restate")
+CORE_BIN = os.path.join(pu.ROOT, "oracle", "_ref", "trim_core")
 PINS = json.load(open(os.path.join(pu.ROOT, "tests", "golden", "pins", "trim_reference_pins.json")))
 
 
@@ -41,3 +42,18 @@ def test_trim_restatement_equals_reference_on_fresh_cases(built):
         raise AssertionError("seed %d line %d: reference %r, restatement %r" % (seed, first, a[first:first + 1], b[first:first + 1]))
     lens = [abs(int(l.split()[3].rstrip(b"+-")) - int(l.split()[5].rstrip(b"+-"))) for l in ref.splitlines() if l.startswith(b"case")]
     assert sum(d > 64 for d in lens) > 50       # the first band (64) was too narrow: the doubling loop ran
+
+
+def cigar_lines(out):
+    return [l for l in out.splitlines() if l.startswith(b"case") or l.startswith(b"  cigar")]
+
+
+def test_device_routine_host_build_gives_the_reference_cigars(built):
+    """flye_b200/csrc/ksw_core.cuh — the scalar routine kswCigarKernel runs, one thread per alignment — compiled for the host
+    (oracle/_ref/trim_core, scratch pre-filled with garbage): every CIGAR equals the restatement's, which is pinned to the
+    reference's above (and compared with it directly where the reference binary exists)."""
+    for cases, seed in ((400, 1), (300, 77)):
+        core, res = _run(CORE_BIN, cases, seed), _run(RESTATE_BIN, cases, seed)
+        assert cigar_lines(core) == cigar_lines(res) and len(cigar_lines(core)) == 2 * cases
+        if os.path.exists(REF_BIN):
+            assert cigar_lines(core) == cigar_lines(_run(REF_BIN, cases, seed))
