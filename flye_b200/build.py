@@ -116,6 +116,11 @@ def build_host_harness():
     if _newer(exe4, [src4, LIB, os.path.join(ROOT, "include", "flye_b200.h")]):
         _run(["g++", "-std=c++17", "-O2", "-DTRIM_DEVICE", "-I" + os.path.join(ROOT, "include"), src4, "-o", exe4,
               "-L" + os.path.join(ROOT, "flye_b200"), "-lflye_b200", "-pthread", "-Wl,-rpath,$ORIGIN/../flye_b200"])
+    # ... and on the mirror's own trimming tail (hpcRange + trimByCigar) around the routine's host build
+    exe5 = os.path.join(BUILD, "flye_b200_trim_mirror")
+    if _newer(exe5, [src4, os.path.join(CSRC, "ksw_core.cuh")] + deps[1:]):
+        _run(["g++", "-std=c++17", "-O2", "-DTRIM_MIRROR", "-I" + host, "-I" + os.path.join(ROOT, "include"), src4, "-o", exe5,
+              "-L" + os.path.join(ROOT, "flye_b200"), "-lflye_b200", "-lz", "-pthread", "-Wl,-rpath,$ORIGIN/../flye_b200"])
     return exe
 
 

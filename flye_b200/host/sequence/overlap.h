@@ -6,6 +6,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdlib>
+#include <functional>
 #include <memory>
 #include <mutex>
 #include <sstream>
@@ -142,6 +143,87 @@ private:
 std::vector<OverlapRange> checkIdyAndTrim(OverlapRange& ovlp, const DnaSequence& curSeq, const DnaSequence& extSeq, float maxDivergence,
                                           int32_t minOverlap, bool useHpc) __attribute__((weak));
 
+// The same trimming with the banded alignment on the device (FLYE_B200_DEVICE_KSW=1; default off until the repeat stage has run with
+// it on a GPU): homopolymer compression (alignment.cpp:52-70), then fg_debug_ksw_cigar for all rejected overlaps of a call in one
+// batch, then the host tail below — the CIGAR's =/X split (alignment.cpp:172-211), the search for the longest stretches below the
+// divergence threshold, their greedy non-overlapping choice (std::sort by length: the same libstdc++ permutation as in the
+// reference) and the mapping back to uncompressed coordinates (alignment.cpp:330-452).  tests/test_oracle_trim.py runs the tail on
+// CIGARs of the routine's host build and compares the pieces with the reference's checkIdyAndTrim.
+namespace flye_b200 {
+struct HpcRange { std::vector<uint8_t> seq; std::vector<int32_t> offsetTable; };
+inline HpcRange hpcRange(const DnaSequence& s, int32_t start, int32_t length, bool compress) {
+    HpcRange h;
+    h.seq.reserve(length); h.offsetTable.reserve(length);
+    for (int32_t i = 0; i < length; ++i) {
+        const uint8_t b = (uint8_t)s.atRaw((size_t)start + i);
+        if (!compress || i == 0 || h.seq.back() != b) { h.seq.push_back(b); h.offsetTable.push_back(i); }
+    }
+    return h;
+}
+// kswCigar: n entries len << 4 | op (0 = M, 1 = I: ext only, 2 = D: cur only) of the alignment of ext.seq (query) against cur.seq (target)
+inline std::vector<OverlapRange> trimByCigar(const OverlapRange& ovlp, const HpcRange& cur, const HpcRange& ext, const uint32_t* kswCigar, size_t n,
+                                             float maxDivergence, int32_t minOverlap) {
+    struct Op { char op; int len; };
+    std::vector<Op> cigar;
+    size_t posQry = 0, posTrg = 0;
+    for (size_t c = 0; c < n; ++c) {
+        const int size = (int)(kswCigar[c] >> 4);
+        const uint32_t code = kswCigar[c] & 0xf;
+        if (code == 0) {
+            for (int k = 0; k < size; ++k) {
+                const char match = cur.seq[posTrg + k] == ext.seq[posQry + k] ? '=' : 'X';
+                if (k == 0 || match != cigar.back().op) cigar.push_back({match, 1});
+                else ++cigar.back().len;
+            }
+            posQry += size; posTrg += size;
+        } else if (code == 1) { cigar.push_back({'I', size}); posQry += size; }
+        else { cigar.push_back({'D', size}); posTrg += size; }
+    }
+    const int m = (int)cigar.size();
+    std::vector<int> sumErrors(1, 0), sumCurLen(1, 0), sumExtLen(1, 0);
+    for (const Op& op : cigar) {
+        const int curConsumed = op.op == 'I' ? 0 : op.len, extConsumed = op.op == 'D' ? 0 : op.len;
+        sumCurLen.push_back(sumCurLen.back() + curConsumed);
+        sumExtLen.push_back(sumExtLen.back() + extConsumed);
+        sumErrors.push_back(sumErrors.back() + (op.op != '=' ? op.len : 0));
+    }
+    struct IntervalDiv { int start, end; float divergence; int realLen; };
+    std::vector<IntervalDiv> good;
+    for (int intLen = m; intLen > 0; --intLen)
+        for (int intStart = 0; intStart < m - intLen + 1; ++intStart) {
+            const int i = intStart, j = intStart + intLen - 1;
+            if (cigar[i].op != '=' || cigar[j].op != '=') continue;
+            const int rangeLen = std::max(sumCurLen[j + 1] - sumCurLen[i], sumExtLen[j + 1] - sumExtLen[i]);
+            const float divergence = float(sumErrors[j + 1] - sumErrors[i]) / rangeLen;
+            if (divergence < maxDivergence) good.push_back({i, j, divergence, rangeLen});
+        }
+    std::sort(good.begin(), good.end(), [](const IntervalDiv& a, const IntervalDiv& b) { return a.realLen > b.realLen; });
+    std::vector<IntervalDiv> chosen;
+    for (const IntervalDiv& iv : good) {
+        bool intersects = false;
+        for (const IntervalDiv& o : chosen)
+            if (std::min(iv.end + 1, o.end + 1) - std::max(iv.start, o.start) > 0) { intersects = true; break; }
+        if (!intersects) chosen.push_back(iv);
+    }
+    std::vector<OverlapRange> trimmed;
+    for (const IntervalDiv& cand : chosen) {
+        OverlapRange o = ovlp;
+        o.seqDivergence = cand.divergence;
+        size_t pq = 0, pt = 0;
+        for (int i = 0; i < m; ++i) {
+            if (i == cand.start) { o.curBegin += cur.offsetTable[pt]; o.extBegin += ext.offsetTable[pq]; }
+            if (cigar[i].op == '=' || cigar[i].op == 'X') { pq += cigar[i].len; pt += cigar[i].len; }
+            else if (cigar[i].op == 'I') pq += cigar[i].len;
+            else pt += cigar[i].len;
+            if (i == cand.end) { o.curEnd = ovlp.curBegin + cur.offsetTable[pt - 1]; o.extEnd = ovlp.extBegin + ext.offsetTable[pq - 1]; }
+        }
+        if (o.curRange() > minOverlap && o.extRange() > minOverlap) trimmed.push_back(o);
+    }
+    return trimmed;
+}
+inline bool deviceKswEnabled() { const char* e = std::getenv("FLYE_B200_DEVICE_KSW"); return e && std::atoi(e) != 0; }
+}  // namespace flye_b200
+
 struct OvlpDivStats {
     static const size_t MAX_STATS = 1000000;
     OvlpDivStats() : divVec(MAX_STATS), vecSize(0) {}
@@ -161,8 +243,8 @@ public:
           _keepAlignment(keepAlignment), _onlyMaxExt(onlyMaxExt), _nuclAlignment(nuclAlignment),
           _partitionBadMappings(partitionBadMappings), _useHpc(useHpc), _maxDivergence(maxDivergence), _vertexIndex(vertexIndex),
           _seqContainer(seqContainer) {
-        if (partitionBadMappings && !checkIdyAndTrim)
-            throw std::runtime_error("flye_b200: partitionBadMappings needs the reference's alignment.cpp (checkIdyAndTrim) linked in");
+        if (partitionBadMappings && !checkIdyAndTrim && !flye_b200::deviceKswEnabled())
+            throw std::runtime_error("flye_b200: partitionBadMappings needs the reference's alignment.cpp (checkIdyAndTrim) linked in (or FLYE_B200_DEVICE_KSW=1)");
     }
     friend class OverlapContainer;
 
@@ -223,7 +305,43 @@ private:
                 for (auto* w : wnd) if (w && w->curRange() > 0) divStats.add(w->seqDivergence);
             }
         }
-        if (!rejected.empty()) {
+        if (!rejected.empty() && flye_b200::deviceKswEnabled()) {
+            // the banded alignments of all rejected overlaps in one device batch; compression and the interval search on host threads
+            std::vector<flye_b200::HpcRange> cur(rejected.size()), ext(rejected.size());
+            std::vector<std::vector<OverlapRange>> pieces(rejected.size());
+            auto parallel = [&](const std::function<void(size_t)>& fn) {
+                std::atomic<size_t> next(0);
+                auto work = [&]() { for (size_t i; (i = next.fetch_add(1)) < rejected.size();) fn(i); };
+                std::vector<std::thread> pool;
+                const size_t nThreads = std::min<size_t>(std::max<size_t>(1, Parameters::get().numThreads), rejected.size());
+                for (size_t t = 1; t < nThreads; ++t) pool.emplace_back(work);
+                work();
+                for (auto& t : pool) t.join();
+            };
+            parallel([&](size_t i) {
+                const OverlapRange& o = rejected[i].ovlp;
+                cur[i] = flye_b200::hpcRange(queryContainer->getSeq(o.curId), o.curBegin, o.curRange(), _useHpc);
+                ext[i] = flye_b200::hpcRange(_seqContainer.getSeq(o.extId), o.extBegin, o.extRange(), _useHpc);
+            });
+            std::vector<uint8_t> T, Q; std::vector<uint64_t> tOff(1, 0), qOff(1, 0);
+            size_t longest = 1;
+            for (size_t i = 0; i < rejected.size(); ++i) {
+                T.insert(T.end(), cur[i].seq.begin(), cur[i].seq.end()); tOff.push_back(T.size());
+                Q.insert(Q.end(), ext[i].seq.begin(), ext[i].seq.end()); qOff.push_back(Q.size());
+                longest = std::max(longest, cur[i].seq.size() + ext[i].seq.size() + 2);
+            }
+            const uint32_t cap = (uint32_t)std::min<size_t>(longest, (size_t)1 << 20);   // a CIGAR has at most tlen + qlen entries
+            std::vector<uint32_t> cigars(rejected.size() * (size_t)cap), nCigar(rejected.size());
+            std::vector<int32_t> status(rejected.size());
+            dev->check(fg_debug_ksw_cigar(dev->ctx, T.data(), tOff.data(), Q.data(), qOff.data(), (uint32_t)rejected.size(), cap, cigars.data(), nCigar.data(),
+                                          status.data()));
+            for (int32_t st : status) if (st == 2) throw std::runtime_error("flye_b200: CIGAR capacity exceeded in the device alignment");
+            parallel([&](size_t i) {
+                pieces[i] = flye_b200::trimByCigar(rejected[i].ovlp, cur[i], ext[i], cigars.data() + i * (size_t)cap, nCigar[i], _maxDivergence, _minOverlap);
+            });
+            for (size_t i = rejected.size(); i-- > 0;)   // back to front: the insertion points of earlier ones stay valid
+                out[rejected[i].q].insert(out[rejected[i].q].begin() + rejected[i].at, pieces[i].begin(), pieces[i].end());
+        } else if (!rejected.empty()) {
             // KSW2 trimming on the host, in parallel; the pieces take the place of the rejected overlap in its query's list
             std::vector<std::vector<OverlapRange>> pieces(rejected.size());
             std::atomic<size_t> next(0);

@@ -9,6 +9,9 @@
 // Two more builds print the CIGAR lines only (the trimming itself stays host code):
 //   (3) -DTRIM_CORE    the host build of flye_b200/csrc/ksw_core.cuh — the scalar routine the device kernel runs,
 //   (4) -DTRIM_DEVICE  the device build of the same routine through the C ABI (fg_debug_ksw_cigar, one batch for all cases).
+// And one more prints everything again:
+//   (5) -DTRIM_MIRROR  the host mirror's own trimming tail (flye_b200/host/sequence/overlap.h: hpcRange + trimByCigar — what
+//                      FLYE_B200_DEVICE_KSW=1 runs around the device alignment) fed with CIGARs of the routine's host build.
 // Usage: trim_check N_CASES SEED      prints per case the CIGAR (digest + head) and the trimmed overlaps.
 #include <cinttypes>
 #include <cstdio>
@@ -22,14 +25,40 @@
 #include "sequence/alignment.h"
 #elif defined(TRIM_CORE)
 #include "../flye_b200/csrc/ksw_core.cuh"
+#elif defined(TRIM_MIRROR)
+#include "sequence/sequence_container.h"
+#include "sequence/overlap.h"
+#include "../flye_b200/csrc/ksw_core.cuh"
 #elif defined(TRIM_DEVICE)
 #include "flye_b200.h"
 #else
 #include "restate/restate.h"
 #endif
 
+#if defined(TRIM_CORE) || defined(TRIM_MIRROR)
+// getAlignmentCigarKsw's band loop (alignment.cpp:150-165) around the shared scalar routine; the ksw-level CIGAR
+static std::vector<uint32_t> coreCigar(const std::vector<uint8_t>& trg, const std::vector<uint8_t>& qry) {
+    std::vector<uint32_t> cg(trg.size() + qry.size() + 2);
+    int nCg = 0;
+    for (int band = 64;; band *= 2) {
+        const fg::KswSizes z = fg::kswSizes((int)qry.size(), (int)trg.size(), band);
+        std::vector<uint8_t> mem(z.memBytes, 0xAB), p(z.pBytes, 0xCD);   // (the routine must not depend on what the scratch held)
+        std::vector<int> off(2 * z.rounds);
+        const int rc = fg::kswExtz2Core(qry.data(), (int)qry.size(), trg.data(), (int)trg.size(), band, mem.data(), p.data(), off.data(),
+                                        off.data() + z.rounds, cg.data(), (int)cg.size(), &nCg);
+        if (rc == fg::KSW_CIGAR_OVERFLOW) { fprintf(stderr, "cigar capacity\n"); exit(3); }
+        if (rc != fg::KSW_BAND_TOO_NARROW) break;
+        if (band > (int)std::max(qry.size(), trg.size())) { nCg = 0; break; }
+    }
+    cg.resize(nCg);
+    return cg;
+}
+#endif
+
 #if defined(TRIM_CORE) || defined(TRIM_DEVICE)
 #define TRIM_CIGAR_ONLY 1
+#endif
+#if defined(TRIM_CORE) || defined(TRIM_DEVICE) || defined(TRIM_MIRROR)
 static std::vector<uint8_t> baseCodes(const std::string& s) {
     std::vector<uint8_t> v(s.size());
     for (size_t i = 0; i < s.size(); ++i) v[i] = s[i] == 'A' ? 0 : s[i] == 'C' ? 1 : s[i] == 'G' ? 2 : 3;
@@ -182,21 +211,30 @@ int main(int argc, char** argv) {
         ov.score = 1234; ov.seqDivergence = 0.5f;
         for (auto& p : checkIdyAndTrim(ov, curSeq, extSeq, maxDiv, minOverlap, useHpc)) pcs.push_back({p.curBegin, p.curEnd, p.extBegin, p.extEnd, p.seqDivergence});
 #elif defined(TRIM_CORE)
-        {   // getAlignmentCigarKsw's band loop around the shared scalar routine
+        {
             const std::vector<uint8_t> trg = baseCodes(t.substr(curBegin, curEnd - curBegin)), qry = baseCodes(q.substr(extBegin, extEnd - extBegin));
-            std::vector<uint32_t> cg(16384);
-            int nCg = 0;
-            for (int band = 64;; band *= 2) {
-                const fg::KswSizes z = fg::kswSizes((int)qry.size(), (int)trg.size(), band);
-                std::vector<uint8_t> mem(z.memBytes, 0xAB), p(z.pBytes, 0xCD);   // (the routine must not depend on what the scratch held)
-                std::vector<int> off(2 * z.rounds);
-                const int rc = fg::kswExtz2Core(qry.data(), (int)qry.size(), trg.data(), (int)trg.size(), band, mem.data(), p.data(), off.data(),
-                                                off.data() + z.rounds, cg.data(), (int)cg.size(), &nCg);
-                if (rc == fg::KSW_CIGAR_OVERFLOW) { fprintf(stderr, "case %d: cigar capacity\n", c); return 3; }
-                if (rc != fg::KSW_BAND_TOO_NARROW) break;
-                if (band > (int)std::max(qry.size(), trg.size())) { nCg = 0; break; }
-            }
-            cigar = decodeKsw(cg.data(), nCg, trg, qry);
+            const std::vector<uint32_t> cg = coreCigar(trg, qry);
+            cigar = decodeKsw(cg.data(), (int)cg.size(), trg, qry);
+        }
+#elif defined(TRIM_MIRROR)
+        {
+            SequenceContainer sc;
+            const FastaRecord::Id curFwd = sc.addSequence(DnaSequence(storedCur), "cur").id;
+            const FastaRecord::Id extFwd = sc.addSequence(DnaSequence(storedExt), "ext").id;
+            const FastaRecord::Id curId = curRc ? curFwd.rc() : curFwd, extId = extRc ? extFwd.rc() : extFwd;
+            const flye_b200::HpcRange rawCur = flye_b200::hpcRange(sc.getSeq(curId), curBegin, curEnd - curBegin, false);
+            const flye_b200::HpcRange rawExt = flye_b200::hpcRange(sc.getSeq(extId), extBegin, extEnd - extBegin, false);
+            const std::vector<uint32_t> cgRaw = coreCigar(rawCur.seq, rawExt.seq);
+            cigar = decodeKsw(cgRaw.data(), (int)cgRaw.size(), rawCur.seq, rawExt.seq);
+            OverlapRange ov;
+            ov.curId = curId; ov.curBegin = curBegin; ov.curEnd = curEnd; ov.curLen = (int32_t)t.size();
+            ov.extId = extId; ov.extBegin = extBegin; ov.extEnd = extEnd; ov.extLen = (int32_t)q.size();
+            ov.score = 1234; ov.seqDivergence = 0.5f;
+            const flye_b200::HpcRange hc = flye_b200::hpcRange(sc.getSeq(curId), ov.curBegin, ov.curRange(), useHpc);
+            const flye_b200::HpcRange he = flye_b200::hpcRange(sc.getSeq(extId), ov.extBegin, ov.extRange(), useHpc);
+            const std::vector<uint32_t> cg = coreCigar(hc.seq, he.seq);
+            for (auto& p : flye_b200::trimByCigar(ov, hc, he, cg.data(), cg.size(), maxDiv, minOverlap))
+                pcs.push_back({p.curBegin, p.curEnd, p.extBegin, p.extEnd, p.seqDivergence});
         }
 #elif defined(TRIM_DEVICE)
         // (computed above)

@@ -16,6 +16,7 @@ import parity_util as pu
 REF_BIN = os.path.join(pu.ROOT, "oracle", "_ref", "trim_ref")
 RESTATE_BIN = os.path.join(pu.ROOT, "oracle", "_ref", "trim_restate")
 CORE_BIN = os.path.join(pu.ROOT, "oracle", "_ref", "trim_core")
+MIRROR_BIN = os.path.join(pu.ROOT, "build", "flye_b200_trim_mirror")
 PINS = json.load(open(os.path.join(pu.ROOT, "tests", "golden", "pins", "trim_reference_pins.json")))
 
 
@@ -57,3 +58,15 @@ def test_device_routine_host_build_gives_the_reference_cigars(built):
         assert cigar_lines(core) == cigar_lines(res) and len(cigar_lines(core)) == 2 * cases
         if os.path.exists(REF_BIN):
             assert cigar_lines(core) == cigar_lines(_run(REF_BIN, cases, seed))
+
+
+@pytest.mark.parametrize("run", PINS["runs"][:2], ids=lambda r: "seed%d" % r["seed"])
+def test_mirror_trimming_tail_matches_reference_digests(built, run):
+    """What the host mirror runs around the device alignment with FLYE_B200_DEVICE_KSW=1 (flye_b200/host/sequence/overlap.h:
+    hpcRange + trimByCigar — homopolymer compression, =/X split, interval search with std::sort, coordinate mapping), fed with
+    the CIGARs of the routine's host build: CIGAR lines and trimmed overlaps with the digest of the reference's checkIdyAndTrim."""
+    if not os.path.exists(MIRROR_BIN):
+        from flye_b200 import build
+        build.build_host_harness()
+    out = _run(MIRROR_BIN, run["cases"], run["seed"])
+    assert hashlib.sha256(out).hexdigest() == run["sha256"]
