@@ -22,7 +22,7 @@ SYMBOLS = ["fg_ctx_create", "fg_ctx_destroy", "fg_last_error", "fg_stream", "fg_
            "fg_reads_upload", "fg_reads_upload_ascii", "fg_queries_upload", "fg_count_kmers", "fg_kmer_hist", "fg_kmer_freq",
            "fg_build_index_solid", "fg_build_index_minimizers", "fg_index_clear", "fg_index_lookup",
            "fg_index_positions", "fg_index_export", "fg_overlaps_batch", "fg_overlaps_refilter", "fg_overlaps_closure", "fg_comm_unique_id", "fg_comm_init",
-           "fg_comm_set_shard", "fg_debug_int_peak", "fg_debug_warp_sort", "fg_debug_edit_distance", "fg_debug_edit_distance_rc", "fg_debug_ksw_cigar"]
+           "fg_comm_set_shard", "fg_debug_int_peak", "fg_debug_warp_sort", "fg_debug_edit_distance", "fg_debug_edit_distance_rc", "fg_align_cigar_batch"]
 
 
 class IndexStats(C.Structure):

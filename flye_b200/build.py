@@ -110,7 +110,7 @@ def build_host_harness():
     if _newer(exe3, [src3] + deps[1:]):
         _run(["g++", "-std=c++17", "-O2", "-I" + host, "-I" + os.path.join(ROOT, "include"), src3, "-o", exe3,
               "-L" + os.path.join(ROOT, "flye_b200"), "-lflye_b200", "-lz", "-pthread", "-Wl,-rpath,$ORIGIN/../flye_b200"])
-    # oracle/trim_check.cpp on the device build of the KSW2 routine (fg_debug_ksw_cigar); the reference / restatement / host builds of
+    # oracle/trim_check.cpp on the device build of the KSW2 routine (fg_align_cigar_batch); the reference / restatement / host builds of
     # the same driver are oracle/_ref/trim_{ref,restate,core}
     src4, exe4 = os.path.join(ROOT, "oracle", "trim_check.cpp"), os.path.join(BUILD, "flye_b200_trim_device")
     if _newer(exe4, [src4, LIB, os.path.join(ROOT, "include", "flye_b200.h")]):

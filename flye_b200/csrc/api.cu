@@ -374,11 +374,11 @@ int fg_debug_edit_distance_rc(fg_ctx* ctx, const uint8_t* a, int n, int rc_a, co
     });
 }
 
-int fg_debug_ksw_cigar(fg_ctx* ctx, const uint8_t* targets, const uint64_t* target_offsets, const uint8_t* queries, const uint64_t* query_offsets,
+int fg_align_cigar_batch(fg_ctx* ctx, const uint8_t* targets, const uint64_t* target_offsets, const uint8_t* queries, const uint64_t* query_offsets,
                        uint32_t n_pairs, uint32_t cigar_cap, uint32_t* cigars, uint32_t* n_cigar, int32_t* status) {
     return guarded(ctx, [&] {
         if (n_pairs && (!target_offsets || !query_offsets || !cigars || !n_cigar || !status)) throw Error(FG_ERR_ARG, "bad argument");
-        fg::debugKswCigar(ctx, targets, target_offsets, queries, query_offsets, n_pairs, cigar_cap, cigars, n_cigar, status);
+        fg::alignCigarBatch(ctx, targets, target_offsets, queries, query_offsets, n_pairs, cigar_cap, cigars, n_cigar, status);
     });
 }
 

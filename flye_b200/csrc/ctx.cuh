@@ -306,7 +306,7 @@ void prepareEditDistances(fg_ctx* ctx, bool useHpc, bool querySet);   // builds 
 double intPeak(fg_ctx* ctx);
 int debugEditDistance(fg_ctx* ctx, const uint8_t* a, int n, const uint8_t* b, int m, int rcA, int rcB);
 void debugWarpSort(fg_ctx* ctx, uint64_t* keys, uint32_t* vals, const uint64_t* segOffsets, uint32_t nSegs);
-void debugKswCigar(fg_ctx* ctx, const uint8_t* targets, const uint64_t* tOff, const uint8_t* queries, const uint64_t* qOff, uint32_t n, uint32_t cigarCap,
+void alignCigarBatch(fg_ctx* ctx, const uint8_t* targets, const uint64_t* tOff, const uint8_t* queries, const uint64_t* qOff, uint32_t n, uint32_t cigarCap,
                    uint32_t* cigars, uint32_t* nCigar, int32_t* status);
 
 }  // namespace fg

@@ -1,9 +1,8 @@
-// flye_b200 — device build of the banded KSW2 alignment behind checkIdyAndTrim (ksw_core.cuh), reachable through the
-// test hook fg_debug_ksw_cigar.  One thread per alignment: the routine is ksw2's own recurrence byte for byte (its results depend
+// flye_b200 — device build of the banded KSW2 alignment behind checkIdyAndTrim (ksw_core.cuh): fg_align_cigar_batch.  One thread per alignment: the routine is ksw2's own recurrence byte for byte (its results depend
 // on ksw2's in-place block updates, see ksw_core.cuh), so the first device version parallelises over alignments only.  The band
 // doubling of getAlignmentCigarKsw (alignment.cpp:150-165) is driven from the host: every round launches the pairs whose band
-// was too narrow with twice the band.  Not wired into the host mirror yet — partitionBadMappings still calls the reference's own
-// checkIdyAndTrim on host threads.
+// was too narrow with twice the band.  The host mirror uses it for partitionBadMappings when FLYE_B200_DEVICE_KSW=1 (default: the
+// reference's own checkIdyAndTrim on host threads).
 #include "ctx.cuh"
 #include "ksw_core.cuh"
 
@@ -29,7 +28,7 @@ __global__ void __launch_bounds__(64) kswCigarKernel(const uint8_t* __restrict__
     nCigar[i] = (uint32_t)n;
 }
 
-void debugKswCigar(fg_ctx* ctx, const uint8_t* targets, const uint64_t* tOff, const uint8_t* queries, const uint64_t* qOff, uint32_t n, uint32_t cigarCap,
+void alignCigarBatch(fg_ctx* ctx, const uint8_t* targets, const uint64_t* tOff, const uint8_t* queries, const uint64_t* qOff, uint32_t n, uint32_t cigarCap,
                    uint32_t* cigars, uint32_t* nCigar, int32_t* status) {
     if (!n) return;
     if (!cigarCap) throw Error(FG_ERR_ARG, "cigar_cap must be positive");

@@ -12,7 +12,7 @@
 // KSW_EZ_APPROX_MAX | KSW_EZ_APPROX_DROP, zdrop = -1, left-aligned gaps, match 2, mismatch -4, gap open 4, gap extend 2, m = 5.
 //
 // Checked on the CPU: oracle/trim_check.cpp built with -DTRIM_CORE runs this header's host build and must print the CIGAR lines
-// of the unmodified reference (tests/test_oracle_trim.py).  The device build is reached through fg_debug_ksw_cigar (ksw.cu).
+// of the unmodified reference (tests/test_oracle_trim.py).  The device build is reached through fg_align_cigar_batch (ksw.cu).
 #pragma once
 #include <cstddef>
 #include <cstdint>

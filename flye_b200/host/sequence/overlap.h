@@ -144,7 +144,7 @@ std::vector<OverlapRange> checkIdyAndTrim(OverlapRange& ovlp, const DnaSequence&
                                           int32_t minOverlap, bool useHpc) __attribute__((weak));
 
 // The same trimming with the banded alignment on the device (FLYE_B200_DEVICE_KSW=1; default off until the repeat stage has run with
-// it on a GPU): homopolymer compression (alignment.cpp:52-70), then fg_debug_ksw_cigar for all rejected overlaps of a call in one
+// it on a GPU): homopolymer compression (alignment.cpp:52-70), then fg_align_cigar_batch for all rejected overlaps of a call in one
 // batch, then the host tail below — the CIGAR's =/X split (alignment.cpp:172-211), the search for the longest stretches below the
 // divergence threshold, their greedy non-overlapping choice (std::sort by length: the same libstdc++ permutation as in the
 // reference) and the mapping back to uncompressed coordinates (alignment.cpp:330-452).  tests/test_oracle_trim.py runs the tail on
@@ -333,7 +333,7 @@ private:
             const uint32_t cap = (uint32_t)std::min<size_t>(longest, (size_t)1 << 20);   // a CIGAR has at most tlen + qlen entries
             std::vector<uint32_t> cigars(rejected.size() * (size_t)cap), nCigar(rejected.size());
             std::vector<int32_t> status(rejected.size());
-            dev->check(fg_debug_ksw_cigar(dev->ctx, T.data(), tOff.data(), Q.data(), qOff.data(), (uint32_t)rejected.size(), cap, cigars.data(), nCigar.data(),
+            dev->check(fg_align_cigar_batch(dev->ctx, T.data(), tOff.data(), Q.data(), qOff.data(), (uint32_t)rejected.size(), cap, cigars.data(), nCigar.data(),
                                           status.data()));
             for (int32_t st : status) if (st == 2) throw std::runtime_error("flye_b200: CIGAR capacity exceeded in the device alignment");
             parallel([&](size_t i) {

@@ -190,13 +190,15 @@ int fg_debug_edit_distance(fg_ctx* ctx, const uint8_t* a, int n, const uint8_t* 
 /* the same with either string read as its reverse complement (base c -> 3 - c), as the kernel reads a reverse strand */
 int fg_debug_edit_distance_rc(fg_ctx* ctx, const uint8_t* a, int n, int rc_a, const uint8_t* b, int m, int rc_b, int* distance);
 int fg_debug_warp_sort(fg_ctx* ctx, uint64_t* keys, uint32_t* vals, const uint64_t* seg_offsets, uint32_t n_segments);
-/* test hook: the device build of the banded affine-gap alignment behind checkIdyAndTrim (getAlignmentCigarKsw, alignment.cpp:102-216;
- * minimap2's ksw_extz2_sse restated byte for byte, csrc/ksw_core.cuh) for a batch of pairs.  Base codes 0..3; pair i aligns
- * queries[query_offsets[i] .. query_offsets[i+1]) against targets[target_offsets[i] .. target_offsets[i+1]); band 64, doubled while
- * it cannot connect the corners.  cigars[i * cigar_cap ..] receives n_cigar[i] entries len << 4 | op (0 = M, 1 = I, 2 = D);
- * status[i]: 0 ok, 1 no band up to the longer sequence connects the corners (empty CIGAR, as the reference), 2 cigar_cap too small.
- * Not yet used by the host mirror (partitionBadMappings calls the reference's own code on host threads). */
-int fg_debug_ksw_cigar(fg_ctx* ctx, const uint8_t* targets, const uint64_t* target_offsets, const uint8_t* queries,
+/* ---- getAlignmentCigarKsw (alignment.cpp:102-216) for a batch of sequence pairs: the banded affine-gap global alignment behind
+ * checkIdyAndTrim (overlap.cpp:475-485, _partitionBadMappings) — minimap2's ksw_extz2_sse restated byte for byte (csrc/ksw_core.cuh; match 2,
+ * mismatch -4, gap open 4, gap extend 2).  Base codes 0..3; pair i aligns queries[query_offsets[i] .. query_offsets[i+1]) against
+ * targets[target_offsets[i] .. target_offsets[i+1]); band 64, doubled while it cannot connect the corners (alignment.cpp:150-165).
+ * cigars[i * cigar_cap ..] receives n_cigar[i] entries len << 4 | op (0 = M, 1 = I: query only, 2 = D: target only); status[i]: 0 ok, 1 no band up
+ * to the longer sequence connects the corners (empty CIGAR, as the reference), 2 cigar_cap too small (tlen + qlen entries always suffice).
+ * The host mirror calls it for the rejected primaries of a batch when FLYE_B200_DEVICE_KSW=1; by default it still hands them to the
+ * reference's own checkIdyAndTrim on host threads. ---- */
+int fg_align_cigar_batch(fg_ctx* ctx, const uint8_t* targets, const uint64_t* target_offsets, const uint8_t* queries,
                        const uint64_t* query_offsets, uint32_t n_pairs, uint32_t cigar_cap, uint32_t* cigars, uint32_t* n_cigar,
                        int32_t* status);
 

@@ -8,7 +8,7 @@
 // strand of either sequence, with and without homopolymer compression, three thresholds.
 // Two more builds print the CIGAR lines only (the trimming itself stays host code):
 //   (3) -DTRIM_CORE    the host build of flye_b200/csrc/ksw_core.cuh — the scalar routine the device kernel runs,
-//   (4) -DTRIM_DEVICE  the device build of the same routine through the C ABI (fg_debug_ksw_cigar, one batch for all cases).
+//   (4) -DTRIM_DEVICE  the device build of the same routine through the C ABI (fg_align_cigar_batch, one batch for all cases).
 // And one more prints everything again:
 //   (5) -DTRIM_MIRROR  the host mirror's own trimming tail (flye_b200/host/sequence/overlap.h: hpcRange + trimByCigar — what
 //                      FLYE_B200_DEVICE_KSW=1 runs around the device alignment) fed with CIGARs of the routine's host build.
@@ -170,8 +170,8 @@ int main(int argc, char** argv) {
         const uint32_t cap = 16384;
         std::vector<uint32_t> cg((size_t)nCases * cap), nCg(nCases);
         std::vector<int32_t> status(nCases);
-        if (fg_debug_ksw_cigar(ctx, T.data(), tOff.data(), Q.data(), qOff.data(), (uint32_t)nCases, cap, cg.data(), nCg.data(), status.data()) != FG_OK) {
-            fprintf(stderr, "fg_debug_ksw_cigar: %s\n", fg_last_error(ctx));
+        if (fg_align_cigar_batch(ctx, T.data(), tOff.data(), Q.data(), qOff.data(), (uint32_t)nCases, cap, cg.data(), nCg.data(), status.data()) != FG_OK) {
+            fprintf(stderr, "fg_align_cigar_batch: %s\n", fg_last_error(ctx));
             return 3;
         }
         for (int c = 0; c < nCases; ++c) {

@@ -1,5 +1,5 @@
 """GPU: the device build of the banded KSW2 alignment behind checkIdyAndTrim (flye_b200/csrc/ksw.cu,
-fg_debug_ksw_cigar) against the oracle: build/flye_b200_trim_device is oracle/trim_check.cpp linked to the library, a separate
+fg_align_cigar_batch) against the oracle: build/flye_b200_trim_device is oracle/trim_check.cpp linked to the library, a separate
 process with its own context; its CIGAR lines must equal the restatement's (pinned to the unmodified reference by
 tests/test_oracle_trim.py) on the same generated cases, including the pairs whose band has to be doubled.
 (First run on a B200: profiles/r2_ksw_device_240_cases.txt — 240 of 240 CIGARs identical.)"""
